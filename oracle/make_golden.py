@@ -1,0 +1,192 @@
+"""TEST INFRASTRUCTURE ONLY — generate golden vectors from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+
+    python -m oracle.make_golden
+
+Writes small fixtures under tests/golden/ that travel to the GPU box:
+
+  schema_readme_default.json  key order + vocab sizes derived from the reference's
+                              meta/metadata.csv via its own classify_columns()
+                              (data/column_classifier.py:67-130) and the +10 safety margin
+                              (src/towers/cat_embed.py:26,70-77).  Derived data, not source.
+  tiny_*.npz                  full-tensor trajectories on tests/golden/tiny_metadata.csv
+                              (our own small schema run through the real reference):
+                              init state_dict, 3 batches (with out-of-range ids), per-step
+                              loss/metrics/similarity matrix, step-1 gradients of every
+                              parameter, state_dict + Adam moments after 3 steps with the
+                              LambdaLR warm-up of scripts/train.py:235-242.
+  readme_default_b256.npz     README-default model (2,204,832 params) at B=256: init
+                              checksums, inputs, 3-step loss trajectory, step-1 tower
+                              embeddings, all dense params and sampled table rows after 3 steps.
+
+The reference's own tests hold no golden vectors — these outputs of the
+reference itself, run here, are what pins oracle/ref_port.py and oracle/two_tower_oracle.py.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import ref_harness as rh
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _vocab_of(task):
+    nt = task.two_tower_model.notice_tower.categorical_embedder
+    ct = task.two_tower_model.company_tower.categorical_embedder
+    return ([[k, int(nt.vocab_sizes[k])] for k in nt.keys], [[k, int(ct.vocab_sizes[k])] for k in ct.keys])
+
+
+def _ids(gen, vocab, bsz, oob_frac=0.0):
+    cols = []
+    for _, v in vocab:
+        col = torch.randint(0, v, (bsz,), generator=gen)
+        if oob_frac > 0:
+            r = torch.rand(bsz, generator=gen)
+            col = torch.where(r < oob_frac / 2, torch.full_like(col, -1), col)
+            col = torch.where(r > 1 - oob_frac / 2, torch.full_like(col, v + 5), col)
+        cols.append(col)
+    return torch.stack(cols, 1).to(torch.int64)
+
+
+def sha(t: torch.Tensor) -> str:
+    return hashlib.sha256(t.detach().contiguous().numpy().tobytes()).hexdigest()
+
+
+def run_trajectory(task, nk, ck, batches, lr=1e-3, wd=1e-5, warmup_steps=2):
+    """scripts/train.py:231-242,319-330 verbatim in spirit: Adam + LambdaLR + the loop body."""
+    opt = torch.optim.Adam(task.parameters(), lr=lr, weight_decay=wd)
+    sched = torch.optim.lr_scheduler.LambdaLR(
+        opt, (lambda s: s / warmup_steps if s < warmup_steps else 1.0), last_epoch=-1)
+    rec = {}
+    task.train()
+    for si, (nid, cid, nd, cd) in enumerate(batches):
+        batch = rh.make_reference_batch(nk, ck, nid, cid, nd, cd)
+        opt.zero_grad()
+        hooks = []
+        if si == 0:  # capture the tower outputs of this very forward (a 2nd forward would move BN running stats)
+            hooks.append(task.two_tower_model.notice_tower.register_forward_hook(
+                lambda m, i, o: rec.__setitem__("s0.notice_emb", o.detach().numpy().copy())))
+            hooks.append(task.two_tower_model.company_tower.register_forward_hook(
+                lambda m, i, o: rec.__setitem__("s0.company_emb", o.detach().numpy().copy())))
+        with rh.silenced():
+            out = task(batch, return_metrics=True)
+        for h in hooks:
+            h.remove()
+        out["loss"].backward()
+        if si == 0:
+            for name, p in task.named_parameters():
+                rec[f"grad0.{name}"] = p.grad.detach().numpy().copy()
+        rec[f"s{si}.lr"] = np.float64(opt.param_groups[0]["lr"])
+        opt.step()
+        sched.step()
+        for k in ("loss", "accuracy", "positive_similarity_mean", "negative_similarity_mean", "similarity_gap"):
+            rec[f"s{si}.{k}"] = np.float32(out[k].item())
+        rec[f"s{si}.similarity_matrix"] = out["similarity_matrix"].numpy().copy()
+    return rec, opt
+
+
+def tiny_case(name, hidden, final_dim, emb_dim, temperature, label_smoothing, oob, bsz=24, seed=0):
+    meta = os.path.join(GOLD, "tiny_metadata.csv")
+    nd_dim, cd_dim = 12, 6
+    task, nk, ck = rh.build_reference_task(
+        categorical_embedding_dim=emb_dim, notice_dense_input_dim=nd_dim, company_dense_input_dim=cd_dim,
+        tower_hidden_dims=hidden, final_embedding_dim=final_dim, dropout_rate=0.0,
+        temperature=temperature, seed=seed, meta=meta, label_smoothing=label_smoothing)
+    nv, cv = _vocab_of(task)
+    out = {f"init.{k}": v.numpy().copy() for k, v in task.state_dict().items()}
+    gen = torch.Generator().manual_seed(1234)
+    batches = []
+    for si in range(3):
+        nid, cid = _ids(gen, nv, bsz, oob), _ids(gen, cv, bsz, oob)
+        nd, cd = torch.randn(bsz, nd_dim, generator=gen), torch.randn(bsz, cd_dim, generator=gen)
+        batches.append((nid, cid, nd, cd))
+        out[f"in{si}.notice_ids"], out[f"in{si}.company_ids"] = nid.numpy(), cid.numpy()
+        out[f"in{si}.notice_dense"], out[f"in{si}.company_dense"] = nd.numpy(), cd.numpy()
+    rec, opt = run_trajectory(task, nk, ck, batches, warmup_steps=2)
+    out.update(rec)
+    for k, v in task.state_dict().items():
+        out[f"final.{k}"] = v.numpy().copy()
+    names = [n for n, _ in task.named_parameters()]
+    for n, p in zip(names, opt.param_groups[0]["params"]):
+        st = opt.state[p]
+        out[f"adam_m.{n}"] = st["exp_avg"].numpy().copy()
+        out[f"adam_v.{n}"] = st["exp_avg_sq"].numpy().copy()
+    cfg = dict(schema={"notice": nv, "company": cv}, emb_dim=emb_dim, notice_dense=nd_dim, company_dense=cd_dim,
+               hidden=list(hidden), final_dim=final_dim, temperature=temperature, label_smoothing=label_smoothing,
+               lr=1e-3, weight_decay=1e-5, warmup_steps=2, bsz=bsz, seed=seed, n_params=int(sum(p.numel() for p in task.parameters())))
+    out["config_json"] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(GOLD, f"tiny_{name}.npz"), **out)
+    print(f"tiny_{name}: loss traj", [float(out[f's{i}.loss']) for i in range(3)], "params", cfg["n_params"])
+
+
+def readme_default_case():
+    task, nk, ck = rh.build_reference_task(dropout_rate=0.0, seed=0)
+    nv, cv = _vocab_of(task)
+    schema = {"notice": nv, "company": cv, "source": "derived from zoongahn/jodalroB-twoTower meta/metadata.csv "
+              "via data/column_classifier.py:67-130; vocab = category count + 10 (src/towers/cat_embed.py:26,70-77)"}
+    with open(os.path.join(GOLD, "schema_readme_default.json"), "w") as f:
+        json.dump(schema, f, indent=1)
+    bsz = 256
+    out = {}
+    init = task.state_dict()
+    out["init_sha_json"] = np.frombuffer(json.dumps({k: sha(v) for k, v in init.items()}).encode(), dtype=np.uint8)
+    gen = torch.Generator().manual_seed(1234)
+    batches = []
+    for si in range(3):
+        nid, cid = _ids(gen, nv, bsz), _ids(gen, cv, bsz)
+        nd, cd = torch.randn(bsz, 256, generator=gen), torch.randn(bsz, 128, generator=gen)
+        batches.append((nid, cid, nd, cd))
+        out[f"in{si}.notice_ids"], out[f"in{si}.company_ids"] = nid.numpy().astype(np.int32), cid.numpy().astype(np.int32)
+        out[f"in{si}.notice_dense_sha"] = np.frombuffer(sha(nd).encode(), dtype=np.uint8)
+        out[f"in{si}.company_dense_sha"] = np.frombuffer(sha(cd).encode(), dtype=np.uint8)
+    rec, opt = run_trajectory(task, nk, ck, batches, warmup_steps=2)
+    for k, v in rec.items():
+        if k.startswith("grad0.") and "embeddings" in k:
+            continue  # dense [V,E] table grads are large; touched rows are checked via the final rows
+        if k.endswith("similarity_matrix"):
+            continue
+        out[k] = v
+    final = task.state_dict()
+    rows = {}
+    g2 = torch.Generator().manual_seed(7)
+    for k, v in final.items():
+        if "embeddings" in k:
+            n = v.shape[0]
+            pick = torch.randperm(n, generator=g2)[: min(n, 16)].sort().values
+            rows[k] = pick
+            out[f"final_rows_idx.{k}"] = pick.numpy().astype(np.int32)
+            out[f"final_rows.{k}"] = v[pick].numpy().copy()
+            out[f"final_sum.{k}"] = np.float64(v.double().sum().item())
+        else:
+            out[f"final.{k}"] = v.numpy().copy()
+    cfg = dict(emb_dim=32, notice_dense=256, company_dense=128, hidden=[128, 64], final_dim=64, temperature=1.0,
+               label_smoothing=0.0, lr=1e-3, weight_decay=1e-5, warmup_steps=2, bsz=bsz, seed=0, input_seed=1234,
+               n_params=int(sum(p.numel() for p in task.parameters())))
+    # the scripts/train.py config (train_results.csv:2-4 pins 2,890,912 params)
+    t2, _, _ = rh.build_reference_task(tower_hidden_dims=(512, 256), final_embedding_dim=128, seed=0)
+    cfg["n_params_train_py_config"] = int(sum(p.numel() for p in t2.parameters()))
+    out["config_json"] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(GOLD, "readme_default_b256.npz"), **out)
+    print("readme_default: loss traj", [float(out[f's{i}.loss']) for i in range(3)], cfg["n_params"], cfg["n_params_train_py_config"])
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(1)  # fixed reduction order → reproducible fixtures
+    tiny_case("base", hidden=(16, 8), final_dim=8, emb_dim=8, temperature=1.0, label_smoothing=0.0, oob=0.0)
+    tiny_case("oob_temp", hidden=(16, 8), final_dim=8, emb_dim=8, temperature=0.5, label_smoothing=0.0, oob=0.1)
+    tiny_case("deep_ls", hidden=(16, 12, 8), final_dim=4, emb_dim=4, temperature=0.25, label_smoothing=0.1, oob=0.05)
+    tiny_case("nohidden", hidden=(16,), final_dim=8, emb_dim=8, temperature=1.0, label_smoothing=0.0, oob=0.0)
+    readme_default_case()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,167 @@
+"""Pins oracle/ref_port.py and oracle/two_tower_oracle.py to the golden vectors generated from the
+unmodified reference (oracle/make_golden.py). CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_port, two_tower_oracle as orc
+from tests.helpers import TINY_CASES, batch_inputs, load_golden, readme_schema, rel_err, sd_from
+
+
+@pytest.mark.parametrize("case", TINY_CASES)
+def test_port_matches_reference_trajectory_bit_exact(case):
+    torch.set_num_threads(1)
+    d, cfg = load_golden(f"tiny_{case}.npz")
+    task = ref_port.build_port_task(cfg["schema"], cfg["emb_dim"], cfg["notice_dense"], cfg["company_dense"], cfg["hidden"],
+                                    cfg["final_dim"], 0.0, cfg["temperature"], "cross_entropy", cfg["label_smoothing"], seed=cfg["seed"])
+    init = sd_from(d, "init.")
+    # seeded construction reproduces the reference init bit-for-bit (same RNG consumption order)
+    for k, v in task.state_dict().items():
+        assert torch.equal(v, init[k]), k
+    assert sum(p.numel() for p in task.parameters()) == cfg["n_params"]
+    tr = ref_port.PortTrainer(task, cfg["lr"], cfg["weight_decay"], cfg["warmup_steps"])
+    for i in range(3):
+        nid, cid, nd, cd = batch_inputs(d, i)
+        out = tr.step(ref_port.make_port_batch(cfg["schema"], nid, cid, nd, cd))
+        assert np.float32(out["loss"].item()) == d[f"s{i}.loss"]
+        assert torch.equal(out["similarity_matrix"], torch.from_numpy(d[f"s{i}.similarity_matrix"]))
+        for m in ("accuracy", "positive_similarity_mean", "negative_similarity_mean", "similarity_gap"):
+            assert np.float32(out[m].item()) == d[f"s{i}.{m}"]
+    fin = sd_from(d, "final.")
+    for k, v in task.state_dict().items():
+        assert torch.equal(v, fin[k]), k
+
+
+@pytest.mark.parametrize("case", TINY_CASES)
+def test_port_loop_decode_equals_vectorized(case):
+    d, cfg = load_golden(f"tiny_{case}.npz")
+    nid, cid, nd, cd = batch_inputs(d, 0)
+    outs = []
+    for dec in ("loop", "vectorized"):
+        task = ref_port.build_port_task(cfg["schema"], cfg["emb_dim"], cfg["notice_dense"], cfg["company_dense"], cfg["hidden"],
+                                        cfg["final_dim"], 0.0, cfg["temperature"], seed=0, decode=dec)
+        outs.append(task(ref_port.make_port_batch(cfg["schema"], nid, cid, nd, cd)))
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("case", TINY_CASES)
+def test_explicit_oracle_matches_reference(case):
+    torch.set_num_threads(1)
+    d, cfg = load_golden(f"tiny_{case}.npz")
+    st = orc.OracleStepper(sd_from(d, "init."), cfg["schema"], cfg["temperature"], cfg["label_smoothing"],
+                           cfg["lr"], cfg["weight_decay"], cfg["warmup_steps"])
+    for i in range(3):
+        nid, cid, nd, cd = batch_inputs(d, i)
+        loss, met, cache, grads, embs = st.step(nid.reshape(-1).numpy(), cid.reshape(-1).numpy(), nd, cd)
+        assert abs(float(loss) - float(d[f"s{i}.loss"])) < 2e-6 * max(1.0, abs(float(d[f"s{i}.loss"])))
+        assert rel_err(cache["s"], torch.from_numpy(d[f"s{i}.similarity_matrix"])) < 1e-5
+        for m in ("accuracy", "positive_similarity_mean", "negative_similarity_mean", "similarity_gap"):
+            assert abs(float(met[m]) - float(d[f"s{i}.{m}"])) < 1e-5
+        if i == 0:
+            assert rel_err(embs[0], torch.from_numpy(d["s0.notice_emb"])) < 1e-5
+            assert rel_err(embs[1], torch.from_numpy(d["s0.company_emb"])) < 1e-5
+            # hand-derived backward vs the reference's autograd, every parameter
+            gexp = st_export_grads(st, grads)
+            for k, g in gexp.items():
+                ref = torch.from_numpy(d[f"grad0.{k}"])
+                assert rel_err(g, ref) < 2e-5, k
+    fin = sd_from(d, "final.")
+    for k, v in st.export().items():
+        if v.is_floating_point():
+            assert rel_err(v, fin[k]) < 1e-5, k
+        else:
+            assert torch.equal(v, fin[k]), k
+
+
+def st_export_grads(st, grads):
+    out = {}
+    for tw, keys in (("notice", st.nk), ("company", st.ck)):
+        g, pre = grads[tw], f"two_tower_model.{tw}_tower."
+        for k, t in zip(keys, g["emb"]):
+            out[pre + f"categorical_embedder.embeddings.{k}.weight"] = t
+        out[pre + "dense_projection.weight"], out[pre + "dense_projection.bias"] = g["Wd"], g["bd"]
+        for bi, blk in enumerate(g["blocks"]):
+            i = 4 * bi
+            out[pre + f"mlp.{i}.weight"], out[pre + f"mlp.{i}.bias"] = blk["W"], blk["b"]
+            out[pre + f"mlp.{i + 2}.weight"], out[pre + f"mlp.{i + 2}.bias"] = blk["gamma"], blk["beta"]
+        i = st.P[tw]["final_index"]
+        out[pre + f"mlp.{i}.weight"], out[pre + f"mlp.{i}.bias"] = g["Wf"], g["bf"]
+    return out
+
+
+def test_decode_clamp_matches_reference_clamping():
+    d, cfg = load_golden("tiny_oob_temp.npz")
+    nid, cid, _, _ = batch_inputs(d, 0)
+    assert (nid < 0).any() and (nid >= torch.tensor([v for _, v in cfg["schema"]["notice"]])).any()
+    vocab = [v for _, v in cfg["schema"]["notice"]]
+    ids = orc.decode_clamp(nid.reshape(-1).numpy(), vocab)
+    exp = torch.minimum(torch.clamp(nid, min=0), torch.tensor(vocab)[None] - 1).numpy()
+    assert np.array_equal(ids, exp)
+    # key-major is the transposed flattening of the same grid
+    assert np.array_equal(orc.decode_clamp(nid.t().reshape(-1).numpy(), vocab, "key_major"), exp)
+    # default vocab 1000 for a key with no category count (cat_embed.py:65-74), +10 margin otherwise
+    sch = dict(cfg["schema"]["notice"])
+    assert sch["nocount"] == 1000 and sch["flag_a"] == 12 and sch["org_code"] == 300
+
+
+def test_readme_default_pins():
+    torch.set_num_threads(1)
+    d, cfg = load_golden("readme_default_b256.npz")
+    assert cfg["n_params"] == 2204832 and cfg["n_params_train_py_config"] == 2890912  # train_results.csv:2-4
+    schema = readme_schema()
+    assert len(schema["notice"]) == 32 and len(schema["company"]) == 6
+    assert sum(v for _, v in schema["notice"]) == 60024 and sum(v for _, v in schema["company"]) == 4117
+    task = ref_port.build_port_task(schema, seed=0)
+    assert sum(p.numel() for p in task.parameters()) == 2204832
+    t2 = ref_port.build_port_task(schema, hidden=(512, 256), final_dim=128, seed=0)
+    assert sum(p.numel() for p in t2.parameters()) == 2890912
+    # loss ~ ln B at random init
+    assert abs(float(d["s0.loss"]) - np.log(256)) < 0.05
+    # unit-norm invariant (two_tower_model.py:84-87)
+    assert np.allclose(np.linalg.norm(d["s0.notice_emb"], axis=1), 1.0, atol=1e-4)
+
+
+def test_port_reproduces_readme_default_trajectory():
+    import hashlib, json
+    torch.set_num_threads(1)
+    d, cfg = load_golden("readme_default_b256.npz")
+    schema = readme_schema()
+    task = ref_port.build_port_task(schema, seed=0)
+    shas = json.loads(bytes(d["init_sha_json"]).decode())
+    for k, v in task.state_dict().items():
+        assert hashlib.sha256(v.contiguous().numpy().tobytes()).hexdigest() == shas[k], k
+    gen = torch.Generator().manual_seed(cfg["input_seed"])
+    tr = ref_port.PortTrainer(task, cfg["lr"], cfg["weight_decay"], cfg["warmup_steps"])
+    for i in range(3):
+        # same generator recipe as oracle/make_golden.py::_ids
+        nid = torch.stack([torch.randint(0, v, (256,), generator=gen) for _, v in schema["notice"]], 1)
+        cid = torch.stack([torch.randint(0, v, (256,), generator=gen) for _, v in schema["company"]], 1)
+        nd, cd = torch.randn(256, 256, generator=gen), torch.randn(256, 128, generator=gen)
+        assert np.array_equal(nid.numpy(), d[f"in{i}.notice_ids"]) and np.array_equal(cid.numpy(), d[f"in{i}.company_ids"])
+        out = tr.step(ref_port.make_port_batch(schema, nid, cid, nd, cd))
+        assert np.float32(out["loss"].item()) == d[f"s{i}.loss"]
+    sd = task.state_dict()
+    for k in sd:
+        if "embeddings" in k:
+            idx = torch.from_numpy(d[f"final_rows_idx.{k}"]).long()
+            assert torch.equal(sd[k][idx], torch.from_numpy(d[f"final_rows.{k}"])), k
+        else:
+            assert torch.equal(sd[k], torch.from_numpy(np.array(d[f"final.{k}"]))), k
+
+
+def test_rw_shard_and_sort_dedup_properties():
+    rng = np.random.default_rng(0)
+    vocab = [12, 300, 25, 1000, 51]
+    ids = np.stack([rng.integers(0, v, 64) for v in vocab], 1)
+    for world in (1, 2, 3, 8):
+        owner, local = orc.rw_shard(ids, vocab, world)
+        blk = np.array([orc.rw_block(v, world) for v in vocab])
+        assert (owner >= 0).all() and (owner < world).all() and (local >= 0).all() and (local < blk[None]).all()
+        assert np.array_equal(owner.astype(np.int64) * blk[None] + local, ids)
+    rows = orc.arena_rows(ids, orc.row_offsets_of(vocab))
+    sdp = orc.sort_dedup(rows)
+    assert np.all(np.diff(sdp["sorted_rows"]) >= 0)
+    assert np.array_equal(rows.reshape(-1)[sdp["positions"]], sdp["sorted_rows"])
+    for s, e in zip(sdp["seg_starts"][:-1], sdp["seg_starts"][1:]):
+        assert np.all(np.diff(sdp["positions"][s:e]) > 0)  # stable: positions ascend inside a segment
+    assert np.array_equal(sdp["unique_rows"], np.unique(rows))
