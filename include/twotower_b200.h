@@ -1,0 +1,237 @@
+/*
+ * twotower_b200 — C ABI of the B200-native (sm_100a) two-tower training step.
+ *
+ * Drop-in boundary for the hot path of zoongahn/jodalroB-twoTower
+ * (TwoTowerTrainTask.forward -> loss.backward() -> Adam.step()).  The reference is
+ * pure Python/PyTorch and has no FFI of its own, so every entry point below names the reference
+ * function (file:line, relative to the reference root) whose arithmetic it replaces; the
+ * reference-side binding is a ctypes stub.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.  All data pointers are DEVICE pointers
+ *     (tensor.data_ptr()); the caller owns every buffer; the library never allocates, frees or
+ *     retains a caller pointer past the call.  Scratch space is passed in (query *_workspace_bytes).
+ *   - every call is stream-ordered on `stream` (a cudaStream_t) and returns immediately.
+ *   - return value: TT_OK (0) or a negative TT_ERR_*; tt_last_error() gives the message
+ *     (thread-local).  No exceptions, no silent fallbacks (the reference's zero-vector fallback,
+ *     src/towers/cat_embed.py:180-190, is deliberately NOT replicated).
+ *   - matrices are row-major; `ld*` are leading dimensions in ELEMENTS.
+ */
+#ifndef TWOTOWER_B200_H_
+#define TWOTOWER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_ABI_VERSION 1
+
+#define TT_OK 0
+#define TT_ERR_INVALID_ARG (-1)
+#define TT_ERR_CUDA (-2)
+#define TT_ERR_UNSUPPORTED (-3)
+#define TT_ERR_WORKSPACE (-4)
+
+/* element types of activations / gradients */
+#define TT_F32 0
+#define TT_BF16 1
+
+/* KeyedJaggedTensor value order.  The reference builds SAMPLE-major values ([B,K] flattened,
+ * src/towers/pairs/unified_bid_data_loader.py:827-841) and decodes values[b*K+k]
+ * (src/towers/cat_embed.py:109-110); canonical TorchRec order is KEY-major ([K][B]). */
+#define TT_LAYOUT_SAMPLE_MAJOR 0
+#define TT_LAYOUT_KEY_MAJOR 1
+
+/* optimizer row-update modes of tt_ebc_backward_adam */
+#define TT_ADAM_DENSE_EXACT 0 /* every arena row every step == torch.optim.Adam (scripts/train.py:231) */
+#define TT_ADAM_SPARSE 1      /* only rows touched by the batch (TorchRec/SparseAdam-style; NOT the reference semantics) */
+
+typedef void* tt_stream_t; /* cudaStream_t */
+
+/* Device-resident optimizer/RNG state (64 bytes, zero-initialised by the caller).  Keeping it on
+ * the device lets the whole step be captured in a CUDA graph: tt_hyper_advance() bumps the step
+ * and derives lr_t / bias corrections on the GPU.  Replaces torch.optim.Adam's python-side step
+ * bookkeeping and LambdaLR (scripts/train.py:231-242,327-330). */
+typedef struct tt_adam_hyper {
+  int64_t step;       /* optimizer steps taken so far (t) */
+  int64_t sched_step; /* scheduler.step() calls so far (LambdaLR counter, starts at 0) */
+  float lr;           /* lr_t used by the current step */
+  float step_size;    /* lr_t / (1 - beta1^t) */
+  float bc2_sqrt;     /* sqrt(1 - beta2^t) */
+  float beta1, beta2, eps, weight_decay;
+  float reserved;
+  uint64_t rng_seed; /* dropout Philox key */
+  uint64_t rng_step; /* dropout Philox step counter (== step) */
+} tt_adam_hyper;
+
+const char* tt_last_error(void);
+int tt_version(void);
+int tt_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer bookkeeping.  t += 1; lr_t = base_lr * (s < warmup ? s / warmup : 1) with s the number
+ * of scheduler steps so far (lr_1 = 0 when warmup > 0, scripts/train.py:235-242); then s += 1.
+ * warmup_steps <= 0 disables the schedule. */
+int tt_hyper_advance(tt_adam_hyper* d_hyper, float base_lr, int64_t warmup_steps, float beta1, float beta2,
+                     float eps, float weight_decay, uint64_t rng_seed, tt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooled embedding-bag lookup for all K tables of a tower in one launch.
+ * Replaces CategoricalEmbedder._kjt_to_dict + per-key nn.Embedding + torch.cat
+ * (src/towers/cat_embed.py:88-123,158-177) and writes straight into the tower's concat buffer
+ * (src/towers/tower/base_tower.py:139).
+ *   arena        f32 [total_rows, E]  all tables of all towers, table k starts at row d_row_base[k]
+ *   d_row_base   i64 [K]   d_vocab i32 [K]    (device arrays; staged through shared memory)
+ *   values       i64 [n_values] raw ids; clamped to [0, vocab-1] in-kernel (cat_embed.py:115-117)
+ *   bag_offsets  i64 [B*K+1] or NULL.  NULL: one id per (sample,key), the reference's only case.
+ *                Otherwise bag j (in `layout` order) owns values[bag_offsets[j] .. bag_offsets[j+1])
+ *                and is sum-pooled (generalisation; oracle torch embedding_bag(mode="sum")).
+ *   out          [B, out_ld] of out_dtype; bag (b,k) is written at columns out_col0 + k*E ..+E
+ *   rows_out     i32 or NULL: clamped arena row of every value (bit-exact integer stage).  Without
+ *                bag_offsets it is indexed by gradient slot b*K+k (whatever the value layout), so the
+ *                backward can use identity slots; with bag_offsets it is indexed by value position.
+ *   slots_out    i32 or NULL, same indexing: slot_base + b*K+k (the pooled-gradient vector the value
+ *                contributes to).  slot_base lets two towers share one slot space (tower 1 starts at
+ *                tower 0's B*K).
+ */
+int tt_ebc_forward(const float* arena, const int64_t* d_row_base, const int32_t* d_vocab, const int64_t* values,
+                   const int64_t* bag_offsets, int64_t n_values, int32_t B, int32_t K, int32_t E, int32_t layout,
+                   void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0, int32_t* rows_out,
+                   int32_t* slots_out, int64_t slot_base, tt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse backward, stage 1: deterministic sort-by-row dedup.  Stable LSD radix sort of
+ * (row, slot) by row, then per-row segment bounds.  Replaces the index side of autograd's
+ * embedding_dense_backward for every nn.Embedding (scripts/train.py:326).
+ *   rows, slots      i32 [n]   (slots NULL => identity)
+ *   sorted_rows/slots i32 [n]  out; inside one row the slots ascend (stable) => fixed summation order
+ *   row_begin/row_end/row_stamp i32 [total_rows]: for every row present, [begin,end) into the sorted
+ *                    arrays and row_stamp[row] = stamp; rows absent keep an older stamp (no memset).
+ *   stamp            effective stamp = stamp + (d_stamp ? (int32)*d_stamp : 0); d_stamp is a device
+ *                    counter so a captured CUDA graph sees a fresh stamp on every replay.
+ */
+int64_t tt_ebc_sort_workspace_bytes(int64_t n, int64_t total_rows);
+int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
+                     int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
+                     int32_t* row_end, int32_t* row_stamp, int32_t stamp, const int64_t* d_stamp,
+                     tt_stream_t stream);
+
+/* Sparse backward, stage 2: segment-sum of the pooled-output gradients in fixed order, fused with
+ * the Adam row update.  Gradient slot s < n0 belongs to source 0 (sample s / K0, key s % K0, vector
+ * at grad0 + b*ld0 + col0_0 + k*E); slots >= n0 to source 1 likewise.
+ *   mode TT_ADAM_DENSE_EXACT: every row of [row_lo,row_hi) is updated with g = segsum + wd*w —
+ *        bit-for-bit the update rule of torch.optim.Adam over dense nn.Embedding grads
+ *        (scripts/train.py:231,327).
+ *   mode TT_ADAM_SPARSE: only stamped rows are updated.
+ *   grad_arena != NULL: also/only materialise the dense gradient ([total_rows,E], zeros elsewhere)
+ *        for the autograd-compatible path (w/m/v may then be NULL).
+ * piece_ws: f32 scratch of tt_ebc_piece_workspace_bytes(n, E) for rows with long segments. */
+int64_t tt_ebc_piece_workspace_bytes(int64_t n, int32_t E);
+int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* grad_arena, int64_t total_rows,
+                         int32_t E, const int32_t* sorted_rows, const int32_t* sorted_slots, int64_t n,
+                         const int32_t* row_begin, const int32_t* row_end, const int32_t* row_stamp, int32_t stamp,
+                         const int64_t* d_stamp, const void* grad0, int64_t ld0, int64_t col0_0, int32_t K0, int64_t n0, const void* grad1,
+                         int64_t ld1, int64_t col0_1, int32_t K1, int64_t n1, int32_t grad_dtype, void* piece_ws,
+                         int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, tt_stream_t stream);
+
+/* Dense-parameter Adam over a flat fp32 buffer (tower Linear/BatchNorm weights), same update rule.
+ * Replaces torch.optim.Adam.step for the non-embedding parameters (scripts/train.py:327). */
+int tt_dense_adam(float* w, const float* g, float* m, float* v, int64_t n, const tt_adam_hyper* d_hyper,
+                  tt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tower Linear layers (nn.Linear at src/towers/tower/base_tower.py:59,89,97).
+ * forward : C[M,N] = act(A[M,K] · W[N,K]^T + bias)       act = ReLU iff relu != 0
+ * dgrad   : dX[M,K] = dY[M,N] · W[N,K]
+ * wgrad   : dW[N,K] = dY[M,N]^T · X[M,K];  dbias[N] = column sums of dY (NULL to skip)
+ * W/bias/dW/dbias are fp32 masters; A/C/dY/dX/X are `act_dtype`.  workspace for wgrad split-K. */
+int tt_linear_forward(const void* A, int64_t lda, const float* W, const float* bias, void* C, int64_t ldc, int64_t M,
+                      int32_t N, int32_t K, int32_t act_dtype, int32_t relu, tt_stream_t stream);
+int tt_linear_dgrad(const void* dY, int64_t ldy, const float* W, void* dX, int64_t ldx, int64_t M, int32_t N,
+                    int32_t K, int32_t act_dtype, tt_stream_t stream);
+int64_t tt_linear_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K);
+int tt_linear_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, float* dW, float* dbias, int64_t M,
+                    int32_t N, int32_t K, int32_t act_dtype, void* workspace, int64_t workspace_bytes,
+                    tt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm1d (train-mode batch statistics) + Dropout, the reference's Linear->ReLU->BN->Dropout
+ * block (src/towers/tower/base_tower.py:88-93).  Split in three so data-parallel ranks can
+ * all-reduce `sums` between stats and finalize (SyncBN == single-device BN on the global batch).
+ *   tt_bn_stats     sums f64 [2N]: sum_b h, sum_b h^2 over the M local rows (deterministic order)
+ *   tt_bn_finalize  mean/rstd f32 [N] from sums over `count` rows; running_mean/var momentum update
+ *                   (unbiased var), num_batches_tracked += 1     (pass NULLs to skip running stats)
+ *   tt_bn_apply     y = ((h - mean) * rstd * gamma + beta) * keep / (1 - p)
+ *                   keep mask: mask_in u8 [M,N] if given (parity tests), else Philox(d_hyper, rng_stream)
+ *   eval mode: call tt_bn_apply with mean = running_mean and rstd from tt_bn_rstd_from_var. */
+int tt_bn_stats(const void* h, int64_t ldh, int64_t M, int32_t N, int32_t act_dtype, double* sums, void* workspace,
+                int64_t workspace_bytes, tt_stream_t stream);
+int64_t tt_bn_workspace_bytes(int64_t M, int32_t N);
+int tt_bn_finalize(const double* sums, int64_t count, int32_t N, float eps, float momentum, float* mean, float* rstd,
+                   float* running_mean, float* running_var, int64_t* num_batches_tracked, tt_stream_t stream);
+int tt_bn_rstd_from_var(const float* var, int32_t N, float eps, float* rstd, tt_stream_t stream);
+int tt_bn_apply(const void* h, int64_t ldh, int64_t M, int32_t N, int32_t act_dtype, const float* mean,
+                const float* rstd, const float* gamma, const float* beta, float dropout_p, const uint8_t* mask_in,
+                const tt_adam_hyper* d_hyper, uint32_t rng_stream, void* y, int64_t ldy, tt_stream_t stream);
+/* backward: sums f64 [2N] = (sum_b dy', sum_b dy'*xhat) with dy' = dy * keep/(1-p);  then
+ * dh = [h>0] * rstd*gamma*(dy' - sums0/count - xhat*sums1/count);  dgamma = sums1, dbeta = sums0.
+ * eval-mode backward (frozen stats) is dh = [h>0]*rstd*gamma*dy' : pass train = 0. */
+int tt_bn_backward_reduce(const void* dy, int64_t lddy, const void* h, int64_t ldh, int64_t M, int32_t N,
+                          int32_t act_dtype, const float* mean, const float* rstd, float dropout_p,
+                          const uint8_t* mask_in, const tt_adam_hyper* d_hyper, uint32_t rng_stream, double* sums,
+                          void* workspace, int64_t workspace_bytes, tt_stream_t stream);
+int tt_bn_backward_apply(const void* dy, int64_t lddy, const void* h, int64_t ldh, int64_t M, int32_t N,
+                         int32_t act_dtype, const float* mean, const float* rstd, const float* gamma,
+                         float dropout_p, const uint8_t* mask_in, const tt_adam_hyper* d_hyper, uint32_t rng_stream,
+                         const double* sums, int64_t count, int32_t train, float* dgamma, float* dbeta, void* dh,
+                         int64_t lddh, tt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * F.normalize(p=2, dim=1, eps=1e-12) (src/towers/tower/base_tower.py:145) and its backward
+ * dz = (de - e*(e·de)) / max(||z||, eps).  z/dz are fp32; e is out_dtype. */
+int tt_l2norm_forward(const float* z, int64_t M, int32_t F, void* e, int32_t out_dtype, float* nrm,
+                      tt_stream_t stream);
+int tt_l2norm_backward(const float* de, const void* e, int32_t e_dtype, const float* nrm, int64_t M, int32_t F,
+                       float* dz, tt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * In-batch-negative similarity logits + symmetric softmax cross-entropy, logits never stored.
+ * Replaces _compute_similarity_matrix / _compute_loss / _compute_metrics
+ * (src/towers/two_tower_train_task.py:99-134,162-179) and their autograd.
+ *   X [Bx,F] are the "row" embeddings held by this rank, Y [By,F] all "column" embeddings
+ *   (By == Bx on one GPU; all-gathered item tower on several).  S = X·Y^T * inv_temp.
+ *   Row r's positive is column diag_offset + r.  exp() is taken as exp(S - inv_temp) (rows are
+ *   unit-norm so S <= inv_temp): sums are shifted by a constant, no running max needed.
+ * forward outputs (all f32 unless noted):
+ *   row_sumexp [Bx], col_sumexp [By] (over this rank's rows), row_sum_s [Bx], col_sum_s [By],
+ *   diag [Bx] = S[r, diag_offset+r], row_argmax i32 [Bx] (first maximum, torch.argmax tie rule).
+ * tt_simce_finalize turns (globally summed) sums into  inv_row [Bx], inv_col [By] for the backward
+ * and partial f64[8] = {sum_i l_row, sum_{j in my diag range} l_col, hits, sum diag, sum S, 0,0,0};
+ * tt_simce_scalars maps (globally summed) partials to {loss, accuracy, pos_mean, neg_mean, gap}. */
+int64_t tt_simce_workspace_bytes(int64_t Bx, int64_t By, int32_t F);
+int tt_simce_forward(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
+                     int64_t diag_offset, float* row_sumexp, float* col_sumexp, float* row_sum_s, float* col_sum_s,
+                     float* diag, int32_t* row_argmax, void* workspace, int64_t workspace_bytes, tt_stream_t stream);
+int tt_simce_finalize(const float* row_sumexp, const float* col_sumexp, const float* row_sum_s,
+                      const float* col_sum_s, const float* diag, const int32_t* row_argmax, int64_t Bx, int64_t By,
+                      int64_t diag_offset, int64_t B_global, float inv_temp, float label_smoothing, float* inv_row,
+                      float* inv_col, double* partial, tt_stream_t stream);
+int tt_simce_scalars(const double* partial, int64_t B_global, float* out5, tt_stream_t stream);
+/* backward: dX[Bx,F] (f32) = dS · Y with
+ *   dS_ij = gscale * (exp(S_ij - inv_temp) * (inv_x[i] + inv_y[j]) - 2*((1-ls)*[j == diag_offset+i] + ls/B_global))
+ * gscale = dloss * 0.5 / B_global * inv_temp.  Call once with (X=notice, Y=company) for d notice and
+ * once with (X=company, Y=notice, inv_x=inv_col, inv_y=inv_row) for d company. */
+int tt_simce_backward(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
+                      int64_t diag_offset, const float* inv_x, const float* inv_y, float gscale,
+                      float label_smoothing, int64_t B_global, float* dX, void* workspace, int64_t workspace_bytes,
+                      tt_stream_t stream);
+/* Lazily materialise S (eval / predict_batch / return_metrics "similarity_matrix" only). */
+int tt_similarity_matrix(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype,
+                         float inv_temp, float* S, int64_t lds, tt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWOTOWER_B200_H_ */

@@ -1,0 +1,617 @@
+// Embedding-bag collection: pooled lookup, deterministic sort-by-row dedup, segment-sum + fused Adam.
+//
+// HBM-bound byte work: every kernel here is a coalesced 128-bit gather/scatter.  One "lane group"
+// of E/4 lanes owns one embedding row (E=32 fp32 -> 8 lanes x float4 = one 128-byte line), so a
+// warp moves 4 rows per instruction and consecutive bags of a sample land contiguously in the
+// tower's concat buffer.  Table metadata (row base, vocab) is staged through shared memory.
+#include "common.cuh"
+
+namespace tt {
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <typename OutT>
+__device__ __forceinline__ void store_vec4(OutT* p, const float4& v);
+template <>
+__device__ __forceinline__ void store_vec4<float>(float* p, const float4& v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void store_vec4<__nv_bfloat16>(__nv_bfloat16* p, const float4& v) {
+  *reinterpret_cast<uint2*>(p) = pack_bf16x4(v);
+}
+
+// L = 1 fast path (the reference's only case): UNROLL bags in flight per lane group.
+template <typename OutT, int UNROLL>
+__global__ void __launch_bounds__(256)
+ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ row_base,
+                  const int32_t* __restrict__ vocab, const int64_t* __restrict__ values, int B, int K, int E,
+                  int layout, OutT* __restrict__ out, int64_t out_ld, int64_t out_col0, int32_t* __restrict__ rows_out,
+                  int32_t* __restrict__ slots_out, int64_t slot_base, int G) {
+  extern __shared__ unsigned char smem_raw[];
+  int64_t* s_base = reinterpret_cast<int64_t*>(smem_raw);
+  int32_t* s_vocab = reinterpret_cast<int32_t*>(s_base + K);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    s_base[i] = row_base[i];
+    s_vocab[i] = vocab[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x % G;
+  const int64_t n_bags = (int64_t)B * K;
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
+  const int64_t group0 = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+  const int vec_per_row = E >> 2;
+  for (int64_t base = group0; base < n_bags; base += groups_total * UNROLL) {
+    int64_t row[UNROLL];
+    int64_t slot[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      slot[u] = base + (int64_t)u * groups_total;
+      row[u] = -1;
+      if (slot[u] < n_bags) {
+        const int b = (int)(slot[u] / K), k = (int)(slot[u] - (int64_t)b * K);
+        const int64_t vi = layout == TT_LAYOUT_SAMPLE_MAJOR ? slot[u] : (int64_t)k * B + b;
+        int64_t id = __ldg(values + vi);
+        const int64_t hi = (int64_t)s_vocab[k] - 1;
+        id = id < 0 ? 0 : (id > hi ? hi : id);  // clamp(id, 0, V_k-1)
+        row[u] = s_base[k] + id;
+        if (lane == 0) {
+          if (rows_out) rows_out[slot[u]] = (int32_t)row[u];
+          if (slots_out) slots_out[slot[u]] = (int32_t)(slot_base + slot[u]);
+        }
+      }
+    }
+    for (int c = lane; c < vec_per_row; c += G) {
+      float4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (row[u] >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(arena + row[u] * E) + c);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (row[u] >= 0) {
+          const int b = (int)(slot[u] / K), k = (int)(slot[u] - (int64_t)b * K);
+          store_vec4<OutT>(out + (int64_t)b * out_ld + out_col0 + (int64_t)k * E + 4 * c, v[u]);
+        }
+    }
+  }
+}
+
+// jagged bags (L >= 0 per bag), sum pooling; block stages its bag offsets through shared memory.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+ebc_fwd_jagged_kernel(const float* __restrict__ arena, const int64_t* __restrict__ row_base,
+                      const int32_t* __restrict__ vocab, const int64_t* __restrict__ values,
+                      const int64_t* __restrict__ bag_offsets, int B, int K, int E, int layout, OutT* __restrict__ out,
+                      int64_t out_ld, int64_t out_col0, int32_t* __restrict__ rows_out,
+                      int32_t* __restrict__ slots_out, int64_t slot_base, int G) {
+  extern __shared__ unsigned char smem_raw[];
+  int64_t* s_base = reinterpret_cast<int64_t*>(smem_raw);
+  int32_t* s_vocab = reinterpret_cast<int32_t*>(s_base + K);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    s_base[i] = row_base[i];
+    s_vocab[i] = vocab[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x % G;
+  const int64_t n_bags = (int64_t)B * K;
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
+  const int vec_per_row = E >> 2;
+  for (int64_t slot = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; slot < n_bags; slot += groups_total) {
+    const int b = (int)(slot / K), k = (int)(slot - (int64_t)b * K);
+    const int64_t j = layout == TT_LAYOUT_SAMPLE_MAJOR ? slot : (int64_t)k * B + b;
+    const int64_t beg = __ldg(bag_offsets + j), end = __ldg(bag_offsets + j + 1);
+    const int64_t hi = (int64_t)s_vocab[k] - 1, rb = s_base[k];
+    for (int c = lane; c < vec_per_row; c += G) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t p = beg; p < end; ++p) {
+        int64_t id = __ldg(values + p);
+        id = id < 0 ? 0 : (id > hi ? hi : id);
+        f4_add(acc, __ldg(reinterpret_cast<const float4*>(arena + (rb + id) * E) + c));
+      }
+      store_vec4<OutT>(out + (int64_t)b * out_ld + out_col0 + (int64_t)k * E + 4 * c, acc);
+    }
+    if (lane == 0 && (rows_out || slots_out)) {
+      for (int64_t p = beg; p < end; ++p) {
+        int64_t id = __ldg(values + p);
+        id = id < 0 ? 0 : (id > hi ? hi : id);
+        if (rows_out) rows_out[p] = (int32_t)(rb + id);
+        if (slots_out) slots_out[p] = (int32_t)(slot_base + slot);
+      }
+    }
+  }
+}
+
+static int lanes_per_row(int E) {
+  int g = 1;
+  while (g < (E >> 2) && g < 32) g <<= 1;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stable LSD radix sort (8-bit digits) of (row, slot) pairs by row
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys per block
+
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int shift, int32_t* __restrict__ hist, int n_tiles) {
+  __shared__ int32_t s_hist[256];
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int64_t idx = base + (int64_t)i * RS_THREADS + threadIdx.x;
+    if (idx < n) atomicAdd(&s_hist[((uint32_t)keys[idx] >> shift) & 255u], 1);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+// exclusive scan of `len` int32 counters in place, one block
+__global__ void __launch_bounds__(1024) scan_exclusive_kernel(int32_t* __restrict__ data, int64_t len) {
+  __shared__ int32_t s_part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (len + 1023) / 1024;
+  const int64_t lo = (int64_t)t * per, hi = (lo + per < len) ? lo + per : len;
+  int32_t sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += data[i];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+    int32_t v = (t >= off) ? s_part[t - off] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int32_t run = s_part[t] - sum;
+  for (int64_t i = lo; i < hi; ++i) {
+    int32_t c = data[i];
+    data[i] = run;
+    run += c;
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n, int shift,
+                     const int32_t* __restrict__ hist_scanned, int n_tiles, int32_t* __restrict__ keys_out,
+                     int32_t* __restrict__ vals_out) {
+  // each warp owns 256 consecutive keys; item i of the warp is keys [i*32, i*32+32) of that chunk, so
+  // (item, lane) order == index order and the ranking below is stable.
+  __shared__ int32_t s_warp_hist[RS_THREADS / 32][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
+  int32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int64_t idx = base + i * 32 + lane;
+    const bool ok = idx < n;
+    key[i] = ok ? keys_in[idx] : 0;
+    val[i] = ok ? (vals_in ? vals_in[idx] : (int32_t)idx) : 0;
+    const unsigned active = __ballot_sync(0xffffffffu, ok);
+    rank[i] = -1;
+    if (ok) {
+      const uint32_t d = ((uint32_t)key[i] >> shift) & 255u;
+      const unsigned peers = __match_any_sync(active, d);
+      const int leader = __ffs(peers) - 1;
+      int32_t prev = 0;
+      if (lane == leader) {
+        prev = s_warp_hist[warp][d];
+        s_warp_hist[warp][d] = prev + __popc(peers);
+      }
+      prev = __shfl_sync(peers, prev, leader);
+      rank[i] = prev + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: exclusive scan over warps, plus this tile's global start for the digit
+  {
+    const int d = threadIdx.x;  // RS_THREADS == 256 digits
+    int32_t run = hist_scanned[(int64_t)d * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; ++w) {
+      int32_t c = s_warp_hist[w][d];
+      s_warp_hist[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    if (rank[i] >= 0) {
+      const uint32_t d = ((uint32_t)key[i] >> shift) & 255u;
+      const int32_t pos = s_warp_hist[warp][d] + rank[i];
+      keys_out[pos] = key[i];
+      vals_out[pos] = val[i];
+    }
+  }
+}
+
+__global__ void segment_bounds_kernel(const int32_t* __restrict__ srow, int64_t n, int32_t* __restrict__ row_begin,
+                                      int32_t* __restrict__ row_end, int32_t* __restrict__ row_stamp, int32_t stamp,
+                                      const int64_t* __restrict__ d_stamp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (d_stamp) stamp += (int32_t)(*d_stamp);
+  const int32_t r = srow[i];
+  if (i == 0 || srow[i - 1] != r) {
+    row_begin[r] = (int32_t)i;
+    row_stamp[r] = stamp;
+  }
+  if (i == n - 1 || srow[i + 1] != r) row_end[r] = (int32_t)(i + 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// segment-sum + Adam
+// ------------------------------------------------------------------------------------------------
+constexpr int SEG_CHUNK = 64;  // rows with more than SEG_CHUNK entries are reduced in two fixed levels
+
+struct GradSrc {
+  const void* g0;
+  const void* g1;
+  int64_t ld0, ld1, col0, col1, n0;
+  int K0, K1;
+};
+
+template <typename GT>
+__device__ __forceinline__ float4 load_grad_vec(const GradSrc& s, int32_t slot, int E, int c) {
+  const GT* base;
+  int64_t off;
+  if (slot < s.n0) {
+    const int b = slot / s.K0, k = slot - b * s.K0;
+    base = reinterpret_cast<const GT*>(s.g0);
+    off = (int64_t)b * s.ld0 + s.col0 + (int64_t)k * E + 4 * c;
+  } else {
+    const int sl = slot - (int32_t)s.n0;
+    const int b = sl / s.K1, k = sl - b * s.K1;
+    base = reinterpret_cast<const GT*>(s.g1);
+    off = (int64_t)b * s.ld1 + s.col1 + (int64_t)k * E + 4 * c;
+  }
+  if constexpr (sizeof(GT) == 4) {
+    return __ldg(reinterpret_cast<const float4*>(base + off));
+  } else {
+    return unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(base + off)));
+  }
+}
+
+// level 1 for long rows: one lane group per chunk of SEG_CHUNK sorted entries
+template <typename GT>
+__global__ void __launch_bounds__(256)
+ebc_piece_kernel(const int32_t* __restrict__ srow, const int32_t* __restrict__ sslot, int64_t n,
+                 const int32_t* __restrict__ row_begin, const int32_t* __restrict__ row_end, GradSrc src, int E, int G,
+                 float* __restrict__ pieces) {
+  const int lane = threadIdx.x % G;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+  const int64_t lo = chunk * SEG_CHUNK;
+  if (lo >= n) return;
+  const int64_t hi = (lo + SEG_CHUNK < n) ? lo + SEG_CHUNK : n;
+  const int vec_per_row = E >> 2;
+  const int32_t r0 = srow[lo], r1 = srow[hi - 1];
+  const int64_t b0 = row_begin[r0], e0 = row_end[r0];
+  const int64_t b1 = row_begin[r1], e1 = row_end[r1];
+  // piece 0: the long row covering index lo
+  if (e0 - b0 > SEG_CHUNK) {
+    const int64_t pe = e0 < hi ? e0 : hi;
+    for (int c = lane; c < vec_per_row; c += G) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t i = lo; i < pe; ++i) f4_add(acc, load_grad_vec<GT>(src, sslot[i], E, c));
+      *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 0) * E) + 4 * c) = acc;
+    }
+  }
+  // piece 1: a long row that begins strictly inside the chunk (it necessarily runs past hi)
+  if (e1 - b1 > SEG_CHUNK && b1 > lo) {
+    for (int c = lane; c < vec_per_row; c += G) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t i = b1; i < hi; ++i) f4_add(acc, load_grad_vec<GT>(src, sslot[i], E, c));
+      *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 1) * E) + 4 * c) = acc;
+    }
+  }
+}
+
+template <typename GT>
+__device__ __forceinline__ float4 row_grad_sum(const int32_t* __restrict__ sslot, int64_t b, int64_t e,
+                                               const GradSrc& src, int E, int c, const float* __restrict__ pieces) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e - b <= SEG_CHUNK) {
+    for (int64_t i = b; i < e; ++i) f4_add(acc, load_grad_vec<GT>(src, sslot[i], E, c));
+  } else {
+    for (int64_t ch = b / SEG_CHUNK; ch <= (e - 1) / SEG_CHUNK; ++ch) {
+      const int which = (b <= ch * SEG_CHUNK) ? 0 : 1;
+      f4_add(acc, *reinterpret_cast<const float4*>(pieces + ((ch * 2 + which) * E) + 4 * c));
+    }
+  }
+  return acc;
+}
+
+// torch.optim.Adam single-tensor update, element-wise (op order of torch/optim/adam.py)
+__device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g, const tt_adam_hyper& h) {
+  g = g + h.weight_decay * w;                     // grad.add(param, alpha=weight_decay)
+  m = m + (1.0f - h.beta1) * (g - m);             // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * h.beta2 + (1.0f - h.beta2) * g * g;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+  const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
+  w = w - h.step_size * (m / denom);              // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+__device__ __forceinline__ void adam_vec4(float4& w, float4& m, float4& v, const float4& g, const tt_adam_hyper& h) {
+  adam_elem(w.x, m.x, v.x, g.x, h);
+  adam_elem(w.y, m.y, v.y, g.y, h);
+  adam_elem(w.z, m.z, v.z, g.z, h);
+  adam_elem(w.w, m.w, v.w, g.w, h);
+}
+
+// one lane group per arena row, every row (dense-exact Adam and/or dense gradient materialisation)
+template <typename GT, bool DO_ADAM, bool WRITE_GRAD>
+__global__ void __launch_bounds__(256)
+ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, float* __restrict__ gout,
+                      int64_t total_rows, int E, int G, const int32_t* __restrict__ sslot,
+                      const int32_t* __restrict__ row_begin, const int32_t* __restrict__ row_end,
+                      const int32_t* __restrict__ row_stamp, int32_t stamp, const int64_t* __restrict__ d_stamp,
+                      GradSrc src, const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
+  if (d_stamp) stamp += (int32_t)(*d_stamp);
+  tt_adam_hyper h;
+  if (DO_ADAM) h = *d_hyper;
+  const int lane = threadIdx.x % G;
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
+  const int vec_per_row = E >> 2;
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; r < total_rows; r += groups_total) {
+    const bool hit = row_stamp[r] == stamp;
+    int64_t b = 0, e = 0;
+    if (hit) {
+      b = row_begin[r];
+      e = row_end[r];
+    }
+    for (int c = lane; c < vec_per_row; c += G) {
+      float4 g = hit ? row_grad_sum<GT>(sslot, b, e, src, E, c, pieces) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t off = r * E + 4 * c;
+      if (WRITE_GRAD) *reinterpret_cast<float4*>(gout + off) = g;
+      if (DO_ADAM) {
+        float4 wv = *reinterpret_cast<float4*>(w + off);
+        float4 mv = *reinterpret_cast<float4*>(m + off);
+        float4 vv = *reinterpret_cast<float4*>(v + off);
+        adam_vec4(wv, mv, vv, g, h);
+        *reinterpret_cast<float4*>(w + off) = wv;
+        *reinterpret_cast<float4*>(m + off) = mv;
+        *reinterpret_cast<float4*>(v + off) = vv;
+      }
+    }
+  }
+}
+
+// sparse mode: one lane group per sorted entry; only segment heads work
+template <typename GT>
+__global__ void __launch_bounds__(256)
+ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int E, int G,
+                       const int32_t* __restrict__ srow, const int32_t* __restrict__ sslot, int64_t n,
+                       const int32_t* __restrict__ row_end, GradSrc src, const float* __restrict__ pieces,
+                       const tt_adam_hyper* __restrict__ d_hyper) {
+  const tt_adam_hyper h = *d_hyper;
+  const int lane = threadIdx.x % G;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+  if (i >= n) return;
+  const int32_t r = srow[i];
+  if (i > 0 && srow[i - 1] == r) return;
+  const int64_t e = row_end[r];
+  const int vec_per_row = E >> 2;
+  for (int c = lane; c < vec_per_row; c += G) {
+    float4 g = row_grad_sum<GT>(sslot, i, e, src, E, c, pieces);
+    const int64_t off = (int64_t)r * E + 4 * c;
+    float4 wv = *reinterpret_cast<float4*>(w + off);
+    float4 mv = *reinterpret_cast<float4*>(m + off);
+    float4 vv = *reinterpret_cast<float4*>(v + off);
+    adam_vec4(wv, mv, vv, g, h);
+    *reinterpret_cast<float4*>(w + off) = wv;
+    *reinterpret_cast<float4*>(m + off) = mv;
+    *reinterpret_cast<float4*>(v + off) = vv;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dense_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  int64_t n, const tt_adam_hyper* __restrict__ d_hyper) {
+  const tt_adam_hyper h = *d_hyper;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 wv = reinterpret_cast<float4*>(w)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    adam_vec4(wv, mv, vv, gv, h);
+    reinterpret_cast<float4*>(w)[i] = wv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    adam_elem(w[i], m[i], v[i], g[i], h);
+}
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" {
+
+int tt_ebc_forward(const float* arena, const int64_t* d_row_base, const int32_t* d_vocab, const int64_t* values,
+                   const int64_t* bag_offsets, int64_t n_values, int32_t B, int32_t K, int32_t E, int32_t layout,
+                   void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0, int32_t* rows_out,
+                   int32_t* slots_out, int64_t slot_base, tt_stream_t stream) {
+  TT_CHECK_ARG(arena && d_row_base && d_vocab && values && out, "tt_ebc_forward: NULL pointer");
+  TT_CHECK_ARG(B >= 0 && K > 0 && E > 0 && (E % 4) == 0, "tt_ebc_forward: need K>0, E%%4==0 (B=%d K=%d E=%d)", B, K, E);
+  TT_CHECK_ARG(layout == TT_LAYOUT_SAMPLE_MAJOR || layout == TT_LAYOUT_KEY_MAJOR, "tt_ebc_forward: bad layout %d", layout);
+  TT_CHECK_ARG(out_dtype == TT_F32 || out_dtype == TT_BF16, "tt_ebc_forward: bad out_dtype %d", out_dtype);
+  TT_CHECK_ARG((out_ld % 4) == 0 && (out_col0 % 4) == 0 && out_ld >= out_col0 + (int64_t)K * E,
+               "tt_ebc_forward: out_ld/out_col0 must be multiples of 4 and fit K*E columns");
+  TT_CHECK_ARG(bag_offsets != nullptr || n_values == (int64_t)B * K,
+               "tt_ebc_forward: without bag_offsets n_values (%lld) must equal B*K (%lld)", (long long)n_values,
+               (long long)B * K);
+  if (B == 0) return TT_OK;
+  const int G = lanes_per_row(E);
+  const int threads = 256;
+  const int64_t n_bags = (int64_t)B * K;
+  const size_t smem = (size_t)K * (sizeof(int64_t) + sizeof(int32_t));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int groups_per_block = threads / G;
+  if (bag_offsets == nullptr) {
+    constexpr int UNROLL = 4;
+    int64_t want = ceil_div(n_bags, (int64_t)groups_per_block * UNROLL);
+    int grid = (int)(want < 1 ? 1 : (want > (int64_t)sm_count() * 16 ? (int64_t)sm_count() * 16 : want));
+    if (out_dtype == TT_F32)
+      ebc_fwd_l1_kernel<float, UNROLL><<<grid, threads, smem, s>>>(arena, d_row_base, d_vocab, values, B, K, E, layout,
+                                                                   (float*)out, out_ld, out_col0, rows_out, slots_out, slot_base, G);
+    else
+      ebc_fwd_l1_kernel<__nv_bfloat16, UNROLL><<<grid, threads, smem, s>>>(
+          arena, d_row_base, d_vocab, values, B, K, E, layout, (__nv_bfloat16*)out, out_ld, out_col0, rows_out,
+          slots_out, slot_base, G);
+  } else {
+    int64_t want = ceil_div(n_bags, groups_per_block);
+    int grid = (int)(want < 1 ? 1 : (want > (int64_t)sm_count() * 16 ? (int64_t)sm_count() * 16 : want));
+    if (out_dtype == TT_F32)
+      ebc_fwd_jagged_kernel<float><<<grid, threads, smem, s>>>(arena, d_row_base, d_vocab, values, bag_offsets, B, K, E,
+                                                               layout, (float*)out, out_ld, out_col0, rows_out,
+                                                               slots_out, slot_base, G);
+    else
+      ebc_fwd_jagged_kernel<__nv_bfloat16><<<grid, threads, smem, s>>>(arena, d_row_base, d_vocab, values, bag_offsets,
+                                                                       B, K, E, layout, (__nv_bfloat16*)out, out_ld,
+                                                                       out_col0, rows_out, slots_out, slot_base, G);
+  }
+  TT_LAUNCH_CHECK("ebc_fwd_kernel");
+  return TT_OK;
+}
+
+int64_t tt_ebc_sort_workspace_bytes(int64_t n, int64_t total_rows) {
+  (void)total_rows;
+  if (n < 0) return 0;
+  const int64_t tiles = (n + RS_TILE - 1) / RS_TILE + 1;
+  return 2 * align_up(n * 4 + 16, 256) + align_up(256 * tiles * 4, 256);
+}
+
+int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
+                     int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
+                     int32_t* row_end, int32_t* row_stamp, int32_t stamp, const int64_t* d_stamp,
+                     tt_stream_t stream) {
+  TT_CHECK_ARG(rows && sorted_rows && sorted_slots && row_begin && row_end && row_stamp, "tt_ebc_sort_rows: NULL pointer");
+  TT_CHECK_ARG(n >= 0 && n < (1ll << 31) && total_rows > 0 && total_rows < (1ll << 31), "tt_ebc_sort_rows: bad sizes");
+  TT_CHECK_ARG(workspace_bytes >= tt_ebc_sort_workspace_bytes(n, total_rows) && (workspace || n == 0),
+               "tt_ebc_sort_rows: workspace too small (%lld < %lld)", (long long)workspace_bytes,
+               (long long)tt_ebc_sort_workspace_bytes(n, total_rows));
+  if (n == 0) return TT_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int bits = 0;
+  while (((int64_t)1 << bits) < total_rows) ++bits;
+  int passes = (bits + 7) / 8;
+  if (passes < 1) passes = 1;
+  const int n_tiles = (int)((n + RS_TILE - 1) / RS_TILE);
+  char* ws = (char*)workspace;
+  int32_t* tmp_keys = (int32_t*)ws;
+  int32_t* tmp_vals = (int32_t*)(ws + align_up(n * 4 + 16, 256));
+  int32_t* hist = (int32_t*)(ws + 2 * align_up(n * 4 + 16, 256));
+  const int32_t* kin = rows;
+  const int32_t* vin = slots;  // NULL => identity on the first pass
+  for (int p = 0; p < passes; ++p) {
+    const bool to_final = ((passes - 1 - p) % 2) == 0;
+    int32_t* kout = to_final ? sorted_rows : tmp_keys;
+    int32_t* vout = to_final ? sorted_slots : tmp_vals;
+    radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, n, p * 8, hist, n_tiles);
+    scan_exclusive_kernel<<<1, 1024, 0, s>>>(hist, (int64_t)256 * n_tiles);
+    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, p * 8, hist, n_tiles, kout, vout);
+    kin = kout;
+    vin = vout;
+  }
+  segment_bounds_kernel<<<ceil_div(n, 256), 256, 0, s>>>(sorted_rows, n, row_begin, row_end, row_stamp, stamp, d_stamp);
+  TT_LAUNCH_CHECK("ebc_sort_rows");
+  return TT_OK;
+}
+
+int64_t tt_ebc_piece_workspace_bytes(int64_t n, int32_t E) {
+  const int64_t chunks = (n + SEG_CHUNK - 1) / SEG_CHUNK + 1;
+  return chunks * 2 * (int64_t)E * 4;
+}
+
+int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* grad_arena, int64_t total_rows,
+                         int32_t E, const int32_t* sorted_rows, const int32_t* sorted_slots, int64_t n,
+                         const int32_t* row_begin, const int32_t* row_end, const int32_t* row_stamp, int32_t stamp,
+                         const int64_t* d_stamp, const void* grad0, int64_t ld0, int64_t col0_0, int32_t K0, int64_t n0, const void* grad1,
+                         int64_t ld1, int64_t col0_1, int32_t K1, int64_t n1, int32_t grad_dtype, void* piece_ws,
+                         int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, tt_stream_t stream) {
+  const bool do_adam = arena_w != nullptr;
+  TT_CHECK_ARG(do_adam || grad_arena, "tt_ebc_backward_adam: nothing to do (arena_w and grad_arena both NULL)");
+  TT_CHECK_ARG(!do_adam || (arena_m && arena_v && d_hyper), "tt_ebc_backward_adam: Adam needs m, v and d_hyper");
+  TT_CHECK_ARG(E > 0 && (E % 4) == 0 && total_rows > 0, "tt_ebc_backward_adam: bad E/total_rows");
+  TT_CHECK_ARG(n == 0 || (sorted_rows && sorted_slots && row_begin && row_end && row_stamp && grad0),
+               "tt_ebc_backward_adam: NULL index/grad pointer");
+  TT_CHECK_ARG(n0 + n1 >= 0 && (n1 == 0 || grad1), "tt_ebc_backward_adam: grad1 missing");
+  TT_CHECK_ARG(K0 > 0 && (n1 == 0 || K1 > 0), "tt_ebc_backward_adam: bad K");
+  TT_CHECK_ARG((ld0 % 4) == 0 && (col0_0 % 4) == 0 && (ld1 % 4) == 0 && (col0_1 % 4) == 0,
+               "tt_ebc_backward_adam: grad ld/col0 must be multiples of 4");
+  TT_CHECK_ARG(grad_dtype == TT_F32 || grad_dtype == TT_BF16, "tt_ebc_backward_adam: bad grad dtype");
+  TT_CHECK_ARG(mode == TT_ADAM_DENSE_EXACT || mode == TT_ADAM_SPARSE, "tt_ebc_backward_adam: bad mode %d", mode);
+  TT_CHECK_ARG(!(mode == TT_ADAM_SPARSE && grad_arena), "tt_ebc_backward_adam: sparse mode cannot emit a dense grad");
+  TT_CHECK_ARG(piece_ws_bytes >= tt_ebc_piece_workspace_bytes(n, E) && (piece_ws || n == 0),
+               "tt_ebc_backward_adam: piece workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int G = lanes_per_row(E);
+  const int threads = 256, gpb = threads / G;
+  GradSrc src{grad0, grad1, ld0, ld1, col0_0, col0_1, n0, K0, K1 > 0 ? K1 : 1};
+  float* pieces = (float*)piece_ws;
+  if (n > 0) {
+    const int64_t chunks = (n + SEG_CHUNK - 1) / SEG_CHUNK;
+    if (grad_dtype == TT_F32)
+      ebc_piece_kernel<float><<<ceil_div(chunks, gpb), threads, 0, s>>>(sorted_rows, sorted_slots, n, row_begin, row_end,
+                                                                        src, E, G, pieces);
+    else
+      ebc_piece_kernel<__nv_bfloat16><<<ceil_div(chunks, gpb), threads, 0, s>>>(sorted_rows, sorted_slots, n, row_begin,
+                                                                                row_end, src, E, G, pieces);
+  }
+  if (mode == TT_ADAM_SPARSE) {
+    if (n > 0) {
+      if (grad_dtype == TT_F32)
+        ebc_rows_sparse_kernel<float><<<ceil_div(n, gpb), threads, 0, s>>>(arena_w, arena_m, arena_v, E, G, sorted_rows,
+                                                                           sorted_slots, n, row_end, src, pieces, d_hyper);
+      else
+        ebc_rows_sparse_kernel<__nv_bfloat16><<<ceil_div(n, gpb), threads, 0, s>>>(
+            arena_w, arena_m, arena_v, E, G, sorted_rows, sorted_slots, n, row_end, src, pieces, d_hyper);
+    }
+  } else {
+    int64_t want = ceil_div(total_rows, gpb);
+    const int64_t cap = (int64_t)sm_count() * 32;
+    const int grid = (int)(want > cap ? cap : want);
+    // rows absent from this batch must not match: stamp only ever matches rows written by this step's sort
+    const int32_t eff_stamp = stamp;
+#define TT_ROWS_LAUNCH(GT, A, W)                                                                                    \
+  ebc_rows_dense_kernel<GT, A, W><<<grid, threads, 0, s>>>(arena_w, arena_m, arena_v, grad_arena, total_rows, E, G, \
+                                                           sorted_slots, row_begin, row_end, row_stamp, eff_stamp,  \
+                                                           d_stamp, src, pieces, d_hyper)
+    const bool wg = grad_arena != nullptr;
+    if (grad_dtype == TT_F32) {
+      if (do_adam && wg) TT_ROWS_LAUNCH(float, true, true);
+      else if (do_adam) TT_ROWS_LAUNCH(float, true, false);
+      else TT_ROWS_LAUNCH(float, false, true);
+    } else {
+      if (do_adam && wg) TT_ROWS_LAUNCH(__nv_bfloat16, true, true);
+      else if (do_adam) TT_ROWS_LAUNCH(__nv_bfloat16, true, false);
+      else TT_ROWS_LAUNCH(__nv_bfloat16, false, true);
+    }
+#undef TT_ROWS_LAUNCH
+  }
+  TT_LAUNCH_CHECK("ebc_backward_adam");
+  return TT_OK;
+}
+
+int tt_dense_adam(float* w, const float* g, float* m, float* v, int64_t n, const tt_adam_hyper* d_hyper,
+                  tt_stream_t stream) {
+  TT_CHECK_ARG(w && g && m && v && d_hyper && n >= 0, "tt_dense_adam: NULL pointer");
+  TT_CHECK_ARG((((uintptr_t)w | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "tt_dense_adam: buffers must be 16-byte aligned");
+  if (n == 0) return TT_OK;
+  int64_t want = ceil_div(n / 4 + 1, 256);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  dense_adam_kernel<<<(int)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(w, g, m, v, n, d_hyper);
+  TT_LAUNCH_CHECK("dense_adam_kernel");
+  return TT_OK;
+}
+
+}  // extern "C"

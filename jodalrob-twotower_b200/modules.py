@@ -1,0 +1,492 @@
+"""nn.Module façade with the reference's names, signatures and state_dict keys.
+
+Mirrors (paths relative to /root/reference):
+  CategoricalEmbedder          src/towers/cat_embed.py:11-190
+  BaseTower/Notice/Company     src/towers/tower/{base,notice,company}_tower.py
+  TwoTowerModel (+factory)     src/towers/two_tower_model.py:10-165
+  TwoTowerTrainTask (+factory) src/towers/two_tower_train_task.py:9-249
+so it drops in behind scripts/train.py:207-220,231,285,320-330,368,394,426.  The modules own no
+arithmetic: parameters are views into the engine's flat HBM buffers and every forward/backward is a
+sequence of C-ABI kernel launches (engine.py).  Two ways to train:
+  (i)  autograd-compatible: `loss = task(batch)["loss"]; loss.backward(); torch.optim.Adam.step()` —
+       gradients of every parameter (dense [V,E] for tables, like nn.Embedding) come from our kernels;
+  (ii) fused: attach `FusedAdam(task, ...)`; then `loss.backward()` runs backward + sort-dedup +
+       fused Adam inside the library and `optimizer.step()` / `scheduler.step()` are no-ops, so the
+       reference's training loop is unchanged.  `task.fused_step(batch)` is the same without autograd.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+
+from . import native
+from .engine import TwoTowerConfig, TwoTowerEngine
+from .kjt import KeyedJaggedTensor
+from .schema import vocab_sizes_from_metadata
+
+__all__ = ["CategoricalEmbedder", "BaseTower", "NoticeTower", "CompanyTower", "TwoTowerModel", "TwoTowerTrainTask",
+           "create_two_tower_model", "create_two_tower_train_task", "FusedAdam", "FusedWarmupScheduler"]
+
+
+class _Table(nn.Module):
+    """Stands where the reference has nn.Embedding (cat_embed.py:41-45): `.weight` is a row view of the arena."""
+
+    def __init__(self, weight: torch.Tensor):
+        super().__init__()
+        self.num_embeddings, self.embedding_dim = weight.shape
+        self.weight = nn.Parameter(weight)
+
+
+class _Linear(nn.Module):
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor):
+        super().__init__()
+        self.out_features, self.in_features = weight.shape
+        self.weight = nn.Parameter(weight)
+        self.bias = nn.Parameter(bias)
+
+
+class _BatchNorm(nn.Module):
+    def __init__(self, weight, bias, running_mean, running_var, num_batches_tracked):
+        super().__init__()
+        self.num_features = weight.shape[0]
+        self.eps, self.momentum = 1e-5, 0.1
+        self.weight = nn.Parameter(weight)
+        self.bias = nn.Parameter(bias)
+        self.register_buffer("running_mean", running_mean)
+        self.register_buffer("running_var", running_var)
+        self.register_buffer("num_batches_tracked", num_batches_tracked)
+
+
+class _Marker(nn.Module):
+    """Parameter-free place holder (ReLU / Dropout slots) so mlp.{0,2,4,...} indices match the reference."""
+
+    def __init__(self, kind: str, p: float = 0.0):
+        super().__init__()
+        self.kind, self.p = kind, p
+
+    def extra_repr(self):
+        return f"{self.kind}" + (f", p={self.p}" if self.kind == "dropout" else "")
+
+
+def _values_of(kjt) -> torch.Tensor:
+    v = kjt.values()
+    return v if v.dtype == torch.int64 else v.to(torch.int64)
+
+
+def _layout_of(kjt) -> Optional[str]:
+    return getattr(kjt, "layout", None)
+
+
+class CategoricalEmbedder(nn.Module):
+    def __init__(self, engine: TwoTowerEngine, tower: int):
+        super().__init__()
+        self._engine = [engine]  # hidden from nn.Module registration
+        self._tower = tower
+        name, keys, vocab, _ = engine.cfg.tower(tower)
+        self.keys = list(keys)
+        self.embedding_dim = engine.cfg.emb_dim
+        self.vocab_sizes = {k: int(v) for k, v in zip(keys, vocab)}
+        self.embeddings = nn.ModuleDict()
+        for ki, k in enumerate(self.keys):
+            lo, hi = engine.table_rows(tower, ki)
+            self.embeddings[k] = _Table(engine.arena[lo:hi])
+
+    def forward(self, kjt, return_dict: bool = True):
+        """Pooled lookup of every key (forward only; training goes through TwoTowerTrainTask).
+        Raises on malformed input instead of the reference's silent zero fallback (cat_embed.py:180-190)."""
+        from . import ops
+        eng = self._engine[0]
+        if kjt is None:
+            raise ValueError("kjt is None")
+        values = _values_of(kjt).to(eng.device)
+        K = len(self.keys)
+        B = values.numel() // K
+        out = ops.ebc_forward(eng, self._tower, values, B, layout=_layout_of(kjt) or eng.default_layout)
+        if return_dict:
+            E = self.embedding_dim
+            return {k: out[:, i * E:(i + 1) * E] for i, k in enumerate(self.keys)}
+        return out
+
+
+class BaseTower(nn.Module):
+    def __init__(self, engine: TwoTowerEngine, tower: int):
+        super().__init__()
+        self._engine = [engine]
+        self._tower = tower
+        cfg = engine.cfg
+        name, keys, _, _ = cfg.tower(tower)
+        pre = f"{name}_tower."
+        self.categorical_keys = list(keys)
+        self.device = engine.device
+        self.categorical_embedder = CategoricalEmbedder(engine, tower)
+        self.dense_projection = _Linear(engine.dense(pre + "dense_projection.weight"), engine.dense(pre + "dense_projection.bias"))
+        layers: List[nn.Module] = []
+        idx = 0
+        for bi, _h in enumerate(cfg.hidden[1:]):
+            layers += [_Linear(engine.dense(pre + f"mlp.{idx}.weight"), engine.dense(pre + f"mlp.{idx}.bias")),
+                       _Marker("relu"),
+                       _BatchNorm(engine.dense(pre + f"mlp.{idx + 2}.weight"), engine.dense(pre + f"mlp.{idx + 2}.bias"),
+                                  engine.bn_rm[tower][bi], engine.bn_rv[tower][bi], engine.bn_nbt[tower][bi]),
+                       _Marker("dropout", cfg.dropout)]
+            idx += 4
+        layers.append(_Linear(engine.dense(pre + f"mlp.{idx}.weight"), engine.dense(pre + f"mlp.{idx}.bias")))
+        self.mlp = nn.Sequential(*layers)
+
+    def forward(self, tower_input: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """[B, final_embedding_dim] L2-normalised embeddings (base_tower.py:101-147), forward only."""
+        eng = self._engine[0]
+        dense = tower_input["dense"].to(eng.device)
+        kjt = tower_input["kjt"].to(eng.device)
+        values = _values_of(kjt)
+        B = dense.shape[0]
+        ws = eng.workspace(B)
+        lay = native.TT_LAYOUT_KEY_MAJOR if (_layout_of(kjt) or eng.default_layout) == "key_major" else native.TT_LAYOUT_SAMPLE_MAJOR
+        eng._check_inputs(self._tower, dense, values, B)
+        with torch.no_grad():
+            return eng.tower_forward(self._tower, ws, dense, values, self.training, lay).clone()
+
+
+class NoticeTower(BaseTower):
+    def __init__(self, engine: TwoTowerEngine):
+        super().__init__(engine, 0)
+
+
+class CompanyTower(BaseTower):
+    def __init__(self, engine: TwoTowerEngine):
+        super().__init__(engine, 1)
+
+
+class TwoTowerModel(nn.Module):
+    def __init__(self, engine: TwoTowerEngine):
+        super().__init__()
+        self._engine = [engine]
+        self.device = engine.device
+        self.final_embedding_dim = engine.cfg.final_dim
+        self.notice_tower = NoticeTower(engine)
+        self.company_tower = CompanyTower(engine)
+
+    @property
+    def engine(self) -> TwoTowerEngine:
+        return self._engine[0]
+
+    def forward(self, notice_input, company_input, return_similarity: bool = False, temperature: float = 1.0):
+        n = self.notice_tower(notice_input)
+        c = self.company_tower(company_input)
+        if n.size(0) != c.size(0):
+            raise ValueError(f"Notice와 Company 배치 크기가 다릅니다: {n.size(0)} vs {c.size(0)}")
+        if return_similarity:
+            from . import ops
+            return {"notice_embeddings": n, "company_embeddings": c,
+                    "similarity_matrix": ops.similarity_matrix(self.engine, n, c, 1.0 / temperature)}
+        return n, c
+
+    def get_notice_embeddings(self, notice_input):
+        return self.notice_tower(notice_input)
+
+    def get_company_embeddings(self, company_input):
+        return self.company_tower(company_input)
+
+    def compute_similarity(self, notice_emb, company_emb, temperature: float = 1.0):
+        from . import ops
+        return ops.similarity_matrix(self.engine, notice_emb, company_emb, 1.0 / temperature)
+
+
+class _LazyResult(dict):
+    """Result dict of TwoTowerTrainTask.forward; the B x B `similarity_matrix` (two_tower_train_task.py:94) is
+    only materialised if somebody reads it — the train step itself never stores the logits."""
+
+    def __init__(self, base: dict, make_sim):
+        super().__init__(base)
+        self._make_sim = make_sim
+
+    def __getitem__(self, k):
+        if k == "similarity_matrix" and not dict.__contains__(self, k):
+            dict.__setitem__(self, k, self._make_sim())
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        return self[k] if (k == "similarity_matrix" or dict.__contains__(self, k)) else default
+
+    def __contains__(self, k):
+        return k == "similarity_matrix" or dict.__contains__(self, k)
+
+    def keys(self):
+        return list(dict.keys(self)) + ([] if dict.__contains__(self, "similarity_matrix") else ["similarity_matrix"])
+
+
+class _TrainStepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, task, nd, nv, cd, cv, layout, masks, *params):
+        eng = task.engine
+        if task._fused_opt is not None:
+            o = task._fused_opt
+            eng.hyper_advance(o.lr, o.warmup_steps, o.betas, o.eps, o.weight_decay)
+        elif eng.cfg.dropout > 0:
+            eng.hyper_advance(0.0, 0, (0.9, 0.999), 1e-8, 0.0)  # only the dropout RNG step matters here
+        out5, ws = eng.forward(nd, nv, cd, cv, True, layout, masks)
+        ctx.task, ctx.ws = task, ws
+        res = out5.clone()
+        ctx.mark_non_differentiable(res)
+        return res[0].clone(), res
+
+    @staticmethod
+    def backward(ctx, dloss, _dres):
+        task, ws = ctx.task, ctx.ws
+        eng = task.engine
+        if task._fused_opt is not None:
+            # backward + sort-dedup + fused Adam all inside the library; upstream gradient is taken as 1
+            eng.backward(ws, 1.0)
+            eng.embedding_backward(ws, apply_adam=True, want_dense_grad=False)
+            eng.dense_adam()
+            return (None,) * 8  # 7 plain arguments + the anchor
+        eng.backward(ws, float(dloss))
+        eng.embedding_backward(ws, apply_adam=False, want_dense_grad=True)
+        grads = []
+        for kind, ref in task._param_src:
+            if kind == "table":
+                lo, hi = ref
+                grads.append(eng.arena_grad[lo:hi].clone())
+            else:
+                grads.append(eng.dense(ref, "g").clone())
+        return (None,) * 7 + tuple(grads)
+
+
+class TwoTowerTrainTask(nn.Module):
+    def __init__(self, two_tower_model: TwoTowerModel, temperature: float = 1.0, loss_type: str = "cross_entropy",
+                 label_smoothing: float = 0.0):
+        super().__init__()
+        if loss_type not in ["cross_entropy", "cosine_embedding"]:
+            raise ValueError(f"Unsupported loss_type: {loss_type}")
+        self.two_tower_model = two_tower_model
+        self.temperature = temperature
+        self.loss_type = loss_type
+        self.label_smoothing = label_smoothing
+        self._fused_opt: Optional["FusedAdam"] = None
+        self._anchor = torch.zeros((), device=two_tower_model.device, requires_grad=True)
+        self.debug_pair_check = False
+        self._index_params()
+
+    @property
+    def engine(self) -> TwoTowerEngine:
+        return self.two_tower_model.engine
+
+    def _index_params(self):
+        eng = self.engine
+        self._param_list, self._param_src = [], []
+        for name, p in self.named_parameters():
+            self._param_list.append(p)
+            short = name[len("two_tower_model."):]
+            if ".embeddings." in short:
+                tower = 0 if short.startswith("notice") else 1
+                key = short.split(".embeddings.")[1].rsplit(".weight", 1)[0]
+                keys = eng.cfg.notice_keys if tower == 0 else eng.cfg.company_keys
+                self._param_src.append(("table", eng.table_rows(tower, keys.index(key))))
+            else:
+                self._param_src.append(("dense", short))
+
+    def _apply(self, fn, *a, **kw):
+        # parameters are views of the engine's flat buffers; moving/casting them would break the aliasing
+        probe = fn(torch.zeros(1, device=self.engine.device))
+        if probe.device != self.engine.device or probe.dtype != torch.float32:
+            raise RuntimeError("TwoTowerTrainTask lives on the device it was created on (fp32 masters); "
+                               "pass device= to create_two_tower_train_task instead of calling .to()/.half()")
+        return self
+
+    def _sync_cfg(self):
+        cfg = self.engine.cfg
+        cfg.temperature, cfg.label_smoothing = float(self.temperature), float(self.label_smoothing)
+
+    def _unpack(self, batch):
+        eng = self.engine
+        n, c = batch["notice"], batch["company"]
+        nb, cb = n["dense"].size(0), c["dense"].size(0)
+        if nb != cb:
+            raise ValueError(f"Notice와 Company 배치 크기가 다릅니다: {nb} vs {cb}")
+        nd, cd = n["dense"].to(eng.device, non_blocking=True), c["dense"].to(eng.device, non_blocking=True)
+        nk, ck = n["kjt"].to(eng.device), c["kjt"].to(eng.device)
+        lay = _layout_of(nk) or eng.default_layout
+        return nd, _values_of(nk), cd, _values_of(ck), lay
+
+    def forward(self, batch, return_metrics: bool = False, dropout_masks=None):
+        self._sync_cfg()
+        eng = self.engine
+        nd, nv, cd, cv, lay = self._unpack(batch)
+        if self.loss_type != "cross_entropy":
+            return self._forward_cosine_embedding(nd, nv, cd, cv, lay, return_metrics)
+        if self.training and torch.is_grad_enabled():
+            params = (self._anchor,) if self._fused_opt is not None else tuple(self._param_list)
+            loss, res = _TrainStepFn.apply(self, nd, nv, cd, cv, lay, dropout_masks, *params)
+            ws = eng.workspace(nd.shape[0])
+        else:
+            with torch.no_grad():
+                out5, ws = eng.forward(nd, nv, cd, cv, self.training, lay, dropout_masks)
+                res = out5.clone()
+                loss = res[0]
+        if self.debug_pair_check and not hasattr(self, "_pair_check_done"):
+            self._verify_positive_pair_alignment(eng.similarity_matrix(ws))
+            self._pair_check_done = True
+        if not return_metrics:
+            return loss
+        det = res.detach()
+        return _LazyResult({"loss": loss, "accuracy": det[1], "positive_similarity_mean": det[2],
+                            "negative_similarity_mean": det[3], "similarity_gap": det[4]},
+                           lambda: eng.similarity_matrix(ws))
+
+    def fused_step(self, batch, lr=None, warmup_steps=None) -> torch.Tensor:
+        """One whole train step inside the library, no autograd. Returns the device tensor
+        [loss, accuracy, positive_similarity_mean, negative_similarity_mean, similarity_gap]."""
+        self._sync_cfg()
+        o = self._fused_opt
+        if o is None:
+            raise RuntimeError("attach a FusedAdam(task, ...) before fused_step")
+        nd, nv, cd, cv, lay = self._unpack(batch)
+        return self.engine.fused_step(nd, nv, cd, cv, lr if lr is not None else o.lr,
+                                      warmup_steps if warmup_steps is not None else o.warmup_steps, o.betas, o.eps,
+                                      o.weight_decay, lay)
+
+    def _forward_cosine_embedding(self, nd, nv, cd, cv, lay, return_metrics):
+        # two_tower_train_task.py:136-158 — the non-default, near-zero-gradient alternative loss; evaluated from the
+        # materialised matrix with torch ops, forward only. Training with it is not on the hot path.
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("loss_type='cosine_embedding' is forward-only here; the hot path is cross_entropy")
+        import torch.nn.functional as F
+        eng = self.engine
+        with torch.no_grad():
+            res, ws = eng.forward(nd, nv, cd, cv, self.training, lay)
+            s = eng.similarity_matrix(ws)
+            b = s.size(0)
+            off = ~torch.eye(b, dtype=torch.bool, device=s.device)
+            sims = torch.cat([torch.diag(s), s[off]])
+            tg = torch.cat([torch.ones(b, device=s.device), -torch.ones(b * b - b, device=s.device)])
+            loss = F.cosine_embedding_loss(sims.unsqueeze(1), torch.ones_like(sims.unsqueeze(1)), tg)
+        if not return_metrics:
+            return loss
+        r = res.clone()
+        return {"loss": loss, "accuracy": r[1], "positive_similarity_mean": r[2], "negative_similarity_mean": r[3],
+                "similarity_gap": r[4], "similarity_matrix": s}
+
+    def predict_batch(self, batch, top_k: int = 10):
+        self.eval()
+        with torch.no_grad():
+            n, c = self.two_tower_model(batch["notice"], batch["company"])
+            from . import ops
+            s = ops.similarity_matrix(self.engine, n, c, 1.0 / self.temperature)
+            top_sim, top_idx = torch.topk(s, k=top_k, dim=1)
+            return {"top_similarities": top_sim, "top_indices": top_idx, "all_similarities": s}
+
+    def _verify_positive_pair_alignment(self, similarity_matrix: torch.Tensor):
+        b = similarity_matrix.size(0)
+        idx = torch.arange(b, device=similarity_matrix.device)
+        row_hit = (similarity_matrix.argmax(dim=1) == idx).float().mean().item()
+        col_hit = (similarity_matrix.argmax(dim=0) == idx).float().mean().item()
+        print(f"[Positive Pair Alignment Check] notice->company top-1 {row_hit:.3f}, company->notice top-1 {col_hit:.3f}")
+
+
+class FusedAdam:
+    """Optimizer shim for the fused path: the Adam update (coupled L2 weight decay, bias correction, the
+    LambdaLR warm-up of scripts/train.py:235-242) runs inside the library during loss.backward();
+    zero_grad()/step() keep the reference loop (scripts/train.py:319-330) unchanged."""
+
+    def __init__(self, task: TwoTowerTrainTask, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, warmup_steps: int = 0):
+        self.task, self.lr, self.betas, self.eps, self.weight_decay = task, lr, tuple(betas), eps, weight_decay
+        self.warmup_steps = int(warmup_steps)
+        self.param_groups = [{"lr": lr, "betas": self.betas, "eps": eps, "weight_decay": weight_decay,
+                              "params": task._param_list}]
+        task._fused_opt = self
+
+    def zero_grad(self, set_to_none: bool = True):
+        return None
+
+    def step(self, closure=None):
+        return None
+
+    def state_dict(self):
+        eng = self.task.engine
+        return {"hyper": eng.hyper.clone(), "arena_m": eng.arena_m.clone(), "arena_v": eng.arena_v.clone(),
+                "dense_m": eng.dense_m.clone(), "dense_v": eng.dense_v.clone(),
+                "config": {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
+                           "warmup_steps": self.warmup_steps}}
+
+    def load_state_dict(self, sd):
+        eng = self.task.engine
+        for k in ("hyper", "arena_m", "arena_v", "dense_m", "dense_v"):
+            getattr(eng, k).copy_(sd[k])
+        c = sd["config"]
+        self.lr, self.betas, self.eps, self.weight_decay = c["lr"], tuple(c["betas"]), c["eps"], c["weight_decay"]
+        self.warmup_steps = c["warmup_steps"]
+
+
+class FusedWarmupScheduler:
+    """Stand-in for LambdaLR(optimizer, lr_lambda) of scripts/train.py:242; the schedule lives on the device."""
+
+    def __init__(self, optimizer: FusedAdam, warmup_steps: int):
+        self.optimizer = optimizer
+        optimizer.warmup_steps = int(warmup_steps)
+
+    def step(self):
+        return None
+
+    def get_last_lr(self):
+        return [self.optimizer.task.engine.hyper_host()["lr"]]
+
+
+def _init_like_reference(engine: TwoTowerEngine):
+    """Same initial distribution AND the same RNG consumption order as the reference constructors
+    (nn.Embedding N(0,1) per key, then nn.Linear defaults, BatchNorm gamma=1/beta=0; notice tower first),
+    so torch.manual_seed(s) before the factory reproduces a seeded reference bit-for-bit."""
+    cfg = engine.cfg
+    for t in range(2):
+        name, keys, vocab, dense_dim = cfg.tower(t)
+        pre = f"{name}_tower."
+        for ki, v in enumerate(vocab):
+            lo, hi = engine.table_rows(t, ki)
+            engine.arena[lo:hi].copy_(nn.Embedding(v, cfg.emb_dim).weight.detach())
+        lin = nn.Linear(dense_dim, cfg.hidden[0])
+        engine.dense(pre + "dense_projection.weight").copy_(lin.weight.detach())
+        engine.dense(pre + "dense_projection.bias").copy_(lin.bias.detach())
+        width, idx = cfg.hidden[0] + len(keys) * cfg.emb_dim, 0
+        for h in cfg.hidden[1:]:
+            lin = nn.Linear(width, h)
+            engine.dense(pre + f"mlp.{idx}.weight").copy_(lin.weight.detach())
+            engine.dense(pre + f"mlp.{idx}.bias").copy_(lin.bias.detach())
+            engine.dense(pre + f"mlp.{idx + 2}.weight").fill_(1.0)
+            engine.dense(pre + f"mlp.{idx + 2}.bias").zero_()
+            width, idx = h, idx + 4
+        lin = nn.Linear(width, cfg.final_dim)
+        engine.dense(pre + f"mlp.{idx}.weight").copy_(lin.weight.detach())
+        engine.dense(pre + f"mlp.{idx}.bias").copy_(lin.bias.detach())
+
+
+def create_two_tower_model(notice_categorical_keys: Sequence[str], company_categorical_keys: Sequence[str],
+                           metadata_path: str = "meta/metadata.csv", categorical_embedding_dim: int = 64,
+                           notice_dense_input_dim: int = 256, company_dense_input_dim: int = 128,
+                           tower_hidden_dims: Optional[List[int]] = None, final_embedding_dim: int = 128,
+                           dropout_rate: float = 0.2, device="cuda:0", vocab_sizes: Optional[Dict[str, Dict[str, int]]] = None,
+                           optimizer_mode: str = "dense_exact", value_layout: str = "sample_major") -> TwoTowerModel:
+    if tower_hidden_dims is None:
+        tower_hidden_dims = [256, 128]
+    nk, ck = list(notice_categorical_keys), list(company_categorical_keys)
+    if vocab_sizes is None:
+        vocab_sizes = {"notice": vocab_sizes_from_metadata(metadata_path, "notice", nk),
+                       "company": vocab_sizes_from_metadata(metadata_path, "company", ck)}
+    cfg = TwoTowerConfig(nk, ck, [int(vocab_sizes["notice"][k]) for k in nk], [int(vocab_sizes["company"][k]) for k in ck],
+                         categorical_embedding_dim, notice_dense_input_dim, company_dense_input_dim,
+                         list(tower_hidden_dims), final_embedding_dim, dropout_rate)
+    engine = TwoTowerEngine(cfg, device, optimizer_mode, value_layout)
+    _init_like_reference(engine)
+    return TwoTowerModel(engine)
+
+
+def create_two_tower_train_task(notice_categorical_keys, company_categorical_keys, metadata_path: str = "meta/metadata.csv",
+                                categorical_embedding_dim: int = 64, notice_dense_input_dim: int = 256,
+                                company_dense_input_dim: int = 128, tower_hidden_dims=None, final_embedding_dim: int = 128,
+                                dropout_rate: float = 0.2, temperature: float = 1.0, loss_type: str = "cross_entropy",
+                                device="cuda:0", label_smoothing: float = 0.0, vocab_sizes=None,
+                                optimizer_mode: str = "dense_exact", value_layout: str = "sample_major") -> TwoTowerTrainTask:
+    model = create_two_tower_model(notice_categorical_keys, company_categorical_keys, metadata_path, categorical_embedding_dim,
+                                   notice_dense_input_dim, company_dense_input_dim, tower_hidden_dims, final_embedding_dim,
+                                   dropout_rate, device, vocab_sizes, optimizer_mode, value_layout)
+    return TwoTowerTrainTask(model, temperature=temperature, loss_type=loss_type, label_smoothing=label_smoothing)

@@ -1,0 +1,486 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Integer stages (decode/clamp, arena rows, sort-dedup, segment bounds) are compared bit-exactly;
+floating point within 1e-5 relative in fp32 (BASELINE.json north_star), tolerance written at each assert.
+Nothing here reads /root/reference: the checker is oracle/ + tests/golden/.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_port, two_tower_oracle as orc
+from tests.helpers import TINY_CASES, batch_inputs, load_golden, readme_schema, rel_err, sd_from
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_RTOL = 1e-5
+
+
+def make_task(cfg, schema, dropout=0.0, optimizer_mode="dense_exact", value_layout="sample_major"):
+    import jodalrob_twotower_b200 as tt
+    nk = [k for k, _ in schema["notice"]]
+    ck = [k for k, _ in schema["company"]]
+    vs = {"notice": dict(schema["notice"]), "company": dict(schema["company"])}
+    return tt.create_two_tower_train_task(
+        nk, ck, categorical_embedding_dim=cfg["emb_dim"], notice_dense_input_dim=cfg["notice_dense"],
+        company_dense_input_dim=cfg["company_dense"], tower_hidden_dims=cfg["hidden"], final_embedding_dim=cfg["final_dim"],
+        dropout_rate=dropout, temperature=cfg["temperature"], device=DEV, label_smoothing=cfg.get("label_smoothing", 0.0),
+        vocab_sizes=vs, optimizer_mode=optimizer_mode, value_layout=value_layout)
+
+
+def make_batch(schema, nid, cid, nd, cd, layout="sample_major", device=DEV):
+    import jodalrob_twotower_b200 as tt
+    nk = [k for k, _ in schema["notice"]]
+    ck = [k for k, _ in schema["company"]]
+    flat = (lambda x: x.reshape(-1)) if layout == "sample_major" else (lambda x: x.t().reshape(-1))
+    mk = lambda keys, ids: tt.KeyedJaggedTensor.from_lengths_sync(keys, flat(ids).contiguous().to(device),
+                                                                  torch.ones(ids.numel(), dtype=torch.int64), layout=layout)
+    return {"notice": {"dense": nd.to(device), "kjt": mk(nk, nid)}, "company": {"dense": cd.to(device), "kjt": mk(ck, cid)}}
+
+
+def test_library_loaded_and_device_is_blackwell():
+    import jodalrob_twotower_b200 as tt
+    lib = tt.native.lib()
+    assert lib.cdll.tt_version() == 1
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    assert lib.cdll.tt_device_sm_count() == torch.cuda.get_device_properties(0).multi_processor_count
+
+
+# ------------------------------------------------------------------------------- EBC forward
+@pytest.mark.parametrize("case", ["oob_temp", "deep_ls"])
+@pytest.mark.parametrize("layout", ["sample_major", "key_major"])
+def test_ebc_forward_bit_exact(case, layout):
+    from jodalrob_twotower_b200 import ops
+    d, cfg = load_golden(f"tiny_{case}.npz")
+    task = make_task(cfg, cfg["schema"])
+    task.load_state_dict(sd_from(d, "init."))
+    eng = task.engine
+    for tower, tname in ((0, "notice"), (1, "company")):
+        ids = torch.from_numpy(d[f"in0.{tname}_ids"]).long()
+        vocab = [v for _, v in cfg["schema"][tname]]
+        values = (ids.reshape(-1) if layout == "sample_major" else ids.t().reshape(-1)).contiguous().to(DEV)
+        out, rows, _ = ops.ebc_forward(eng, tower, values, ids.shape[0], layout=layout, want_rows=True)
+        clamped = orc.decode_clamp(values.cpu().numpy(), vocab, layout)
+        assert np.array_equal(clamped, orc.decode_clamp(ids.reshape(-1).numpy(), vocab))  # layouts agree
+        base = eng.row_base_host[0 if tower == 0 else eng.K[0]:][:len(vocab)]
+        exp_rows = orc.arena_rows(clamped, base)
+        assert np.array_equal(rows.cpu().numpy().reshape(ids.shape), exp_rows)  # bit-exact routing
+        p = orc.tower_params(sd_from(d, "init."), tname, [k for k, _ in cfg["schema"][tname]])
+        exp = torch.cat([p["emb"][k][torch.from_numpy(clamped[:, k])] for k in range(len(vocab))], 1)
+        assert torch.equal(out.cpu(), exp)  # a gather is a copy: 0 ulp
+
+
+def test_ebc_forward_readme_schema_large_batch_and_bf16():
+    from jodalrob_twotower_b200 import ops
+    schema = readme_schema()
+    cfg = dict(emb_dim=32, notice_dense=256, company_dense=128, hidden=[128, 64], final_dim=64, temperature=1.0)
+    task = make_task(cfg, schema)
+    eng = task.engine
+    g = torch.Generator().manual_seed(5)
+    B = 4096
+    vocab = [v for _, v in schema["notice"]]
+    ids = torch.stack([torch.randint(-2, v + 3, (B,), generator=g) for v in vocab], 1)
+    out, rows, _ = ops.ebc_forward(eng, 0, ids.reshape(-1).to(DEV), B, want_rows=True)
+    clamped = orc.decode_clamp(ids.reshape(-1).numpy(), vocab)
+    exp_rows = orc.arena_rows(clamped, eng.row_base_host[:len(vocab)])
+    assert np.array_equal(rows.cpu().numpy().reshape(B, -1), exp_rows)
+    exp = eng.arena[torch.from_numpy(exp_rows).long().to(DEV)].reshape(B, -1)
+    assert torch.equal(out, exp)
+    out16 = ops.ebc_forward(eng, 0, ids.reshape(-1).to(DEV), B, out_dtype=torch.bfloat16)
+    assert torch.equal(out16, exp.to(torch.bfloat16))  # round-to-nearest-even like torch
+
+
+def test_ebc_forward_jagged_bags_sum_pooling():
+    """L>1 generalisation (BASELINE config 5); oracle = torch embedding_bag(mode='sum')."""
+    from jodalrob_twotower_b200 import ops
+    d, cfg = load_golden("tiny_base.npz")
+    task = make_task(cfg, cfg["schema"])
+    eng = task.engine
+    vocab = [v for _, v in cfg["schema"]["notice"]]
+    K, B = len(vocab), 37
+    g = torch.Generator().manual_seed(3)
+    lengths = torch.randint(0, 6, (B, K), generator=g)  # sample-major bags, some empty
+    offsets = torch.zeros(B * K + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(lengths.reshape(-1), 0)
+    vals = torch.cat([torch.randint(0, vocab[k], (int(lengths[b, k]),), generator=g) for b in range(B) for k in range(K)])
+    out = ops.ebc_forward(eng, 0, vals.to(DEV), B, bag_offsets=offsets.to(DEV))
+    exp = torch.zeros(B, K * cfg["emb_dim"])
+    E = cfg["emb_dim"]
+    for b in range(B):
+        for k in range(K):
+            lo, hi = int(offsets[b * K + k]), int(offsets[b * K + k + 1])
+            tab = eng.arena[eng.row_base_host[k]:eng.row_base_host[k] + vocab[k]].cpu()
+            exp[b, k * E:(k + 1) * E] = torch.nn.functional.embedding_bag(
+                vals[lo:hi], tab, torch.tensor([0]), mode="sum") if hi > lo else 0
+    assert rel_err(out.cpu(), exp) < 1e-6
+    # L == 1 everywhere reduces to the reference's case bit-for-bit
+    ids = torch.stack([torch.randint(0, v, (B,), generator=g) for v in vocab], 1)
+    one = ops.ebc_forward(eng, 0, ids.reshape(-1).to(DEV), B, bag_offsets=torch.arange(B * K + 1, dtype=torch.int64, device=DEV))
+    assert torch.equal(one, ops.ebc_forward(eng, 0, ids.reshape(-1).to(DEV), B))
+
+
+# ------------------------------------------------------------------------------- sort / dedup
+@pytest.mark.parametrize("n,total_rows", [(1, 1), (5, 3), (2048, 70), (2049, 64141), (100003, 64141), (50000, 300000), (7000, 20_000_000)])
+def test_sort_dedup_bit_exact(n, total_rows):
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200.native import ptr
+    lib = tt.native.lib()
+    rng = np.random.default_rng(n)
+    # skewed like the real schema: many hits on a few rows plus a uniform tail
+    rows = np.where(rng.random(n) < 0.6, rng.integers(0, min(total_rows, 13), n), rng.integers(0, total_rows, n)).astype(np.int32)
+    d_rows = torch.from_numpy(rows).to(DEV)
+    srt, ssl = torch.empty_like(d_rows), torch.empty_like(d_rows)
+    rb = torch.full((total_rows,), -7, dtype=torch.int32, device=DEV)
+    re_ = torch.full((total_rows,), -7, dtype=torch.int32, device=DEV)
+    st = torch.zeros(total_rows, dtype=torch.int32, device=DEV)
+    ws = torch.empty(lib.query("tt_ebc_sort_workspace_bytes", n, total_rows), dtype=torch.uint8, device=DEV)
+    stamp = torch.tensor([41], dtype=torch.int64, device=DEV)
+    lib.call("tt_ebc_sort_rows", ptr(d_rows), 0, n, total_rows, ptr(ws), ws.numel(), ptr(srt), ptr(ssl), ptr(rb), ptr(re_),
+             ptr(st), 1, ptr(stamp), torch.cuda.current_stream().cuda_stream)
+    exp = orc.sort_dedup(rows)
+    assert np.array_equal(srt.cpu().numpy(), exp["sorted_rows"])
+    assert np.array_equal(ssl.cpu().numpy(), exp["positions"])  # stable: ties keep slot order
+    u = exp["unique_rows"].astype(np.int64)
+    assert np.array_equal(rb.cpu().numpy()[u], exp["seg_starts"][:-1])
+    assert np.array_equal(re_.cpu().numpy()[u], exp["seg_starts"][1:])
+    stc = st.cpu().numpy()
+    assert (stc[u] == 42).all() and (np.delete(stc, u) == 0).all()
+
+
+# ------------------------------------------------------------------------------- whole step vs golden
+@pytest.mark.parametrize("case", TINY_CASES)
+def test_autograd_mode_matches_reference_golden(case):
+    """façade mode (i): our kernels under loss.backward() + stock torch.optim.Adam + LambdaLR, exactly the
+    loop of scripts/train.py:319-330, against the reference's own trajectory."""
+    d, cfg = load_golden(f"tiny_{case}.npz")
+    task = make_task(cfg, cfg["schema"])
+    missing = task.load_state_dict(sd_from(d, "init."))
+    assert not missing.missing_keys and not missing.unexpected_keys  # state_dict key compatibility
+    assert sum(p.numel() for p in task.parameters()) == cfg["n_params"]
+    opt = torch.optim.Adam(task.parameters(), lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+    w = cfg["warmup_steps"]
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: s / w if s < w else 1.0, last_epoch=-1)
+    task.train()
+    for i in range(3):
+        nid, cid, nd, cd = batch_inputs(d, i)
+        opt.zero_grad()
+        out = task(make_batch(cfg["schema"], nid, cid, nd, cd), return_metrics=True)
+        out["loss"].backward()
+        assert abs(out["loss"].item() - float(d[f"s{i}.loss"])) <= FP32_RTOL * abs(float(d[f"s{i}.loss"])) + 1e-6
+        for m in ("accuracy", "positive_similarity_mean", "negative_similarity_mean", "similarity_gap"):
+            assert abs(out[m].item() - float(d[f"s{i}.{m}"])) < 2e-6, m
+        assert rel_err(out["similarity_matrix"].cpu(), torch.from_numpy(d[f"s{i}.similarity_matrix"])) < FP32_RTOL
+        if i == 0:
+            for name, p in task.named_parameters():
+                assert rel_err(p.grad.cpu(), torch.from_numpy(d[f"grad0.{name}"])) < 2e-5, name
+        opt.step()
+        sched.step()
+    fin = sd_from(d, "final.")
+    for k, v in task.state_dict().items():
+        if v.is_floating_point():
+            assert rel_err(v.cpu(), fin[k]) < FP32_RTOL, k
+        else:
+            assert torch.equal(v.cpu(), fin[k]), k
+
+
+@pytest.mark.parametrize("case", TINY_CASES)
+def test_fused_step_matches_reference_golden(case):
+    """façade mode (ii): backward + sort-dedup + fused exact-dense Adam + on-device warm-up inside the library."""
+    import jodalrob_twotower_b200 as tt
+    d, cfg = load_golden(f"tiny_{case}.npz")
+    task = make_task(cfg, cfg["schema"])
+    task.load_state_dict(sd_from(d, "init."))
+    opt = tt.FusedAdam(task, lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+    sched = tt.FusedWarmupScheduler(opt, cfg["warmup_steps"])
+    task.train()
+    for i in range(3):
+        nid, cid, nd, cd = batch_inputs(d, i)
+        opt.zero_grad()
+        out = task(make_batch(cfg["schema"], nid, cid, nd, cd), return_metrics=True)
+        out["loss"].backward()
+        opt.step()
+        sched.step()
+        assert abs(out["loss"].item() - float(d[f"s{i}.loss"])) <= FP32_RTOL * abs(float(d[f"s{i}.loss"])) + 1e-6
+        assert abs(sched.get_last_lr()[0] - float(d[f"s{i}.lr"])) < 1e-12 + 1e-6 * float(d[f"s{i}.lr"])
+    fin = sd_from(d, "final.")
+    for k, v in task.state_dict().items():
+        if v.is_floating_point():
+            assert rel_err(v.cpu(), fin[k]) < FP32_RTOL, k
+        else:
+            assert torch.equal(v.cpu(), fin[k]), k
+    # Adam moments of every parameter, including rows no batch ever touched (dense semantics)
+    eng = task.engine
+    for (kind, ref), (name, _p) in zip(task._param_src, task.named_parameters()):
+        m = eng.arena_m[ref[0]:ref[1]] if kind == "table" else eng.dense(ref, "m")
+        v = eng.arena_v[ref[0]:ref[1]] if kind == "table" else eng.dense(ref, "v")
+        assert rel_err(m.cpu(), torch.from_numpy(d[f"adam_m.{name}"])) < 2e-5, name
+        assert rel_err(v.cpu(), torch.from_numpy(d[f"adam_v.{name}"])) < 2e-5, name
+
+
+def test_key_major_layout_gives_same_step():
+    d, cfg = load_golden("tiny_oob_temp.npz")
+    outs = []
+    for layout in ("sample_major", "key_major"):
+        task = make_task(cfg, cfg["schema"])
+        task.load_state_dict(sd_from(d, "init."))
+        nid, cid, nd, cd = batch_inputs(d, 0)
+        task.train()
+        out = task(make_batch(cfg["schema"], nid, cid, nd, cd, layout=layout), return_metrics=True)
+        out["loss"].backward()
+        outs.append((out["loss"].item(), [p.grad.clone() for p in task.parameters()]))
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+
+
+def test_readme_default_b256_trajectory_vs_golden():
+    import jodalrob_twotower_b200 as tt
+    d, cfg = load_golden("readme_default_b256.npz")
+    schema = readme_schema()
+    torch.manual_seed(cfg["seed"])
+    task = make_task(cfg, schema)  # same RNG consumption order as the reference constructors
+    assert sum(p.numel() for p in task.parameters()) == 2204832
+    port = ref_port.build_port_task(schema, seed=cfg["seed"])
+    for (k, v), (k2, v2) in zip(task.state_dict().items(), port.state_dict().items()):
+        assert k == k2 and torch.equal(v.cpu(), v2), k  # seeded init reproduces the reference init
+    opt = tt.FusedAdam(task, lr=cfg["lr"], weight_decay=cfg["weight_decay"], warmup_steps=cfg["warmup_steps"])
+    gen = torch.Generator().manual_seed(cfg["input_seed"])
+    task.train()
+    for i in range(3):
+        nid = torch.stack([torch.randint(0, v, (256,), generator=gen) for _, v in schema["notice"]], 1)
+        cid = torch.stack([torch.randint(0, v, (256,), generator=gen) for _, v in schema["company"]], 1)
+        nd, cd = torch.randn(256, 256, generator=gen), torch.randn(256, 128, generator=gen)
+        assert np.array_equal(nid.numpy(), d[f"in{i}.notice_ids"])
+        out = task(make_batch(schema, nid, cid, nd, cd), return_metrics=True)
+        out["loss"].backward()
+        assert abs(out["loss"].item() - float(d[f"s{i}.loss"])) <= FP32_RTOL * float(d[f"s{i}.loss"])
+        if i == 0:
+            n, c = task.engine.workspace(256).e
+            assert rel_err(n.cpu(), torch.from_numpy(d["s0.notice_emb"])) < FP32_RTOL
+            assert rel_err(c.cpu(), torch.from_numpy(d["s0.company_emb"])) < FP32_RTOL
+            assert torch.allclose(n.norm(dim=1), torch.ones(256, device=DEV), atol=1e-4)  # two_tower_model.py:84-87
+    sd = task.state_dict()
+    for k, v in sd.items():
+        if "embeddings" in k:
+            idx = torch.from_numpy(d[f"final_rows_idx.{k}"]).long()
+            assert rel_err(v[idx.to(DEV)].cpu(), torch.from_numpy(d[f"final_rows.{k}"])) < FP32_RTOL, k
+            assert abs(v.double().sum().item() - float(d[f"final_sum.{k}"])) < 1e-6 * v.abs().double().sum().item()
+        elif v.is_floating_point():
+            assert rel_err(v.cpu(), torch.from_numpy(np.array(d[f"final.{k}"]))) < FP32_RTOL, k
+        else:
+            assert torch.equal(v.cpu(), torch.from_numpy(np.array(d[f"final.{k}"]))), k
+
+
+@pytest.mark.parametrize("B", [1000, 4096])
+def test_large_batch_step_vs_port(B):
+    """README-default model at bench-like batch sizes against the torch-CPU port (same seeded init, same inputs):
+    loss/metrics, every gradient (dense table grads included) and the weights after 2 exact-dense Adam steps."""
+    import jodalrob_twotower_b200 as tt
+    schema = readme_schema()
+    cfg = dict(emb_dim=32, notice_dense=256, company_dense=128, hidden=[128, 64], final_dim=64, temperature=1.0)
+    torch.manual_seed(11)
+    task = make_task(cfg, schema)
+    port = ref_port.build_port_task(schema, seed=11)
+    g = torch.Generator().manual_seed(99)
+    # skewed ids (24 of 32 notice vocabularies are <= 25 rows anyway) with out-of-range values
+    mk = lambda vocab: torch.stack([torch.randint(-1, v + 2, (B,), generator=g) for _, v in vocab], 1)
+    task.train()
+    port.train()
+    tr = ref_port.PortTrainer(port, 1e-3, 1e-5, 0)
+    opt = tt.FusedAdam(task, lr=1e-3, weight_decay=1e-5, warmup_steps=0)
+    for step in range(2):
+        nid, cid = mk(schema["notice"]), mk(schema["company"])
+        nd, cd = torch.randn(B, 256, generator=g), torch.randn(B, 128, generator=g)
+        if step == 0:  # gradients, via the autograd-compatible mode on a twin
+            twin = make_task(cfg, schema)
+            twin.load_state_dict(task.state_dict())
+            twin.train()
+            o = twin(make_batch(schema, nid, cid, nd, cd), return_metrics=True)
+            o["loss"].backward()
+            import copy
+            port2 = copy.deepcopy(port)  # keeps the BN running stats of `port` untouched
+            po = port2(ref_port.make_port_batch(schema, nid, cid, nd, cd), return_metrics=True)
+            po["loss"].backward()
+            assert abs(o["loss"].item() - po["loss"].item()) < FP32_RTOL * po["loss"].item()
+            for (n1, p1), (n2, p2) in zip(twin.named_parameters(), port2.named_parameters()):
+                assert rel_err(p1.grad.cpu(), p2.grad) < 3e-5, n1
+        ref = tr.step(ref_port.make_port_batch(schema, nid, cid, nd, cd))
+        out = task(make_batch(schema, nid, cid, nd, cd), return_metrics=True)
+        out["loss"].backward()
+        assert abs(out["loss"].item() - ref["loss"].item()) < FP32_RTOL * ref["loss"].item()
+        assert abs(out["accuracy"].item() - ref["accuracy"].item()) <= 2.0 / B
+        assert abs(out["similarity_gap"].item() - ref["similarity_gap"].item()) < 1e-5
+    for (k, v), (k2, v2) in zip(task.state_dict().items(), port.state_dict().items()):
+        if v.is_floating_point():
+            assert rel_err(v.cpu(), v2) < FP32_RTOL, k
+
+
+def test_step_is_bitwise_deterministic():
+    d, cfg = load_golden("readme_default_b256.npz")
+    schema = readme_schema()
+    finals = []
+    for _ in range(2):
+        torch.manual_seed(3)
+        task = make_task(cfg, schema)
+        import jodalrob_twotower_b200 as tt
+        tt.FusedAdam(task, lr=1e-3, weight_decay=1e-5)
+        g = torch.Generator().manual_seed(8)
+        B = 2048
+        task.train()
+        for _s in range(2):
+            nid = torch.stack([torch.randint(0, v, (B,), generator=g) for _, v in schema["notice"]], 1)
+            cid = torch.stack([torch.randint(0, v, (B,), generator=g) for _, v in schema["company"]], 1)
+            out = task.fused_step(make_batch(schema, nid, cid, torch.randn(B, 256, generator=g), torch.randn(B, 128, generator=g)))
+        finals.append((out.clone(), task.engine.arena.clone(), task.engine.dense_w.clone()))
+    for a, b in zip(finals[0], finals[1]):
+        assert torch.equal(a, b)  # fixed summation order everywhere: run-to-run bitwise identical
+
+
+def test_sparse_mode_only_touches_batch_rows():
+    d, cfg = load_golden("tiny_base.npz")
+    import jodalrob_twotower_b200 as tt
+    task = make_task(cfg, cfg["schema"], optimizer_mode="sparse")
+    task.load_state_dict(sd_from(d, "init."))
+    tt.FusedAdam(task, lr=1e-3, weight_decay=1e-5)
+    before = task.engine.arena.clone()
+    nid, cid, nd, cd = batch_inputs(d, 0)
+    task.train()
+    task.fused_step(make_batch(cfg["schema"], nid, cid, nd, cd))
+    eng = task.engine
+    rows = np.concatenate([
+        orc.arena_rows(orc.decode_clamp(nid.reshape(-1).numpy(), [v for _, v in cfg["schema"]["notice"]]), eng.row_base_host[:eng.K[0]]).reshape(-1),
+        orc.arena_rows(orc.decode_clamp(cid.reshape(-1).numpy(), [v for _, v in cfg["schema"]["company"]]), eng.row_base_host[eng.K[0]:]).reshape(-1)])
+    touched = torch.zeros(eng.total_rows, dtype=torch.bool)
+    touched[torch.from_numpy(np.unique(rows)).long()] = True
+    changed = (eng.arena != before).any(dim=1).cpu()
+    assert torch.equal(changed, touched)
+    # touched rows follow the same Adam rule as the dense oracle (first step: no history to differ on)
+    st = orc.OracleStepper(sd_from(d, "init."), cfg["schema"], cfg["temperature"], 0.0, 1e-3, 1e-5, 0)
+    st.step(nid.reshape(-1).numpy(), cid.reshape(-1).numpy(), nd, cd)
+    exp = torch.cat(st.P["notice"]["emb"] + st.P["company"]["emb"], 0)
+    assert rel_err(eng.arena.cpu()[touched], exp[touched]) < FP32_RTOL
+
+
+def test_dropout_keep_rate_scaling_and_backward_mask():
+    d, cfg = load_golden("tiny_base.npz")
+    cfg = dict(cfg, hidden=[16, 64])
+    schema = cfg["schema"]
+    p = 0.3
+    task = make_task(cfg, schema, dropout=p)
+    g = torch.Generator().manual_seed(0)
+    B = 4096
+    nid = torch.stack([torch.randint(0, v, (B,), generator=g) for _, v in schema["notice"]], 1)
+    cid = torch.stack([torch.randint(0, v, (B,), generator=g) for _, v in schema["company"]], 1)
+    nd, cd = torch.randn(B, 12, generator=g), torch.randn(B, 6, generator=g)
+    task.train()
+    out = task(make_batch(schema, nid, cid, nd, cd))
+    ws = task.engine.workspace(B)
+    y, h = ws.y[0][0], ws.h[0][0]
+    bn = (h - ws.mean[0][0]) * ws.rstd[0][0] * task.engine.dense("notice_tower.mlp.2.weight") + task.engine.dense("notice_tower.mlp.2.bias")
+    kept = y != 0
+    assert abs(kept.float().mean().item() - (1 - p)) < 0.01  # keep-rate
+    assert rel_err(y[kept], (bn / (1 - p))[kept]) < 1e-5  # 1/(1-p) scaling
+    out.backward()
+    # a second forward in the same step would redraw; the mask used by backward is the forward's (same Philox counter)
+    dh = ws.dh[0][0]
+    assert (dh[~kept & (h > 0)] != 0).float().mean().item() > 0.5  # BN couples columns, grads still flow
+    # explicit mask-in path: oracle-supplied mask gives oracle-equal output
+    mask = (torch.rand(B, 64, generator=g) > p).to(torch.uint8).to(DEV)
+    task2 = make_task(cfg, schema, dropout=p)
+    task2.load_state_dict(task.state_dict())
+    task2.train()
+    l2 = task2(make_batch(schema, nid, cid, nd, cd), dropout_masks=[[mask], [mask]])
+    ws2 = task2.engine.workspace(B)
+    bn2 = (ws2.h[0][0] - ws2.mean[0][0]) * ws2.rstd[0][0] * task2.engine.dense("notice_tower.mlp.2.weight") + task2.engine.dense("notice_tower.mlp.2.bias")
+    assert rel_err(ws2.y[0][0], bn2 * mask.float() / (1 - p)) < 1e-5
+
+
+def test_eval_mode_uses_running_stats_and_predict_batch():
+    d, cfg = load_golden("tiny_base.npz")
+    task = make_task(cfg, cfg["schema"])
+    sd = sd_from(d, "final.")
+    task.load_state_dict(sd)
+    port = ref_port.build_port_task(cfg["schema"], cfg["emb_dim"], cfg["notice_dense"], cfg["company_dense"], cfg["hidden"],
+                                    cfg["final_dim"], 0.0, cfg["temperature"], seed=0)
+    port.load_state_dict(sd)
+    nid, cid, nd, cd = batch_inputs(d, 1)
+    task.eval()
+    port.eval()
+    with torch.no_grad():
+        out = task(make_batch(cfg["schema"], nid, cid, nd, cd), return_metrics=True)
+        ref = port(ref_port.make_port_batch(cfg["schema"], nid, cid, nd, cd), return_metrics=True)
+    assert abs(out["loss"].item() - ref["loss"].item()) < FP32_RTOL * ref["loss"].item()
+    assert rel_err(out["similarity_matrix"].cpu(), ref["similarity_matrix"]) < FP32_RTOL
+    pb = task.predict_batch(make_batch(cfg["schema"], nid, cid, nd, cd), top_k=5)
+    top = torch.topk(ref["similarity_matrix"], k=5, dim=1)
+    assert pb["top_indices"].shape == (nid.shape[0], 5)
+    assert rel_err(pb["top_similarities"].cpu(), top.values) < FP32_RTOL
+    n_emb = task.two_tower_model.get_notice_embeddings(make_batch(cfg["schema"], nid, cid, nd, cd)["notice"])
+    assert n_emb.shape == (nid.shape[0], cfg["final_dim"])
+
+
+def test_error_behaviour_matches_reference_contract():
+    import jodalrob_twotower_b200 as tt
+    d, cfg = load_golden("tiny_base.npz")
+    task = make_task(cfg, cfg["schema"])
+    nid, cid, nd, cd = batch_inputs(d, 0)
+    bad = make_batch(cfg["schema"], nid, cid[:-1], nd, cd[:-1])
+    with pytest.raises(ValueError):  # two_tower_train_task.py:64-67
+        task(bad)
+    with pytest.raises(ValueError):  # two_tower_train_task.py:37-38
+        tt.TwoTowerTrainTask(task.two_tower_model, loss_type="hinge")
+    short = make_batch(cfg["schema"], nid, cid, nd, cd)
+    short["notice"]["kjt"] = tt.KeyedJaggedTensor(short["notice"]["kjt"].keys(), short["notice"]["kjt"].values()[:-3])
+    with pytest.raises(ValueError):  # no silent zero-vector fallback (cat_embed.py:180-190 is NOT replicated)
+        task(short)
+    lib = tt.native.lib()
+    with pytest.raises(tt.native.TwoTowerNativeError):
+        lib.call("tt_dense_adam", 0, 0, 0, 0, 10, 0, 0)
+    assert "NULL" in lib.last_error()
+
+
+# ------------------------------------------------------------------------------- single kernels vs fp64
+@pytest.mark.parametrize("M,N,K", [(1, 8, 6), (37, 16, 12), (300, 64, 1152), (8192, 128, 256), (1000, 70, 50)])
+def test_linear_kernels_vs_fp64(M, N, K):
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200.native import ptr, TT_F32
+    lib = tt.native.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(M + N + K)
+    X, W, b = torch.randn(M, K, generator=g).to(DEV), torch.randn(N, K, generator=g).to(DEV), torch.randn(N, generator=g).to(DEV)
+    dY = torch.randn(M, N, generator=g).to(DEV)
+    Y = torch.empty(M, N, device=DEV)
+    lib.call("tt_linear_forward", ptr(X), K, ptr(W), ptr(b), ptr(Y), N, M, N, K, TT_F32, 1, s)
+    assert rel_err(Y, torch.relu(X.double() @ W.double().t() + b.double())) < 2e-6
+    dX = torch.empty(M, K, device=DEV)
+    lib.call("tt_linear_dgrad", ptr(dY), N, ptr(W), ptr(dX), K, M, N, K, TT_F32, s)
+    assert rel_err(dX, dY.double() @ W.double()) < 2e-6
+    dW, db = torch.empty(N, K, device=DEV), torch.empty(N, device=DEV)
+    ws = torch.empty(lib.query("tt_linear_wgrad_workspace_bytes", M, N, K), dtype=torch.uint8, device=DEV)
+    lib.call("tt_linear_wgrad", ptr(dY), N, ptr(X), K, ptr(dW), ptr(db), M, N, K, TT_F32, ptr(ws), ws.numel(), s)
+    assert rel_err(dW, dY.double().t() @ X.double()) < 2e-6
+    assert rel_err(db, dY.double().sum(0)) < 2e-6
+
+
+@pytest.mark.parametrize("B,F,T,ls", [(24, 8, 1.0, 0.0), (200, 64, 0.5, 0.1), (1025, 128, 0.05, 0.0), (4096, 64, 1.0, 0.0)])
+def test_simce_kernels_vs_oracle(B, F, T, ls):
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200.engine import TwoTowerConfig, TwoTowerEngine
+    cfg = TwoTowerConfig(["a"], ["b"], [4], [4], 4, 4, 4, [4], F, 0.0, T, ls)
+    eng = TwoTowerEngine(cfg, DEV)
+    g = torch.Generator().manual_seed(B)
+    n = torch.nn.functional.normalize(torch.randn(B, F, generator=g), dim=1)
+    c = torch.nn.functional.normalize(torch.randn(B, F, generator=g) + 0.5 * n, dim=1)
+    ws = eng.workspace(B)
+    ws.e[0].copy_(n)
+    ws.e[1].copy_(c)
+    out5 = eng.loss_forward(ws).cpu()
+    eng.loss_backward(ws, 1.0)
+    loss, met, cache = orc.simce_forward(n.double(), c.double(), T, ls)
+    dn, dc = orc.simce_backward(n.double(), c.double(), cache, T, ls)
+    assert abs(out5[0].item() - loss.item()) < FP32_RTOL * abs(loss.item())
+    assert abs(out5[1].item() - met["accuracy"].item()) <= 1.0 / B
+    assert abs(out5[2].item() - met["positive_similarity_mean"].item()) < 1e-5 / T
+    assert abs(out5[3].item() - met["negative_similarity_mean"].item()) < 1e-5 / T
+    assert rel_err(ws.de[0].cpu(), dn) < 2e-5 and rel_err(ws.de[1].cpu(), dc) < 2e-5
+    assert rel_err(eng.similarity_matrix(ws).cpu(), cache["s"]) < FP32_RTOL
