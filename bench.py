@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Benchmark of the two-tower train step (BASELINE.json metric: train samples/sec, device-timed).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on the host cores
+
+A "step" is one whole train step (hyper advance, both towers forward, sim-CE loss, backward, sort-dedup +
+segment-sum + exact-dense Adam on all embedding rows, Adam on the dense weights) over one synthetic batch of
+the configured schema (tests/golden/schema_readme_default.json: 32 notice + 6 company keys, vocab = count+10),
+README-default model (emb 32, towers [128,64] -> 64), B = 8192 per GPU (BASELINE.json configs[1]).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train_samples_per_sec"
+UNIT = "samples/s"
+MODEL = dict(emb_dim=32, notice_dense=256, company_dense=128, hidden=[128, 64], final_dim=64, dropout=0.1, temperature=1.0,
+             lr=1e-3, weight_decay=1e-5)
+N_ROTATE = 16  # distinct resident input batches cycled through the timed region
+
+
+def load_schema():
+    with open(os.path.join(ROOT, "tests", "golden", "schema_readme_default.json")) as f:
+        s = json.load(f)
+    return {"notice": s["notice"], "company": s["company"]}
+
+
+def synth_batch(schema, B, gen):
+    nid = torch.stack([torch.randint(0, v, (B,), generator=gen) for _, v in schema["notice"]], 1)
+    cid = torch.stack([torch.randint(0, v, (B,), generator=gen) for _, v in schema["company"]], 1)
+    return nid, cid, torch.randn(B, MODEL["notice_dense"], generator=gen), torch.randn(B, MODEL["company_dense"], generator=gen)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def run_reference(args):
+    """The reference's own CPU implementation of the path, as the oracle port (the reference is pure Python and cannot
+    travel to the GPU box; oracle/ref_port.py is pinned bit-exactly to it by tests/golden). 'as-is' = with the reference's
+    per-scalar KJT decode loop (src/towers/cat_embed.py:103-121)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_port
+    schema = load_schema()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    total_steps = args.steps + args.warmup
+    # bounded sample: the as-is reference runs ~1.5 k samples/s; keep the whole run near two minutes
+    B = args.batch
+    budget_samples = 150_000
+    while B > 256 and B * total_steps > budget_samples:
+        B //= 2
+    task = ref_port.build_port_task(schema, MODEL["emb_dim"], MODEL["notice_dense"], MODEL["company_dense"], MODEL["hidden"],
+                                    MODEL["final_dim"], MODEL["dropout"], MODEL["temperature"], seed=0, decode="loop")
+    tr = ref_port.PortTrainer(task, MODEL["lr"], MODEL["weight_decay"], 0)
+    gen = torch.Generator().manual_seed(1234)
+    batches = [ref_port.make_port_batch(schema, *synth_batch(schema, B, gen)) for _ in range(min(4, total_steps))]
+    for i in range(args.warmup):
+        tr.step(batches[i % len(batches)])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = tr.step(batches[i % len(batches)])
+        float(out["loss"])
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    sample = f"{args.steps} steps of B={B} (bounded sample of the B={args.batch} workload), decode=as-is python loop, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"README-default two-tower train step, B={B} sample, fp32, CPU", "batch": B},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(schema, B, budget_s=25.0):
+    """Oracle port timed on the host cores, bounded sample of the same workload (reported baseline, not the target)."""
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    out = {}
+    for decode in ("loop", "vectorized"):
+        task = ref_port.build_port_task(schema, MODEL["emb_dim"], MODEL["notice_dense"], MODEL["company_dense"], MODEL["hidden"],
+                                        MODEL["final_dim"], MODEL["dropout"], MODEL["temperature"], seed=0, decode=decode)
+        tr = ref_port.PortTrainer(task, MODEL["lr"], MODEL["weight_decay"], 0)
+        gen = torch.Generator().manual_seed(1234)
+        batch = ref_port.make_port_batch(schema, *synth_batch(schema, B, gen))
+        t0 = time.perf_counter()
+        tr.step(batch)  # warm-up
+        warm = time.perf_counter() - t0
+        n = max(1, min(10, int((budget_s / 2) / max(warm, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            float(tr.step(batch)["loss"])
+        dt = time.perf_counter() - t0
+        out[decode] = (B * n / dt, n)
+    return {"value": out["loop"][0], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{out['loop'][1]} timed steps of B={B} after 1 warm-up, reference as-is (python KJT decode loop), {cores} torch threads",
+            "vectorized_decode_value": out["vectorized"][0]}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def algorithmic(tag: str, B: int, schema) -> dict:
+    """Algorithmic bytes / flops of one C-ABI call."""
+    E, F, H0, H1 = MODEL["emb_dim"], MODEL["final_dim"], MODEL["hidden"][0], MODEL["hidden"][1]
+    Kn, Kc = len(schema["notice"]), len(schema["company"])
+    rows = sum(v for _, v in schema["notice"]) + sum(v for _, v in schema["company"])
+    K = Kn if "notice" in tag else Kc
+    D = MODEL["notice_dense"] if "notice" in tag else MODEL["company_dense"]
+    if tag.startswith("tt_ebc_forward"):
+        return {"bytes": B * K * (E * 4 + 8) + B * K * E * 4}
+    if tag.startswith("tt_ebc_backward_adam"):
+        return {"bytes": B * (Kn + Kc) * (E * 4 + 4) + rows * E * 24}
+    if tag.startswith("tt_ebc_sort_rows"):
+        return {"bytes": B * (Kn + Kc) * 4 * 2 * 3}
+    if tag.startswith("tt_dense_adam"):
+        return {"bytes": 152320 * 28}
+    if tag.startswith("tt_simce_forward"):
+        return {"flops": 2 * B * B * F}
+    if tag.startswith("tt_simce_backward"):
+        return {"flops": 2 * B * B * F}
+    return {}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} must be launched under torchrun with {args.gpus} ranks")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import jodalrob_twotower_b200 as tt
+
+    schema = load_schema()
+    nk, ck = [k for k, _ in schema["notice"]], [k for k, _ in schema["company"]]
+    B = args.batch
+    torch.manual_seed(0)
+    if world > 1:
+        from jodalrob_twotower_b200 import dist as ttdist
+        task = ttdist.create_distributed_train_task(nk, ck, schema, MODEL, dev)
+    else:
+        task = tt.create_two_tower_train_task(
+            nk, ck, categorical_embedding_dim=MODEL["emb_dim"], notice_dense_input_dim=MODEL["notice_dense"],
+            company_dense_input_dim=MODEL["company_dense"], tower_hidden_dims=MODEL["hidden"], final_embedding_dim=MODEL["final_dim"],
+            dropout_rate=MODEL["dropout"], temperature=MODEL["temperature"], device=dev,
+            vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])})
+    tt.FusedAdam(task, lr=MODEL["lr"], weight_decay=MODEL["weight_decay"], warmup_steps=0)
+    task.train()
+    eng = task.engine
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host = [synth_batch(schema, B, gen) for _ in range(N_ROTATE)]
+    pinned = [tuple(t.pin_memory() for t in (nid.reshape(-1), cid.reshape(-1), nd, cd)) for nid, cid, nd, cd in host]
+    resident = [tuple(t.to(dev) for t in p) for p in pinned]
+    in_bytes = sum(t.numel() * t.element_size() for t in pinned[0])
+
+    def step_resident(i):
+        nv, cv, nd, cd = resident[i % N_ROTATE]
+        return eng.fused_step(nd, nv, cd, cv, MODEL["lr"], 0, (0.9, 0.999), 1e-8, MODEL["weight_decay"])
+
+    # ---- CUDA graph of the whole step over static input buffers (launch-bound at this size) ----
+    static = tuple(torch.empty_like(t) for t in resident[0])
+    use_graph = not args.no_graph
+    graph = None
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for t, s in zip(resident[0], static):
+            s.copy_(t)
+        for _ in range(2):
+            eng.fused_step(static[2], static[0], static[3], static[1], MODEL["lr"], 0, (0.9, 0.999), 1e-8, MODEL["weight_decay"])
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    launches_per_step = 0
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        l0 = eng.launches
+        with torch.cuda.graph(graph):
+            out_static = eng.fused_step(static[2], static[0], static[3], static[1], MODEL["lr"], 0, (0.9, 0.999), 1e-8,
+                                        MODEL["weight_decay"])
+        launches_per_step = eng.launches - l0
+    else:
+        l0 = eng.launches
+        out_static = step_resident(0)
+        launches_per_step = eng.launches - l0
+
+    def run_step(i):
+        if graph is not None:
+            for t, s in zip(resident[i % N_ROTATE], static):
+                s.copy_(t, non_blocking=True)  # device-to-device stage of the next resident batch (inputs already in HBM)
+            graph.replay()
+            return out_static
+        return step_resident(i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        run_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.current_stream(dev)
+    barrier()
+    e0.record(st)
+    for i in range(args.steps):
+        run_step(i)
+    e1.record(st)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    loss_last = float(out_static[0].item())
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the result, every step, through the public API ----
+    copy_stream = torch.cuda.Stream(dev)
+    stage = [tuple(torch.empty_like(t) for t in resident[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    out_host = torch.empty(5, dtype=torch.float32).pin_memory()
+    mk = lambda keys, v: tt.KeyedJaggedTensor(keys, v)
+
+    def e2e_loop(n):
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(copy_stream):
+            for t, s in zip(pinned[0], stage[0]):
+                s.copy_(t, non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n):
+            cur, nxt = i % 2, (i + 1) % 2
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(freed[nxt])
+                    for t, s in zip(pinned[(i + 1) % N_ROTATE], stage[nxt]):
+                        s.copy_(t, non_blocking=True)
+                    ready[nxt].record(copy_stream)
+            main.wait_event(ready[cur])
+            nv, cv, nd, cd = stage[cur]
+            batch = {"notice": {"dense": nd, "kjt": mk(nk, nv)}, "company": {"dense": cd, "kjt": mk(ck, cv)}}
+            res = task.fused_step(batch)
+            freed[cur].record(main)
+            out_host.copy_(res, non_blocking=True)
+            main.synchronize()  # the D2H read of this step's loss/metrics
+        return float(out_host[0])
+
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record(torch.cuda.current_stream(dev))
+    e2e_loop(args.steps)
+    ee1.record(torch.cuda.current_stream(dev))
+    barrier()
+    e2e_ms = torch.tensor([max(ee0.elapsed_time(ee1), (time.perf_counter() - t0) * 1e3 * 0.0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * args.steps / (float(e2e_ms.item()) * 1e-3)
+
+    # ---- per-kernel device times (eager launches bracketed by CUDA events on the launching stream) ----
+    kern = {}
+    if rank == 0 or world > 1:
+        eng.profile = []
+        n_prof = 5
+        for i in range(n_prof):
+            step_resident(i)
+        torch.cuda.synchronize(dev)
+        for tag, nker, a, b in eng.profile:
+            d = kern.setdefault(tag, {"ms": 0.0, "calls": 0, "kernels": nker})
+            d["ms"] += a.elapsed_time(b)
+            d["calls"] += 1
+        eng.profile = None
+        for d in kern.values():
+            d["ms"] = d["ms"] / n_prof
+            d["calls"] = d["calls"] // n_prof
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    table = []
+    for tag, d in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
+        a = algorithmic(tag, B, schema)
+        row = {"call": tag, "ms": round(d["ms"], 5), "kernels": d["kernels"] * max(d["calls"], 1)}
+        per_call = d["ms"] / max(d["calls"], 1) * 1e-3
+        if "bytes" in a:
+            row["GBps"] = round(a["bytes"] / per_call / 1e9, 1)
+            row["frac_hbm"] = round(row["GBps"] / pk["hbm_gbs"], 4)
+        if "flops" in a:
+            row["TFLOPs"] = round(a["flops"] / per_call / 1e12, 2)
+        table.append(row)
+    top = table[0] if table else None
+    roofline = None
+    if top is not None:
+        a = algorithmic(top["call"], B, schema)
+        per_call_s = kern[top["call"]]["ms"] / max(kern[top["call"]]["calls"], 1) * 1e-3
+        if "flops" in a:
+            ach = a["flops"] / per_call_s / 1e12
+            roofline = {"kernel": top["call"], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                        "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + ", burst bf16"}
+        elif "bytes" in a:
+            ach = a["bytes"] / per_call_s / 1e9
+            roofline = {"kernel": top["call"], "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}
+        else:
+            roofline = {"kernel": top["call"], "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None,
+                        "traffic": None, "peak_source": pk["source"]}
+    cpu = cpu_baseline(schema, B) if (world == 1 and not args.no_cpu_baseline) else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"README-default two-tower train step (emb 32, towers [128,64]->64, 38 tables / 64,141 rows), "
+                                   f"B={B} per GPU, in-batch negatives, dropout 0.1, exact dense Adam lr 1e-3 wd 1e-5",
+                       "batch_per_gpu": B, "global_batch": B * world, "optimizer": "dense_exact",
+                       "parallelism": f"dp{world}" + (" row-wise sharded tables" if world > 1 else ""),
+                       "l2_policy": f"inputs rotate over {N_ROTATE} resident batches ({in_bytes * N_ROTATE / 1e6:.0f} MB > 126 MB L2)",
+                       "cuda_graph": bool(use_graph)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 20},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": table, "loss_last": loss_last}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="samples per GPU per step")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

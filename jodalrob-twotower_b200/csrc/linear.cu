@@ -16,29 +16,29 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int64_t str
 // column sums of X[M,N] in two fixed levels: chunk partials (float) then a sequential double sum
 constexpr int CS_ROWS = 256;
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int N, float* __restrict__ part) {
-  __shared__ float s[8][33];
+colsum_partial_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int N, double* __restrict__ part) {
+  __shared__ double s[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
   const int64_t m_lo = (int64_t)blockIdx.y * CS_ROWS;
   const int64_t m_hi = (m_lo + CS_ROWS < M) ? m_lo + CS_ROWS : M;
-  float a = 0.f;
+  double a = 0.0;  // bias gradients cancel heavily; keep the column sums in fp64
   if (n < N)
-    for (int64_t m = m_lo + ty; m < m_hi; m += 8) a += X[m * ld + n];
+    for (int64_t m = m_lo + ty; m < m_hi; m += 8) a += (double)X[m * ld + n];
   s[ty][tx] = a;
   __syncthreads();
   if (ty == 0 && n < N) {
-    float t = 0.f;
+    double t = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += s[k][tx];
     part[(int64_t)blockIdx.y * N + n] = t;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out) {
+__global__ void colsum_final_kernel(const double* __restrict__ part, int chunks, int N, float* __restrict__ out) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   double t = 0.0;
-  for (int c = 0; c < chunks; ++c) t += (double)part[(int64_t)c * N + n];
+  for (int c = 0; c < chunks; ++c) t += part[(int64_t)c * N + n];
   out[n] = (float)t;
 }
 
@@ -97,7 +97,7 @@ static int wgrad_splits(int64_t M, int32_t N, int32_t K) {
 
 int64_t tt_linear_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K) {
   const int64_t chunks = (M + CS_ROWS - 1) / CS_ROWS + 1;
-  return (int64_t)wgrad_splits(M, N, K) * N * K * 4 + chunks * N * 4 + 256;
+  return (int64_t)wgrad_splits(M, N, K) * N * K * 4 + chunks * N * 8 + 256;
 }
 
 int tt_linear_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, float* dW, float* dbias, int64_t M,
@@ -127,7 +127,7 @@ int tt_linear_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, flo
     splitk_reduce_kernel<<<ceil_div((int64_t)N * K, 256), 256, 0, s>>>(part, (int64_t)N * K, eff_splits, dW, (int64_t)N * K);
   }
   if (dbias) {
-    float* cpart = part + (int64_t)splits * N * K;
+    double* cpart = reinterpret_cast<double*>(part + (((int64_t)splits * N * K + 1) & ~(int64_t)1));
     const int chunks = (int)((M + CS_ROWS - 1) / CS_ROWS);
     colsum_partial_kernel<<<dim3(ceil_div(N, 32), chunks), 256, 0, s>>>((const float*)dY, ldy, M, N, cpart);
     colsum_final_kernel<<<ceil_div(N, 128), 128, 0, s>>>(cpart, chunks, N, dbias);

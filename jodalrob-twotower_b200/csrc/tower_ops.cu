@@ -23,26 +23,26 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 bn_partial_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ H, int64_t ldh, int64_t M, int N,
                   const float* __restrict__ mean, const float* __restrict__ rstd, float p, const uint8_t* mask_in,
-                  const tt_adam_hyper* __restrict__ hyp, uint32_t stream, float* __restrict__ part) {
-  __shared__ float s0[8][33], s1[8][33];
+                  const tt_adam_hyper* __restrict__ hyp, uint32_t stream, double* __restrict__ part) {
+  __shared__ double s0[8][33], s1[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
   const int64_t m_lo = (int64_t)blockIdx.y * BN_ROWS;
   const int64_t m_hi = (m_lo + BN_ROWS < M) ? m_lo + BN_ROWS : M;
-  float a = 0.f, b = 0.f;
+  double a = 0.0, b = 0.0;  // fp64 accumulation: sum_b dy cancels heavily and Adam's m/sqrt(v) amplifies the noise
   if (n < N) {
     const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
     const float mu = MODE == 1 ? mean[n] : 0.f, rs = MODE == 1 ? rstd[n] : 0.f;
     for (int64_t m = m_lo + ty; m < m_hi; m += 8) {
       const float x = ldf<T>(X + m * ldx + n);
       if (MODE == 0) {
-        a += x;
-        b += x * x;
+        a += (double)x;
+        b += (double)x * (double)x;
       } else {
         const float dyp = x * keep_scale<T>(mask_in, hyp, stream, m, n, N, p, inv_keep);
         const float xhat = (ldf<T>(H + m * ldh + n) - mu) * rs;
-        a += dyp;
-        b += dyp * xhat;
+        a += (double)dyp;
+        b += (double)dyp * (double)xhat;
       }
     }
   }
@@ -50,7 +50,7 @@ bn_partial_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ H,
   s1[ty][tx] = b;
   __syncthreads();
   if (ty == 0 && n < N) {
-    float t0 = 0.f, t1 = 0.f;
+    double t0 = 0.0, t1 = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       t0 += s0[k][tx];
@@ -61,13 +61,13 @@ bn_partial_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ H,
   }
 }
 
-__global__ void bn_partial_final_kernel(const float* __restrict__ part, int chunks, int N, double* __restrict__ sums) {
+__global__ void bn_partial_final_kernel(const double* __restrict__ part, int chunks, int N, double* __restrict__ sums) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   double t0 = 0.0, t1 = 0.0;
   for (int c = 0; c < chunks; ++c) {
-    t0 += (double)part[((int64_t)c * 2 + 0) * N + n];
-    t1 += (double)part[((int64_t)c * 2 + 1) * N + n];
+    t0 += part[((int64_t)c * 2 + 0) * N + n];
+    t1 += part[((int64_t)c * 2 + 1) * N + n];
   }
   sums[n] = t0;
   sums[N + n] = t1;
@@ -189,7 +189,7 @@ extern "C" {
 
 int64_t tt_bn_workspace_bytes(int64_t M, int32_t N) {
   const int64_t chunks = (M + BN_ROWS - 1) / BN_ROWS + 1;
-  return chunks * 2 * (int64_t)N * 4 + 256;
+  return chunks * 2 * (int64_t)N * 8 + 256;
 }
 
 int tt_bn_stats(const void* h, int64_t ldh, int64_t M, int32_t N, int32_t act_dtype, double* sums, void* workspace,
@@ -202,11 +202,11 @@ int tt_bn_stats(const void* h, int64_t ldh, int64_t M, int32_t N, int32_t act_dt
   dim3 grid(ceil_div(N, 32), chunks);
   if (act_dtype == TT_F32)
     bn_partial_kernel<float, 0><<<grid, 256, 0, s>>>((const float*)h, ldh, nullptr, 0, M, N, nullptr, nullptr, 0.f,
-                                                     nullptr, nullptr, 0, (float*)workspace);
+                                                     nullptr, nullptr, 0, (double*)workspace);
   else
     bn_partial_kernel<__nv_bfloat16, 0><<<grid, 256, 0, s>>>((const __nv_bfloat16*)h, ldh, nullptr, 0, M, N, nullptr,
-                                                             nullptr, 0.f, nullptr, nullptr, 0, (float*)workspace);
-  bn_partial_final_kernel<<<ceil_div(N, 128), 128, 0, s>>>((const float*)workspace, chunks, N, sums);
+                                                             nullptr, 0.f, nullptr, nullptr, 0, (double*)workspace);
+  bn_partial_final_kernel<<<ceil_div(N, 128), 128, 0, s>>>((const double*)workspace, chunks, N, sums);
   TT_LAUNCH_CHECK("bn_stats");
   return TT_OK;
 }
@@ -260,12 +260,12 @@ int tt_bn_backward_reduce(const void* dy, int64_t lddy, const void* h, int64_t l
   dim3 grid(ceil_div(N, 32), chunks);
   if (act_dtype == TT_F32)
     bn_partial_kernel<float, 1><<<grid, 256, 0, s>>>((const float*)dy, lddy, (const float*)h, ldh, M, N, mean, rstd,
-                                                     dropout_p, mask_in, d_hyper, rng_stream, (float*)workspace);
+                                                     dropout_p, mask_in, d_hyper, rng_stream, (double*)workspace);
   else
     bn_partial_kernel<__nv_bfloat16, 1><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)h, ldh,
                                                              M, N, mean, rstd, dropout_p, mask_in, d_hyper, rng_stream,
-                                                             (float*)workspace);
-  bn_partial_final_kernel<<<ceil_div(N, 128), 128, 0, s>>>((const float*)workspace, chunks, N, sums);
+                                                             (double*)workspace);
+  bn_partial_final_kernel<<<ceil_div(N, 128), 128, 0, s>>>((const double*)workspace, chunks, N, sums);
   TT_LAUNCH_CHECK("bn_backward_reduce");
   return TT_OK;
 }

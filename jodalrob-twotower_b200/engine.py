@@ -133,6 +133,8 @@ class TwoTowerEngine:
         self._ws: Dict[int, _Ws] = {}
         self.rng_seed = 0x5EED
         self.launches = 0  # kernels launched through the C ABI (bench.py's gpu_launches)
+        self.profile: Optional[list] = None  # set to [] to collect (tag, n_kernels, ev0, ev1) per C-ABI call
+        self.profile_tag = ""
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
@@ -140,7 +142,17 @@ class TwoTowerEngine:
 
     def _call(self, name: str, *args, n_kernels: int = 1):
         self.launches += n_kernels
+        prof = self.profile
+        if prof is None:
+            self.lib.call(name, *args)
+            return
+        # per-entry-point device timing (bench.py's kernel table): CUDA events on the launching stream
+        st = torch.cuda.current_stream(self.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
         self.lib.call(name, *args)
+        e1.record(st)
+        prof.append((f"{name}[{self.profile_tag}]" if self.profile_tag else name, n_kernels, e0, e1))
 
     def dense(self, name: str, which: str = "w") -> torch.Tensor:
         return self.layout.view({"w": self.dense_w, "g": self.dense_g, "m": self.dense_m, "v": self.dense_v}[which], name)
@@ -225,6 +237,7 @@ class TwoTowerEngine:
                       masks: Optional[Sequence[torch.Tensor]] = None):
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
         name, keys, _, dense_dim = cfg.tower(t)
+        self.profile_tag = name
         K = len(keys)
         k0 = 0 if t == 0 else self.K[0]
         H0 = cfg.hidden[0]
@@ -275,6 +288,7 @@ class TwoTowerEngine:
 
     def loss_forward(self, ws: _Ws):
         cfg, B, s = self.cfg, ws.B, self._stream()
+        self.profile_tag = ""
         inv_t = 1.0 / cfg.temperature
         self._call("tt_simce_forward", ptr(ws.e[0]), ptr(ws.e[1]), B, B, cfg.final_dim, TT_F32, inv_t, 0, ptr(ws.row_sumexp),
                    ptr(ws.col_sumexp), ptr(ws.row_sum_s), ptr(ws.col_sum_s), ptr(ws.diag), ptr(ws.row_argmax),
@@ -308,6 +322,7 @@ class TwoTowerEngine:
     # ------------------------------------------------------------------ backward
     def loss_backward(self, ws: _Ws, dloss: float = 1.0):
         cfg, B, s = self.cfg, ws.B, self._stream()
+        self.profile_tag = ""
         inv_t = 1.0 / cfg.temperature
         gscale = dloss * 0.5 / B * inv_t
         F = cfg.final_dim
@@ -319,6 +334,7 @@ class TwoTowerEngine:
     def tower_backward(self, t: int, ws: _Ws):
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
         name, keys, _, dense_dim = cfg.tower(t)
+        self.profile_tag = name + ".bwd"
         H0, F = cfg.hidden[0], cfg.final_dim
         ld = H0 + len(keys) * E
         pre = f"{name}_tower."
@@ -371,6 +387,7 @@ class TwoTowerEngine:
         n0, n1 = B * self.K[0], B * self.K[1]
         n = n0 + n1
         H0 = cfg.hidden[0]
+        self.profile_tag = ""
         self.stamp.add_(1)
         self._call("tt_ebc_sort_rows", ptr(ws.rows), 0, n, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
                    ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
