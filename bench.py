@@ -215,7 +215,7 @@ def run_ours(args):
             nk, ck, categorical_embedding_dim=MODEL["emb_dim"], notice_dense_input_dim=MODEL["notice_dense"],
             company_dense_input_dim=MODEL["company_dense"], tower_hidden_dims=MODEL["hidden"], final_embedding_dim=MODEL["final_dim"],
             dropout_rate=MODEL["dropout"], temperature=MODEL["temperature"], device=dev,
-            vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])})
+            vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])}, dtype=args.dtype)
     tt.FusedAdam(task, lr=MODEL["lr"], weight_decay=MODEL["weight_decay"], warmup_steps=0)
     task.train()
     eng = task.engine
@@ -386,9 +386,11 @@ def run_ours(args):
                         "traffic": None, "peak_source": pk["source"]}
     cpu = cpu_baseline(schema, B) if (world == 1 and not args.no_cpu_baseline) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"README-default two-tower train step (emb 32, towers [128,64]->64, 38 tables / 64,141 rows), "
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+            "config": {"precision": ("bf16 embeddings + tcgen05 sim-CE (fp32 accumulate in TMEM); towers, reductions, master weights "
+                                     "and Adam in fp32") if args.dtype == "bf16" else "fp32 everywhere (SIMT)",
+                       "workload": f"README-default two-tower train step (emb 32, towers [128,64]->64, 38 tables / 64,141 rows), "
                                    f"B={B} per GPU, in-batch negatives, dropout 0.1, exact dense Adam lr 1e-3 wd 1e-5",
                        "batch_per_gpu": B, "global_batch": B * world, "optimizer": "dense_exact",
                        "parallelism": f"dp{world}" + (" row-wise sharded tables" if world > 1 else ""),
@@ -410,6 +412,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8192, help="samples per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -227,6 +227,8 @@ int tt_simce_backward(const void* X, const void* Y, int64_t Bx, int64_t By, int3
                       int64_t diag_offset, const float* inv_x, const float* inv_y, float gscale,
                       float label_smoothing, int64_t B_global, float* dX, void* workspace, int64_t workspace_bytes,
                       tt_stream_t stream);
+/* Test hook: make the tcgen05 (bf16) sim-CE kernels stage operands with the generic-proxy loader instead of TMA. */
+int tt_debug_simce_force_manual_loads(int32_t on);
 /* Lazily materialise S (eval / predict_batch / return_metrics "similarity_matrix" only). */
 int tt_similarity_matrix(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype,
                          float inv_temp, float* S, int64_t lds, tt_stream_t stream);

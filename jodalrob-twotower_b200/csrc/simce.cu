@@ -3,6 +3,7 @@
 // written to memory.  (The bf16 path does the same contraction on tcgen05 tensor cores with the
 // tile held in TMEM: simce_tc.cu.)
 #include "sgemm.cuh"
+#include "simce_tc.h"
 #include <float.h>
 
 namespace tt {
@@ -298,9 +299,16 @@ using namespace tt;
 extern "C" {
 
 int64_t tt_simce_workspace_bytes(int64_t Bx, int64_t By, int32_t F) {
-  (void)F;
   const int64_t nCT = (By + GN - 1) / GN, nRT = (Bx + GM - 1) / GM;
-  return 4 * a256(nCT * Bx * 4) + 2 * a256(nRT * By * 4) + 256;
+  const int64_t simt = 4 * a256(nCT * Bx * 4) + 2 * a256(nRT * By * 4) + 256;
+  const int64_t tc = (F == 64 || F == 128) ? simce_tc_workspace_bytes(Bx, By, F) : 0;
+  return simt > tc ? simt : tc;
+}
+
+/* test hook: force the generic-proxy operand loader instead of TMA in the tcgen05 kernels */
+int tt_debug_simce_force_manual_loads(int32_t on) {
+  simce_tc_set_force_manual(on);
+  return TT_OK;
 }
 
 int tt_simce_forward(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
@@ -311,11 +319,22 @@ int tt_simce_forward(const void* X, const void* Y, int64_t Bx, int64_t By, int32
                (long long)diag_offset, (long long)(diag_offset + Bx), (long long)By);
   TT_CHECK_ARG(workspace && workspace_bytes >= tt_simce_workspace_bytes(Bx, By, F), "tt_simce_forward: workspace too small");
   TT_CHECK_ARG(inv_temp > 0.f && inv_temp <= 40.f, "tt_simce_forward: temperature must be >= 0.025 (inv_temp=%f)", inv_temp);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == TT_BF16) {
+    if (F != 64 && F != 128) {
+      set_error("tt_simce_forward: the tcgen05 bf16 path needs final_embedding_dim 64 or 128 (got %d)", F);
+      return TT_ERR_UNSUPPORTED;
+    }
+    TT_CHECK_ARG(((uintptr_t)X & 15) == 0 && ((uintptr_t)Y & 15) == 0, "tt_simce_forward: bf16 operands must be 16-byte aligned");
+    // rows of S (with metrics), then rows of S^T == columns of S
+    int rc = simce_tc_rows(X, Y, Bx, By, F, inv_temp, diag_offset, row_sumexp, row_sum_s, diag, row_argmax, 1, workspace, s);
+    if (rc != TT_OK) return rc;
+    return simce_tc_rows(Y, X, By, Bx, F, inv_temp, 0, col_sumexp, col_sum_s, nullptr, nullptr, 0, workspace, s);
+  }
   if (dtype != TT_F32) {
-    set_error("tt_simce_forward: dtype %d not supported by the fp32 path", dtype);
+    set_error("tt_simce_forward: bad dtype %d", dtype);
     return TT_ERR_UNSUPPORTED;
   }
-  cudaStream_t s = (cudaStream_t)stream;
   SimceFwdWs ws = carve_ws(workspace, Bx, By);
   const int nCT = ceil_div(By, GN), nRT = ceil_div(Bx, GM);
   simce_fwd_tile_kernel<<<dim3(nCT, nRT), GTHREADS, 0, s>>>((const float*)X, (const float*)Y, Bx, By, F, inv_temp,
@@ -351,11 +370,19 @@ int tt_simce_backward(const void* X, const void* Y, int64_t Bx, int64_t By, int3
                       int64_t diag_offset, const float* inv_x, const float* inv_y, float gscale,
                       float label_smoothing, int64_t B_global, float* dX, void* workspace, int64_t workspace_bytes,
                       tt_stream_t stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   TT_CHECK_ARG(X && Y && inv_x && inv_y && dX && Bx > 0 && By > 0 && F > 0 && B_global > 0, "tt_simce_backward: bad arguments");
+  if (dtype == TT_BF16) {
+    if (F != 64 && F != 128) {
+      set_error("tt_simce_backward: the tcgen05 bf16 path needs final_embedding_dim 64 or 128 (got %d)", F);
+      return TT_ERR_UNSUPPORTED;
+    }
+    TT_CHECK_ARG(workspace && workspace_bytes >= simce_tc_workspace_bytes(Bx, By, F), "tt_simce_backward: workspace too small");
+    const float t_off = label_smoothing / (float)B_global;
+    return simce_tc_bwd(X, Y, Bx, By, F, inv_temp, diag_offset, inv_x, inv_y, gscale, (1.f - label_smoothing) + t_off, t_off, dX,
+                        workspace, (cudaStream_t)stream);
+  }
   if (dtype != TT_F32) {
-    set_error("tt_simce_backward: dtype %d not supported by the fp32 path", dtype);
+    set_error("tt_simce_backward: bad dtype %d", dtype);
     return TT_ERR_UNSUPPORTED;
   }
   if (F > 128) {

@@ -88,8 +88,18 @@ class _Ws:
 
 
 class TwoTowerEngine:
-    def __init__(self, cfg: TwoTowerConfig, device, optimizer_mode: str = "dense_exact", value_layout: str = "sample_major"):
+    def __init__(self, cfg: TwoTowerConfig, device, optimizer_mode: str = "dense_exact", value_layout: str = "sample_major",
+                 dtype: str = "fp32"):
         self.cfg = cfg
+        if dtype not in ("fp32", "bf16"):
+            raise ValueError(f"dtype must be 'fp32' or 'bf16', got {dtype}")
+        # bf16: tower outputs are stored in bf16 and the B x B logits / loss / gradients run on tcgen05 tensor cores
+        # (fp32 accumulation in TMEM); master weights, Adam state and reductions stay fp32.
+        self.dtype = dtype
+        if dtype == "bf16" and cfg.final_dim not in (64, 128):
+            raise ValueError("dtype='bf16' (tcgen05 sim-CE) needs final_embedding_dim 64 or 128")
+        self.emb_tt = native.TT_BF16 if dtype == "bf16" else TT_F32
+        self.emb_torch = torch.bfloat16 if dtype == "bf16" else torch.float32
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise native.TwoTowerNativeError("TwoTowerEngine needs a CUDA device: the hot path is sm_100a CUDA only, no CPU fallback")
@@ -191,7 +201,7 @@ class TwoTowerEngine:
             ws.mean.append([torch.empty(h, **f32) for h in cfg.hidden[1:]])
             ws.rstd.append([torch.empty(h, **f32) for h in cfg.hidden[1:]])
             ws.z.append(torch.empty(B, cfg.final_dim, **f32))
-            ws.e.append(torch.empty(B, cfg.final_dim, **f32))
+            ws.e.append(torch.empty(B, cfg.final_dim, dtype=self.emb_torch, device=dev))
             ws.nrm.append(torch.empty(B, **f32))
             ws.de.append(torch.empty(B, cfg.final_dim, **f32))
             ws.dz.append(torch.empty(B, cfg.final_dim, **f32))
@@ -279,7 +289,7 @@ class TwoTowerEngine:
         F = cfg.final_dim
         self._call("tt_linear_forward", ptr(x), width, ptr(self.dense(pre + f"mlp.{idx}.weight")),
                    ptr(self.dense(pre + f"mlp.{idx}.bias")), ptr(ws.z[t]), F, B, F, width, self.act, 0, s)
-        self._call("tt_l2norm_forward", ptr(ws.z[t]), B, F, ptr(ws.e[t]), TT_F32, ptr(ws.nrm[t]), s)
+        self._call("tt_l2norm_forward", ptr(ws.z[t]), B, F, ptr(ws.e[t]), self.emb_tt, ptr(ws.nrm[t]), s)
         return ws.e[t]
 
     def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int) -> int:
@@ -290,7 +300,7 @@ class TwoTowerEngine:
         cfg, B, s = self.cfg, ws.B, self._stream()
         self.profile_tag = ""
         inv_t = 1.0 / cfg.temperature
-        self._call("tt_simce_forward", ptr(ws.e[0]), ptr(ws.e[1]), B, B, cfg.final_dim, TT_F32, inv_t, 0, ptr(ws.row_sumexp),
+        self._call("tt_simce_forward", ptr(ws.e[0]), ptr(ws.e[1]), B, B, cfg.final_dim, self.emb_tt, inv_t, 0, ptr(ws.row_sumexp),
                    ptr(ws.col_sumexp), ptr(ws.row_sum_s), ptr(ws.col_sum_s), ptr(ws.diag), ptr(ws.row_argmax),
                    ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=3)
         self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), ptr(ws.col_sum_s),
@@ -326,10 +336,10 @@ class TwoTowerEngine:
         inv_t = 1.0 / cfg.temperature
         gscale = dloss * 0.5 / B * inv_t
         F = cfg.final_dim
-        self._call("tt_simce_backward", ptr(ws.e[0]), ptr(ws.e[1]), B, B, F, TT_F32, inv_t, 0, ptr(ws.inv_row), ptr(ws.inv_col),
-                   gscale, cfg.label_smoothing, B, ptr(ws.de[0]), 0, 0, s)
-        self._call("tt_simce_backward", ptr(ws.e[1]), ptr(ws.e[0]), B, B, F, TT_F32, inv_t, 0, ptr(ws.inv_col), ptr(ws.inv_row),
-                   gscale, cfg.label_smoothing, B, ptr(ws.de[1]), 0, 0, s)
+        self._call("tt_simce_backward", ptr(ws.e[0]), ptr(ws.e[1]), B, B, F, self.emb_tt, inv_t, 0, ptr(ws.inv_row), ptr(ws.inv_col),
+                   gscale, cfg.label_smoothing, B, ptr(ws.de[0]), ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=2)
+        self._call("tt_simce_backward", ptr(ws.e[1]), ptr(ws.e[0]), B, B, F, self.emb_tt, inv_t, 0, ptr(ws.inv_col), ptr(ws.inv_row),
+                   gscale, cfg.label_smoothing, B, ptr(ws.de[1]), ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=2)
 
     def tower_backward(self, t: int, ws: _Ws):
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
@@ -341,7 +351,7 @@ class TwoTowerEngine:
         train = ws.train
         nblk = len(cfg.hidden) - 1
         widths = [ld] + list(cfg.hidden[1:])
-        self._call("tt_l2norm_backward", ptr(ws.de[t]), ptr(ws.e[t]), TT_F32, ptr(ws.nrm[t]), B, F, ptr(ws.dz[t]), s)
+        self._call("tt_l2norm_backward", ptr(ws.de[t]), ptr(ws.e[t]), self.emb_tt, ptr(ws.nrm[t]), B, F, ptr(ws.dz[t]), s)
         idx = 4 * nblk
         xlast = ws.y[t][nblk - 1] if nblk > 0 else ws.c[t]
         wl = widths[-1]
@@ -435,6 +445,7 @@ class TwoTowerEngine:
     def similarity_matrix(self, ws: _Ws) -> torch.Tensor:
         B = ws.B
         S = torch.empty(B, B, dtype=torch.float32, device=self.device)
-        self._call("tt_similarity_matrix", ptr(ws.e[0]), ptr(ws.e[1]), B, B, self.cfg.final_dim, TT_F32,
+        n, c = ws.e[0].float(), ws.e[1].float()  # eval / debugging only: the train step never stores the logits
+        self._call("tt_similarity_matrix", ptr(n), ptr(c), B, B, self.cfg.final_dim, TT_F32,
                    1.0 / self.cfg.temperature, ptr(S), B, self._stream())
         return S

@@ -465,7 +465,8 @@ def create_two_tower_model(notice_categorical_keys: Sequence[str], company_categ
                            notice_dense_input_dim: int = 256, company_dense_input_dim: int = 128,
                            tower_hidden_dims: Optional[List[int]] = None, final_embedding_dim: int = 128,
                            dropout_rate: float = 0.2, device="cuda:0", vocab_sizes: Optional[Dict[str, Dict[str, int]]] = None,
-                           optimizer_mode: str = "dense_exact", value_layout: str = "sample_major") -> TwoTowerModel:
+                           optimizer_mode: str = "dense_exact", value_layout: str = "sample_major",
+                           dtype: str = "fp32") -> TwoTowerModel:
     if tower_hidden_dims is None:
         tower_hidden_dims = [256, 128]
     nk, ck = list(notice_categorical_keys), list(company_categorical_keys)
@@ -475,7 +476,7 @@ def create_two_tower_model(notice_categorical_keys: Sequence[str], company_categ
     cfg = TwoTowerConfig(nk, ck, [int(vocab_sizes["notice"][k]) for k in nk], [int(vocab_sizes["company"][k]) for k in ck],
                          categorical_embedding_dim, notice_dense_input_dim, company_dense_input_dim,
                          list(tower_hidden_dims), final_embedding_dim, dropout_rate)
-    engine = TwoTowerEngine(cfg, device, optimizer_mode, value_layout)
+    engine = TwoTowerEngine(cfg, device, optimizer_mode, value_layout, dtype)
     _init_like_reference(engine)
     return TwoTowerModel(engine)
 
@@ -485,8 +486,9 @@ def create_two_tower_train_task(notice_categorical_keys, company_categorical_key
                                 company_dense_input_dim: int = 128, tower_hidden_dims=None, final_embedding_dim: int = 128,
                                 dropout_rate: float = 0.2, temperature: float = 1.0, loss_type: str = "cross_entropy",
                                 device="cuda:0", label_smoothing: float = 0.0, vocab_sizes=None,
-                                optimizer_mode: str = "dense_exact", value_layout: str = "sample_major") -> TwoTowerTrainTask:
+                                optimizer_mode: str = "dense_exact", value_layout: str = "sample_major",
+                                dtype: str = "fp32") -> TwoTowerTrainTask:
     model = create_two_tower_model(notice_categorical_keys, company_categorical_keys, metadata_path, categorical_embedding_dim,
                                    notice_dense_input_dim, company_dense_input_dim, tower_hidden_dims, final_embedding_dim,
-                                   dropout_rate, device, vocab_sizes, optimizer_mode, value_layout)
+                                   dropout_rate, device, vocab_sizes, optimizer_mode, value_layout, dtype)
     return TwoTowerTrainTask(model, temperature=temperature, loss_type=loss_type, label_smoothing=label_smoothing)
