@@ -209,7 +209,7 @@ def run_ours(args):
     torch.manual_seed(0)
     if world > 1:
         from jodalrob_twotower_b200 import dist as ttdist
-        task = ttdist.create_distributed_train_task(nk, ck, schema, MODEL, dev)
+        task = ttdist.create_distributed_train_task(nk, ck, schema, MODEL, dev, dtype=args.dtype)
     else:
         task = tt.create_two_tower_train_task(
             nk, ck, categorical_embedding_dim=MODEL["emb_dim"], notice_dense_input_dim=MODEL["notice_dense"],
@@ -353,8 +353,7 @@ def run_ours(args):
             d["ms"] = d["ms"] / n_prof
             d["calls"] = d["calls"] // n_prof
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dev)
         return
     pk = peaks()
     table = []
@@ -401,8 +400,16 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "roofline": roofline, "cpu_baseline": cpu, "kernels": table, "loss_last": loss_last}
     print(json.dumps(line), flush=True)
+    _finish(world, dev)
+
+
+def _finish(world, dev):
+    """Multi-rank teardown: captured graphs hold NCCL work and symmetric-memory handles; skip the destructors."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -111,12 +111,14 @@ int tt_ebc_forward(const float* arena, const int64_t* d_row_base, const int32_t*
  *                    arrays and row_stamp[row] = stamp; rows absent keep an older stamp (no memset).
  *   stamp            effective stamp = stamp + (d_stamp ? (int32)*d_stamp : 0); d_stamp is a device
  *                    counter so a captured CUDA graph sees a fresh stamp on every replay.
+ *   d_n              optional device count: the number of valid pairs is *d_n (<= n, n = capacity). Used by
+ *                    the row-wise sharded path where the owner only learns on the device how many ids it owns.
  */
 int64_t tt_ebc_sort_workspace_bytes(int64_t n, int64_t total_rows);
 int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
                      int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
                      int32_t* row_end, int32_t* row_stamp, int32_t stamp, const int64_t* d_stamp,
-                     tt_stream_t stream);
+                     const int32_t* d_n, tt_stream_t stream);
 
 /* Sparse backward, stage 2: segment-sum of the pooled-output gradients in fixed order, fused with
  * the Adam row update.  Gradient slot s < n0 belongs to source 0 (sample s / K0, key s % K0, vector
@@ -127,14 +129,39 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
  *   mode TT_ADAM_SPARSE: only stamped rows are updated.
  *   grad_arena != NULL: also/only materialise the dense gradient ([total_rows,E], zeros elsewhere)
  *        for the autograd-compatible path (w/m/v may then be NULL).
- * piece_ws: f32 scratch of tt_ebc_piece_workspace_bytes(n, E) for rows with long segments. */
+ * piece_ws: f32 scratch of tt_ebc_piece_workspace_bytes(n, E) for rows with long segments.
+ * Sharded tables (multi-GPU): grad_table != NULL is a device array [world*2] of peer-mapped base pointers
+ * (rank r's source 0 / source 1 buffers); slot = r * n_per_rank + local slot and the segment-sum PULLS the
+ * gradient vectors over NVLink — the gradient all-to-all is fused into this kernel. d_n: see tt_ebc_sort_rows. */
 int64_t tt_ebc_piece_workspace_bytes(int64_t n, int32_t E);
 int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* grad_arena, int64_t total_rows,
                          int32_t E, const int32_t* sorted_rows, const int32_t* sorted_slots, int64_t n,
                          const int32_t* row_begin, const int32_t* row_end, const int32_t* row_stamp, int32_t stamp,
                          const int64_t* d_stamp, const void* grad0, int64_t ld0, int64_t col0_0, int32_t K0, int64_t n0, const void* grad1,
                          int64_t ld1, int64_t col0_1, int32_t K1, int64_t n1, int32_t grad_dtype, void* piece_ws,
-                         int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, tt_stream_t stream);
+                         int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, const int32_t* d_n,
+                         const void* const* grad_table, int64_t n_per_rank, tt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise sharded tables across GPUs (no counterpart in the single-GPU reference; TorchRec RW convention:
+ * block_k = ceil(V_k/world), owner = id / block_k, local row = local_base[k] + id - owner*block_k).
+ *   tt_ebc_clamp_ids       ids_out i32 [B*K] in slot order b*K+k = clamp(values, 0, V_k-1)  (cat_embed.py:115-117)
+ *   tt_shard_select_owned  ids_all i32 [world*n_per_rank] = every rank's clamped ids (rank-major; per rank n0 slots of
+ *                          tower 0 with K0 keys, then tower 1 with K1 keys; table index = k resp. K0+k).
+ *                          Deterministic stable compaction of the ids this rank owns: rows_out (local arena row),
+ *                          slots_out (global slot = rank*n_per_rank + local slot), *d_n_owned.  Bit-exact integer stage.
+ *   tt_ebc_push_rows       fused lookup + row all-to-all: for every owned id, gather the row and store it into the
+ *                          requester's concat buffer dst_table[rank*2 + tower] (peer-mapped over NVLink) at
+ *                          [b, col0 + k*E].  The matching gradient return is tt_ebc_backward_adam with grad_table. */
+int tt_ebc_clamp_ids(const int64_t* values, const int32_t* d_vocab, int32_t B, int32_t K, int32_t layout, int32_t* ids_out,
+                     tt_stream_t stream);
+int64_t tt_shard_workspace_bytes(int64_t n_total);
+int tt_shard_select_owned(const int32_t* ids_all, const int32_t* d_block, const int32_t* d_local_base, int64_t n_per_rank,
+                          int64_t n0, int32_t K0, int32_t K1, int32_t world, int32_t me, int32_t* rows_out, int32_t* slots_out,
+                          int32_t* d_n_owned, void* workspace, int64_t workspace_bytes, tt_stream_t stream);
+int tt_ebc_push_rows(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
+                     int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
+                     int64_t ld1, int64_t col0_0, int64_t col0_1, int32_t out_dtype, tt_stream_t stream);
 
 /* Dense-parameter Adam over a flat fp32 buffer (tower Linear/BatchNorm weights), same update rule.
  * Replaces torch.optim.Adam.step for the non-embedding parameters (scripts/train.py:327). */

@@ -136,8 +136,10 @@ constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys per block
 
 __global__ void __launch_bounds__(RS_THREADS)
-radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int shift, int32_t* __restrict__ hist, int n_tiles) {
+radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ d_n, int shift,
+                  int32_t* __restrict__ hist, int n_tiles) {
   __shared__ int32_t s_hist[256];
+  if (d_n) n = *d_n;
   s_hist[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
@@ -175,9 +177,10 @@ __global__ void __launch_bounds__(1024) scan_exclusive_kernel(int32_t* __restric
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
-radix_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n, int shift,
-                     const int32_t* __restrict__ hist_scanned, int n_tiles, int32_t* __restrict__ keys_out,
-                     int32_t* __restrict__ vals_out) {
+radix_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n,
+                     const int32_t* __restrict__ d_n, int shift, const int32_t* __restrict__ hist_scanned, int n_tiles,
+                     int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
+  if (d_n) n = *d_n;
   // each warp owns 256 consecutive keys; item i of the warp is keys [i*32, i*32+32) of that chunk, so
   // (item, lane) order == index order and the ranking below is stable.
   __shared__ int32_t s_warp_hist[RS_THREADS / 32][256];
@@ -234,8 +237,9 @@ radix_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restr
 
 __global__ void segment_bounds_kernel(const int32_t* __restrict__ srow, int64_t n, int32_t* __restrict__ row_begin,
                                       int32_t* __restrict__ row_end, int32_t* __restrict__ row_stamp, int32_t stamp,
-                                      const int64_t* __restrict__ d_stamp) {
+                                      const int64_t* __restrict__ d_stamp, const int32_t* __restrict__ d_n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_n) n = *d_n;
   if (i >= n) return;
   if (d_stamp) stamp += (int32_t)(*d_stamp);
   const int32_t r = srow[i];
@@ -256,20 +260,32 @@ struct GradSrc {
   const void* g1;
   int64_t ld0, ld1, col0, col1, n0;
   int K0, K1;
+  // row-wise sharded tables: slot = src_rank * n_per_rank + local slot; the pooled-gradient buffers of every rank are
+  // peer-mapped (NVLink) and listed in `table` as [rank*2 + tower] — the segment-sum pulls them directly
+  const void* const* table;
+  int64_t n_per_rank;
 };
 
 template <typename GT>
 __device__ __forceinline__ float4 load_grad_vec(const GradSrc& s, int32_t slot, int E, int c) {
   const GT* base;
   int64_t off;
+  const void* p0 = s.g0;
+  const void* p1 = s.g1;
+  if (s.table) {
+    const int r = (int)(slot / s.n_per_rank);
+    slot -= (int32_t)(r * s.n_per_rank);
+    p0 = s.table[2 * r];
+    p1 = s.table[2 * r + 1];
+  }
   if (slot < s.n0) {
     const int b = slot / s.K0, k = slot - b * s.K0;
-    base = reinterpret_cast<const GT*>(s.g0);
+    base = reinterpret_cast<const GT*>(p0);
     off = (int64_t)b * s.ld0 + s.col0 + (int64_t)k * E + 4 * c;
   } else {
     const int sl = slot - (int32_t)s.n0;
     const int b = sl / s.K1, k = sl - b * s.K1;
-    base = reinterpret_cast<const GT*>(s.g1);
+    base = reinterpret_cast<const GT*>(p1);
     off = (int64_t)b * s.ld1 + s.col1 + (int64_t)k * E + 4 * c;
   }
   if constexpr (sizeof(GT) == 4) {
@@ -279,12 +295,30 @@ __device__ __forceinline__ float4 load_grad_vec(const GradSrc& s, int32_t slot, 
   }
 }
 
+// acc += sum_{i in [lo,hi)} grad(sslot[i]) in ascending i, with 8 independent (possibly peer/NVLink) loads in flight
+template <typename GT>
+__device__ __forceinline__ void gather_sum(float4& acc, const int32_t* __restrict__ sslot, int64_t lo, int64_t hi,
+                                           const GradSrc& src, int E, int c) {
+  for (int64_t i = lo; i < hi; i += 8) {
+    int32_t sl[8];
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sl[u] = (i + u < hi) ? __ldg(sslot + i + u) : -1;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = sl[u] >= 0 ? load_grad_vec<GT>(src, sl[u], E, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (sl[u] >= 0) f4_add(acc, v[u]);
+  }
+}
+
 // level 1 for long rows: one lane group per chunk of SEG_CHUNK sorted entries
 template <typename GT>
 __global__ void __launch_bounds__(256)
 ebc_piece_kernel(const int32_t* __restrict__ srow, const int32_t* __restrict__ sslot, int64_t n,
-                 const int32_t* __restrict__ row_begin, const int32_t* __restrict__ row_end, GradSrc src, int E, int G,
-                 float* __restrict__ pieces) {
+                 const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_begin,
+                 const int32_t* __restrict__ row_end, GradSrc src, int E, int G, float* __restrict__ pieces) {
+  if (d_n) n = *d_n;
   const int lane = threadIdx.x % G;
   const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
   const int64_t lo = chunk * SEG_CHUNK;
@@ -299,7 +333,7 @@ ebc_piece_kernel(const int32_t* __restrict__ srow, const int32_t* __restrict__ s
     const int64_t pe = e0 < hi ? e0 : hi;
     for (int c = lane; c < vec_per_row; c += G) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int64_t i = lo; i < pe; ++i) f4_add(acc, load_grad_vec<GT>(src, sslot[i], E, c));
+      gather_sum<GT>(acc, sslot, lo, pe, src, E, c);
       *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 0) * E) + 4 * c) = acc;
     }
   }
@@ -307,7 +341,7 @@ ebc_piece_kernel(const int32_t* __restrict__ srow, const int32_t* __restrict__ s
   if (e1 - b1 > SEG_CHUNK && b1 > lo) {
     for (int c = lane; c < vec_per_row; c += G) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int64_t i = b1; i < hi; ++i) f4_add(acc, load_grad_vec<GT>(src, sslot[i], E, c));
+      gather_sum<GT>(acc, sslot, b1, hi, src, E, c);
       *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 1) * E) + 4 * c) = acc;
     }
   }
@@ -318,7 +352,7 @@ __device__ __forceinline__ float4 row_grad_sum(const int32_t* __restrict__ sslot
                                                const GradSrc& src, int E, int c, const float* __restrict__ pieces) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e - b <= SEG_CHUNK) {
-    for (int64_t i = b; i < e; ++i) f4_add(acc, load_grad_vec<GT>(src, sslot[i], E, c));
+    gather_sum<GT>(acc, sslot, b, e, src, E, c);
   } else {
     for (int64_t ch = b / SEG_CHUNK; ch <= (e - 1) / SEG_CHUNK; ++ch) {
       const int which = (b <= ch * SEG_CHUNK) ? 0 : 1;
@@ -387,8 +421,9 @@ template <typename GT>
 __global__ void __launch_bounds__(256)
 ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int E, int G,
                        const int32_t* __restrict__ srow, const int32_t* __restrict__ sslot, int64_t n,
-                       const int32_t* __restrict__ row_end, GradSrc src, const float* __restrict__ pieces,
-                       const tt_adam_hyper* __restrict__ d_hyper) {
+                       const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_end, GradSrc src,
+                       const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
+  if (d_n) n = *d_n;
   const tt_adam_hyper h = *d_hyper;
   const int lane = threadIdx.x % G;
   const int64_t i = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
@@ -493,7 +528,7 @@ int64_t tt_ebc_sort_workspace_bytes(int64_t n, int64_t total_rows) {
 int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
                      int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
                      int32_t* row_end, int32_t* row_stamp, int32_t stamp, const int64_t* d_stamp,
-                     tt_stream_t stream) {
+                     const int32_t* d_n, tt_stream_t stream) {
   TT_CHECK_ARG(rows && sorted_rows && sorted_slots && row_begin && row_end && row_stamp, "tt_ebc_sort_rows: NULL pointer");
   TT_CHECK_ARG(n >= 0 && n < (1ll << 31) && total_rows > 0 && total_rows < (1ll << 31), "tt_ebc_sort_rows: bad sizes");
   TT_CHECK_ARG(workspace_bytes >= tt_ebc_sort_workspace_bytes(n, total_rows) && (workspace || n == 0),
@@ -516,13 +551,13 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
     const bool to_final = ((passes - 1 - p) % 2) == 0;
     int32_t* kout = to_final ? sorted_rows : tmp_keys;
     int32_t* vout = to_final ? sorted_slots : tmp_vals;
-    radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, n, p * 8, hist, n_tiles);
+    radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles);
     scan_exclusive_kernel<<<1, 1024, 0, s>>>(hist, (int64_t)256 * n_tiles);
-    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, p * 8, hist, n_tiles, kout, vout);
+    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, d_n, p * 8, hist, n_tiles, kout, vout);
     kin = kout;
     vin = vout;
   }
-  segment_bounds_kernel<<<ceil_div(n, 256), 256, 0, s>>>(sorted_rows, n, row_begin, row_end, row_stamp, stamp, d_stamp);
+  segment_bounds_kernel<<<ceil_div(n, 256), 256, 0, s>>>(sorted_rows, n, row_begin, row_end, row_stamp, stamp, d_stamp, d_n);
   TT_LAUNCH_CHECK("ebc_sort_rows");
   return TT_OK;
 }
@@ -537,14 +572,16 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
                          const int32_t* row_begin, const int32_t* row_end, const int32_t* row_stamp, int32_t stamp,
                          const int64_t* d_stamp, const void* grad0, int64_t ld0, int64_t col0_0, int32_t K0, int64_t n0, const void* grad1,
                          int64_t ld1, int64_t col0_1, int32_t K1, int64_t n1, int32_t grad_dtype, void* piece_ws,
-                         int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, tt_stream_t stream) {
+                         int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, const int32_t* d_n,
+                         const void* const* grad_table, int64_t n_per_rank, tt_stream_t stream) {
   const bool do_adam = arena_w != nullptr;
   TT_CHECK_ARG(do_adam || grad_arena, "tt_ebc_backward_adam: nothing to do (arena_w and grad_arena both NULL)");
   TT_CHECK_ARG(!do_adam || (arena_m && arena_v && d_hyper), "tt_ebc_backward_adam: Adam needs m, v and d_hyper");
   TT_CHECK_ARG(E > 0 && (E % 4) == 0 && total_rows > 0, "tt_ebc_backward_adam: bad E/total_rows");
-  TT_CHECK_ARG(n == 0 || (sorted_rows && sorted_slots && row_begin && row_end && row_stamp && grad0),
+  TT_CHECK_ARG(n == 0 || (sorted_rows && sorted_slots && row_begin && row_end && row_stamp && (grad0 || grad_table)),
                "tt_ebc_backward_adam: NULL index/grad pointer");
-  TT_CHECK_ARG(n0 + n1 >= 0 && (n1 == 0 || grad1), "tt_ebc_backward_adam: grad1 missing");
+  TT_CHECK_ARG(n0 + n1 >= 0 && (n1 == 0 || grad1 || grad_table), "tt_ebc_backward_adam: grad1 missing");
+  TT_CHECK_ARG(!grad_table || n_per_rank == n0 + n1, "tt_ebc_backward_adam: n_per_rank must equal n0 + n1 with a grad table");
   TT_CHECK_ARG(K0 > 0 && (n1 == 0 || K1 > 0), "tt_ebc_backward_adam: bad K");
   TT_CHECK_ARG((ld0 % 4) == 0 && (col0_0 % 4) == 0 && (ld1 % 4) == 0 && (col0_1 % 4) == 0,
                "tt_ebc_backward_adam: grad ld/col0 must be multiples of 4");
@@ -556,25 +593,25 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
   cudaStream_t s = (cudaStream_t)stream;
   const int G = lanes_per_row(E);
   const int threads = 256, gpb = threads / G;
-  GradSrc src{grad0, grad1, ld0, ld1, col0_0, col0_1, n0, K0, K1 > 0 ? K1 : 1};
+  GradSrc src{grad0, grad1, ld0, ld1, col0_0, col0_1, n0, K0, K1 > 0 ? K1 : 1, grad_table, n_per_rank > 0 ? n_per_rank : 1};
   float* pieces = (float*)piece_ws;
   if (n > 0) {
     const int64_t chunks = (n + SEG_CHUNK - 1) / SEG_CHUNK;
     if (grad_dtype == TT_F32)
-      ebc_piece_kernel<float><<<ceil_div(chunks, gpb), threads, 0, s>>>(sorted_rows, sorted_slots, n, row_begin, row_end,
-                                                                        src, E, G, pieces);
+      ebc_piece_kernel<float><<<ceil_div(chunks, gpb), threads, 0, s>>>(sorted_rows, sorted_slots, n, d_n, row_begin,
+                                                                        row_end, src, E, G, pieces);
     else
-      ebc_piece_kernel<__nv_bfloat16><<<ceil_div(chunks, gpb), threads, 0, s>>>(sorted_rows, sorted_slots, n, row_begin,
-                                                                                row_end, src, E, G, pieces);
+      ebc_piece_kernel<__nv_bfloat16><<<ceil_div(chunks, gpb), threads, 0, s>>>(sorted_rows, sorted_slots, n, d_n,
+                                                                                row_begin, row_end, src, E, G, pieces);
   }
   if (mode == TT_ADAM_SPARSE) {
     if (n > 0) {
       if (grad_dtype == TT_F32)
         ebc_rows_sparse_kernel<float><<<ceil_div(n, gpb), threads, 0, s>>>(arena_w, arena_m, arena_v, E, G, sorted_rows,
-                                                                           sorted_slots, n, row_end, src, pieces, d_hyper);
+                                                                           sorted_slots, n, d_n, row_end, src, pieces, d_hyper);
       else
         ebc_rows_sparse_kernel<__nv_bfloat16><<<ceil_div(n, gpb), threads, 0, s>>>(
-            arena_w, arena_m, arena_v, E, G, sorted_rows, sorted_slots, n, row_end, src, pieces, d_hyper);
+            arena_w, arena_m, arena_v, E, G, sorted_rows, sorted_slots, n, d_n, row_end, src, pieces, d_hyper);
     }
   } else {
     int64_t want = ceil_div(total_rows, gpb);

@@ -1,0 +1,225 @@
+// Row-wise sharded embedding tables across GPUs (one process per GPU, NVLink peer memory).
+//
+// Shard map (TorchRec row-wise convention; the reference itself is single-GPU, SURVEY.md §8(c),(e)):
+//     block_k = ceil(V_k / world), owner = id / block_k, local row = local_base[k] + id - owner * block_k.
+// Per step every rank (1) clamps its ids, (2) all-gathers them (NCCL, 4 B per id), (3) picks out the ids it owns
+// with a deterministic stable compaction, (4) PUSHES the looked-up rows straight into the requesters' concat
+// buffers through peer-mapped pointers — lookup and the row all-to-all are one kernel — and in the backward
+// (5) PULLS the pooled-output gradients of its rows from the requesters' buffers inside the segment-sum kernel
+// (ebc.cu, GradSrc::table).  Every buffer has a static size, so the whole step stays CUDA-graph capturable.
+#include "common.cuh"
+
+namespace tt {
+
+// ids[slot] = clamp(values, 0, V_k-1) as int32, slot = b*K + k (whatever the value layout)
+__global__ void __launch_bounds__(256)
+clamp_ids_kernel(const int64_t* __restrict__ values, const int32_t* __restrict__ vocab, int B, int K, int layout,
+                 int32_t* __restrict__ ids) {
+  const int64_t n = (int64_t)B * K;
+  for (int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(slot / K), k = (int)(slot - (int64_t)b * K);
+    int64_t id = values[layout == TT_LAYOUT_SAMPLE_MAJOR ? slot : (int64_t)k * B + b];
+    const int64_t hi = (int64_t)vocab[k] - 1;
+    id = id < 0 ? 0 : (id > hi ? hi : id);
+    ids[slot] = (int32_t)id;
+  }
+}
+
+struct RouteMeta {
+  const int32_t* ids_all;     // [world * n_per_rank] clamped global ids in slot order, rank-major
+  const int32_t* block;       // [K0+K1] rows per rank of table k
+  const int32_t* local_base;  // [K0+K1] first local row of table k
+  int64_t n_total, n_per_rank, n0;
+  int K0, K1, me;
+};
+
+__device__ __forceinline__ bool route_one(const RouteMeta& m, int64_t g, int32_t& local_row) {
+  const int64_t s = g % m.n_per_rank;
+  const int k = s < m.n0 ? (int)(s % m.K0) : m.K0 + (int)((s - m.n0) % m.K1);
+  const int32_t id = m.ids_all[g];
+  const int32_t blk = m.block[k];
+  const int32_t owner = id / blk;
+  local_row = m.local_base[k] + id - owner * blk;
+  return owner == m.me;
+}
+
+constexpr int RT_THREADS = 256, RT_ITEMS = 8, RT_TILE = RT_THREADS * RT_ITEMS;
+
+// pass 1: how many ids of each 2048-entry tile does this rank own
+__global__ void __launch_bounds__(RT_THREADS) route_count_kernel(RouteMeta m, int32_t* __restrict__ tile_counts, int n_tiles) {
+  __shared__ int32_t s_cnt[RT_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t base = (int64_t)blockIdx.x * RT_TILE + (int64_t)warp * (32 * RT_ITEMS);
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < RT_ITEMS; ++i) {
+    const int64_t g = base + i * 32 + lane;
+    int32_t lr;
+    const bool own = g < m.n_total && route_one(m, g, lr);
+    cnt += __popc(__ballot_sync(0xffffffffu, own));
+  }
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < RT_THREADS / 32; ++w) t += s_cnt[w];
+    tile_counts[blockIdx.x] = t;
+    if (blockIdx.x == 0) tile_counts[n_tiles] = 0;  // becomes the grand total after the exclusive scan
+  }
+}
+
+// pass 2 (after an exclusive scan of tile_counts): stable compaction, order == global slot order
+__global__ void __launch_bounds__(RT_THREADS)
+route_compact_kernel(RouteMeta m, const int32_t* __restrict__ tile_offsets, int n_tiles, int32_t* __restrict__ rows_c,
+                     int32_t* __restrict__ slots_c, int32_t* __restrict__ n_owned) {
+  __shared__ int32_t s_cnt[RT_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t base = (int64_t)blockIdx.x * RT_TILE + (int64_t)warp * (32 * RT_ITEMS);
+  bool own[RT_ITEMS];
+  int32_t lr[RT_ITEMS];
+  int rank_in_warp[RT_ITEMS];
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < RT_ITEMS; ++i) {
+    const int64_t g = base + i * 32 + lane;
+    own[i] = g < m.n_total && route_one(m, g, lr[i]);
+    const unsigned b = __ballot_sync(0xffffffffu, own[i]);
+    rank_in_warp[i] = cnt + __popc(b & ((1u << lane) - 1u));
+    cnt += __popc(b);
+  }
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  int warp_off = tile_offsets[blockIdx.x];
+  for (int w = 0; w < warp; ++w) warp_off += s_cnt[w];
+#pragma unroll
+  for (int i = 0; i < RT_ITEMS; ++i) {
+    if (own[i]) {
+      const int64_t g = base + i * 32 + lane;
+      rows_c[warp_off + rank_in_warp[i]] = lr[i];
+      slots_c[warp_off + rank_in_warp[i]] = (int32_t)g;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_owned = tile_offsets[n_tiles];
+}
+
+__global__ void __launch_bounds__(1024) scan_exclusive_small_kernel(int32_t* __restrict__ data, int64_t len) {
+  __shared__ int32_t s_part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (len + 1023) / 1024;
+  const int64_t lo = (int64_t)t * per, hi = (lo + per < len) ? lo + per : len;
+  int32_t sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += data[i];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    int32_t v = (t >= off) ? s_part[t - off] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int32_t run = s_part[t] - sum;
+  for (int64_t i = lo; i < hi; ++i) {
+    int32_t c = data[i];
+    data[i] = run;
+    run += c;
+  }
+}
+
+// fused lookup + all-to-all: one lane group per owned id gathers the row and stores it into the requester's
+// concat buffer (peer-mapped, 128-byte coalesced stores over NVLink)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+push_rows_kernel(const float* __restrict__ arena, int E, int G, const int32_t* __restrict__ rows_c,
+                 const int32_t* __restrict__ slots_c, const int32_t* __restrict__ n_owned, void* const* __restrict__ dst_table,
+                 int64_t n_per_rank, int64_t n0, int K0, int K1, int64_t ld0, int64_t ld1, int64_t col0_0, int64_t col0_1) {
+  const int n = *n_owned;
+  const int lane = threadIdx.x % G;
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
+  const int vec_per_row = E >> 2;
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; e < n; e += groups_total) {
+    const int32_t row = rows_c[e];
+    int64_t g = slots_c[e];
+    const int r = (int)(g / n_per_rank);
+    g -= (int64_t)r * n_per_rank;
+    OutT* dst;
+    if (g < n0) {
+      const int b = (int)(g / K0), k = (int)(g - (int64_t)b * K0);
+      dst = reinterpret_cast<OutT*>(dst_table[2 * r]) + (int64_t)b * ld0 + col0_0 + (int64_t)k * E;
+    } else {
+      g -= n0;
+      const int b = (int)(g / K1), k = (int)(g - (int64_t)b * K1);
+      dst = reinterpret_cast<OutT*>(dst_table[2 * r + 1]) + (int64_t)b * ld1 + col0_1 + (int64_t)k * E;
+    }
+    for (int c = lane; c < vec_per_row; c += G) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(arena + (int64_t)row * E) + c);
+      if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(dst + 4 * c) = v;
+      else *reinterpret_cast<uint2*>(dst + 4 * c) = pack_bf16x4(v);
+    }
+  }
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" {
+
+int tt_ebc_clamp_ids(const int64_t* values, const int32_t* d_vocab, int32_t B, int32_t K, int32_t layout, int32_t* ids_out,
+                     tt_stream_t stream) {
+  TT_CHECK_ARG(values && d_vocab && ids_out && B >= 0 && K > 0, "tt_ebc_clamp_ids: bad arguments");
+  if (B == 0) return TT_OK;
+  int64_t want = ceil_div((int64_t)B * K, 256);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  clamp_ids_kernel<<<(int)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(values, d_vocab, B, K, layout, ids_out);
+  TT_LAUNCH_CHECK("clamp_ids_kernel");
+  return TT_OK;
+}
+
+int64_t tt_shard_workspace_bytes(int64_t n_total) {
+  const int64_t tiles = (n_total + RT_TILE - 1) / RT_TILE + 2;
+  return tiles * 4 + 256;
+}
+
+int tt_shard_select_owned(const int32_t* ids_all, const int32_t* d_block, const int32_t* d_local_base, int64_t n_per_rank,
+                          int64_t n0, int32_t K0, int32_t K1, int32_t world, int32_t me, int32_t* rows_out, int32_t* slots_out,
+                          int32_t* d_n_owned, void* workspace, int64_t workspace_bytes, tt_stream_t stream) {
+  TT_CHECK_ARG(ids_all && d_block && d_local_base && rows_out && slots_out && d_n_owned && workspace, "tt_shard_select_owned: NULL pointer");
+  TT_CHECK_ARG(world > 0 && me >= 0 && me < world && n_per_rank > 0 && n0 >= 0 && n0 <= n_per_rank && K0 > 0, "tt_shard_select_owned: bad sizes");
+  TT_CHECK_ARG(n0 == n_per_rank || K1 > 0, "tt_shard_select_owned: K1 missing");
+  const int64_t n_total = n_per_rank * world;
+  TT_CHECK_ARG(n_total < (1ll << 31), "tt_shard_select_owned: too many ids for int32 slots");
+  TT_CHECK_ARG(workspace_bytes >= tt_shard_workspace_bytes(n_total), "tt_shard_select_owned: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  RouteMeta m{ids_all, d_block, d_local_base, n_total, n_per_rank, n0, K0, K1 > 0 ? K1 : 1, me};
+  const int n_tiles = (int)((n_total + RT_TILE - 1) / RT_TILE);
+  int32_t* counts = (int32_t*)workspace;
+  route_count_kernel<<<n_tiles, RT_THREADS, 0, s>>>(m, counts, n_tiles);
+  scan_exclusive_small_kernel<<<1, 1024, 0, s>>>(counts, n_tiles + 1);
+  route_compact_kernel<<<n_tiles, RT_THREADS, 0, s>>>(m, counts, n_tiles, rows_out, slots_out, d_n_owned);
+  TT_LAUNCH_CHECK("shard_select_owned");
+  return TT_OK;
+}
+
+int tt_ebc_push_rows(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
+                     int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
+                     int64_t ld1, int64_t col0_0, int64_t col0_1, int32_t out_dtype, tt_stream_t stream) {
+  TT_CHECK_ARG(arena && rows && slots && d_n_owned && dst_table && E > 0 && (E % 4) == 0, "tt_ebc_push_rows: bad arguments");
+  TT_CHECK_ARG(out_dtype == TT_F32 || out_dtype == TT_BF16, "tt_ebc_push_rows: bad dtype");
+  int g = 1;
+  while (g < (E >> 2) && g < 32) g <<= 1;
+  int64_t want = ceil_div(capacity, 256 / g);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_dtype == TT_F32)
+    push_rows_kernel<float><<<grid, 256, 0, s>>>(arena, E, g, rows, slots, d_n_owned, dst_table, n_per_rank, n0, K0, K1 > 0 ? K1 : 1,
+                                                 ld0, ld1, col0_0, col0_1);
+  else
+    push_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(arena, E, g, rows, slots, d_n_owned, dst_table, n_per_rank, n0, K0,
+                                                         K1 > 0 ? K1 : 1, ld0, ld1, col0_0, col0_1);
+  TT_LAUNCH_CHECK("push_rows_kernel");
+  return TT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+"""Multi-GPU two-tower step: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch) for the
+plumbing, our own kernels over peer-mapped memory for the embedding exchange.
+
+The reference is single-GPU (no torch.distributed anywhere); the oracle for everything here is the
+single-device step on the concatenated global batch.
+
+Per step and rank (B_l local samples, B_g = world * B_l):
+  ids        clamp -> NCCL all-gather of int32 ids (static size; also the barrier that separates steps)
+  lookup     tt_shard_select_owned (deterministic compaction of the ids this rank owns) -> tt_ebc_push_rows: rows are
+             gathered and stored directly into the requesters' concat buffers through peer pointers (fused lookup +
+             all-to-all) -> light barrier
+  towers     replicated dense weights; BatchNorm statistics all-reduced (SyncBN == BN on the global batch)
+  loss       all-gather both towers' embeddings; each rank owns its rows of S: row statistics are local, column
+             statistics are all-reduced; global diagonal = rank * B_l + i; loss means are over B_g
+  backward   dN from (local notice rows x all company columns), dC from (local company rows x all notice columns) —
+             the transposed problem, so no reduce-scatter is needed; dense grads all-reduced (flat buffer);
+  tables     sort-dedup of the owned ids, then the segment-sum kernel PULLS the pooled gradients out of the
+             requesters' buffers over NVLink (fused gradient all-to-all) and applies Adam to the local shard.
+"""
+from __future__ import annotations
+
+import math
+import threading
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import native
+from .engine import TwoTowerConfig, TwoTowerEngine, _Ws
+from .native import TT_ADAM_DENSE_EXACT, TT_F32, ptr
+
+
+# ------------------------------------------------------------------------------------------------ shard plan (pure integers)
+class ShardPlan:
+    """Row-wise shard map. block_k = ceil(V_k / world); owner = id // block_k; local = id - owner * block_k."""
+
+    def __init__(self, vocab: Sequence[int], world: int):
+        self.world = int(world)
+        self.vocab = [int(v) for v in vocab]
+        self.block = [-(-v // self.world) for v in self.vocab]
+        self.local_base = [0]
+        for b in self.block[:-1]:
+            self.local_base.append(self.local_base[-1] + b)
+        self.local_rows = sum(self.block)
+
+    def owner(self, k: int, idx: int) -> int:
+        return idx // self.block[k]
+
+    def local_row(self, k: int, idx: int) -> int:
+        return self.local_base[k] + idx - self.owner(k, idx) * self.block[k]
+
+    def shard_range(self, k: int, rank: int):
+        """global id range [lo, hi) of table k held by `rank` (may be empty for the last ranks of tiny tables)."""
+        lo = min(rank * self.block[k], self.vocab[k])
+        return lo, min(lo + self.block[k], self.vocab[k])
+
+
+# ------------------------------------------------------------------------------------------------ communicators
+class NcclComm:
+    """torch.distributed backend (NCCL). Peer-mapped buffers come from torch symmetric memory."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self._tiny = None
+
+    def all_gather(self, out: torch.Tensor, inp: torch.Tensor):
+        self.dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def all_reduce(self, t: torch.Tensor):
+        self.dist.all_reduce(t, group=self.group)
+
+    def barrier(self, device):
+        if self._tiny is None:
+            self._tiny = torch.zeros(1, dtype=torch.float32, device=device)
+        self.dist.all_reduce(self._tiny, group=self.group)
+
+    def peer_buffer(self, nbytes: int, device) -> "tuple[torch.Tensor, List[int]]":
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        hdl = symm_mem.rendezvous(t, self.group)
+        self._keep = getattr(self, "_keep", []) + [hdl]
+        return t, [int(p) for p in hdl.buffer_ptrs]
+
+
+class ThreadWorld:
+    """In-process emulation of `world` ranks on ONE GPU, one Python thread per rank; collectives are host-mediated
+    (no kernel ever waits on another), so it is safe on a single device. Used by the -m gpu tests to cover the N>1 path."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self.bar = threading.Barrier(world)
+        self.slots: List[Optional[torch.Tensor]] = [None] * world
+        self.ptrs: List[Optional[int]] = [None] * world
+
+
+class ThreadComm:
+    def __init__(self, tw: ThreadWorld, rank: int):
+        self.tw, self.world, self.rank = tw, tw.world, rank
+
+    def _exchange(self, t: torch.Tensor) -> List[torch.Tensor]:
+        torch.cuda.current_stream(t.device).synchronize()
+        self.tw.slots[self.rank] = t
+        self.tw.bar.wait()
+        got = list(self.tw.slots)
+        return got
+
+    def all_gather(self, out: torch.Tensor, inp: torch.Tensor):
+        got = self._exchange(inp)
+        n = inp.numel()
+        flat = out.view(-1)
+        for r, t in enumerate(got):
+            flat[r * n:(r + 1) * n].copy_(t.view(-1))
+        torch.cuda.current_stream(out.device).synchronize()
+        self.tw.bar.wait()
+
+    def all_reduce(self, t: torch.Tensor):
+        got = self._exchange(t)
+        acc = got[0].clone()
+        for o in got[1:]:
+            acc += o  # fixed rank order on every rank -> identical result everywhere
+        torch.cuda.current_stream(t.device).synchronize()
+        self.tw.bar.wait()
+        t.copy_(acc)
+        torch.cuda.current_stream(t.device).synchronize()
+        self.tw.bar.wait()
+
+    def barrier(self, device):
+        torch.cuda.current_stream(device).synchronize()
+        self.tw.bar.wait()
+
+    def peer_buffer(self, nbytes: int, device):
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.tw.ptrs[self.rank] = t.data_ptr()
+        self.tw.bar.wait()
+        ptrs = [int(p) for p in self.tw.ptrs]
+        self.tw.bar.wait()
+        return t, ptrs
+
+
+class SingleComm:
+    """world == 1: the sharded pipeline with itself as the only peer (exercises select/push/pull on one GPU)."""
+    world, rank = 1, 0
+
+    def all_gather(self, out, inp):
+        out.view(-1).copy_(inp.view(-1))
+
+    def all_reduce(self, t):
+        return None
+
+    def barrier(self, device):
+        return None
+
+    def peer_buffer(self, nbytes, device):
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        return t, [t.data_ptr()]
+
+
+# ------------------------------------------------------------------------------------------------ engine
+def _a256(n: int) -> int:
+    return (n + 255) // 256 * 256
+
+
+class DistributedEngine(TwoTowerEngine):
+    def __init__(self, cfg: TwoTowerConfig, device, comm, optimizer_mode: str = "dense_exact", value_layout: str = "sample_major",
+                 dtype: str = "fp32"):
+        self.comm = comm
+        self.world, self.rank = comm.world, comm.rank
+        self.full_cfg = cfg
+        self.plan = ShardPlan(list(cfg.notice_vocab) + list(cfg.company_vocab), self.world)
+        Kn = len(cfg.notice_keys)
+        # the local engine sees tables of block_k rows each (its shard); ids are routed before they reach it
+        local = TwoTowerConfig(cfg.notice_keys, cfg.company_keys, self.plan.block[:Kn], self.plan.block[Kn:], cfg.emb_dim,
+                               cfg.notice_dense_dim, cfg.company_dense_dim, cfg.hidden, cfg.final_dim, cfg.dropout,
+                               cfg.temperature, cfg.label_smoothing)
+        super().__init__(local, device, optimizer_mode, value_layout, dtype)
+        dev = self.device
+        self.vocab_global = torch.tensor(self.plan.vocab, dtype=torch.int32, device=dev)
+        self.block = torch.tensor(self.plan.block, dtype=torch.int32, device=dev)
+        self.local_base = torch.tensor(self.plan.local_base, dtype=torch.int32, device=dev)
+        self.rng_stream_base = 64 * self.rank
+        assert self.total_rows == self.plan.local_rows
+
+    # ---- workspace: concat / gradient buffers live in one peer-mapped allocation
+    def workspace(self, B: int) -> _Ws:
+        ws = self._ws.get(B)
+        if ws is not None:
+            return ws
+        cfg, dev, E, W = self.cfg, self.device, self.cfg.emb_dim, self.world
+        H0 = cfg.hidden[0]
+        ld = [H0 + self.K[t] * E for t in range(2)]
+        sizes = [_a256(B * ld[t] * 4) for t in range(2)]
+        total = 2 * (sizes[0] + sizes[1])
+        buf, peer = self.comm.peer_buffer(total, dev)
+        offs = [0, sizes[0], sizes[0] + sizes[1], 2 * sizes[0] + sizes[1]]
+        views = [buf[offs[i]:offs[i] + B * ld[i % 2] * 4].view(torch.float32).view(B, ld[i % 2]) for i in range(4)]
+        # build the generic workspace first, then swap the four buffers for the peer-mapped ones
+        ws = super().workspace(B)
+        ws.c, ws.dc = [views[0], views[1]], [views[2], views[3]]
+        ws.peer_buf = buf
+        ws.c_table = torch.tensor([p + offs[t] for p in peer for t in range(2)], dtype=torch.int64, device=dev)
+        ws.dc_table = torch.tensor([p + offs[2 + t] for p in peer for t in range(2)], dtype=torch.int64, device=dev)
+        n_l = B * (self.K[0] + self.K[1])
+        cap = n_l * W
+        i32 = dict(dtype=torch.int32, device=dev)
+        ws.ids_local = torch.zeros(n_l, **i32)
+        ws.ids_all = torch.zeros(cap, **i32)
+        ws.rows = torch.zeros(cap, **i32)          # owned local rows (compact)
+        ws.slots = torch.zeros(cap, **i32)         # their global slots
+        ws.sorted_rows = torch.zeros(cap, **i32)
+        ws.sorted_slots = torch.zeros(cap, **i32)
+        ws.n_owned = torch.zeros(1, **i32)
+        q = self.lib.query
+        ws.shard_ws = torch.empty(q("tt_shard_workspace_bytes", cap), dtype=torch.uint8, device=dev)
+        ws.sort_ws = torch.empty(q("tt_ebc_sort_workspace_bytes", cap, self.total_rows), dtype=torch.uint8, device=dev)
+        ws.piece_ws = torch.empty(q("tt_ebc_piece_workspace_bytes", cap, E), dtype=torch.uint8, device=dev)
+        Bg = B * W
+        f32 = dict(dtype=torch.float32, device=dev)
+        ws.e_all = [torch.empty(Bg, cfg.final_dim, dtype=self.emb_torch, device=dev) for _ in range(2)]
+        ws.col_sumexp = torch.empty(Bg, **f32)
+        ws.col_sum_s = torch.empty(Bg, **f32)
+        ws.inv_col = torch.empty(Bg, **f32)
+        ws.inv_row_all = torch.empty(Bg, **f32)
+        ws.sim_ws = torch.empty(q("tt_simce_workspace_bytes", Bg, Bg, cfg.final_dim), dtype=torch.uint8, device=dev)
+        return ws
+
+    # ---- forward pieces
+    def embedding_forward(self, ws: _Ws, values, layout: int):
+        E, B, s = self.cfg.emb_dim, ws.B, self._stream()
+        H0 = self.cfg.hidden[0]
+        K0, K1 = self.K
+        n0, n_l = B * K0, B * (K0 + K1)
+        if values[0] is None or values[1] is None:
+            raise NotImplementedError("the sharded lookup serves both towers in one exchange; call the train task, not a single tower")
+        self.profile_tag = "sharded"
+        self._call("tt_ebc_clamp_ids", ptr(values[0]), ptr(self.vocab_global), B, K0, layout, ptr(ws.ids_local), s)
+        self._call("tt_ebc_clamp_ids", ptr(values[1]), self.vocab_global.data_ptr() + 4 * K0, B, K1, layout,
+                   ws.ids_local.data_ptr() + 4 * n0, s)
+        self.comm.all_gather(ws.ids_all, ws.ids_local)
+        self._call("tt_shard_select_owned", ptr(ws.ids_all), ptr(self.block), ptr(self.local_base), n_l, n0, K0, K1, self.world,
+                   self.rank, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), ptr(ws.shard_ws), ws.shard_ws.numel(), s, n_kernels=3)
+        self._call("tt_ebc_push_rows", ptr(self.arena), E, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), n_l * self.world,
+                   ptr(ws.c_table), n_l, n0, K0, K1, H0 + K0 * E, H0 + K1 * E, H0, H0, self.act, s)
+        self.comm.barrier(self.device)  # every owner has finished writing into my concat buffers
+
+    def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int) -> int:
+        self.comm.all_reduce(sums[:n])
+        return local_count * self.world
+
+    def loss_forward(self, ws: _Ws):
+        cfg, B, s = self.cfg, ws.B, self._stream()
+        Bg, off = B * self.world, B * self.rank
+        self.profile_tag = ""
+        inv_t = 1.0 / cfg.temperature
+        self.comm.all_gather(ws.e_all[0], ws.e[0])
+        self.comm.all_gather(ws.e_all[1], ws.e[1])
+        self._call("tt_simce_forward", ptr(ws.e[0]), ptr(ws.e_all[1]), B, Bg, cfg.final_dim, self.emb_tt, inv_t, off,
+                   ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), ptr(ws.col_sum_s), ptr(ws.diag), ptr(ws.row_argmax),
+                   ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=3)
+        self.comm.all_reduce(ws.col_sumexp)
+        self.comm.all_reduce(ws.col_sum_s)
+        self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), ptr(ws.col_sum_s),
+                   ptr(ws.diag), ptr(ws.row_argmax), B, Bg, off, Bg, inv_t, cfg.label_smoothing, ptr(ws.inv_row),
+                   ptr(ws.inv_col), ptr(ws.partial), s)
+        self.comm.all_reduce(ws.partial)
+        self._call("tt_simce_scalars", ptr(ws.partial), Bg, ptr(ws.out5), s)
+        self.comm.all_gather(ws.inv_row_all, ws.inv_row)
+        return ws.out5
+
+    def loss_backward(self, ws: _Ws, dloss: float = 1.0):
+        cfg, B, s = self.cfg, ws.B, self._stream()
+        Bg, off = B * self.world, B * self.rank
+        self.profile_tag = ""
+        inv_t = 1.0 / cfg.temperature
+        gscale = dloss * 0.5 / Bg * inv_t
+        F = cfg.final_dim
+        self._call("tt_simce_backward", ptr(ws.e[0]), ptr(ws.e_all[1]), B, Bg, F, self.emb_tt, inv_t, off, ptr(ws.inv_row),
+                   ptr(ws.inv_col), gscale, cfg.label_smoothing, Bg, ptr(ws.de[0]), ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=2)
+        self._call("tt_simce_backward", ptr(ws.e[1]), ptr(ws.e_all[0]), B, Bg, F, self.emb_tt, inv_t, off,
+                   ws.inv_col.data_ptr() + 4 * off, ptr(ws.inv_row_all), gscale, cfg.label_smoothing, Bg, ptr(ws.de[1]),
+                   ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=2)
+
+    def reduce_dense_grads(self):
+        # also the barrier that guarantees every rank's pooled-gradient buffers are complete before anyone pulls from them
+        self.comm.all_reduce(self.dense_g)
+
+    def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool):
+        cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
+        K0, K1 = self.K
+        n0, n_l = B * K0, B * (K0 + K1)
+        cap = n_l * self.world
+        H0 = cfg.hidden[0]
+        self.profile_tag = "sharded"
+        self.stamp.add_(1)
+        self._call("tt_ebc_sort_rows", ptr(ws.rows), ptr(ws.slots), cap, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
+                   ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
+                   0, ptr(self.stamp), ptr(ws.n_owned), s, n_kernels=7)
+        if want_dense_grad and self.arena_grad is None:
+            self.arena_grad = torch.zeros_like(self.arena)
+        self._call("tt_ebc_backward_adam", ptr(self.arena) if apply_adam else 0, ptr(self.arena_m) if apply_adam else 0,
+                   ptr(self.arena_v) if apply_adam else 0, ptr(self.arena_grad) if want_dense_grad else 0,
+                   self.total_rows, E, ptr(ws.sorted_rows), ptr(ws.sorted_slots), cap, ptr(self.row_begin), ptr(self.row_end),
+                   ptr(self.row_stamp), 0, ptr(self.stamp), 0, H0 + K0 * E, H0, K0, n0, 0, H0 + K1 * E, H0, K1, n_l - n0,
+                   self.act, ptr(ws.piece_ws), ws.piece_ws.numel(), ptr(self.hyper),
+                   self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, ptr(ws.n_owned), ptr(ws.dc_table), n_l, s, n_kernels=2)
+
+    def similarity_matrix(self, ws: _Ws) -> torch.Tensor:
+        """This rank's rows of the global logits: [B_l, B_g]."""
+        B, Bg = ws.B, ws.B * self.world
+        S = torch.empty(B, Bg, dtype=torch.float32, device=self.device)
+        n, c = ws.e[0].float(), ws.e_all[1].float()
+        self._call("tt_similarity_matrix", ptr(n), ptr(c), B, Bg, self.cfg.final_dim, TT_F32, 1.0 / self.cfg.temperature, ptr(S),
+                   Bg, self._stream())
+        return S
+
+    # ---- full <-> sharded parameter exchange (reference-named state_dict lives on the full tables)
+    def load_full_tables(self, full_tables: Sequence[torch.Tensor]):
+        """full_tables[k]: [V_k, E] for notice keys then company keys; copies this rank's shard into the local arena."""
+        self.arena.zero_()
+        for k, tab in enumerate(full_tables):
+            lo, hi = self.plan.shard_range(k, self.rank)
+            if hi > lo:
+                b = self.plan.local_base[k]
+                self.arena[b:b + hi - lo].copy_(tab[lo:hi])
+
+    def gather_full_tables(self, which: str = "w") -> List[torch.Tensor]:
+        src = {"w": self.arena, "m": self.arena_m, "v": self.arena_v}[which]
+        allsh = torch.empty(self.world * src.numel(), dtype=src.dtype, device=self.device)
+        self.comm.all_gather(allsh, src.contiguous().view(-1))
+        allsh = allsh.view(self.world, self.total_rows, self.cfg.emb_dim)
+        out = []
+        for k, v in enumerate(self.plan.vocab):
+            b, blk = self.plan.local_base[k], self.plan.block[k]
+            out.append(allsh[:, b:b + blk].reshape(-1, self.cfg.emb_dim)[:v].clone())
+        return out
+
+
+def create_distributed_train_task(notice_keys, company_keys, schema: dict, model: dict, device, comm=None, dtype: str = "bf16",
+                                  optimizer_mode: str = "dense_exact", seed_full_init: bool = True):
+    """Build the façade on a DistributedEngine. `schema` = {"notice": [[key, vocab], ...], "company": [...]};
+    `model` has emb_dim / notice_dense / company_dense / hidden / final_dim / dropout / temperature.
+    With seed_full_init every rank draws the full tables with the current torch RNG (same on every rank) and keeps its
+    shard, so the initial weights equal a single-GPU model built with the same seed."""
+    import torch.nn as nn
+    from .modules import TwoTowerModel, TwoTowerTrainTask, _init_like_reference
+    if comm is None:
+        comm = NcclComm()
+    nv = [int(dict(schema["notice"])[k]) for k in notice_keys]
+    cv = [int(dict(schema["company"])[k]) for k in company_keys]
+    cfg = TwoTowerConfig(list(notice_keys), list(company_keys), nv, cv, model["emb_dim"], model["notice_dense"],
+                         model["company_dense"], list(model["hidden"]), model["final_dim"], model.get("dropout", 0.0),
+                         model.get("temperature", 1.0), model.get("label_smoothing", 0.0))
+    eng = DistributedEngine(cfg, device, comm, optimizer_mode, "sample_major", dtype)
+    # same RNG consumption order as the single-GPU factory: all notice tables, notice dense layers, then company
+    full = []
+    E = cfg.emb_dim
+    for t in range(2):
+        name, keys, vocab, dense_dim = cfg.tower(t)
+        pre = f"{name}_tower."
+        for v in vocab:
+            full.append(nn.Embedding(v, E).weight.detach())
+        lin = nn.Linear(dense_dim, cfg.hidden[0])
+        eng.dense(pre + "dense_projection.weight").copy_(lin.weight.detach())
+        eng.dense(pre + "dense_projection.bias").copy_(lin.bias.detach())
+        width, idx = cfg.hidden[0] + len(keys) * E, 0
+        for h in cfg.hidden[1:]:
+            lin = nn.Linear(width, h)
+            eng.dense(pre + f"mlp.{idx}.weight").copy_(lin.weight.detach())
+            eng.dense(pre + f"mlp.{idx}.bias").copy_(lin.bias.detach())
+            eng.dense(pre + f"mlp.{idx + 2}.weight").fill_(1.0)
+            eng.dense(pre + f"mlp.{idx + 2}.bias").zero_()
+            width, idx = h, idx + 4
+        lin = nn.Linear(width, cfg.final_dim)
+        eng.dense(pre + f"mlp.{idx}.weight").copy_(lin.weight.detach())
+        eng.dense(pre + f"mlp.{idx}.bias").copy_(lin.bias.detach())
+    eng.load_full_tables(full)
+    del full
+    model_mod = TwoTowerModel(eng)
+    return TwoTowerTrainTask(model_mod, temperature=cfg.temperature, label_smoothing=cfg.label_smoothing)
+
+
+def load_reference_state_dict(task, sd: Dict[str, torch.Tensor]):
+    """Scatter a reference-named (full-table) state_dict into a task built on a DistributedEngine."""
+    eng: DistributedEngine = task.engine
+    cfg = eng.full_cfg
+    full = []
+    for t in range(2):
+        name, keys, _, _ = cfg.tower(t)
+        for k in keys:
+            full.append(sd[f"two_tower_model.{name}_tower.categorical_embedder.embeddings.{k}.weight"].to(eng.device))
+    eng.load_full_tables(full)
+    own = task.state_dict()
+    for k, v in sd.items():
+        if ".embeddings." in k:
+            continue
+        own[k].copy_(v.to(eng.device))
+
+
+def gather_reference_state_dict(task) -> Dict[str, torch.Tensor]:
+    """All-gather the shards back into the reference's state_dict names (SURVEY.md §5 checkpoint compatibility)."""
+    eng: DistributedEngine = task.engine
+    cfg = eng.full_cfg
+    tabs = eng.gather_full_tables("w")
+    out, i = {}, 0
+    for k, v in task.state_dict().items():
+        if ".embeddings." in k:
+            continue
+        out[k] = v.detach().clone()
+    for t in range(2):
+        name, keys, _, _ = cfg.tower(t)
+        for k in keys:
+            out[f"two_tower_model.{name}_tower.categorical_embedder.embeddings.{k}.weight"] = tabs[i]
+            i += 1
+    return out

@@ -142,6 +142,7 @@ class TwoTowerEngine:
         self.row_stamp = torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
         self._ws: Dict[int, _Ws] = {}
         self.rng_seed = 0x5EED
+        self.rng_stream_base = 0  # distributed engines offset it by rank so ranks draw different dropout masks
         self.launches = 0  # kernels launched through the C ABI (bench.py's gpu_launches)
         self.profile: Optional[list] = None  # set to [] to collect (tag, n_kernels, ev0, ev1) per C-ABI call
         self.profile_tag = ""
@@ -242,9 +243,29 @@ class TwoTowerEngine:
         if dense.device != self.device or values.device != self.device:
             raise ValueError(f"{name} inputs must live on {self.device}")
 
-    def tower_forward(self, t: int, ws: _Ws, dense: torch.Tensor, values: torch.Tensor, train: bool,
-                      layout: int = TT_LAYOUT_SAMPLE_MAJOR, bag_offsets: Optional[torch.Tensor] = None,
-                      masks: Optional[Sequence[torch.Tensor]] = None):
+    def embedding_forward(self, ws: _Ws, values: Sequence[Optional[torch.Tensor]], layout: int):
+        """Pooled lookup of every key of the given towers (None = skip) straight into the concat buffers; also records
+        the clamped arena rows for the backward. One id per bag, like the reference (unified_bid_data_loader.py:835);
+        jagged bags go through ops.ebc_forward."""
+        E, B, s = self.cfg.emb_dim, ws.B, self._stream()
+        H0 = self.cfg.hidden[0]
+        for t, v in enumerate(values):
+            if v is None:
+                continue
+            K = self.K[t]
+            k0 = 0 if t == 0 else self.K[0]
+            rows_off = 0 if t == 0 else B * self.K[0]
+            self.profile_tag = self.cfg.tower(t)[0]
+            self._call("tt_ebc_forward", ptr(self.arena), self.row_base.data_ptr() + 8 * k0, self.vocab.data_ptr() + 4 * k0,
+                       ptr(v), 0, B * K, B, K, E, layout, ptr(ws.c[t]), self.act, H0 + K * E, H0,
+                       ws.rows.data_ptr() + 4 * rows_off, 0, 0, s)
+
+    def tower_forward(self, t: int, ws: _Ws, dense: torch.Tensor, values: Optional[torch.Tensor], train: bool,
+                      layout: int = TT_LAYOUT_SAMPLE_MAJOR, masks: Optional[Sequence[torch.Tensor]] = None):
+        """Dense projection + MLP + L2 norm of one tower. If `values` is given the embedding lookup of this tower is
+        done here first (stand-alone tower call); the train step looks both towers up front via embedding_forward."""
+        if values is not None:
+            self.embedding_forward(ws, [values if i == t else None for i in range(2)], layout)
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
         name, keys, _, dense_dim = cfg.tower(t)
         self.profile_tag = name
@@ -256,13 +277,6 @@ class TwoTowerEngine:
         dense = dense.contiguous()
         if dense.dtype != torch.float32:
             dense = dense.float()
-        rows_off = 0 if t == 0 else B * self.K[0]
-        if bag_offsets is not None:
-            raise NotImplementedError("jagged bags go through ops.ebc_forward; the train step uses one id per bag "
-                                      "like the reference (unified_bid_data_loader.py:835)")
-        self._call("tt_ebc_forward", ptr(self.arena), self.row_base.data_ptr() + 8 * k0, self.vocab.data_ptr() + 4 * k0,
-                   ptr(values), 0, B * K, B, K, E, layout, ptr(ws.c[t]), self.act, ld, H0,
-                   ws.rows.data_ptr() + 4 * rows_off, 0, 0, s)
         self._call("tt_linear_forward", ptr(dense), dense_dim, ptr(self.dense(pre + "dense_projection.weight")),
                    ptr(self.dense(pre + "dense_projection.bias")), ptr(ws.c[t]), ld, B, H0, dense_dim, self.act, 0, s)
         x, width, idx = ws.c[t], ld, 0
@@ -284,7 +298,7 @@ class TwoTowerEngine:
                 p = 0.0
             mask = masks[bi] if (masks is not None and p > 0) else None
             self._call("tt_bn_apply", ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean), ptr(ws.rstd[t][bi]), ptr(gamma),
-                       ptr(beta), p, ptr(mask), ptr(self.hyper), t * 16 + bi, ptr(ws.y[t][bi]), h, s)
+                       ptr(beta), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.y[t][bi]), h, s)
             x, width, idx = ws.y[t][bi], h, idx + 4
         F = cfg.final_dim
         self._call("tt_linear_forward", ptr(x), width, ptr(self.dense(pre + f"mlp.{idx}.weight")),
@@ -322,8 +336,9 @@ class TwoTowerEngine:
         lay = TT_LAYOUT_KEY_MAJOR if (layout or self.default_layout) == "key_major" else TT_LAYOUT_SAMPLE_MAJOR
         ws = self.workspace(B)
         ws.inputs = (notice_dense.contiguous(), company_dense.contiguous())
-        self.tower_forward(0, ws, notice_dense, notice_values, train, lay, masks=None if masks is None else masks[0])
-        self.tower_forward(1, ws, company_dense, company_values, train, lay, masks=None if masks is None else masks[1])
+        self.embedding_forward(ws, [notice_values, company_values], lay)
+        self.tower_forward(0, ws, notice_dense, None, train, lay, masks=None if masks is None else masks[0])
+        self.tower_forward(1, ws, company_dense, None, train, lay, masks=None if masks is None else masks[1])
         out5 = self.loss_forward(ws)
         ws.train = train
         ws.masks = masks
@@ -369,11 +384,11 @@ class TwoTowerEngine:
             mean = ws.mean[t][bi] if train else self.bn_rm[t][bi]
             gamma = self.dense(pre + f"mlp.{idx + 2}.weight")
             self._call("tt_bn_backward_reduce", ptr(ws.dy[t][bi]), h, ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean),
-                       ptr(ws.rstd[t][bi]), p, ptr(mask), ptr(self.hyper), t * 16 + bi, ptr(ws.bn_sums[t]),
+                       ptr(ws.rstd[t][bi]), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.bn_sums[t]),
                        ptr(ws.bn_ws[t]), ws.bn_ws[t].numel(), s, n_kernels=2)
             count = self.bn_allreduce(ws.bn_sums[t], 2 * h, B)
             self._call("tt_bn_backward_apply", ptr(ws.dy[t][bi]), h, ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean),
-                       ptr(ws.rstd[t][bi]), ptr(gamma), p, ptr(mask), ptr(self.hyper), t * 16 + bi, ptr(ws.bn_sums[t]),
+                       ptr(ws.rstd[t][bi]), ptr(gamma), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.bn_sums[t]),
                        count, 1 if train else 0, ptr(self.dense(pre + f"mlp.{idx + 2}.weight", "g")),
                        ptr(self.dense(pre + f"mlp.{idx + 2}.bias", "g")), ptr(ws.dh[t][bi]), h, s)
             xin = ws.y[t][bi - 1] if bi > 0 else ws.c[t]
@@ -401,7 +416,7 @@ class TwoTowerEngine:
         self.stamp.add_(1)
         self._call("tt_ebc_sort_rows", ptr(ws.rows), 0, n, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
                    ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
-                   0, ptr(self.stamp), s, n_kernels=7)
+                   0, ptr(self.stamp), 0, s, n_kernels=7)
         if want_dense_grad and self.arena_grad is None:
             self.arena_grad = torch.zeros_like(self.arena)
         self._call("tt_ebc_backward_adam", ptr(self.arena) if apply_adam else 0, ptr(self.arena_m) if apply_adam else 0,
@@ -409,7 +424,7 @@ class TwoTowerEngine:
                    self.total_rows, E, ptr(ws.sorted_rows), ptr(ws.sorted_slots), n, ptr(self.row_begin), ptr(self.row_end),
                    ptr(self.row_stamp), 0, ptr(self.stamp), ptr(ws.dc[0]), H0 + self.K[0] * E, H0, self.K[0], n0,
                    ptr(ws.dc[1]), H0 + self.K[1] * E, H0, self.K[1], n1, self.act, ptr(ws.piece_ws), ws.piece_ws.numel(),
-                   ptr(self.hyper), self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, s, n_kernels=2)
+                   ptr(self.hyper), self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, 0, 0, 0, s, n_kernels=2)
 
     def backward(self, ws: _Ws, dloss: float = 1.0):
         self.loss_backward(ws, dloss)
@@ -431,9 +446,14 @@ class TwoTowerEngine:
         self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
         out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks)
         self.backward(ws)
+        self.reduce_dense_grads()
         self.embedding_backward(ws, apply_adam=True, want_dense_grad=False)
         self.dense_adam()
         return out5
+
+    def reduce_dense_grads(self):
+        """Single GPU: nothing. Distributed engines all-reduce the flat dense gradient buffer here."""
+        return None
 
     def hyper_host(self) -> dict:
         import struct

@@ -238,6 +238,7 @@ class _TrainStepFn(torch.autograd.Function):
         if task._fused_opt is not None:
             # backward + sort-dedup + fused Adam all inside the library; upstream gradient is taken as 1
             eng.backward(ws, 1.0)
+            eng.reduce_dense_grads()
             eng.embedding_backward(ws, apply_adam=True, want_dense_grad=False)
             eng.dense_adam()
             return (None,) * 8  # 7 plain arguments + the anchor
