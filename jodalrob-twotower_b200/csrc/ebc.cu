@@ -295,21 +295,23 @@ __device__ __forceinline__ float4 load_grad_vec(const GradSrc& s, int32_t slot, 
   }
 }
 
-// acc += sum_{i in [lo,hi)} grad(sslot[i]) in ascending i, with 8 independent (possibly peer/NVLink) loads in flight
+// acc += sum_{i in [lo,hi)} grad(sslot[i]) in ascending i.  Full batches of 8 issue their (possibly peer / NVLink)
+// loads unconditionally before the first add, so 8 gathers are in flight; the tail is a plain loop.
 template <typename GT>
 __device__ __forceinline__ void gather_sum(float4& acc, const int32_t* __restrict__ sslot, int64_t lo, int64_t hi,
                                            const GradSrc& src, int E, int c) {
-  for (int64_t i = lo; i < hi; i += 8) {
+  int64_t i = lo;
+  for (; i + 8 <= hi; i += 8) {
     int32_t sl[8];
     float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) sl[u] = (i + u < hi) ? __ldg(sslot + i + u) : -1;
+    for (int u = 0; u < 8; ++u) sl[u] = __ldg(sslot + i + u);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = sl[u] >= 0 ? load_grad_vec<GT>(src, sl[u], E, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < 8; ++u) v[u] = load_grad_vec<GT>(src, sl[u], E, c);
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (sl[u] >= 0) f4_add(acc, v[u]);
+    for (int u = 0; u < 8; ++u) f4_add(acc, v[u]);
   }
+  for (; i < hi; ++i) f4_add(acc, load_grad_vec<GT>(src, __ldg(sslot + i), E, c));
 }
 
 // level 1 for long rows: one lane group per chunk of SEG_CHUNK sorted entries

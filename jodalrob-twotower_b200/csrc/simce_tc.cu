@@ -11,8 +11,8 @@
 // Column statistics / the other tower's gradient come from running the same kernel on the transposed problem
 // (X and Y swapped), so no cross-CTA column reduction and no atomics: everything is deterministic.
 //
-// Warp roles (224 threads): warps 0-3 epilogue (TMEM lane quarter == warp id), warp 4 MMA issuer + TMEM
-// allocator, warps 5-6 operand loaders (TMA: one elected lane issues cp.async.bulk.tensor with 128B swizzle;
+// Warp roles (352 threads): warps 0-7 epilogue (TMEM lane quarter == warp % 4, column half == warp / 4), warp 8 MMA
+// issuer + TMEM allocator, warps 9-10 operand loaders (TMA: one elected lane issues cp.async.bulk.tensor with 128B swizzle;
 // the generic-proxy fallback loads 16-byte chunks and applies the same swizzle by hand).
 // Pipelines: Y tiles through a 3-stage smem ring (full/empty mbarriers), S through 2 TMEM buffers, dS through
 // 2 smem buffers; tcgen05.commit arrives on the barriers when the MMAs that read a buffer have retired.
@@ -25,8 +25,9 @@ namespace tt {
 constexpr int TCM = 128;          // rows per CTA block (UMMA M)
 constexpr int TCN = 128;          // columns per tile  (UMMA N)
 constexpr int TC_STAGES = 3;      // Y smem ring
-constexpr int TC_THREADS = 224;   // 4 epilogue + 1 mma + 2 loader warps
-constexpr int TC_EPI_THREADS = 128;
+constexpr int TC_EPI_WARPS = 8;   // two per SM sub-partition: rows = TMEM lane quarter (warp % 4), column half = warp / 4
+constexpr int TC_MMA_WARP = 8;
+constexpr int TC_THREADS = 352;   // 8 epilogue + 1 mma + 2 loader warps
 constexpr int TC_LOADER_THREADS = 64;
 constexpr int ATOM_BYTES = TCM * 128;  // one 128-row x 64-bf16 swizzle atom = 16 KB
 
@@ -154,6 +155,7 @@ struct TcSmem {  // carved from dynamic smem after the 1024-aligned tiles
   uint64_t p_full[2], p_empty[2];
   uint64_t d_full, d_empty;
   uint32_t tmem_base;
+  alignas(16) float iy[2 * TCN];
 };
 
 // copy a [128 x F] bf16 row-major tile (rows row0.. of G, zero past `rows`) into 128B-swizzled K-major atoms
@@ -182,6 +184,73 @@ __device__ __forceinline__ void manual_tile_load(unsigned char* dst, const __nv_
   }
 }
 
+// ---- epilogue helpers -------------------------------------------------------------------------------
+// row statistics of 32 logits (forward).  GENERIC handles ragged column tiles and the diagonal.
+template <bool GENERIC>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int64_t cbase, const TcParams& p, int64_t dcol, float (&acc)[4],
+                                          float& best, int32_t& best_j, float& dval, bool& have_diag) {
+  float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float raw = __uint_as_float(r[j]);
+    if (GENERIC) {
+      const int64_t col = cbase + j;
+      if (col < p.By) {
+        acc[j & 3] += ex2f(fmaf(raw, p.c1, p.c0));
+        m4[j & 3] = fmaxf(m4[j & 3], raw);
+        if (col == dcol) {
+          dval = raw;
+          have_diag = true;
+        }
+      }
+    } else {
+      acc[j & 3] += ex2f(fmaf(raw, p.c1, p.c0));
+      m4[j & 3] = fmaxf(m4[j & 3], raw);
+    }
+  }
+  const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  if (m > best) {  // rare after the first few chunks: locate the first column that attains the chunk maximum
+    best = m;
+    int32_t jj = 31;
+#pragma unroll
+    for (int j = 31; j >= 0; --j)
+      if (__uint_as_float(r[j]) == m && (!GENERIC || cbase + j < p.By)) jj = j;
+    best_j = (int32_t)(cbase + jj);
+  }
+}
+
+// dS for 32 logits -> bf16, written as four 16-byte chunks of this row into the swizzled K-major P tile
+template <bool GENERIC>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], int64_t cbase, int c_in_tile, const TcParams& p, int64_t dcol,
+                                          bool row_ok, float ixs, const float* __restrict__ s_iy, unsigned char* prow, int rsw) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16-byte chunk
+    const float4 a = *reinterpret_cast<const float4*>(s_iy + c_in_tile + q * 8);
+    const float4 b = *reinterpret_cast<const float4*>(s_iy + c_in_tile + q * 8 + 4);
+    const float iy[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float d[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = q * 8 + u;
+      const float e = ex2f(fmaf(__uint_as_float(r[j]), p.c1, p.c0));
+      float v = fmaf(e, ixs + iy[u], -p.tgt_off2);
+      if (GENERIC) {
+        if (cbase + j == dcol) v = fmaf(e, ixs + iy[u], -p.tgt_diag2);
+        if (cbase + j >= p.By || !row_ok) v = 0.f;
+      }
+      d[u] = v;
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(d[2 * u], d[2 * u + 1]);
+      w[u] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    const int cc = ((c_in_tile & 63) >> 3) + q;  // 16-byte chunk index inside the 64-column atom
+    *reinterpret_cast<uint4*>(prow + ((cc ^ rsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const TcParams p) {
@@ -206,15 +275,15 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb->s_full[i], 1);
-      mbar_init(&sb->s_empty[i], TC_EPI_THREADS);
-      mbar_init(&sb->p_full[i], TC_EPI_THREADS);
+      mbar_init(&sb->s_empty[i], TC_EPI_WARPS);
+      mbar_init(&sb->p_full[i], TC_EPI_WARPS);
       mbar_init(&sb->p_empty[i], 1);
     }
     mbar_init(&sb->d_full, 1);
-    mbar_init(&sb->d_empty, TC_EPI_THREADS);
+    mbar_init(&sb->d_empty, TC_EPI_WARPS);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(&sb->tmem_base, 512);
+  if (warp == TC_MMA_WARP) tmem_alloc(&sb->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -222,12 +291,9 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const uint32_t tmem_s[2] = {tmem, tmem + TCN};
   const uint32_t tmem_d = tmem + 2 * TCN;
 
-  const int n_row_blocks = (int)((p.Bx + TCM - 1) / TCM);
-  (void)n_row_blocks;
-
-  if (warp >= 5) {
+  if (warp > TC_MMA_WARP) {
     // =========================== operand loaders ===========================
-    const int lt = threadIdx.x - 5 * 32;
+    const int lt = threadIdx.x - (TC_MMA_WARP + 1) * 32;
     uint32_t x_phase = 0, y_iter = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int rb = item / p.n_chunks, ch = item - rb * p.n_chunks;
@@ -262,7 +328,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == TC_MMA_WARP) {
     // =========================== MMA issuer (one lane) ===========================
     if (lane == 0) {
       const uint32_t idesc1 = make_idesc(TCM, TCN, 0, 0);
@@ -319,9 +385,13 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
     }
   } else {
-    // =========================== epilogue warps 0-3: thread == one row of the block ===========================
-    const int r_in_blk = warp * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    // =========================== epilogue warps 0-7 ===========================
+    // thread == one row of the block (TMEM lane quarter = warp % 4) and one 64-column half of every tile (warp / 4)
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r_in_blk = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int et = threadIdx.x;  // 0..255
+    float* s_iy = sb->iy;        // [2][128] gscale * inv_y of the current tiles (backward)
     uint32_t s_iter = 0, p_iter = 0, d_phase = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int rb = item / p.n_chunks, ch = item - rb * p.n_chunks;
@@ -329,113 +399,78 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const int t1 = min(t0 + p.tiles_per_chunk, p.n_col_tiles);
       const int64_t row = (int64_t)rb * TCM + r_in_blk;
       const bool row_ok = row < p.Bx;
+      const bool rows_full = (int64_t)rb * TCM + TCM <= p.Bx;
       const int64_t dcol = p.diag_offset + row;  // this row's positive column
-      float acc_e = 0.f, acc_s = 0.f, best = -FLT_MAX, dval = 0.f;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float best = -FLT_MAX, dval = 0.f;
       int32_t best_j = 0x7fffffff;
       bool have_diag = false;
-      float ixs = 0.f;
-      if (BWD) ixs = row_ok ? p.gscale * p.inv_x[row] : 0.f;
+      float ixs = 0.f, iy_next = 0.f;
+      if (BWD) {
+        ixs = row_ok ? p.gscale * p.inv_x[row] : 0.f;
+        if (et < TCN) {
+          const int64_t c = (int64_t)t0 * TCN + et;
+          iy_next = c < p.By ? p.gscale * p.inv_y[c] : 0.f;
+        }
+      }
       for (int t = t0; t < t1; ++t, ++s_iter) {
         const int sbuf = s_iter & 1;
         const int64_t col0 = (int64_t)t * TCN;
         const bool partial = col0 + TCN > p.By;
         const bool diag_tile = (p.diag_offset + (int64_t)rb * TCM < col0 + TCN) && (p.diag_offset + (int64_t)rb * TCM + TCM > col0);
-        mbar_wait(&sb->s_full[sbuf], (s_iter >> 1) & 1);
-        tc_fence_after();
+        const bool generic = partial || diag_tile || (BWD && !rows_full);
         int pb = 0;
         if (BWD) {
+          // publish this tile's column scales, prefetch the next tile's
+          if (et < TCN) s_iy[sbuf * TCN + et] = iy_next;
+          asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+          if (et < TCN && t + 1 < t1) {
+            const int64_t c = col0 + TCN + et;
+            iy_next = c < p.By ? p.gscale * p.inv_y[c] : 0.f;
+          }
           pb = p_iter & 1;
           mbar_wait(&sb->p_empty[pb], ((p_iter >> 1) & 1) ^ 1);
         }
-#pragma unroll 1
-        for (int c32 = 0; c32 < TCN / 32; ++c32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_s[sbuf] + lane_addr + c32 * 32, r);
-          tmem_ld_wait();
-          const int64_t cbase = col0 + c32 * 32;
-          if (!BWD) {
-            if (!partial && !diag_tile) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float raw = __uint_as_float(r[j]);
-                acc_e += ex2f(fmaf(raw, p.c1, p.c0));
-                acc_s += raw;
-                if (raw > best) {
-                  best = raw;
-                  best_j = (int32_t)(cbase + j);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float raw = __uint_as_float(r[j]);
-                const int64_t col = cbase + j;
-                if (col < p.By) {
-                  acc_e += ex2f(fmaf(raw, p.c1, p.c0));
-                  acc_s += raw;
-                  if (raw > best) {
-                    best = raw;
-                    best_j = (int32_t)col;
-                  }
-                  if (col == dcol) {
-                    dval = raw;
-                    have_diag = true;
-                  }
-                }
-              }
-            }
+        mbar_wait(&sb->s_full[sbuf], (s_iter >> 1) & 1);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t ta = tmem_s[sbuf] + lane_addr + half * 64;
+        tmem_ld32(ta, r0);
+        tmem_ld32(ta + 32, r1);
+        tmem_ld_wait();
+        const int64_t cb = col0 + half * 64;
+        if (!BWD) {
+          if (generic) {
+            fwd_chunk<true>(r0, cb, p, dcol, acc, best, best_j, dval, have_diag);
+            fwd_chunk<true>(r1, cb + 32, p, dcol, acc, best, best_j, dval, have_diag);
           } else {
-            uint32_t packed[16];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float4 iy = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (!partial) iy = __ldg(reinterpret_cast<const float4*>(p.inv_y + cbase) + j4);
-              else {
-                if (cbase + j4 * 4 + 0 < p.By) iy.x = p.inv_y[cbase + j4 * 4 + 0];
-                if (cbase + j4 * 4 + 1 < p.By) iy.y = p.inv_y[cbase + j4 * 4 + 1];
-                if (cbase + j4 * 4 + 2 < p.By) iy.z = p.inv_y[cbase + j4 * 4 + 2];
-                if (cbase + j4 * 4 + 3 < p.By) iy.w = p.inv_y[cbase + j4 * 4 + 3];
-              }
-              const float iyv[4] = {iy.x, iy.y, iy.z, iy.w};
-              float d[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int j = j4 * 4 + q;
-                const float raw = __uint_as_float(r[j]);
-                const float e = ex2f(fmaf(raw, p.c1, p.c0));
-                float v = fmaf(e, fmaf(p.gscale, iyv[q], ixs), -p.tgt_off2);
-                if (diag_tile && (cbase + j == dcol)) v = fmaf(e, fmaf(p.gscale, iyv[q], ixs), -p.tgt_diag2);
-                if (partial && (cbase + j >= p.By)) v = 0.f;
-                d[q] = row_ok ? v : 0.f;
-              }
-              __nv_bfloat162 lo = __floats2bfloat162_rn(d[0], d[1]);
-              __nv_bfloat162 hi = __floats2bfloat162_rn(d[2], d[3]);
-              packed[j4 * 2 + 0] = *reinterpret_cast<uint32_t*>(&lo);
-              packed[j4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
-            }
-            // 32 columns = four 16-byte chunks of this row inside atom (c32 / 2)
-            unsigned char* prow = sP + pb * 2 * ATOM_BYTES + (c32 >> 1) * ATOM_BYTES + r_in_blk * 128;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int cc = (c32 & 1) * 4 + q;
-              *reinterpret_cast<uint4*>(prow + ((cc ^ (r_in_blk & 7)) << 4)) =
-                  make_uint4(packed[q * 4 + 0], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
-            }
+            fwd_chunk<false>(r0, cb, p, dcol, acc, best, best_j, dval, have_diag);
+            fwd_chunk<false>(r1, cb + 32, p, dcol, acc, best, best_j, dval, have_diag);
           }
+        } else {
+          unsigned char* prow = sP + pb * 2 * ATOM_BYTES + half * ATOM_BYTES + r_in_blk * 128;
+          const float* iy = s_iy + sbuf * TCN;
+          if (generic) {
+            bwd_chunk<true>(r0, cb, half * 64, p, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
+            bwd_chunk<true>(r1, cb + 32, half * 64 + 32, p, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
+          } else {
+            bwd_chunk<false>(r0, cb, half * 64, p, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
+            bwd_chunk<false>(r1, cb + 32, half * 64 + 32, p, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
+          }
+          fence_proxy_async();
         }
         tc_fence_before();
-        mbar_arrive(&sb->s_empty[sbuf]);
-        if (BWD) {
-          fence_proxy_async();
-          mbar_arrive(&sb->p_full[pb]);
-          ++p_iter;
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sb->s_empty[sbuf]);
+          if (BWD) mbar_arrive(&sb->p_full[pb]);
         }
+        if (BWD) ++p_iter;
       }
       if (!BWD) {
         if (row_ok) {
-          const int64_t o = (int64_t)ch * p.Bx + row;
-          p.row_e[o] = acc_e;
-          p.row_s[o] = acc_s * p.inv_temp;
+          const int64_t o = ((int64_t)ch * 2 + half) * p.Bx + row;
+          p.row_e[o] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
           if (p.want_metrics) {
             p.row_max[o] = best * p.inv_temp;
             p.row_arg[o] = best_j;
@@ -446,10 +481,11 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         mbar_wait(&sb->d_full, d_phase);
         d_phase ^= 1;
         tc_fence_after();
-        float* out = p.dx_part + ((int64_t)ch * p.Bx + row) * p.F;
-        for (int c32 = 0; c32 < (p.F >> 5); ++c32) {
+        const int fh = p.F >> 1;  // this warp's half of the F output columns
+        float* out = p.dx_part + ((int64_t)ch * p.Bx + row) * p.F + half * fh;
+        for (int c32 = 0; c32 < (fh >> 5); ++c32) {
           uint32_t r[32];
-          tmem_ld32(tmem_d + lane_addr + c32 * 32, r);
+          tmem_ld32(tmem_d + lane_addr + half * fh + c32 * 32, r);
           tmem_ld_wait();
           if (row_ok) {
 #pragma unroll
@@ -460,31 +496,30 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
         }
         tc_fence_before();
-        mbar_arrive(&sb->d_empty);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb->d_empty);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
 }
 
 // ---------------------------------------------------------------- small deterministic reductions
-__global__ void tc_rows_reduce_kernel(const float* __restrict__ row_e, const float* __restrict__ row_s,
-                                      const float* __restrict__ row_max, const int32_t* __restrict__ row_arg, int64_t Bx,
-                                      int n_chunks, float* __restrict__ out_e, float* __restrict__ out_s,
-                                      int32_t* __restrict__ out_arg) {
+__global__ void tc_rows_reduce_kernel(const float* __restrict__ row_e, const float* __restrict__ row_max,
+                                      const int32_t* __restrict__ row_arg, int64_t Bx, int n_parts,
+                                      float* __restrict__ out_e, int32_t* __restrict__ out_arg) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Bx) return;
-  float e = 0.f, s = 0.f, mx = -FLT_MAX;
+  float e = 0.f, mx = -FLT_MAX;
   int32_t arg = 0x7fffffff;
-  for (int c = 0; c < n_chunks; ++c) {
+  for (int c = 0; c < n_parts; ++c) {
     const int64_t o = (int64_t)c * Bx + m;
     e += row_e[o];
-    s += row_s[o];
     if (out_arg) {
       const float tm = row_max[o];
       const int32_t ta = row_arg[o];
@@ -495,8 +530,44 @@ __global__ void tc_rows_reduce_kernel(const float* __restrict__ row_e, const flo
     }
   }
   out_e[m] = e;
-  if (out_s) out_s[m] = s;
   if (out_arg) out_arg[m] = arg;
+}
+
+// sum_j S_ij = inv_temp * X_i . (sum_j Y_j): the row sums of the logits need no pass over the B x B tile at all
+constexpr int YS_BLOCKS = 64;
+__global__ void __launch_bounds__(256) tc_ysum_partial_kernel(const __nv_bfloat16* __restrict__ Y, int64_t By, int F,
+                                                               float* __restrict__ part) {
+  __shared__ float sm[256];
+  const int f = threadIdx.x % F, lanes = 256 / F, sub = threadIdx.x / F;  // F = 64 or 128
+  const int64_t per = (By + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = (lo + per < By) ? lo + per : By;
+  float a = 0.f;
+  for (int64_t j = lo + sub; j < hi; j += lanes) a += __bfloat162float(Y[j * F + f]);
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  if (sub == 0) {
+    float t = 0.f;
+    for (int k = 0; k < lanes; ++k) t += sm[k * F + f];
+    part[blockIdx.x * F + f] = t;
+  }
+}
+__global__ void __launch_bounds__(256) tc_row_sum_s_kernel(const __nv_bfloat16* __restrict__ X, int64_t Bx, int F,
+                                                            const float* __restrict__ part, int n_part, float inv_temp,
+                                                            float* __restrict__ row_sum_s) {
+  __shared__ float ysum[128];
+  if (threadIdx.x < F) {
+    float t = 0.f;
+    for (int k = 0; k < n_part; ++k) t += part[k * F + threadIdx.x];
+    ysum[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= Bx) return;
+  float d = 0.f;
+  for (int f = lane; f < F; f += 32) d += __bfloat162float(X[row * F + f]) * ysum[f];
+  d = warp_sum(d);
+  if (lane == 0) row_sum_s[row] = d * inv_temp;
 }
 
 __global__ void tc_dx_reduce_kernel(const float* __restrict__ part, int64_t n, int n_chunks, float* __restrict__ dX) {
@@ -581,7 +652,7 @@ int64_t simce_tc_workspace_bytes(int64_t Bx, int64_t By, int F) {
   const int64_t B = Bx > By ? Bx : By;
   TcPlan a = make_plan(Bx, By), b = make_plan(By, Bx);
   const int64_t chunks = a.n_chunks > b.n_chunks ? a.n_chunks : b.n_chunks;
-  const int64_t fwd = 4 * ((chunks * B * 4 + 255) / 256 * 256);
+  const int64_t fwd = 3 * ((2 * chunks * B * 4 + 255) / 256 * 256) + YS_BLOCKS * 128 * 4 + 256;
   const int64_t bwd = chunks * B * F * 4 + 256;
   return (fwd > bwd ? fwd : bwd) + 1024;
 }
@@ -601,9 +672,10 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   const float log2e = 1.4426950408889634f;
   p.c1 = inv_temp * log2e; p.c0 = -inv_temp * log2e; p.inv_temp = inv_temp;
   p.diag_offset = diag_offset;
-  const int64_t stride = (pl.n_chunks * Bx * 4 + 255) / 256 * 256;
+  const int64_t stride = (2 * pl.n_chunks * Bx * 4 + 255) / 256 * 256;
   char* w = (char*)workspace;
-  p.row_e = (float*)w; p.row_s = (float*)(w + stride); p.row_max = (float*)(w + 2 * stride); p.row_arg = (int32_t*)(w + 3 * stride);
+  p.row_e = (float*)w; p.row_s = nullptr; p.row_max = (float*)(w + stride); p.row_arg = (int32_t*)(w + 2 * stride);
+  float* ypart = (float*)(w + 3 * stride);
   p.diag = diag; p.want_metrics = want_metrics;
   CUtensorMap mx, my;
   p.use_tma = (!g_tc_force_manual && make_map(&mx, X, Bx, F) && make_map(&my, Y, By, F)) ? 1 : 0;
@@ -611,8 +683,13 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   const size_t smem = tc_smem_bytes(F, false);
   TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   simce_tc_kernel<false><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, p);
-  tc_rows_reduce_kernel<<<ceil_div(Bx, 256), 256, 0, s>>>(p.row_e, p.row_s, p.row_max, p.row_arg, Bx, pl.n_chunks, row_sumexp,
-                                                          row_sum_s, want_metrics ? row_argmax : nullptr);
+  tc_rows_reduce_kernel<<<ceil_div(Bx, 256), 256, 0, s>>>(p.row_e, p.row_max, p.row_arg, Bx, 2 * pl.n_chunks, row_sumexp,
+                                                          want_metrics ? row_argmax : nullptr);
+  if (row_sum_s) {
+    const int nb = (int)(By < 256 * YS_BLOCKS ? ceil_div(By, 256) : YS_BLOCKS);
+    tc_ysum_partial_kernel<<<nb, 256, 0, s>>>((const __nv_bfloat16*)Y, By, F, ypart);
+    tc_row_sum_s_kernel<<<ceil_div(Bx, 8), 256, 0, s>>>((const __nv_bfloat16*)X, Bx, F, ypart, nb, inv_temp, row_sum_s);
+  }
   TT_LAUNCH_CHECK("simce_tc_rows");
   return TT_OK;
 }
