@@ -183,6 +183,18 @@ int tt_linear_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, flo
                     int32_t N, int32_t K, int32_t act_dtype, void* workspace, int64_t workspace_bytes,
                     tt_stream_t stream);
 
+/* bf16 tensor-core variants (tcgen05.mma, fp32 accumulation in TMEM, TMA-fed): activations / gradients are bf16,
+ * W_bf16 is a bf16 copy of the fp32 master weight (tt_cast_bf16), dW / dbias stay fp32.  All leading dimensions must
+ * be multiples of 8 elements and all pointers 16-byte aligned (TMA).  out_dtype selects bf16 or fp32 for C / dX. */
+int tt_cast_bf16(const float* src, void* dst, int64_t n, tt_stream_t stream);
+int tt_linear_forward_bf16(const void* A, int64_t lda, const void* W_bf16, const float* bias, void* C, int64_t ldc,
+                           int32_t out_dtype, int64_t M, int32_t N, int32_t K, int32_t relu, tt_stream_t stream);
+int tt_linear_dgrad_bf16(const void* dY, int64_t ldy, const void* W_bf16, void* dX, int64_t ldx, int32_t out_dtype, int64_t M,
+                         int32_t N, int32_t K, tt_stream_t stream);
+int64_t tt_linear_wgrad_bf16_workspace_bytes(int64_t M, int32_t N, int32_t K);
+int tt_linear_wgrad_bf16(const void* dY, int64_t ldy, const void* X, int64_t ldx, float* dW, float* dbias, int64_t M, int32_t N,
+                         int32_t K, void* workspace, int64_t workspace_bytes, tt_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm1d (train-mode batch statistics) + Dropout, the reference's Linear->ReLU->BN->Dropout
  * block (src/towers/tower/base_tower.py:88-93).  Split in three so data-parallel ranks can

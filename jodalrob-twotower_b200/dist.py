@@ -192,11 +192,12 @@ class DistributedEngine(TwoTowerEngine):
         cfg, dev, E, W = self.cfg, self.device, self.cfg.emb_dim, self.world
         H0 = cfg.hidden[0]
         ld = [H0 + self.K[t] * E for t in range(2)]
-        sizes = [_a256(B * ld[t] * 4) for t in range(2)]
+        esz = 4 if self.act == TT_F32 else 2
+        sizes = [_a256(B * ld[t] * esz) for t in range(2)]
         total = 2 * (sizes[0] + sizes[1])
         buf, peer = self.comm.peer_buffer(total, dev)
         offs = [0, sizes[0], sizes[0] + sizes[1], 2 * sizes[0] + sizes[1]]
-        views = [buf[offs[i]:offs[i] + B * ld[i % 2] * 4].view(torch.float32).view(B, ld[i % 2]) for i in range(4)]
+        views = [buf[offs[i]:offs[i] + B * ld[i % 2] * esz].view(self.act_torch).view(B, ld[i % 2]) for i in range(4)]
         # build the generic workspace first, then swap the four buffers for the peer-mapped ones
         ws = super().workspace(B)
         ws.c, ws.dc = [views[0], views[1]], [views[2], views[3]]

@@ -100,11 +100,16 @@ class TwoTowerEngine:
             raise ValueError("dtype='bf16' (tcgen05 sim-CE) needs final_embedding_dim 64 or 128")
         self.emb_tt = native.TT_BF16 if dtype == "bf16" else TT_F32
         self.emb_torch = torch.bfloat16 if dtype == "bf16" else torch.float32
+        if dtype == "bf16":
+            widths = [cfg.notice_dense_dim, cfg.company_dense_dim, cfg.final_dim, cfg.emb_dim] + list(cfg.hidden)
+            if any(w % 8 for w in widths):
+                raise ValueError("dtype='bf16' (TMA-fed tcgen05 GEMMs) needs every layer width to be a multiple of 8")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise native.TwoTowerNativeError("TwoTowerEngine needs a CUDA device: the hot path is sm_100a CUDA only, no CPU fallback")
         self.lib = native.lib()
-        self.act = TT_F32
+        self.act = native.TT_BF16 if dtype == "bf16" else TT_F32
+        self.act_torch = torch.bfloat16 if dtype == "bf16" else torch.float32
         self.adam_mode = {"dense_exact": TT_ADAM_DENSE_EXACT, "sparse": TT_ADAM_SPARSE}[optimizer_mode]
         self.default_layout = value_layout
         E = cfg.emb_dim
@@ -131,6 +136,7 @@ class TwoTowerEngine:
         self.dense_g = torch.zeros(P, dtype=torch.float32, device=dev)
         self.dense_m = torch.zeros(P, dtype=torch.float32, device=dev)
         self.dense_v = torch.zeros(P, dtype=torch.float32, device=dev)
+        self.dense_w16 = torch.zeros(P, dtype=torch.bfloat16, device=dev) if dtype == "bf16" else None  # bf16 mirror for the GEMMs
         nblk = len(cfg.hidden) - 1
         self.bn_rm = [[torch.zeros(h, device=dev) for h in cfg.hidden[1:]] for _ in range(2)]
         self.bn_rv = [[torch.ones(h, device=dev) for h in cfg.hidden[1:]] for _ in range(2)]
@@ -193,12 +199,18 @@ class TwoTowerEngine:
         for t in range(2):
             _, keys, _, dense_dim = cfg.tower(t)
             ld = cfg.hidden[0] + len(keys) * E
-            ws.c.append(torch.empty(B, ld, **f32))
-            ws.dc.append(torch.empty(B, ld, **f32))
-            ws.h.append([torch.empty(B, h, **f32) for h in cfg.hidden[1:]])
-            ws.y.append([torch.empty(B, h, **f32) for h in cfg.hidden[1:]])
-            ws.dh.append([torch.empty(B, h, **f32) for h in cfg.hidden[1:]])
-            ws.dy.append([torch.empty(B, h, **f32) for h in cfg.hidden[1:]])
+            act = dict(dtype=self.act_torch, device=dev)
+            ws.c.append(torch.empty(B, ld, **act))
+            ws.dc.append(torch.empty(B, ld, **act))
+            ws.h.append([torch.empty(B, h, **act) for h in cfg.hidden[1:]])
+            ws.y.append([torch.empty(B, h, **act) for h in cfg.hidden[1:]])
+            ws.dh.append([torch.empty(B, h, **act) for h in cfg.hidden[1:]])
+            ws.dy.append([torch.empty(B, h, **act) for h in cfg.hidden[1:]])
+            if self.act != TT_F32:
+                if t == 0:
+                    ws.x16, ws.dz16 = [], []
+                ws.x16.append(torch.empty(B, dense_dim, **act))
+                ws.dz16.append(torch.empty(B, cfg.final_dim, **act))
             ws.mean.append([torch.empty(h, **f32) for h in cfg.hidden[1:]])
             ws.rstd.append([torch.empty(h, **f32) for h in cfg.hidden[1:]])
             ws.z.append(torch.empty(B, cfg.final_dim, **f32))
@@ -207,12 +219,13 @@ class TwoTowerEngine:
             ws.de.append(torch.empty(B, cfg.final_dim, **f32))
             ws.dz.append(torch.empty(B, cfg.final_dim, **f32))
             width = ld
-            max_wg = max(max_wg, q("tt_linear_wgrad_workspace_bytes", B, cfg.hidden[0], dense_dim))
+            wgq = "tt_linear_wgrad_workspace_bytes" if self.act == TT_F32 else "tt_linear_wgrad_bf16_workspace_bytes"
+            max_wg = max(max_wg, q(wgq, B, cfg.hidden[0], dense_dim))
             for h in cfg.hidden[1:]:
                 max_bn = max(max_bn, q("tt_bn_workspace_bytes", B, h))
-                max_wg = max(max_wg, q("tt_linear_wgrad_workspace_bytes", B, h, width))
+                max_wg = max(max_wg, q(wgq, B, h, width))
                 width = h
-            max_wg = max(max_wg, q("tt_linear_wgrad_workspace_bytes", B, cfg.final_dim, width))
+            max_wg = max(max_wg, q(wgq, B, cfg.final_dim, width))
         # one scratch per tower so the two towers may run on different streams
         ws.bn_ws = [torch.empty(max(max_bn, 256), dtype=torch.uint8, device=dev) for _ in range(2)]
         ws.bn_sums = [torch.zeros(2 * max(cfg.hidden[1:] + [1]), dtype=torch.float64, device=dev) for _ in range(2)]
@@ -232,6 +245,39 @@ class TwoTowerEngine:
         ws.piece_ws = torch.empty(q("tt_ebc_piece_workspace_bytes", n_tot, E), dtype=torch.uint8, device=dev)
         self._ws[B] = ws
         return ws
+
+    # ------------------------------------------------------------------ Linear dispatch (fp32 SIMT / bf16 tcgen05)
+    def _w16(self, name: str) -> torch.Tensor:
+        return self.layout.view(self.dense_w16, name)
+
+    def _lin_fwd(self, x, ldx, wname, bname, out, ldo, out_f32: bool, M, N, K, relu):
+        s = self._stream()
+        if self.act == TT_F32:
+            self._call("tt_linear_forward", ptr(x), ldx, ptr(self.dense(wname)), ptr(self.dense(bname)), ptr(out), ldo, M, N, K,
+                       TT_F32, relu, s)
+        else:
+            self._call("tt_linear_forward_bf16", ptr(x), ldx, ptr(self._w16(wname)), ptr(self.dense(bname)), ptr(out), ldo,
+                       TT_F32 if out_f32 else native.TT_BF16, M, N, K, relu, s)
+
+    def _lin_dgrad(self, dy, ldy, wname, dx, ldx, M, N, K):
+        s = self._stream()
+        if self.act == TT_F32:
+            self._call("tt_linear_dgrad", ptr(dy), ldy, ptr(self.dense(wname)), ptr(dx), ldx, M, N, K, TT_F32, s)
+        else:
+            self._call("tt_linear_dgrad_bf16", ptr(dy), ldy, ptr(self._w16(wname)), ptr(dx), ldx, native.TT_BF16, M, N, K, s)
+
+    def _lin_wgrad(self, dy, ldy, x, ldx, wname, bname, M, N, K, wsbuf):
+        s = self._stream()
+        if self.act == TT_F32:
+            self._call("tt_linear_wgrad", ptr(dy), ldy, ptr(x), ldx, ptr(self.dense(wname, "g")), ptr(self.dense(bname, "g")), M, N, K,
+                       TT_F32, ptr(wsbuf), wsbuf.numel(), s, n_kernels=4)
+        else:
+            self._call("tt_linear_wgrad_bf16", ptr(dy), ldy, ptr(x), ldx, ptr(self.dense(wname, "g")), ptr(self.dense(bname, "g")),
+                       M, N, K, ptr(wsbuf), wsbuf.numel(), s, n_kernels=4)
+
+    def refresh_bf16_weights(self):
+        if self.dense_w16 is not None:
+            self._call("tt_cast_bf16", ptr(self.dense_w), ptr(self.dense_w16), self.layout.total, self._stream())
 
     # ------------------------------------------------------------------ forward
     def _check_inputs(self, t: int, dense: torch.Tensor, values: torch.Tensor, B: int):
@@ -277,12 +323,14 @@ class TwoTowerEngine:
         dense = dense.contiguous()
         if dense.dtype != torch.float32:
             dense = dense.float()
-        self._call("tt_linear_forward", ptr(dense), dense_dim, ptr(self.dense(pre + "dense_projection.weight")),
-                   ptr(self.dense(pre + "dense_projection.bias")), ptr(ws.c[t]), ld, B, H0, dense_dim, self.act, 0, s)
+        if self.act != TT_F32:
+            self._call("tt_cast_bf16", ptr(dense), ptr(ws.x16[t]), B * dense_dim, s)
+            dense = ws.x16[t]
+        self._lin_fwd(dense, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", ws.c[t], ld, False, B, H0,
+                      dense_dim, 0)
         x, width, idx = ws.c[t], ld, 0
         for bi, h in enumerate(cfg.hidden[1:]):
-            self._call("tt_linear_forward", ptr(x), width, ptr(self.dense(pre + f"mlp.{idx}.weight")),
-                       ptr(self.dense(pre + f"mlp.{idx}.bias")), ptr(ws.h[t][bi]), h, B, h, width, self.act, 1, s)
+            self._lin_fwd(x, width, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", ws.h[t][bi], h, False, B, h, width, 1)
             gamma, beta = self.dense(pre + f"mlp.{idx + 2}.weight"), self.dense(pre + f"mlp.{idx + 2}.bias")
             if train:
                 self._call("tt_bn_stats", ptr(ws.h[t][bi]), h, B, h, self.act, ptr(ws.bn_sums[t]), ptr(ws.bn_ws[t]),
@@ -301,8 +349,7 @@ class TwoTowerEngine:
                        ptr(beta), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.y[t][bi]), h, s)
             x, width, idx = ws.y[t][bi], h, idx + 4
         F = cfg.final_dim
-        self._call("tt_linear_forward", ptr(x), width, ptr(self.dense(pre + f"mlp.{idx}.weight")),
-                   ptr(self.dense(pre + f"mlp.{idx}.bias")), ptr(ws.z[t]), F, B, F, width, self.act, 0, s)
+        self._lin_fwd(x, width, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", ws.z[t], F, True, B, F, width, 0)
         self._call("tt_l2norm_forward", ptr(ws.z[t]), B, F, ptr(ws.e[t]), self.emb_tt, ptr(ws.nrm[t]), s)
         return ws.e[t]
 
@@ -336,6 +383,7 @@ class TwoTowerEngine:
         lay = TT_LAYOUT_KEY_MAJOR if (layout or self.default_layout) == "key_major" else TT_LAYOUT_SAMPLE_MAJOR
         ws = self.workspace(B)
         ws.inputs = (notice_dense.contiguous(), company_dense.contiguous())
+        self.refresh_bf16_weights()
         self.embedding_forward(ws, [notice_values, company_values], lay)
         self.tower_forward(0, ws, notice_dense, None, train, lay, masks=None if masks is None else masks[0])
         self.tower_forward(1, ws, company_dense, None, train, lay, masks=None if masks is None else masks[1])
@@ -370,12 +418,13 @@ class TwoTowerEngine:
         idx = 4 * nblk
         xlast = ws.y[t][nblk - 1] if nblk > 0 else ws.c[t]
         wl = widths[-1]
-        self._call("tt_linear_wgrad", ptr(ws.dz[t]), F, ptr(xlast), wl, ptr(self.dense(pre + f"mlp.{idx}.weight", "g")),
-                   ptr(self.dense(pre + f"mlp.{idx}.bias", "g")), B, F, wl, self.act, ptr(ws.wg_ws[t]), ws.wg_ws[t].numel(), s,
-                   n_kernels=4)
+        dz = ws.dz[t]
+        if self.act != TT_F32:
+            self._call("tt_cast_bf16", ptr(ws.dz[t]), ptr(ws.dz16[t]), B * F, s)
+            dz = ws.dz16[t]
+        self._lin_wgrad(dz, F, xlast, wl, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", B, F, wl, ws.wg_ws[t])
         dx = ws.dy[t][nblk - 1] if nblk > 0 else ws.dc[t]
-        self._call("tt_linear_dgrad", ptr(ws.dz[t]), F, ptr(self.dense(pre + f"mlp.{idx}.weight")), ptr(dx), wl, B, F, wl,
-                   self.act, s)
+        self._lin_dgrad(dz, F, pre + f"mlp.{idx}.weight", dx, wl, B, F, wl)
         for bi in range(nblk - 1, -1, -1):
             h = cfg.hidden[1 + bi]
             idx = 4 * bi
@@ -393,18 +442,17 @@ class TwoTowerEngine:
                        ptr(self.dense(pre + f"mlp.{idx + 2}.bias", "g")), ptr(ws.dh[t][bi]), h, s)
             xin = ws.y[t][bi - 1] if bi > 0 else ws.c[t]
             win = widths[bi]
-            self._call("tt_linear_wgrad", ptr(ws.dh[t][bi]), h, ptr(xin), win, ptr(self.dense(pre + f"mlp.{idx}.weight", "g")),
-                       ptr(self.dense(pre + f"mlp.{idx}.bias", "g")), B, h, win, self.act, ptr(ws.wg_ws[t]),
-                       ws.wg_ws[t].numel(), s, n_kernels=4)
+            self._lin_wgrad(ws.dh[t][bi], h, xin, win, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", B, h, win, ws.wg_ws[t])
             dxin = ws.dy[t][bi - 1] if bi > 0 else ws.dc[t]
-            self._call("tt_linear_dgrad", ptr(ws.dh[t][bi]), h, ptr(self.dense(pre + f"mlp.{idx}.weight")), ptr(dxin), win,
-                       B, h, win, self.act, s)
-        dense_in = ws.inputs[t]
-        if dense_in.dtype != torch.float32:
-            dense_in = dense_in.float()
-        self._call("tt_linear_wgrad", ptr(ws.dc[t]), ld, ptr(dense_in), dense_dim,
-                   ptr(self.dense(pre + "dense_projection.weight", "g")), ptr(self.dense(pre + "dense_projection.bias", "g")),
-                   B, H0, dense_dim, self.act, ptr(ws.wg_ws[t]), ws.wg_ws[t].numel(), s, n_kernels=4)
+            self._lin_dgrad(ws.dh[t][bi], h, pre + f"mlp.{idx}.weight", dxin, win, B, h, win)
+        if self.act != TT_F32:
+            dense_in = ws.x16[t]
+        else:
+            dense_in = ws.inputs[t]
+            if dense_in.dtype != torch.float32:
+                dense_in = dense_in.float()
+        self._lin_wgrad(ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", B, H0,
+                        dense_dim, ws.wg_ws[t])
 
     def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool):
         """sort-by-row dedup of both towers' (row, slot) pairs, then segment-sum (+ fused Adam)."""
