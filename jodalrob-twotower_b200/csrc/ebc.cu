@@ -176,6 +176,47 @@ __global__ void __launch_bounds__(1024) scan_exclusive_kernel(int32_t* __restric
   }
 }
 
+// same scan with the counters staged in shared memory (coalesced global traffic); len <= ~48k entries
+__global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __restrict__ data, int len, int per) {
+  extern __shared__ int32_t sh[];
+  __shared__ int32_t s_part[1024];
+  const int t = threadIdx.x;
+  for (int i = t; i < len; i += 1024) sh[(i / per) * (per | 1) + (i % per)] = data[i];  // odd row pitch: no bank conflicts
+  __syncthreads();
+  int32_t* mine = sh + t * (per | 1);
+  const int lo = t * per, cnt = lo >= len ? 0 : (lo + per <= len ? per : len - lo);
+  int32_t sum = 0;
+  for (int i = 0; i < cnt; ++i) sum += mine[i];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    int32_t v = (t >= off) ? s_part[t - off] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int32_t run = s_part[t] - sum;
+  for (int i = 0; i < cnt; ++i) {
+    const int32_t c = mine[i];
+    mine[i] = run;
+    run += c;
+  }
+  __syncthreads();
+  for (int i = t; i < len; i += 1024) data[i] = sh[(i / per) * (per | 1) + (i % per)];
+}
+
+static int launch_scan(int32_t* data, int64_t len, cudaStream_t s) {
+  const int per = (int)((len + 1023) / 1024);
+  const size_t smem = (size_t)1024 * (per | 1) * 4;
+  if (smem <= 160 * 1024) {
+    TT_CUDA(cudaFuncSetAttribute(scan_exclusive_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scan_exclusive_smem_kernel<<<1, 1024, smem, s>>>(data, (int)len, per);
+  } else {
+    scan_exclusive_kernel<<<1, 1024, 0, s>>>(data, len);
+  }
+  return TT_OK;
+}
+
 __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n,
                      const int32_t* __restrict__ d_n, int shift, const int32_t* __restrict__ hist_scanned, int n_tiles,
@@ -382,7 +423,7 @@ __device__ __forceinline__ void adam_vec4(float4& w, float4& m, float4& v, const
 
 // one lane group per arena row, every row (dense-exact Adam and/or dense gradient materialisation)
 template <typename GT, bool DO_ADAM, bool WRITE_GRAD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, float* __restrict__ gout,
                       int64_t total_rows, int E, int G, const int32_t* __restrict__ sslot,
                       const int32_t* __restrict__ row_begin, const int32_t* __restrict__ row_end,
@@ -402,13 +443,17 @@ ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __res
       e = row_end[r];
     }
     for (int c = lane; c < vec_per_row; c += G) {
-      float4 g = hit ? row_grad_sum<GT>(sslot, b, e, src, E, c, pieces) : make_float4(0.f, 0.f, 0.f, 0.f);
       const int64_t off = r * E + 4 * c;
+      // issue the streaming w/m/v loads first: they overlap with the dependent stamp -> bounds -> slot -> gradient chain
+      float4 wv, mv, vv;
+      if (DO_ADAM) {
+        wv = *reinterpret_cast<const float4*>(w + off);
+        mv = *reinterpret_cast<const float4*>(m + off);
+        vv = *reinterpret_cast<const float4*>(v + off);
+      }
+      float4 g = hit ? row_grad_sum<GT>(sslot, b, e, src, E, c, pieces) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (WRITE_GRAD) *reinterpret_cast<float4*>(gout + off) = g;
       if (DO_ADAM) {
-        float4 wv = *reinterpret_cast<float4*>(w + off);
-        float4 mv = *reinterpret_cast<float4*>(m + off);
-        float4 vv = *reinterpret_cast<float4*>(v + off);
         adam_vec4(wv, mv, vv, g, h);
         *reinterpret_cast<float4*>(w + off) = wv;
         *reinterpret_cast<float4*>(m + off) = mv;
@@ -554,7 +599,7 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
     int32_t* kout = to_final ? sorted_rows : tmp_keys;
     int32_t* vout = to_final ? sorted_slots : tmp_vals;
     radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles);
-    scan_exclusive_kernel<<<1, 1024, 0, s>>>(hist, (int64_t)256 * n_tiles);
+    { int rc = launch_scan(hist, (int64_t)256 * n_tiles, s); if (rc != TT_OK) return rc; }
     radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, d_n, p * 8, hist, n_tiles, kout, vout);
     kin = kout;
     vin = vout;

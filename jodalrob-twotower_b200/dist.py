@@ -182,6 +182,7 @@ class DistributedEngine(TwoTowerEngine):
         self.block = torch.tensor(self.plan.block, dtype=torch.int32, device=dev)
         self.local_base = torch.tensor(self.plan.local_base, dtype=torch.int32, device=dev)
         self.rng_stream_base = 64 * self.rank
+        self.two_streams = False  # both towers issue collectives on one communicator: keep them on one stream
         assert self.total_rows == self.plan.local_rows
 
     # ---- workspace: concat / gradient buffers live in one peer-mapped allocation

@@ -149,6 +149,10 @@ class TwoTowerEngine:
         self._ws: Dict[int, _Ws] = {}
         self.rng_seed = 0x5EED
         self.rng_stream_base = 0  # distributed engines offset it by rank so ranks draw different dropout masks
+        # the two towers are independent until the loss: run the company tower on a side stream (fork/join with events;
+        # inside a CUDA graph capture this becomes two parallel branches)
+        self.two_streams = True
+        self._side = torch.cuda.Stream(self.device)
         self.launches = 0  # kernels launched through the C ABI (bench.py's gpu_launches)
         self.profile: Optional[list] = None  # set to [] to collect (tag, n_kernels, ev0, ev1) per C-ABI call
         self.profile_tag = ""
@@ -385,8 +389,17 @@ class TwoTowerEngine:
         ws.inputs = (notice_dense.contiguous(), company_dense.contiguous())
         self.refresh_bf16_weights()
         self.embedding_forward(ws, [notice_values, company_values], lay)
-        self.tower_forward(0, ws, notice_dense, None, train, lay, masks=None if masks is None else masks[0])
-        self.tower_forward(1, ws, company_dense, None, train, lay, masks=None if masks is None else masks[1])
+        m0, m1 = (None, None) if masks is None else (masks[0], masks[1])
+        if self.two_streams:
+            main = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.tower_forward(1, ws, company_dense, None, train, lay, masks=m1)
+            self.tower_forward(0, ws, notice_dense, None, train, lay, masks=m0)
+            main.wait_stream(self._side)
+        else:
+            self.tower_forward(0, ws, notice_dense, None, train, lay, masks=m0)
+            self.tower_forward(1, ws, company_dense, None, train, lay, masks=m1)
         out5 = self.loss_forward(ws)
         ws.train = train
         ws.masks = masks
@@ -476,8 +489,16 @@ class TwoTowerEngine:
 
     def backward(self, ws: _Ws, dloss: float = 1.0):
         self.loss_backward(ws, dloss)
-        self.tower_backward(0, ws)
-        self.tower_backward(1, ws)
+        if self.two_streams:
+            main = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.tower_backward(1, ws)
+            self.tower_backward(0, ws)
+            main.wait_stream(self._side)
+        else:
+            self.tower_backward(0, ws)
+            self.tower_backward(1, ws)
 
     # ------------------------------------------------------------------ optimizer
     def hyper_advance(self, lr: float, warmup_steps: int, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
