@@ -140,7 +140,26 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
                          const int64_t* d_stamp, const void* grad0, int64_t ld0, int64_t col0_0, int32_t K0, int64_t n0, const void* grad1,
                          int64_t ld1, int64_t col0_1, int32_t K1, int64_t n1, int32_t grad_dtype, void* piece_ws,
                          int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, const int32_t* d_n,
-                         const void* const* grad_table, int64_t n_per_rank, tt_stream_t stream);
+                         const void* const* grad_table, int64_t n_per_rank, const int32_t* d_colmap0, const int32_t* d_colmap1,
+                         tt_stream_t stream);
+
+/* Two table classes.  "Large" tables go through the sort-dedup path above.  "Small" tables (a few dozen rows: 24 of the
+ * reference's 32 notice keys have <= 25) are hit by every sample, so sorting them is wasted work and sharding them across
+ * GPUs only creates hot rows: they live next to the dense parameters, their gradient is a dense one-hot reduction
+ * (deterministic two-level sum, no atomics) and tt_dense_adam updates them (same exact-dense semantics).
+ *   tt_ebc_forward_mixed   like tt_ebc_forward (one id per bag) for a tower whose keys are split into classes: keys with
+ *                          d_vocab[k] <= 0 are skipped; d_large_rank[k] is the key's index among the large tables (or -1);
+ *                          rows_out[b*K_large + rank] = arena row - row_sub (compact keys for the sort).
+ *   tt_ebc_small_backward  gout[g_off .. g_off + vocab*E) = sum_b [id(b,key) == row] * grad[b, col .. col+E) for every
+ *                          descriptor {int32 key, int32 vocab, int32 col, int64 g_off} (24 bytes, 8-byte aligned).
+ *   d_colmap0/1 (tt_ebc_backward_adam): per large key, the column offset of its slice in the pooled-gradient row. */
+int tt_ebc_forward_mixed(const float* arena, const int64_t* d_row_base, const int32_t* d_vocab, const int64_t* values, int32_t B,
+                         int32_t K, int32_t E, int32_t layout, void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0,
+                         const int32_t* d_large_rank, int32_t K_large, int64_t row_sub, int32_t* rows_out, tt_stream_t stream);
+int64_t tt_ebc_small_workspace_bytes(int32_t B, int64_t small_floats);
+int tt_ebc_small_backward(const int64_t* values, int32_t B, int32_t K, int32_t layout, const void* grad, int64_t ld,
+                          int32_t grad_dtype, int32_t E, const void* d_small_tabs, int32_t n_small, int32_t max_vocab,
+                          int64_t small_floats, float* gout, void* workspace, int64_t workspace_bytes, tt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row-wise sharded tables across GPUs (no counterpart in the single-GPU reference; TorchRec RW convention:
@@ -155,13 +174,16 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
  *                          [b, col0 + k*E].  The matching gradient return is tt_ebc_backward_adam with grad_table. */
 int tt_ebc_clamp_ids(const int64_t* values, const int32_t* d_vocab, int32_t B, int32_t K, int32_t layout, int32_t* ids_out,
                      tt_stream_t stream);
+int tt_ebc_clamp_ids_subset(const int64_t* values, const int32_t* d_vocab, const int32_t* d_keys, int32_t B, int32_t K, int32_t KL,
+                            int32_t layout, int32_t* ids_out, tt_stream_t stream); /* ids_out[b*KL+kl] for keys d_keys[kl] only */
 int64_t tt_shard_workspace_bytes(int64_t n_total);
 int tt_shard_select_owned(const int32_t* ids_all, const int32_t* d_block, const int32_t* d_local_base, int64_t n_per_rank,
                           int64_t n0, int32_t K0, int32_t K1, int32_t world, int32_t me, int32_t* rows_out, int32_t* slots_out,
                           int32_t* d_n_owned, void* workspace, int64_t workspace_bytes, tt_stream_t stream);
 int tt_ebc_push_rows(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
                      int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
-                     int64_t ld1, int64_t col0_0, int64_t col0_1, int32_t out_dtype, tt_stream_t stream);
+                     int64_t ld1, int64_t col0_0, int64_t col0_1, const int32_t* d_colmap0, const int32_t* d_colmap1,
+                     int32_t out_dtype, tt_stream_t stream);
 
 /* Dense-parameter Adam over a flat fp32 buffer (tower Linear/BatchNorm weights), same update rule.
  * Replaces torch.optim.Adam.step for the non-embedding parameters (scripts/train.py:327). */

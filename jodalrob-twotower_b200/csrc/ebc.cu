@@ -28,19 +28,23 @@ __global__ void __launch_bounds__(256)
 ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ row_base,
                   const int32_t* __restrict__ vocab, const int64_t* __restrict__ values, int B, int K, int E,
                   int layout, OutT* __restrict__ out, int64_t out_ld, int64_t out_col0, int32_t* __restrict__ rows_out,
-                  int32_t* __restrict__ slots_out, int64_t slot_base, int G) {
+                  int32_t* __restrict__ slots_out, int64_t slot_base, int G, const int32_t* __restrict__ large_rank,
+                  int K_large, int64_t row_sub) {
   extern __shared__ unsigned char smem_raw[];
   int64_t* s_base = reinterpret_cast<int64_t*>(smem_raw);
   int32_t* s_vocab = reinterpret_cast<int32_t*>(s_base + K);
+  int32_t* s_rank = s_vocab + K;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     s_base[i] = row_base[i];
     s_vocab[i] = vocab[i];
+    s_rank[i] = large_rank ? large_rank[i] : i;
   }
   __syncthreads();
   const int lane = threadIdx.x % G;
   const int64_t n_bags = (int64_t)B * K;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
   const int64_t group0 = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+  const int K_out = large_rank ? K_large : K;
   const int vec_per_row = E >> 2;
   for (int64_t base = group0; base < n_bags; base += groups_total * UNROLL) {
     int64_t row[UNROLL];
@@ -51,14 +55,18 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
       row[u] = -1;
       if (slot[u] < n_bags) {
         const int b = (int)(slot[u] / K), k = (int)(slot[u] - (int64_t)b * K);
-        const int64_t vi = layout == TT_LAYOUT_SAMPLE_MAJOR ? slot[u] : (int64_t)k * B + b;
-        int64_t id = __ldg(values + vi);
         const int64_t hi = (int64_t)s_vocab[k] - 1;
-        id = id < 0 ? 0 : (id > hi ? hi : id);  // clamp(id, 0, V_k-1)
-        row[u] = s_base[k] + id;
-        if (lane == 0) {
-          if (rows_out) rows_out[slot[u]] = (int32_t)row[u];
-          if (slots_out) slots_out[slot[u]] = (int32_t)(slot_base + slot[u]);
+        if (hi >= 0) {  // vocab <= 0 marks a key this launch must skip (tables served by another path)
+          const int64_t vi = layout == TT_LAYOUT_SAMPLE_MAJOR ? slot[u] : (int64_t)k * B + b;
+          int64_t id = __ldg(values + vi);
+          id = id < 0 ? 0 : (id > hi ? hi : id);  // clamp(id, 0, V_k-1)
+          row[u] = s_base[k] + id;
+          const int rk = s_rank[k];
+          if (lane == 0 && rk >= 0) {  // only tables on the sort-dedup path record their (compact) row
+            const int64_t o = (int64_t)b * K_out + rk;
+            if (rows_out) rows_out[o] = (int32_t)(row[u] - row_sub);
+            if (slots_out) slots_out[o] = (int32_t)(slot_base + o);
+          }
         }
       }
     }
@@ -305,6 +313,10 @@ struct GradSrc {
   // peer-mapped (NVLink) and listed in `table` as [rank*2 + tower] — the segment-sum pulls them directly
   const void* const* table;
   int64_t n_per_rank;
+  // optional per-key column offsets (elements) inside a sample's row of the pooled-gradient buffer; NULL => col + k*E.
+  // Used when only a subset of a tower's keys (the large tables) goes through the sort-dedup path.
+  const int32_t* cmap0;
+  const int32_t* cmap1;
 };
 
 template <typename GT>
@@ -322,12 +334,12 @@ __device__ __forceinline__ float4 load_grad_vec(const GradSrc& s, int32_t slot, 
   if (slot < s.n0) {
     const int b = slot / s.K0, k = slot - b * s.K0;
     base = reinterpret_cast<const GT*>(p0);
-    off = (int64_t)b * s.ld0 + s.col0 + (int64_t)k * E + 4 * c;
+    off = (int64_t)b * s.ld0 + (s.cmap0 ? (int64_t)__ldg(s.cmap0 + k) : s.col0 + (int64_t)k * E) + 4 * c;
   } else {
     const int sl = slot - (int32_t)s.n0;
     const int b = sl / s.K1, k = sl - b * s.K1;
     base = reinterpret_cast<const GT*>(p1);
-    off = (int64_t)b * s.ld1 + s.col1 + (int64_t)k * E + 4 * c;
+    off = (int64_t)b * s.ld1 + (s.cmap1 ? (int64_t)__ldg(s.cmap1 + k) : s.col1 + (int64_t)k * E) + 4 * c;
   }
   if constexpr (sizeof(GT) == 4) {
     return __ldg(reinterpret_cast<const float4*>(base + off));
@@ -492,6 +504,59 @@ ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// small tables: dense one-hot reduction instead of sort-dedup
+// ------------------------------------------------------------------------------------------------
+// Tables with a handful of rows (24 of the 32 notice keys have <= 25) receive every sample of the batch: hundreds to
+// thousands of gradient vectors per row. Sorting them is wasted work; instead each CTA reduces a fixed chunk of samples
+// into per-warp shared-memory accumulators [V_k][E] (fixed sample order per warp, warps combined in fixed order) and a
+// second pass sums the chunk partials in order: deterministic, fully coalesced, no atomics.
+struct SmallTab {
+  int key;        // key index inside the tower
+  int vocab;      // rows
+  int col;        // column offset (elements) of the key's slice in the pooled-gradient row
+  int64_t g_off;  // offset (floats) of the table's gradient inside gout
+};
+constexpr int SM_CHUNK = 128;  // samples per CTA
+
+template <typename GT>
+__global__ void __launch_bounds__(256)
+ebc_small_partial_kernel(const int64_t* __restrict__ values, int B, int K, int layout, const GT* __restrict__ grad, int64_t ld,
+                         int E, const SmallTab* __restrict__ tabs, float* __restrict__ part, int64_t part_stride) {
+  extern __shared__ float s_acc[];  // [8 warps][vocab * E]
+  const SmallTab tb = tabs[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ve = tb.vocab * E;
+  for (int i = threadIdx.x; i < 8 * ve; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  float* mine = s_acc + warp * ve;
+  const int b_lo = blockIdx.y * SM_CHUNK;
+  const int b_hi = min(b_lo + SM_CHUNK, B);
+  for (int b = b_lo + warp; b < b_hi; b += 8) {
+    int64_t id = __ldg(values + (layout == TT_LAYOUT_SAMPLE_MAJOR ? (int64_t)b * K + tb.key : (int64_t)tb.key * B + b));
+    id = id < 0 ? 0 : (id > tb.vocab - 1 ? tb.vocab - 1 : id);
+    const GT* g = grad + (int64_t)b * ld + tb.col;
+    for (int e = lane; e < E; e += 32) mine[id * E + e] += ldf<GT>(g + e);
+  }
+  __syncthreads();
+  float* out = part + (int64_t)blockIdx.y * part_stride + tb.g_off;
+  for (int i = threadIdx.x; i < ve; i += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_acc[w * ve + i];
+    out[i] = t;
+  }
+}
+
+__global__ void ebc_small_reduce_kernel(const float* __restrict__ part, int64_t part_stride, int chunks, int64_t n,
+                                        float* __restrict__ gout) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = 0.f;
+  for (int c = 0; c < chunks; ++c) t += part[(int64_t)c * part_stride + i];
+  gout[i] = t;
+}
+
 __global__ void __launch_bounds__(256)
 dense_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   int64_t n, const tt_adam_hyper* __restrict__ d_hyper) {
@@ -518,10 +583,11 @@ using namespace tt;
 
 extern "C" {
 
-int tt_ebc_forward(const float* arena, const int64_t* d_row_base, const int32_t* d_vocab, const int64_t* values,
-                   const int64_t* bag_offsets, int64_t n_values, int32_t B, int32_t K, int32_t E, int32_t layout,
-                   void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0, int32_t* rows_out,
-                   int32_t* slots_out, int64_t slot_base, tt_stream_t stream) {
+static int ebc_forward_impl(const float* arena, const int64_t* d_row_base, const int32_t* d_vocab, const int64_t* values,
+                            const int64_t* bag_offsets, int64_t n_values, int32_t B, int32_t K, int32_t E, int32_t layout,
+                            void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0, int32_t* rows_out,
+                            int32_t* slots_out, int64_t slot_base, const int32_t* large_rank, int32_t K_large, int64_t row_sub,
+                            tt_stream_t stream) {
   TT_CHECK_ARG(arena && d_row_base && d_vocab && values && out, "tt_ebc_forward: NULL pointer");
   TT_CHECK_ARG(B >= 0 && K > 0 && E > 0 && (E % 4) == 0, "tt_ebc_forward: need K>0, E%%4==0 (B=%d K=%d E=%d)", B, K, E);
   TT_CHECK_ARG(layout == TT_LAYOUT_SAMPLE_MAJOR || layout == TT_LAYOUT_KEY_MAJOR, "tt_ebc_forward: bad layout %d", layout);
@@ -535,7 +601,7 @@ int tt_ebc_forward(const float* arena, const int64_t* d_row_base, const int32_t*
   const int G = lanes_per_row(E);
   const int threads = 256;
   const int64_t n_bags = (int64_t)B * K;
-  const size_t smem = (size_t)K * (sizeof(int64_t) + sizeof(int32_t));
+  const size_t smem = (size_t)K * (sizeof(int64_t) + 2 * sizeof(int32_t));
   cudaStream_t s = (cudaStream_t)stream;
   const int groups_per_block = threads / G;
   if (bag_offsets == nullptr) {
@@ -544,11 +610,12 @@ int tt_ebc_forward(const float* arena, const int64_t* d_row_base, const int32_t*
     int grid = (int)(want < 1 ? 1 : (want > (int64_t)sm_count() * 16 ? (int64_t)sm_count() * 16 : want));
     if (out_dtype == TT_F32)
       ebc_fwd_l1_kernel<float, UNROLL><<<grid, threads, smem, s>>>(arena, d_row_base, d_vocab, values, B, K, E, layout,
-                                                                   (float*)out, out_ld, out_col0, rows_out, slots_out, slot_base, G);
+                                                                   (float*)out, out_ld, out_col0, rows_out, slots_out, slot_base, G,
+                                                                   large_rank, K_large, row_sub);
     else
       ebc_fwd_l1_kernel<__nv_bfloat16, UNROLL><<<grid, threads, smem, s>>>(
           arena, d_row_base, d_vocab, values, B, K, E, layout, (__nv_bfloat16*)out, out_ld, out_col0, rows_out,
-          slots_out, slot_base, G);
+          slots_out, slot_base, G, large_rank, K_large, row_sub);
   } else {
     int64_t want = ceil_div(n_bags, groups_per_block);
     int grid = (int)(want < 1 ? 1 : (want > (int64_t)sm_count() * 16 ? (int64_t)sm_count() * 16 : want));
@@ -563,6 +630,22 @@ int tt_ebc_forward(const float* arena, const int64_t* d_row_base, const int32_t*
   }
   TT_LAUNCH_CHECK("ebc_fwd_kernel");
   return TT_OK;
+}
+
+int tt_ebc_forward(const float* arena, const int64_t* d_row_base, const int32_t* d_vocab, const int64_t* values,
+                   const int64_t* bag_offsets, int64_t n_values, int32_t B, int32_t K, int32_t E, int32_t layout,
+                   void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0, int32_t* rows_out,
+                   int32_t* slots_out, int64_t slot_base, tt_stream_t stream) {
+  return ebc_forward_impl(arena, d_row_base, d_vocab, values, bag_offsets, n_values, B, K, E, layout, out, out_dtype, out_ld,
+                          out_col0, rows_out, slots_out, slot_base, nullptr, 0, 0, stream);
+}
+
+int tt_ebc_forward_mixed(const float* arena, const int64_t* d_row_base, const int32_t* d_vocab, const int64_t* values, int32_t B,
+                         int32_t K, int32_t E, int32_t layout, void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0,
+                         const int32_t* d_large_rank, int32_t K_large, int64_t row_sub, int32_t* rows_out, tt_stream_t stream) {
+  TT_CHECK_ARG(d_large_rank && K_large >= 0 && K_large <= K, "tt_ebc_forward_mixed: bad large-table map");
+  return ebc_forward_impl(arena, d_row_base, d_vocab, values, nullptr, (int64_t)B * K, B, K, E, layout, out, out_dtype, out_ld,
+                          out_col0, rows_out, nullptr, 0, d_large_rank, K_large, row_sub, stream);
 }
 
 int64_t tt_ebc_sort_workspace_bytes(int64_t n, int64_t total_rows) {
@@ -620,7 +703,8 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
                          const int64_t* d_stamp, const void* grad0, int64_t ld0, int64_t col0_0, int32_t K0, int64_t n0, const void* grad1,
                          int64_t ld1, int64_t col0_1, int32_t K1, int64_t n1, int32_t grad_dtype, void* piece_ws,
                          int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, const int32_t* d_n,
-                         const void* const* grad_table, int64_t n_per_rank, tt_stream_t stream) {
+                         const void* const* grad_table, int64_t n_per_rank, const int32_t* d_colmap0, const int32_t* d_colmap1,
+                         tt_stream_t stream) {
   const bool do_adam = arena_w != nullptr;
   TT_CHECK_ARG(do_adam || grad_arena, "tt_ebc_backward_adam: nothing to do (arena_w and grad_arena both NULL)");
   TT_CHECK_ARG(!do_adam || (arena_m && arena_v && d_hyper), "tt_ebc_backward_adam: Adam needs m, v and d_hyper");
@@ -640,7 +724,7 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
   cudaStream_t s = (cudaStream_t)stream;
   const int G = lanes_per_row(E);
   const int threads = 256, gpb = threads / G;
-  GradSrc src{grad0, grad1, ld0, ld1, col0_0, col0_1, n0, K0, K1 > 0 ? K1 : 1, grad_table, n_per_rank > 0 ? n_per_rank : 1};
+  GradSrc src{grad0, grad1, ld0, ld1, col0_0, col0_1, n0, K0, K1 > 0 ? K1 : 1, grad_table, n_per_rank > 0 ? n_per_rank : 1, d_colmap0, d_colmap1};
   float* pieces = (float*)piece_ws;
   if (n > 0) {
     const int64_t chunks = (n + SEG_CHUNK - 1) / SEG_CHUNK;
@@ -683,6 +767,39 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
 #undef TT_ROWS_LAUNCH
   }
   TT_LAUNCH_CHECK("ebc_backward_adam");
+  return TT_OK;
+}
+
+int64_t tt_ebc_small_workspace_bytes(int32_t B, int64_t small_floats) {
+  const int64_t chunks = (B + SM_CHUNK - 1) / SM_CHUNK;
+  return chunks * small_floats * 4 + 256;
+}
+
+int tt_ebc_small_backward(const int64_t* values, int32_t B, int32_t K, int32_t layout, const void* grad, int64_t ld,
+                          int32_t grad_dtype, int32_t E, const void* d_small_tabs, int32_t n_small, int32_t max_vocab,
+                          int64_t small_floats, float* gout, void* workspace, int64_t workspace_bytes, tt_stream_t stream) {
+  TT_CHECK_ARG(values && grad && gout && workspace && B > 0 && K > 0 && E > 0, "tt_ebc_small_backward: bad arguments");
+  TT_CHECK_ARG(grad_dtype == TT_F32 || grad_dtype == TT_BF16, "tt_ebc_small_backward: bad dtype");
+  if (n_small == 0) return TT_OK;
+  TT_CHECK_ARG(d_small_tabs && max_vocab > 0, "tt_ebc_small_backward: missing table descriptors");
+  TT_CHECK_ARG(workspace_bytes >= tt_ebc_small_workspace_bytes(B, small_floats), "tt_ebc_small_backward: workspace too small");
+  const size_t smem = (size_t)8 * max_vocab * E * sizeof(float);
+  TT_CHECK_ARG(smem <= 160 * 1024, "tt_ebc_small_backward: max_vocab * E too large for the shared-memory accumulators");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int chunks = (B + SM_CHUNK - 1) / SM_CHUNK;
+  float* part = (float*)workspace;
+  dim3 grid(n_small, chunks);
+  if (grad_dtype == TT_F32) {
+    TT_CUDA(cudaFuncSetAttribute(ebc_small_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ebc_small_partial_kernel<float><<<grid, 256, smem, s>>>(values, B, K, layout, (const float*)grad, ld, E,
+                                                            (const SmallTab*)d_small_tabs, part, small_floats);
+  } else {
+    TT_CUDA(cudaFuncSetAttribute(ebc_small_partial_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ebc_small_partial_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(values, B, K, layout, (const __nv_bfloat16*)grad, ld, E,
+                                                                    (const SmallTab*)d_small_tabs, part, small_floats);
+  }
+  ebc_small_reduce_kernel<<<ceil_div(small_floats, 256), 256, 0, s>>>(part, small_floats, chunks, small_floats, gout);
+  TT_LAUNCH_CHECK("ebc_small_backward");
   return TT_OK;
 }
 

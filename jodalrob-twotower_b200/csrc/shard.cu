@@ -25,6 +25,21 @@ clamp_ids_kernel(const int64_t* __restrict__ values, const int32_t* __restrict__
   }
 }
 
+// same for a subset of a tower's keys (the sharded "large" tables): ids[b*KL + kl] = clamp(values(b, keys[kl]))
+__global__ void __launch_bounds__(256)
+clamp_ids_subset_kernel(const int64_t* __restrict__ values, const int32_t* __restrict__ vocab, const int32_t* __restrict__ keys,
+                        int B, int K, int KL, int layout, int32_t* __restrict__ ids) {
+  const int64_t n = (int64_t)B * KL;
+  for (int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(slot / KL), kl = (int)(slot - (int64_t)b * KL);
+    const int k = keys[kl];
+    int64_t id = values[layout == TT_LAYOUT_SAMPLE_MAJOR ? (int64_t)b * K + k : (int64_t)k * B + b];
+    const int64_t hi = (int64_t)vocab[k] - 1;
+    id = id < 0 ? 0 : (id > hi ? hi : id);
+    ids[slot] = (int32_t)id;
+  }
+}
+
 struct RouteMeta {
   const int32_t* ids_all;     // [world * n_per_rank] clamped global ids in slot order, rank-major
   const int32_t* block;       // [K0+K1] rows per rank of table k
@@ -132,7 +147,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(256)
 push_rows_kernel(const float* __restrict__ arena, int E, int G, const int32_t* __restrict__ rows_c,
                  const int32_t* __restrict__ slots_c, const int32_t* __restrict__ n_owned, void* const* __restrict__ dst_table,
-                 int64_t n_per_rank, int64_t n0, int K0, int K1, int64_t ld0, int64_t ld1, int64_t col0_0, int64_t col0_1) {
+                 int64_t n_per_rank, int64_t n0, int K0, int K1, int64_t ld0, int64_t ld1, int64_t col0_0, int64_t col0_1,
+                 const int32_t* __restrict__ cmap0, const int32_t* __restrict__ cmap1) {
   const int n = *n_owned;
   const int lane = threadIdx.x % G;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
@@ -145,11 +161,11 @@ push_rows_kernel(const float* __restrict__ arena, int E, int G, const int32_t* _
     OutT* dst;
     if (g < n0) {
       const int b = (int)(g / K0), k = (int)(g - (int64_t)b * K0);
-      dst = reinterpret_cast<OutT*>(dst_table[2 * r]) + (int64_t)b * ld0 + col0_0 + (int64_t)k * E;
+      dst = reinterpret_cast<OutT*>(dst_table[2 * r]) + (int64_t)b * ld0 + (cmap0 ? (int64_t)cmap0[k] : col0_0 + (int64_t)k * E);
     } else {
       g -= n0;
       const int b = (int)(g / K1), k = (int)(g - (int64_t)b * K1);
-      dst = reinterpret_cast<OutT*>(dst_table[2 * r + 1]) + (int64_t)b * ld1 + col0_1 + (int64_t)k * E;
+      dst = reinterpret_cast<OutT*>(dst_table[2 * r + 1]) + (int64_t)b * ld1 + (cmap1 ? (int64_t)cmap1[k] : col0_1 + (int64_t)k * E);
     }
     for (int c = lane; c < vec_per_row; c += G) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(arena + (int64_t)row * E) + c);
@@ -173,6 +189,18 @@ int tt_ebc_clamp_ids(const int64_t* values, const int32_t* d_vocab, int32_t B, i
   const int64_t cap = (int64_t)sm_count() * 8;
   clamp_ids_kernel<<<(int)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(values, d_vocab, B, K, layout, ids_out);
   TT_LAUNCH_CHECK("clamp_ids_kernel");
+  return TT_OK;
+}
+
+int tt_ebc_clamp_ids_subset(const int64_t* values, const int32_t* d_vocab, const int32_t* d_keys, int32_t B, int32_t K, int32_t KL,
+                            int32_t layout, int32_t* ids_out, tt_stream_t stream) {
+  TT_CHECK_ARG(values && d_vocab && d_keys && ids_out && B >= 0 && K > 0 && KL >= 0 && KL <= K, "tt_ebc_clamp_ids_subset: bad arguments");
+  if (B == 0 || KL == 0) return TT_OK;
+  int64_t want = ceil_div((int64_t)B * KL, 256);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  clamp_ids_subset_kernel<<<(int)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(values, d_vocab, d_keys, B, K, KL, layout,
+                                                                                            ids_out);
+  TT_LAUNCH_CHECK("clamp_ids_subset_kernel");
   return TT_OK;
 }
 
@@ -203,7 +231,8 @@ int tt_shard_select_owned(const int32_t* ids_all, const int32_t* d_block, const 
 
 int tt_ebc_push_rows(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
                      int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
-                     int64_t ld1, int64_t col0_0, int64_t col0_1, int32_t out_dtype, tt_stream_t stream) {
+                     int64_t ld1, int64_t col0_0, int64_t col0_1, const int32_t* d_colmap0, const int32_t* d_colmap1,
+                     int32_t out_dtype, tt_stream_t stream) {
   TT_CHECK_ARG(arena && rows && slots && d_n_owned && dst_table && E > 0 && (E % 4) == 0, "tt_ebc_push_rows: bad arguments");
   TT_CHECK_ARG(out_dtype == TT_F32 || out_dtype == TT_BF16, "tt_ebc_push_rows: bad dtype");
   int g = 1;
@@ -214,10 +243,10 @@ int tt_ebc_push_rows(const float* arena, int32_t E, const int32_t* rows, const i
   cudaStream_t s = (cudaStream_t)stream;
   if (out_dtype == TT_F32)
     push_rows_kernel<float><<<grid, 256, 0, s>>>(arena, E, g, rows, slots, d_n_owned, dst_table, n_per_rank, n0, K0, K1 > 0 ? K1 : 1,
-                                                 ld0, ld1, col0_0, col0_1);
+                                                 ld0, ld1, col0_0, col0_1, d_colmap0, d_colmap1);
   else
     push_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(arena, E, g, rows, slots, d_n_owned, dst_table, n_per_rank, n0, K0,
-                                                         K1 > 0 ? K1 : 1, ld0, ld1, col0_0, col0_1);
+                                                         K1 > 0 ? K1 : 1, ld0, ld1, col0_0, col0_1, d_colmap0, d_colmap1);
   TT_LAUNCH_CHECK("push_rows_kernel");
   return TT_OK;
 }

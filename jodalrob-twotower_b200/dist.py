@@ -165,25 +165,39 @@ def _a256(n: int) -> int:
 
 
 class DistributedEngine(TwoTowerEngine):
+    """Small tables (V*E <= SMALL_TABLE_FLOATS) are replicated with the dense weights and their gradients ride the dense
+    all-reduce; large tables are sharded row-wise and exchanged over peer memory."""
+
     def __init__(self, cfg: TwoTowerConfig, device, comm, optimizer_mode: str = "dense_exact", value_layout: str = "sample_major",
-                 dtype: str = "fp32"):
+                 dtype: str = "fp32", small_tables: bool = True):
         self.comm = comm
         self.world, self.rank = comm.world, comm.rank
         self.full_cfg = cfg
-        self.plan = ShardPlan(list(cfg.notice_vocab) + list(cfg.company_vocab), self.world)
-        Kn = len(cfg.notice_keys)
-        # the local engine sees tables of block_k rows each (its shard); ids are routed before they reach it
-        local = TwoTowerConfig(cfg.notice_keys, cfg.company_keys, self.plan.block[:Kn], self.plan.block[Kn:], cfg.emb_dim,
-                               cfg.notice_dense_dim, cfg.company_dense_dim, cfg.hidden, cfg.final_dim, cfg.dropout,
-                               cfg.temperature, cfg.label_smoothing)
-        super().__init__(local, device, optimizer_mode, value_layout, dtype)
+        super().__init__(cfg, device, optimizer_mode, value_layout, dtype, small_tables)
         dev = self.device
-        self.vocab_global = torch.tensor(self.plan.vocab, dtype=torch.int32, device=dev)
+        # large keys in slot order (notice large keys, then company large keys) and their shard map
+        self.large_keys = [[k for k in range(self.K[t]) if not self.is_small[t][k]] for t in range(2)]
+        lv = [cfg.tower(t)[2][k] for t in range(2) for k in self.large_keys[t]]
+        self.plan = ShardPlan(lv if lv else [1], self.world)
         self.block = torch.tensor(self.plan.block, dtype=torch.int32, device=dev)
         self.local_base = torch.tensor(self.plan.local_base, dtype=torch.int32, device=dev)
+        self.d_large_keys = [torch.tensor(k if k else [0], dtype=torch.int32, device=dev) for k in self.large_keys]
+        # the local mixed lookup serves the replicated small tables only: large keys are marked "skip" (vocab 0)
+        vf = self.vocab.clone()
+        off = 0
+        for t in range(2):
+            for k in self.large_keys[t]:
+                vf[off + k] = 0
+            off += self.K[t]
+        self.vocab_small_only = vf
+        self.no_rank = torch.full((self.K[0] + self.K[1],), -1, dtype=torch.int32, device=dev)
         self.rng_stream_base = 64 * self.rank
         self.two_streams = False  # both towers issue collectives on one communicator: keep them on one stream
-        assert self.total_rows == self.plan.local_rows
+        if lv:
+            assert self.total_rows == self.plan.local_rows, (self.total_rows, self.plan.local_rows)
+
+    def _alloc_rows(self, t: int, k: int, vocab: int, small: bool) -> int:
+        return vocab if small else -(-vocab // self.world)
 
     # ---- workspace: concat / gradient buffers live in one peer-mapped allocation
     def workspace(self, B: int) -> _Ws:
@@ -205,10 +219,10 @@ class DistributedEngine(TwoTowerEngine):
         ws.peer_buf = buf
         ws.c_table = torch.tensor([p + offs[t] for p in peer for t in range(2)], dtype=torch.int64, device=dev)
         ws.dc_table = torch.tensor([p + offs[2 + t] for p in peer for t in range(2)], dtype=torch.int64, device=dev)
-        n_l = B * (self.K[0] + self.K[1])
-        cap = n_l * W
+        n_l = B * (self.KL[0] + self.KL[1])
+        cap = max(n_l * W, 1)
         i32 = dict(dtype=torch.int32, device=dev)
-        ws.ids_local = torch.zeros(n_l, **i32)
+        ws.ids_local = torch.zeros(max(n_l, 1), **i32)
         ws.ids_all = torch.zeros(cap, **i32)
         ws.rows = torch.zeros(cap, **i32)          # owned local rows (compact)
         ws.slots = torch.zeros(cap, **i32)         # their global slots
@@ -217,7 +231,7 @@ class DistributedEngine(TwoTowerEngine):
         ws.n_owned = torch.zeros(1, **i32)
         q = self.lib.query
         ws.shard_ws = torch.empty(q("tt_shard_workspace_bytes", cap), dtype=torch.uint8, device=dev)
-        ws.sort_ws = torch.empty(q("tt_ebc_sort_workspace_bytes", cap, self.total_rows), dtype=torch.uint8, device=dev)
+        ws.sort_ws = torch.empty(q("tt_ebc_sort_workspace_bytes", cap, max(self.total_rows, 1)), dtype=torch.uint8, device=dev)
         ws.piece_ws = torch.empty(q("tt_ebc_piece_workspace_bytes", cap, E), dtype=torch.uint8, device=dev)
         Bg = B * W
         f32 = dict(dtype=torch.float32, device=dev)
@@ -234,18 +248,33 @@ class DistributedEngine(TwoTowerEngine):
         E, B, s = self.cfg.emb_dim, ws.B, self._stream()
         H0 = self.cfg.hidden[0]
         K0, K1 = self.K
-        n0, n_l = B * K0, B * (K0 + K1)
+        KL0, KL1 = self.KL
+        n0, n_l = B * KL0, B * (KL0 + KL1)
         if values[0] is None or values[1] is None:
             raise NotImplementedError("the sharded lookup serves both towers in one exchange; call the train task, not a single tower")
         self.profile_tag = "sharded"
-        self._call("tt_ebc_clamp_ids", ptr(values[0]), ptr(self.vocab_global), B, K0, layout, ptr(ws.ids_local), s)
-        self._call("tt_ebc_clamp_ids", ptr(values[1]), self.vocab_global.data_ptr() + 4 * K0, B, K1, layout,
-                   ws.ids_local.data_ptr() + 4 * n0, s)
+        # replicated small tables: plain local lookup (large keys skipped)
+        for t, v in enumerate(values):
+            k0 = 0 if t == 0 else K0
+            if self.n_small[t]:
+                self._call("tt_ebc_forward_mixed", ptr(self.flat_w), self.row_base.data_ptr() + 8 * k0,
+                           self.vocab_small_only.data_ptr() + 4 * k0, ptr(v), B, self.K[t], E, layout, ptr(ws.c[t]), self.act,
+                           H0 + self.K[t] * E, H0, self.no_rank.data_ptr() + 4 * k0, 0, 0, 0, s)
+        ws.values, ws.layout = list(values), layout
+        if n_l == 0:
+            return
+        # sharded large tables: clamp -> all-gather ids -> owned-id compaction -> fused lookup + push over peer memory
+        self._call("tt_ebc_clamp_ids_subset", ptr(values[0]), ptr(self.vocab), ptr(self.d_large_keys[0]), B, K0, KL0, layout,
+                   ptr(ws.ids_local), s)
+        self._call("tt_ebc_clamp_ids_subset", ptr(values[1]), self.vocab.data_ptr() + 4 * K0, ptr(self.d_large_keys[1]), B, K1, KL1,
+                   layout, ws.ids_local.data_ptr() + 4 * n0, s)
         self.comm.all_gather(ws.ids_all, ws.ids_local)
-        self._call("tt_shard_select_owned", ptr(ws.ids_all), ptr(self.block), ptr(self.local_base), n_l, n0, K0, K1, self.world,
-                   self.rank, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), ptr(ws.shard_ws), ws.shard_ws.numel(), s, n_kernels=3)
+        self._call("tt_shard_select_owned", ptr(ws.ids_all), ptr(self.block), ptr(self.local_base), n_l, n0, max(KL0, 1), KL1,
+                   self.world, self.rank, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), ptr(ws.shard_ws), ws.shard_ws.numel(), s,
+                   n_kernels=3)
         self._call("tt_ebc_push_rows", ptr(self.arena), E, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), n_l * self.world,
-                   ptr(ws.c_table), n_l, n0, K0, K1, H0 + K0 * E, H0 + K1 * E, H0, H0, self.act, s)
+                   ptr(ws.c_table), n_l, n0, max(KL0, 1), KL1, H0 + K0 * E, H0 + K1 * E, H0, H0, ptr(self.colmap[0]),
+                   ptr(self.colmap[1]), self.act, s)
         self.comm.barrier(self.device)  # every owner has finished writing into my concat buffers
 
     def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int) -> int:
@@ -286,13 +315,17 @@ class DistributedEngine(TwoTowerEngine):
                    ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=2)
 
     def reduce_dense_grads(self):
-        # also the barrier that guarantees every rank's pooled-gradient buffers are complete before anyone pulls from them
+        # dense weights AND the replicated small tables; also the barrier that guarantees every rank's pooled-gradient
+        # buffers are complete before anyone pulls from them
         self.comm.all_reduce(self.dense_g)
 
     def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool):
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
         K0, K1 = self.K
-        n0, n_l = B * K0, B * (K0 + K1)
+        KL0, KL1 = self.KL
+        n0, n_l = B * KL0, B * (KL0 + KL1)
+        if n_l == 0 or self.total_rows == 0:
+            return
         cap = n_l * self.world
         H0 = cfg.hidden[0]
         self.profile_tag = "sharded"
@@ -305,9 +338,10 @@ class DistributedEngine(TwoTowerEngine):
         self._call("tt_ebc_backward_adam", ptr(self.arena) if apply_adam else 0, ptr(self.arena_m) if apply_adam else 0,
                    ptr(self.arena_v) if apply_adam else 0, ptr(self.arena_grad) if want_dense_grad else 0,
                    self.total_rows, E, ptr(ws.sorted_rows), ptr(ws.sorted_slots), cap, ptr(self.row_begin), ptr(self.row_end),
-                   ptr(self.row_stamp), 0, ptr(self.stamp), 0, H0 + K0 * E, H0, K0, n0, 0, H0 + K1 * E, H0, K1, n_l - n0,
-                   self.act, ptr(ws.piece_ws), ws.piece_ws.numel(), ptr(self.hyper),
-                   self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, ptr(ws.n_owned), ptr(ws.dc_table), n_l, s, n_kernels=2)
+                   ptr(self.row_stamp), 0, ptr(self.stamp), 0, H0 + K0 * E, H0, max(KL0, 1), n0, 0, H0 + K1 * E, H0, max(KL1, 1),
+                   n_l - n0, self.act, ptr(ws.piece_ws), ws.piece_ws.numel(), ptr(self.hyper),
+                   self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, ptr(ws.n_owned), ptr(ws.dc_table), n_l,
+                   ptr(self.colmap[0]), ptr(self.colmap[1]), s, n_kernels=2)
 
     def similarity_matrix(self, ws: _Ws) -> torch.Tensor:
         """This rank's rows of the global logits: [B_l, B_g]."""
@@ -319,29 +353,47 @@ class DistributedEngine(TwoTowerEngine):
         return S
 
     # ---- full <-> sharded parameter exchange (reference-named state_dict lives on the full tables)
+    def _large_index(self, t: int, k: int) -> int:
+        return (0 if t == 0 else self.KL[0]) + self.large_keys[t].index(k)
+
     def load_full_tables(self, full_tables: Sequence[torch.Tensor]):
-        """full_tables[k]: [V_k, E] for notice keys then company keys; copies this rank's shard into the local arena."""
-        self.arena.zero_()
-        for k, tab in enumerate(full_tables):
-            lo, hi = self.plan.shard_range(k, self.rank)
-            if hi > lo:
-                b = self.plan.local_base[k]
-                self.arena[b:b + hi - lo].copy_(tab[lo:hi])
+        """full_tables: [V_k, E] for notice keys then company keys; small tables are copied whole (replicated), of a large
+        table this rank keeps its row shard."""
+        i = 0
+        for t in range(2):
+            for k in range(self.K[t]):
+                tab, view = full_tables[i], self.table_view(t, k)
+                i += 1
+                if self.is_small[t][k]:
+                    view.copy_(tab)
+                else:
+                    view.zero_()
+                    lo, hi = self.plan.shard_range(self._large_index(t, k), self.rank)
+                    if hi > lo:
+                        view[:hi - lo].copy_(tab[lo:hi])
 
     def gather_full_tables(self, which: str = "w") -> List[torch.Tensor]:
-        src = {"w": self.arena, "m": self.arena_m, "v": self.arena_v}[which]
-        allsh = torch.empty(self.world * src.numel(), dtype=src.dtype, device=self.device)
-        self.comm.all_gather(allsh, src.contiguous().view(-1))
-        allsh = allsh.view(self.world, self.total_rows, self.cfg.emb_dim)
         out = []
-        for k, v in enumerate(self.plan.vocab):
-            b, blk = self.plan.local_base[k], self.plan.block[k]
-            out.append(allsh[:, b:b + blk].reshape(-1, self.cfg.emb_dim)[:v].clone())
+        E = self.cfg.emb_dim
+        if self.total_rows > 0:
+            src = {"w": self.arena, "m": self.arena_m, "v": self.arena_v}[which]
+            allsh = torch.empty(self.world * src.numel(), dtype=src.dtype, device=self.device)
+            self.comm.all_gather(allsh, src.contiguous().view(-1))
+            allsh = allsh.view(self.world, self.total_rows, E)
+        for t in range(2):
+            vocab = self.cfg.tower(t)[2]
+            for k in range(self.K[t]):
+                if self.is_small[t][k]:
+                    out.append(self.table_view(t, k, which).clone())
+                else:
+                    j = self._large_index(t, k)
+                    b, blk = self.plan.local_base[j], self.plan.block[j]
+                    out.append(allsh[:, b:b + blk].reshape(-1, E)[:vocab[k]].clone())
         return out
 
 
 def create_distributed_train_task(notice_keys, company_keys, schema: dict, model: dict, device, comm=None, dtype: str = "bf16",
-                                  optimizer_mode: str = "dense_exact", seed_full_init: bool = True):
+                                  optimizer_mode: str = "dense_exact", seed_full_init: bool = True, small_tables: bool = True):
     """Build the façade on a DistributedEngine. `schema` = {"notice": [[key, vocab], ...], "company": [...]};
     `model` has emb_dim / notice_dense / company_dense / hidden / final_dim / dropout / temperature.
     With seed_full_init every rank draws the full tables with the current torch RNG (same on every rank) and keeps its
@@ -355,7 +407,7 @@ def create_distributed_train_task(notice_keys, company_keys, schema: dict, model
     cfg = TwoTowerConfig(list(notice_keys), list(company_keys), nv, cv, model["emb_dim"], model["notice_dense"],
                          model["company_dense"], list(model["hidden"]), model["final_dim"], model.get("dropout", 0.0),
                          model.get("temperature", 1.0), model.get("label_smoothing", 0.0))
-    eng = DistributedEngine(cfg, device, comm, optimizer_mode, "sample_major", dtype)
+    eng = DistributedEngine(cfg, device, comm, optimizer_mode, "sample_major", dtype, small_tables)
     # same RNG consumption order as the single-GPU factory: all notice tables, notice dense layers, then company
     full = []
     E = cfg.emb_dim

@@ -88,8 +88,10 @@ class _Ws:
 
 
 class TwoTowerEngine:
+    SMALL_TABLE_FLOATS = 2048  # tables with V*E <= this are "small": one-hot dense reduction + dense Adam, never sorted
+
     def __init__(self, cfg: TwoTowerConfig, device, optimizer_mode: str = "dense_exact", value_layout: str = "sample_major",
-                 dtype: str = "fp32"):
+                 dtype: str = "fp32", small_tables: bool = True):
         self.cfg = cfg
         if dtype not in ("fp32", "bf16"):
             raise ValueError(f"dtype must be 'fp32' or 'bf16', got {dtype}")
@@ -116,36 +118,29 @@ class TwoTowerEngine:
         if E % 4 != 0 or cfg.hidden[0] % 4 != 0:
             raise ValueError("emb_dim and tower_hidden_dims[0] must be multiples of 4 (128-bit vector path)")
         dev = self.device
-        vocab = list(cfg.notice_vocab) + list(cfg.company_vocab)
-        base, acc = [], 0
-        for v in vocab:
-            base.append(acc)
-            acc += int(v)
-        self.total_rows = acc
         self.K = (len(cfg.notice_keys), len(cfg.company_keys))
-        self.row_base_host = base
-        self.row_base = torch.tensor(base, dtype=torch.int64, device=dev)
-        self.vocab = torch.tensor(vocab, dtype=torch.int32, device=dev)
-        self.arena = torch.empty(self.total_rows, E, dtype=torch.float32, device=dev)
-        self.arena_m = torch.zeros_like(self.arena)
-        self.arena_v = torch.zeros_like(self.arena)
-        self.arena_grad: Optional[torch.Tensor] = None
         self.layout = DenseLayout(cfg)
-        P = self.layout.total
-        self.dense_w = torch.zeros(P, dtype=torch.float32, device=dev)
-        self.dense_g = torch.zeros(P, dtype=torch.float32, device=dev)
-        self.dense_m = torch.zeros(P, dtype=torch.float32, device=dev)
-        self.dense_v = torch.zeros(P, dtype=torch.float32, device=dev)
-        self.dense_w16 = torch.zeros(P, dtype=torch.bfloat16, device=dev) if dtype == "bf16" else None  # bf16 mirror for the GEMMs
+        self._plan_tables(small_tables and optimizer_mode == "dense_exact")
+        P_tot, RL = self.P_tot, self.total_rows
+        # ONE flat fp32 allocation: [dense params | small tables | large-table arena]; Adam moments mirror it
+        self.flat_w = torch.zeros(P_tot + RL * E, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros_like(self.flat_w)
+        self.flat_v = torch.zeros_like(self.flat_w)
+        self.dense_w, self.dense_m, self.dense_v = self.flat_w[:P_tot], self.flat_m[:P_tot], self.flat_v[:P_tot]
+        self.dense_g = torch.zeros(P_tot, dtype=torch.float32, device=dev)
+        self.arena = self.flat_w[P_tot:].view(RL, E)
+        self.arena_m, self.arena_v = self.flat_m[P_tot:].view(RL, E), self.flat_v[P_tot:].view(RL, E)
+        self.arena_grad: Optional[torch.Tensor] = None
+        self.dense_w16 = torch.zeros(self.layout.total, dtype=torch.bfloat16, device=dev) if dtype == "bf16" else None
         nblk = len(cfg.hidden) - 1
         self.bn_rm = [[torch.zeros(h, device=dev) for h in cfg.hidden[1:]] for _ in range(2)]
         self.bn_rv = [[torch.ones(h, device=dev) for h in cfg.hidden[1:]] for _ in range(2)]
         self.bn_nbt = [[torch.zeros((), dtype=torch.int64, device=dev) for _ in range(nblk)] for _ in range(2)]
         self.hyper = torch.zeros(native.HYPER_BYTES, dtype=torch.uint8, device=dev)
         self.stamp = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.row_begin = torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
-        self.row_end = torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
-        self.row_stamp = torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
+        self.row_begin = torch.zeros(max(self.total_rows, 1), dtype=torch.int32, device=dev)
+        self.row_end = torch.zeros(max(self.total_rows, 1), dtype=torch.int32, device=dev)
+        self.row_stamp = torch.zeros(max(self.total_rows, 1), dtype=torch.int32, device=dev)
         self._ws: Dict[int, _Ws] = {}
         self.rng_seed = 0x5EED
         self.rng_stream_base = 0  # distributed engines offset it by rank so ranks draw different dropout masks
@@ -175,13 +170,89 @@ class TwoTowerEngine:
         e1.record(st)
         prof.append((f"{name}[{self.profile_tag}]" if self.profile_tag else name, n_kernels, e0, e1))
 
+    def _alloc_rows(self, t: int, k: int, vocab: int, small: bool) -> int:
+        """Rows this process allocates for table (t,k). Distributed engines shard the large tables."""
+        return vocab
+
+    def _plan_tables(self, use_small: bool):
+        """Split the tables into classes and lay everything out in one flat buffer (see module docstring)."""
+        import numpy as np
+        cfg, E, dev = self.cfg, self.cfg.emb_dim, self.device
+        H0 = cfg.hidden[0]
+        unit = E * 64 // math.gcd(E, 64)
+        self.P_dense = (self.layout.total + unit - 1) // unit * unit
+        self.is_small, self.small_off, self.large_base, self.alloc_rows = [], [], [], []
+        s_off, l_row = 0, 0
+        large_rank, colmaps, small_tabs, small_floats, small_region = [], [], [], [], []
+        self.max_small_vocab = 1
+        for t in range(2):
+            _, keys, vocab, _ = cfg.tower(t)
+            sm, so, lb, ar, rank, cm, tabs = [], [], [], [], [], [], []
+            region0 = s_off
+            nl = 0
+            for k, v in enumerate(vocab):
+                small = bool(use_small and v * E <= self.SMALL_TABLE_FLOATS)
+                rows = self._alloc_rows(t, k, int(v), small)
+                sm.append(small)
+                ar.append(rows)
+                if small:
+                    so.append(s_off)
+                    lb.append(-1)
+                    rank.append(-1)
+                    tabs.append((k, int(v), H0 + k * E, s_off - region0))
+                    s_off += rows * E
+                    self.max_small_vocab = max(self.max_small_vocab, int(v))
+                else:
+                    so.append(-1)
+                    lb.append(l_row)
+                    rank.append(nl)
+                    cm.append(H0 + k * E)
+                    nl += 1
+                    l_row += rows
+            self.is_small.append(sm); self.small_off.append(so); self.large_base.append(lb); self.alloc_rows.append(ar)
+            large_rank += rank
+            colmaps.append(cm)
+            small_region.append(region0)
+            small_floats.append(s_off - region0)
+            arr = np.zeros(len(tabs), dtype=np.dtype([("key", "<i4"), ("vocab", "<i4"), ("col", "<i4"), ("pad", "<i4"), ("g_off", "<i8")]))
+            for i, (k, v, col, go) in enumerate(tabs):
+                arr[i] = (k, v, col, 0, go)
+            small_tabs.append(torch.from_numpy(arr.view(np.uint8).copy()).to(dev) if len(tabs) else None)
+        self.S_floats = s_off
+        self.P_tot = (self.P_dense + s_off + unit - 1) // unit * unit
+        self.total_rows = l_row  # rows of the large-table arena (sort keys live in [0, total_rows))
+        self.KL = (len(colmaps[0]), len(colmaps[1]))
+        self.n_small = (0 if small_tabs[0] is None else small_tabs[0].numel() // 24, 0 if small_tabs[1] is None else small_tabs[1].numel() // 24)
+        self.small_tabs, self.small_floats, self.small_region = small_tabs, small_floats, small_region
+        self.large_rank = torch.tensor(large_rank, dtype=torch.int32, device=dev)
+        self.colmap = [torch.tensor(c if c else [0], dtype=torch.int32, device=dev) for c in colmaps]
+        base, vocab_all = [], []
+        for t in range(2):
+            _, keys, vocab, _ = cfg.tower(t)
+            for k, v in enumerate(vocab):
+                if self.is_small[t][k]:
+                    base.append((self.P_dense + self.small_off[t][k]) // E)
+                else:
+                    base.append(self.P_tot // E + self.large_base[t][k])
+                vocab_all.append(int(v))
+        self.row_base_host = base
+        self.row_base = torch.tensor(base, dtype=torch.int64, device=dev)  # rows relative to flat_w
+        self.vocab = torch.tensor(vocab_all, dtype=torch.int32, device=dev)
+
     def dense(self, name: str, which: str = "w") -> torch.Tensor:
         return self.layout.view({"w": self.dense_w, "g": self.dense_g, "m": self.dense_m, "v": self.dense_v}[which], name)
 
-    def table_rows(self, t: int, k: int) -> Tuple[int, int]:
-        gk = k if t == 0 else self.K[0] + k
-        v = (self.cfg.notice_vocab if t == 0 else self.cfg.company_vocab)[k]
-        return self.row_base_host[gk], self.row_base_host[gk] + v
+    def table_view(self, t: int, k: int, which: str = "w") -> torch.Tensor:
+        """[rows, E] view of table (t,k): weights / Adam moments / gradient (gradient of a large table needs arena_grad)."""
+        E = self.cfg.emb_dim
+        rows = self.alloc_rows[t][k]
+        if self.is_small[t][k]:
+            buf = {"w": self.dense_w, "m": self.dense_m, "v": self.dense_v, "g": self.dense_g}[which]
+            o = self.P_dense + self.small_off[t][k]
+            return buf[o:o + rows * E].view(rows, E)
+        buf = {"w": self.arena, "m": self.arena_m, "v": self.arena_v, "g": self.arena_grad}[which]
+        lo = self.large_base[t][k]
+        return buf[lo:lo + rows]
 
     def workspace(self, B: int) -> _Ws:
         ws = self._ws.get(B)
@@ -194,7 +265,7 @@ class TwoTowerEngine:
         f32 = dict(dtype=torch.float32, device=dev)
         ws.c, ws.dc, ws.h, ws.y, ws.dh, ws.dy = [], [], [], [], [], []
         ws.mean, ws.rstd, ws.z, ws.e, ws.nrm, ws.de, ws.dz = [], [], [], [], [], [], []
-        n_tot = B * (self.K[0] + self.K[1])
+        n_tot = B * (self.KL[0] + self.KL[1])
         ws.rows = torch.zeros(max(n_tot, 1), dtype=torch.int32, device=dev)
         ws.sorted_rows = torch.zeros_like(ws.rows)
         ws.sorted_slots = torch.zeros_like(ws.rows)
@@ -245,8 +316,10 @@ class TwoTowerEngine:
         ws.inv_col = torch.empty(B, **f32)
         ws.partial = torch.zeros(8, dtype=torch.float64, device=dev)
         ws.out5 = torch.zeros(5, **f32)
-        ws.sort_ws = torch.empty(q("tt_ebc_sort_workspace_bytes", n_tot, self.total_rows), dtype=torch.uint8, device=dev)
+        ws.sort_ws = torch.empty(q("tt_ebc_sort_workspace_bytes", n_tot, max(self.total_rows, 1)), dtype=torch.uint8, device=dev)
         ws.piece_ws = torch.empty(q("tt_ebc_piece_workspace_bytes", n_tot, E), dtype=torch.uint8, device=dev)
+        ws.small_ws = [torch.empty(q("tt_ebc_small_workspace_bytes", B, max(self.small_floats[t], 1)), dtype=torch.uint8, device=dev)
+                       for t in range(2)]
         self._ws[B] = ws
         return ws
 
@@ -304,11 +377,12 @@ class TwoTowerEngine:
                 continue
             K = self.K[t]
             k0 = 0 if t == 0 else self.K[0]
-            rows_off = 0 if t == 0 else B * self.K[0]
+            rows_off = 0 if t == 0 else B * self.KL[0]
             self.profile_tag = self.cfg.tower(t)[0]
-            self._call("tt_ebc_forward", ptr(self.arena), self.row_base.data_ptr() + 8 * k0, self.vocab.data_ptr() + 4 * k0,
-                       ptr(v), 0, B * K, B, K, E, layout, ptr(ws.c[t]), self.act, H0 + K * E, H0,
-                       ws.rows.data_ptr() + 4 * rows_off, 0, 0, s)
+            self._call("tt_ebc_forward_mixed", ptr(self.flat_w), self.row_base.data_ptr() + 8 * k0, self.vocab.data_ptr() + 4 * k0,
+                       ptr(v), B, K, E, layout, ptr(ws.c[t]), self.act, H0 + K * E, H0, self.large_rank.data_ptr() + 4 * k0,
+                       self.KL[t], self.P_tot // E, ws.rows.data_ptr() + 4 * rows_off, s)
+        ws.values, ws.layout = list(values), layout
 
     def tower_forward(self, t: int, ws: _Ws, dense: torch.Tensor, values: Optional[torch.Tensor], train: bool,
                       layout: int = TT_LAYOUT_SAMPLE_MAJOR, masks: Optional[Sequence[torch.Tensor]] = None):
@@ -467,11 +541,26 @@ class TwoTowerEngine:
         self._lin_wgrad(ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", B, H0,
                         dense_dim, ws.wg_ws[t])
 
-    def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool):
-        """sort-by-row dedup of both towers' (row, slot) pairs, then segment-sum (+ fused Adam)."""
+    def small_tables_backward(self, ws: _Ws):
+        """Gradient of the small tables into the flat dense gradient buffer (dense one-hot reduction, deterministic)."""
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
-        n0, n1 = B * self.K[0], B * self.K[1]
+        H0 = cfg.hidden[0]
+        for t in range(2):
+            if self.n_small[t] == 0:
+                continue
+            self.profile_tag = cfg.tower(t)[0]
+            gout = self.dense_g.data_ptr() + 4 * (self.P_dense + self.small_region[t])
+            self._call("tt_ebc_small_backward", ptr(ws.values[t]), B, self.K[t], ws.layout, ptr(ws.dc[t]), H0 + self.K[t] * E, self.act,
+                       E, ptr(self.small_tabs[t]), self.n_small[t], self.max_small_vocab, self.small_floats[t], gout,
+                       ptr(ws.small_ws[t]), ws.small_ws[t].numel(), s, n_kernels=2)
+
+    def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool):
+        """Large tables: sort-by-row dedup of both towers' (row, slot) pairs, then segment-sum (+ fused Adam)."""
+        cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
+        n0, n1 = B * self.KL[0], B * self.KL[1]
         n = n0 + n1
+        if n == 0 or self.total_rows == 0:
+            return
         H0 = cfg.hidden[0]
         self.profile_tag = ""
         self.stamp.add_(1)
@@ -483,9 +572,10 @@ class TwoTowerEngine:
         self._call("tt_ebc_backward_adam", ptr(self.arena) if apply_adam else 0, ptr(self.arena_m) if apply_adam else 0,
                    ptr(self.arena_v) if apply_adam else 0, ptr(self.arena_grad) if want_dense_grad else 0,
                    self.total_rows, E, ptr(ws.sorted_rows), ptr(ws.sorted_slots), n, ptr(self.row_begin), ptr(self.row_end),
-                   ptr(self.row_stamp), 0, ptr(self.stamp), ptr(ws.dc[0]), H0 + self.K[0] * E, H0, self.K[0], n0,
-                   ptr(ws.dc[1]), H0 + self.K[1] * E, H0, self.K[1], n1, self.act, ptr(ws.piece_ws), ws.piece_ws.numel(),
-                   ptr(self.hyper), self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, 0, 0, 0, s, n_kernels=2)
+                   ptr(self.row_stamp), 0, ptr(self.stamp), ptr(ws.dc[0]), H0 + self.K[0] * E, H0, max(self.KL[0], 1), n0,
+                   ptr(ws.dc[1]), H0 + self.K[1] * E, H0, max(self.KL[1], 1), n1, self.act, ptr(ws.piece_ws), ws.piece_ws.numel(),
+                   ptr(self.hyper), self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, 0, 0, 0, ptr(self.colmap[0]),
+                   ptr(self.colmap[1]), s, n_kernels=2)
 
     def backward(self, ws: _Ws, dloss: float = 1.0):
         self.loss_backward(ws, dloss)
@@ -499,6 +589,7 @@ class TwoTowerEngine:
         else:
             self.tower_backward(0, ws)
             self.tower_backward(1, ws)
+        self.small_tables_backward(ws)
 
     # ------------------------------------------------------------------ optimizer
     def hyper_advance(self, lr: float, warmup_steps: int, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
@@ -507,7 +598,7 @@ class TwoTowerEngine:
 
     def dense_adam(self):
         self._call("tt_dense_adam", ptr(self.dense_w), ptr(self.dense_g), ptr(self.dense_m), ptr(self.dense_v),
-                   self.layout.total, ptr(self.hyper), self._stream())
+                   self.P_tot, ptr(self.hyper), self._stream())
 
     def fused_step(self, notice_dense, notice_values, company_dense, company_values, lr=1e-3, warmup_steps=0,
                    betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, layout=None, masks=None):

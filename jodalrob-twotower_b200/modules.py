@@ -90,8 +90,7 @@ class CategoricalEmbedder(nn.Module):
         self.vocab_sizes = {k: int(v) for k, v in zip(keys, vocab)}
         self.embeddings = nn.ModuleDict()
         for ki, k in enumerate(self.keys):
-            lo, hi = engine.table_rows(tower, ki)
-            self.embeddings[k] = _Table(engine.arena[lo:hi])
+            self.embeddings[k] = _Table(engine.table_view(tower, ki))
 
     def forward(self, kjt, return_dict: bool = True):
         """Pooled lookup of every key (forward only; training goes through TwoTowerTrainTask).
@@ -247,8 +246,7 @@ class _TrainStepFn(torch.autograd.Function):
         grads = []
         for kind, ref in task._param_src:
             if kind == "table":
-                lo, hi = ref
-                grads.append(eng.arena_grad[lo:hi].clone())
+                grads.append(eng.table_view(ref[0], ref[1], "g").clone())
             else:
                 grads.append(eng.dense(ref, "g").clone())
         return (None,) * 7 + tuple(grads)
@@ -283,7 +281,7 @@ class TwoTowerTrainTask(nn.Module):
                 tower = 0 if short.startswith("notice") else 1
                 key = short.split(".embeddings.")[1].rsplit(".weight", 1)[0]
                 keys = eng.cfg.notice_keys if tower == 0 else eng.cfg.company_keys
-                self._param_src.append(("table", eng.table_rows(tower, keys.index(key))))
+                self._param_src.append(("table", (tower, keys.index(key))))
             else:
                 self._param_src.append(("dense", short))
 
@@ -406,14 +404,13 @@ class FusedAdam:
 
     def state_dict(self):
         eng = self.task.engine
-        return {"hyper": eng.hyper.clone(), "arena_m": eng.arena_m.clone(), "arena_v": eng.arena_v.clone(),
-                "dense_m": eng.dense_m.clone(), "dense_v": eng.dense_v.clone(),
+        return {"hyper": eng.hyper.clone(), "flat_m": eng.flat_m.clone(), "flat_v": eng.flat_v.clone(),
                 "config": {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
                            "warmup_steps": self.warmup_steps}}
 
     def load_state_dict(self, sd):
         eng = self.task.engine
-        for k in ("hyper", "arena_m", "arena_v", "dense_m", "dense_v"):
+        for k in ("hyper", "flat_m", "flat_v"):
             getattr(eng, k).copy_(sd[k])
         c = sd["config"]
         self.lr, self.betas, self.eps, self.weight_decay = c["lr"], tuple(c["betas"]), c["eps"], c["weight_decay"]
@@ -443,8 +440,7 @@ def _init_like_reference(engine: TwoTowerEngine):
         name, keys, vocab, dense_dim = cfg.tower(t)
         pre = f"{name}_tower."
         for ki, v in enumerate(vocab):
-            lo, hi = engine.table_rows(t, ki)
-            engine.arena[lo:hi].copy_(nn.Embedding(v, cfg.emb_dim).weight.detach())
+            engine.table_view(t, ki).copy_(nn.Embedding(v, cfg.emb_dim).weight.detach())
         lin = nn.Linear(dense_dim, cfg.hidden[0])
         engine.dense(pre + "dense_projection.weight").copy_(lin.weight.detach())
         engine.dense(pre + "dense_projection.bias").copy_(lin.bias.detach())

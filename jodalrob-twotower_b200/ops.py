@@ -29,7 +29,7 @@ def ebc_forward(engine, tower: int, values: torch.Tensor, B: int, layout="sample
     n_values = values.numel()
     rows = torch.empty(max(n_values, 1), dtype=torch.int32, device=engine.device) if want_rows else None
     slots = torch.empty(max(n_values, 1), dtype=torch.int32, device=engine.device) if want_rows else None
-    engine._call("tt_ebc_forward", ptr(engine.arena), engine.row_base.data_ptr() + 8 * k0, engine.vocab.data_ptr() + 4 * k0,
+    engine._call("tt_ebc_forward", ptr(engine.flat_w), engine.row_base.data_ptr() + 8 * k0, engine.vocab.data_ptr() + 4 * k0,
                  ptr(values), ptr(bag_offsets), n_values, B, K, E, _lay(layout), ptr(out),
                  TT_F32 if out_dtype == torch.float32 else TT_BF16, K * E, 0, ptr(rows), ptr(slots), 0, _stream(engine.device))
     return (out, rows, slots) if want_rows else out
