@@ -290,6 +290,12 @@ int tt_simce_backward(const void* X, const void* Y, int64_t Bx, int64_t By, int3
                       tt_stream_t stream);
 /* Test hook: make the tcgen05 (bf16) sim-CE kernels stage operands with the generic-proxy loader instead of TMA. */
 int tt_debug_simce_force_manual_loads(int32_t on);
+/* Profiling knobs for the tcgen05 kernels (results become meaningless): 2 = no TMEM loads, 8 = no TMA after the ring
+ * fill, 16 = no MMAs (barrier skeleton only). */
+int tt_debug_simce_knobs(int32_t bits);
+/* Profiling: CTA 0 of the next metric-pass forward kernels writes clock64 stamps into an i64[3*2048] device buffer
+ * ([mma | epilogue | loader][tile*4 + event]); pass NULL to switch it off. */
+int tt_debug_simce_timeline(void* d_buf_3x2048_i64);
 /* Lazily materialise S (eval / predict_batch / return_metrics "similarity_matrix" only). */
 int tt_similarity_matrix(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype,
                          float inv_temp, float* S, int64_t lds, tt_stream_t stream);

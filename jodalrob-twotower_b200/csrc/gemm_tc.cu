@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 }
 
 // column sums of a bf16 matrix (bias gradients), fp64 partials like the fp32 path
-constexpr int GCS_ROWS = 256;
+constexpr int GCS_ROWS = 64;
 __global__ void __launch_bounds__(256)
 colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ X, int64_t ld, int64_t M, int N, double* __restrict__ part) {
   __shared__ double s[8][33];
@@ -220,12 +220,15 @@ colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ X, int64_t ld, int6
     part[(int64_t)blockIdx.y * N + n] = t;
   }
 }
-__global__ void colsum_bf16_final_kernel(const double* __restrict__ part, int chunks, int N, float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_bf16_final_kernel(const double* __restrict__ part, int chunks, int N, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per column, fixed shuffle tree
   if (n >= N) return;
   double t = 0.0;
-  for (int c = 0; c < chunks; ++c) t += part[(int64_t)c * N + n];
-  out[n] = (float)t;
+  for (int c = lane; c < chunks; c += 32) t += part[(int64_t)c * N + n];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) out[n] = (float)t;
 }
 
 static size_t gt_smem_bytes(int tn) { return 1024 + (size_t)GT_STAGES * (ATOM_BYTES + tn * 128) + sizeof(GemmTcSmem) + 64; }
@@ -338,7 +341,7 @@ int tt_linear_wgrad_bf16(const void* dY, int64_t ldy, const void* X, int64_t ldx
     double* cpart = reinterpret_cast<double*>((char*)workspace + (((int64_t)splits * N * K * 4 + 255) / 256 * 256));
     const int chunks = (int)((M + GCS_ROWS - 1) / GCS_ROWS);
     colsum_bf16_partial_kernel<<<dim3(ceil_div(N, 32), chunks), 256, 0, s>>>((const __nv_bfloat16*)dY, ldy, M, N, cpart);
-    colsum_bf16_final_kernel<<<ceil_div(N, 128), 128, 0, s>>>(cpart, chunks, N, dbias);
+    colsum_bf16_final_kernel<<<ceil_div(N, 8), 256, 0, s>>>(cpart, chunks, N, dbias);
   }
   TT_LAUNCH_CHECK("linear_wgrad_bf16");
   return TT_OK;

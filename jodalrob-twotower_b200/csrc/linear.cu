@@ -14,7 +14,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int64_t str
 }
 
 // column sums of X[M,N] in two fixed levels: chunk partials (float) then a sequential double sum
-constexpr int CS_ROWS = 256;
+constexpr int CS_ROWS = 64;
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int N, double* __restrict__ part) {
   __shared__ double s[8][33];
@@ -34,12 +34,15 @@ colsum_partial_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int N,
     part[(int64_t)blockIdx.y * N + n] = t;
   }
 }
-__global__ void colsum_final_kernel(const double* __restrict__ part, int chunks, int N, float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_final_kernel(const double* __restrict__ part, int chunks, int N, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per column, fixed shuffle tree
   if (n >= N) return;
   double t = 0.0;
-  for (int c = 0; c < chunks; ++c) t += part[(int64_t)c * N + n];
-  out[n] = (float)t;
+  for (int c = lane; c < chunks; c += 32) t += part[(int64_t)c * N + n];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) out[n] = (float)t;
 }
 
 static int pick_splits(int64_t M, int tiles) {
@@ -130,7 +133,7 @@ int tt_linear_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, flo
     double* cpart = reinterpret_cast<double*>(part + (((int64_t)splits * N * K + 1) & ~(int64_t)1));
     const int chunks = (int)((M + CS_ROWS - 1) / CS_ROWS);
     colsum_partial_kernel<<<dim3(ceil_div(N, 32), chunks), 256, 0, s>>>((const float*)dY, ldy, M, N, cpart);
-    colsum_final_kernel<<<ceil_div(N, 128), 128, 0, s>>>(cpart, chunks, N, dbias);
+    colsum_final_kernel<<<ceil_div(N, 8), 256, 0, s>>>(cpart, chunks, N, dbias);
   }
   TT_LAUNCH_CHECK("linear_wgrad");
   return TT_OK;

@@ -144,13 +144,13 @@ simce_finalize_kernel(const float* __restrict__ row_sumexp, const float* __restr
   for (int64_t i = t; i < Bx; i += 1024) {
     const float se = row_sumexp[i];
     inv_row[i] = 1.f / se;
-    const double lse_r = (double)inv_temp + log((double)se);
+    const double lse_r = (double)inv_temp + (double)logf(se);  // fp32 log (1 ulp) is plenty: the sum over rows is fp64
     const double d = (double)diag[i];
     const double rss = row_sum_s ? (double)row_sum_s[i] : 0.0;
     a[0] += lse_r - (1.0 - ls) * d - (double)ls * inv_bg * rss;
     const int64_t j = diag_offset + i;
     if (j < By) {
-      const double lse_c = (double)inv_temp + log((double)col_sumexp[j]);
+      const double lse_c = (double)inv_temp + (double)logf(col_sumexp[j]);
       const double css = col_sum_s ? (double)col_sum_s[j] : 0.0;
       a[1] += lse_c - (1.0 - ls) * d - (double)ls * inv_bg * css;
     }
@@ -303,6 +303,16 @@ int64_t tt_simce_workspace_bytes(int64_t Bx, int64_t By, int32_t F) {
   const int64_t simt = 4 * a256(nCT * Bx * 4) + 2 * a256(nRT * By * 4) + 256;
   const int64_t tc = (F == 64 || F == 128) ? simce_tc_workspace_bytes(Bx, By, F) : 0;
   return simt > tc ? simt : tc;
+}
+
+int tt_debug_simce_timeline(void* d_buf_3x2048_i64) {
+  simce_tc_set_timeline((long long*)d_buf_3x2048_i64);
+  return TT_OK;
+}
+
+int tt_debug_simce_knobs(int32_t bits) {
+  simce_tc_set_debug(bits);
+  return TT_OK;
 }
 
 /* test hook: force the generic-proxy operand loader instead of TMA in the tcgen05 kernels */

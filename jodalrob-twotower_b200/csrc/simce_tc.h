@@ -11,4 +11,6 @@ int simce_tc_bwd(const void* X, const void* Y, int64_t Bx, int64_t By, int F, fl
                  const float* inv_x, const float* inv_y, float gscale, float tgt_diag, float tgt_off, float* dX, void* workspace,
                  cudaStream_t s);
 void simce_tc_set_force_manual(int v);
+void simce_tc_set_debug(int v);
+void simce_tc_set_timeline(long long* buf);
 }  // namespace tt

@@ -5,7 +5,7 @@
 
 namespace tt {
 
-constexpr int BN_ROWS = 256;  // rows per partial chunk
+constexpr int BN_ROWS = 64;  // rows per partial chunk (8 rows per thread): enough CTAs to cover the machine
 
 template <typename T>
 __device__ __forceinline__ float keep_scale(const uint8_t* mask_in, const tt_adam_hyper* hyp, uint32_t stream,
@@ -61,16 +61,16 @@ bn_partial_kernel(const T* __restrict__ X, int64_t ldx, const T* __restrict__ H,
   }
 }
 
-__global__ void bn_partial_final_kernel(const double* __restrict__ part, int chunks, int N, double* __restrict__ sums) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  double t0 = 0.0, t1 = 0.0;
-  for (int c = 0; c < chunks; ++c) {
-    t0 += part[((int64_t)c * 2 + 0) * N + n];
-    t1 += part[((int64_t)c * 2 + 1) * N + n];
-  }
-  sums[n] = t0;
-  sums[N + n] = t1;
+// one warp per output column: lanes stride over the chunk partials, then a fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) bn_partial_final_kernel(const double* __restrict__ part, int chunks, int N, double* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 8 + (threadIdx.x >> 5);  // column index in [0, 2N): (which sum) * N + n
+  if (col >= 2 * N) return;
+  double t = 0.0;
+  for (int c = lane; c < chunks; c += 32) t += part[(int64_t)c * 2 * N + col];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) sums[col] = t;
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long count, int N, float eps, float momentum,
@@ -206,7 +206,7 @@ int tt_bn_stats(const void* h, int64_t ldh, int64_t M, int32_t N, int32_t act_dt
   else
     bn_partial_kernel<__nv_bfloat16, 0><<<grid, 256, 0, s>>>((const __nv_bfloat16*)h, ldh, nullptr, 0, M, N, nullptr,
                                                              nullptr, 0.f, nullptr, nullptr, 0, (double*)workspace);
-  bn_partial_final_kernel<<<ceil_div(N, 128), 128, 0, s>>>((const double*)workspace, chunks, N, sums);
+  bn_partial_final_kernel<<<ceil_div(2 * N, 8), 256, 0, s>>>((const double*)workspace, chunks, N, sums);
   TT_LAUNCH_CHECK("bn_stats");
   return TT_OK;
 }
@@ -265,7 +265,7 @@ int tt_bn_backward_reduce(const void* dy, int64_t lddy, const void* h, int64_t l
     bn_partial_kernel<__nv_bfloat16, 1><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)h, ldh,
                                                              M, N, mean, rstd, dropout_p, mask_in, d_hyper, rng_stream,
                                                              (double*)workspace);
-  bn_partial_final_kernel<<<ceil_div(N, 128), 128, 0, s>>>((const double*)workspace, chunks, N, sums);
+  bn_partial_final_kernel<<<ceil_div(2 * N, 8), 256, 0, s>>>((const double*)workspace, chunks, N, sums);
   TT_LAUNCH_CHECK("bn_backward_reduce");
   return TT_OK;
 }

@@ -288,12 +288,14 @@ class DistributedEngine(TwoTowerEngine):
         inv_t = 1.0 / cfg.temperature
         self.comm.all_gather(ws.e_all[0], ws.e[0])
         self.comm.all_gather(ws.e_all[1], ws.e[1])
+        css = ptr(ws.col_sum_s) if cfg.label_smoothing > 0 else 0
         self._call("tt_simce_forward", ptr(ws.e[0]), ptr(ws.e_all[1]), B, Bg, cfg.final_dim, self.emb_tt, inv_t, off,
-                   ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), ptr(ws.col_sum_s), ptr(ws.diag), ptr(ws.row_argmax),
-                   ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=3)
+                   ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), css, ptr(ws.diag), ptr(ws.row_argmax),
+                   ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=4)
         self.comm.all_reduce(ws.col_sumexp)
-        self.comm.all_reduce(ws.col_sum_s)
-        self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), ptr(ws.col_sum_s),
+        if css:
+            self.comm.all_reduce(ws.col_sum_s)
+        self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), css,
                    ptr(ws.diag), ptr(ws.row_argmax), B, Bg, off, Bg, inv_t, cfg.label_smoothing, ptr(ws.inv_row),
                    ptr(ws.inv_col), ptr(ws.partial), s)
         self.comm.all_reduce(ws.partial)

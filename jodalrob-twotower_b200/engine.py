@@ -439,10 +439,11 @@ class TwoTowerEngine:
         cfg, B, s = self.cfg, ws.B, self._stream()
         self.profile_tag = ""
         inv_t = 1.0 / cfg.temperature
+        css = ptr(ws.col_sum_s) if cfg.label_smoothing > 0 else 0  # column sums of S are only needed for label smoothing
         self._call("tt_simce_forward", ptr(ws.e[0]), ptr(ws.e[1]), B, B, cfg.final_dim, self.emb_tt, inv_t, 0, ptr(ws.row_sumexp),
-                   ptr(ws.col_sumexp), ptr(ws.row_sum_s), ptr(ws.col_sum_s), ptr(ws.diag), ptr(ws.row_argmax),
-                   ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=3)
-        self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), ptr(ws.col_sum_s),
+                   ptr(ws.col_sumexp), ptr(ws.row_sum_s), css, ptr(ws.diag), ptr(ws.row_argmax),
+                   ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=4)
+        self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), css,
                    ptr(ws.diag), ptr(ws.row_argmax), B, B, 0, B, inv_t, cfg.label_smoothing, ptr(ws.inv_row),
                    ptr(ws.inv_col), ptr(ws.partial), s)
         self._call("tt_simce_scalars", ptr(ws.partial), B, ptr(ws.out5), s)
