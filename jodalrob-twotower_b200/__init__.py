@@ -12,7 +12,7 @@ def __getattr__(name):
     # modules/engine need the CUDA library; resolve lazily so `import jodalrob_twotower_b200` works for
     # the host-side helpers (KJT, schema) everywhere, while any compute entry fails loudly without the .so
     if name in ("CategoricalEmbedder", "BaseTower", "NoticeTower", "CompanyTower", "TwoTowerModel", "TwoTowerTrainTask",
-                "create_two_tower_model", "create_two_tower_train_task", "FusedAdam", "FusedWarmupScheduler"):
+                "create_two_tower_model", "create_two_tower_train_task", "FusedAdam", "FusedWarmupScheduler", "GraphedFusedStep"):
         from . import modules
         return getattr(modules, name)
     if name in ("TwoTowerEngine", "TwoTowerConfig"):

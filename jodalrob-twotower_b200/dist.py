@@ -321,7 +321,19 @@ class DistributedEngine(TwoTowerEngine):
         # buffers are complete before anyone pulls from them
         self.comm.all_reduce(self.dense_g)
 
-    def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool):
+    def embedding_sort(self, ws: _Ws):
+        B, s = ws.B, self._stream()
+        n_l = B * (self.KL[0] + self.KL[1])
+        if n_l == 0 or self.total_rows == 0:
+            return
+        cap = n_l * self.world
+        self.profile_tag = "sharded"
+        self.stamp.add_(1)
+        self._call("tt_ebc_sort_rows", ptr(ws.rows), ptr(ws.slots), cap, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
+                   ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
+                   0, ptr(self.stamp), ptr(ws.n_owned), s, n_kernels=7)
+
+    def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool, sorted_already: bool = False):
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
         K0, K1 = self.K
         KL0, KL1 = self.KL
@@ -330,11 +342,9 @@ class DistributedEngine(TwoTowerEngine):
             return
         cap = n_l * self.world
         H0 = cfg.hidden[0]
+        if not sorted_already:
+            self.embedding_sort(ws)
         self.profile_tag = "sharded"
-        self.stamp.add_(1)
-        self._call("tt_ebc_sort_rows", ptr(ws.rows), ptr(ws.slots), cap, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
-                   ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
-                   0, ptr(self.stamp), ptr(ws.n_owned), s, n_kernels=7)
         if want_dense_grad and self.arena_grad is None:
             self.arena_grad = torch.zeros_like(self.arena)
         self._call("tt_ebc_backward_adam", ptr(self.arena) if apply_adam else 0, ptr(self.arena_m) if apply_adam else 0,

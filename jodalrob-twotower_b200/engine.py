@@ -148,6 +148,7 @@ class TwoTowerEngine:
         # inside a CUDA graph capture this becomes two parallel branches)
         self.two_streams = True
         self._side = torch.cuda.Stream(self.device)
+        self._sort_stream = torch.cuda.Stream(self.device)
         self.launches = 0  # kernels launched through the C ABI (bench.py's gpu_launches)
         self.profile: Optional[list] = None  # set to [] to collect (tag, n_kernels, ev0, ev1) per C-ABI call
         self.profile_tag = ""
@@ -450,7 +451,7 @@ class TwoTowerEngine:
         return ws.out5
 
     def forward(self, notice_dense, notice_values, company_dense, company_values, train: bool = True,
-                layout: Optional[str] = None, masks=None) -> Tuple[torch.Tensor, _Ws]:
+                layout: Optional[str] = None, masks=None, sort_on_side: bool = False) -> Tuple[torch.Tensor, _Ws]:
         B = notice_dense.shape[0]
         if company_dense.shape[0] != B:
             raise ValueError(f"notice/company batch sizes differ: {B} vs {company_dense.shape[0]}")
@@ -464,6 +465,10 @@ class TwoTowerEngine:
         ws.inputs = (notice_dense.contiguous(), company_dense.contiguous())
         self.refresh_bf16_weights()
         self.embedding_forward(ws, [notice_values, company_values], lay)
+        if sort_on_side:  # the index side of the sparse backward only needs the looked-up rows
+            self._sort_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._sort_stream):
+                self.embedding_sort(ws)
         m0, m1 = (None, None) if masks is None else (masks[0], masks[1])
         if self.two_streams:
             main = torch.cuda.current_stream(self.device)
@@ -542,11 +547,11 @@ class TwoTowerEngine:
         self._lin_wgrad(ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", B, H0,
                         dense_dim, ws.wg_ws[t])
 
-    def small_tables_backward(self, ws: _Ws):
+    def small_tables_backward(self, ws: _Ws, towers=(0, 1)):
         """Gradient of the small tables into the flat dense gradient buffer (dense one-hot reduction, deterministic)."""
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
         H0 = cfg.hidden[0]
-        for t in range(2):
+        for t in towers:
             if self.n_small[t] == 0:
                 continue
             self.profile_tag = cfg.tower(t)[0]
@@ -555,19 +560,30 @@ class TwoTowerEngine:
                        E, ptr(self.small_tabs[t]), self.n_small[t], self.max_small_vocab, self.small_floats[t], gout,
                        ptr(ws.small_ws[t]), ws.small_ws[t].numel(), s, n_kernels=2)
 
-    def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool):
-        """Large tables: sort-by-row dedup of both towers' (row, slot) pairs, then segment-sum (+ fused Adam)."""
+    def embedding_sort(self, ws: _Ws):
+        """Large tables, index side: sort-by-row dedup of both towers' (row, slot) pairs. Depends only on the forward
+        lookup, so the fused step runs it on a side stream underneath the towers and the loss."""
+        B, s = ws.B, self._stream()
+        n = B * (self.KL[0] + self.KL[1])
+        if n == 0 or self.total_rows == 0:
+            return
+        self.profile_tag = ""
+        self.stamp.add_(1)
+        self._call("tt_ebc_sort_rows", ptr(ws.rows), 0, n, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
+                   ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
+                   0, ptr(self.stamp), 0, s, n_kernels=7)
+
+    def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool, sorted_already: bool = False):
+        """Large tables: (sort-by-row dedup, then) segment-sum of the pooled gradients (+ fused Adam)."""
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
         n0, n1 = B * self.KL[0], B * self.KL[1]
         n = n0 + n1
         if n == 0 or self.total_rows == 0:
             return
         H0 = cfg.hidden[0]
+        if not sorted_already:
+            self.embedding_sort(ws)
         self.profile_tag = ""
-        self.stamp.add_(1)
-        self._call("tt_ebc_sort_rows", ptr(ws.rows), 0, n, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
-                   ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
-                   0, ptr(self.stamp), 0, s, n_kernels=7)
         if want_dense_grad and self.arena_grad is None:
             self.arena_grad = torch.zeros_like(self.arena)
         self._call("tt_ebc_backward_adam", ptr(self.arena) if apply_adam else 0, ptr(self.arena_m) if apply_adam else 0,
@@ -585,12 +601,14 @@ class TwoTowerEngine:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self.tower_backward(1, ws)
+                self.small_tables_backward(ws, (1,))
             self.tower_backward(0, ws)
+            self.small_tables_backward(ws, (0,))
             main.wait_stream(self._side)
         else:
             self.tower_backward(0, ws)
             self.tower_backward(1, ws)
-        self.small_tables_backward(ws)
+            self.small_tables_backward(ws)
 
     # ------------------------------------------------------------------ optimizer
     def hyper_advance(self, lr: float, warmup_steps: int, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
@@ -605,11 +623,20 @@ class TwoTowerEngine:
                    betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, layout=None, masks=None):
         """hyper_advance -> forward -> backward -> sparse-dedup + Adam on tables -> Adam on dense. Returns out5."""
         self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
-        out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks)
+        out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
         self.backward(ws)
         self.reduce_dense_grads()
-        self.embedding_backward(ws, apply_adam=True, want_dense_grad=False)
-        self.dense_adam()
+        main = torch.cuda.current_stream(self.device)
+        main.wait_stream(self._sort_stream)  # the sort-dedup ran underneath the towers and the loss
+        if self.two_streams:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.dense_adam()
+            self.embedding_backward(ws, apply_adam=True, want_dense_grad=False, sorted_already=True)
+            main.wait_stream(self._side)
+        else:
+            self.embedding_backward(ws, apply_adam=True, want_dense_grad=False, sorted_already=True)
+            self.dense_adam()
         return out5
 
     def reduce_dense_grads(self):

@@ -27,7 +27,7 @@ from .kjt import KeyedJaggedTensor
 from .schema import vocab_sizes_from_metadata
 
 __all__ = ["CategoricalEmbedder", "BaseTower", "NoticeTower", "CompanyTower", "TwoTowerModel", "TwoTowerTrainTask",
-           "create_two_tower_model", "create_two_tower_train_task", "FusedAdam", "FusedWarmupScheduler"]
+           "create_two_tower_model", "create_two_tower_train_task", "FusedAdam", "FusedWarmupScheduler", "GraphedFusedStep"]
 
 
 class _Table(nn.Module):
@@ -381,6 +381,73 @@ class TwoTowerTrainTask(nn.Module):
         row_hit = (similarity_matrix.argmax(dim=1) == idx).float().mean().item()
         col_hit = (similarity_matrix.argmax(dim=0) == idx).float().mean().item()
         print(f"[Positive Pair Alignment Check] notice->company top-1 {row_hit:.3f}, company->notice top-1 {col_hit:.3f}")
+
+
+class GraphedFusedStep:
+    """The whole fused train step captured once as a CUDA graph (the step is launch-bound at the reference's model size:
+    ~85 kernels of a few microseconds each). Every per-step scalar (Adam step, lr schedule, bias corrections, dropout
+    counter, dedup stamp) lives on the device, so replaying the graph IS a new optimizer step.
+
+        step = GraphedFusedStep(task, example_batch)      # needs FusedAdam(task, ...) attached
+        for batch in loader: out5 = step(batch)           # [loss, acc, pos_mean, neg_mean, gap] on the device
+    """
+
+    def __init__(self, task: "TwoTowerTrainTask", example_batch):
+        if task._fused_opt is None:
+            raise RuntimeError("attach a FusedAdam(task, ...) before capturing the fused step")
+        self.task = task
+        eng = task.engine
+        task._sync_cfg()
+        nd, nv, cd, cv, lay = task._unpack(example_batch)
+        self.layout = lay
+        self.static = [torch.empty_like(t.contiguous()) for t in (nd, nv, cd, cv)]
+        for s, t in zip(self.static, (nd, nv, cd, cv)):
+            s.copy_(t)
+        o = task._fused_opt
+        self._args = (o.lr, o.warmup_steps, o.betas, o.eps, o.weight_decay)
+        hyper0, stamp0 = eng.hyper.clone(), eng.stamp.clone()
+        state0 = (eng.flat_w.clone(), eng.flat_m.clone(), eng.flat_v.clone(),
+                  [[b.clone() for b in bl] for bl in eng.bn_rm], [[b.clone() for b in bl] for bl in eng.bn_rv],
+                  [[b.clone() for b in bl] for bl in eng.bn_nbt])
+        side = torch.cuda.Stream(eng.device)
+        side.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(side):  # warm-up (allocates the workspace, sets kernel attributes)
+            for _ in range(2):
+                self._run()
+        torch.cuda.current_stream(eng.device).wait_stream(side)
+        torch.cuda.synchronize(eng.device)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = eng.launches
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+        self.launches_per_step = eng.launches - l0
+        # capture and warm-up must not count as training: restore the parameters and optimizer state
+        torch.cuda.synchronize(eng.device)
+        eng.hyper.copy_(hyper0); eng.stamp.copy_(stamp0)
+        eng.flat_w.copy_(state0[0]); eng.flat_m.copy_(state0[1]); eng.flat_v.copy_(state0[2])
+        for dst, src in ((eng.bn_rm, state0[3]), (eng.bn_rv, state0[4]), (eng.bn_nbt, state0[5])):
+            for dl, sl in zip(dst, src):
+                for d, s_ in zip(dl, sl):
+                    d.copy_(s_)
+
+    def _run(self):
+        nd, nv, cd, cv = self.static
+        return self.task.engine.fused_step(nd, nv, cd, cv, *self._args, self.layout)
+
+    def load(self, batch):
+        """Stage a batch into the graph's static input buffers (device-to-device or host-to-device, async)."""
+        n, c = batch["notice"], batch["company"]
+        self.static[0].copy_(n["dense"], non_blocking=True)
+        self.static[1].copy_(n["kjt"].values(), non_blocking=True)
+        self.static[2].copy_(c["dense"], non_blocking=True)
+        self.static[3].copy_(c["kjt"].values(), non_blocking=True)
+
+    def __call__(self, batch=None) -> torch.Tensor:
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        self.task.engine.launches += self.launches_per_step
+        return self.out
 
 
 class FusedAdam:
