@@ -348,31 +348,43 @@ __device__ __forceinline__ float4 load_grad_vec(const GradSrc& s, int32_t slot, 
   }
 }
 
-// acc += sum_{i in [lo,hi)} grad(sslot[i]) in ascending i.  Full batches of 8 issue their (possibly peer / NVLink)
-// loads unconditionally before the first add, so 8 gathers are in flight; the tail is a plain loop.
+// Compaction: gs[i] = the pooled-gradient vector of sorted entry i (fp32). Every thread is an independent
+// index -> address -> load -> store chain, so tens of thousands of (possibly peer / NVLink) 16-byte gathers are in flight at
+// once; the segment sums below then stream `gs` contiguously instead of chasing slots one dependent load at a time.
 template <typename GT>
-__device__ __forceinline__ void gather_sum(float4& acc, const int32_t* __restrict__ sslot, int64_t lo, int64_t hi,
-                                           const GradSrc& src, int E, int c) {
+__global__ void __launch_bounds__(256)
+ebc_gather_sorted_kernel(const int32_t* __restrict__ sslot, int64_t n, const int32_t* __restrict__ d_n, GradSrc src,
+                         int E, float* __restrict__ gs) {
+  if (d_n) n = *d_n;
+  const int vec_per_row = E >> 2;
+  const int64_t total = n * vec_per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / vec_per_row;
+    const int c = (int)(t - i * vec_per_row);
+    *reinterpret_cast<float4*>(gs + i * E + 4 * c) = load_grad_vec<GT>(src, __ldg(sslot + i), E, c);
+  }
+}
+
+// acc += sum_{i in [lo,hi)} gs[i] in ascending i; batches of 8 keep 8 loads in flight before the first add
+__device__ __forceinline__ void gather_sum(float4& acc, const float* __restrict__ gs, int64_t lo, int64_t hi, int E, int c) {
+  const float* p = gs + lo * E + 4 * c;
   int64_t i = lo;
-  for (; i + 8 <= hi; i += 8) {
-    int32_t sl[8];
+  for (; i + 8 <= hi; i += 8, p += 8 * (int64_t)E) {
     float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) sl[u] = __ldg(sslot + i + u);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = load_grad_vec<GT>(src, sl[u], E, c);
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(p + u * (int64_t)E));
 #pragma unroll
     for (int u = 0; u < 8; ++u) f4_add(acc, v[u]);
   }
-  for (; i < hi; ++i) f4_add(acc, load_grad_vec<GT>(src, __ldg(sslot + i), E, c));
+  for (; i < hi; ++i, p += E) f4_add(acc, __ldg(reinterpret_cast<const float4*>(p)));
 }
 
 // level 1 for long rows: one lane group per chunk of SEG_CHUNK sorted entries
-template <typename GT>
 __global__ void __launch_bounds__(256)
-ebc_piece_kernel(const int32_t* __restrict__ srow, const int32_t* __restrict__ sslot, int64_t n,
+ebc_piece_kernel(const int32_t* __restrict__ srow, const float* __restrict__ gs, int64_t n,
                  const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_begin,
-                 const int32_t* __restrict__ row_end, GradSrc src, int E, int G, float* __restrict__ pieces) {
+                 const int32_t* __restrict__ row_end, int E, int G, float* __restrict__ pieces) {
   if (d_n) n = *d_n;
   const int lane = threadIdx.x % G;
   const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
@@ -388,7 +400,7 @@ ebc_piece_kernel(const int32_t* __restrict__ srow, const int32_t* __restrict__ s
     const int64_t pe = e0 < hi ? e0 : hi;
     for (int c = lane; c < vec_per_row; c += G) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      gather_sum<GT>(acc, sslot, lo, pe, src, E, c);
+      gather_sum(acc, gs, lo, pe, E, c);
       *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 0) * E) + 4 * c) = acc;
     }
   }
@@ -396,18 +408,17 @@ ebc_piece_kernel(const int32_t* __restrict__ srow, const int32_t* __restrict__ s
   if (e1 - b1 > SEG_CHUNK && b1 > lo) {
     for (int c = lane; c < vec_per_row; c += G) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      gather_sum<GT>(acc, sslot, b1, hi, src, E, c);
+      gather_sum(acc, gs, b1, hi, E, c);
       *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 1) * E) + 4 * c) = acc;
     }
   }
 }
 
-template <typename GT>
-__device__ __forceinline__ float4 row_grad_sum(const int32_t* __restrict__ sslot, int64_t b, int64_t e,
-                                               const GradSrc& src, int E, int c, const float* __restrict__ pieces) {
+__device__ __forceinline__ float4 row_grad_sum(const float* __restrict__ gs, int64_t b, int64_t e, int E, int c,
+                                               const float* __restrict__ pieces) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e - b <= SEG_CHUNK) {
-    gather_sum<GT>(acc, sslot, b, e, src, E, c);
+    gather_sum(acc, gs, b, e, E, c);
   } else {
     for (int64_t ch = b / SEG_CHUNK; ch <= (e - 1) / SEG_CHUNK; ++ch) {
       const int which = (b <= ch * SEG_CHUNK) ? 0 : 1;
@@ -434,13 +445,13 @@ __device__ __forceinline__ void adam_vec4(float4& w, float4& m, float4& v, const
 }
 
 // one lane group per arena row, every row (dense-exact Adam and/or dense gradient materialisation)
-template <typename GT, bool DO_ADAM, bool WRITE_GRAD>
+template <bool DO_ADAM, bool WRITE_GRAD>
 __global__ void __launch_bounds__(256, 3)
 ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, float* __restrict__ gout,
-                      int64_t total_rows, int E, int G, const int32_t* __restrict__ sslot,
+                      int64_t total_rows, int E, int G, const float* __restrict__ gs,
                       const int32_t* __restrict__ row_begin, const int32_t* __restrict__ row_end,
                       const int32_t* __restrict__ row_stamp, int32_t stamp, const int64_t* __restrict__ d_stamp,
-                      GradSrc src, const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
+                      const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
   if (d_stamp) stamp += (int32_t)(*d_stamp);
   tt_adam_hyper h;
   if (DO_ADAM) h = *d_hyper;
@@ -456,14 +467,14 @@ ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __res
     }
     for (int c = lane; c < vec_per_row; c += G) {
       const int64_t off = r * E + 4 * c;
-      // issue the streaming w/m/v loads first: they overlap with the dependent stamp -> bounds -> slot -> gradient chain
+      // issue the streaming w/m/v loads first: they overlap with the dependent stamp -> bounds -> gradient chain
       float4 wv, mv, vv;
       if (DO_ADAM) {
         wv = *reinterpret_cast<const float4*>(w + off);
         mv = *reinterpret_cast<const float4*>(m + off);
         vv = *reinterpret_cast<const float4*>(v + off);
       }
-      float4 g = hit ? row_grad_sum<GT>(sslot, b, e, src, E, c, pieces) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 g = hit ? row_grad_sum(gs, b, e, E, c, pieces) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (WRITE_GRAD) *reinterpret_cast<float4*>(gout + off) = g;
       if (DO_ADAM) {
         adam_vec4(wv, mv, vv, g, h);
@@ -476,11 +487,10 @@ ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __res
 }
 
 // sparse mode: one lane group per sorted entry; only segment heads work
-template <typename GT>
 __global__ void __launch_bounds__(256)
 ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int E, int G,
-                       const int32_t* __restrict__ srow, const int32_t* __restrict__ sslot, int64_t n,
-                       const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_end, GradSrc src,
+                       const int32_t* __restrict__ srow, const float* __restrict__ gs, int64_t n,
+                       const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_end,
                        const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
   if (d_n) n = *d_n;
   const tt_adam_hyper h = *d_hyper;
@@ -492,7 +502,7 @@ ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __re
   const int64_t e = row_end[r];
   const int vec_per_row = E >> 2;
   for (int c = lane; c < vec_per_row; c += G) {
-    float4 g = row_grad_sum<GT>(sslot, i, e, src, E, c, pieces);
+    float4 g = row_grad_sum(gs, i, e, E, c, pieces);
     const int64_t off = (int64_t)r * E + 4 * c;
     float4 wv = *reinterpret_cast<float4*>(w + off);
     float4 mv = *reinterpret_cast<float4*>(m + off);
@@ -693,8 +703,9 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
 }
 
 int64_t tt_ebc_piece_workspace_bytes(int64_t n, int32_t E) {
+  // [pieces: 2 per SEG_CHUNK of sorted entries][gs: the compacted pooled gradients, one fp32 vector per sorted entry]
   const int64_t chunks = (n + SEG_CHUNK - 1) / SEG_CHUNK + 1;
-  return chunks * 2 * (int64_t)E * 4;
+  return align_up(chunks * 2 * (int64_t)E * 4, 256) + (n > 0 ? n : 0) * (int64_t)E * 4;
 }
 
 int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* grad_arena, int64_t total_rows,
@@ -726,44 +737,33 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
   const int threads = 256, gpb = threads / G;
   GradSrc src{grad0, grad1, ld0, ld1, col0_0, col0_1, n0, K0, K1 > 0 ? K1 : 1, grad_table, n_per_rank > 0 ? n_per_rank : 1, d_colmap0, d_colmap1};
   float* pieces = (float*)piece_ws;
+  const int64_t n_chunks = (n + SEG_CHUNK - 1) / SEG_CHUNK;
+  const float* gs = (const float*)((const char*)piece_ws + align_up((n_chunks + 1) * 2 * (int64_t)E * 4, 256));
   if (n > 0) {
-    const int64_t chunks = (n + SEG_CHUNK - 1) / SEG_CHUNK;
+    int64_t want = ceil_div(n * (E / 4), (int64_t)threads);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    const int ggrid = (int)(want > cap ? cap : want);
     if (grad_dtype == TT_F32)
-      ebc_piece_kernel<float><<<ceil_div(chunks, gpb), threads, 0, s>>>(sorted_rows, sorted_slots, n, d_n, row_begin,
-                                                                        row_end, src, E, G, pieces);
+      ebc_gather_sorted_kernel<float><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs);
     else
-      ebc_piece_kernel<__nv_bfloat16><<<ceil_div(chunks, gpb), threads, 0, s>>>(sorted_rows, sorted_slots, n, d_n,
-                                                                                row_begin, row_end, src, E, G, pieces);
+      ebc_gather_sorted_kernel<__nv_bfloat16><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs);
+    ebc_piece_kernel<<<ceil_div(n_chunks, gpb), threads, 0, s>>>(sorted_rows, gs, n, d_n, row_begin, row_end, E, G, pieces);
   }
   if (mode == TT_ADAM_SPARSE) {
-    if (n > 0) {
-      if (grad_dtype == TT_F32)
-        ebc_rows_sparse_kernel<float><<<ceil_div(n, gpb), threads, 0, s>>>(arena_w, arena_m, arena_v, E, G, sorted_rows,
-                                                                           sorted_slots, n, d_n, row_end, src, pieces, d_hyper);
-      else
-        ebc_rows_sparse_kernel<__nv_bfloat16><<<ceil_div(n, gpb), threads, 0, s>>>(
-            arena_w, arena_m, arena_v, E, G, sorted_rows, sorted_slots, n, d_n, row_end, src, pieces, d_hyper);
-    }
+    if (n > 0)
+      ebc_rows_sparse_kernel<<<ceil_div(n, gpb), threads, 0, s>>>(arena_w, arena_m, arena_v, E, G, sorted_rows, gs, n, d_n,
+                                                                  row_end, pieces, d_hyper);
   } else {
     int64_t want = ceil_div(total_rows, gpb);
     const int64_t cap = (int64_t)sm_count() * 32;
     const int grid = (int)(want > cap ? cap : want);
-    // rows absent from this batch must not match: stamp only ever matches rows written by this step's sort
-    const int32_t eff_stamp = stamp;
-#define TT_ROWS_LAUNCH(GT, A, W)                                                                                    \
-  ebc_rows_dense_kernel<GT, A, W><<<grid, threads, 0, s>>>(arena_w, arena_m, arena_v, grad_arena, total_rows, E, G, \
-                                                           sorted_slots, row_begin, row_end, row_stamp, eff_stamp,  \
-                                                           d_stamp, src, pieces, d_hyper)
+#define TT_ROWS_LAUNCH(A, W)                                                                                         \
+  ebc_rows_dense_kernel<A, W><<<grid, threads, 0, s>>>(arena_w, arena_m, arena_v, grad_arena, total_rows, E, G, gs, \
+                                                       row_begin, row_end, row_stamp, stamp, d_stamp, pieces, d_hyper)
     const bool wg = grad_arena != nullptr;
-    if (grad_dtype == TT_F32) {
-      if (do_adam && wg) TT_ROWS_LAUNCH(float, true, true);
-      else if (do_adam) TT_ROWS_LAUNCH(float, true, false);
-      else TT_ROWS_LAUNCH(float, false, true);
-    } else {
-      if (do_adam && wg) TT_ROWS_LAUNCH(__nv_bfloat16, true, true);
-      else if (do_adam) TT_ROWS_LAUNCH(__nv_bfloat16, true, false);
-      else TT_ROWS_LAUNCH(__nv_bfloat16, false, true);
-    }
+    if (do_adam && wg) TT_ROWS_LAUNCH(true, true);
+    else if (do_adam) TT_ROWS_LAUNCH(true, false);
+    else TT_ROWS_LAUNCH(false, true);
 #undef TT_ROWS_LAUNCH
   }
   TT_LAUNCH_CHECK("ebc_backward_adam");

@@ -31,10 +31,22 @@ def timeit(fn, n=20):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); [g.replay() for _ in range(5)]; e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / (5 * n) * 1000
-for knobs in (0, 2, 26):
+for knobs in (0,):
     lib.call("tt_debug_simce_knobs", knobs)
     print(f"knobs={knobs}: fwd call (2 passes + reduces) {timeit(fwd):7.1f} us   bwd call {timeit(bwd):7.1f} us", flush=True)
 lib.call("tt_debug_simce_knobs", 0)
+
+# ---- per-kernel device durations (CUPTI through torch.profiler)
+if os.environ.get("TT_KINETO", "1") == "1":
+    from torch.profiler import profile, ProfilerActivity
+    s = torch.cuda.current_stream().cuda_stream
+    for _ in range(3): fwd(); bwd()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(10): fwd(); bwd()
+        torch.cuda.synchronize()
+    for ev in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:8]:
+        print(f"  {ev.key[:70]:70s} n={ev.count:3d} avg={ev.device_time_total / ev.count:8.1f} us")
 
 # ---- timeline of CTA 0 (forward metric pass): where does a tile's time go
 ts = torch.zeros(3 * 2048, dtype=torch.int64, device=DEV)
