@@ -295,7 +295,7 @@ int tt_debug_simce_force_manual_loads(int32_t on);
 int tt_debug_simce_knobs(int32_t bits);
 /* Profiling: CTA 0 of the next metric-pass forward kernels writes clock64 stamps into an i64[3*2048] device buffer
  * ([mma | epilogue | loader][tile*4 + event]); pass NULL to switch it off. */
-int tt_debug_simce_timeline(void* d_buf_3x2048_i64);
+int tt_debug_simce_timeline(void* d_buf_4x2048_i64);
 /* Lazily materialise S (eval / predict_batch / return_metrics "similarity_matrix" only). */
 int tt_similarity_matrix(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype,
                          float inv_temp, float* S, int64_t lds, tt_stream_t stream);

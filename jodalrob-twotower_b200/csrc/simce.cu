@@ -305,8 +305,8 @@ int64_t tt_simce_workspace_bytes(int64_t Bx, int64_t By, int32_t F) {
   return simt > tc ? simt : tc;
 }
 
-int tt_debug_simce_timeline(void* d_buf_3x2048_i64) {
-  simce_tc_set_timeline((long long*)d_buf_3x2048_i64);
+int tt_debug_simce_timeline(void* d_buf_4x2048_i64) {
+  simce_tc_set_timeline((long long*)d_buf_4x2048_i64);
   return TT_OK;
 }
 

@@ -27,9 +27,11 @@ constexpr int TC_STAGES = 4;      // Y smem ring
 constexpr int TC_SBUF = 3;        // S accumulators in TMEM (3 x 128 columns) so the MMA runs two tiles ahead of the epilogue
 constexpr int TC_EPI_WARPS = 16;  // four per SM sub-partition (the epilogue is MUFU/latency bound): rows = TMEM lane quarter
                                   // (warp % 4), columns = the 32-column slice warp / 4 of every 128-column tile
-constexpr int TC_MMA_WARP = 16;
-constexpr int TC_THREADS = 608;   // 16 epilogue + 1 mma + 2 loader warps
-constexpr int TC_LOADER_THREADS = 64;
+constexpr int TC_MMA_WARP = 16;   // issues S = X Y^T (and owns the TMEM allocation)
+constexpr int TC_MMA2_WARP = 17;  // backward: issues dX += dS Y, so neither issue chain waits for the other
+constexpr int TC_LOAD_WARP = 18;
+constexpr int TC_THREADS = 608;   // 16 epilogue + 2 mma + 1 loader warps
+constexpr int TC_LOADER_THREADS = 32;
 
 struct TcParams {
   const __nv_bfloat16* X;
@@ -46,7 +48,8 @@ struct TcParams {
   int use_tma;
   int n_stages;          // Y smem ring depth (<= TC_STAGES)
   int n_xbuf;            // X row-block buffers (1 or 2)
-  long long* dbg_ts;     // optional timeline buffer (block 0): [role][event] clock64 stamps, see scripts/time_simce.py
+  int n_dbuf;            // backward: dX accumulators in TMEM (2 when 3 * 128 + 2 * F <= 512 columns)
+  long long* dbg_ts;     // optional timeline buffer (block 0): [4 roles][512 tiles][4 events] clock64 stamps, see scripts/time_simce.py
   // forward outputs: partials per (chunk, row)
   float* row_e;
   float* row_max;
@@ -65,7 +68,7 @@ struct TcSmem {  // carved from dynamic smem after the 1024-aligned tiles
   uint64_t y_full[TC_STAGES], y_empty[TC_STAGES];
   uint64_t s_full[TC_SBUF], s_empty[TC_SBUF];
   uint64_t p_full[2], p_empty[2];
-  uint64_t d_full, d_empty;
+  uint64_t d_full[2], d_empty[2];
   uint32_t tmem_base;
   alignas(16) float iy[TC_SBUF * TCN];
 };
@@ -179,7 +182,9 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   unsigned char* sP = sY + NST * tile_bytes;    // 2 x [128 x 128] bf16 (backward only)
   TcSmem* sb = reinterpret_cast<TcSmem*>(sP + (BWD ? 2 * 2 * ATOM_BYTES : 0));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then treats the role dispatch (and everything computed under it from
+  // kernel parameters) as warp-uniform, which keeps tcgen05 operands in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n_loader_arrivals = p.use_tma ? 1 : TC_LOADER_THREADS;
 
   if (threadIdx.x == 0) {
@@ -199,8 +204,10 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       mbar_init(&sb->p_full[i], TC_EPI_WARPS);
       mbar_init(&sb->p_empty[i], 1);
     }
-    mbar_init(&sb->d_full, 1);
-    mbar_init(&sb->d_empty, TC_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sb->d_full[i], 1);
+      mbar_init(&sb->d_empty[i], TC_EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == TC_MMA_WARP) tmem_alloc(&sb->tmem_base, 512);
@@ -208,11 +215,12 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
-  const uint32_t tmem_d = tmem + TC_SBUF * TCN;
+  const uint32_t tmem_d = tmem + TC_SBUF * TCN;  // dX accumulator(s): n_dbuf x F columns behind the three S buffers
+  const int n_dbuf = p.n_dbuf;
 
-  if (warp > TC_MMA_WARP) {
-    // =========================== operand loaders ===========================
-    const int lt = threadIdx.x - (TC_MMA_WARP + 1) * 32;
+  if (warp == TC_LOAD_WARP) {
+    // =========================== operand loader ===========================
+    const int lt = lane;
     uint32_t x_iter = 0, y_iter = 0;
     int st = 0;           // Y ring cursor kept incrementally: no runtime division on the per-tile path
     uint32_t ph = 0;
@@ -224,7 +232,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       unsigned char* sXb = sX + xb * tile_bytes;
       mbar_wait(&sb->x_empty[xb], ((p.n_xbuf == 2 ? (x_iter >> 1) : x_iter) & 1) ^ 1);
       if (p.use_tma) {
-        if (lt == 0) {
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&sb->x_full[xb], (uint32_t)tile_bytes);
           for (int a = 0; a < NA; ++a) tma_load_2d(sXb + a * ATOM_BYTES, &map_x, a * 64, rb * TCM, &sb->x_full[xb]);
         }
@@ -239,7 +247,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (p.dbg_ts && blockIdx.x == 0 && lt == 0 && y_iter < 500) p.dbg_ts[2 * 2048 + y_iter * 4 + 1] = clock64();
         unsigned char* dst = sY + st * tile_bytes;
         if (p.use_tma) {
-          if (lt == 0) {
+          if (elect_one_sync()) {
             mbar_arrive_expect_tx(&sb->y_full[st], (uint32_t)tile_bytes);
             for (int a = 0; a < NA; ++a) tma_load_2d(dst + a * ATOM_BYTES, &map_y, a * 64, t * TCN, &sb->y_full[st]);
           }
@@ -255,24 +263,25 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
     }
   } else if (warp == TC_MMA_WARP) {
-    // =========================== MMA issuer (one lane) ===========================
-    if (lane == 0) {
-      const uint32_t idesc1 = make_idesc(TCM, TCN, 0, 0);
-      const uint32_t idesc2 = make_idesc(TCM, p.F, 0, 1);  // dX += P(K-major) * Y(MN-major)
-      const uint32_t sX_a = smem_u32(sX), sY_a = smem_u32(sY), sP_a = smem_u32(sP);
-      const int ksteps1 = p.F >> 4;
-      uint32_t x_iter = 0, s_iter = 0, p_iter = 0, d_phase = 0;
-      // descriptors differ only in their 14-bit start-address field: build them once, then one 64-bit add per operand
-      const uint64_t dX0 = make_desc(sX_a, 16, 1024), dY0 = make_desc(sY_a, 16, 1024);
-      const uint64_t dP0 = make_desc(sP_a, 16, 1024), dYmn0 = make_desc(sY_a, ATOM_BYTES, 1024);
-      const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
-      uint64_t dXb = dX0;
-      // ring cursors kept incrementally (this single thread's per-tile latency chain paces the whole CTA: no divisions here)
-      int y_st = 0, s_buf = 0;            // stage / S buffer of the next MMA1
-      uint32_t y_ph = 0, s_ph = 0;
-      int y2_st = 0;                      // backward: stage of the next MMA2 (trails MMA1 by up to two tiles)
-      auto issue_mma1 = [&]() {
-        const bool ts = p.dbg_ts && blockIdx.x == 0 && s_iter < 500;
+    // =========================== MMA issuer 1: S = X Y^T ===========================
+    // The whole warp runs the loop (uniform control flow, operands in uniform registers); one elected lane issues.
+    const uint32_t idesc1 = make_idesc(TCM, TCN, 0, 0);
+    const int ksteps1 = p.F >> 4;
+    // descriptors differ only in their 14-bit start-address field: build them once, then one 64-bit add per operand
+    const uint64_t dX0 = make_desc(smem_u32(sX), 16, 1024), dY0 = make_desc(smem_u32(sY), 16, 1024);
+    const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
+    uint32_t x_iter = 0, s_iter = 0;
+    int y_st = 0, s_buf = 0;  // ring cursors kept incrementally: this warp's per-tile latency chain paces the CTA
+    uint32_t y_ph = 0, s_ph = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++x_iter) {
+      const int ch = item % p.n_chunks;
+      const int t0 = ch * p.tiles_per_chunk;
+      const int nt = min(t0 + p.tiles_per_chunk, p.n_col_tiles) - t0;
+      const int xb = p.n_xbuf == 2 ? (x_iter & 1) : 0;
+      const uint64_t dXb = dX0 + (uint64_t)(xb * tile16);
+      mbar_wait(&sb->x_full[xb], (p.n_xbuf == 2 ? (x_iter >> 1) : x_iter) & 1);
+      for (int t = 0; t < nt; ++t, ++s_iter) {
+        const bool ts = p.dbg_ts && blockIdx.x == 0 && lane == 0 && s_iter < 500;
         if (ts) p.dbg_ts[0 * 2048 + s_iter * 4 + 0] = clock64();
         mbar_wait(&sb->y_full[y_st], y_ph);
         if (ts) p.dbg_ts[0 * 2048 + s_iter * 4 + 1] = clock64();
@@ -281,16 +290,19 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tc_fence_after();
         const uint64_t dYs = dY0 + (uint64_t)(y_st * tile16);
         const uint32_t d_tmem = tmem + s_buf * TCN;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, dXb + 2 * k, dYs + 2 * k, idesc1, k > 0 ? 1u : 0u);
-        if (ksteps1 > 4) {
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, dXb + 2 * k, dYs + 2 * k, idesc1, k > 0 ? 1u : 0u);
+          if (ksteps1 > 4) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, dXb + (ATOM_BYTES >> 4) + 2 * k, dYs + (ATOM_BYTES >> 4) + 2 * k, idesc1, 1u);
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, dXb + (ATOM_BYTES >> 4) + 2 * k, dYs + (ATOM_BYTES >> 4) + 2 * k, idesc1, 1u);
+          }
+          umma_commit(&sb->s_full[s_buf]);
+          if (!BWD) umma_commit(&sb->y_empty[y_st]);          // backward: the stage is released after MMA2 has read it too
+          if (t == nt - 1) umma_commit(&sb->x_empty[xb]);     // every MMA that reads this item's X has been issued
         }
-        umma_commit(&sb->s_full[s_buf]);
-        if (!BWD) umma_commit(&sb->y_empty[y_st]);
+        __syncwarp();
         if (ts) p.dbg_ts[0 * 2048 + s_iter * 4 + 3] = clock64();
-        ++s_iter;
         if (++y_st == NST) {
           y_st = 0;
           y_ph ^= 1;
@@ -299,45 +311,52 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           s_buf = 0;
           s_ph ^= 1;
         }
-      };
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++x_iter) {
+      }
+    }
+  } else if (warp == TC_MMA2_WARP) {
+    // =========================== MMA issuer 2 (backward): dX += dS(K-major) * Y(MN-major) ===========================
+    if (BWD) {
+      const uint32_t idesc2 = make_idesc(TCM, p.F, 0, 1);
+      const uint64_t dP0 = make_desc(smem_u32(sP), 16, 1024), dYmn0 = make_desc(smem_u32(sY), ATOM_BYTES, 1024);
+      const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
+      uint32_t p_iter = 0;
+      int y_st = 0, d_buf = 0;
+      uint32_t y_ph = 0, d_ph = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int ch = item % p.n_chunks;
         const int t0 = ch * p.tiles_per_chunk;
         const int nt = min(t0 + p.tiles_per_chunk, p.n_col_tiles) - t0;
-        const int xb = p.n_xbuf == 2 ? (x_iter & 1) : 0;
-        dXb = dX0 + (uint64_t)(xb * tile16);
-        mbar_wait(&sb->x_full[xb], (p.n_xbuf == 2 ? (x_iter >> 1) : x_iter) & 1);
-        if (!BWD) {
-          for (int t = 0; t < nt; ++t) issue_mma1();
-          umma_commit(&sb->x_empty[xb]);
-        } else {
-          bool x_released = false;
-          issue_mma1();
-          if (nt > 1) issue_mma1();
-          for (int t = 0; t < nt; ++t) {
-            if (t + 2 < nt) issue_mma1();
-            if (t + 2 >= nt && !x_released) {  // every MMA that reads X of this item has been issued
-              umma_commit(&sb->x_empty[xb]);
-              x_released = true;
-            }
-            const int pb = p_iter & 1;
-            mbar_wait(&sb->p_full[pb], (p_iter >> 1) & 1);
-            if (t == 0) mbar_wait(&sb->d_empty, d_phase ^ 1);
-            tc_fence_after();
-            const int st = y2_st;
-            if (++y2_st == NST) y2_st = 0;
-            const uint64_t dPb = dP0 + (uint64_t)(pb * ((2 * ATOM_BYTES) >> 4));
-            const uint64_t dYm = dYmn0 + (uint64_t)(st * tile16);
+        const uint32_t d_tmem = tmem_d + d_buf * p.F;
+        for (int t = 0; t < nt; ++t, ++p_iter) {
+          const int pb = p_iter & 1;
+          const bool ts2 = p.dbg_ts && blockIdx.x == 0 && lane == 0 && p_iter < 500;
+          if (ts2) p.dbg_ts[3 * 2048 + p_iter * 4 + 0] = clock64();
+          mbar_wait(&sb->p_full[pb], (p_iter >> 1) & 1);
+          if (ts2) p.dbg_ts[3 * 2048 + p_iter * 4 + 1] = clock64();
+          mbar_wait(&sb->y_full[y_st], y_ph);  // long complete (MMA1 consumed it); acquires the TMA-written stage for this warp
+          if (t == 0) mbar_wait(&sb->d_empty[d_buf], d_ph ^ 1);
+          tc_fence_after();
+          const uint64_t dPb = dP0 + (uint64_t)(pb * ((2 * ATOM_BYTES) >> 4));
+          const uint64_t dYm = dYmn0 + (uint64_t)(y_st * tile16);
+          if (elect_one_sync()) {
 #pragma unroll
             for (int kk = 0; kk < TCN / 16; ++kk)
-              umma_bf16(tmem_d, dPb + (uint64_t)((kk >> 2) * (ATOM_BYTES >> 4) + (kk & 3) * 2), dYm + (uint64_t)(kk * (2048 >> 4)), idesc2,
+              umma_bf16(d_tmem, dPb + (uint64_t)((kk >> 2) * (ATOM_BYTES >> 4) + (kk & 3) * 2), dYm + (uint64_t)(kk * (2048 >> 4)), idesc2,
                         (t > 0 || kk > 0) ? 1u : 0u);
             umma_commit(&sb->p_empty[pb]);
-            umma_commit(&sb->y_empty[st]);
-            ++p_iter;
+            umma_commit(&sb->y_empty[y_st]);
+            if (t == nt - 1) umma_commit(&sb->d_full[d_buf]);
           }
-          umma_commit(&sb->d_full);
-          d_phase ^= 1;
+          __syncwarp();
+          if (ts2) p.dbg_ts[3 * 2048 + p_iter * 4 + 2] = clock64();
+          if (++y_st == NST) {
+            y_st = 0;
+            y_ph ^= 1;
+          }
+        }
+        if (++d_buf == n_dbuf) {
+          d_buf = 0;
+          d_ph ^= 1;
         }
       }
     }
@@ -352,9 +371,40 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int By = (int)p.By;
     const float c1 = p.c1, c0 = p.c0;
     const int t_part = (By & (TCN - 1)) ? p.n_col_tiles - 1 : -1;  // the ragged last column tile, if any
-    uint32_t p_iter = 0, d_phase = 0;
+    uint32_t p_iter = 0, e_iter = 0;
+    // backward: the dX accumulator of an item is read out one tile into the NEXT item (when TMEM holds two accumulators), so
+    // the epilogue never idles while the last dS tiles of an item drain through MMA2
+    int d_buf = 0;
+    uint32_t d_ph = 0;
+    bool pend = false;
+    float* pend_out = nullptr;
+    int pend_buf = 0;
+    uint32_t pend_ph = 0;
+    bool pend_ok = false;
     int s_cur = 0;           // S ring cursor of the tile being processed; the phase flips when it wraps
     uint32_t s_cur_ph = 0;
+    // read one dX accumulator out of TMEM: the warps with slice * 32 < F own a 32-column slice of the F output columns each
+    auto drain_d = [&](float* out, int db, uint32_t ph, bool ok, uint32_t (&r)[TC_CW]) {
+      mbar_wait(&sb->d_full[db], ph);
+      tc_fence_after();
+      if (slice * 32 < p.F) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld16(tmem_d + db * p.F + ((uint32_t)(quarter * 32) << 16) + slice * 32 + h * TC_CW, r);
+          tmem_ld_wait_dep(r);
+          if (ok) {
+#pragma unroll
+            for (int q = 0; q < TC_CW / 4; ++q)
+              *reinterpret_cast<float4*>(out + h * TC_CW + q * 4) =
+                  make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                              __uint_as_float(r[q * 4 + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb->d_empty[db]);
+    };
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int rb = item / p.n_chunks, ch = item - rb * p.n_chunks;
       const int t0 = ch * p.tiles_per_chunk;
@@ -396,6 +446,8 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           s_nxt = 0;
           s_nxt_ph ^= 1;
         }
+        const bool stamp = stamp0 && e_iter < 500;
+        if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 0] = clock64();
         tmem_ld_wait_dep(rA);                        // first half landed
         tmem_ld16(t_base + s_cur * TCN + TC_CW, rB);  // second half in flight ...
         int pb = 0;
@@ -414,6 +466,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           prow = sP + pb * 2 * ATOM_BYTES + (slice >> 1) * ATOM_BYTES + r_in_blk * 128;
           iy = s_iy + s_cur * TCN;
         }
+        if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 1] = clock64();
         // ... while the first is processed
         if (!BWD) {
           if (generic) fwd_chunk<true>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
@@ -422,6 +475,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (generic) bwd_chunk<true>(rA, cb, slice * 32, By, c1, c0, p.tgt_off2, p.tgt_diag2, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
           else bwd_chunk<false>(rA, cb, slice * 32, By, c1, c0, p.tgt_off2, p.tgt_diag2, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
         }
+        if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 2] = clock64();
         tmem_ld_wait_dep(rB);
         // the whole slice is in registers: S buffer back to the MMA warp
         tc_fence_before();
@@ -443,7 +497,12 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (lane == 0) mbar_arrive(&sb->p_full[pb]);
           ++p_iter;
         }
-        if (stamp0 && t - t0 < 8) p.dbg_ts[1 * 2048 + ((item / (int)gridDim.x) * 8 + (t - t0)) * 4 + 2] = clock64();
+        if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 3] = clock64();
+        ++e_iter;
+        if (BWD && pend) {  // rB is dead here, rA already holds the next tile's first half
+          drain_d(pend_out, pend_buf, pend_ph, pend_ok, rB);
+          pend = false;
+        }
         s_cur = s_nxt;
         s_cur_ph = s_nxt_ph;
       }
@@ -458,26 +517,20 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
         }
       } else {
-        mbar_wait(&sb->d_full, d_phase);
-        d_phase ^= 1;
-        tc_fence_after();
-        // 32-column slices of the F output columns: slice s < F/32 is read out by the warps with warp / 4 == s
-        if (slice * 32 < p.F) {
-          float* out = p.dx_part + ((int64_t)ch * p.Bx + row) * p.F + slice * 32;
-          uint32_t r[32];
-          tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + slice * 32, r);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(out + q * 4) =
-                  make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                              __uint_as_float(r[q * 4 + 3]));
-          }
+        float* out = p.dx_part + ((int64_t)ch * p.Bx + row) * p.F + slice * 32;
+        if (n_dbuf == 2 && item + (int)gridDim.x < p.n_items) {
+          pend = true;
+          pend_out = out;
+          pend_buf = d_buf;
+          pend_ph = d_ph;
+          pend_ok = row_ok;
+        } else {
+          drain_d(out, d_buf, d_ph, row_ok, rB);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sb->d_empty);
+        if (++d_buf == n_dbuf) {
+          d_buf = 0;
+          d_ph ^= 1;
+        }
       }
     }
   }
@@ -716,6 +769,7 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   float* ysum_part = (float*)(w + 3 * stride);
   p.diag = diag; p.want_metrics = want_metrics; p.dbg_ts = want_metrics ? g_tc_dbg_ts : nullptr;
   tc_buffers(F, false, p.n_stages, p.n_xbuf);
+  p.n_dbuf = 1;
   CUtensorMap mx, my;
   p.use_tma = (!g_tc_force_manual && make_map(&mx, X, Bx, F) && make_map(&my, Y, By, F)) ? 1 : 0;
   if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); }
@@ -745,7 +799,9 @@ int simce_tc_bwd(const void* X, const void* Y, int64_t Bx, int64_t By, int F, fl
   p.inv_x = inv_x; p.inv_y = inv_y; p.gscale = gscale;
   p.tgt_diag2 = 2.f * gscale * tgt_diag; p.tgt_off2 = 2.f * gscale * tgt_off;
   p.dx_part = pl.n_chunks == 1 ? dX : (float*)workspace;
+  p.dbg_ts = g_tc_dbg_ts;
   tc_buffers(F, true, p.n_stages, p.n_xbuf);
+  p.n_dbuf = (TC_SBUF * TCN + 2 * F <= 512) ? 2 : 1;
   CUtensorMap mx, my;
   p.use_tma = (!g_tc_force_manual && make_map(&mx, X, Bx, F) && make_map(&my, Y, By, F)) ? 1 : 0;
   if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); }

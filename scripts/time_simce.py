@@ -16,6 +16,10 @@ inv = torch.full((B,), 1.0 / B, **f32); dX = torch.empty(B, F, **f32)
 s = torch.cuda.current_stream().cuda_stream
 def fwd(): lib.call("tt_simce_forward", ptr(x), ptr(y), B, B, F, TT_BF16, 1.0, 0, ptr(rse), ptr(cse), ptr(rss), ptr(css), ptr(dg), ptr(arg), ptr(ws), ws.numel(), s)
 def bwd(): lib.call("tt_simce_backward", ptr(x), ptr(y), B, B, F, TT_BF16, 1.0, 0, ptr(inv), ptr(inv), 0.5 / B, 0.0, B, ptr(dX), ptr(ws), ws.numel(), s)
+if os.environ.get("TT_ONLY") == "bwd":  # for ncu: just the backward kernels
+    fwd(); torch.cuda.synchronize()
+    for _ in range(3): bwd()
+    torch.cuda.synchronize(); sys.exit(0)
 def timeit(fn, n=20):
     """device-bound timing: n calls captured in one CUDA graph, replayed 5 times"""
     for _ in range(3): fn()
@@ -48,18 +52,21 @@ if os.environ.get("TT_KINETO", "1") == "1":
     for ev in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:8]:
         print(f"  {ev.key[:70]:70s} n={ev.count:3d} avg={ev.device_time_total / ev.count:8.1f} us")
 
-# ---- timeline of CTA 0 (forward metric pass): where does a tile's time go
-ts = torch.zeros(3 * 2048, dtype=torch.int64, device=DEV)
-lib.call("tt_debug_simce_timeline", ptr(ts))
+# ---- timeline of CTA 0: where does a tile's time go
+def timeline(fn, name):
+    ts = torch.zeros(4 * 2048, dtype=torch.int64, device=DEV)
+    lib.call("tt_debug_simce_timeline", ptr(ts))
+    fn(); torch.cuda.synchronize()
+    lib.call("tt_debug_simce_timeline", 0)
+    t = ts.cpu().view(4, 512, 4)
+    mma, epi, ld, mma2 = t[0], t[1], t[2], t[3]
+    n = int((mma[:, 3] > 0).sum())
+    t0 = int(mma[0, 0])
+    print(name, "tiles stamped:", n)
+    print("tile | MMA1: start yfull-wait sempty-wait issue+commit | EPI: top  ld+sync+pwait  half1  ldwait+release+half2 | LD: yempty-wait | MMA2: start pfull-wait issue+commit")
+    for i in range(min(n, 30)):
+        m, e, l, m2 = mma[i], epi[i], ld[i], mma2[i]
+        print(f"{i:3d} | {int(m[0])-t0:7d} {int(m[1]-m[0]):6d} {int(m[2]-m[1]):6d} {int(m[3]-m[2]):6d} | {int(e[0])-t0:7d} {int(e[1]-e[0]):6d} {int(e[2]-e[1]):6d} {int(e[3]-e[2]):6d} | {int(l[0])-t0:7d} {int(l[1]-l[0]):6d} | {int(m2[0])-t0:7d} {int(m2[1]-m2[0]):6d} {int(m2[2]-m2[1]):6d}")
 s = torch.cuda.current_stream().cuda_stream
-fwd(); torch.cuda.synchronize()
-lib.call("tt_debug_simce_timeline", 0)
-t = ts.cpu().view(3, 512, 4)
-mma, epi, ld = t[0], t[1], t[2]
-n = int((mma[:, 3] > 0).sum())
-t0 = int(mma[0, 0])
-print("tiles stamped:", n)
-print("tile | MMA: start  yfull-wait  sempty-wait  issue+commit | EPI: start  sfull-wait  work  arrive | LD: yempty-wait")
-for i in range(min(n, 32)):
-    m, e, l = mma[i], epi[i], ld[i]
-    print(f"{i:3d} | {int(m[0])-t0:7d} {int(m[1]-m[0]):7d} {int(m[2]-m[1]):7d} {int(m[3]-m[2]):7d} | {int(e[0])-t0:7d} {int(e[1]-e[0]):7d} {int(e[2]-e[1]):7d} {int(e[3]-e[2]):6d} | {int(l[0])-t0:7d} {int(l[1]-l[0]):7d}")
+timeline(fwd, "fwd")
+timeline(bwd, "bwd")
