@@ -2,20 +2,26 @@
 //
 // One CTA owns a 128-row block of X and walks a chunk of 128-column tiles of Y:
 //     S_tile[128x128] = X_blk[128xF] · Y_tile[128xF]^T      tcgen05.mma, fp32 accumulator in TMEM
-// The logits never leave the SM: the epilogue warps pull the tile out of TMEM with tcgen05.ld (one row per
-// thread, so row reductions need no shuffles), take exp2 of the shifted logits and
-//   forward : keep per-row running sum(exp), sum(S), max/argmax and the diagonal;
-//   backward: build dS = E*(inv_x_i + inv_y_j) - 2*target in registers, park it as bf16 in shared memory
-//             (K-major, 128B-swizzled) and feed it straight back to the tensor core:
-//             dX_blk[128xF] += dS_tile[128x128] · Y_tile[128xF]   accumulated in TMEM across the chunk.
+// The logits never leave the SM: the epilogue warps pull the tile out of TMEM with tcgen05.ld (one row per thread, so row
+// reductions need no shuffles) and take E = exp2 of the shifted logits. The epilogue is MUFU- and issue-bound, so it does
+// the bare minimum per logit and everything else is moved to the tensor core or to the small reduce kernels:
+//   forward : per-row running sum(E) and maximum; the arg-max is kept per 16-column chunk and resolved afterwards, sum_j S_ij
+//             is X_i . (sum_j Y_j);
+//   backward: dS_ij = E_ij (ix_i + iy_j) - target_ij. Only E is formed per logit; it is parked as bf16 in shared memory
+//             (K-major, 128B-swizzled) and fed straight back to the tensor core against the operand [Y | Ys], Ys = diag(iy) Y:
+//             [E.Y | E.Ys][128 x 2F] accumulates in TMEM across the chunk, the read-out applies ix_i, and the target terms are
+//             a rank-one and a diagonal correction added by tc_dx_reduce_kernel.
 // Column statistics / the other tower's gradient come from running the same kernel on the transposed problem
 // (X and Y swapped), so no cross-CTA column reduction and no atomics: everything is deterministic.
 //
-// Warp roles (608 threads): warps 0-15 epilogue (TMEM lane quarter == warp % 4, 32-column slice == warp / 4), warp 16 MMA
-// issuer + TMEM allocator, warps 9-10 operand loaders (TMA: one elected lane issues cp.async.bulk.tensor with 128B swizzle;
-// the generic-proxy fallback loads 16-byte chunks and applies the same swizzle by hand).
-// Pipelines: Y tiles through a 3-stage smem ring (full/empty mbarriers), S through 2 TMEM buffers, dS through
-// 2 smem buffers; tcgen05.commit arrives on the barriers when the MMAs that read a buffer have retired.
+// Warp roles (608 threads): warps 0-15 epilogue (TMEM lane quarter == warp % 4, 32-column slice == warp / 4), warp 16 issues
+// S = X Y^T and owns the TMEM allocation, warp 17 issues the backward MMA, warp 18 loads operands (TMA: one elected lane
+// issues cp.async.bulk.tensor with 128B swizzle; the generic-proxy fallback loads 16-byte chunks and applies the same swizzle
+// by hand). The issuing warps run warp-uniform code with elect.sync around the tcgen05 / TMA instructions, so their operands
+// stay in uniform registers.
+// Pipelines: Y (and Ys) tiles through a 3-4 stage smem ring (full/empty mbarriers), S through 3 (forward) or 2 (backward)
+// TMEM buffers read one 16-column half ahead, E through 2 smem buffers, the backward accumulator double-buffered in TMEM
+// when it fits; tcgen05.commit arrives on the barriers when the MMAs that read a buffer have retired.
 #include "tc_common.cuh"
 #include <float.h>
 
@@ -24,7 +30,8 @@ namespace tt {
 constexpr int TCM = 128;          // rows per CTA block (UMMA M)
 constexpr int TCN = 128;          // columns per tile  (UMMA N)
 constexpr int TC_STAGES = 4;      // Y smem ring
-constexpr int TC_SBUF = 3;        // S accumulators in TMEM (3 x 128 columns) so the MMA runs two tiles ahead of the epilogue
+constexpr int TC_SBUF = 3;        // forward: S accumulators in TMEM (3 x 128 columns), the MMA runs two tiles ahead of the
+                                  // epilogue; backward: 2, the other 256 columns hold the [E.Y | E.Ys] accumulator(s)
 constexpr int TC_EPI_WARPS = 16;  // four per SM sub-partition (the epilogue is MUFU/latency bound): rows = TMEM lane quarter
                                   // (warp % 4), columns = the 32-column slice warp / 4 of every 128-column tile
 constexpr int TC_MMA_WARP = 16;   // issues S = X Y^T (and owns the TMEM allocation)
@@ -57,9 +64,9 @@ struct TcParams {
   float* diag;
   int want_metrics;
   // backward
+  const __nv_bfloat16* Ys;  // [By][F] = bf16(gscale * inv_y[j] * Y[j,:]) (column scales folded into the second MMA operand)
   const float* inv_x;    // [Bx] (unscaled)
-  const float* inv_y;    // [By]
-  float gscale, tgt_diag2, tgt_off2;  // 2*gscale*target values
+  float gscale;
   float* dx_part;        // [n_chunks][Bx][F]
 };
 
@@ -70,7 +77,6 @@ struct TcSmem {  // carved from dynamic smem after the 1024-aligned tiles
   uint64_t p_full[2], p_empty[2];
   uint64_t d_full[2], d_empty[2];
   uint32_t tmem_base;
-  alignas(16) float iy[TC_SBUF * TCN];
 };
 
 // copy a [128 x F] bf16 row-major tile (rows row0.. of G, zero past `rows`) into 128B-swizzled K-major atoms
@@ -136,32 +142,21 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
   }
 }
 
-// dS for TC_CW logits -> bf16, written as 16-byte chunks of this row into the swizzled K-major P tile
-template <bool GENERIC>
-__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], int cbase, int c_in_tile, int By, float c1, float c0,
-                                          float tgt_off2, float tgt_diag2, int dcol, bool row_ok, float ixs,
-                                          const float* __restrict__ s_iy, unsigned char* prow, int rsw) {
+// Backward: E = exp(S - 1/T) for TC_CW logits -> bf16, written as 16-byte chunks of this row into the swizzled K-major P
+// tile. Nothing else happens per logit: with dS_ij = E_ij (ix_i + iy_j) - target_ij the row scale ix_i is applied to the
+// accumulator, the column scale iy_j is folded into the second MMA operand (Ys = diag(iy) Y), and the target terms are rank-one
+// / diagonal corrections added by tc_dx_reduce_kernel:
+//   dX_i = ix_i (E Y)_i + (E Ys)_i - t_off sum_j Y_j - (t_diag - t_off) Y_dcol(i).
+// Ragged tiles need no masks: rows / columns past the edge are zero-filled operands (they contribute nothing, or are not stored).
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], int c_in_tile, float c1, float c0, unsigned char* prow, int rsw) {
 #pragma unroll
   for (int q = 0; q < TC_CW / 8; ++q) {  // 8 columns -> one 16-byte chunk
-    const float4 a = *reinterpret_cast<const float4*>(s_iy + c_in_tile + q * 8);
-    const float4 b = *reinterpret_cast<const float4*>(s_iy + c_in_tile + q * 8 + 4);
-    const float iy[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    float d[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = q * 8 + u;
-      const float e = ex2f(fmaf(__uint_as_float(r[j]), c1, c0));
-      float v = fmaf(e, ixs + iy[u], -tgt_off2);
-      if (GENERIC) {
-        if (cbase + j == dcol) v = fmaf(e, ixs + iy[u], -tgt_diag2);
-        if (cbase + j >= By || !row_ok) v = 0.f;
-      }
-      d[u] = v;
-    }
     uint32_t w[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      __nv_bfloat162 t = __floats2bfloat162_rn(d[2 * u], d[2 * u + 1]);
+      const float e0 = ex2f(fmaf(__uint_as_float(r[q * 8 + 2 * u]), c1, c0));
+      const float e1 = ex2f(fmaf(__uint_as_float(r[q * 8 + 2 * u + 1]), c1, c0));
+      __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);
       w[u] = *reinterpret_cast<uint32_t*>(&t);
     }
     const int cc = ((c_in_tile & 63) >> 3) + q;  // 16-byte chunk index inside the 64-column atom
@@ -171,15 +166,18 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
 
 template <bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const TcParams p) {
+simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                const __grid_constant__ CUtensorMap map_ys, const TcParams p) {
+  constexpr int NSB = BWD ? 2 : TC_SBUF;        // S buffers in TMEM
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int NA = p.F >> 6;                      // swizzle atoms along K (1 or 2)
   const int tile_bytes = NA * ATOM_BYTES;       // X / Y tile
+  const int stage_bytes = (BWD ? 2 : 1) * tile_bytes;  // backward stages hold the Y tile and, right behind it, the Ys tile
   const int NST = p.n_stages;
   unsigned char* sX = base;                     // n_xbuf tiles (double-buffered across work items when they fit)
-  unsigned char* sY = sX + p.n_xbuf * tile_bytes;  // NST tiles
-  unsigned char* sP = sY + NST * tile_bytes;    // 2 x [128 x 128] bf16 (backward only)
+  unsigned char* sY = sX + p.n_xbuf * tile_bytes;  // NST stages
+  unsigned char* sP = sY + NST * stage_bytes;   // 2 x [128 x 128] bf16 (backward only)
   TcSmem* sb = reinterpret_cast<TcSmem*>(sP + (BWD ? 2 * 2 * ATOM_BYTES : 0));
 
   // warp index through a shuffle: the compiler then treats the role dispatch (and everything computed under it from
@@ -215,7 +213,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
-  const uint32_t tmem_d = tmem + TC_SBUF * TCN;  // dX accumulator(s): n_dbuf x F columns behind the three S buffers
+  const uint32_t tmem_d = tmem + NSB * TCN;  // backward accumulator(s): n_dbuf x 2F columns behind the S buffers
   const int n_dbuf = p.n_dbuf;
 
   if (warp == TC_LOAD_WARP) {
@@ -245,14 +243,17 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (p.dbg_ts && blockIdx.x == 0 && lt == 0 && y_iter < 500) p.dbg_ts[2 * 2048 + y_iter * 4 + 0] = clock64();
         mbar_wait(&sb->y_empty[st], ph ^ 1);
         if (p.dbg_ts && blockIdx.x == 0 && lt == 0 && y_iter < 500) p.dbg_ts[2 * 2048 + y_iter * 4 + 1] = clock64();
-        unsigned char* dst = sY + st * tile_bytes;
+        unsigned char* dst = sY + st * stage_bytes;
         if (p.use_tma) {
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&sb->y_full[st], (uint32_t)tile_bytes);
+            mbar_arrive_expect_tx(&sb->y_full[st], (uint32_t)stage_bytes);
             for (int a = 0; a < NA; ++a) tma_load_2d(dst + a * ATOM_BYTES, &map_y, a * 64, t * TCN, &sb->y_full[st]);
+            if (BWD)
+              for (int a = 0; a < NA; ++a) tma_load_2d(dst + tile_bytes + a * ATOM_BYTES, &map_ys, a * 64, t * TCN, &sb->y_full[st]);
           }
         } else {
           manual_tile_load(dst, p.Y, (int64_t)t * TCN, p.By, p.F, lt);
+          if (BWD) manual_tile_load(dst + tile_bytes, p.Ys, (int64_t)t * TCN, p.By, p.F, lt);
           fence_proxy_async();
           mbar_arrive(&sb->y_full[st]);
         }
@@ -269,7 +270,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int ksteps1 = p.F >> 4;
     // descriptors differ only in their 14-bit start-address field: build them once, then one 64-bit add per operand
     const uint64_t dX0 = make_desc(smem_u32(sX), 16, 1024), dY0 = make_desc(smem_u32(sY), 16, 1024);
-    const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
+    const uint32_t tile16 = (uint32_t)tile_bytes >> 4, stage16 = (uint32_t)stage_bytes >> 4;
     uint32_t x_iter = 0, s_iter = 0;
     int y_st = 0, s_buf = 0;  // ring cursors kept incrementally: this warp's per-tile latency chain paces the CTA
     uint32_t y_ph = 0, s_ph = 0;
@@ -288,7 +289,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         mbar_wait(&sb->s_empty[s_buf], s_ph ^ 1);
         if (ts) p.dbg_ts[0 * 2048 + s_iter * 4 + 2] = clock64();
         tc_fence_after();
-        const uint64_t dYs = dY0 + (uint64_t)(y_st * tile16);
+        const uint64_t dYs = dY0 + (uint64_t)(y_st * stage16);
         const uint32_t d_tmem = tmem + s_buf * TCN;
         if (elect_one_sync()) {
 #pragma unroll
@@ -307,18 +308,19 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           y_st = 0;
           y_ph ^= 1;
         }
-        if (++s_buf == TC_SBUF) {
+        if (++s_buf == NSB) {
           s_buf = 0;
           s_ph ^= 1;
         }
       }
     }
   } else if (warp == TC_MMA2_WARP) {
-    // =========================== MMA issuer 2 (backward): dX += dS(K-major) * Y(MN-major) ===========================
+    // ====================== MMA issuer 2 (backward): [E.Y | E.Ys] += E(K-major) * [Y | Ys](MN-major) ======================
+    // The stage holds the Y tile and the Ys tile back to back, i.e. 2F/64 consecutive 64-column atoms: one N = 2F operand.
     if (BWD) {
-      const uint32_t idesc2 = make_idesc(TCM, p.F, 0, 1);
+      const uint32_t idesc2 = make_idesc(TCM, 2 * p.F, 0, 1);
       const uint64_t dP0 = make_desc(smem_u32(sP), 16, 1024), dYmn0 = make_desc(smem_u32(sY), ATOM_BYTES, 1024);
-      const uint32_t tile16 = (uint32_t)tile_bytes >> 4;
+      const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
       uint32_t p_iter = 0;
       int y_st = 0, d_buf = 0;
       uint32_t y_ph = 0, d_ph = 0;
@@ -326,7 +328,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const int ch = item % p.n_chunks;
         const int t0 = ch * p.tiles_per_chunk;
         const int nt = min(t0 + p.tiles_per_chunk, p.n_col_tiles) - t0;
-        const uint32_t d_tmem = tmem_d + d_buf * p.F;
+        const uint32_t d_tmem = tmem_d + d_buf * 2 * p.F;
         for (int t = 0; t < nt; ++t, ++p_iter) {
           const int pb = p_iter & 1;
           const bool ts2 = p.dbg_ts && blockIdx.x == 0 && lane == 0 && p_iter < 500;
@@ -337,7 +339,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (t == 0) mbar_wait(&sb->d_empty[d_buf], d_ph ^ 1);
           tc_fence_after();
           const uint64_t dPb = dP0 + (uint64_t)(pb * ((2 * ATOM_BYTES) >> 4));
-          const uint64_t dYm = dYmn0 + (uint64_t)(y_st * tile16);
+          const uint64_t dYm = dYmn0 + (uint64_t)(y_st * stage16);
           if (elect_one_sync()) {
 #pragma unroll
             for (int kk = 0; kk < TCN / 16; ++kk)
@@ -366,8 +368,6 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int quarter = warp & 3, slice = warp >> 2;
     const int r_in_blk = quarter * 32 + lane;
     const uint32_t t_base = tmem + ((uint32_t)(quarter * 32) << 16) + slice * 32;  // this thread's lanes / columns of S buffer 0
-    const int et = threadIdx.x;  // 0..511
-    float* s_iy = sb->iy;        // [TC_SBUF][128] gscale * inv_y of the current tiles (backward)
     const int By = (int)p.By;
     const float c1 = p.c1, c0 = p.c0;
     const int t_part = (By & (TCN - 1)) ? p.n_col_tiles - 1 : -1;  // the ragged last column tile, if any
@@ -381,23 +381,31 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     int pend_buf = 0;
     uint32_t pend_ph = 0;
     bool pend_ok = false;
+    float pend_ixs = 0.f;
     int s_cur = 0;           // S ring cursor of the tile being processed; the phase flips when it wraps
     uint32_t s_cur_ph = 0;
-    // read one dX accumulator out of TMEM: the warps with slice * 32 < F own a 32-column slice of the F output columns each
-    auto drain_d = [&](float* out, int db, uint32_t ph, bool ok, uint32_t (&r)[TC_CW]) {
+    // read one [E.Y | E.Ys] accumulator out of TMEM and apply the row scale: out = ix * (E.Y) + (E.Ys); the warps with
+    // slice * 32 < F own a 32-column slice of the F output columns each
+    auto drain_d = [&](float* out, int db, uint32_t ph, bool ok, float ix, uint32_t (&r)[TC_CW]) {
       mbar_wait(&sb->d_full[db], ph);
       tc_fence_after();
       if (slice * 32 < p.F) {
+        const uint32_t ta = tmem_d + db * 2 * p.F + ((uint32_t)(quarter * 32) << 16) + slice * 32;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          tmem_ld16(tmem_d + db * p.F + ((uint32_t)(quarter * 32) << 16) + slice * 32 + h * TC_CW, r);
+          uint32_t r2[TC_CW];
+          tmem_ld16(ta + h * TC_CW, r);
+          tmem_ld16(ta + p.F + h * TC_CW, r2);
           tmem_ld_wait_dep(r);
+          tmem_ld_wait_dep(r2);
           if (ok) {
 #pragma unroll
             for (int q = 0; q < TC_CW / 4; ++q)
               *reinterpret_cast<float4*>(out + h * TC_CW + q * 4) =
-                  make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                              __uint_as_float(r[q * 4 + 3]));
+                  make_float4(fmaf(ix, __uint_as_float(r[q * 4]), __uint_as_float(r2[q * 4])),
+                              fmaf(ix, __uint_as_float(r[q * 4 + 1]), __uint_as_float(r2[q * 4 + 1])),
+                              fmaf(ix, __uint_as_float(r[q * 4 + 2]), __uint_as_float(r2[q * 4 + 2])),
+                              fmaf(ix, __uint_as_float(r[q * 4 + 3]), __uint_as_float(r2[q * 4 + 3])));
           }
         }
       }
@@ -411,7 +419,6 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const int t1 = min(t0 + p.tiles_per_chunk, p.n_col_tiles);
       const int64_t row = (int64_t)rb * TCM + r_in_blk;
       const bool row_ok = row < p.Bx;
-      const bool rows_full = (int64_t)rb * TCM + TCM <= p.Bx;
       // this row's positive column, and the (at most two) column tiles the block's diagonal crosses
       const int64_t d0 = p.diag_offset + (int64_t)rb * TCM;
       const int dcol = (d0 + r_in_blk >= 0 && d0 + r_in_blk < p.By) ? (int)(d0 + r_in_blk) : -1;
@@ -421,14 +428,8 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       float best = -FLT_MAX, dval = 0.f;
       int32_t best_cb = 0x7fffffff;
       bool have_diag = false;
-      float ixs = 0.f, iy_next = 0.f;
-      if (BWD) {
-        ixs = row_ok ? p.gscale * p.inv_x[row] : 0.f;
-        if (et < TCN) {
-          const int64_t c = (int64_t)t0 * TCN + et;
-          iy_next = c < p.By ? p.gscale * p.inv_y[c] : 0.f;
-        }
-      }
+      float ixs = 0.f;
+      if (BWD) ixs = row_ok ? p.gscale * p.inv_x[row] : 0.f;
       // Each warp reads its 32-column slice of an S tile as two 16-column TMEM loads, software-pipelined one half ahead:
       // the tcgen05.ld of the next half (or of the next tile's first half) is in flight while the current half is processed
       // out of the other register set, and the S buffer returns to the MMA warp as soon as its second half sits in registers.
@@ -438,11 +439,11 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       tc_fence_after();
       tmem_ld16(t_base + s_cur * TCN, rA);
       for (int t = t0; t < t1; ++t) {
-        const bool generic = t == t_d0 || t == t_d1 || t == t_part || (BWD && !rows_full);
+        const bool generic = !BWD && (t == t_d0 || t == t_d1 || t == t_part);
         const int cb = t * TCN + slice * 32;
         int s_nxt = s_cur + 1;
         uint32_t s_nxt_ph = s_cur_ph;
-        if (s_nxt == TC_SBUF) {
+        if (s_nxt == NSB) {
           s_nxt = 0;
           s_nxt_ph ^= 1;
         }
@@ -452,19 +453,10 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tmem_ld16(t_base + s_cur * TCN + TC_CW, rB);  // second half in flight ...
         int pb = 0;
         unsigned char* prow = nullptr;
-        const float* iy = nullptr;
-        if (BWD) {
-          // publish this tile's column scales, prefetch the next tile's, and wait for a free P buffer
-          if (et < TCN) s_iy[s_cur * TCN + et] = iy_next;
-          asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
-          if (et < TCN && t + 1 < t1) {
-            const int64_t c = (int64_t)(t + 1) * TCN + et;
-            iy_next = c < p.By ? p.gscale * p.inv_y[c] : 0.f;
-          }
+        if (BWD) {  // a free P buffer
           pb = p_iter & 1;
           mbar_wait(&sb->p_empty[pb], ((p_iter >> 1) & 1) ^ 1);
           prow = sP + pb * 2 * ATOM_BYTES + (slice >> 1) * ATOM_BYTES + r_in_blk * 128;
-          iy = s_iy + s_cur * TCN;
         }
         if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 1] = clock64();
         // ... while the first is processed
@@ -472,8 +464,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (generic) fwd_chunk<true>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
           else fwd_chunk<false>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
         } else {
-          if (generic) bwd_chunk<true>(rA, cb, slice * 32, By, c1, c0, p.tgt_off2, p.tgt_diag2, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
-          else bwd_chunk<false>(rA, cb, slice * 32, By, c1, c0, p.tgt_off2, p.tgt_diag2, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
+          bwd_chunk(rA, slice * 32, c1, c0, prow, r_in_blk & 7);
         }
         if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 2] = clock64();
         tmem_ld_wait_dep(rB);
@@ -490,8 +481,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (generic) fwd_chunk<true>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
           else fwd_chunk<false>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
         } else {
-          if (generic) bwd_chunk<true>(rB, cb + TC_CW, slice * 32 + TC_CW, By, c1, c0, p.tgt_off2, p.tgt_diag2, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
-          else bwd_chunk<false>(rB, cb + TC_CW, slice * 32 + TC_CW, By, c1, c0, p.tgt_off2, p.tgt_diag2, dcol, row_ok, ixs, iy, prow, r_in_blk & 7);
+          bwd_chunk(rB, slice * 32 + TC_CW, c1, c0, prow, r_in_blk & 7);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sb->p_full[pb]);
@@ -500,7 +490,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 3] = clock64();
         ++e_iter;
         if (BWD && pend) {  // rB is dead here, rA already holds the next tile's first half
-          drain_d(pend_out, pend_buf, pend_ph, pend_ok, rB);
+          drain_d(pend_out, pend_buf, pend_ph, pend_ok, pend_ixs, rB);
           pend = false;
         }
         s_cur = s_nxt;
@@ -524,8 +514,9 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           pend_buf = d_buf;
           pend_ph = d_ph;
           pend_ok = row_ok;
+          pend_ixs = ixs;
         } else {
-          drain_d(out, d_buf, d_ph, row_ok, rB);
+          drain_d(out, d_buf, d_ph, row_ok, ixs, rB);
         }
         if (++d_buf == n_dbuf) {
           d_buf = 0;
@@ -681,11 +672,57 @@ tc_rows_reduce_kernel(const float* __restrict__ row_e, const float* __restrict__
   }
 }
 
-__global__ void tc_dx_reduce_kernel(const float* __restrict__ part, int64_t n, int n_chunks, float* __restrict__ dX) {
+// Ys[j,:] = bf16(gscale * inv_y[j] * Y[j,:]): the column scales of dS folded into the second operand of the backward MMA
+__global__ void __launch_bounds__(256)
+tc_scale_rows_kernel(const __nv_bfloat16* __restrict__ Y, const float* __restrict__ inv_y, float gscale, int64_t By, int F,
+                     __nv_bfloat16* __restrict__ Ys) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= By * F) return;
+  const float sc = gscale * inv_y[i / F];
+  const uint4 v = *reinterpret_cast<const uint4*>(Y + i);
+  const __nv_bfloat162* in = reinterpret_cast<const __nv_bfloat162*>(&v);
+  uint4 o;
+  __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float2 f = __bfloat1622float2(in[u]);
+    out[u] = __floats2bfloat162_rn(f.x * sc, f.y * sc);
+  }
+  *reinterpret_cast<uint4*>(Ys + i) = o;
+}
+
+__global__ void tc_ysum_final_kernel(const float* __restrict__ part, int F, float* __restrict__ ysum) {
+  const int c = threadIdx.x;
+  if (c >= F) return;
+  float a = 0.f;
+  for (int b = 0; b < YS_BLOCKS; ++b) a += part[b * F + c];
+  ysum[c] = a;
+}
+
+// dX = sum of the chunk partials (fixed order) - t_off * sum_j Y_j - (t_diag - t_off) * Y[diag_offset + row]
+__global__ void __launch_bounds__(256)
+tc_dx_reduce_kernel(const float* __restrict__ part, int64_t n, int n_chunks, int F, const __nv_bfloat16* __restrict__ Y,
+                    int64_t diag_offset, float t_off2, float t_dd2, const float* __restrict__ ysum, float* __restrict__ dX) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float4 a = *reinterpret_cast<const float4*>(part + i);
   for (int c = 1; c < n_chunks; ++c) f4_add(a, *reinterpret_cast<const float4*>(part + (int64_t)c * n + i));
+  const int64_t row = i / F;
+  const int col = (int)(i - row * F);
+  const uint2 yv = *reinterpret_cast<const uint2*>(Y + (diag_offset + row) * F + col);
+  const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.x));
+  const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.y));
+  a.x = fmaf(-t_dd2, y01.x, a.x);
+  a.y = fmaf(-t_dd2, y01.y, a.y);
+  a.z = fmaf(-t_dd2, y23.x, a.z);
+  a.w = fmaf(-t_dd2, y23.y, a.w);
+  if (ysum) {
+    const float4 ys = *reinterpret_cast<const float4*>(ysum + col);
+    a.x = fmaf(-t_off2, ys.x, a.x);
+    a.y = fmaf(-t_off2, ys.y, a.y);
+    a.z = fmaf(-t_off2, ys.z, a.z);
+    a.w = fmaf(-t_off2, ys.w, a.w);
+  }
   *reinterpret_cast<float4*>(dX + i) = a;
 }
 
@@ -727,15 +764,16 @@ static TcPlan make_plan(int64_t Bx, int64_t By) {
 }
 
 static void tc_buffers(int F, bool bwd, int& n_stages, int& n_xbuf) {
-  const bool tight = bwd && F > 64;  // 32 KB tiles + 64 KB of dS buffers: stay under 227 KB
-  n_stages = tight ? 3 : TC_STAGES;
+  // backward stages hold Y and Ys (2 tiles) and 64 KB go to the two E buffers: stay under 227 KB
+  const bool tight = bwd && F > 64;
+  n_stages = !bwd ? TC_STAGES : (tight ? 2 : 4);  // F = 64 backward: 32 + 4 * 32 + 64 KB
   n_xbuf = tight ? 1 : 2;
 }
 static size_t tc_smem_bytes(int F, bool bwd) {
   const int tile = (F >> 6) * ATOM_BYTES;
   int ns, nx;
   tc_buffers(F, bwd, ns, nx);
-  return 1024 + (size_t)tile * (nx + ns) + (bwd ? 4 * ATOM_BYTES : 0) + sizeof(TcSmem) + 64;
+  return 1024 + (size_t)tile * (nx + ns * (bwd ? 2 : 1)) + (bwd ? 4 * ATOM_BYTES : 0) + sizeof(TcSmem) + 64;
 }
 
 int64_t simce_tc_workspace_bytes(int64_t Bx, int64_t By, int F) {
@@ -743,7 +781,7 @@ int64_t simce_tc_workspace_bytes(int64_t Bx, int64_t By, int F) {
   TcPlan a = make_plan(Bx, By), b = make_plan(By, Bx);
   const int64_t chunks = a.n_chunks > b.n_chunks ? a.n_chunks : b.n_chunks;
   const int64_t fwd = 3 * ((4 * chunks * B * 4 + 255) / 256 * 256) + YS_BLOCKS * 128 * 4 + 256;
-  const int64_t bwd = chunks * B * F * 4 + 256;
+  const int64_t bwd = chunks * B * F * 4 + 256 + (B * F * 2 + 256) + YS_BLOCKS * 128 * 4 + 128 * 4 + 256;
   return (fwd > bwd ? fwd : bwd) + 1024;
 }
 
@@ -775,7 +813,7 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); }
   const size_t smem = tc_smem_bytes(F, false);
   TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  simce_tc_kernel<false><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, p);
+  simce_tc_kernel<false><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, my, p);
   if (row_sum_s) tc_ysum_partial_kernel<<<YS_BLOCKS, 512, 0, s>>>(p.Y, By, F, ysum_part);
   tc_rows_reduce_kernel<<<ceil_div(Bx, 32), 32 * RR_LANES, 0, s>>>(p.row_e, p.row_max, p.row_arg, Bx, 4 * pl.n_chunks, p.X, p.Y, By, F,
                                                                    inv_temp, ysum_part, row_sumexp, row_sum_s,
@@ -796,20 +834,34 @@ int simce_tc_bwd(const void* X, const void* Y, int64_t Bx, int64_t By, int F, fl
   const float log2e = 1.4426950408889634f;
   p.c1 = inv_temp * log2e; p.c0 = -inv_temp * log2e; p.inv_temp = inv_temp;
   p.diag_offset = diag_offset;
-  p.inv_x = inv_x; p.inv_y = inv_y; p.gscale = gscale;
-  p.tgt_diag2 = 2.f * gscale * tgt_diag; p.tgt_off2 = 2.f * gscale * tgt_off;
-  p.dx_part = pl.n_chunks == 1 ? dX : (float*)workspace;
+  p.inv_x = inv_x; p.gscale = gscale;
+  const float t_diag2 = 2.f * gscale * tgt_diag, t_off2 = 2.f * gscale * tgt_off;
+  // workspace: [chunk partials of dX][Ys][column-sum partials][column sums]
+  char* w = (char*)workspace;
+  p.dx_part = (float*)w;
+  w += ((int64_t)pl.n_chunks * Bx * F * 4 + 255) / 256 * 256;
+  __nv_bfloat16* Ys = (__nv_bfloat16*)w;
+  w += (By * F * 2 + 255) / 256 * 256;
+  float* ysum_part = (float*)w;
+  float* ysum = ysum_part + YS_BLOCKS * 128;
+  p.Ys = Ys;
   p.dbg_ts = g_tc_dbg_ts;
   tc_buffers(F, true, p.n_stages, p.n_xbuf);
-  p.n_dbuf = (TC_SBUF * TCN + 2 * F <= 512) ? 2 : 1;
-  CUtensorMap mx, my;
-  p.use_tma = (!g_tc_force_manual && make_map(&mx, X, Bx, F) && make_map(&my, Y, By, F)) ? 1 : 0;
-  if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); }
+  p.n_dbuf = (2 * TCN + 2 * 2 * F <= 512) ? 2 : 1;
+  tc_scale_rows_kernel<<<ceil_div(By * F / 8, 256), 256, 0, s>>>(p.Y, inv_y, gscale, By, F, Ys);
+  const bool smooth = tgt_off != 0.f;
+  if (smooth) {
+    tc_ysum_partial_kernel<<<YS_BLOCKS, 512, 0, s>>>(p.Y, By, F, ysum_part);
+    tc_ysum_final_kernel<<<1, 128, 0, s>>>(ysum_part, F, ysum);
+  }
+  CUtensorMap mx, my, mys;
+  p.use_tma = (!g_tc_force_manual && make_map(&mx, X, Bx, F) && make_map(&my, Y, By, F) && make_map(&mys, Ys, By, F)) ? 1 : 0;
+  if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); memset(&mys, 0, sizeof(mys)); }
   const size_t smem = tc_smem_bytes(F, true);
   TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  simce_tc_kernel<true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, p);
-  if (pl.n_chunks > 1)
-    tc_dx_reduce_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(p.dx_part, Bx * F, pl.n_chunks, dX);
+  simce_tc_kernel<true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, mys, p);
+  tc_dx_reduce_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(p.dx_part, Bx * F, pl.n_chunks, F, p.Y, diag_offset, t_off2,
+                                                                  t_diag2 - t_off2, smooth ? ysum : nullptr, dX);
   TT_LAUNCH_CHECK("simce_tc_bwd");
   return TT_OK;
 }
