@@ -246,9 +246,14 @@ def run_ours(args):
     else:
         launches_per_step = gstep.launches_per_step
 
+    # batches packed in the layout of the graph's static input buffer: staging is ONE copy (device->device here, and
+    # host->device in the end-to-end loop)
+    packed_res = [gstep.pack(as_batch(r)) for r in resident] if gstep is not None else None
+    packed_pin = [gstep.pack(as_batch(h), pin=True) for h in pinned] if gstep is not None else None
+
     def run_step(i):
         if gstep is not None:
-            return gstep(as_batch(resident[i % N_ROTATE]))  # device-to-device stage of a resident batch + graph replay
+            return gstep(packed=packed_res[i % N_ROTATE])  # device-to-device stage of a resident batch + graph replay
         return step_resident(i)
 
     def barrier():
@@ -282,7 +287,12 @@ def run_ours(args):
     # ---- end to end through the public API: pinned host inputs -> H2D -> step -> D2H of the result, every step.
     # H2D of batch i+1 (copy stream, double-buffered staging) overlaps the step of batch i. ----
     copy_stream = torch.cuda.Stream(dev)
-    stage = [tuple(torch.empty_like(t) for t in resident[0]) for _ in range(2)]
+    if gstep is not None:
+        stage = [(torch.empty_like(packed_res[0]),) for _ in range(2)]
+        src = [(b,) for b in packed_pin]
+    else:
+        stage = [tuple(torch.empty_like(t) for t in resident[0]) for _ in range(2)]
+        src = pinned
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     out_host = torch.empty(5, dtype=torch.float32).pin_memory()
@@ -290,7 +300,7 @@ def run_ours(args):
     def e2e_loop(n):
         main = torch.cuda.current_stream(dev)
         with torch.cuda.stream(copy_stream):
-            for t, s_ in zip(pinned[0], stage[0]):
+            for t, s_ in zip(src[0], stage[0]):
                 s_.copy_(t, non_blocking=True)
             ready[0].record(copy_stream)
         for i in range(n):
@@ -299,11 +309,11 @@ def run_ours(args):
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
                         copy_stream.wait_event(freed[nxt])
-                    for t, s_ in zip(pinned[(i + 1) % N_ROTATE], stage[nxt]):
+                    for t, s_ in zip(src[(i + 1) % N_ROTATE], stage[nxt]):
                         s_.copy_(t, non_blocking=True)
                     ready[nxt].record(copy_stream)
             main.wait_event(ready[cur])
-            res = gstep(as_batch(stage[cur])) if gstep is not None else task.fused_step(as_batch(stage[cur]))
+            res = gstep(packed=stage[cur][0]) if gstep is not None else task.fused_step(as_batch(stage[cur]))
             freed[cur].record(main)
             out_host.copy_(res, non_blocking=True)
             main.synchronize()  # the D2H read of this step's loss/metrics

@@ -138,37 +138,65 @@ simce_finalize_kernel(const float* __restrict__ row_sumexp, const float* __restr
                       const float* __restrict__ diag, const int32_t* __restrict__ row_argmax, int64_t Bx, int64_t By,
                       int64_t diag_offset, double inv_bg, float inv_temp, float ls, float* __restrict__ inv_row,
                       float* __restrict__ inv_col, double* __restrict__ partial) {
-  __shared__ double red[5][1024];
+  __shared__ double red[5][32];
   const int t = threadIdx.x;
   double a[5] = {0, 0, 0, 0, 0};
-  for (int64_t i = t; i < Bx; i += 1024) {
-    const float se = row_sumexp[i];
-    inv_row[i] = 1.f / se;
-    const double lse_r = (double)inv_temp + (double)logf(se);  // fp32 log (1 ulp) is plenty: the sum over rows is fp64
-    const double d = (double)diag[i];
-    const double rss = row_sum_s ? (double)row_sum_s[i] : 0.0;
-    a[0] += lse_r - (1.0 - ls) * d - (double)ls * inv_bg * rss;
-    const int64_t j = diag_offset + i;
-    if (j < By) {
-      const double lse_c = (double)inv_temp + (double)logf(col_sumexp[j]);
-      const double css = col_sum_s ? (double)col_sum_s[j] : 0.0;
-      a[1] += lse_c - (1.0 - ls) * d - (double)ls * inv_bg * css;
+  // one block (fixed summation order); rows are taken four at a time so the independent loads of a batch are all in flight
+  constexpr int U = 4;
+  for (int64_t i0 = t; i0 < Bx; i0 += 1024 * U) {
+    float se[U], dg[U], rs[U], ce[U], cs[U];
+    int32_t am[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + (int64_t)u * 1024, j = diag_offset + i;
+      const bool ok = i < Bx, okc = ok && j < By;
+      se[u] = ok ? row_sumexp[i] : 1.f;
+      dg[u] = ok ? diag[i] : 0.f;
+      rs[u] = (ok && row_sum_s) ? row_sum_s[i] : 0.f;
+      ce[u] = okc ? col_sumexp[j] : 1.f;
+      cs[u] = (okc && col_sum_s) ? col_sum_s[j] : 0.f;
+      am[u] = (ok && row_argmax) ? row_argmax[i] : -1;
     }
-    if (row_argmax && (int64_t)row_argmax[i] == j) a[2] += 1.0;
-    a[3] += d;
-    a[4] += rss;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + (int64_t)u * 1024, j = diag_offset + i;
+      if (i >= Bx) break;
+      inv_row[i] = 1.f / se[u];
+      const double lse_r = (double)inv_temp + (double)logf(se[u]);  // fp32 log (1 ulp) is plenty: the sum over rows is fp64
+      const double d = (double)dg[u];
+      const double rss = (double)rs[u];
+      a[0] += lse_r - (1.0 - ls) * d - (double)ls * inv_bg * rss;
+      if (j < By) {
+        const double lse_c = (double)inv_temp + (double)logf(ce[u]);
+        a[1] += lse_c - (1.0 - ls) * d - (double)ls * inv_bg * (double)cs[u];
+      }
+      if (row_argmax && (int64_t)am[u] == j) a[2] += 1.0;
+      a[3] += d;
+      a[4] += rss;
+    }
   }
   for (int64_t j = t; j < By; j += 1024) inv_col[j] = 1.f / col_sumexp[j];
+  // fixed-shape reduction: butterfly inside each warp, then warp 0 folds the 32 warp sums
 #pragma unroll
-  for (int k = 0; k < 5; ++k) red[k][t] = a[k];
-  __syncthreads();
-  for (int off = 512; off > 0; off >>= 1) {
-    if (t < off)
+  for (int k = 0; k < 5; ++k) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) red[k][t] += red[k][t + off];
-    __syncthreads();
+    for (int off = 16; off > 0; off >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
   }
-  if (t < 8) partial[t] = t < 5 ? red[t][0] : 0.0;
+  if ((t & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) red[k][t >> 5] = a[k];
+  }
+  __syncthreads();
+  if (t < 32) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      double v = red[k][t];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (t == 0) partial[k] = v;
+    }
+    if (t >= 5 && t < 8) partial[t] = 0.0;
+  }
 }
 
 __global__ void simce_scalars_kernel(const double* __restrict__ p, long long Bg, float* __restrict__ out) {

@@ -483,6 +483,7 @@ class TwoTowerEngine:
         out5 = self.loss_forward(ws)
         ws.train = train
         ws.masks = masks
+        ws.dc_ready = [None, None]
         return out5, ws
 
     # ------------------------------------------------------------------ backward
@@ -515,9 +516,12 @@ class TwoTowerEngine:
         if self.act != TT_F32:
             self._call("tt_cast_bf16", ptr(ws.dz[t]), ptr(ws.dz16[t]), B * F, s)
             dz = ws.dz16[t]
-        self._lin_wgrad(dz, F, xlast, wl, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", B, F, wl, ws.wg_ws[t])
+        # data gradients first: they are the critical path (the next layer and, at the bottom, the table update wait for them)
         dx = ws.dy[t][nblk - 1] if nblk > 0 else ws.dc[t]
         self._lin_dgrad(dz, F, pre + f"mlp.{idx}.weight", dx, wl, B, F, wl)
+        if nblk == 0:
+            self._mark_dc_ready(t, ws)
+        self._lin_wgrad(dz, F, xlast, wl, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", B, F, wl, ws.wg_ws[t])
         for bi in range(nblk - 1, -1, -1):
             h = cfg.hidden[1 + bi]
             idx = 4 * bi
@@ -535,9 +539,11 @@ class TwoTowerEngine:
                        ptr(self.dense(pre + f"mlp.{idx + 2}.bias", "g")), ptr(ws.dh[t][bi]), h, s)
             xin = ws.y[t][bi - 1] if bi > 0 else ws.c[t]
             win = widths[bi]
-            self._lin_wgrad(ws.dh[t][bi], h, xin, win, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", B, h, win, ws.wg_ws[t])
             dxin = ws.dy[t][bi - 1] if bi > 0 else ws.dc[t]
             self._lin_dgrad(ws.dh[t][bi], h, pre + f"mlp.{idx}.weight", dxin, win, B, h, win)
+            if bi == 0:
+                self._mark_dc_ready(t, ws)
+            self._lin_wgrad(ws.dh[t][bi], h, xin, win, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", B, h, win, ws.wg_ws[t])
         if self.act != TT_F32:
             dense_in = ws.x16[t]
         else:
@@ -546,6 +552,12 @@ class TwoTowerEngine:
                 dense_in = dense_in.float()
         self._lin_wgrad(ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", B, H0,
                         dense_dim, ws.wg_ws[t])
+
+    def _mark_dc_ready(self, t: int, ws: _Ws):
+        """The gradient w.r.t. the tower's concat buffer is complete: everything the large-table update needs from this tower."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        ws.dc_ready[t] = ev
 
     def small_tables_backward(self, ws: _Ws, towers=(0, 1)):
         """Gradient of the small tables into the flat dense gradient buffer (dense one-hot reduction, deterministic)."""
@@ -624,17 +636,30 @@ class TwoTowerEngine:
         """hyper_advance -> forward -> backward -> sparse-dedup + Adam on tables -> Adam on dense. Returns out5."""
         self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
         out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
-        self.backward(ws)
-        self.reduce_dense_grads()
         main = torch.cuda.current_stream(self.device)
-        main.wait_stream(self._sort_stream)  # the sort-dedup ran underneath the towers and the loss
         if self.two_streams:
+            # Three streams below the loss: the towers' backward passes on `main` / `_side`, and on `_sort_stream` (where the
+            # sort-dedup already ran underneath the forward pass) the large-table segment-sum + Adam, which starts as soon as
+            # both concat-buffer gradients exist and overlaps the first-layer weight gradients and the small-table reductions.
+            self.loss_backward(ws)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                self.dense_adam()
-            self.embedding_backward(ws, apply_adam=True, want_dense_grad=False, sorted_already=True)
+                self.tower_backward(1, ws)
+                self.small_tables_backward(ws, (1,))
+            self.tower_backward(0, ws)
+            self.small_tables_backward(ws, (0,))
+            with torch.cuda.stream(self._sort_stream):
+                self._sort_stream.wait_event(ws.dc_ready[0])
+                self._sort_stream.wait_event(ws.dc_ready[1])
+                self.embedding_backward(ws, apply_adam=True, want_dense_grad=False, sorted_already=True)
             main.wait_stream(self._side)
+            self.reduce_dense_grads()
+            self.dense_adam()
+            main.wait_stream(self._sort_stream)
         else:
+            self.backward(ws)
+            self.reduce_dense_grads()
+            main.wait_stream(self._sort_stream)  # the sort-dedup ran underneath the towers and the loss
             self.embedding_backward(ws, apply_adam=True, want_dense_grad=False, sorted_already=True)
             self.dense_adam()
         return out5

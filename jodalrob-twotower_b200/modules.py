@@ -400,7 +400,14 @@ class GraphedFusedStep:
         task._sync_cfg()
         nd, nv, cd, cv, lay = task._unpack(example_batch)
         self.layout = lay
-        self.static = [torch.empty_like(t.contiguous()) for t in (nd, nv, cd, cv)]
+        # the four inputs live back to back in ONE buffer, so a pre-packed batch is staged with a single copy
+        self._slots, off = [], 0
+        for t in (nd, nv, cd, cv):
+            nbytes = t.numel() * t.element_size()
+            self._slots.append((off, nbytes, t.dtype, tuple(t.shape)))
+            off += (nbytes + 255) // 256 * 256
+        self.static_blob = torch.empty(max(off, 256), dtype=torch.uint8, device=eng.device)
+        self.static = [self.static_blob[o:o + n].view(dt).view(shape) for o, n, dt, shape in self._slots]
         for s, t in zip(self.static, (nd, nv, cd, cv)):
             s.copy_(t)
         o = task._fused_opt
@@ -442,8 +449,20 @@ class GraphedFusedStep:
         self.static[2].copy_(c["dense"], non_blocking=True)
         self.static[3].copy_(c["kjt"].values(), non_blocking=True)
 
-    def __call__(self, batch=None) -> torch.Tensor:
-        if batch is not None:
+    def pack(self, batch, pin: bool = False) -> torch.Tensor:
+        """The batch as one uint8 tensor in the layout of the static input buffer (same device as the batch; pinned host
+        memory with pin=True). `step(packed=...)` stages it with a single asynchronous copy."""
+        n, c = batch["notice"], batch["company"]
+        parts = (n["dense"], n["kjt"].values(), c["dense"], c["kjt"].values())
+        out = torch.empty(self.static_blob.numel(), dtype=torch.uint8, device=parts[0].device, pin_memory=pin and parts[0].device.type == "cpu")
+        for (o, nb, dt, shape), t in zip(self._slots, parts):
+            out[o:o + nb].view(dt).view(shape).copy_(t.to(dt).reshape(shape))
+        return out
+
+    def __call__(self, batch=None, packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if packed is not None:
+            self.static_blob.copy_(packed, non_blocking=True)
+        elif batch is not None:
             self.load(batch)
         self.graph.replay()
         self.task.engine.launches += self.launches_per_step
