@@ -542,11 +542,37 @@ ebc_small_partial_kernel(const int64_t* __restrict__ values, int B, int K, int l
   float* mine = s_acc + warp * ve;
   const int b_lo = blockIdx.y * SM_CHUNK;
   const int b_hi = min(b_lo + SM_CHUNK, B);
-  for (int b = b_lo + warp; b < b_hi; b += 8) {
-    int64_t id = __ldg(values + (layout == TT_LAYOUT_SAMPLE_MAJOR ? (int64_t)b * K + tb.key : (int64_t)tb.key * B + b));
-    id = id < 0 ? 0 : (id > tb.vocab - 1 ? tb.vocab - 1 : id);
-    const GT* g = grad + (int64_t)b * ld + tb.col;
-    for (int e = lane; e < E; e += 32) mine[id * E + e] += ldf<GT>(g + e);
+  if (E <= 32) {
+    // eight samples of this warp per round: their ids (one lane each) and gradient vectors (one element per lane) are all in
+    // flight together; the shared-memory accumulation then runs in ascending sample order (same order as the plain loop)
+    for (int base = b_lo + warp; base < b_hi; base += 64) {
+      int my_id = 0;
+      {
+        const int b = base + lane * 8;
+        if (lane < 8 && b < b_hi) {
+          int64_t id = __ldg(values + (layout == TT_LAYOUT_SAMPLE_MAJOR ? (int64_t)b * K + tb.key : (int64_t)tb.key * B + b));
+          my_id = (int)(id < 0 ? 0 : (id > tb.vocab - 1 ? tb.vocab - 1 : id));
+        }
+      }
+      float gv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = base + u * 8;
+        gv[u] = (b < b_hi && lane < E) ? ldf<GT>(grad + (int64_t)b * ld + tb.col + lane) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int id = __shfl_sync(0xffffffffu, my_id, u);
+        if (base + u * 8 < b_hi && lane < E) mine[id * E + lane] += gv[u];
+      }
+    }
+  } else {
+    for (int b = b_lo + warp; b < b_hi; b += 8) {
+      int64_t id = __ldg(values + (layout == TT_LAYOUT_SAMPLE_MAJOR ? (int64_t)b * K + tb.key : (int64_t)tb.key * B + b));
+      id = id < 0 ? 0 : (id > tb.vocab - 1 ? tb.vocab - 1 : id);
+      const GT* g = grad + (int64_t)b * ld + tb.col;
+      for (int e = lane; e < E; e += 32) mine[id * E + e] += ldf<GT>(g + e);
+    }
   }
   __syncthreads();
   float* out = part + (int64_t)blockIdx.y * part_stride + tb.g_off;

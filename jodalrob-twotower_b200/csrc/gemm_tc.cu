@@ -23,6 +23,7 @@ struct GemmTcParams {
   int tn;                 // output tile width: 64 or 128
   int a_mn, b_mn;         // operand major-ness (0 = reduction-contiguous "K-major", 1 = MN-major)
   int stages_per_split;   // reduction stages handled by one CTA (grid.z splits)
+  int ring;               // smem ring depth = min(GT_STAGES, stages per CTA): short reductions leave room for 2-3 CTAs per SM
   int epi;
   // EPI_STORE
   void* C;
@@ -40,14 +41,15 @@ struct GemmTcSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(GT_THREADS, 1)
+__global__ void __launch_bounds__(GT_THREADS, 3)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmTcParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int a_bytes = ATOM_BYTES;                 // 128 x 64 bf16 either way (1 K-major atom or 2 MN-major half-atoms)
   const int b_bytes = p.tn * 128;                 // tn x 64 bf16
   const int stage_bytes = a_bytes + b_bytes;
-  GemmTcSmem* sb = reinterpret_cast<GemmTcSmem*>(base + GT_STAGES * stage_bytes);
+  const int ring = p.ring;
+  GemmTcSmem* sb = reinterpret_cast<GemmTcSmem*>(base + ring * stage_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * 128, n0 = (int64_t)blockIdx.y * p.tn;
   const int total_stages = (int)((p.R + GT_BK - 1) / GT_BK);
@@ -71,9 +73,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 5) {
     if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < n_stages; ++i) {
-        const int st = i % GT_STAGES;
-        mbar_wait(&sb->empty[st], ((i / GT_STAGES) & 1) ^ 1);
+        mbar_wait(&sb->empty[st], ph ^ 1);
         unsigned char* sa = base + st * stage_bytes;
         unsigned char* sbm = sa + a_bytes;
         const int r0 = (s_begin + i) * GT_BK;
@@ -90,15 +93,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tma_load_2d(sbm, &map_b, (int)n0, r0, &sb->full[st]);             // box {64 n, 64 r} x (tn / 64)
           if (p.tn == 128) tma_load_2d(sbm + 8192, &map_b, (int)n0 + 64, r0, &sb->full[st]);
         }
+        if (++st == ring) {
+          st = 0;
+          ph ^= 1;
+        }
       }
     }
   } else if (warp == 4) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, p.tn, p.a_mn, p.b_mn);
       const uint32_t base_a = smem_u32(base);
+      int st = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < n_stages; ++i) {
-        const int st = i % GT_STAGES;
-        mbar_wait(&sb->full[st], (i / GT_STAGES) & 1);
+        mbar_wait(&sb->full[st], ph);
         tc_fence_after();
         const uint32_t sa = base_a + st * stage_bytes, sbm = sa + a_bytes;
 #pragma unroll
@@ -108,6 +116,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           umma_bf16(tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&sb->empty[st]);
+        if (++st == ring) {
+          st = 0;
+          ph ^= 1;
+        }
       }
       umma_commit(&sb->acc_full);
     }
@@ -231,11 +243,14 @@ __global__ void __launch_bounds__(256) colsum_bf16_final_kernel(const double* __
   if (lane == 0) out[n] = (float)t;
 }
 
-static size_t gt_smem_bytes(int tn) { return 1024 + (size_t)GT_STAGES * (ATOM_BYTES + tn * 128) + sizeof(GemmTcSmem) + 64; }
+static size_t gt_smem_bytes(int tn, int ring) { return 1024 + (size_t)ring * (ATOM_BYTES + tn * 128) + sizeof(GemmTcSmem) + 64; }
 
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmTcParams& p, int splits, cudaStream_t s) {
-  const size_t smem = gt_smem_bytes(p.tn);
-  TT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int total_stages = ceil_div(p.R, (int64_t)GT_BK);
+  const int per_cta = p.stages_per_split < total_stages ? p.stages_per_split : total_stages;
+  p.ring = per_cta < GT_STAGES ? (per_cta < 1 ? 1 : per_cta) : GT_STAGES;
+  const size_t smem = gt_smem_bytes(p.tn, p.ring);
+  TT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_bytes(128, GT_STAGES)));
   dim3 grid(ceil_div(p.M, 128), ceil_div(p.N, p.tn), splits);
   gemm_tc_kernel<<<grid, GT_THREADS, smem, s>>>(ma, mb, p);
   TT_LAUNCH_CHECK("gemm_tc_kernel");

@@ -516,12 +516,11 @@ class TwoTowerEngine:
         if self.act != TT_F32:
             self._call("tt_cast_bf16", ptr(ws.dz[t]), ptr(ws.dz16[t]), B * F, s)
             dz = ws.dz16[t]
-        # data gradients first: they are the critical path (the next layer and, at the bottom, the table update wait for them)
+        # The chain of data gradients runs first, top to bottom: it is the critical path (at its end the large-table update can
+        # start). Every layer's dY stays in its own buffer, so the weight gradients are formed afterwards, off that path.
+        wgrads = [(dz, F, xlast, wl, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", F, wl)]
         dx = ws.dy[t][nblk - 1] if nblk > 0 else ws.dc[t]
         self._lin_dgrad(dz, F, pre + f"mlp.{idx}.weight", dx, wl, B, F, wl)
-        if nblk == 0:
-            self._mark_dc_ready(t, ws)
-        self._lin_wgrad(dz, F, xlast, wl, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", B, F, wl, ws.wg_ws[t])
         for bi in range(nblk - 1, -1, -1):
             h = cfg.hidden[1 + bi]
             idx = 4 * bi
@@ -541,9 +540,10 @@ class TwoTowerEngine:
             win = widths[bi]
             dxin = ws.dy[t][bi - 1] if bi > 0 else ws.dc[t]
             self._lin_dgrad(ws.dh[t][bi], h, pre + f"mlp.{idx}.weight", dxin, win, B, h, win)
-            if bi == 0:
-                self._mark_dc_ready(t, ws)
-            self._lin_wgrad(ws.dh[t][bi], h, xin, win, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", B, h, win, ws.wg_ws[t])
+            wgrads.append((ws.dh[t][bi], h, xin, win, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", h, win))
+        self._mark_dc_ready(t, ws)
+        for dy_, ldy_, x_, ldx_, wn_, bn_, n_, k_ in wgrads:
+            self._lin_wgrad(dy_, ldy_, x_, ldx_, wn_, bn_, B, n_, k_, ws.wg_ws[t])
         if self.act != TT_F32:
             dense_in = ws.x16[t]
         else:
