@@ -147,7 +147,11 @@ __global__ void __launch_bounds__(RS_THREADS)
 radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ d_n, int shift,
                   int32_t* __restrict__ hist, int n_tiles) {
   __shared__ int32_t s_hist[256];
-  if (d_n) n = *d_n;
+  if (d_n) {  // device-side count (sharded tables): the launch covers the capacity, the work and the histogram pitch follow n
+    n = *d_n;
+    n_tiles = n > 0 ? (int)((n + RS_TILE - 1) / RS_TILE) : 1;
+    if ((int)blockIdx.x >= n_tiles) return;
+  }
   s_hist[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
@@ -161,9 +165,10 @@ radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, const int32_t* __
 }
 
 // exclusive scan of `len` int32 counters in place, one block
-__global__ void __launch_bounds__(1024) scan_exclusive_kernel(int32_t* __restrict__ data, int64_t len) {
+__global__ void __launch_bounds__(1024) scan_exclusive_kernel(int32_t* __restrict__ data, int64_t len, const int32_t* __restrict__ d_n) {
   __shared__ int32_t s_part[1024];
   const int t = threadIdx.x;
+  if (d_n) len = 256 * (int64_t)(*d_n > 0 ? (*d_n + RS_TILE - 1) / RS_TILE : 1);
   const int64_t per = (len + 1023) / 1024;
   const int64_t lo = (int64_t)t * per, hi = (lo + per < len) ? lo + per : len;
   int32_t sum = 0;
@@ -185,10 +190,15 @@ __global__ void __launch_bounds__(1024) scan_exclusive_kernel(int32_t* __restric
 }
 
 // same scan with the counters staged in shared memory (coalesced global traffic); len <= ~48k entries
-__global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __restrict__ data, int len, int per) {
+__global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __restrict__ data, int len, int per,
+                                                                   const int32_t* __restrict__ d_n) {
   extern __shared__ int32_t sh[];
   __shared__ int32_t s_part[1024];
   const int t = threadIdx.x;
+  if (d_n) {  // shorter than the launch-time bound: shared memory was sized for the bound
+    len = 256 * (*d_n > 0 ? (*d_n + RS_TILE - 1) / RS_TILE : 1);
+    per = (len + 1023) / 1024;
+  }
   for (int i = t; i < len; i += 1024) sh[(i / per) * (per | 1) + (i % per)] = data[i];  // odd row pitch: no bank conflicts
   __syncthreads();
   int32_t* mine = sh + t * (per | 1);
@@ -213,14 +223,14 @@ __global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __re
   for (int i = t; i < len; i += 1024) data[i] = sh[(i / per) * (per | 1) + (i % per)];
 }
 
-static int launch_scan(int32_t* data, int64_t len, cudaStream_t s) {
+static int launch_scan(int32_t* data, int64_t len, const int32_t* d_n, cudaStream_t s) {
   const int per = (int)((len + 1023) / 1024);
   const size_t smem = (size_t)1024 * (per | 1) * 4;
   if (smem <= 160 * 1024) {
     TT_CUDA(cudaFuncSetAttribute(scan_exclusive_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    scan_exclusive_smem_kernel<<<1, 1024, smem, s>>>(data, (int)len, per);
+    scan_exclusive_smem_kernel<<<1, 1024, smem, s>>>(data, (int)len, per, d_n);
   } else {
-    scan_exclusive_kernel<<<1, 1024, 0, s>>>(data, len);
+    scan_exclusive_kernel<<<1, 1024, 0, s>>>(data, len, d_n);
   }
   return TT_OK;
 }
@@ -229,7 +239,11 @@ __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n,
                      const int32_t* __restrict__ d_n, int shift, const int32_t* __restrict__ hist_scanned, int n_tiles,
                      int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
-  if (d_n) n = *d_n;
+  if (d_n) {
+    n = *d_n;
+    n_tiles = n > 0 ? (int)((n + RS_TILE - 1) / RS_TILE) : 1;
+    if ((int)blockIdx.x >= n_tiles) return;
+  }
   // each warp owns 256 consecutive keys; item i of the warp is keys [i*32, i*32+32) of that chunk, so
   // (item, lane) order == index order and the ranking below is stable.
   __shared__ int32_t s_warp_hist[RS_THREADS / 32][256];
@@ -718,7 +732,7 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
     int32_t* kout = to_final ? sorted_rows : tmp_keys;
     int32_t* vout = to_final ? sorted_slots : tmp_vals;
     radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles);
-    { int rc = launch_scan(hist, (int64_t)256 * n_tiles, s); if (rc != TT_OK) return rc; }
+    { int rc = launch_scan(hist, (int64_t)256 * n_tiles, d_n, s); if (rc != TT_OK) return rc; }
     radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, d_n, p * 8, hist, n_tiles, kout, vout);
     kin = kout;
     vin = vout;

@@ -78,6 +78,11 @@ class NcclComm:
             self._tiny = torch.zeros(1, dtype=torch.float32, device=device)
         self.dist.all_reduce(self._tiny, group=self.group)
 
+    def clone(self) -> "NcclComm":
+        """A second communicator over the same ranks: collectives issued on another stream (the company tower) must not share
+        a communicator with the main stream's, NCCL orders the operations of one communicator."""
+        return NcclComm(self.dist.new_group(ranks=self.dist.get_process_group_ranks(self.group), backend="nccl"))
+
     def peer_buffer(self, nbytes: int, device) -> "tuple[torch.Tensor, List[int]]":
         import torch.distributed._symmetric_memory as symm_mem
         t = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
@@ -132,6 +137,9 @@ class ThreadComm:
         torch.cuda.current_stream(device).synchronize()
         self.tw.bar.wait()
 
+    def clone(self):
+        return self  # host-mediated and blocking: one rank thread never has two collectives in flight
+
     def peer_buffer(self, nbytes: int, device):
         t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         self.tw.ptrs[self.rank] = t.data_ptr()
@@ -153,6 +161,9 @@ class SingleComm:
 
     def barrier(self, device):
         return None
+
+    def clone(self):
+        return self
 
     def peer_buffer(self, nbytes, device):
         t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
@@ -192,7 +203,9 @@ class DistributedEngine(TwoTowerEngine):
         self.vocab_small_only = vf
         self.no_rank = torch.full((self.K[0] + self.K[1],), -1, dtype=torch.int32, device=dev)
         self.rng_stream_base = 64 * self.rank
-        self.two_streams = False  # both towers issue collectives on one communicator: keep them on one stream
+        # the company tower runs on the side stream with its own communicator for the SyncBN all-reduces
+        self.comm_t = [comm, comm.clone()]
+        self.two_streams = True
         if lv:
             assert self.total_rows == self.plan.local_rows, (self.total_rows, self.plan.local_rows)
 
@@ -277,9 +290,26 @@ class DistributedEngine(TwoTowerEngine):
                    ptr(self.colmap[1]), self.act, s)
         self.comm.barrier(self.device)  # every owner has finished writing into my concat buffers
 
-    def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int) -> int:
-        self.comm.all_reduce(sums[:n])
+    def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int, tower: int = 0) -> int:
+        self.comm_t[tower].all_reduce(sums[:n])
         return local_count * self.world
+
+    def fused_step(self, notice_dense, notice_values, company_dense, company_values, lr=1e-3, warmup_steps=0,
+                   betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, layout=None, masks=None):
+        """Like the single-GPU step, except that the large-table update pulls gradients from every rank: it has to wait for the
+        all-reduce of the dense gradients, which doubles as the barrier that says every rank's pooled gradients are complete."""
+        self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
+        out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
+        main = torch.cuda.current_stream(self.device)
+        self.backward(ws)  # towers on two streams, joined on main
+        self.reduce_dense_grads()
+        main.wait_stream(self._sort_stream)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self.dense_adam()
+        self.embedding_backward(ws, apply_adam=True, want_dense_grad=False, sorted_already=True)
+        main.wait_stream(self._side)
+        return out5
 
     def loss_forward(self, ws: _Ws):
         cfg, B, s = self.cfg, ws.B, self._stream()

@@ -414,7 +414,7 @@ class TwoTowerEngine:
             if train:
                 self._call("tt_bn_stats", ptr(ws.h[t][bi]), h, B, h, self.act, ptr(ws.bn_sums[t]), ptr(ws.bn_ws[t]),
                            ws.bn_ws[t].numel(), s, n_kernels=2)
-                count = self.bn_allreduce(ws.bn_sums[t], 2 * h, B)
+                count = self.bn_allreduce(ws.bn_sums[t], 2 * h, B, t)
                 self._call("tt_bn_finalize", ptr(ws.bn_sums[t]), count, h, BN_EPS, BN_MOMENTUM, ptr(ws.mean[t][bi]),
                            ptr(ws.rstd[t][bi]), ptr(self.bn_rm[t][bi]), ptr(self.bn_rv[t][bi]), ptr(self.bn_nbt[t][bi]), s)
                 mean = ws.mean[t][bi]
@@ -432,7 +432,7 @@ class TwoTowerEngine:
         self._call("tt_l2norm_forward", ptr(ws.z[t]), B, F, ptr(ws.e[t]), self.emb_tt, ptr(ws.nrm[t]), s)
         return ws.e[t]
 
-    def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int) -> int:
+    def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int, tower: int = 0) -> int:
         """Single GPU: nothing to do. Distributed engines all-reduce `sums[:n]` and return the global count."""
         return local_count
 
@@ -531,7 +531,7 @@ class TwoTowerEngine:
             self._call("tt_bn_backward_reduce", ptr(ws.dy[t][bi]), h, ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean),
                        ptr(ws.rstd[t][bi]), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.bn_sums[t]),
                        ptr(ws.bn_ws[t]), ws.bn_ws[t].numel(), s, n_kernels=2)
-            count = self.bn_allreduce(ws.bn_sums[t], 2 * h, B)
+            count = self.bn_allreduce(ws.bn_sums[t], 2 * h, B, t)
             self._call("tt_bn_backward_apply", ptr(ws.dy[t][bi]), h, ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean),
                        ptr(ws.rstd[t][bi]), ptr(gamma), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.bn_sums[t]),
                        count, 1 if train else 0, ptr(self.dense(pre + f"mlp.{idx + 2}.weight", "g")),
