@@ -181,10 +181,14 @@ def algorithmic(tag: str, B: int, schema) -> dict:
         return {"bytes": B * (Kn + Kc) * 4 * 2 * 3}
     if tag.startswith("tt_dense_adam"):
         return {"bytes": 152320 * 28}
+    # sim-CE flops: a forward call needs S = N C^T once (2 B^2 F; its second, transposed pass is an implementation choice and is
+    # not counted); a backward call forms one tower's gradient from logits that were never stored: S again (2 B^2 F) and
+    # dX = dS Y (2 B^2 F); the widened [Y|Ys] operand is not counted. `exps` is the number of exp evaluations a call executes
+    # (one per logit per pass), the quantity the MUFU pipe bounds.
     if tag.startswith("tt_simce_forward"):
-        return {"flops": 2 * B * B * F}
+        return {"flops": 2 * B * B * F, "exps": 2 * B * B}
     if tag.startswith("tt_simce_backward"):
-        return {"flops": 2 * B * B * F}
+        return {"flops": 4 * B * B * F, "exps": B * B}
     return {}
 
 
@@ -369,8 +373,20 @@ def run_ours(args):
         per_call_s = kern[top["call"]]["ms"] / max(kern[top["call"]]["calls"], 1) * 1e-3
         if "flops" in a:
             ach = a["flops"] / per_call_s / 1e12
-            roofline = {"kernel": top["call"], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                        "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + ", burst bf16"}
+            traffic = None
+            prof = os.path.join(ROOT, "profiles", "r01_ncu_simce_bwd.json")
+            if top["call"].startswith("tt_simce_backward") and os.path.isfile(prof) and B == 8192:
+                with open(prof) as f:
+                    traffic = json.load(f)["dram_bytes_per_launch"]  # dram read+write of one launch, ncu --set full capture
+            sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+            mufu_peak = 16 * 148 * sm_hz * 1e6  # ex2.approx per second: 16 / clk / SM (scripts/microbench/mufu.cu)
+            roofline = {"kernel": top["call"] + " (simce_tc_kernel + 2 small kernels per call)", "bound": "tensor", "achieved": ach,
+                        "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic,
+                        "peak_source": pk["source"] + ", burst bf16",
+                        "note": "the kernel is bound by the exp of every logit (MUFU) and by instruction issue, not by the tensor "
+                                "pipe or HBM: see `mufu`",
+                        "mufu": {"achieved_exps_per_s": a["exps"] / per_call_s, "peak_exps_per_s": mufu_peak,
+                                 "frac": a["exps"] / per_call_s / mufu_peak}}
         elif "bytes" in a:
             ach = a["bytes"] / per_call_s / 1e9
             roofline = {"kernel": top["call"], "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
