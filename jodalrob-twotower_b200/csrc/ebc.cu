@@ -394,36 +394,53 @@ __device__ __forceinline__ void gather_sum(float4& acc, const float* __restrict_
   for (; i < hi; ++i, p += E) f4_add(acc, __ldg(reinterpret_cast<const float4*>(p)));
 }
 
-// level 1 for long rows: one lane group per chunk of SEG_CHUNK sorted entries
+// level 1 for long rows: SUB lane groups per chunk of SEG_CHUNK sorted entries. Each group sums a contiguous
+// SEG_CHUNK / SUB slice of the piece in order, the SUB partial sums are folded by a fixed butterfly ((0+1)+(2+3)):
+// deterministic, and SUB times the parallelism of one group per chunk (the kernel is latency bound: few chunks, long chains).
 __global__ void __launch_bounds__(256)
 ebc_piece_kernel(const int32_t* __restrict__ srow, const float* __restrict__ gs, int64_t n,
                  const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_begin,
-                 const int32_t* __restrict__ row_end, int E, int G, float* __restrict__ pieces) {
+                 const int32_t* __restrict__ row_end, int E, int G, int SUB, float* __restrict__ pieces) {
   if (d_n) n = *d_n;
+  const int unit = G * SUB;  // lanes per chunk: divides 32
   const int lane = threadIdx.x % G;
-  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+  const int sub = (threadIdx.x % unit) / G;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x / unit) + threadIdx.x / unit;
   const int64_t lo = chunk * SEG_CHUNK;
-  if (lo >= n) return;
-  const int64_t hi = (lo + SEG_CHUNK < n) ? lo + SEG_CHUNK : n;
+  const bool live = lo < n;  // whole warps stay converged for the shuffles: no early return
+  const int64_t hi = live ? ((lo + SEG_CHUNK < n) ? lo + SEG_CHUNK : n) : lo;
   const int vec_per_row = E >> 2;
-  const int32_t r0 = srow[lo], r1 = srow[hi - 1];
-  const int64_t b0 = row_begin[r0], e0 = row_end[r0];
-  const int64_t b1 = row_begin[r1], e1 = row_end[r1];
-  // piece 0: the long row covering index lo
-  if (e0 - b0 > SEG_CHUNK) {
-    const int64_t pe = e0 < hi ? e0 : hi;
-    for (int c = lane; c < vec_per_row; c += G) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      gather_sum(acc, gs, lo, pe, E, c);
-      *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 0) * E) + 4 * c) = acc;
-    }
+  const int span = SEG_CHUNK / SUB;
+  int64_t b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+  if (live) {
+    const int32_t r0 = srow[lo], r1 = srow[hi - 1];
+    b0 = row_begin[r0]; e0 = row_end[r0];
+    b1 = row_begin[r1]; e1 = row_end[r1];
   }
-  // piece 1: a long row that begins strictly inside the chunk (it necessarily runs past hi)
-  if (e1 - b1 > SEG_CHUNK && b1 > lo) {
-    for (int c = lane; c < vec_per_row; c += G) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      gather_sum(acc, gs, b1, hi, E, c);
-      *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 1) * E) + 4 * c) = acc;
+  // piece 0: the long row covering index lo; piece 1: a long row that begins strictly inside the chunk (it runs past hi)
+  const bool p0 = live && (e0 - b0 > SEG_CHUNK), p1 = live && (e1 - b1 > SEG_CHUNK) && b1 > lo;
+  const int64_t pe = e0 < hi ? e0 : hi;
+  for (int c0 = 0; c0 < vec_per_row; c0 += G) {  // uniform trip count: every lane of the warp reaches the shuffles
+    const int c = c0 + lane;
+    const bool cv = c < vec_per_row;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p0 && cv) {
+      const int64_t s_lo = lo + (int64_t)sub * span, s_hi = s_lo + span < pe ? s_lo + span : pe;
+      if (s_lo < s_hi) gather_sum(a0, gs, s_lo, s_hi, E, c);
+    }
+    if (p1 && cv) {
+      const int64_t s_lo = b1 + (int64_t)sub * span, s_hi = s_lo + span < hi ? s_lo + span : hi;
+      if (s_lo < s_hi) gather_sum(a1, gs, s_lo, s_hi, E, c);
+    }
+    for (int off = G; off < unit; off <<= 1) {
+      a0.x += __shfl_xor_sync(0xffffffffu, a0.x, off); a0.y += __shfl_xor_sync(0xffffffffu, a0.y, off);
+      a0.z += __shfl_xor_sync(0xffffffffu, a0.z, off); a0.w += __shfl_xor_sync(0xffffffffu, a0.w, off);
+      a1.x += __shfl_xor_sync(0xffffffffu, a1.x, off); a1.y += __shfl_xor_sync(0xffffffffu, a1.y, off);
+      a1.z += __shfl_xor_sync(0xffffffffu, a1.z, off); a1.w += __shfl_xor_sync(0xffffffffu, a1.w, off);
+    }
+    if (sub == 0 && cv) {
+      if (p0) *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 0) * E) + 4 * c) = a0;
+      if (p1) *reinterpret_cast<float4*>(pieces + ((chunk * 2 + 1) * E) + 4 * c) = a1;
     }
   }
 }
@@ -787,7 +804,11 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
       ebc_gather_sorted_kernel<float><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs);
     else
       ebc_gather_sorted_kernel<__nv_bfloat16><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs);
-    ebc_piece_kernel<<<ceil_div(n_chunks, gpb), threads, 0, s>>>(sorted_rows, gs, n, d_n, row_begin, row_end, E, G, pieces);
+    int SUB = 4;
+    while (SUB > 1 && (G * SUB > 32 || 32 % (G * SUB) != 0)) SUB >>= 1;
+    if (32 % G != 0) SUB = 1;  // lane groups that straddle warps cannot shuffle: one group per chunk
+    ebc_piece_kernel<<<ceil_div(n_chunks, threads / (G * SUB)), threads, 0, s>>>(sorted_rows, gs, n, d_n, row_begin, row_end, E, G,
+                                                                                 SUB, pieces);
   }
   if (mode == TT_ADAM_SPARSE) {
     if (n > 0)

@@ -149,6 +149,8 @@ class TwoTowerEngine:
         self.two_streams = True
         self._side = torch.cuda.Stream(self.device)
         self._sort_stream = torch.cuda.Stream(self.device)
+        # two helper streams per tower: the weight gradients of a tower's layers are independent of each other
+        self._wg_streams = [[torch.cuda.Stream(self.device) for _ in range(2)] for _ in range(2)]
         self.launches = 0  # kernels launched through the C ABI (bench.py's gpu_launches)
         self.profile: Optional[list] = None  # set to [] to collect (tag, n_kernels, ev0, ev1) per C-ABI call
         self.profile_tag = ""
@@ -305,7 +307,7 @@ class TwoTowerEngine:
         # one scratch per tower so the two towers may run on different streams
         ws.bn_ws = [torch.empty(max(max_bn, 256), dtype=torch.uint8, device=dev) for _ in range(2)]
         ws.bn_sums = [torch.zeros(2 * max(cfg.hidden[1:] + [1]), dtype=torch.float64, device=dev) for _ in range(2)]
-        ws.wg_ws = [torch.empty(max_wg, dtype=torch.uint8, device=dev) for _ in range(2)]
+        ws.wg_ws = [[torch.empty(max_wg, dtype=torch.uint8, device=dev) for _ in range(3)] for _ in range(2)]
         ws.sim_ws = torch.empty(q("tt_simce_workspace_bytes", B, B, cfg.final_dim), dtype=torch.uint8, device=dev)
         ws.row_sumexp = torch.empty(B, **f32)
         ws.col_sumexp = torch.empty(B, **f32)
@@ -542,16 +544,32 @@ class TwoTowerEngine:
             self._lin_dgrad(ws.dh[t][bi], h, pre + f"mlp.{idx}.weight", dxin, win, B, h, win)
             wgrads.append((ws.dh[t][bi], h, xin, win, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", h, win))
         self._mark_dc_ready(t, ws)
-        for dy_, ldy_, x_, ldx_, wn_, bn_, n_, k_ in wgrads:
-            self._lin_wgrad(dy_, ldy_, x_, ldx_, wn_, bn_, B, n_, k_, ws.wg_ws[t])
         if self.act != TT_F32:
             dense_in = ws.x16[t]
         else:
             dense_in = ws.inputs[t]
             if dense_in.dtype != torch.float32:
                 dense_in = dense_in.float()
-        self._lin_wgrad(ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", B, H0,
-                        dense_dim, ws.wg_ws[t])
+        wgrads.append((ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", H0, dense_dim))
+        # every dY exists now; the layers' weight gradients are independent: fan them out over the tower's stream and its two
+        # helper streams (own scratch each), join at the end
+        cur = torch.cuda.current_stream(self.device)
+        fan = self.two_streams and self.profile is None
+        joins = []
+        for i, (dy_, ldy_, x_, ldx_, wn_, bn_, n_, k_) in enumerate(wgrads):
+            lane = i % 3 if fan else 0
+            if lane == 0:
+                self._lin_wgrad(dy_, ldy_, x_, ldx_, wn_, bn_, B, n_, k_, ws.wg_ws[t][0])
+            else:
+                st = self._wg_streams[t][lane - 1]
+                st.wait_event(ws.dc_ready[t])
+                with torch.cuda.stream(st):
+                    self._lin_wgrad(dy_, ldy_, x_, ldx_, wn_, bn_, B, n_, k_, ws.wg_ws[t][lane])
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                joins.append(ev)
+        for ev in joins:
+            cur.wait_event(ev)
 
     def _mark_dc_ready(self, t: int, ws: _Ws):
         """The gradient w.r.t. the tower's concat buffer is complete: everything the large-table update needs from this tower."""
