@@ -50,7 +50,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int stage_bytes = a_bytes + b_bytes;
   const int ring = p.ring;
   GemmTcSmem* sb = reinterpret_cast<GemmTcSmem*>(base + ring * stage_bytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: role dispatch and everything derived from kernel parameters stays warp-uniform, so the
+  // tcgen05 / TMA operands live in uniform registers (a divergent `if (lane == 0)` makes ptxas wrap each one in a waterfall loop)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * 128, n0 = (int64_t)blockIdx.y * p.tn;
   const int total_stages = (int)((p.R + GT_BK - 1) / GT_BK);
   const int s_begin = blockIdx.z * p.stages_per_split;
@@ -72,14 +74,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem = sb->tmem_base;
 
   if (warp == 5) {
-    if (lane == 0) {
-      int st = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < n_stages; ++i) {
-        mbar_wait(&sb->empty[st], ph ^ 1);
-        unsigned char* sa = base + st * stage_bytes;
-        unsigned char* sbm = sa + a_bytes;
-        const int r0 = (s_begin + i) * GT_BK;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_wait(&sb->empty[st], ph ^ 1);
+      unsigned char* sa = base + st * stage_bytes;
+      unsigned char* sbm = sa + a_bytes;
+      const int r0 = (s_begin + i) * GT_BK;
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&sb->full[st], (uint32_t)stage_bytes);
         if (!p.a_mn) {
           tma_load_2d(sa, &map_a, r0, (int)m0, &sb->full[st]);              // box {64 r, 128 m}
@@ -93,35 +95,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tma_load_2d(sbm, &map_b, (int)n0, r0, &sb->full[st]);             // box {64 n, 64 r} x (tn / 64)
           if (p.tn == 128) tma_load_2d(sbm + 8192, &map_b, (int)n0 + 64, r0, &sb->full[st]);
         }
-        if (++st == ring) {
-          st = 0;
-          ph ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++st == ring) {
+        st = 0;
+        ph ^= 1;
       }
     }
   } else if (warp == 4) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.tn, p.a_mn, p.b_mn);
-      const uint32_t base_a = smem_u32(base);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < n_stages; ++i) {
-        mbar_wait(&sb->full[st], ph);
-        tc_fence_after();
-        const uint32_t sa = base_a + st * stage_bytes, sbm = sa + a_bytes;
+    const uint32_t idesc = make_idesc(128, p.tn, p.a_mn, p.b_mn);
+    const uint32_t base_a = smem_u32(base);
+    // descriptors of stage 0, k-step 0; stages and k-steps only move the 14-bit start-address field
+    const uint64_t da0 = p.a_mn ? make_desc(base_a, 8192, 1024) : make_desc(base_a, 16, 1024);
+    const uint64_t db0 = p.b_mn ? make_desc(base_a + a_bytes, 8192, 1024) : make_desc(base_a + a_bytes, 16, 1024);
+    const uint32_t ka = p.a_mn ? (2048 >> 4) : (32 >> 4), kb = p.b_mn ? (2048 >> 4) : (32 >> 4);
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_wait(&sb->full[st], ph);
+      tc_fence_after();
+      const uint64_t da = da0 + (uint64_t)(st * stage16), db = db0 + (uint64_t)(st * stage16);
+      if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < GT_BK / 16; ++k) {
-          const uint64_t da = p.a_mn ? make_desc(sa + k * 2048, 8192, 1024) : make_desc(sa + k * 32, 16, 1024);
-          const uint64_t db = p.b_mn ? make_desc(sbm + k * 2048, 8192, 1024) : make_desc(sbm + k * 32, 16, 1024);
-          umma_bf16(tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < GT_BK / 16; ++k) umma_bf16(tmem, da + (uint64_t)(k * ka), db + (uint64_t)(k * kb), idesc, (i > 0 || k > 0) ? 1u : 0u);
         umma_commit(&sb->empty[st]);
-        if (++st == ring) {
-          st = 0;
-          ph ^= 1;
-        }
+        if (i == n_stages - 1) umma_commit(&sb->acc_full);
       }
-      umma_commit(&sb->acc_full);
+      __syncwarp();
+      if (++st == ring) {
+        st = 0;
+        ph ^= 1;
+      }
     }
   } else {
     // epilogue: thread == output row
