@@ -206,6 +206,7 @@ class DistributedEngine(TwoTowerEngine):
         # the company tower runs on the side stream with its own communicator for the SyncBN all-reduces
         self.comm_t = [comm, comm.clone()]
         self.two_streams = True
+        self.sharded_lookup = True
         if lv:
             assert self.total_rows == self.plan.local_rows, (self.total_rows, self.plan.local_rows)
 

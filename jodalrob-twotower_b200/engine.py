@@ -147,6 +147,7 @@ class TwoTowerEngine:
         # the two towers are independent until the loss: run the company tower on a side stream (fork/join with events;
         # inside a CUDA graph capture this becomes two parallel branches)
         self.two_streams = True
+        self.sharded_lookup = False  # DistributedEngine: the lookup is one exchange for both towers
         self._side = torch.cuda.Stream(self.device)
         self._sort_stream = torch.cuda.Stream(self.device)
         # two helper streams per tower: the weight gradients of a tower's layers are independent of each other
@@ -387,8 +388,27 @@ class TwoTowerEngine:
                        self.KL[t], self.P_tot // E, ws.rows.data_ptr() + 4 * rows_off, s)
         ws.values, ws.layout = list(values), layout
 
+    def tower_prefix(self, t: int, ws: _Ws, dense: torch.Tensor):
+        """The part of a tower that does not need the embedding lookup: the dense projection into columns [0, H0) of the
+        concat buffer. The train step runs it on a helper stream underneath the lookup."""
+        cfg, B, s = self.cfg, ws.B, self._stream()
+        name, keys, _, dense_dim = cfg.tower(t)
+        self.profile_tag = name
+        H0 = cfg.hidden[0]
+        ld = H0 + len(keys) * cfg.emb_dim
+        pre = f"{name}_tower."
+        dense = dense.contiguous()
+        if dense.dtype != torch.float32:
+            dense = dense.float()
+        if self.act != TT_F32:
+            self._call("tt_cast_bf16", ptr(dense), ptr(ws.x16[t]), B * dense_dim, s)
+            dense = ws.x16[t]
+        self._lin_fwd(dense, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", ws.c[t], ld, False, B, H0,
+                      dense_dim, 0)
+
     def tower_forward(self, t: int, ws: _Ws, dense: torch.Tensor, values: Optional[torch.Tensor], train: bool,
-                      layout: int = TT_LAYOUT_SAMPLE_MAJOR, masks: Optional[Sequence[torch.Tensor]] = None):
+                      layout: int = TT_LAYOUT_SAMPLE_MAJOR, masks: Optional[Sequence[torch.Tensor]] = None,
+                      skip_prefix: bool = False):
         """Dense projection + MLP + L2 norm of one tower. If `values` is given the embedding lookup of this tower is
         done here first (stand-alone tower call); the train step looks both towers up front via embedding_forward."""
         if values is not None:
@@ -401,14 +421,9 @@ class TwoTowerEngine:
         H0 = cfg.hidden[0]
         ld = H0 + K * E
         pre = f"{name}_tower."
-        dense = dense.contiguous()
-        if dense.dtype != torch.float32:
-            dense = dense.float()
-        if self.act != TT_F32:
-            self._call("tt_cast_bf16", ptr(dense), ptr(ws.x16[t]), B * dense_dim, s)
-            dense = ws.x16[t]
-        self._lin_fwd(dense, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", ws.c[t], ld, False, B, H0,
-                      dense_dim, 0)
+        if not skip_prefix:
+            self.tower_prefix(t, ws, dense)
+            self.profile_tag = name
         x, width, idx = ws.c[t], ld, 0
         for bi, h in enumerate(cfg.hidden[1:]):
             self._lin_fwd(x, width, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", ws.h[t][bi], h, False, B, h, width, 1)
@@ -466,18 +481,39 @@ class TwoTowerEngine:
         ws = self.workspace(B)
         ws.inputs = (notice_dense.contiguous(), company_dense.contiguous())
         self.refresh_bf16_weights()
-        self.embedding_forward(ws, [notice_values, company_values], lay)
+        main = torch.cuda.current_stream(self.device)
+        overlap = self.two_streams and self.profile is None
+        if overlap:  # the dense projections do not need the lookup: run them underneath it on helper streams
+            pre = [self._wg_streams[0][0], self._wg_streams[1][0]]
+            for t, d in ((0, notice_dense), (1, company_dense)):
+                pre[t].wait_stream(main)
+                with torch.cuda.stream(pre[t]):
+                    self.tower_prefix(t, ws, d)
+        split = overlap and not self.sharded_lookup
+        if split:  # the two towers' lookups side by side (the company tower continues on `_side` anyway)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.embedding_forward(ws, [None, company_values], lay)
+            self.embedding_forward(ws, [notice_values, None], lay)
+            ws.values = [notice_values, company_values]
+        else:
+            self.embedding_forward(ws, [notice_values, company_values], lay)
         if sort_on_side:  # the index side of the sparse backward only needs the looked-up rows
-            self._sort_stream.wait_stream(torch.cuda.current_stream(self.device))
+            self._sort_stream.wait_stream(main)
+            if split:
+                self._sort_stream.wait_stream(self._side)
             with torch.cuda.stream(self._sort_stream):
                 self.embedding_sort(ws)
         m0, m1 = (None, None) if masks is None else (masks[0], masks[1])
         if self.two_streams:
-            main = torch.cuda.current_stream(self.device)
-            self._side.wait_stream(main)
+            if not split:
+                self._side.wait_stream(main)
+            if overlap:
+                main.wait_stream(pre[0])
+                self._side.wait_stream(pre[1])
             with torch.cuda.stream(self._side):
-                self.tower_forward(1, ws, company_dense, None, train, lay, masks=m1)
-            self.tower_forward(0, ws, notice_dense, None, train, lay, masks=m0)
+                self.tower_forward(1, ws, company_dense, None, train, lay, masks=m1, skip_prefix=overlap)
+            self.tower_forward(0, ws, notice_dense, None, train, lay, masks=m0, skip_prefix=overlap)
             main.wait_stream(self._side)
         else:
             self.tower_forward(0, ws, notice_dense, None, train, lay, masks=m0)
