@@ -269,7 +269,8 @@ int tt_l2norm_backward(const float* de, const void* e, int32_t e_dtype, const fl
  *   row_sumexp [Bx], col_sumexp [By] (over this rank's rows), row_sum_s [Bx], col_sum_s [By],
  *   diag [Bx] = S[r, diag_offset+r], row_argmax i32 [Bx] (first maximum, torch.argmax tie rule).
  * tt_simce_finalize turns (globally summed) sums into  inv_row [Bx], inv_col [By] for the backward
- * and partial f64[8] = {sum_i l_row, sum_{j in my diag range} l_col, hits, sum diag, sum S, 0,0,0};
+ * and partial f64[16][8]: 16 block partials of {sum_i l_row, sum_{j in my diag range} l_col, hits, sum diag, sum S, 0,0,0}
+ * (the buffer must hold 128 doubles; distributed callers all-reduce all of it);
  * tt_simce_scalars maps (globally summed) partials to {loss, accuracy, pos_mean, neg_mean, gap}. */
 int64_t tt_simce_workspace_bytes(int64_t Bx, int64_t By, int32_t F);
 int tt_simce_forward(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,

@@ -132,51 +132,37 @@ __global__ void simce_cols_reduce_kernel(SimceFwdWs ws, int64_t By, int nRT, flo
 // ------------------------------------------------------------------------------------------------
 // finalize: sums -> reciprocal sums for the backward + five partial scalars (deterministic tree)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+constexpr int FIN_BLOCKS = 16;  // partial is f64[FIN_BLOCKS][8]: block partials, summed in block order by simce_scalars_kernel
+
+__global__ void __launch_bounds__(512)
 simce_finalize_kernel(const float* __restrict__ row_sumexp, const float* __restrict__ col_sumexp,
                       const float* __restrict__ row_sum_s, const float* __restrict__ col_sum_s,
                       const float* __restrict__ diag, const int32_t* __restrict__ row_argmax, int64_t Bx, int64_t By,
                       int64_t diag_offset, double inv_bg, float inv_temp, float ls, float* __restrict__ inv_row,
                       float* __restrict__ inv_col, double* __restrict__ partial) {
-  __shared__ double red[5][32];
+  __shared__ double red[5][16];
   const int t = threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   double a[5] = {0, 0, 0, 0, 0};
-  // one block (fixed summation order); rows are taken four at a time so the independent loads of a batch are all in flight
-  constexpr int U = 4;
-  for (int64_t i0 = t; i0 < Bx; i0 += 1024 * U) {
-    float se[U], dg[U], rs[U], ce[U], cs[U];
-    int32_t am[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + (int64_t)u * 1024, j = diag_offset + i;
-      const bool ok = i < Bx, okc = ok && j < By;
-      se[u] = ok ? row_sumexp[i] : 1.f;
-      dg[u] = ok ? diag[i] : 0.f;
-      rs[u] = (ok && row_sum_s) ? row_sum_s[i] : 0.f;
-      ce[u] = okc ? col_sumexp[j] : 1.f;
-      cs[u] = (okc && col_sum_s) ? col_sum_s[j] : 0.f;
-      am[u] = (ok && row_argmax) ? row_argmax[i] : -1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < Bx; i += stride) {
+    const float se = row_sumexp[i];
+    inv_row[i] = 1.f / se;
+    const double lse_r = (double)inv_temp + (double)logf(se);  // fp32 log (1 ulp) is plenty: the sum over rows is fp64
+    const double d = (double)diag[i];
+    const double rss = row_sum_s ? (double)row_sum_s[i] : 0.0;
+    a[0] += lse_r - (1.0 - ls) * d - (double)ls * inv_bg * rss;
+    const int64_t j = diag_offset + i;
+    if (j < By) {
+      const double lse_c = (double)inv_temp + (double)logf(col_sumexp[j]);
+      const double css = col_sum_s ? (double)col_sum_s[j] : 0.0;
+      a[1] += lse_c - (1.0 - ls) * d - (double)ls * inv_bg * css;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + (int64_t)u * 1024, j = diag_offset + i;
-      if (i >= Bx) break;
-      inv_row[i] = 1.f / se[u];
-      const double lse_r = (double)inv_temp + (double)logf(se[u]);  // fp32 log (1 ulp) is plenty: the sum over rows is fp64
-      const double d = (double)dg[u];
-      const double rss = (double)rs[u];
-      a[0] += lse_r - (1.0 - ls) * d - (double)ls * inv_bg * rss;
-      if (j < By) {
-        const double lse_c = (double)inv_temp + (double)logf(ce[u]);
-        a[1] += lse_c - (1.0 - ls) * d - (double)ls * inv_bg * (double)cs[u];
-      }
-      if (row_argmax && (int64_t)am[u] == j) a[2] += 1.0;
-      a[3] += d;
-      a[4] += rss;
-    }
+    if (row_argmax && (int64_t)row_argmax[i] == j) a[2] += 1.0;
+    a[3] += d;
+    a[4] += rss;
   }
-  for (int64_t j = t; j < By; j += 1024) inv_col[j] = 1.f / col_sumexp[j];
-  // fixed-shape reduction: butterfly inside each warp, then warp 0 folds the 32 warp sums
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + t; j < By; j += stride) inv_col[j] = 1.f / col_sumexp[j];
+  // fixed-shape reduction: butterfly inside each warp, then warp 0 folds the 16 warp sums; blocks are folded in order later
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
 #pragma unroll
@@ -190,17 +176,20 @@ simce_finalize_kernel(const float* __restrict__ row_sumexp, const float* __restr
   if (t < 32) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-      double v = red[k][t];
+      double v = t < 16 ? red[k][t] : 0.0;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (t == 0) partial[k] = v;
+      for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (t == 0) partial[blockIdx.x * 8 + k] = v;
     }
-    if (t >= 5 && t < 8) partial[t] = 0.0;
+    if (t >= 5 && t < 8) partial[blockIdx.x * 8 + t] = 0.0;
   }
 }
 
-__global__ void simce_scalars_kernel(const double* __restrict__ p, long long Bg, float* __restrict__ out) {
+__global__ void simce_scalars_kernel(const double* __restrict__ part, long long Bg, float* __restrict__ out) {
   if (threadIdx.x != 0) return;
+  double p[5] = {0, 0, 0, 0, 0};
+  for (int blk = 0; blk < FIN_BLOCKS; ++blk)
+    for (int k = 0; k < 5; ++k) p[k] += part[blk * 8 + k];
   const double b = (double)Bg;
   const double loss = 0.5 * (p[0] + p[1]) / b;
   const double pos = p[3] / b;
@@ -390,7 +379,7 @@ int tt_simce_finalize(const float* row_sumexp, const float* col_sumexp, const fl
   TT_CHECK_ARG(row_sumexp && col_sumexp && diag && inv_row && inv_col && partial && Bx > 0 && By > 0 && B_global > 0,
                "tt_simce_finalize: bad arguments");
   TT_CHECK_ARG(label_smoothing == 0.f || (row_sum_s && col_sum_s), "tt_simce_finalize: label smoothing needs the sum_s vectors");
-  simce_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_sumexp, col_sumexp, row_sum_s, col_sum_s, diag,
+  simce_finalize_kernel<<<FIN_BLOCKS, 512, 0, (cudaStream_t)stream>>>(row_sumexp, col_sumexp, row_sum_s, col_sum_s, diag,
                                                              row_argmax, Bx, By, diag_offset, 1.0 / (double)B_global,
                                                              inv_temp, label_smoothing, inv_row, inv_col, partial);
   TT_LAUNCH_CHECK("simce_finalize_kernel");

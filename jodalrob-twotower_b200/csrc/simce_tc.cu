@@ -534,20 +534,32 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 }
 
 // ---------------------------------------------------------------- small deterministic reductions
-// sum_j S_ij = inv_temp * X_i . (sum_j Y_j): partial column sums of Y, block b folds rows b*4+l, b*4+l + 4*YS_BLOCKS, ... in order
-constexpr int YS_BLOCKS = 64;
+// sum_j S_ij = inv_temp * X_i . (sum_j Y_j): partial column sums of Y. 512 threads = (F/8) column groups x row lanes, 16-byte
+// loads; block b takes rows b*L + l, +L*YS_BLOCKS, ... (fixed order), the row lanes are folded in order through shared memory
+constexpr int YS_BLOCKS = 32;
 __global__ void __launch_bounds__(512)
 tc_ysum_partial_kernel(const __nv_bfloat16* __restrict__ Y, int64_t By, int F, float* __restrict__ part /* [YS_BLOCKS][F] */) {
-  __shared__ float sh[8][128];  // 512 / F row lanes (8 at F = 64)
-  const int c = threadIdx.x % F, l = threadIdx.x / F;  // F in {64, 128}: 512 threads = (512 / F) row lanes x F columns
-  const int lanes = 512 / F;
-  float a = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * lanes + l; r < By; r += (int64_t)YS_BLOCKS * lanes) a += __bfloat162float(Y[r * F + c]);
-  sh[l][c] = a;
+  __shared__ float sh[64][129];  // [row lane][column], odd pitch
+  const int groups = F >> 3, lanes = 512 / groups;  // F = 64: 8 x 64; F = 128: 16 x 32
+  const int g = threadIdx.x % groups, l = threadIdx.x / groups;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = (int64_t)blockIdx.x * lanes + l; r < By; r += (int64_t)YS_BLOCKS * lanes) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(Y + r * F) + g);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 f = __bfloat1622float2(h[u]);
+      a[2 * u] += f.x;
+      a[2 * u + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) sh[l][g * 8 + u] = a[u];
   __syncthreads();
-  if (l == 0) {
-    for (int k = 1; k < lanes; ++k) a += sh[k][c];
-    part[blockIdx.x * F + c] = a;
+  if (threadIdx.x < F) {
+    float t = sh[0][threadIdx.x];
+    for (int k = 1; k < lanes; ++k) t += sh[k][threadIdx.x];
+    part[blockIdx.x * F + threadIdx.x] = t;
   }
 }
 

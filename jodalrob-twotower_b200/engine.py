@@ -318,7 +318,7 @@ class TwoTowerEngine:
         ws.row_argmax = torch.empty(B, dtype=torch.int32, device=dev)
         ws.inv_row = torch.empty(B, **f32)
         ws.inv_col = torch.empty(B, **f32)
-        ws.partial = torch.zeros(8, dtype=torch.float64, device=dev)
+        ws.partial = torch.zeros(128, dtype=torch.float64, device=dev)  # 16 block partials x 8
         ws.out5 = torch.zeros(5, **f32)
         ws.sort_ws = torch.empty(q("tt_ebc_sort_workspace_bytes", n_tot, max(self.total_rows, 1)), dtype=torch.uint8, device=dev)
         ws.piece_ws = torch.empty(q("tt_ebc_piece_workspace_bytes", n_tot, E), dtype=torch.uint8, device=dev)
