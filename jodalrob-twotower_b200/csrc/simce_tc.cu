@@ -29,7 +29,7 @@ namespace tt {
 
 constexpr int TCM = 128;          // rows per CTA block (UMMA M)
 constexpr int TCN = 128;          // columns per tile  (UMMA N)
-constexpr int TC_STAGES = 4;      // Y smem ring
+constexpr int TC_STAGES = 6;      // Y smem ring (upper bound; the depth in use is TcParams::n_stages)
 constexpr int TC_SBUF = 3;        // forward: S accumulators in TMEM (3 x 128 columns), the MMA runs two tiles ahead of the
                                   // epilogue; backward: 2, the other 256 columns hold the [E.Y | E.Ys] accumulator(s)
 constexpr int TC_EPI_WARPS = 16;  // four per SM sub-partition (the epilogue is MUFU/latency bound): rows = TMEM lane quarter
@@ -55,7 +55,8 @@ struct TcParams {
   int use_tma;
   int n_stages;          // Y smem ring depth (<= TC_STAGES)
   int n_xbuf;            // X row-block buffers (1 or 2)
-  int n_dbuf;            // backward: dX accumulators in TMEM (2 when 3 * 128 + 2 * F <= 512 columns)
+  int n_dbuf;            // backward: [E.Y | E.Ys] accumulators in TMEM
+  int n_sbuf;            // S buffers in TMEM: 3 forward; backward 2 (F = 64) or 1 (F = 128), see the TMEM map in the kernel
   long long* dbg_ts;     // optional timeline buffer (block 0): [4 roles][512 tiles][4 events] clock64 stamps, see scripts/time_simce.py
   // forward outputs: partials per (chunk, row)
   float* row_e;
@@ -142,34 +143,37 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
   }
 }
 
-// Backward: E = exp(S - 1/T) for TC_CW logits -> bf16, written as 16-byte chunks of this row into the swizzled K-major P
-// tile. Nothing else happens per logit: with dS_ij = E_ij (ix_i + iy_j) - target_ij the row scale ix_i is applied to the
+// Backward: E = exp(S - 1/T) for TC_CW logits -> bf16 pairs, stored straight back into tensor memory (tcgen05.st) where the
+// second MMA reads them as its A operand: the E tile never touches shared memory. Nothing else happens per logit: with dS_ij = E_ij (ix_i + iy_j) - target_ij the row scale ix_i is applied to the
 // accumulator, the column scale iy_j is folded into the second MMA operand (Ys = diag(iy) Y), and the target terms are rank-one
 // / diagonal corrections added by tc_dx_reduce_kernel:
 //   dX_i = ix_i (E Y)_i + (E Ys)_i - t_off sum_j Y_j - (t_diag - t_off) Y_dcol(i).
 // Ragged tiles need no masks: rows / columns past the edge are zero-filled operands (they contribute nothing, or are not stored).
-__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], int c_in_tile, float c1, float c0, unsigned char* prow, int rsw) {
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], float c1, float c0, uint32_t p_taddr) {
+  uint32_t w[TC_CW / 2];
 #pragma unroll
-  for (int q = 0; q < TC_CW / 8; ++q) {  // 8 columns -> one 16-byte chunk
-    uint32_t w[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float e0 = ex2f(fmaf(__uint_as_float(r[q * 8 + 2 * u]), c1, c0));
-      const float e1 = ex2f(fmaf(__uint_as_float(r[q * 8 + 2 * u + 1]), c1, c0));
-      __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);
-      w[u] = *reinterpret_cast<uint32_t*>(&t);
-    }
-    const int cc = ((c_in_tile & 63) >> 3) + q;  // 16-byte chunk index inside the 64-column atom
-    *reinterpret_cast<uint4*>(prow + ((cc ^ rsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  for (int u = 0; u < TC_CW / 2; ++u) {
+    const float e0 = ex2f(fmaf(__uint_as_float(r[2 * u]), c1, c0));
+    const float e1 = ex2f(fmaf(__uint_as_float(r[2 * u + 1]), c1, c0));
+    __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);  // low half = even column
+    w[u] = *reinterpret_cast<uint32_t*>(&t);
   }
+  tmem_st8(p_taddr, w);
 }
 
 template <bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                 const __grid_constant__ CUtensorMap map_ys, const TcParams p) {
-  constexpr int NSB = BWD ? 2 : TC_SBUF;        // S buffers in TMEM
+  // TMEM map (512 columns). Forward: three S buffers. Backward: n_sbuf S buffers | [E.Y | E.Ys] accumulator (2F columns) |
+  // two E buffers (64 columns each: 128 bf16 per row, two per column): F = 64 -> 256 + 128 + 128, F = 128 -> 128 + 256 + 128.
+  const int NSB = p.n_sbuf;
   extern __shared__ unsigned char smem_raw[];
+  if (p.dbg_ts && threadIdx.x == 0) {  // per-CTA wall-clock stamps (ns): entry, after set-up, exit
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg_ts[2 * 2048 + 1024 + blockIdx.x * 4 + 0] = (long long)g;
+  }
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int NA = p.F >> 6;                      // swizzle atoms along K (1 or 2)
   const int tile_bytes = NA * ATOM_BYTES;       // X / Y tile
@@ -177,8 +181,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int NST = p.n_stages;
   unsigned char* sX = base;                     // n_xbuf tiles (double-buffered across work items when they fit)
   unsigned char* sY = sX + p.n_xbuf * tile_bytes;  // NST stages
-  unsigned char* sP = sY + NST * stage_bytes;   // 2 x [128 x 128] bf16 (backward only)
-  TcSmem* sb = reinterpret_cast<TcSmem*>(sP + (BWD ? 2 * 2 * ATOM_BYTES : 0));
+  TcSmem* sb = reinterpret_cast<TcSmem*>(sY + NST * stage_bytes);
 
   // warp index through a shuffle: the compiler then treats the role dispatch (and everything computed under it from
   // kernel parameters) as warp-uniform, which keeps tcgen05 operands in uniform registers
@@ -204,7 +207,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb->d_full[i], 1);
-      mbar_init(&sb->d_empty[i], TC_EPI_WARPS);
+      mbar_init(&sb->d_empty[i], 8);  // the eight read-out warps
     }
     fence_barrier_init();
   }
@@ -213,8 +216,14 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
+  if (p.dbg_ts && threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg_ts[2 * 2048 + 1024 + blockIdx.x * 4 + 1] = (long long)g;
+  }
   const uint32_t tmem_d = tmem + NSB * TCN;  // backward accumulator(s): n_dbuf x 2F columns behind the S buffers
   const int n_dbuf = p.n_dbuf;
+  const uint32_t tmem_p = tmem_d + n_dbuf * 2 * p.F;  // two E buffers of 64 columns
 
   if (warp == TC_LOAD_WARP) {
     // =========================== operand loader ===========================
@@ -319,7 +328,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // The stage holds the Y tile and the Ys tile back to back, i.e. 2F/64 consecutive 64-column atoms: one N = 2F operand.
     if (BWD) {
       const uint32_t idesc2 = make_idesc(TCM, 2 * p.F, 0, 1);
-      const uint64_t dP0 = make_desc(smem_u32(sP), 16, 1024), dYmn0 = make_desc(smem_u32(sY), ATOM_BYTES, 1024);
+      const uint64_t dYmn0 = make_desc(smem_u32(sY), ATOM_BYTES, 1024);
       const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
       uint32_t p_iter = 0;
       int y_st = 0, d_buf = 0;
@@ -338,13 +347,12 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           mbar_wait(&sb->y_full[y_st], y_ph);  // long complete (MMA1 consumed it); acquires the TMA-written stage for this warp
           if (t == 0) mbar_wait(&sb->d_empty[d_buf], d_ph ^ 1);
           tc_fence_after();
-          const uint64_t dPb = dP0 + (uint64_t)(pb * ((2 * ATOM_BYTES) >> 4));
+          const uint32_t a_tmem = tmem_p + pb * (TCN / 2);
           const uint64_t dYm = dYmn0 + (uint64_t)(y_st * stage16);
           if (elect_one_sync()) {
 #pragma unroll
-            for (int kk = 0; kk < TCN / 16; ++kk)
-              umma_bf16(d_tmem, dPb + (uint64_t)((kk >> 2) * (ATOM_BYTES >> 4) + (kk & 3) * 2), dYm + (uint64_t)(kk * (2048 >> 4)), idesc2,
-                        (t > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < TCN / 16; ++kk)  // K = 16 logits columns per step = 8 TMEM columns of E
+              umma_bf16_ts(d_tmem, a_tmem + kk * 8, dYm + (uint64_t)(kk * (2048 >> 4)), idesc2, (t > 0 || kk > 0) ? 1u : 0u);
             umma_commit(&sb->p_empty[pb]);
             umma_commit(&sb->y_empty[y_st]);
             if (t == nt - 1) umma_commit(&sb->d_full[d_buf]);
@@ -372,8 +380,9 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const float c1 = p.c1, c0 = p.c0;
     const int t_part = (By & (TCN - 1)) ? p.n_col_tiles - 1 : -1;  // the ragged last column tile, if any
     uint32_t p_iter = 0, e_iter = 0;
-    // backward: the dX accumulator of an item is read out one tile into the NEXT item (when TMEM holds two accumulators), so
-    // the epilogue never idles while the last dS tiles of an item drain through MMA2
+    // backward: the accumulator of an item is read out one tile into the NEXT item, so the epilogue never idles while the last
+    // E tile of an item drains through MMA2 (with a single accumulator the next item's first MMA2 waits for that read-out, the
+    // epilogue itself does not wait for anything)
     int d_buf = 0;
     uint32_t d_ph = 0;
     bool pend = false;
@@ -384,36 +393,39 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     float pend_ixs = 0.f;
     int s_cur = 0;           // S ring cursor of the tile being processed; the phase flips when it wraps
     uint32_t s_cur_ph = 0;
-    // read one [E.Y | E.Ys] accumulator out of TMEM and apply the row scale: out = ix * (E.Y) + (E.Ys); the warps with
-    // slice * 32 < F own a 32-column slice of the F output columns each
+    // read one [E.Y | E.Ys] accumulator out of TMEM and apply the row scale: out = ix * (E.Y) + (E.Ys). Two of the four warps
+    // of each scheduler do this (half of the F columns of their 32 rows each): they need no MUFU meanwhile, so the other two
+    // run ahead into the next tile (one S / E buffer of slack) and the read-out stays off the MUFU-bound critical path.
     auto drain_d = [&](float* out, int db, uint32_t ph, bool ok, float ix, uint32_t (&r)[TC_CW]) {
+      if (slice >= 2) return;
       mbar_wait(&sb->d_full[db], ph);
       tc_fence_after();
-      if (slice * 32 < p.F) {
-        const uint32_t ta = tmem_d + db * 2 * p.F + ((uint32_t)(quarter * 32) << 16) + slice * 32;
+      const int h0 = slice * (p.F >> 1), h1 = h0 + (p.F >> 1);
+      const uint32_t ta = tmem_d + db * 2 * p.F + ((uint32_t)(quarter * 32) << 16);
+      for (int h = h0; h < h1; h += TC_CW) {
+        uint32_t r2[TC_CW];
+        tmem_ld16(ta + h, r);
+        tmem_ld16(ta + p.F + h, r2);
+        tmem_ld_wait_dep(r);
+        tmem_ld_wait_dep(r2);
+        if (ok) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r2[TC_CW];
-          tmem_ld16(ta + h * TC_CW, r);
-          tmem_ld16(ta + p.F + h * TC_CW, r2);
-          tmem_ld_wait_dep(r);
-          tmem_ld_wait_dep(r2);
-          if (ok) {
-#pragma unroll
-            for (int q = 0; q < TC_CW / 4; ++q)
-              *reinterpret_cast<float4*>(out + h * TC_CW + q * 4) =
-                  make_float4(fmaf(ix, __uint_as_float(r[q * 4]), __uint_as_float(r2[q * 4])),
-                              fmaf(ix, __uint_as_float(r[q * 4 + 1]), __uint_as_float(r2[q * 4 + 1])),
-                              fmaf(ix, __uint_as_float(r[q * 4 + 2]), __uint_as_float(r2[q * 4 + 2])),
-                              fmaf(ix, __uint_as_float(r[q * 4 + 3]), __uint_as_float(r2[q * 4 + 3])));
-          }
+          for (int q = 0; q < TC_CW / 4; ++q)
+            *reinterpret_cast<float4*>(out + h + q * 4) =
+                make_float4(fmaf(ix, __uint_as_float(r[q * 4]), __uint_as_float(r2[q * 4])),
+                            fmaf(ix, __uint_as_float(r[q * 4 + 1]), __uint_as_float(r2[q * 4 + 1])),
+                            fmaf(ix, __uint_as_float(r[q * 4 + 2]), __uint_as_float(r2[q * 4 + 2])),
+                            fmaf(ix, __uint_as_float(r[q * 4 + 3]), __uint_as_float(r2[q * 4 + 3])));
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb->d_empty[db]);
     };
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    int it_iter = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_iter) {
+      const bool istamp = p.dbg_ts && blockIdx.x == 0 && threadIdx.x == 0 && it_iter < 64;
+      if (istamp) p.dbg_ts[1 * 2048 + 1024 + it_iter * 4 + 0] = clock64();
       const int rb = item / p.n_chunks, ch = item - rb * p.n_chunks;
       const int t0 = ch * p.tiles_per_chunk;
       const int t1 = min(t0 + p.tiles_per_chunk, p.n_col_tiles);
@@ -438,6 +450,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       mbar_wait(&sb->s_full[s_cur], s_cur_ph);
       tc_fence_after();
       tmem_ld16(t_base + s_cur * TCN, rA);
+      if (istamp) p.dbg_ts[1 * 2048 + 1024 + it_iter * 4 + 1] = clock64();
       for (int t = t0; t < t1; ++t) {
         const bool generic = !BWD && (t == t_d0 || t == t_d1 || t == t_part);
         const int cb = t * TCN + slice * 32;
@@ -452,11 +465,12 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tmem_ld_wait_dep(rA);                        // first half landed
         tmem_ld16(t_base + s_cur * TCN + TC_CW, rB);  // second half in flight ...
         int pb = 0;
-        unsigned char* prow = nullptr;
-        if (BWD) {  // a free P buffer
+        uint32_t p_taddr = 0;
+        if (BWD) {  // a free E buffer: this thread's lane, the 16 columns that hold its 32 logits
           pb = p_iter & 1;
           mbar_wait(&sb->p_empty[pb], ((p_iter >> 1) & 1) ^ 1);
-          prow = sP + pb * 2 * ATOM_BYTES + (slice >> 1) * ATOM_BYTES + r_in_blk * 128;
+          tc_fence_after();
+          p_taddr = tmem_p + pb * (TCN / 2) + ((uint32_t)(quarter * 32) << 16) + slice * 16;
         }
         if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 1] = clock64();
         // ... while the first is processed
@@ -464,7 +478,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (generic) fwd_chunk<true>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
           else fwd_chunk<false>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
         } else {
-          bwd_chunk(rA, slice * 32, c1, c0, prow, r_in_blk & 7);
+          bwd_chunk(rA, c1, c0, p_taddr);
         }
         if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 2] = clock64();
         tmem_ld_wait_dep(rB);
@@ -481,8 +495,9 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (generic) fwd_chunk<true>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
           else fwd_chunk<false>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
         } else {
-          bwd_chunk(rB, slice * 32 + TC_CW, c1, c0, prow, r_in_blk & 7);
-          fence_proxy_async();
+          bwd_chunk(rB, c1, c0, p_taddr + TC_CW / 2);
+          tmem_st_wait();
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sb->p_full[pb]);
           ++p_iter;
@@ -507,8 +522,9 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
         }
       } else {
-        float* out = p.dx_part + ((int64_t)ch * p.Bx + row) * p.F + slice * 32;
-        if (n_dbuf == 2 && item + (int)gridDim.x < p.n_items) {
+        float* out = p.dx_part + ((int64_t)ch * p.Bx + row) * p.F;
+        if (istamp) p.dbg_ts[1 * 2048 + 1024 + it_iter * 4 + 2] = clock64();
+        if (item + (int)gridDim.x < p.n_items) {  // deferred: read out after the next item's first tile (no wait for MMA2 then)
           pend = true;
           pend_out = out;
           pend_buf = d_buf;
@@ -522,6 +538,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           d_buf = 0;
           d_ph ^= 1;
         }
+        if (istamp) p.dbg_ts[1 * 2048 + 1024 + it_iter * 4 + 3] = clock64();
       }
     }
   }
@@ -530,6 +547,11 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == TC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
+  }
+  if (p.dbg_ts && threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg_ts[2 * 2048 + 1024 + blockIdx.x * 4 + 2] = (long long)g;
   }
 }
 
@@ -778,14 +800,14 @@ static TcPlan make_plan(int64_t Bx, int64_t By) {
 static void tc_buffers(int F, bool bwd, int& n_stages, int& n_xbuf) {
   // backward stages hold Y and Ys (2 tiles) and 64 KB go to the two E buffers: stay under 227 KB
   const bool tight = bwd && F > 64;
-  n_stages = !bwd ? TC_STAGES : (tight ? 2 : 4);  // F = 64 backward: 32 + 4 * 32 + 64 KB
+  n_stages = !bwd ? 4 : (tight ? 3 : 6);  // backward stages hold Y and Ys: F = 64: 32 + 6 * 32 KB, F = 128: 32 + 3 * 64 KB
   n_xbuf = tight ? 1 : 2;
 }
 static size_t tc_smem_bytes(int F, bool bwd) {
   const int tile = (F >> 6) * ATOM_BYTES;
   int ns, nx;
   tc_buffers(F, bwd, ns, nx);
-  return 1024 + (size_t)tile * (nx + ns * (bwd ? 2 : 1)) + (bwd ? 4 * ATOM_BYTES : 0) + sizeof(TcSmem) + 64;
+  return 1024 + (size_t)tile * (nx + ns * (bwd ? 2 : 1)) + sizeof(TcSmem) + 64;
 }
 
 int64_t simce_tc_workspace_bytes(int64_t Bx, int64_t By, int F) {
@@ -820,6 +842,7 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   p.diag = diag; p.want_metrics = want_metrics; p.dbg_ts = want_metrics ? g_tc_dbg_ts : nullptr;
   tc_buffers(F, false, p.n_stages, p.n_xbuf);
   p.n_dbuf = 1;
+  p.n_sbuf = TC_SBUF;
   CUtensorMap mx, my;
   p.use_tma = (!g_tc_force_manual && make_map(&mx, X, Bx, F) && make_map(&my, Y, By, F)) ? 1 : 0;
   if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); }
@@ -859,7 +882,8 @@ int simce_tc_bwd(const void* X, const void* Y, int64_t Bx, int64_t By, int F, fl
   p.Ys = Ys;
   p.dbg_ts = g_tc_dbg_ts;
   tc_buffers(F, true, p.n_stages, p.n_xbuf);
-  p.n_dbuf = (2 * TCN + 2 * 2 * F <= 512) ? 2 : 1;
+  p.n_dbuf = 1;
+  p.n_sbuf = F == 64 ? 2 : 1;  // S buffers + 2F accumulator columns + 128 columns of E must fit 512
   tc_scale_rows_kernel<<<ceil_div(By * F / 8, 256), 256, 0, s>>>(p.Y, inv_y, gscale, By, F, Ys);
   const bool smooth = tgt_off != 0.f;
   if (smooth) {

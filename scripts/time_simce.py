@@ -68,5 +68,25 @@ def timeline(fn, name):
         m, e, l, m2 = mma[i], epi[i], ld[i], mma2[i]
         print(f"{i:3d} | {int(m[0])-t0:7d} {int(m[1]-m[0]):6d} {int(m[2]-m[1]):6d} {int(m[3]-m[2]):6d} | {int(e[0])-t0:7d} {int(e[1]-e[0]):6d} {int(e[2]-e[1]):6d} {int(e[3]-e[2]):6d} | {int(l[0])-t0:7d} {int(l[1]-l[0]):6d} | {int(m2[0])-t0:7d} {int(m2[1]-m2[0]):6d} {int(m2[2]-m2[1]):6d}")
 s = torch.cuda.current_stream().cuda_stream
+def items(fn, name):
+    ts = torch.zeros(4 * 2048, dtype=torch.int64, device=DEV)
+    lib.call("tt_debug_simce_timeline", ptr(ts))
+    fn(); torch.cuda.synchronize()
+    lib.call("tt_debug_simce_timeline", 0)
+    t = ts.cpu().view(4, 512, 4)
+    t0 = int(t[0][0, 0])
+    it = t[1][256:]
+    w = t[2][256:256 + 148]
+    w = w[w[:, 0] > 0]
+    if len(w):
+        k0 = int(w[:, 0].min())
+        print(f"{name} CTAs {len(w)}: first entry 0, last entry {int(w[:,0].max())-k0} ns, set-up done (mean) {float((w[:,1]-w[:,0]).float().mean()):.0f} ns after entry, "
+              f"first exit {int(w[:,2].min())-k0} ns, last exit {int(w[:,2].max())-k0} ns")
+    print(name, "items of CTA 0: start | prologue | tiles | drain  (cycles)")
+    for i in range(8):
+        if int(it[i, 0]) == 0: break
+        print(f"  {i}: {int(it[i,0])-t0:7d} | {int(it[i,1]-it[i,0]):6d} | {int(it[i,2]-it[i,1]):6d} | {int(it[i,3]-it[i,2]):6d}")
 timeline(fwd, "fwd")
 timeline(bwd, "bwd")
+items(bwd, "bwd")
+items(fwd, "fwd")
