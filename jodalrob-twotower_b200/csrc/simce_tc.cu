@@ -46,9 +46,8 @@ struct TcParams {
   int64_t Bx, By;
   int F;                 // 64 or 128
   int n_col_tiles;       // ceil(By / 128)
-  int tiles_per_chunk;
-  int n_chunks;
-  int n_items;           // row blocks * chunks
+  long long total_tiles; // row blocks * column tiles: CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G) of the row-block-
+                         // major tile sequence, i.e. one or two long items instead of many short ones
   float c1, c0;          // e = exp2(s_raw * c1 + c0):  c1 = inv_temp*log2e, c0 = -inv_temp*log2e
   float inv_temp;
   int64_t diag_offset;
@@ -68,7 +67,7 @@ struct TcParams {
   const __nv_bfloat16* Ys;  // [By][F] = bf16(gscale * inv_y[j] * Y[j,:]) (column scales folded into the second MMA operand)
   const float* inv_x;    // [Bx] (unscaled)
   float gscale;
-  float* dx_part;        // [n_chunks][Bx][F]
+  float* dx_part;        // [max parts][Bx][F]: part = owning CTA - first CTA of the row block
 };
 
 struct TcSmem {  // carved from dynamic smem after the 1024-aligned tiles
@@ -161,6 +160,19 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], float c1, 
   tmem_st8(p_taddr, w);
 }
 
+// ---- work partition: the T = row blocks x column tiles tiles, row-block-major, cut into G equal contiguous ranges ----
+__host__ __device__ __forceinline__ long long tc_range_begin(int c, long long T, int G) { return (long long)c * T / G; }
+__host__ __device__ __forceinline__ int tc_cta_of_tile(long long g, long long T, int G) {
+  int c = (int)(g * G / T);
+  while (c + 1 < G && tc_range_begin(c + 1, T, G) <= g) ++c;
+  while (c > 0 && tc_range_begin(c, T, G) > g) --c;
+  return c;
+}
+// the pieces of row block rb are numbered by owning CTA, starting at the CTA that owns the block's first tile
+__host__ __device__ __forceinline__ int tc_parts_of_row_block(int rb, int n_ct, long long T, int G) {
+  return tc_cta_of_tile((long long)rb * n_ct + n_ct - 1, T, G) - tc_cta_of_tile((long long)rb * n_ct, T, G) + 1;
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
@@ -224,6 +236,8 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const uint32_t tmem_d = tmem + NSB * TCN;  // backward accumulator(s): n_dbuf x 2F columns behind the S buffers
   const int n_dbuf = p.n_dbuf;
   const uint32_t tmem_p = tmem_d + n_dbuf * 2 * p.F;  // two E buffers of 64 columns
+  const long long g_begin = tc_range_begin((int)blockIdx.x, p.total_tiles, (int)gridDim.x);
+  const long long g_end = tc_range_begin((int)blockIdx.x + 1, p.total_tiles, (int)gridDim.x);
 
   if (warp == TC_LOAD_WARP) {
     // =========================== operand loader ===========================
@@ -231,10 +245,10 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     uint32_t x_iter = 0, y_iter = 0;
     int st = 0;           // Y ring cursor kept incrementally: no runtime division on the per-tile path
     uint32_t ph = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++x_iter) {
-      const int rb = item / p.n_chunks, ch = item - rb * p.n_chunks;
-      const int t0 = ch * p.tiles_per_chunk;
-      const int t1 = min(t0 + p.tiles_per_chunk, p.n_col_tiles);
+    for (long long g = g_begin; g < g_end; ++x_iter) {
+      const int rb = (int)(g / p.n_col_tiles), t0 = (int)(g - (long long)rb * p.n_col_tiles);
+      const int t1 = t0 + (int)min((long long)(p.n_col_tiles - t0), g_end - g);
+      g += t1 - t0;
       const int xb = p.n_xbuf == 2 ? (x_iter & 1) : 0;
       unsigned char* sXb = sX + xb * tile_bytes;
       mbar_wait(&sb->x_empty[xb], ((p.n_xbuf == 2 ? (x_iter >> 1) : x_iter) & 1) ^ 1);
@@ -283,10 +297,10 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     uint32_t x_iter = 0, s_iter = 0;
     int y_st = 0, s_buf = 0;  // ring cursors kept incrementally: this warp's per-tile latency chain paces the CTA
     uint32_t y_ph = 0, s_ph = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++x_iter) {
-      const int ch = item % p.n_chunks;
-      const int t0 = ch * p.tiles_per_chunk;
-      const int nt = min(t0 + p.tiles_per_chunk, p.n_col_tiles) - t0;
+    for (long long g = g_begin; g < g_end; ++x_iter) {
+      const int t0 = (int)(g % p.n_col_tiles);
+      const int nt = (int)min((long long)(p.n_col_tiles - t0), g_end - g);
+      g += nt;
       const int xb = p.n_xbuf == 2 ? (x_iter & 1) : 0;
       const uint64_t dXb = dX0 + (uint64_t)(xb * tile16);
       mbar_wait(&sb->x_full[xb], (p.n_xbuf == 2 ? (x_iter >> 1) : x_iter) & 1);
@@ -333,10 +347,10 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       uint32_t p_iter = 0;
       int y_st = 0, d_buf = 0;
       uint32_t y_ph = 0, d_ph = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int ch = item % p.n_chunks;
-        const int t0 = ch * p.tiles_per_chunk;
-        const int nt = min(t0 + p.tiles_per_chunk, p.n_col_tiles) - t0;
+      for (long long g = g_begin; g < g_end;) {
+        const int t0 = (int)(g % p.n_col_tiles);
+        const int nt = (int)min((long long)(p.n_col_tiles - t0), g_end - g);
+        g += nt;
         const uint32_t d_tmem = tmem_d + d_buf * 2 * p.F;
         for (int t = 0; t < nt; ++t, ++p_iter) {
           const int pb = p_iter & 1;
@@ -423,12 +437,14 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (lane == 0) mbar_arrive(&sb->d_empty[db]);
     };
     int it_iter = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_iter) {
+    for (long long g = g_begin; g < g_end; ++it_iter) {
       const bool istamp = p.dbg_ts && blockIdx.x == 0 && threadIdx.x == 0 && it_iter < 64;
       if (istamp) p.dbg_ts[1 * 2048 + 1024 + it_iter * 4 + 0] = clock64();
-      const int rb = item / p.n_chunks, ch = item - rb * p.n_chunks;
-      const int t0 = ch * p.tiles_per_chunk;
-      const int t1 = min(t0 + p.tiles_per_chunk, p.n_col_tiles);
+      const int rb = (int)(g / p.n_col_tiles), t0 = (int)(g - (long long)rb * p.n_col_tiles);
+      const int t1 = t0 + (int)min((long long)(p.n_col_tiles - t0), g_end - g);
+      g += t1 - t0;
+      const bool last_item = g >= g_end;
+      const int ch = (int)blockIdx.x - tc_cta_of_tile((long long)rb * p.n_col_tiles, p.total_tiles, (int)gridDim.x);  // part index
       const int64_t row = (int64_t)rb * TCM + r_in_blk;
       const bool row_ok = row < p.Bx;
       // this row's positive column, and the (at most two) column tiles the block's diagonal crosses
@@ -524,7 +540,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       } else {
         float* out = p.dx_part + ((int64_t)ch * p.Bx + row) * p.F;
         if (istamp) p.dbg_ts[1 * 2048 + 1024 + it_iter * 4 + 2] = clock64();
-        if (item + (int)gridDim.x < p.n_items) {  // deferred: read out after the next item's first tile (no wait for MMA2 then)
+        if (!last_item) {  // deferred: read out after the next item's first tile (no wait for MMA2 then)
           pend = true;
           pend_out = out;
           pend_buf = d_buf;
@@ -592,7 +608,7 @@ tc_ysum_partial_kernel(const __nv_bfloat16* __restrict__ Y, int64_t By, int F, f
 constexpr int RR_LANES = 8;
 __global__ void __launch_bounds__(32 * RR_LANES)
 tc_rows_reduce_kernel(const float* __restrict__ row_e, const float* __restrict__ row_max, const int32_t* __restrict__ row_arg,
-                      int64_t Bx, int n_parts, const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Y, int64_t By,
+                      int64_t Bx, int n_ct, long long T, int G, const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Y, int64_t By,
                       int F, float inv_temp, const float* __restrict__ ysum_part, float* __restrict__ out_e,
                       float* __restrict__ out_s, int32_t* __restrict__ out_arg) {
   __shared__ float sh_e[RR_LANES][32], sh_m[RR_LANES][32], sh_d[2 * RR_LANES][32], sh_y[128];
@@ -610,6 +626,7 @@ tc_rows_reduce_kernel(const float* __restrict__ row_e, const float* __restrict__
   float e = 0.f, mx = -FLT_MAX;
   int32_t arg = 0x7fffffff;
   if (ok) {
+    const int n_parts = 4 * tc_parts_of_row_block((int)(m / TCM), n_ct, T, G);  // 4 column slices per piece of the row block
 #pragma unroll 4
     for (int c = q; c < n_parts; c += RR_LANES) {
       const int64_t o = (int64_t)c * Bx + m;
@@ -735,13 +752,14 @@ __global__ void tc_ysum_final_kernel(const float* __restrict__ part, int F, floa
 
 // dX = sum of the chunk partials (fixed order) - t_off * sum_j Y_j - (t_diag - t_off) * Y[diag_offset + row]
 __global__ void __launch_bounds__(256)
-tc_dx_reduce_kernel(const float* __restrict__ part, int64_t n, int n_chunks, int F, const __nv_bfloat16* __restrict__ Y,
+tc_dx_reduce_kernel(const float* __restrict__ part, int64_t n, int n_ct, long long T, int G, int F, const __nv_bfloat16* __restrict__ Y,
                     int64_t diag_offset, float t_off2, float t_dd2, const float* __restrict__ ysum, float* __restrict__ dX) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
-  float4 a = *reinterpret_cast<const float4*>(part + i);
-  for (int c = 1; c < n_chunks; ++c) f4_add(a, *reinterpret_cast<const float4*>(part + (int64_t)c * n + i));
   const int64_t row = i / F;
+  const int n_parts = tc_parts_of_row_block((int)(row / TCM), n_ct, T, G);
+  float4 a = *reinterpret_cast<const float4*>(part + i);
+  for (int c = 1; c < n_parts; ++c) f4_add(a, *reinterpret_cast<const float4*>(part + (int64_t)c * n + i));
   const int col = (int)(i - row * F);
   const uint2 yv = *reinterpret_cast<const uint2*>(Y + (diag_offset + row) * F + col);
   const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.x));
@@ -766,34 +784,25 @@ static bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int F) {
 }
 
 struct TcPlan {
-  int n_row_blocks, n_col_tiles, tiles_per_chunk, n_chunks, n_items, grid;
+  int n_row_blocks, n_col_tiles, grid, max_parts;
+  long long total_tiles;
 };
 
-// split the column tiles so that (row blocks x chunks) fills whole waves of the machine, >= 4 tiles per chunk if possible
+// One contiguous tile range per CTA (see tc_range_begin): a CTA works through at most a few long items, a row block is split over
+// at most max_parts CTAs (so that many partial results per row), and every CTA gets floor or ceil of T/G tiles.
 static TcPlan make_plan(int64_t Bx, int64_t By) {
   TcPlan pl;
   pl.n_row_blocks = (int)((Bx + TCM - 1) / TCM);
   pl.n_col_tiles = (int)((By + TCN - 1) / TCN);
+  pl.total_tiles = (long long)pl.n_row_blocks * pl.n_col_tiles;
   const int sms = sm_count();
-  int best_s = 1;
-  double best_eff = -1.0;
-  const int max_s = pl.n_col_tiles < 64 ? pl.n_col_tiles : 64;
-  for (int s = 1; s <= max_s; ++s) {
-    const int tpc = (pl.n_col_tiles + s - 1) / s;
-    if (tpc < 4 && s > 1) break;
-    const int chunks = (pl.n_col_tiles + tpc - 1) / tpc;
-    const long items = (long)pl.n_row_blocks * chunks;
-    const long waves = (items + sms - 1) / sms;
-    const double eff = (double)items / (double)(waves * sms) - 0.002 * s;  // mild preference for fewer partials
-    if (eff > best_eff) {
-      best_eff = eff;
-      best_s = s;
-    }
+  pl.grid = pl.total_tiles < sms ? (int)pl.total_tiles : sms;
+  int mp = 1;
+  for (int rb = 0; rb < pl.n_row_blocks; ++rb) {
+    const int n = tc_parts_of_row_block(rb, pl.n_col_tiles, pl.total_tiles, pl.grid);
+    if (n > mp) mp = n;
   }
-  pl.tiles_per_chunk = (pl.n_col_tiles + best_s - 1) / best_s;
-  pl.n_chunks = (pl.n_col_tiles + pl.tiles_per_chunk - 1) / pl.tiles_per_chunk;
-  pl.n_items = pl.n_row_blocks * pl.n_chunks;
-  pl.grid = pl.n_items < sms ? pl.n_items : sms;
+  pl.max_parts = mp;
   return pl;
 }
 
@@ -813,7 +822,7 @@ static size_t tc_smem_bytes(int F, bool bwd) {
 int64_t simce_tc_workspace_bytes(int64_t Bx, int64_t By, int F) {
   const int64_t B = Bx > By ? Bx : By;
   TcPlan a = make_plan(Bx, By), b = make_plan(By, Bx);
-  const int64_t chunks = a.n_chunks > b.n_chunks ? a.n_chunks : b.n_chunks;
+  const int64_t chunks = a.max_parts > b.max_parts ? a.max_parts : b.max_parts;
   const int64_t fwd = 3 * ((4 * chunks * B * 4 + 255) / 256 * 256) + YS_BLOCKS * 128 * 4 + 256;
   const int64_t bwd = chunks * B * F * 4 + 256 + (B * F * 2 + 256) + YS_BLOCKS * 128 * 4 + 128 * 4 + 256;
   return (fwd > bwd ? fwd : bwd) + 1024;
@@ -831,11 +840,11 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   p.X = (const __nv_bfloat16*)X;
   p.Y = (const __nv_bfloat16*)Y;
   p.Bx = Bx; p.By = By; p.F = F;
-  p.n_col_tiles = pl.n_col_tiles; p.tiles_per_chunk = pl.tiles_per_chunk; p.n_chunks = pl.n_chunks; p.n_items = pl.n_items;
+  p.n_col_tiles = pl.n_col_tiles; p.total_tiles = pl.total_tiles;
   const float log2e = 1.4426950408889634f;
   p.c1 = inv_temp * log2e; p.c0 = -inv_temp * log2e; p.inv_temp = inv_temp;
   p.diag_offset = diag_offset;
-  const int64_t stride = (4 * pl.n_chunks * Bx * 4 + 255) / 256 * 256;
+  const int64_t stride = (4 * pl.max_parts * Bx * 4 + 255) / 256 * 256;
   char* w = (char*)workspace;
   p.row_e = (float*)w; p.row_max = (float*)(w + stride); p.row_arg = (int32_t*)(w + 2 * stride);
   float* ysum_part = (float*)(w + 3 * stride);
@@ -850,7 +859,7 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   simce_tc_kernel<false><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, my, p);
   if (row_sum_s) tc_ysum_partial_kernel<<<YS_BLOCKS, 512, 0, s>>>(p.Y, By, F, ysum_part);
-  tc_rows_reduce_kernel<<<ceil_div(Bx, 32), 32 * RR_LANES, 0, s>>>(p.row_e, p.row_max, p.row_arg, Bx, 4 * pl.n_chunks, p.X, p.Y, By, F,
+  tc_rows_reduce_kernel<<<ceil_div(Bx, 32), 32 * RR_LANES, 0, s>>>(p.row_e, p.row_max, p.row_arg, Bx, pl.n_col_tiles, pl.total_tiles, pl.grid, p.X, p.Y, By, F,
                                                                    inv_temp, ysum_part, row_sumexp, row_sum_s,
                                                                    want_metrics ? row_argmax : nullptr);
   TT_LAUNCH_CHECK("simce_tc_rows");
@@ -865,7 +874,7 @@ int simce_tc_bwd(const void* X, const void* Y, int64_t Bx, int64_t By, int F, fl
   p.X = (const __nv_bfloat16*)X;
   p.Y = (const __nv_bfloat16*)Y;
   p.Bx = Bx; p.By = By; p.F = F;
-  p.n_col_tiles = pl.n_col_tiles; p.tiles_per_chunk = pl.tiles_per_chunk; p.n_chunks = pl.n_chunks; p.n_items = pl.n_items;
+  p.n_col_tiles = pl.n_col_tiles; p.total_tiles = pl.total_tiles;
   const float log2e = 1.4426950408889634f;
   p.c1 = inv_temp * log2e; p.c0 = -inv_temp * log2e; p.inv_temp = inv_temp;
   p.diag_offset = diag_offset;
@@ -874,7 +883,7 @@ int simce_tc_bwd(const void* X, const void* Y, int64_t Bx, int64_t By, int F, fl
   // workspace: [chunk partials of dX][Ys][column-sum partials][column sums]
   char* w = (char*)workspace;
   p.dx_part = (float*)w;
-  w += ((int64_t)pl.n_chunks * Bx * F * 4 + 255) / 256 * 256;
+  w += ((int64_t)pl.max_parts * Bx * F * 4 + 255) / 256 * 256;
   __nv_bfloat16* Ys = (__nv_bfloat16*)w;
   w += (By * F * 2 + 255) / 256 * 256;
   float* ysum_part = (float*)w;
@@ -896,7 +905,7 @@ int simce_tc_bwd(const void* X, const void* Y, int64_t Bx, int64_t By, int F, fl
   const size_t smem = tc_smem_bytes(F, true);
   TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   simce_tc_kernel<true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, mys, p);
-  tc_dx_reduce_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(p.dx_part, Bx * F, pl.n_chunks, F, p.Y, diag_offset, t_off2,
+  tc_dx_reduce_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(p.dx_part, Bx * F, pl.n_col_tiles, pl.total_tiles, pl.grid, F, p.Y, diag_offset, t_off2,
                                                                   t_diag2 - t_off2, smooth ? ysum : nullptr, dX);
   TT_LAUNCH_CHECK("simce_tc_bwd");
   return TT_OK;
