@@ -148,8 +148,14 @@ class TwoTowerEngine:
         # inside a CUDA graph capture this becomes two parallel branches)
         self.two_streams = True
         self.sharded_lookup = False  # DistributedEngine: the lookup is one exchange for both towers
-        self._side = torch.cuda.Stream(self.device)
-        self._sort_stream = torch.cuda.Stream(self.device)
+        # Streams on the critical path (the towers' data-gradient chains, the table update) get high priority, so that their
+        # CTAs are placed before those of the weight-gradient helper streams whenever SMs free up
+        import os as _os
+        hi = 0 if _os.environ.get("TT_NO_PRIO") else -1
+        self._side = torch.cuda.Stream(self.device, priority=hi)
+        self._hi0 = torch.cuda.Stream(self.device, priority=hi)
+        self._sort_stream = torch.cuda.Stream(self.device)  # the sort has the whole forward + loss to hide under: normal priority
+        self._adam_stream = torch.cuda.Stream(self.device, priority=hi)
         # two helper streams per tower: the weight gradients of a tower's layers are independent of each other
         self._wg_streams = [[torch.cuda.Stream(self.device) for _ in range(2)] for _ in range(2)]
         self.launches = 0  # kernels launched through the C ABI (bench.py's gpu_launches)
@@ -536,7 +542,10 @@ class TwoTowerEngine:
         self._call("tt_simce_backward", ptr(ws.e[1]), ptr(ws.e[0]), B, B, F, self.emb_tt, inv_t, 0, ptr(ws.inv_col), ptr(ws.inv_row),
                    gscale, cfg.label_smoothing, B, ptr(ws.de[1]), ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=2)
 
-    def tower_backward(self, t: int, ws: _Ws):
+    def tower_backward(self, t: int, ws: _Ws, after_dc=None):
+        """Backward of one tower. `after_dc`, if given, is called on this tower's stream as soon as the gradient of the concat
+        buffer exists (the fused step hangs the large-table update there: same stream, no cross-stream hand-off on the
+        critical path); the rest of this tower (small tables, weight gradients) then goes to the helper streams."""
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
         name, keys, _, dense_dim = cfg.tower(t)
         self.profile_tag = name + ".bwd"
@@ -580,6 +589,21 @@ class TwoTowerEngine:
             self._lin_dgrad(ws.dh[t][bi], h, pre + f"mlp.{idx}.weight", dxin, win, B, h, win)
             wgrads.append((ws.dh[t][bi], h, xin, win, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", h, win))
         self._mark_dc_ready(t, ws)
+        cur = torch.cuda.current_stream(self.device)
+        fan = self.two_streams and self.profile is None
+        inline = after_dc is not None and fan
+        joins, used = [], set()
+        if after_dc is not None:
+            after_dc()
+        if inline:  # this stream is busy with the table update: small tables on a helper
+            st = self._wg_streams[t][0]
+            st.wait_event(ws.dc_ready[t])
+            used.add(0)
+            with torch.cuda.stream(st):
+                self.small_tables_backward(ws, (t,))
+        else:
+            self.small_tables_backward(ws, (t,))  # needs dc only; the dense Adam at the very end of the step waits for it
+        self.profile_tag = name + ".bwd"
         if self.act != TT_F32:
             dense_in = ws.x16[t]
         else:
@@ -589,21 +613,20 @@ class TwoTowerEngine:
         wgrads.append((ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", H0, dense_dim))
         # every dY exists now; the layers' weight gradients are independent: fan them out over the tower's stream and its two
         # helper streams (own scratch each), join at the end
-        cur = torch.cuda.current_stream(self.device)
-        fan = self.two_streams and self.profile is None
-        joins = []
         for i, (dy_, ldy_, x_, ldx_, wn_, bn_, n_, k_) in enumerate(wgrads):
-            lane = i % 3 if fan else 0
+            lane = (1 + i % 2 if inline else i % 3) if fan else 0
             if lane == 0:
                 self._lin_wgrad(dy_, ldy_, x_, ldx_, wn_, bn_, B, n_, k_, ws.wg_ws[t][0])
             else:
                 st = self._wg_streams[t][lane - 1]
                 st.wait_event(ws.dc_ready[t])
+                used.add(lane - 1)
                 with torch.cuda.stream(st):
                     self._lin_wgrad(dy_, ldy_, x_, ldx_, wn_, bn_, B, n_, k_, ws.wg_ws[t][lane])
-                    ev = torch.cuda.Event()
-                    ev.record(st)
-                joins.append(ev)
+        for j in sorted(used):
+            ev = torch.cuda.Event()
+            ev.record(self._wg_streams[t][j])
+            joins.append(ev)
         for ev in joins:
             cur.wait_event(ev)
 
@@ -667,14 +690,11 @@ class TwoTowerEngine:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self.tower_backward(1, ws)
-                self.small_tables_backward(ws, (1,))
             self.tower_backward(0, ws)
-            self.small_tables_backward(ws, (0,))
             main.wait_stream(self._side)
         else:
             self.tower_backward(0, ws)
             self.tower_backward(1, ws)
-            self.small_tables_backward(ws)
 
     # ------------------------------------------------------------------ optimizer
     def hyper_advance(self, lr: float, warmup_steps: int, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
@@ -697,19 +717,20 @@ class TwoTowerEngine:
             # both concat-buffer gradients exist and overlaps the first-layer weight gradients and the small-table reductions.
             self.loss_backward(ws)
             self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                self.tower_backward(1, ws)
-                self.small_tables_backward(ws, (1,))
-            self.tower_backward(0, ws)
-            self.small_tables_backward(ws, (0,))
-            with torch.cuda.stream(self._sort_stream):
-                self._sort_stream.wait_event(ws.dc_ready[0])
-                self._sort_stream.wait_event(ws.dc_ready[1])
+            self._hi0.wait_stream(main)
+            def table_update():  # on `_side`, right behind the company tower's last data gradient
+                self._side.wait_event(ws.dc_ready[0])
+                self._side.wait_stream(self._sort_stream)
                 self.embedding_backward(ws, apply_adam=True, want_dense_grad=False, sorted_already=True)
+
+            with torch.cuda.stream(self._hi0):
+                self.tower_backward(0, ws)
+            with torch.cuda.stream(self._side):
+                self.tower_backward(1, ws, after_dc=table_update)
             main.wait_stream(self._side)
+            main.wait_stream(self._hi0)
             self.reduce_dense_grads()
             self.dense_adam()
-            main.wait_stream(self._sort_stream)
         else:
             self.backward(ws)
             self.reduce_dense_grads()
