@@ -106,6 +106,14 @@ __device__ __forceinline__ void manual_tile_load(unsigned char* dst, const __nv_
 }
 
 // ---- epilogue helpers -------------------------------------------------------------------------------
+// Experiment knob: every N-th logit takes exp2 on the FMA pipe (ex2_poly) instead of the MUFU pipe. Measured at B = 8192: N = 4
+// and N = 8 are both SLOWER (forward 26.3 -> 28.2 / 27.2 us): with four warps per scheduler the epilogue is bound by instruction
+// issue and dependency latency before it is bound by the 16/clk/SM MUFU rate, so trading one MUFU for eight FMA-pipe
+// instructions loses. Left at 0 (off).
+constexpr int TC_POLY_EVERY = 0;
+__device__ __forceinline__ float tc_exp2(float x, int j) {
+  return (TC_POLY_EVERY > 0 && (j % (TC_POLY_EVERY > 0 ? TC_POLY_EVERY : 1)) == TC_POLY_EVERY - 1) ? ex2_poly(x) : ex2f(x);
+}
 constexpr int TC_CW = 16;  // columns per TMEM load / epilogue chunk: half of a warp's 32-column slice
 
 // The epilogue is issue-bound, not just MUFU-bound (four warps per scheduler): every instruction per logit counts.
@@ -123,7 +131,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
     if (GENERIC) {
       const int col = cbase + j;
       if (col < By) {
-        acc[j & 3] += ex2f(fmaf(raw, c1, c0));
+        acc[j & 3] += tc_exp2(fmaf(raw, c1, c0), j);
         m4[j & 3] = fmaxf(m4[j & 3], raw);
         if (col == dcol) {
           dval = raw;
@@ -131,7 +139,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
         }
       }
     } else {
-      acc[j & 3] += ex2f(fmaf(raw, c1, c0));
+      acc[j & 3] += tc_exp2(fmaf(raw, c1, c0), j);
       m4[j & 3] = fmaxf(m4[j & 3], raw);
     }
   }
@@ -152,8 +160,8 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], float c1, 
   uint32_t w[TC_CW / 2];
 #pragma unroll
   for (int u = 0; u < TC_CW / 2; ++u) {
-    const float e0 = ex2f(fmaf(__uint_as_float(r[2 * u]), c1, c0));
-    const float e1 = ex2f(fmaf(__uint_as_float(r[2 * u + 1]), c1, c0));
+    const float e0 = tc_exp2(fmaf(__uint_as_float(r[2 * u]), c1, c0), 2 * u);
+    const float e1 = tc_exp2(fmaf(__uint_as_float(r[2 * u + 1]), c1, c0), 2 * u + 1);
     __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);  // low half = even column
     w[u] = *reinterpret_cast<uint32_t*>(&t);
   }
