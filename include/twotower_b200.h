@@ -172,6 +172,15 @@ int tt_ebc_small_backward(const int64_t* values, int32_t B, int32_t K, int32_t l
  *   tt_ebc_push_rows       fused lookup + row all-to-all: for every owned id, gather the row and store it into the
  *                          requester's concat buffer dst_table[rank*2 + tower] (peer-mapped over NVLink) at
  *                          [b, col0 + k*E].  The matching gradient return is tt_ebc_backward_adam with grad_table. */
+/* One-shot all-reduce (sum) of a small f64 vector over NVLink peer memory, in place, bit-identical on every rank (fixed rank
+ * order). For the latency-bound reductions of the sharded step (SyncBN sums, loss partials, barriers) in place of a collective
+ * library call. Every rank owns a mailbox of tt_peer_mailbox_bytes(world, n_max) bytes per call site, zero-initialised once
+ * and peer-mapped; d_mailboxes is the device array of the world mailbox pointers (same order on every rank), d_epoch a
+ * zero-initialised device counter per call site (graph-replay safe). One process per GPU only: kernels of different ranks wait
+ * for each other. A peer that never arrives traps after ~2 s. */
+int64_t tt_peer_mailbox_bytes(int32_t world, int32_t n_max);
+int tt_peer_allreduce_f64(double* data, int32_t n, int32_t rank, int32_t world, const void* const* d_mailboxes, int32_t n_max,
+                          int64_t* d_epoch, tt_stream_t stream);
 int tt_ebc_clamp_ids(const int64_t* values, const int32_t* d_vocab, int32_t B, int32_t K, int32_t layout, int32_t* ids_out,
                      tt_stream_t stream);
 int tt_ebc_clamp_ids_subset(const int64_t* values, const int32_t* d_vocab, const int32_t* d_keys, int32_t B, int32_t K, int32_t KL,

@@ -58,6 +58,7 @@ class ShardPlan:
 # ------------------------------------------------------------------------------------------------ communicators
 class NcclComm:
     """torch.distributed backend (NCCL). Peer-mapped buffers come from torch symmetric memory."""
+    peer_kernels = True  # one process per GPU: kernels of different ranks may wait for each other (tt_peer_allreduce_f64)
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -103,6 +104,8 @@ class ThreadWorld:
 
 
 class ThreadComm:
+    peer_kernels = False  # all "ranks" share one GPU: collectives stay host-mediated, no kernel ever waits on another
+
     def __init__(self, tw: ThreadWorld, rank: int):
         self.tw, self.world, self.rank = tw, tw.world, rank
 
@@ -152,6 +155,7 @@ class ThreadComm:
 class SingleComm:
     """world == 1: the sharded pipeline with itself as the only peer (exercises select/push/pull on one GPU)."""
     world, rank = 1, 0
+    peer_kernels = False
 
     def all_gather(self, out, inp):
         out.view(-1).copy_(inp.view(-1))
@@ -205,10 +209,37 @@ class DistributedEngine(TwoTowerEngine):
         self.rng_stream_base = 64 * self.rank
         # the company tower runs on the side stream with its own communicator for the SyncBN all-reduces
         self.comm_t = [comm, comm.clone()]
+        self._setup_peer_sites()
         self.two_streams = True
         self.sharded_lookup = True
         if lv:
             assert self.total_rows == self.plan.local_rows, (self.total_rows, self.plan.local_rows)
+
+    # ---- tiny reductions over NVLink peer memory instead of collective-library calls (csrc/peer.cu)
+    PEER_SITES = ("tower0", "tower1", "partial", "barrier")
+
+    def _setup_peer_sites(self):
+        self.peer_sites = None
+        if not getattr(self.comm, "peer_kernels", False) or self.world == 1:
+            return
+        dev = self.device
+        self.peer_n_max = max(2 * max(self.cfg.hidden[1:] + [1]), 128)
+        mb = self.lib.query("tt_peer_mailbox_bytes", self.world, self.peer_n_max)
+        mb = (mb + 255) // 256 * 256
+        buf, peers = self.comm.peer_buffer(mb * len(self.PEER_SITES), dev)
+        buf.zero_()
+        torch.cuda.synchronize(dev)
+        self.comm.dist.barrier(group=self.comm.group, device_ids=[dev.index if dev.index is not None else torch.cuda.current_device()])  # every mailbox is zero before anyone writes
+        self._peer_buf = buf
+        self.peer_sites = {name: torch.tensor([p + i * mb for p in peers], dtype=torch.int64, device=dev)
+                           for i, name in enumerate(self.PEER_SITES)}
+        self.peer_epochs = torch.zeros(len(self.PEER_SITES), dtype=torch.int64, device=dev)
+        self._peer_dummy = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def _peer_allreduce(self, buf: torch.Tensor, n: int, site: str):
+        i = self.PEER_SITES.index(site)
+        self._call("tt_peer_allreduce_f64", ptr(buf), n, self.rank, self.world, ptr(self.peer_sites[site]), self.peer_n_max,
+                   self.peer_epochs.data_ptr() + 8 * i, self._stream())
 
     def _alloc_rows(self, t: int, k: int, vocab: int, small: bool) -> int:
         return vocab if small else -(-vocab // self.world)
@@ -289,10 +320,17 @@ class DistributedEngine(TwoTowerEngine):
         self._call("tt_ebc_push_rows", ptr(self.arena), E, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), n_l * self.world,
                    ptr(ws.c_table), n_l, n0, max(KL0, 1), KL1, H0 + K0 * E, H0 + K1 * E, H0, H0, ptr(self.colmap[0]),
                    ptr(self.colmap[1]), self.act, s)
-        self.comm.barrier(self.device)  # every owner has finished writing into my concat buffers
+        # every owner has finished writing into my concat buffers
+        if self.peer_sites is not None:
+            self._peer_allreduce(self._peer_dummy, 1, "barrier")
+        else:
+            self.comm.barrier(self.device)
 
     def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int, tower: int = 0) -> int:
-        self.comm_t[tower].all_reduce(sums[:n])
+        if self.peer_sites is not None and n <= self.peer_n_max:
+            self._peer_allreduce(sums, n, "tower%d" % tower)
+        else:
+            self.comm_t[tower].all_reduce(sums[:n])
         return local_count * self.world
 
     def fused_step(self, notice_dense, notice_values, company_dense, company_values, lr=1e-3, warmup_steps=0,
@@ -329,7 +367,10 @@ class DistributedEngine(TwoTowerEngine):
         self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), css,
                    ptr(ws.diag), ptr(ws.row_argmax), B, Bg, off, Bg, inv_t, cfg.label_smoothing, ptr(ws.inv_row),
                    ptr(ws.inv_col), ptr(ws.partial), s)
-        self.comm.all_reduce(ws.partial)
+        if self.peer_sites is not None:
+            self._peer_allreduce(ws.partial, ws.partial.numel(), "partial")
+        else:
+            self.comm.all_reduce(ws.partial)
         self._call("tt_simce_scalars", ptr(ws.partial), Bg, ptr(ws.out5), s)
         self.comm.all_gather(ws.inv_row_all, ws.inv_row)
         return ws.out5
