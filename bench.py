@@ -165,6 +165,69 @@ def cpu_baseline(schema, B, budget_s=25.0):
             "vectorized_decode_value": out["vectorized"][0]}
 
 
+
+# ------------------------------------------------------------------------------------------------ large-table section
+def tables_section(dev, pk, quick=False):
+    """BASELINE.json's second metric ("lookup HBM GB/s vs peak") on the shapes where the embedding kernels are HBM-bound:
+    one GPU's row-wise shard of config 5 (500 M rows x E=64 over 8 GPUs = 62.5 M rows, 16 GB fp32 + 32 GB Adam state; multi-hot
+    bags, pooling factor 20) and of config 3 (38 tables x 10 M rows x E=32 over 8 GPUs, one id per bag). Uniform ids (no L2 reuse:
+    the worst case; tables >> 126 MB L2), B = 8192 samples per step, 38 keys. Algorithmic bytes: SURVEY.md §8(d)."""
+    from jodalrob_twotower_b200.tables import PooledTables
+    out = {}
+    K, B = 38, 8192
+    cases = [("config5_shard_E64_L20", 62_500_000 // K, 64, 20), ("config3_shard_E32_L1", 1_250_000, 32, 1)]
+    for name, rows_per, E, L in cases:
+        res = {}
+        for mode in ("sparse", "dense_exact"):
+            if mode == "dense_exact" and quick:
+                continue
+            torch.cuda.empty_cache()
+            tab = PooledTables([rows_per] * K, E, dev, optimizer_mode=mode, seed=1, init_std=0.0 if mode == "dense_exact" else 1.0)
+            g = torch.Generator(device=dev).manual_seed(7)
+            n = B * K * L
+            key = (torch.arange(n, device=dev) // L) % K
+            sets = []
+            for _ in range(3):
+                u = torch.rand(n, generator=g, device=dev)
+                sets.append(((u * rows_per).long().clamp_(max=rows_per - 1), torch.randn(B, K * E, generator=g, device=dev)))
+            offs = torch.arange(B * K + 1, dtype=torch.int64, device=dev) * L if L > 1 else None
+            outbuf = torch.empty(B, K * E, dtype=torch.float32, device=dev)
+            st = torch.cuda.current_stream(dev)
+
+            def timed(fn, reps):
+                evs = []
+                for i in range(reps + 2):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(st); fn(i); b.record(st)
+                    evs.append((a, b))
+                torch.cuda.synchronize(dev)
+                t = sorted(a.elapsed_time(b) for a, b in evs[2:])
+                return t[len(t) // 2] * 1e-3
+
+            reps = 3 if mode == "dense_exact" else 10
+            if mode == "sparse":
+                t_f = timed(lambda i: tab.forward(sets[i % 3][0], B, offs, out=outbuf), reps)
+                fb = tab.forward_bytes(B, n, 4, jagged=L > 1)
+                res["lookup"] = {"ms": t_f * 1e3, "bytes": fb, "GBps": fb / t_f / 1e9, "frac_hbm": fb / t_f / 1e9 / pk["hbm_gbs"]}
+                t_s = timed(lambda i: tab.sort(), reps)
+                res["sort_dedup"] = {"ms": t_s * 1e3, "pairs": n, "Mpairs_per_s": n / t_s / 1e6}
+            tab.forward(sets[0][0], B, offs, out=outbuf)
+            tab.sort()
+            uniq = int(torch.unique(tab.rows[:n]).numel())
+
+            def upd(i):
+                tab.hyper_advance()
+                tab.backward_adam(sets[0][1])
+            t_u = timed(upd, reps)
+            ub = tab.update_bytes(B, n, uniq, 4)
+            res["update_" + mode] = {"ms": t_u * 1e3, "bytes": ub, "unique_rows": uniq, "GBps": ub / t_u / 1e9,
+                                     "frac_hbm": ub / t_u / 1e9 / pk["hbm_gbs"]}
+            del tab, sets
+        res["shape"] = {"tables": K, "rows_per_table": rows_per, "emb_dim": E, "ids_per_bag": L, "batch": B, "ids": "uniform"}
+        out[name] = res
+    torch.cuda.empty_cache()
+    return out
+
 # ------------------------------------------------------------------------------------------------ our arm
 def algorithmic(tag: str, B: int, schema) -> dict:
     """Algorithmic bytes / flops of one C-ABI call."""
@@ -366,7 +429,8 @@ def run_ours(args):
         if "flops" in a:
             row["TFLOPs"] = round(a["flops"] / per_call / 1e12, 2)
         table.append(row)
-    top = table[0] if table else None
+    # dominant call among those with an algorithmic figure (eager per-call times of a multi-rank run include peer waits)
+    top = next((r for r in table if algorithmic(r["call"], B, schema)), table[0] if table else None)
     roofline = None
     if top is not None:
         a = algorithmic(top["call"], B, schema)
@@ -394,6 +458,11 @@ def run_ours(args):
         else:
             roofline = {"kernel": top["call"], "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None,
                         "traffic": None, "peak_source": pk["source"]}
+    tables = None
+    if world == 1 and not args.no_tables:
+        del gstep, packed_res, resident
+        torch.cuda.empty_cache()
+        tables = tables_section(dev, pk)
     cpu = cpu_baseline(schema, B) if (world == 1 and not args.no_cpu_baseline) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -409,7 +478,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 20},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "roofline": roofline, "cpu_baseline": cpu, "kernels": table, "loss_last": loss_last}
+            "roofline": roofline, "cpu_baseline": cpu, "tables": tables, "kernels": table, "loss_last": loss_last}
     print(json.dumps(line), flush=True)
     _finish(world, dev)
 
@@ -433,8 +502,13 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tables-only", nargs="?", const="full", default=None, choices=["full", "quick"])
+    ap.add_argument("--no-tables", action="store_true", help="skip the large-table (HBM-bound lookup/update) section")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.tables_only:  # development aid: only the large-table section (not the contract line)
+        torch.cuda.set_device(0)
+        print(json.dumps({"tables": tables_section(torch.device("cuda", 0), peaks(), quick=args.tables_only == "quick")}), flush=True)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

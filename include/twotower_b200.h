@@ -310,6 +310,23 @@ int tt_debug_simce_timeline(void* d_buf_4x2048_i64);
 int tt_similarity_matrix(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype,
                          float inv_temp, float* S, int64_t lds, tt_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Retrieval metrics without the B x B matrix.  Replaces
+ * TwoTowerEvaluator.compute_recall_at_k / compute_mrr (src/evaluation/evaluator.py:20-71: two topk calls, a full
+ * argsort and a Python loop over the rows of a materialised S) by one integer per row:
+ *   rank[i] = #{j : S_ij > S_ip} + #{j < p : S_ij == S_ip},  p = diag_offset + i the positive's column
+ * (the positive's 0-based position in a stable descending sort of row i), S = X·Yᵀ * inv_temp computed tile by tile with
+ * the same fp32 main loop as tt_similarity_matrix (bit-identical logits), never stored.
+ *   tt_eval_ranks              X f32 [Bx,F], Y f32 [By,F] -> diag f32 [Bx] (the positives' logits), rank i32 [Bx]
+ *   tt_eval_ranks_from_matrix  the same ranks from a materialised S [Bx, lds] (the reference evaluator's entry points take S)
+ *   tt_eval_rank_metrics       out f32 [nk+2] = {recall@ks[0..nk) = mean(rank < k), MRR = mean(1/(rank+1)), top-1 accuracy};
+ *                              d_ks i32 [nk] on the device, nk <= 8; integer hit counts, fp64 reciprocal-rank sum, fixed order. */
+int tt_eval_ranks(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
+                  int64_t diag_offset, float* diag, int32_t* rank, tt_stream_t stream);
+int tt_eval_ranks_from_matrix(const float* S, int64_t Bx, int64_t By, int64_t lds, int64_t diag_offset, int32_t* rank,
+                              tt_stream_t stream);
+int tt_eval_rank_metrics(const int32_t* rank, int64_t B, const int32_t* d_ks, int32_t nk, float* out, tt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,10 +15,16 @@ def __getattr__(name):
                 "create_two_tower_model", "create_two_tower_train_task", "FusedAdam", "FusedWarmupScheduler", "GraphedFusedStep"):
         from . import modules
         return getattr(modules, name)
+    if name == "TwoTowerEvaluator":
+        from . import evaluator
+        return evaluator.TwoTowerEvaluator
+    if name == "PooledTables":
+        from . import tables
+        return tables.PooledTables
     if name in ("TwoTowerEngine", "TwoTowerConfig"):
         from . import engine
         return getattr(engine, name)
-    if name in ("native", "ops", "modules", "engine", "dist"):
+    if name in ("native", "ops", "modules", "engine", "dist", "tables", "evaluator"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

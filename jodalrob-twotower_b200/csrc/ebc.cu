@@ -85,9 +85,13 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
   }
 }
 
-// jagged bags (L >= 0 per bag), sum pooling; block stages its bag offsets through shared memory.
+// jagged bags (L >= 0 per bag), sum pooling. HBM-bound at scale (BASELINE config 5: pooling factor 20, E=64, tables >> L2), so the
+// kernel is built for memory-level parallelism: the G lanes of a group fetch G ids of the bag at once (one coalesced load, the
+// clamped arena rows and gradient slots are recorded with coalesced stores), then rows are gathered JAG_MLP at a time — all
+// loads of a batch are issued before the first add. The sum runs in ascending value position (embedding_bag's order).
+constexpr int JAG_MLP = 8;
 template <typename OutT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 ebc_fwd_jagged_kernel(const float* __restrict__ arena, const int64_t* __restrict__ row_base,
                       const int32_t* __restrict__ vocab, const int64_t* __restrict__ values,
                       const int64_t* __restrict__ bag_offsets, int B, int K, int E, int layout, OutT* __restrict__ out,
@@ -102,6 +106,9 @@ ebc_fwd_jagged_kernel(const float* __restrict__ arena, const int64_t* __restrict
   }
   __syncthreads();
   const int lane = threadIdx.x % G;
+  // the lanes of this group inside its warp: groups of one warp walk bags of different lengths, so the shuffles
+  // below name only the group's own lanes
+  const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int64_t n_bags = (int64_t)B * K;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
   const int vec_per_row = E >> 2;
@@ -110,22 +117,36 @@ ebc_fwd_jagged_kernel(const float* __restrict__ arena, const int64_t* __restrict
     const int64_t j = layout == TT_LAYOUT_SAMPLE_MAJOR ? slot : (int64_t)k * B + b;
     const int64_t beg = __ldg(bag_offsets + j), end = __ldg(bag_offsets + j + 1);
     const int64_t hi = (int64_t)s_vocab[k] - 1, rb = s_base[k];
-    for (int c = lane; c < vec_per_row; c += G) {
+    for (int c0 = 0; c0 < vec_per_row; c0 += G) {  // one trip for E <= 128
+      const int c = c0 + lane;
+      const bool cv = c < vec_per_row;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int64_t p = beg; p < end; ++p) {
-        int64_t id = __ldg(values + p);
-        id = id < 0 ? 0 : (id > hi ? hi : id);
-        f4_add(acc, __ldg(reinterpret_cast<const float4*>(arena + (rb + id) * E) + c));
+      for (int64_t p0 = beg; p0 < end; p0 += G) {
+        const int cnt = (int)(end - p0 < G ? end - p0 : G);
+        int32_t my_row = 0;  // arena rows fit 31 bits (checked on the host)
+        if (lane < cnt) {
+          int64_t id = __ldg(values + p0 + lane);
+          id = id < 0 ? 0 : (id > hi ? hi : id);
+          my_row = (int32_t)(rb + id);
+          if (c0 == 0) {
+            if (rows_out) rows_out[p0 + lane] = my_row;
+            if (slots_out) slots_out[p0 + lane] = (int32_t)(slot_base + slot);
+          }
+        }
+        for (int q = 0; q < cnt; q += JAG_MLP) {
+          int32_t r[JAG_MLP];
+          float4 v[JAG_MLP];
+#pragma unroll
+          for (int u = 0; u < JAG_MLP; ++u) r[u] = __shfl_sync(gmask, my_row, (q + u) & (G - 1), G);
+#pragma unroll
+          for (int u = 0; u < JAG_MLP; ++u)
+            if (q + u < cnt && cv) v[u] = __ldg(reinterpret_cast<const float4*>(arena + (int64_t)r[u] * E) + c);
+#pragma unroll
+          for (int u = 0; u < JAG_MLP; ++u)
+            if (q + u < cnt && cv) f4_add(acc, v[u]);
+        }
       }
-      store_vec4<OutT>(out + (int64_t)b * out_ld + out_col0 + (int64_t)k * E + 4 * c, acc);
-    }
-    if (lane == 0 && (rows_out || slots_out)) {
-      for (int64_t p = beg; p < end; ++p) {
-        int64_t id = __ldg(values + p);
-        id = id < 0 ? 0 : (id > hi ? hi : id);
-        if (rows_out) rows_out[p] = (int32_t)(rb + id);
-        if (slots_out) slots_out[p] = (int32_t)(slot_base + slot);
-      }
+      if (cv) store_vec4<OutT>(out + (int64_t)b * out_ld + out_col0 + (int64_t)k * E + 4 * c, acc);
     }
   }
 }
@@ -164,32 +185,8 @@ radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, const int32_t* __
   hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// exclusive scan of `len` int32 counters in place, one block
-__global__ void __launch_bounds__(1024) scan_exclusive_kernel(int32_t* __restrict__ data, int64_t len, const int32_t* __restrict__ d_n) {
-  __shared__ int32_t s_part[1024];
-  const int t = threadIdx.x;
-  if (d_n) len = 256 * (int64_t)(*d_n > 0 ? (*d_n + RS_TILE - 1) / RS_TILE : 1);
-  const int64_t per = (len + 1023) / 1024;
-  const int64_t lo = (int64_t)t * per, hi = (lo + per < len) ? lo + per : len;
-  int32_t sum = 0;
-  for (int64_t i = lo; i < hi; ++i) sum += data[i];
-  s_part[t] = sum;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
-    int32_t v = (t >= off) ? s_part[t - off] : 0;
-    __syncthreads();
-    s_part[t] += v;
-    __syncthreads();
-  }
-  int32_t run = s_part[t] - sum;
-  for (int64_t i = lo; i < hi; ++i) {
-    int32_t c = data[i];
-    data[i] = run;
-    run += c;
-  }
-}
-
-// same scan with the counters staged in shared memory (coalesced global traffic); len <= ~48k entries
+// exclusive scan of `len` int32 counters in place, one block, the counters staged in shared memory (coalesced global traffic);
+// len <= ~40k entries (the reference-sized step)
 __global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __restrict__ data, int len, int per,
                                                                    const int32_t* __restrict__ d_n) {
   extern __shared__ int32_t sh[];
@@ -223,14 +220,119 @@ __global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __re
   for (int i = t; i < len; i += 1024) data[i] = sh[(i / per) * (per | 1) + (i % per)];
 }
 
-static int launch_scan(int32_t* data, int64_t len, const int32_t* d_n, cudaStream_t s) {
+// Large inputs (millions of pairs: the multi-hot configurations): the counter array no longer fits one CTA's shared memory and a
+// single-CTA scan would dominate the sort. Three-kernel scan instead: per-block totals, a one-block scan of those totals, and
+// a per-block exclusive scan seeded with the block's offset. SCAN_CHUNK counters per block, 128-bit loads/stores.
+constexpr int SCAN_PER = 8;
+constexpr int SCAN_CHUNK = 1024 * SCAN_PER;
+
+__device__ __forceinline__ int64_t scan_len(int64_t len, const int32_t* __restrict__ d_n) {
+  return d_n ? 256 * (int64_t)(*d_n > 0 ? (*d_n + RS_TILE - 1) / RS_TILE : 1) : len;
+}
+
+// block-wide inclusive scan of one value per thread (1024 threads); returns the inclusive prefix, *total = block sum
+__device__ __forceinline__ int32_t block_scan_1024(int32_t x, int32_t* s_warp, int32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int32_t w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  if (total) *total = s_warp[31];
+  return x + (warp > 0 ? s_warp[warp - 1] : 0);
+}
+
+__global__ void __launch_bounds__(1024)
+scan_chunk_totals_kernel(const int32_t* __restrict__ data, int64_t len, const int32_t* __restrict__ d_n, int32_t* __restrict__ totals) {
+  __shared__ int32_t s_warp[32];
+  len = scan_len(len, d_n);
+  const int64_t lo = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER;
+  int32_t sum = 0;
+  if (lo + SCAN_PER <= len) {
+    const int4 a = *reinterpret_cast<const int4*>(data + lo), b = *reinterpret_cast<const int4*>(data + lo + 4);
+    sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  } else {
+    for (int64_t i = lo; i < len; ++i) sum += data[i];
+  }
+  int32_t total;
+  block_scan_1024(sum, s_warp, &total);
+  if (threadIdx.x == 0) totals[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+scan_totals_kernel(int32_t* __restrict__ totals, int64_t len, const int32_t* __restrict__ d_n) {
+  __shared__ int32_t s_warp[32];
+  len = scan_len(len, d_n);
+  const int nb = (int)((len + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  const int per = (nb + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = lo + per < nb ? lo + per : nb;
+  int32_t sum = 0;
+  for (int i = lo; i < hi; ++i) sum += totals[i];
+  int32_t run = block_scan_1024(sum, s_warp, nullptr) - sum;
+  for (int i = lo; i < hi; ++i) {
+    const int32_t c = totals[i];
+    totals[i] = run;
+    run += c;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+scan_chunk_apply_kernel(int32_t* __restrict__ data, int64_t len, const int32_t* __restrict__ d_n, const int32_t* __restrict__ totals) {
+  __shared__ int32_t s_warp[32];
+  len = scan_len(len, d_n);
+  const int64_t lo = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER;
+  int32_t v[SCAN_PER];
+  const bool full = lo + SCAN_PER <= len;
+  if (full) {
+    const int4 a = *reinterpret_cast<const int4*>(data + lo), b = *reinterpret_cast<const int4*>(data + lo + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_PER; ++i) v[i] = lo + i < len ? data[lo + i] : 0;
+  }
+  int32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_PER; ++i) sum += v[i];
+  int32_t run = block_scan_1024(sum, s_warp, nullptr) - sum + totals[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_PER; ++i) {
+    const int32_t c = v[i];
+    v[i] = run;
+    run += c;
+  }
+  if (full) {
+    *reinterpret_cast<int4*>(data + lo) = make_int4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<int4*>(data + lo + 4) = make_int4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_PER; ++i)
+      if (lo + i < len) data[lo + i] = v[i];
+  }
+}
+
+static int launch_scan(int32_t* data, int64_t len, const int32_t* d_n, int32_t* totals, cudaStream_t s) {
   const int per = (int)((len + 1023) / 1024);
   const size_t smem = (size_t)1024 * (per | 1) * 4;
   if (smem <= 160 * 1024) {
     TT_CUDA(cudaFuncSetAttribute(scan_exclusive_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     scan_exclusive_smem_kernel<<<1, 1024, smem, s>>>(data, (int)len, per, d_n);
   } else {
-    scan_exclusive_kernel<<<1, 1024, 0, s>>>(data, len, d_n);
+    const int nb = (int)((len + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    scan_chunk_totals_kernel<<<nb, 1024, 0, s>>>(data, len, d_n, totals);
+    scan_totals_kernel<<<1, 1024, 0, s>>>(totals, len, d_n);
+    scan_chunk_apply_kernel<<<nb, 1024, 0, s>>>(data, len, d_n, totals);
   }
   return TT_OK;
 }
@@ -380,25 +482,44 @@ ebc_gather_sorted_kernel(const int32_t* __restrict__ sslot, int64_t n, const int
   }
 }
 
-// acc += sum_{i in [lo,hi)} gs[i] in ascending i; batches of 8 keep 8 loads in flight before the first add
-__device__ __forceinline__ void gather_sum(float4& acc, const float* __restrict__ gs, int64_t lo, int64_t hi, int E, int c) {
-  const float* p = gs + lo * E + 4 * c;
+// Where the segment sums read the gradient vector of sorted entry i: from the compacted copy `gs` (small steps: the copy is
+// L2-resident and the sums stream it), or straight from the pooled-gradient buffers through the sorted slot (`gs` NULL; large
+// multi-hot steps: B*K*L compacted vectors would cost an HBM round trip while the B*K pooled gradients themselves stay in L2).
+// Same values in the same order either way, so the two modes are bit-identical.
+struct GradFetch {
+  const float* gs;
+  const int32_t* sslot;
+  GradSrc src;
+  int bf16;
+};
+
+template <bool DIRECT>
+__device__ __forceinline__ float4 fetch_grad(const GradFetch& f, int64_t i, int E, int c) {
+  if (!DIRECT) return __ldg(reinterpret_cast<const float4*>(f.gs + i * E + 4 * c));
+  const int32_t slot = __ldg(f.sslot + i);
+  return f.bf16 ? load_grad_vec<__nv_bfloat16>(f.src, slot, E, c) : load_grad_vec<float>(f.src, slot, E, c);
+}
+
+// acc += sum_{i in [lo,hi)} grad(i) in ascending i; batches of 8 keep 8 loads in flight before the first add
+template <bool DIRECT>
+__device__ __forceinline__ void gather_sum(float4& acc, const GradFetch& f, int64_t lo, int64_t hi, int E, int c) {
   int64_t i = lo;
-  for (; i + 8 <= hi; i += 8, p += 8 * (int64_t)E) {
+  for (; i + 8 <= hi; i += 8) {
     float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(p + u * (int64_t)E));
+    for (int u = 0; u < 8; ++u) v[u] = fetch_grad<DIRECT>(f, i + u, E, c);
 #pragma unroll
     for (int u = 0; u < 8; ++u) f4_add(acc, v[u]);
   }
-  for (; i < hi; ++i, p += E) f4_add(acc, __ldg(reinterpret_cast<const float4*>(p)));
+  for (; i < hi; ++i) f4_add(acc, fetch_grad<DIRECT>(f, i, E, c));
 }
 
 // level 1 for long rows: SUB lane groups per chunk of SEG_CHUNK sorted entries. Each group sums a contiguous
 // SEG_CHUNK / SUB slice of the piece in order, the SUB partial sums are folded by a fixed butterfly ((0+1)+(2+3)):
 // deterministic, and SUB times the parallelism of one group per chunk (the kernel is latency bound: few chunks, long chains).
+template <bool DIRECT>
 __global__ void __launch_bounds__(256)
-ebc_piece_kernel(const int32_t* __restrict__ srow, const float* __restrict__ gs, int64_t n,
+ebc_piece_kernel(const int32_t* __restrict__ srow, const GradFetch gs, int64_t n,
                  const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_begin,
                  const int32_t* __restrict__ row_end, int E, int G, int SUB, float* __restrict__ pieces) {
   if (d_n) n = *d_n;
@@ -426,11 +547,11 @@ ebc_piece_kernel(const int32_t* __restrict__ srow, const float* __restrict__ gs,
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p0 && cv) {
       const int64_t s_lo = lo + (int64_t)sub * span, s_hi = s_lo + span < pe ? s_lo + span : pe;
-      if (s_lo < s_hi) gather_sum(a0, gs, s_lo, s_hi, E, c);
+      if (s_lo < s_hi) gather_sum<DIRECT>(a0, gs, s_lo, s_hi, E, c);
     }
     if (p1 && cv) {
       const int64_t s_lo = b1 + (int64_t)sub * span, s_hi = s_lo + span < hi ? s_lo + span : hi;
-      if (s_lo < s_hi) gather_sum(a1, gs, s_lo, s_hi, E, c);
+      if (s_lo < s_hi) gather_sum<DIRECT>(a1, gs, s_lo, s_hi, E, c);
     }
     for (int off = G; off < unit; off <<= 1) {
       a0.x += __shfl_xor_sync(0xffffffffu, a0.x, off); a0.y += __shfl_xor_sync(0xffffffffu, a0.y, off);
@@ -445,11 +566,12 @@ ebc_piece_kernel(const int32_t* __restrict__ srow, const float* __restrict__ gs,
   }
 }
 
-__device__ __forceinline__ float4 row_grad_sum(const float* __restrict__ gs, int64_t b, int64_t e, int E, int c,
+template <bool DIRECT>
+__device__ __forceinline__ float4 row_grad_sum(const GradFetch& gs, int64_t b, int64_t e, int E, int c,
                                                const float* __restrict__ pieces) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e - b <= SEG_CHUNK) {
-    gather_sum(acc, gs, b, e, E, c);
+    gather_sum<DIRECT>(acc, gs, b, e, E, c);
   } else {
     for (int64_t ch = b / SEG_CHUNK; ch <= (e - 1) / SEG_CHUNK; ++ch) {
       const int which = (b <= ch * SEG_CHUNK) ? 0 : 1;
@@ -476,10 +598,10 @@ __device__ __forceinline__ void adam_vec4(float4& w, float4& m, float4& v, const
 }
 
 // one lane group per arena row, every row (dense-exact Adam and/or dense gradient materialisation)
-template <bool DO_ADAM, bool WRITE_GRAD>
+template <bool DO_ADAM, bool WRITE_GRAD, bool DIRECT>
 __global__ void __launch_bounds__(256, 3)
 ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, float* __restrict__ gout,
-                      int64_t total_rows, int E, int G, const float* __restrict__ gs,
+                      int64_t total_rows, int E, int G, const GradFetch gs,
                       const int32_t* __restrict__ row_begin, const int32_t* __restrict__ row_end,
                       const int32_t* __restrict__ row_stamp, int32_t stamp, const int64_t* __restrict__ d_stamp,
                       const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
@@ -505,7 +627,7 @@ ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __res
         mv = *reinterpret_cast<const float4*>(m + off);
         vv = *reinterpret_cast<const float4*>(v + off);
       }
-      float4 g = hit ? row_grad_sum(gs, b, e, E, c, pieces) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 g = hit ? row_grad_sum<DIRECT>(gs, b, e, E, c, pieces) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (WRITE_GRAD) *reinterpret_cast<float4*>(gout + off) = g;
       if (DO_ADAM) {
         adam_vec4(wv, mv, vv, g, h);
@@ -517,31 +639,91 @@ ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __res
   }
 }
 
-// sparse mode: one lane group per sorted entry; only segment heads work
-__global__ void __launch_bounds__(256)
+// dense-exact Adam over an arena that is much larger than the L2 (the 10 M-row / 500 M-row configurations): pure streaming of
+// w/m/v (24 B per element). Two rows per lane group and iteration keep six 128-bit loads per lane in flight ahead of the
+// stamp -> bounds -> gradient chain; loads and stores are evict-first so the sorted gradients survive in the L2.
+template <bool DIRECT>
+__global__ void __launch_bounds__(256, 3)
+ebc_rows_dense_stream_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int64_t total_rows, int E, int G,
+                             const GradFetch gs, const int32_t* __restrict__ row_begin, const int32_t* __restrict__ row_end,
+                             const int32_t* __restrict__ row_stamp, int32_t stamp, const int64_t* __restrict__ d_stamp,
+                             const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
+  if (d_stamp) stamp += (int32_t)(*d_stamp);
+  const tt_adam_hyper h = *d_hyper;
+  const int lane = threadIdx.x % G;
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
+  const int vec_per_row = E >> 2;
+  for (int64_t r0 = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; r0 < total_rows; r0 += 2 * groups_total) {
+    const int64_t r1 = r0 + groups_total;
+    const bool two = r1 < total_rows;
+    for (int c = lane; c < vec_per_row; c += G) {
+      const int64_t o0 = r0 * E + 4 * c, o1 = r1 * E + 4 * c;
+      float4 w0 = __ldcs(reinterpret_cast<const float4*>(w + o0)), m0 = __ldcs(reinterpret_cast<const float4*>(m + o0)),
+             v0 = __ldcs(reinterpret_cast<const float4*>(v + o0));
+      float4 w1, m1, v1;
+      if (two) {
+        w1 = __ldcs(reinterpret_cast<const float4*>(w + o1));
+        m1 = __ldcs(reinterpret_cast<const float4*>(m + o1));
+        v1 = __ldcs(reinterpret_cast<const float4*>(v + o1));
+      }
+      const bool hit0 = __ldg(row_stamp + r0) == stamp, hit1 = two && __ldg(row_stamp + r1) == stamp;
+      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+      if (hit0) g0 = row_grad_sum<DIRECT>(gs, row_begin[r0], row_end[r0], E, c, pieces);
+      if (hit1) g1 = row_grad_sum<DIRECT>(gs, row_begin[r1], row_end[r1], E, c, pieces);
+      adam_vec4(w0, m0, v0, g0, h);
+      __stcs(reinterpret_cast<float4*>(w + o0), w0);
+      __stcs(reinterpret_cast<float4*>(m + o0), m0);
+      __stcs(reinterpret_cast<float4*>(v + o0), v0);
+      if (two) {
+        adam_vec4(w1, m1, v1, g1, h);
+        __stcs(reinterpret_cast<float4*>(w + o1), w1);
+        __stcs(reinterpret_cast<float4*>(m + o1), m1);
+        __stcs(reinterpret_cast<float4*>(v + o1), v1);
+      }
+    }
+  }
+}
+
+// sparse mode: one lane group per sorted entry; only segment heads work. HBM-bound at scale (millions of touched rows, each a
+// random 3 x E*4-byte read-modify-write), so the dependent chain in front of the row loads is kept to ONE sequential read:
+// the head finds its segment end by scanning the sorted rows forward (coalesced, mostly 1-2 entries) instead of a random
+// row_end[r] lookup, and the w/m/v accesses are streaming (evict-first) so the pooled gradients stay in the L2.
+template <bool DIRECT>
+__global__ void __launch_bounds__(256, 4)
 ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int E, int G,
-                       const int32_t* __restrict__ srow, const float* __restrict__ gs, int64_t n,
+                       const int32_t* __restrict__ srow, const GradFetch gs, int64_t n,
                        const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_end,
                        const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
   if (d_n) n = *d_n;
-  const tt_adam_hyper h = *d_hyper;
   const int lane = threadIdx.x % G;
   const int64_t i = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
   if (i >= n) return;
   const int32_t r = srow[i];
   if (i > 0 && srow[i - 1] == r) return;
-  const int64_t e = row_end[r];
   const int vec_per_row = E >> 2;
+  const int64_t off0 = (int64_t)r * E + 4 * lane;
+  float4 wv, mv, vv;
+  if (lane < vec_per_row) {  // first (for E <= 128: only) vector of the row: issued before anything else
+    wv = __ldcs(reinterpret_cast<const float4*>(w + off0));
+    mv = __ldcs(reinterpret_cast<const float4*>(m + off0));
+    vv = __ldcs(reinterpret_cast<const float4*>(v + off0));
+  }
+  int64_t e = i + 1;
+  while (e < n && e - i <= SEG_CHUNK && __ldg(srow + e) == r) ++e;
+  if (e - i > SEG_CHUNK) e = row_end[r];  // long rows were reduced to pieces: take the recorded end
+  const tt_adam_hyper h = *d_hyper;
   for (int c = lane; c < vec_per_row; c += G) {
-    float4 g = row_grad_sum(gs, i, e, E, c, pieces);
     const int64_t off = (int64_t)r * E + 4 * c;
-    float4 wv = *reinterpret_cast<float4*>(w + off);
-    float4 mv = *reinterpret_cast<float4*>(m + off);
-    float4 vv = *reinterpret_cast<float4*>(v + off);
+    if (c != lane) {
+      wv = __ldcs(reinterpret_cast<const float4*>(w + off));
+      mv = __ldcs(reinterpret_cast<const float4*>(m + off));
+      vv = __ldcs(reinterpret_cast<const float4*>(v + off));
+    }
+    float4 g = row_grad_sum<DIRECT>(gs, i, e, E, c, pieces);
     adam_vec4(wv, mv, vv, g, h);
-    *reinterpret_cast<float4*>(w + off) = wv;
-    *reinterpret_cast<float4*>(m + off) = mv;
-    *reinterpret_cast<float4*>(v + off) = vv;
+    __stcs(reinterpret_cast<float4*>(w + off), wv);
+    __stcs(reinterpret_cast<float4*>(m + off), mv);
+    __stcs(reinterpret_cast<float4*>(v + off), vv);
   }
 }
 
@@ -719,7 +901,7 @@ int64_t tt_ebc_sort_workspace_bytes(int64_t n, int64_t total_rows) {
   (void)total_rows;
   if (n < 0) return 0;
   const int64_t tiles = (n + RS_TILE - 1) / RS_TILE + 1;
-  return 2 * align_up(n * 4 + 16, 256) + align_up(256 * tiles * 4, 256);
+  return 2 * align_up(n * 4 + 16, 256) + align_up(256 * tiles * 4, 256) + align_up((256 * tiles / SCAN_CHUNK + 2) * 4, 256);
 }
 
 int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
@@ -742,6 +924,7 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
   int32_t* tmp_keys = (int32_t*)ws;
   int32_t* tmp_vals = (int32_t*)(ws + align_up(n * 4 + 16, 256));
   int32_t* hist = (int32_t*)(ws + 2 * align_up(n * 4 + 16, 256));
+  int32_t* scan_totals = (int32_t*)((char*)hist + align_up(256 * (int64_t)((n + RS_TILE - 1) / RS_TILE + 1) * 4, 256));
   const int32_t* kin = rows;
   const int32_t* vin = slots;  // NULL => identity on the first pass
   for (int p = 0; p < passes; ++p) {
@@ -749,7 +932,7 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
     int32_t* kout = to_final ? sorted_rows : tmp_keys;
     int32_t* vout = to_final ? sorted_slots : tmp_vals;
     radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles);
-    { int rc = launch_scan(hist, (int64_t)256 * n_tiles, d_n, s); if (rc != TT_OK) return rc; }
+    { int rc = launch_scan(hist, (int64_t)256 * n_tiles, d_n, scan_totals, s); if (rc != TT_OK) return rc; }
     radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, d_n, p * 8, hist, n_tiles, kout, vout);
     kin = kout;
     vin = vout;
@@ -795,34 +978,49 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
   GradSrc src{grad0, grad1, ld0, ld1, col0_0, col0_1, n0, K0, K1 > 0 ? K1 : 1, grad_table, n_per_rank > 0 ? n_per_rank : 1, d_colmap0, d_colmap1};
   float* pieces = (float*)piece_ws;
   const int64_t n_chunks = (n + SEG_CHUNK - 1) / SEG_CHUNK;
-  const float* gs = (const float*)((const char*)piece_ws + align_up((n_chunks + 1) * 2 * (int64_t)E * 4, 256));
+  const float* gs_buf = (const float*)((const char*)piece_ws + align_up((n_chunks + 1) * 2 * (int64_t)E * 4, 256));
+  // The gradients are compacted in sorted order first (independent 16-byte gathers, then streaming sums). TT_EBC_DIRECT=1 makes
+  // the segment sums fetch through the sorted slots instead (no [n,E] copy); measured on B200 at the config-5 shard it is slower
+  // (4.7 ms vs 2.9 ms: the dependent slot -> gradient chain sits in front of every Adam update), so it stays an experiment knob.
+  static const int direct_env = [] { const char* e = getenv("TT_EBC_DIRECT"); return e ? atoi(e) : -1; }();
+  const bool direct = !grad_table && direct_env > 0;
+  const GradFetch gs{direct ? nullptr : gs_buf, sorted_slots, src, grad_dtype == TT_BF16 ? 1 : 0};
   if (n > 0) {
-    int64_t want = ceil_div(n * (E / 4), (int64_t)threads);
-    const int64_t cap = (int64_t)sm_count() * 16;
-    const int ggrid = (int)(want > cap ? cap : want);
-    if (grad_dtype == TT_F32)
-      ebc_gather_sorted_kernel<float><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs);
-    else
-      ebc_gather_sorted_kernel<__nv_bfloat16><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs);
+    if (!direct) {
+      int64_t want = ceil_div(n * (E / 4), (int64_t)threads);
+      const int64_t cap = (int64_t)sm_count() * 16;
+      const int ggrid = (int)(want > cap ? cap : want);
+      if (grad_dtype == TT_F32)
+        ebc_gather_sorted_kernel<float><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs_buf);
+      else
+        ebc_gather_sorted_kernel<__nv_bfloat16><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs_buf);
+    }
     int SUB = 4;
     while (SUB > 1 && (G * SUB > 32 || 32 % (G * SUB) != 0)) SUB >>= 1;
     if (32 % G != 0) SUB = 1;  // lane groups that straddle warps cannot shuffle: one group per chunk
-    ebc_piece_kernel<<<ceil_div(n_chunks, threads / (G * SUB)), threads, 0, s>>>(sorted_rows, gs, n, d_n, row_begin, row_end, E, G,
+    if (direct)
+      ebc_piece_kernel<true><<<ceil_div(n_chunks, threads / (G * SUB)), threads, 0, s>>>(sorted_rows, gs, n, d_n, row_begin, row_end,
+                                                                                         E, G, SUB, pieces);
+    else
+    ebc_piece_kernel<false><<<ceil_div(n_chunks, threads / (G * SUB)), threads, 0, s>>>(sorted_rows, gs, n, d_n, row_begin, row_end, E, G,
                                                                                  SUB, pieces);
   }
   if (mode == TT_ADAM_SPARSE) {
     if (n > 0)
-      ebc_rows_sparse_kernel<<<ceil_div(n, gpb), threads, 0, s>>>(arena_w, arena_m, arena_v, E, G, sorted_rows, gs, n, d_n,
+      (direct ? ebc_rows_sparse_kernel<true> : ebc_rows_sparse_kernel<false>)<<<ceil_div(n, gpb), threads, 0, s>>>(arena_w, arena_m, arena_v, E, G, sorted_rows, gs, n, d_n,
                                                                   row_end, pieces, d_hyper);
   } else {
     int64_t want = ceil_div(total_rows, gpb);
     const int64_t cap = (int64_t)sm_count() * 32;
     const int grid = (int)(want > cap ? cap : want);
 #define TT_ROWS_LAUNCH(A, W)                                                                                         \
-  ebc_rows_dense_kernel<A, W><<<grid, threads, 0, s>>>(arena_w, arena_m, arena_v, grad_arena, total_rows, E, G, gs, \
+  (direct ? ebc_rows_dense_kernel<A, W, true> : ebc_rows_dense_kernel<A, W, false>)<<<grid, threads, 0, s>>>(arena_w, arena_m, arena_v, grad_arena, total_rows, E, G, gs, \
                                                        row_begin, row_end, row_stamp, stamp, d_stamp, pieces, d_hyper)
     const bool wg = grad_arena != nullptr;
-    if (do_adam && wg) TT_ROWS_LAUNCH(true, true);
+    if (do_adam && !wg && total_rows * (int64_t)E * 4 >= ((int64_t)256 << 20))  // arena >> L2: the streaming variant
+      (direct ? ebc_rows_dense_stream_kernel<true> : ebc_rows_dense_stream_kernel<false>)<<<grid, threads, 0, s>>>(
+          arena_w, arena_m, arena_v, total_rows, E, G, gs, row_begin, row_end, row_stamp, stamp, d_stamp, pieces, d_hyper);
+    else if (do_adam && wg) TT_ROWS_LAUNCH(true, true);
     else if (do_adam) TT_ROWS_LAUNCH(true, false);
     else TT_ROWS_LAUNCH(false, true);
 #undef TT_ROWS_LAUNCH

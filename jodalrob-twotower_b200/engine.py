@@ -683,8 +683,11 @@ class TwoTowerEngine:
                    ptr(self.hyper), self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, 0, 0, 0, ptr(self.colmap[0]),
                    ptr(self.colmap[1]), s, n_kernels=2)
 
-    def backward(self, ws: _Ws, dloss: float = 1.0):
-        self.loss_backward(ws, dloss)
+    def backward(self, ws: _Ws, dloss: float = 1.0, de_given: bool = False):
+        """Backward of the loss and both towers. `de_given`: ws.de already holds the gradients of the two tower outputs
+        (a loss evaluated outside the library, e.g. loss_type="cosine_embedding"); only the towers run."""
+        if not de_given:
+            self.loss_backward(ws, dloss)
         if self.two_streams:
             main = torch.cuda.current_stream(self.device)
             self._side.wait_stream(main)

@@ -252,6 +252,63 @@ class _TrainStepFn(torch.autograd.Function):
         return (None,) * 7 + tuple(grads)
 
 
+def _cosine_embedding_loss(s: torch.Tensor) -> torch.Tensor:
+    """two_tower_train_task.py:136-158 verbatim in meaning: diagonal sims with target +1, off-diagonal with target -1, through the
+    (degenerate, 1-D) F.cosine_embedding_loss against a vector of ones."""
+    import torch.nn.functional as F
+    b = s.size(0)
+    off = ~torch.eye(b, dtype=torch.bool, device=s.device)
+    sims = torch.cat([torch.diag(s), s[off]])
+    tg = torch.cat([torch.ones(b, device=s.device), -torch.ones(b * b - b, device=s.device)])
+    return F.cosine_embedding_loss(sims.unsqueeze(1), torch.ones_like(sims.unsqueeze(1)), tg)
+
+
+class _CosineStepFn(torch.autograd.Function):
+    """Train step with loss_type="cosine_embedding" (not the default, off the fast path): the towers, their
+    backward and the optimizer run in the library; the loss on the materialised [B,B] matrix and dS -> (dN, dC) are torch CUDA
+    ops. Its gradient is numerically ~0 by construction (d sign(s)/ds), exactly like the reference's."""
+
+    @staticmethod
+    def forward(ctx, task, nd, nv, cd, cv, layout, masks, *params):
+        eng = task.engine
+        if task._fused_opt is not None:
+            o = task._fused_opt
+            eng.hyper_advance(o.lr, o.warmup_steps, o.betas, o.eps, o.weight_decay)
+        elif eng.cfg.dropout > 0:
+            eng.hyper_advance(0.0, 0, (0.9, 0.999), 1e-8, 0.0)
+        out5, ws = eng.forward(nd, nv, cd, cv, True, layout, masks)
+        s = eng.similarity_matrix(ws)
+        res = out5.clone()
+        res[0] = _cosine_embedding_loss(s)
+        ctx.task, ctx.ws, ctx.s = task, ws, s
+        ctx.mark_non_differentiable(res)
+        return res[0].clone(), res
+
+    @staticmethod
+    def backward(ctx, dloss, _dres):
+        task, ws = ctx.task, ctx.ws
+        eng = task.engine
+        with torch.enable_grad():
+            s_ = ctx.s.detach().requires_grad_(True)
+            (ds,) = torch.autograd.grad(_cosine_embedding_loss(s_), s_)
+        fused = task._fused_opt is not None
+        scale = (1.0 if fused else float(dloss)) / eng.cfg.temperature
+        n, c = ws.e[0].float(), ws.e[1].float()
+        ws.de[0].copy_(torch.mm(ds, c) * scale)
+        ws.de[1].copy_(torch.mm(ds.t(), n) * scale)
+        eng.backward(ws, 1.0, de_given=True)
+        if fused:
+            eng.reduce_dense_grads()
+            eng.embedding_backward(ws, apply_adam=True, want_dense_grad=False)
+            eng.dense_adam()
+            return (None,) * 8
+        eng.embedding_backward(ws, apply_adam=False, want_dense_grad=True)
+        grads = []
+        for kind, ref in task._param_src:
+            grads.append(eng.table_view(ref[0], ref[1], "g").clone() if kind == "table" else eng.dense(ref, "g").clone())
+        return (None,) * 7 + tuple(grads)
+
+
 class TwoTowerTrainTask(nn.Module):
     def __init__(self, two_tower_model: TwoTowerModel, temperature: float = 1.0, loss_type: str = "cross_entropy",
                  label_smoothing: float = 0.0):
@@ -312,8 +369,9 @@ class TwoTowerTrainTask(nn.Module):
         self._sync_cfg()
         eng = self.engine
         nd, nv, cd, cv, lay = self._unpack(batch)
+        self._last_B = nd.shape[0]
         if self.loss_type != "cross_entropy":
-            return self._forward_cosine_embedding(nd, nv, cd, cv, lay, return_metrics)
+            return self._forward_cosine_embedding(nd, nv, cd, cv, lay, return_metrics, dropout_masks)
         if self.training and torch.is_grad_enabled():
             params = (self._anchor,) if self._fused_opt is not None else tuple(self._param_list)
             loss, res = _TrainStepFn.apply(self, nd, nv, cd, cv, lay, dropout_masks, *params)
@@ -340,31 +398,54 @@ class TwoTowerTrainTask(nn.Module):
         o = self._fused_opt
         if o is None:
             raise RuntimeError("attach a FusedAdam(task, ...) before fused_step")
+        if self.loss_type != "cross_entropy":  # non-default loss: library towers/optimizer around a torch-evaluated loss
+            if lr is not None or warmup_steps is not None:
+                raise ValueError("per-call lr/warmup overrides are only supported for loss_type='cross_entropy'")
+            was = self.training
+            self.train()
+            out = self(batch, return_metrics=True)
+            out["loss"].backward()
+            self.train(was)
+            return torch.stack([out[k].detach().float() for k in ("loss", "accuracy", "positive_similarity_mean",
+                                                                    "negative_similarity_mean", "similarity_gap")])
         nd, nv, cd, cv, lay = self._unpack(batch)
         return self.engine.fused_step(nd, nv, cd, cv, lr if lr is not None else o.lr,
                                       warmup_steps if warmup_steps is not None else o.warmup_steps, o.betas, o.eps,
                                       o.weight_decay, lay)
 
-    def _forward_cosine_embedding(self, nd, nv, cd, cv, lay, return_metrics):
-        # two_tower_train_task.py:136-158 — the non-default, near-zero-gradient alternative loss; evaluated from the
-        # materialised matrix with torch ops, forward only. Training with it is not on the hot path.
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("loss_type='cosine_embedding' is forward-only here; the hot path is cross_entropy")
-        import torch.nn.functional as F
+    def _forward_cosine_embedding(self, nd, nv, cd, cv, lay, return_metrics, dropout_masks=None):
+        # two_tower_train_task.py:136-158 — the non-default, near-zero-gradient alternative loss, evaluated from the
+        # materialised matrix. Training goes through _CosineStepFn; not on the hot path.
         eng = self.engine
-        with torch.no_grad():
-            res, ws = eng.forward(nd, nv, cd, cv, self.training, lay)
-            s = eng.similarity_matrix(ws)
-            b = s.size(0)
-            off = ~torch.eye(b, dtype=torch.bool, device=s.device)
-            sims = torch.cat([torch.diag(s), s[off]])
-            tg = torch.cat([torch.ones(b, device=s.device), -torch.ones(b * b - b, device=s.device)])
-            loss = F.cosine_embedding_loss(sims.unsqueeze(1), torch.ones_like(sims.unsqueeze(1)), tg)
+        if self.training and torch.is_grad_enabled():
+            params = (self._anchor,) if self._fused_opt is not None else tuple(self._param_list)
+            loss, res = _CosineStepFn.apply(self, nd, nv, cd, cv, lay, dropout_masks, *params)
+            ws = eng.workspace(nd.shape[0])
+            s = None
+        else:
+            with torch.no_grad():
+                res, ws = eng.forward(nd, nv, cd, cv, self.training, lay, dropout_masks)
+                res = res.clone()
+                s = eng.similarity_matrix(ws)
+                loss = _cosine_embedding_loss(s)
         if not return_metrics:
             return loss
-        r = res.clone()
-        return {"loss": loss, "accuracy": r[1], "positive_similarity_mean": r[2], "negative_similarity_mean": r[3],
-                "similarity_gap": r[4], "similarity_matrix": s}
+        r = res.detach()
+        return _LazyResult({"loss": loss, "accuracy": r[1], "positive_similarity_mean": r[2], "negative_similarity_mean": r[3],
+                            "similarity_gap": r[4]}, (lambda: s) if s is not None else (lambda: eng.similarity_matrix(ws)))
+
+    def eval_ranks(self, batch=None):
+        """(rank i32 [B], positive logit f32 [B]): position of every notice's own company in a stable descending sort of its
+        row of S, from the tower embeddings of the last forward (or of `batch`, forwarded in the current mode) — the B x B
+        matrix is never stored. recall@k / MRR follow from it (evaluator.py:20-71)."""
+        from .evaluator import ranks_from_embeddings
+        if batch is not None:
+            with torch.no_grad():
+                self(batch)
+        if getattr(self, "_last_B", None) is None:
+            raise RuntimeError("eval_ranks() needs a forward first (or pass a batch)")
+        ws = self.engine.workspace(self._last_B)
+        return ranks_from_embeddings(ws.e[0], ws.e[1], 1.0 / self.temperature)
 
     def predict_batch(self, batch, top_k: int = 10):
         self.eval()
@@ -395,6 +476,8 @@ class GraphedFusedStep:
     def __init__(self, task: "TwoTowerTrainTask", example_batch):
         if task._fused_opt is None:
             raise RuntimeError("attach a FusedAdam(task, ...) before capturing the fused step")
+        if task.loss_type != "cross_entropy":
+            raise ValueError("GraphedFusedStep captures the cross_entropy hot path; loss_type='cosine_embedding' runs eagerly")
         self.task = task
         eng = task.engine
         task._sync_cfg()

@@ -93,13 +93,13 @@ def run_trajectory(task, nk, ck, batches, lr=1e-3, wd=1e-5, warmup_steps=2):
     return rec, opt
 
 
-def tiny_case(name, hidden, final_dim, emb_dim, temperature, label_smoothing, oob, bsz=24, seed=0):
+def tiny_case(name, hidden, final_dim, emb_dim, temperature, label_smoothing, oob, bsz=24, seed=0, loss_type="cross_entropy"):
     meta = os.path.join(GOLD, "tiny_metadata.csv")
     nd_dim, cd_dim = 12, 6
     task, nk, ck = rh.build_reference_task(
         categorical_embedding_dim=emb_dim, notice_dense_input_dim=nd_dim, company_dense_input_dim=cd_dim,
         tower_hidden_dims=hidden, final_embedding_dim=final_dim, dropout_rate=0.0,
-        temperature=temperature, seed=seed, meta=meta, label_smoothing=label_smoothing)
+        temperature=temperature, seed=seed, meta=meta, label_smoothing=label_smoothing, loss_type=loss_type)
     nv, cv = _vocab_of(task)
     out = {f"init.{k}": v.numpy().copy() for k, v in task.state_dict().items()}
     gen = torch.Generator().manual_seed(1234)
@@ -121,7 +121,8 @@ def tiny_case(name, hidden, final_dim, emb_dim, temperature, label_smoothing, oo
         out[f"adam_v.{n}"] = st["exp_avg_sq"].numpy().copy()
     cfg = dict(schema={"notice": nv, "company": cv}, emb_dim=emb_dim, notice_dense=nd_dim, company_dense=cd_dim,
                hidden=list(hidden), final_dim=final_dim, temperature=temperature, label_smoothing=label_smoothing,
-               lr=1e-3, weight_decay=1e-5, warmup_steps=2, bsz=bsz, seed=seed, n_params=int(sum(p.numel() for p in task.parameters())))
+               lr=1e-3, weight_decay=1e-5, warmup_steps=2, bsz=bsz, seed=seed, loss_type=loss_type,
+               n_params=int(sum(p.numel() for p in task.parameters())))
     out["config_json"] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(GOLD, f"tiny_{name}.npz"), **out)
     print(f"tiny_{name}: loss traj", [float(out[f's{i}.loss']) for i in range(3)], "params", cfg["n_params"])
@@ -178,9 +179,41 @@ def readme_default_case():
     print("readme_default: loss traj", [float(out[f's{i}.loss']) for i in range(3)], cfg["n_params"], cfg["n_params_train_py_config"])
 
 
+def eval_case():
+    """Retrieval metrics of the UNMODIFIED reference evaluator (src/evaluation/evaluator.py:20-71) on fixed matrices."""
+    rh.install_shims()
+    from src.evaluation.evaluator import TwoTowerEvaluator
+    ev = TwoTowerEvaluator(device="cpu")
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    for name, B, boost in (("a", 64, 1.0), ("b", 257, 2.5), ("c", 5, 0.0)):
+        S = torch.randn(B, B, generator=g)
+        S[torch.arange(B), torch.arange(B)] += boost
+        out[f"{name}.S"] = S.numpy().copy()
+        for k in (1, 5, 10):
+            out[f"{name}.recall@{k}"] = np.float32(ev.compute_recall_at_k(S, k).item())
+        out[f"{name}.mrr"] = np.float32(ev.compute_mrr(S).item())
+        cm = ev.compute_comprehensive_metrics(S, {"loss": 1.25, "accuracy": 0.5})
+        out[f"{name}.comprehensive_json"] = np.frombuffer(json.dumps({k: (bool(v) if isinstance(v, (bool, np.bool_)) else float(v))
+                                                                       for k, v in cm.items()}).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(GOLD, "eval_metrics.npz"), **out)
+    print("eval_metrics:", {k: float(v) for k, v in out.items() if "recall@5" in k or "mrr" in k})
+
+
 def main():
+    import sys
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order → reproducible fixtures
+    if "eval" in sys.argv[1:] or len(sys.argv) == 1:
+        eval_case()
+        if len(sys.argv) > 1 and "cosine" not in sys.argv[1:]:
+            return
+    if "cosine" in sys.argv[1:] or len(sys.argv) == 1:
+        # the non-default loss (two_tower_train_task.py:136-158): near-zero gradients, so the trajectory is driven by weight decay
+        tiny_case("cosine", hidden=(16, 8), final_dim=8, emb_dim=8, temperature=0.5, label_smoothing=0.0, oob=0.0,
+                  loss_type="cosine_embedding")
+        if len(sys.argv) > 1:
+            return
     tiny_case("base", hidden=(16, 8), final_dim=8, emb_dim=8, temperature=1.0, label_smoothing=0.0, oob=0.0)
     tiny_case("oob_temp", hidden=(16, 8), final_dim=8, emb_dim=8, temperature=0.5, label_smoothing=0.0, oob=0.1)
     tiny_case("deep_ls", hidden=(16, 12, 8), final_dim=4, emb_dim=4, temperature=0.25, label_smoothing=0.1, oob=0.05)

@@ -287,3 +287,70 @@ class OracleStepper:
             i = p["final_index"]
             out[pre + f"mlp.{i}.weight"], out[pre + f"mlp.{i}.bias"] = p["Wf"], p["bf"]
         return out
+
+
+# ----------------------------------------------------------------------------- pooled (multi-hot) tables, L >= 0 ids per bag
+def pooled_forward(tables: Sequence[torch.Tensor], values: torch.Tensor, offsets: torch.Tensor, B: int,
+                   layout: str = "sample_major") -> torch.Tensor:
+    """Sum-pooled EmbeddingBagCollection forward -> [B, K*E]. The reference has one id per bag
+    (unified_bid_data_loader.py:835); L>1 is the BASELINE config-5 generalisation whose oracle is
+    torch embedding_bag(mode="sum") (SURVEY.md §8c). Bag j = b*K+k (sample-major) or k*B+b (key-major);
+    ids clamp to [0, V_k-1] like cat_embed.py:115-117."""
+    K, E = len(tables), tables[0].shape[1]
+    out = torch.zeros(B, K * E, dtype=tables[0].dtype)
+    for b in range(B):
+        for k in range(K):
+            j = b * K + k if layout == "sample_major" else k * B + b
+            lo, hi = int(offsets[j]), int(offsets[j + 1])
+            if hi > lo:
+                ids = values[lo:hi].clamp(0, tables[k].shape[0] - 1)
+                out[b, k * E:(k + 1) * E] = torch.nn.functional.embedding_bag(ids, tables[k], torch.tensor([0]), mode="sum")[0]
+    return out
+
+
+def pooled_dense_grads(vocab: Sequence[int], E: int, values: torch.Tensor, offsets: torch.Tensor, B: int, grad: torch.Tensor,
+                       layout: str = "sample_major") -> List[torch.Tensor]:
+    """Dense [V_k, E] gradient of every table (what autograd's embedding_dense_backward produces), accumulated in
+    ascending value position, the order the deterministic sort-dedup fixes."""
+    K = len(vocab)
+    gs = [torch.zeros(v, E, dtype=grad.dtype) for v in vocab]
+    for b in range(B):
+        for k in range(K):
+            j = b * K + k if layout == "sample_major" else k * B + b
+            lo, hi = int(offsets[j]), int(offsets[j + 1])
+            if hi > lo:
+                ids = values[lo:hi].clamp(0, vocab[k] - 1)
+                gs[k].index_add_(0, ids, grad[b, k * E:(k + 1) * E].expand(hi - lo, E))
+    return gs
+
+
+def pooled_touched(vocab: Sequence[int], values: torch.Tensor, offsets: torch.Tensor, B: int, layout: str = "sample_major"):
+    K = len(vocab)
+    t = [torch.zeros(v, dtype=torch.bool) for v in vocab]
+    for b in range(B):
+        for k in range(K):
+            j = b * K + k if layout == "sample_major" else k * B + b
+            lo, hi = int(offsets[j]), int(offsets[j + 1])
+            if hi > lo:
+                t[k][values[lo:hi].clamp(0, vocab[k] - 1)] = True
+    return t
+
+
+# ----------------------------------------------------------------------------- retrieval metrics (evaluator.py:20-71)
+def positive_ranks(S: np.ndarray, diag_offset: int = 0) -> np.ndarray:
+    """0-based position of column diag_offset+i in a STABLE descending sort of row i — what
+    `(argsort(S, descending=True)[i] == i).nonzero()` (evaluator.py:56-66) yields when ties keep column order."""
+    S = np.asarray(S)
+    order = np.argsort(-S, axis=1, kind="stable")
+    pos = np.arange(S.shape[0]) + diag_offset
+    return np.argmax(order == pos[:, None], axis=1).astype(np.int32)
+
+
+def recall_at_k(S: np.ndarray, k: int) -> float:
+    """evaluator.py:20-43: mean over rows of [positive among the top-k columns]."""
+    return float((positive_ranks(S) < min(k, S.shape[1])).astype(np.float32).mean())
+
+
+def mrr(S: np.ndarray) -> float:
+    """evaluator.py:45-71: mean of 1/(rank+1) (python floats, then a float32 tensor mean)."""
+    return float(np.mean((1.0 / (positive_ranks(S).astype(np.float64) + 1.0)).astype(np.float32)))

@@ -26,7 +26,7 @@ def make_task(cfg, schema, dropout=0.0, optimizer_mode="dense_exact", value_layo
         nk, ck, categorical_embedding_dim=cfg["emb_dim"], notice_dense_input_dim=cfg["notice_dense"],
         company_dense_input_dim=cfg["company_dense"], tower_hidden_dims=cfg["hidden"], final_embedding_dim=cfg["final_dim"],
         dropout_rate=dropout, temperature=cfg["temperature"], device=DEV, label_smoothing=cfg.get("label_smoothing", 0.0),
-        vocab_sizes=vs, optimizer_mode=optimizer_mode, value_layout=value_layout)
+        vocab_sizes=vs, optimizer_mode=optimizer_mode, value_layout=value_layout, loss_type=cfg.get("loss_type", "cross_entropy"))
 
 
 def make_batch(schema, nid, cid, nd, cd, layout="sample_major", device=DEV):
@@ -121,7 +121,8 @@ def test_ebc_forward_jagged_bags_sum_pooling():
 
 
 # ------------------------------------------------------------------------------- sort / dedup
-@pytest.mark.parametrize("n,total_rows", [(1, 1), (5, 3), (2048, 70), (2049, 64141), (100003, 64141), (50000, 300000), (7000, 20_000_000)])
+@pytest.mark.parametrize("n,total_rows", [(1, 1), (5, 3), (2048, 70), (2049, 64141), (100003, 64141), (50000, 300000), (7000, 20_000_000),
+                                          (1_000_003, 5_000_000), (400_000, 70)])  # the last two: multi-block counter scan
 def test_sort_dedup_bit_exact(n, total_rows):
     import jodalrob_twotower_b200 as tt
     from jodalrob_twotower_b200.native import ptr
@@ -216,6 +217,48 @@ def test_fused_step_matches_reference_golden(case):
         v = eng.table_view(ref[0], ref[1], "v") if kind == "table" else eng.dense(ref, "v")
         assert rel_err(m.cpu(), torch.from_numpy(d[f"adam_m.{name}"])) < 2e-5, name
         assert rel_err(v.cpu(), torch.from_numpy(d[f"adam_v.{name}"])) < 2e-5, name
+
+
+@pytest.mark.parametrize("mode", ["autograd", "fused"])
+def test_cosine_embedding_loss_trajectory_vs_reference_golden(mode):
+    """loss_type="cosine_embedding" (two_tower_train_task.py:136-158). The loss only counts signs of the
+    similarities and its gradient is rounding noise (~1e-8 in the reference itself), so: losses/metrics/S to fp32 tolerance,
+    gradients noise-level on both sides, and the weight-decay-driven 3-step trajectory to 1e-4 (Adam amplifies the noise)."""
+    import jodalrob_twotower_b200 as tt
+    d, cfg = load_golden("tiny_cosine.npz")
+    assert cfg["loss_type"] == "cosine_embedding"
+    task = make_task(cfg, cfg["schema"])
+    task.load_state_dict(sd_from(d, "init."))
+    w = cfg["warmup_steps"]
+    if mode == "autograd":
+        opt = torch.optim.Adam(task.parameters(), lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: s / w if s < w else 1.0, last_epoch=-1)
+    else:
+        opt = tt.FusedAdam(task, lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+        sched = tt.FusedWarmupScheduler(opt, w)
+    task.train()
+    for i in range(3):
+        nid, cid, nd, cd = batch_inputs(d, i)
+        opt.zero_grad()
+        out = task(make_batch(cfg["schema"], nid, cid, nd, cd), return_metrics=True)
+        out["loss"].backward()
+        assert abs(out["loss"].item() - float(d[f"s{i}.loss"])) <= 1e-6
+        for m in ("accuracy", "positive_similarity_mean", "negative_similarity_mean", "similarity_gap"):
+            assert abs(out[m].item() - float(d[f"s{i}.{m}"])) < 2e-6, m
+        assert rel_err(out["similarity_matrix"].cpu(), torch.from_numpy(d[f"s{i}.similarity_matrix"])) < FP32_RTOL
+        if i == 0 and mode == "autograd":
+            for name, p in task.named_parameters():
+                assert float(p.grad.abs().max()) < 1e-6 and float(np.abs(d[f"grad0.{name}"]).max()) < 1e-6, name
+        opt.step()
+        sched.step()
+    fin = sd_from(d, "final.")
+    for k, v in task.state_dict().items():
+        if v.is_floating_point():
+            assert rel_err(v.cpu(), fin[k]) < 1e-4, k
+    task.eval()
+    with torch.no_grad():
+        ev = task(make_batch(cfg["schema"], *batch_inputs(d, 0)), return_metrics=True)
+    assert ev["similarity_matrix"].shape == (cfg["bsz"], cfg["bsz"]) and torch.isfinite(ev["loss"])
 
 
 def test_key_major_layout_gives_same_step():

@@ -8,12 +8,13 @@ from oracle import ref_port, two_tower_oracle as orc
 from tests.helpers import TINY_CASES, batch_inputs, load_golden, readme_schema, rel_err, sd_from
 
 
-@pytest.mark.parametrize("case", TINY_CASES)
+@pytest.mark.parametrize("case", TINY_CASES + ["cosine"])
 def test_port_matches_reference_trajectory_bit_exact(case):
     torch.set_num_threads(1)
     d, cfg = load_golden(f"tiny_{case}.npz")
     task = ref_port.build_port_task(cfg["schema"], cfg["emb_dim"], cfg["notice_dense"], cfg["company_dense"], cfg["hidden"],
-                                    cfg["final_dim"], 0.0, cfg["temperature"], "cross_entropy", cfg["label_smoothing"], seed=cfg["seed"])
+                                    cfg["final_dim"], 0.0, cfg["temperature"], cfg.get("loss_type", "cross_entropy"), cfg["label_smoothing"],
+                                    seed=cfg["seed"])
     init = sd_from(d, "init.")
     # seeded construction reproduces the reference init bit-for-bit (same RNG consumption order)
     for k, v in task.state_dict().items():
@@ -165,3 +166,19 @@ def test_rw_shard_and_sort_dedup_properties():
     for s, e in zip(sdp["seg_starts"][:-1], sdp["seg_starts"][1:]):
         assert np.all(np.diff(sdp["positions"][s:e]) > 0)  # stable: positions ascend inside a segment
     assert np.array_equal(sdp["unique_rows"], np.unique(rows))
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_retrieval_metric_oracle_matches_reference_evaluator(name):
+    """oracle positive_ranks/recall_at_k/mrr vs the unmodified reference TwoTowerEvaluator (tests/golden/eval_metrics.npz,
+    generated by oracle/make_golden.py eval_case from src/evaluation/evaluator.py:20-117)."""
+    import json
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "eval_metrics.npz"))
+    S = z[f"{name}.S"]
+    for k in (1, 5, 10):
+        assert abs(orc.recall_at_k(S, k) - float(z[f"{name}.recall@{k}"])) < 1e-7
+    assert abs(orc.mrr(S) - float(z[f"{name}.mrr"])) < 1e-6
+    cm = json.loads(bytes(z[f"{name}.comprehensive_json"]).decode())
+    assert abs(cm["recall@10"] - orc.recall_at_k(S, 10)) < 1e-7 and cm["batch_size"] == S.shape[0]
