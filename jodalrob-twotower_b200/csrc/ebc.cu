@@ -500,16 +500,16 @@ __device__ __forceinline__ float4 fetch_grad(const GradFetch& f, int64_t i, int 
   return f.bf16 ? load_grad_vec<__nv_bfloat16>(f.src, slot, E, c) : load_grad_vec<float>(f.src, slot, E, c);
 }
 
-// acc += sum_{i in [lo,hi)} grad(i) in ascending i; batches of 8 keep 8 loads in flight before the first add
-template <bool DIRECT>
+// acc += sum_{i in [lo,hi)} grad(i) in ascending i; batches of BATCH keep that many loads in flight before the first add
+template <bool DIRECT, int BATCH = 8>
 __device__ __forceinline__ void gather_sum(float4& acc, const GradFetch& f, int64_t lo, int64_t hi, int E, int c) {
   int64_t i = lo;
-  for (; i + 8 <= hi; i += 8) {
-    float4 v[8];
+  for (; i + BATCH <= hi; i += BATCH) {
+    float4 v[BATCH];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = fetch_grad<DIRECT>(f, i + u, E, c);
+    for (int u = 0; u < BATCH; ++u) v[u] = fetch_grad<DIRECT>(f, i + u, E, c);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) f4_add(acc, v[u]);
+    for (int u = 0; u < BATCH; ++u) f4_add(acc, v[u]);
   }
   for (; i < hi; ++i) f4_add(acc, fetch_grad<DIRECT>(f, i, E, c));
 }
@@ -684,46 +684,83 @@ ebc_rows_dense_stream_kernel(float* __restrict__ w, float* __restrict__ m, float
   }
 }
 
-// sparse mode: one lane group per sorted entry; only segment heads work. HBM-bound at scale (millions of touched rows, each a
-// random 3 x E*4-byte read-modify-write), so the dependent chain in front of the row loads is kept to ONE sequential read:
-// the head finds its segment end by scanning the sorted rows forward (coalesced, mostly 1-2 entries) instead of a random
-// row_end[r] lookup, and the w/m/v accesses are streaming (evict-first) so the pooled gradients stay in the L2.
+// sparse mode: lane groups walk the sorted entries; only segment heads work. HBM-bound at scale (millions of touched rows, each
+// a random 3 x E*4-byte read-modify-write), so the kernel is built around memory-level parallelism:
+//   * persistent grid-stride CTAs, SP_ROWS entries per lane group and iteration: the w/m/v loads of all of them are issued
+//     before anything that depends on memory;
+//   * the dependent chain in front of the gradient is ONE sequential read: a head finds its segment end by scanning the sorted
+//     rows forward (coalesced, mostly 1-2 entries) instead of a random row_end[r] lookup;
+//   * w/m/v accesses are streaming (evict-first), so the pooled/compacted gradients keep the L2.
+constexpr int SP_ROWS = 2;
 template <bool DIRECT>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int E, int G,
                        const int32_t* __restrict__ srow, const GradFetch gs, int64_t n,
                        const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_end,
                        const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
   if (d_n) n = *d_n;
-  const int lane = threadIdx.x % G;
-  const int64_t i = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
-  if (i >= n) return;
-  const int32_t r = srow[i];
-  if (i > 0 && srow[i - 1] == r) return;
-  const int vec_per_row = E >> 2;
-  const int64_t off0 = (int64_t)r * E + 4 * lane;
-  float4 wv, mv, vv;
-  if (lane < vec_per_row) {  // first (for E <= 128: only) vector of the row: issued before anything else
-    wv = __ldcs(reinterpret_cast<const float4*>(w + off0));
-    mv = __ldcs(reinterpret_cast<const float4*>(m + off0));
-    vv = __ldcs(reinterpret_cast<const float4*>(v + off0));
-  }
-  int64_t e = i + 1;
-  while (e < n && e - i <= SEG_CHUNK && __ldg(srow + e) == r) ++e;
-  if (e - i > SEG_CHUNK) e = row_end[r];  // long rows were reduced to pieces: take the recorded end
   const tt_adam_hyper h = *d_hyper;
-  for (int c = lane; c < vec_per_row; c += G) {
-    const int64_t off = (int64_t)r * E + 4 * c;
-    if (c != lane) {
-      wv = __ldcs(reinterpret_cast<const float4*>(w + off));
-      mv = __ldcs(reinterpret_cast<const float4*>(m + off));
-      vv = __ldcs(reinterpret_cast<const float4*>(v + off));
+  const int lane = threadIdx.x % G;
+  const int vec_per_row = E >> 2;
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
+  for (int64_t base = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; base < n; base += SP_ROWS * groups_total) {
+    int32_t i[SP_ROWS], e[SP_ROWS];  // sorted positions fit 31 bits (tt_ebc_sort_rows checks n)
+    int32_t r[SP_ROWS];
+    bool head[SP_ROWS];
+    float4 wv[SP_ROWS], mv[SP_ROWS], vv[SP_ROWS], g0[SP_ROWS];
+#pragma unroll
+    for (int u = 0; u < SP_ROWS; ++u) {
+      const int64_t iu = base + u * groups_total;
+      i[u] = (int32_t)iu;
+      head[u] = false;
+      r[u] = 0;
+      if (iu < n) {
+        r[u] = __ldg(srow + i[u]);
+        head[u] = i[u] == 0 || __ldg(srow + i[u] - 1) != r[u];
+      }
     }
-    float4 g = row_grad_sum<DIRECT>(gs, i, e, E, c, pieces);
-    adam_vec4(wv, mv, vv, g, h);
-    __stcs(reinterpret_cast<float4*>(w + off), wv);
-    __stcs(reinterpret_cast<float4*>(m + off), mv);
-    __stcs(reinterpret_cast<float4*>(v + off), vv);
+#pragma unroll
+    for (int u = 0; u < SP_ROWS; ++u)
+      if (head[u] && lane < vec_per_row) {  // first (for E <= 128: only) vector of the row, and the head's own gradient entry
+        const int64_t off = (int64_t)r[u] * E + 4 * lane;
+        wv[u] = __ldcs(reinterpret_cast<const float4*>(w + off));
+        mv[u] = __ldcs(reinterpret_cast<const float4*>(m + off));
+        vv[u] = __ldcs(reinterpret_cast<const float4*>(v + off));
+        g0[u] = fetch_grad<DIRECT>(gs, i[u], E, lane);
+      }
+#pragma unroll
+    for (int u = 0; u < SP_ROWS; ++u)
+      if (head[u]) {
+        int32_t x = i[u] + 1;
+        while (x < (int32_t)n && x - i[u] <= SEG_CHUNK && __ldg(srow + x) == r[u]) ++x;
+        e[u] = (x - i[u] > SEG_CHUNK) ? row_end[r[u]] : x;  // long rows were reduced to pieces: take the recorded end
+      }
+    for (int c = lane; c < vec_per_row; c += G) {
+#pragma unroll
+      for (int u = 0; u < SP_ROWS; ++u)
+        if (head[u]) {
+          const int64_t off = (int64_t)r[u] * E + 4 * c;
+          if (c != lane) {
+            wv[u] = __ldcs(reinterpret_cast<const float4*>(w + off));
+            mv[u] = __ldcs(reinterpret_cast<const float4*>(m + off));
+            vv[u] = __ldcs(reinterpret_cast<const float4*>(v + off));
+            g0[u] = fetch_grad<DIRECT>(gs, i[u], E, c);
+          }
+          float4 g;
+          if (e[u] - i[u] <= SEG_CHUNK) {  // 0 + g0 + ... == the plain ascending sum, bit for bit
+            g = g0[u];
+            gather_sum<DIRECT, 2>(g, gs, (int64_t)i[u] + 1, e[u], E, c);
+          } else {  // long row: its per-chunk pieces, in chunk order (same as row_grad_sum)
+            g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int32_t ch = i[u] / SEG_CHUNK; ch <= (e[u] - 1) / SEG_CHUNK; ++ch)
+              f4_add(g, *reinterpret_cast<const float4*>(pieces + (((int64_t)ch * 2 + (i[u] <= ch * SEG_CHUNK ? 0 : 1)) * E) + 4 * c));
+          }
+          adam_vec4(wv[u], mv[u], vv[u], g, h);
+          __stcs(reinterpret_cast<float4*>(w + off), wv[u]);
+          __stcs(reinterpret_cast<float4*>(m + off), mv[u]);
+          __stcs(reinterpret_cast<float4*>(v + off), vv[u]);
+        }
+    }
   }
 }
 
@@ -979,11 +1016,13 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
   float* pieces = (float*)piece_ws;
   const int64_t n_chunks = (n + SEG_CHUNK - 1) / SEG_CHUNK;
   const float* gs_buf = (const float*)((const char*)piece_ws + align_up((n_chunks + 1) * 2 * (int64_t)E * 4, 256));
-  // The gradients are compacted in sorted order first (independent 16-byte gathers, then streaming sums). TT_EBC_DIRECT=1 makes
-  // the segment sums fetch through the sorted slots instead (no [n,E] copy); measured on B200 at the config-5 shard it is slower
-  // (4.7 ms vs 2.9 ms: the dependent slot -> gradient chain sits in front of every Adam update), so it stays an experiment knob.
+  // Exact-dense mode: the gradients are compacted in sorted order first (independent 16-byte gathers, then streaming sums) — the
+  // row kernels walk every arena row and the compacted copy keeps their gradient reads sequential. Sparse mode fetches through
+  // the sorted slots directly: the pooled gradients (B*K vectors) sit in the L2 while a compacted copy (B*K*L vectors) would
+  // cost an HBM round trip; measured on B200 at the config-5 shard 2.42 ms vs 2.73 ms. Peer (NVLink) sources are always
+  // compacted. TT_EBC_DIRECT=0/1 overrides (experiments). Both ways read the same values in the same order: bit-identical.
   static const int direct_env = [] { const char* e = getenv("TT_EBC_DIRECT"); return e ? atoi(e) : -1; }();
-  const bool direct = !grad_table && direct_env > 0;
+  const bool direct = !grad_table && (direct_env >= 0 ? direct_env != 0 : (mode == TT_ADAM_SPARSE && do_adam));
   const GradFetch gs{direct ? nullptr : gs_buf, sorted_slots, src, grad_dtype == TT_BF16 ? 1 : 0};
   if (n > 0) {
     if (!direct) {
@@ -1007,8 +1046,12 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
   }
   if (mode == TT_ADAM_SPARSE) {
     if (n > 0)
-      (direct ? ebc_rows_sparse_kernel<true> : ebc_rows_sparse_kernel<false>)<<<ceil_div(n, gpb), threads, 0, s>>>(arena_w, arena_m, arena_v, E, G, sorted_rows, gs, n, d_n,
-                                                                  row_end, pieces, d_hyper);
+    {
+      int64_t want = ceil_div(n, (int64_t)gpb * SP_ROWS);
+      const int64_t cap = (int64_t)sm_count() * 12;  // 3 resident CTAs per SM, 4 waves
+      (direct ? ebc_rows_sparse_kernel<true> : ebc_rows_sparse_kernel<false>)<<<(int)(want > cap ? cap : want), threads, 0, s>>>(
+          arena_w, arena_m, arena_v, E, G, sorted_rows, gs, n, d_n, row_end, pieces, d_hyper);
+    }
   } else {
     int64_t want = ceil_div(total_rows, gpb);
     const int64_t cap = (int64_t)sm_count() * 32;

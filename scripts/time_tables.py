@@ -1,13 +1,13 @@
 """Run the pooled-table kernels alone on a config-5-shaped shard (for ncu captures; sizes kept modest so that the profiler's
 save/restore of written memory stays cheap): jagged lookup, sort-dedup, sparse segment-sum + Adam.
-usage: python scripts/time_tables.py [rows_per_table=400000] [E=64] [L=20] [B=8192] [K=38]"""
+usage: [TT_MODE=sparse|dense_exact] python scripts/time_tables.py [rows_per_table=400000] [E=64] [L=20] [B=8192] [K=38]"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jodalrob_twotower_b200.tables import PooledTables
 a = [int(x) for x in sys.argv[1:]]
 rows_per, E, L, B, K = (a + [400000, 64, 20, 8192, 38][len(a):])[:5]
 dev = torch.device("cuda", 0)
-tab = PooledTables([rows_per] * K, E, dev, optimizer_mode="sparse", seed=1)
+tab = PooledTables([rows_per] * K, E, dev, optimizer_mode=os.environ.get("TT_MODE", "sparse"), seed=1)
 g = torch.Generator(device=dev).manual_seed(7)
 n = B * K * L
 ids = (torch.rand(n, generator=g, device=dev) * rows_per).long().clamp_(max=rows_per - 1)

@@ -222,8 +222,11 @@ def test_fused_step_matches_reference_golden(case):
 @pytest.mark.parametrize("mode", ["autograd", "fused"])
 def test_cosine_embedding_loss_trajectory_vs_reference_golden(mode):
     """loss_type="cosine_embedding" (two_tower_train_task.py:136-158). The loss only counts signs of the
-    similarities and its gradient is rounding noise (~1e-8 in the reference itself), so: losses/metrics/S to fp32 tolerance,
-    gradients noise-level on both sides, and the weight-decay-driven 3-step trajectory to 1e-4 (Adam amplifies the noise)."""
+    similarities and its gradient is rounding noise (~1e-8 in the reference itself). Adam normalises that noise: every
+    zero-initialised parameter (biases, BN beta) moves by +-lr per step with the SIGN OF THE NOISE, so the reference trajectory
+    is not reproducible beyond the first step by any other implementation (nor by the reference on other hardware). Hence:
+    step 0 (same weights) to fp32 tolerance, gradients noise-level on both sides, later steps and the final weights inside the
+    envelope Adam allows (|dw| <= sum of the learning rates)."""
     import jodalrob_twotower_b200 as tt
     d, cfg = load_golden("tiny_cosine.npz")
     assert cfg["loss_type"] == "cosine_embedding"
@@ -237,24 +240,31 @@ def test_cosine_embedding_loss_trajectory_vs_reference_golden(mode):
         opt = tt.FusedAdam(task, lr=cfg["lr"], weight_decay=cfg["weight_decay"])
         sched = tt.FusedWarmupScheduler(opt, w)
     task.train()
+    lr_sum = 0.0
     for i in range(3):
         nid, cid, nd, cd = batch_inputs(d, i)
         opt.zero_grad()
         out = task(make_batch(cfg["schema"], nid, cid, nd, cd), return_metrics=True)
         out["loss"].backward()
-        assert abs(out["loss"].item() - float(d[f"s{i}.loss"])) <= 1e-6
-        for m in ("accuracy", "positive_similarity_mean", "negative_similarity_mean", "similarity_gap"):
-            assert abs(out[m].item() - float(d[f"s{i}.{m}"])) < 2e-6, m
-        assert rel_err(out["similarity_matrix"].cpu(), torch.from_numpy(d[f"s{i}.similarity_matrix"])) < FP32_RTOL
-        if i == 0 and mode == "autograd":
-            for name, p in task.named_parameters():
-                assert float(p.grad.abs().max()) < 1e-6 and float(np.abs(d[f"grad0.{name}"]).max()) < 1e-6, name
+        tol_l, tol_m, tol_s = (1e-6, 2e-6, FP32_RTOL) if i == 0 else (0.05, 5e-3, 2e-2)
+        assert abs(out["loss"].item() - float(d[f"s{i}.loss"])) <= tol_l, i
+        for m in ("positive_similarity_mean", "negative_similarity_mean", "similarity_gap"):
+            assert abs(out[m].item() - float(d[f"s{i}.{m}"])) < tol_m, (i, m)
+        assert rel_err(out["similarity_matrix"].cpu(), torch.from_numpy(d[f"s{i}.similarity_matrix"])) < tol_s, i
+        if i == 0:
+            assert abs(out["accuracy"].item() - float(d["s0.accuracy"])) < 2e-6
+            if mode == "autograd":
+                for name, p in task.named_parameters():
+                    assert float(p.grad.abs().max()) < 1e-6 and float(np.abs(d[f"grad0.{name}"]).max()) < 1e-6, name
+        lr_sum += float(d[f"s{i}.lr"])
         opt.step()
         sched.step()
-    fin = sd_from(d, "final.")
+    fin, init = sd_from(d, "final."), sd_from(d, "init.")
     for k, v in task.state_dict().items():
-        if v.is_floating_point():
-            assert rel_err(v.cpu(), fin[k]) < 1e-4, k
+        if v.is_floating_point() and "running_" not in k:
+            assert float((v.cpu() - fin[k]).abs().max()) <= 2.2 * lr_sum, k       # both within lr_sum of the initial weights
+            assert float((v.cpu() - init[k]).abs().max()) <= 1.1 * lr_sum, k
+            assert float((v.cpu() - init[k]).abs().max()) > 0.0, k               # ... and it did train (weight decay + noise)
     task.eval()
     with torch.no_grad():
         ev = task(make_batch(cfg["schema"], *batch_inputs(d, 0)), return_metrics=True)
