@@ -398,6 +398,62 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = world * B * args.steps / (float(e2e_ms.item()) * 1e-3)
 
+    # ---- end to end with HBM-resident feature stores: the reference's Dataset yields row indices and
+    # collates on the CPU; here only the two index vectors cross PCIe, the batch is gathered on the GPU straight into the
+    # captured step's input buffers (tt_batch_gather), then step + D2H of the result, every step. ----
+    e2e_store = None
+    if gstep is not None and not args.no_device_store:
+        from jodalrob_twotower_b200.loader import DeviceFeatureStore, GpuBatchAssembler
+        n_notice, n_company = 1_000_000, 500_000
+        gdev = torch.Generator(device=dev).manual_seed(99 + rank)
+        mk_store = lambda n, d, sch: DeviceFeatureStore(
+            torch.randn(n, d, generator=gdev, device=dev),
+            torch.stack([torch.randint(0, v, (n,), generator=gdev, device=dev) for _, v in sch], 1), [k for k, _ in sch], dev)
+        asm = GpuBatchAssembler(mk_store(n_notice, MODEL["notice_dense"], schema["notice"]),
+                                mk_store(n_company, MODEL["company_dense"], schema["company"]))
+        idx_pin = [torch.stack([torch.randint(0, n_notice, (B,), generator=gen), torch.randint(0, n_company, (B,), generator=gen)]).pin_memory()
+                   for _ in range(N_ROTATE)]
+        idx_stage = [torch.empty(2, B, dtype=torch.int64, device=dev) for _ in range(2)]
+
+        def store_loop(n):
+            main = torch.cuda.current_stream(dev)
+            with torch.cuda.stream(copy_stream):
+                idx_stage[0].copy_(idx_pin[0], non_blocking=True)
+                ready[0].record(copy_stream)
+            for i in range(n):
+                cur, nxt = i % 2, (i + 1) % 2
+                if i + 1 < n:
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(freed[nxt])
+                        idx_stage[nxt].copy_(idx_pin[(i + 1) % N_ROTATE], non_blocking=True)
+                        ready[nxt].record(copy_stream)
+                main.wait_event(ready[cur])
+                asm.assemble_into(gstep, idx_stage[cur][0], idx_stage[cur][1])
+                freed[cur].record(main)
+                res = gstep()
+                out_host.copy_(res, non_blocking=True)
+                main.synchronize()
+            return float(out_host[0])
+
+        store_loop(3)
+        barrier()
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record(torch.cuda.current_stream(dev))
+        store_loop(args.steps)
+        es1.record(torch.cuda.current_stream(dev))
+        barrier()
+        asm.check()
+        es_ms = torch.tensor([es0.elapsed_time(es1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(es_ms, op=dist.ReduceOp.MAX)
+        e2e_store = {"value": world * B * args.steps / (float(es_ms.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * B,
+                     "d2h_bytes_per_step": 20, "gather_launches_per_step": 2,
+                     "store": f"{n_notice:,} notice rows + {n_company:,} company rows resident in HBM "
+                              f"({(asm.notice.nbytes() + asm.company.nbytes()) / 1e9:.2f} GB, fp32 dense + int64 ids), uniform row indices"}
+        del asm
+        torch.cuda.empty_cache()
+
     # ---- per-kernel device times (eager launches bracketed by CUDA events on the launching stream) ----
     kern = {}
     if rank == 0 or world > 1:
@@ -438,8 +494,9 @@ def run_ours(args):
         if "flops" in a:
             ach = a["flops"] / per_call_s / 1e12
             traffic = None
-            prof = os.path.join(ROOT, "profiles", "r01_ncu_simce_bwd.json")
-            if top["call"].startswith("tt_simce_backward") and os.path.isfile(prof) and B == 8192:
+            prof = os.path.join(ROOT, "profiles", "r01_ncu_simce_bwd.json" if top["call"].startswith("tt_simce_backward")
+                                else "r01_ncu_simce_fwd.json")
+            if os.path.isfile(prof) and B == 8192 and world == 1:
                 with open(prof) as f:
                     traffic = json.load(f)["dram_bytes_per_launch"]  # dram read+write of one launch, ncu --set full capture
             sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
@@ -477,6 +534,7 @@ def run_ours(args):
                        "cuda_graph": bool(use_graph)},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 20},
+            "e2e_device_store": e2e_store,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "roofline": roofline, "cpu_baseline": cpu, "tables": tables, "kernels": table, "loss_last": loss_last}
     print(json.dumps(line), flush=True)
@@ -503,6 +561,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tables-only", nargs="?", const="full", default=None, choices=["full", "quick"])
+    ap.add_argument("--no-device-store", action="store_true", help="skip the end-to-end loop with HBM-resident feature stores")
     ap.add_argument("--no-tables", action="store_true", help="skip the large-table (HBM-bound lookup/update) section")
     args = ap.parse_args()
     if args.tables_only:  # development aid: only the large-table section (not the contract line)

@@ -37,6 +37,9 @@ extern "C" {
 /* element types of activations / gradients */
 #define TT_F32 0
 #define TT_BF16 1
+#define TT_F16 2 /* feature stores only (tt_batch_gather) */
+#define TT_I64 3
+#define TT_I32 4
 
 /* KeyedJaggedTensor value order.  The reference builds SAMPLE-major values ([B,K] flattened,
  * src/towers/pairs/unified_bid_data_loader.py:827-841) and decodes values[b*K+k]
@@ -326,6 +329,22 @@ int tt_eval_ranks(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t 
 int tt_eval_ranks_from_matrix(const float* S, int64_t Bx, int64_t By, int64_t lds, int64_t diag_offset, int32_t* rank,
                               tt_stream_t stream);
 int tt_eval_rank_metrics(const int32_t* rank, int64_t B, const int32_t* d_ks, int32_t nk, float* out, tt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * On-GPU batch assembly from HBM-resident feature stores.  Replaces the CPU collate
+ * (create_collate_fn, src/towers/pairs/unified_bid_data_loader.py:630-684: numpy fancy-indexing of
+ * dataset.*_store['dense_projected'|'categorical'] by the batch's row indices), _build_batch_kjt (:827-841: [B,K] ids
+ * flattened sample-major into the KJT values) and the H2D copy of the batch (scripts/train.py:261-273) for one tower:
+ *   dense_out[b, 0:D]       = float(dense_store[idx[b], 0:D])          dense_store [n_rows, dense_ld] f32|bf16|f16
+ *   values_out[slot(b,k)]   = int64(cat_store[idx[b], k])              cat_store   [n_rows, cat_ld]   i64|i32
+ * slot(b,k) = b*K+k (TT_LAYOUT_SAMPLE_MAJOR, the reference's order) or k*B+b. Either output may be NULL. The outputs can be the
+ * static input buffers of a captured train step, so only idx (8 bytes per sample and tower) crosses PCIe. The store must be
+ * 16-byte aligned with dense_ld % 4 == 0; 128-bit stores are used when dense_out is 16-byte aligned with out_ld % 4 == 0.
+ * An index outside [0, n_rows) yields zeros / id 0 and adds 1 to *d_err (device int32, may be NULL; the reference raises
+ * IndexError at this point, the host-side wrapper turns a non-zero *d_err into the same exception). */
+int tt_batch_gather(const void* dense_store, int32_t dense_dtype, int64_t dense_ld, int32_t D, const void* cat_store,
+                    int32_t cat_dtype, int64_t cat_ld, int32_t K, int64_t n_rows, const int64_t* idx, int32_t B, float* dense_out,
+                    int64_t out_ld, int64_t* values_out, int32_t layout, int32_t* d_err, tt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -200,10 +200,53 @@ def eval_case():
     print("eval_metrics:", {k: float(v) for k, v in out.items() if "recall@5" in k or "mrr" in k})
 
 
+def collate_case():
+    """Batch produced by the UNMODIFIED reference collate (create_collate_fn, unified_bid_data_loader.py:630-684, with its
+    _build_batch_kjt :827-841) on small synthetic feature stores. sqlalchemy & co. are stubbed: the function only touches
+    dataset.notice_store / company_store / schema.*.categorical."""
+    import sys
+    import types
+    rh.install_shims()
+    for name in ("sqlalchemy", "sqlalchemy.engine", "psycopg", "psycopg2", "tensorflow", "sentence_transformers"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["sqlalchemy.engine"].Engine = object
+    sys.modules["sqlalchemy"].engine = sys.modules["sqlalchemy.engine"]
+    sys.modules["sqlalchemy"].create_engine = lambda *a, **k: None
+    sys.modules["sqlalchemy"].text = lambda q: q
+    from src.towers.pairs import unified_bid_data_loader as L
+    rng = np.random.default_rng(5)
+    nk = ["n_a", "n_b", "n_c", "n_d", "n_e"]
+    ck = ["c_a", "c_b"]
+    N, M, B = 97, 41, 19
+    ds = types.SimpleNamespace(
+        notice_store={"dense_projected": rng.standard_normal((N, 12)).astype(np.float32),
+                      "categorical": rng.integers(-2, 500, (N, len(nk))).astype(np.int64)},
+        company_store={"dense_projected": rng.standard_normal((M, 6)).astype(np.float32),
+                       "categorical": rng.integers(0, 90, (M, len(ck))).astype(np.int64)},
+        schema=types.SimpleNamespace(notice=types.SimpleNamespace(categorical=nk), company=types.SimpleNamespace(categorical=ck)))
+    items = [{"notice_idx": int(rng.integers(0, N)), "company_idx": int(rng.integers(0, M)), "pair_info": {}} for _ in range(B)]
+    batch = L.create_collate_fn(ds)(items)
+    out = {"notice_store.dense": ds.notice_store["dense_projected"], "notice_store.cat": ds.notice_store["categorical"],
+           "company_store.dense": ds.company_store["dense_projected"], "company_store.cat": ds.company_store["categorical"],
+           "notice_idx": np.array([i["notice_idx"] for i in items], dtype=np.int64),
+           "company_idx": np.array([i["company_idx"] for i in items], dtype=np.int64)}
+    for t in ("notice", "company"):
+        out[f"batch.{t}.dense"] = batch[t]["dense"].numpy().copy()
+        out[f"batch.{t}.values"] = batch[t]["kjt"].values().numpy().copy()
+        out[f"batch.{t}.lengths"] = batch[t]["kjt"].lengths().numpy().copy()
+        out[f"batch.{t}.keys_json"] = np.frombuffer(json.dumps(list(batch[t]["kjt"].keys())).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(GOLD, "collate_batch.npz"), **out)
+    print("collate_batch:", {k: v.shape for k, v in out.items() if k.startswith("batch.") and "json" not in k})
+
+
 def main():
     import sys
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order → reproducible fixtures
+    if "collate" in sys.argv[1:] or len(sys.argv) == 1:
+        collate_case()
+        if len(sys.argv) > 1 and not {"cosine", "eval"} & set(sys.argv[1:]):
+            return
     if "eval" in sys.argv[1:] or len(sys.argv) == 1:
         eval_case()
         if len(sys.argv) > 1 and "cosine" not in sys.argv[1:]:

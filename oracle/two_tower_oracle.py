@@ -354,3 +354,17 @@ def recall_at_k(S: np.ndarray, k: int) -> float:
 def mrr(S: np.ndarray) -> float:
     """evaluator.py:45-71: mean of 1/(rank+1) (python floats, then a float32 tensor mean)."""
     return float(np.mean((1.0 / (positive_ranks(S).astype(np.float64) + 1.0)).astype(np.float32)))
+
+
+# ----------------------------------------------------------------------------- batch assembly (collate)
+def collate_batch(notice_store: dict, company_store: dict, notice_idx, company_idx) -> dict:
+    """create_collate_fn + _build_batch_kjt (unified_bid_data_loader.py:630-684,827-841) restated with numpy:
+    dense = store['dense_projected'][idx] as float32, values = store['categorical'][idx] flattened SAMPLE-major as int64,
+    lengths = ones. numpy raises IndexError for an out-of-range index, like the reference."""
+    out = {}
+    for name, st, idx in (("notice", notice_store, notice_idx), ("company", company_store, company_idx)):
+        idx = np.asarray(idx, dtype=np.int64)
+        cat = np.asarray(st["categorical"])[idx]
+        out[name] = {"dense": np.asarray(st["dense_projected"])[idx].astype(np.float32),
+                     "values": cat.reshape(-1).astype(np.int64), "lengths": np.ones(cat.size, dtype=np.int64)}
+    return out

@@ -182,3 +182,20 @@ def test_retrieval_metric_oracle_matches_reference_evaluator(name):
     assert abs(orc.mrr(S) - float(z[f"{name}.mrr"])) < 1e-6
     cm = json.loads(bytes(z[f"{name}.comprehensive_json"]).decode())
     assert abs(cm["recall@10"] - orc.recall_at_k(S, 10)) < 1e-7 and cm["batch_size"] == S.shape[0]
+
+
+def test_collate_oracle_matches_reference_collate_fn():
+    """oracle collate_batch vs the batch the unmodified reference create_collate_fn produced (tests/golden/collate_batch.npz)."""
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "collate_batch.npz"))
+    got = orc.collate_batch({"dense_projected": z["notice_store.dense"], "categorical": z["notice_store.cat"]},
+                            {"dense_projected": z["company_store.dense"], "categorical": z["company_store.cat"]},
+                            z["notice_idx"], z["company_idx"])
+    for t in ("notice", "company"):
+        assert np.array_equal(got[t]["dense"], z[f"batch.{t}.dense"])
+        assert np.array_equal(got[t]["values"], z[f"batch.{t}.values"]) and got[t]["values"].dtype == np.int64
+        assert np.array_equal(got[t]["lengths"], z[f"batch.{t}.lengths"])
+    with pytest.raises(IndexError):
+        orc.collate_batch({"dense_projected": z["notice_store.dense"], "categorical": z["notice_store.cat"]},
+                          {"dense_projected": z["company_store.dense"], "categorical": z["company_store.cat"]}, [10 ** 6], [0])
