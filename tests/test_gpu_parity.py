@@ -742,6 +742,77 @@ def test_sharded_multirank_step_matches_single_device_reference(case, world):
                 assert torch.equal(v.cpu(), fin[k]), (r, k)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_large_vocab_step_vs_port(world):
+    """BASELINE config 3 in miniature: tables far larger than the batch (150 k / 90 k / 70 k rows: multi-pass radix keys, mostly
+    untouched rows), row-wise sharded over emulated ranks next to replicated small tables; Zipf-like ids with out-of-range values.
+    Oracle: oracle/ref_port.py (pinned bit-exactly to the reference) on the concatenated global batch, two Adam steps."""
+    import threading
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200 import dist as ttd
+    schema = {"notice": [["a", 150_000], ["b", 40], ["c", 70_000], ["d", 9]], "company": [["x", 90_000], ["y", 12]]}
+    model = dict(emb_dim=16, notice_dense=24, company_dense=12, hidden=[32, 16], final_dim=16, dropout=0.0, temperature=0.5,
+                 label_smoothing=0.0)
+    nk, ck = [k for k, _ in schema["notice"]], [k for k, _ in schema["company"]]
+    port = ref_port.build_port_task(schema, model["emb_dim"], model["notice_dense"], model["company_dense"], model["hidden"],
+                                    model["final_dim"], 0.0, model["temperature"], seed=3)
+    init = {k: v.clone() for k, v in port.state_dict().items()}
+    B = 512
+    Bl = B // world
+    g = torch.Generator().manual_seed(77)
+
+    def ids(vocab):
+        cols = []
+        for _, v in vocab:
+            u = torch.rand(B, generator=g)
+            col = (u.pow(3) * v).long()  # skewed towards small ids: repeated rows inside a batch
+            col[torch.rand(B, generator=g) < 0.02] = v + 5  # out of range -> clamped to V-1
+            col[torch.rand(B, generator=g) < 0.02] = -1     # -> 0
+            cols.append(col)
+        return torch.stack(cols, 1)
+
+    batches = [(ids(schema["notice"]), ids(schema["company"]), torch.randn(B, 24, generator=g), torch.randn(B, 12, generator=g))
+               for _ in range(2)]
+    tr = ref_port.PortTrainer(port, 1e-3, 1e-5, 0)
+    ref_losses = [float(tr.step(ref_port.make_port_batch(schema, *b))["loss"]) for b in batches]
+    fin = port.state_dict()
+    tw = ttd.ThreadWorld(world)
+    tt.native.lib()
+    results, errors = [None] * world, []
+
+    def rank_main(r):
+        try:
+            torch.cuda.set_device(0)
+            task = ttd.create_distributed_train_task(nk, ck, schema, model, DEV, comm=ttd.ThreadComm(tw, r), dtype="fp32")
+            ttd.load_reference_state_dict(task, init)
+            tt.FusedAdam(task, lr=1e-3, weight_decay=1e-5, warmup_steps=0)
+            task.train()
+            sl = slice(r * Bl, (r + 1) * Bl)
+            losses = [task.fused_step(make_batch(schema, b[0][sl], b[1][sl], b[2][sl], b[3][sl])).clone() for b in batches]
+            results[r] = (losses, ttd.gather_reference_state_dict(task), sum(task.engine.KL))
+        except Exception:
+            import traceback
+            errors.append(traceback.format_exc())
+            try:
+                tw.bar.abort()
+            except Exception:
+                pass
+
+    ths = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=300)
+    assert not errors, errors[0]
+    assert results[0][2] == 3  # a, c, x go through the sharded sort-dedup path; b, d, y are replicated small tables
+    for r, (losses, sd, _) in enumerate(results):
+        for i in range(2):
+            assert abs(losses[i][0].item() - ref_losses[i]) <= FP32_RTOL * abs(ref_losses[i]) + 1e-6, (r, i)
+        for k, v in sd.items():
+            if v.is_floating_point():
+                assert_updated_close(v.cpu(), fin[k], None, 2e-5, name=f"rank{r}.{k}")
+
+
 def test_shard_routing_bit_exact_vs_oracle():
     import jodalrob_twotower_b200 as tt
     from jodalrob_twotower_b200.native import ptr
