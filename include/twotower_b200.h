@@ -50,6 +50,9 @@ extern "C" {
 /* optimizer row-update modes of tt_ebc_backward_adam */
 #define TT_ADAM_DENSE_EXACT 0 /* every arena row every step == torch.optim.Adam (scripts/train.py:231) */
 #define TT_ADAM_SPARSE 1      /* only rows touched by the batch (TorchRec/SparseAdam-style; NOT the reference semantics) */
+#define TT_ADAM_DENSE_UNTOUCHED 2 /* only rows the batch does NOT touch (g = wd*w): first half of a split exact-dense step. It
+                                   * needs the stamps of tt_ebc_sort_rows but no gradients, so it can run underneath the towers;
+                                   * TT_ADAM_SPARSE on the same sort then completes the step, bit-identical to TT_ADAM_DENSE_EXACT */
 
 typedef void* tt_stream_t; /* cudaStream_t */
 

@@ -41,23 +41,28 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
   }
   __syncthreads();
   const int lane = threadIdx.x % G;
-  const int64_t n_bags = (int64_t)B * K;
-  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
-  const int64_t group0 = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+  // 32-bit slot arithmetic (the host checks B*K < 2^31): a 64-bit division by K is a long instruction sequence per bag
+  const int n_bags = B * K;
+  const int groups_total = gridDim.x * (blockDim.x / G);
+  const int group0 = blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
   const int K_out = large_rank ? K_large : K;
   const int vec_per_row = E >> 2;
-  for (int64_t base = group0; base < n_bags; base += groups_total * UNROLL) {
+  for (int64_t base = group0; base < n_bags; base += (int64_t)groups_total * UNROLL) {
     int64_t row[UNROLL];
-    int64_t slot[UNROLL];
+    int bb[UNROLL], kk[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      slot[u] = base + (int64_t)u * groups_total;
+      const int64_t s64 = base + (int64_t)u * groups_total;
       row[u] = -1;
-      if (slot[u] < n_bags) {
-        const int b = (int)(slot[u] / K), k = (int)(slot[u] - (int64_t)b * K);
+      bb[u] = kk[u] = 0;
+      if (s64 < n_bags) {
+        const int slot = (int)s64;
+        const int b = slot / K, k = slot - b * K;
+        bb[u] = b;
+        kk[u] = k;
         const int64_t hi = (int64_t)s_vocab[k] - 1;
         if (hi >= 0) {  // vocab <= 0 marks a key this launch must skip (tables served by another path)
-          const int64_t vi = layout == TT_LAYOUT_SAMPLE_MAJOR ? slot[u] : (int64_t)k * B + b;
+          const int64_t vi = layout == TT_LAYOUT_SAMPLE_MAJOR ? (int64_t)slot : (int64_t)k * B + b;
           int64_t id = __ldg(values + vi);
           id = id < 0 ? 0 : (id > hi ? hi : id);  // clamp(id, 0, V_k-1)
           row[u] = s_base[k] + id;
@@ -77,10 +82,7 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
         if (row[u] >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(arena + row[u] * E) + c);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
-        if (row[u] >= 0) {
-          const int b = (int)(slot[u] / K), k = (int)(slot[u] - (int64_t)b * K);
-          store_vec4<OutT>(out + (int64_t)b * out_ld + out_col0 + (int64_t)k * E + 4 * c, v[u]);
-        }
+        if (row[u] >= 0) store_vec4<OutT>(out + (int64_t)bb[u] * out_ld + out_col0 + (int64_t)kk[u] * E + 4 * c, v[u]);
     }
   }
 }
@@ -161,12 +163,17 @@ static int lanes_per_row(int E) {
 // stable LSD radix sort (8-bit digits) of (row, slot) pairs by row
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys per block
+// keys per thread: 8 (2048-key tiles) for large sorts; 2 (512-key tiles) below 2^19 pairs — the reference-sized step sorts 65 k
+// pairs, which is 32 long-lived CTAs at 8 keys per thread: four times as many short-lived ones finish the latency-bound chain
+// sooner and do not block SMs that the persistent sim-CE kernel is waiting for
+constexpr int RS_ITEMS_BIG = 8, RS_ITEMS_SMALL = 2;
+static inline int rs_items_for(int64_t n) { return n < ((int64_t)1 << 19) ? RS_ITEMS_SMALL : RS_ITEMS_BIG; }
 
+template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
 radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ d_n, int shift,
                   int32_t* __restrict__ hist, int n_tiles) {
+  constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
   __shared__ int32_t s_hist[256];
   if (d_n) {  // device-side count (sharded tables): the launch covers the capacity, the work and the histogram pitch follow n
     n = *d_n;
@@ -188,7 +195,7 @@ radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, const int32_t* __
 // exclusive scan of `len` int32 counters in place, one block, the counters staged in shared memory (coalesced global traffic);
 // len <= ~40k entries (the reference-sized step)
 __global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __restrict__ data, int len, int per,
-                                                                   const int32_t* __restrict__ d_n) {
+                                                                   const int32_t* __restrict__ d_n, int RS_TILE) {
   extern __shared__ int32_t sh[];
   __shared__ int32_t s_part[1024];
   const int t = threadIdx.x;
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __re
 constexpr int SCAN_PER = 8;
 constexpr int SCAN_CHUNK = 1024 * SCAN_PER;
 
-__device__ __forceinline__ int64_t scan_len(int64_t len, const int32_t* __restrict__ d_n) {
+__device__ __forceinline__ int64_t scan_len(int64_t len, const int32_t* __restrict__ d_n, int RS_TILE) {
   return d_n ? 256 * (int64_t)(*d_n > 0 ? (*d_n + RS_TILE - 1) / RS_TILE : 1) : len;
 }
 
@@ -255,9 +262,9 @@ __device__ __forceinline__ int32_t block_scan_1024(int32_t x, int32_t* s_warp, i
 }
 
 __global__ void __launch_bounds__(1024)
-scan_chunk_totals_kernel(const int32_t* __restrict__ data, int64_t len, const int32_t* __restrict__ d_n, int32_t* __restrict__ totals) {
+scan_chunk_totals_kernel(const int32_t* __restrict__ data, int64_t len, const int32_t* __restrict__ d_n, int32_t* __restrict__ totals, int tile) {
   __shared__ int32_t s_warp[32];
-  len = scan_len(len, d_n);
+  len = scan_len(len, d_n, tile);
   const int64_t lo = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER;
   int32_t sum = 0;
   if (lo + SCAN_PER <= len) {
@@ -272,9 +279,9 @@ scan_chunk_totals_kernel(const int32_t* __restrict__ data, int64_t len, const in
 }
 
 __global__ void __launch_bounds__(1024)
-scan_totals_kernel(int32_t* __restrict__ totals, int64_t len, const int32_t* __restrict__ d_n) {
+scan_totals_kernel(int32_t* __restrict__ totals, int64_t len, const int32_t* __restrict__ d_n, int tile) {
   __shared__ int32_t s_warp[32];
-  len = scan_len(len, d_n);
+  len = scan_len(len, d_n, tile);
   const int nb = (int)((len + SCAN_CHUNK - 1) / SCAN_CHUNK);
   const int per = (nb + 1023) / 1024;
   const int lo = threadIdx.x * per, hi = lo + per < nb ? lo + per : nb;
@@ -289,9 +296,9 @@ scan_totals_kernel(int32_t* __restrict__ totals, int64_t len, const int32_t* __r
 }
 
 __global__ void __launch_bounds__(1024)
-scan_chunk_apply_kernel(int32_t* __restrict__ data, int64_t len, const int32_t* __restrict__ d_n, const int32_t* __restrict__ totals) {
+scan_chunk_apply_kernel(int32_t* __restrict__ data, int64_t len, const int32_t* __restrict__ d_n, const int32_t* __restrict__ totals, int tile) {
   __shared__ int32_t s_warp[32];
-  len = scan_len(len, d_n);
+  len = scan_len(len, d_n, tile);
   const int64_t lo = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER;
   int32_t v[SCAN_PER];
   const bool full = lo + SCAN_PER <= len;
@@ -322,25 +329,27 @@ scan_chunk_apply_kernel(int32_t* __restrict__ data, int64_t len, const int32_t* 
   }
 }
 
-static int launch_scan(int32_t* data, int64_t len, const int32_t* d_n, int32_t* totals, cudaStream_t s) {
+static int launch_scan(int32_t* data, int64_t len, const int32_t* d_n, int32_t* totals, int tile, cudaStream_t s) {
   const int per = (int)((len + 1023) / 1024);
   const size_t smem = (size_t)1024 * (per | 1) * 4;
   if (smem <= 160 * 1024) {
     TT_CUDA(cudaFuncSetAttribute(scan_exclusive_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    scan_exclusive_smem_kernel<<<1, 1024, smem, s>>>(data, (int)len, per, d_n);
+    scan_exclusive_smem_kernel<<<1, 1024, smem, s>>>(data, (int)len, per, d_n, tile);
   } else {
     const int nb = (int)((len + SCAN_CHUNK - 1) / SCAN_CHUNK);
-    scan_chunk_totals_kernel<<<nb, 1024, 0, s>>>(data, len, d_n, totals);
-    scan_totals_kernel<<<1, 1024, 0, s>>>(totals, len, d_n);
-    scan_chunk_apply_kernel<<<nb, 1024, 0, s>>>(data, len, d_n, totals);
+    scan_chunk_totals_kernel<<<nb, 1024, 0, s>>>(data, len, d_n, totals, tile);
+    scan_totals_kernel<<<1, 1024, 0, s>>>(totals, len, d_n, tile);
+    scan_chunk_apply_kernel<<<nb, 1024, 0, s>>>(data, len, d_n, totals, tile);
   }
   return TT_OK;
 }
 
+template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n,
                      const int32_t* __restrict__ d_n, int shift, const int32_t* __restrict__ hist_scanned, int n_tiles,
                      int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
+  constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
   if (d_n) {
     n = *d_n;
     n_tiles = n > 0 ? (int)((n + RS_TILE - 1) / RS_TILE) : 1;
@@ -604,7 +613,7 @@ ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __res
                       int64_t total_rows, int E, int G, const GradFetch gs,
                       const int32_t* __restrict__ row_begin, const int32_t* __restrict__ row_end,
                       const int32_t* __restrict__ row_stamp, int32_t stamp, const int64_t* __restrict__ d_stamp,
-                      const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
+                      const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper, int untouched_only) {
   if (d_stamp) stamp += (int32_t)(*d_stamp);
   tt_adam_hyper h;
   if (DO_ADAM) h = *d_hyper;
@@ -613,6 +622,7 @@ ebc_rows_dense_kernel(float* __restrict__ w, float* __restrict__ m, float* __res
   const int vec_per_row = E >> 2;
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; r < total_rows; r += groups_total) {
     const bool hit = row_stamp[r] == stamp;
+    if (untouched_only && hit) continue;  // the touched rows are updated later, once their gradients exist
     int64_t b = 0, e = 0;
     if (hit) {
       b = row_begin[r];
@@ -749,7 +759,7 @@ ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __re
           float4 g;
           if (e[u] - i[u] <= SEG_CHUNK) {  // 0 + g0 + ... == the plain ascending sum, bit for bit
             g = g0[u];
-            gather_sum<DIRECT, 2>(g, gs, (int64_t)i[u] + 1, e[u], E, c);
+            gather_sum<DIRECT, DIRECT ? 2 : 8>(g, gs, (int64_t)i[u] + 1, e[u], E, c);  // compacted: a contiguous stream
           } else {  // long row: its per-chunk pieces, in chunk order (same as row_grad_sum)
             g = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int32_t ch = i[u] / SEG_CHUNK; ch <= (e[u] - 1) / SEG_CHUNK; ++ch)
@@ -884,6 +894,7 @@ static int ebc_forward_impl(const float* arena, const int64_t* d_row_base, const
                "tt_ebc_forward: without bag_offsets n_values (%lld) must equal B*K (%lld)", (long long)n_values,
                (long long)B * K);
   if (B == 0) return TT_OK;
+  TT_CHECK_ARG((int64_t)B * K < ((int64_t)1 << 31), "tt_ebc_forward: B*K must be below 2^31");
   const int G = lanes_per_row(E);
   const int threads = 256;
   const int64_t n_bags = (int64_t)B * K;
@@ -893,7 +904,10 @@ static int ebc_forward_impl(const float* arena, const int64_t* d_row_base, const
   if (bag_offsets == nullptr) {
     constexpr int UNROLL = 4;
     int64_t want = ceil_div(n_bags, (int64_t)groups_per_block * UNROLL);
-    int grid = (int)(want < 1 ? 1 : (want > (int64_t)sm_count() * 16 ? (int64_t)sm_count() * 16 : want));
+    // (capping the grid at 5 CTAs per SM to leave slots for the concurrent dense-projection GEMMs was measured: the lookup went
+    // from 18.8 to 31.9 us and the step got slower)
+    const int64_t gcap = (int64_t)sm_count() * 16;
+    int grid = (int)(want < 1 ? 1 : (want > gcap ? gcap : want));
     if (out_dtype == TT_F32)
       ebc_fwd_l1_kernel<float, UNROLL><<<grid, threads, smem, s>>>(arena, d_row_base, d_vocab, values, B, K, E, layout,
                                                                    (float*)out, out_ld, out_col0, rows_out, slots_out, slot_base, G,
@@ -937,7 +951,8 @@ int tt_ebc_forward_mixed(const float* arena, const int64_t* d_row_base, const in
 int64_t tt_ebc_sort_workspace_bytes(int64_t n, int64_t total_rows) {
   (void)total_rows;
   if (n < 0) return 0;
-  const int64_t tiles = (n + RS_TILE - 1) / RS_TILE + 1;
+  const int64_t tile = RS_THREADS * rs_items_for(n);
+  const int64_t tiles = (n + tile - 1) / tile + 1;
   return 2 * align_up(n * 4 + 16, 256) + align_up(256 * tiles * 4, 256) + align_up((256 * tiles / SCAN_CHUNK + 2) * 4, 256);
 }
 
@@ -956,21 +971,26 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
   while (((int64_t)1 << bits) < total_rows) ++bits;
   int passes = (bits + 7) / 8;
   if (passes < 1) passes = 1;
-  const int n_tiles = (int)((n + RS_TILE - 1) / RS_TILE);
+  const int items = rs_items_for(n), tile = RS_THREADS * items;
+  const int n_tiles = (int)((n + tile - 1) / tile);
   char* ws = (char*)workspace;
   int32_t* tmp_keys = (int32_t*)ws;
   int32_t* tmp_vals = (int32_t*)(ws + align_up(n * 4 + 16, 256));
   int32_t* hist = (int32_t*)(ws + 2 * align_up(n * 4 + 16, 256));
-  int32_t* scan_totals = (int32_t*)((char*)hist + align_up(256 * (int64_t)((n + RS_TILE - 1) / RS_TILE + 1) * 4, 256));
+  int32_t* scan_totals = (int32_t*)((char*)hist + align_up(256 * (int64_t)((n + tile - 1) / tile + 1) * 4, 256));
   const int32_t* kin = rows;
   const int32_t* vin = slots;  // NULL => identity on the first pass
   for (int p = 0; p < passes; ++p) {
     const bool to_final = ((passes - 1 - p) % 2) == 0;
     int32_t* kout = to_final ? sorted_rows : tmp_keys;
     int32_t* vout = to_final ? sorted_slots : tmp_vals;
-    radix_hist_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles);
-    { int rc = launch_scan(hist, (int64_t)256 * n_tiles, d_n, scan_totals, s); if (rc != TT_OK) return rc; }
-    radix_scatter_kernel<<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, d_n, p * 8, hist, n_tiles, kout, vout);
+    if (items == RS_ITEMS_SMALL) radix_hist_kernel<RS_ITEMS_SMALL><<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles);
+    else radix_hist_kernel<RS_ITEMS_BIG><<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles);
+    { int rc = launch_scan(hist, (int64_t)256 * n_tiles, d_n, scan_totals, tile, s); if (rc != TT_OK) return rc; }
+    if (items == RS_ITEMS_SMALL)
+      radix_scatter_kernel<RS_ITEMS_SMALL><<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, d_n, p * 8, hist, n_tiles, kout, vout);
+    else
+      radix_scatter_kernel<RS_ITEMS_BIG><<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, d_n, p * 8, hist, n_tiles, kout, vout);
     kin = kout;
     vin = vout;
   }
@@ -1005,7 +1025,19 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
   TT_CHECK_ARG((ld0 % 4) == 0 && (col0_0 % 4) == 0 && (ld1 % 4) == 0 && (col0_1 % 4) == 0,
                "tt_ebc_backward_adam: grad ld/col0 must be multiples of 4");
   TT_CHECK_ARG(grad_dtype == TT_F32 || grad_dtype == TT_BF16, "tt_ebc_backward_adam: bad grad dtype");
-  TT_CHECK_ARG(mode == TT_ADAM_DENSE_EXACT || mode == TT_ADAM_SPARSE, "tt_ebc_backward_adam: bad mode %d", mode);
+  TT_CHECK_ARG(mode == TT_ADAM_DENSE_EXACT || mode == TT_ADAM_SPARSE || mode == TT_ADAM_DENSE_UNTOUCHED, "tt_ebc_backward_adam: bad mode %d", mode);
+  if (mode == TT_ADAM_DENSE_UNTOUCHED) {
+    // first half of a split exact-dense step: every row the batch does NOT touch (g = wd*w), needs only the stamps of the sort
+    TT_CHECK_ARG(do_adam && !grad_arena && row_stamp, "tt_ebc_backward_adam: TT_ADAM_DENSE_UNTOUCHED needs w/m/v, d_hyper and row_stamp");
+    const int G0 = lanes_per_row(E);
+    int64_t want0 = ceil_div(total_rows, 256 / G0);
+    const int64_t cap0 = (int64_t)sm_count() * 32;
+    const GradFetch none{nullptr, nullptr, GradSrc{}, 0};
+    ebc_rows_dense_kernel<true, false, false><<<(int)(want0 > cap0 ? cap0 : want0), 256, 0, (cudaStream_t)stream>>>(
+        arena_w, arena_m, arena_v, nullptr, total_rows, E, G0, none, row_begin, row_end, row_stamp, stamp, d_stamp, nullptr, d_hyper, 1);
+    TT_LAUNCH_CHECK("ebc_rows_dense_kernel(untouched)");
+    return TT_OK;
+  }
   TT_CHECK_ARG(!(mode == TT_ADAM_SPARSE && grad_arena), "tt_ebc_backward_adam: sparse mode cannot emit a dense grad");
   TT_CHECK_ARG(piece_ws_bytes >= tt_ebc_piece_workspace_bytes(n, E) && (piece_ws || n == 0),
                "tt_ebc_backward_adam: piece workspace too small");
@@ -1019,10 +1051,13 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
   // Exact-dense mode: the gradients are compacted in sorted order first (independent 16-byte gathers, then streaming sums) — the
   // row kernels walk every arena row and the compacted copy keeps their gradient reads sequential. Sparse mode fetches through
   // the sorted slots directly: the pooled gradients (B*K vectors) sit in the L2 while a compacted copy (B*K*L vectors) would
-  // cost an HBM round trip; measured on B200 at the config-5 shard 2.42 ms vs 2.73 ms. Peer (NVLink) sources are always
-  // compacted. TT_EBC_DIRECT=0/1 overrides (experiments). Both ways read the same values in the same order: bit-identical.
+  // cost an HBM round trip; measured on B200 at the config-5 shard 2.42 ms vs 2.73 ms. That holds for large steps with short
+  // segments; a reference-sized step (65 k entries, dozens of entries per row of the smaller tables) is latency-bound and the
+  // dependent slot -> gradient chain per entry makes the direct form several times slower there (76 us vs ~10 us), so it is used
+  // from 2^19 entries up. Peer (NVLink) sources are always compacted. TT_EBC_DIRECT=0/1 overrides (experiments). Both ways read
+  // the same values in the same order: bit-identical.
   static const int direct_env = [] { const char* e = getenv("TT_EBC_DIRECT"); return e ? atoi(e) : -1; }();
-  const bool direct = !grad_table && (direct_env >= 0 ? direct_env != 0 : (mode == TT_ADAM_SPARSE && do_adam));
+  const bool direct = !grad_table && (direct_env >= 0 ? direct_env != 0 : (mode == TT_ADAM_SPARSE && do_adam && n >= ((int64_t)1 << 19)));
   const GradFetch gs{direct ? nullptr : gs_buf, sorted_slots, src, grad_dtype == TT_BF16 ? 1 : 0};
   if (n > 0) {
     if (!direct) {
@@ -1058,7 +1093,7 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
     const int grid = (int)(want > cap ? cap : want);
 #define TT_ROWS_LAUNCH(A, W)                                                                                         \
   (direct ? ebc_rows_dense_kernel<A, W, true> : ebc_rows_dense_kernel<A, W, false>)<<<grid, threads, 0, s>>>(arena_w, arena_m, arena_v, grad_arena, total_rows, E, G, gs, \
-                                                       row_begin, row_end, row_stamp, stamp, d_stamp, pieces, d_hyper)
+                                                       row_begin, row_end, row_stamp, stamp, d_stamp, pieces, d_hyper, 0)
     const bool wg = grad_arena != nullptr;
     if (do_adam && !wg && total_rows * (int64_t)E * 4 >= ((int64_t)256 << 20))  // arena >> L2: the streaming variant
       (direct ? ebc_rows_dense_stream_kernel<true> : ebc_rows_dense_stream_kernel<false>)<<<grid, threads, 0, s>>>(

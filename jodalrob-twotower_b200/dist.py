@@ -338,7 +338,11 @@ class DistributedEngine(TwoTowerEngine):
         """Like the single-GPU step, except that the large-table update pulls gradients from every rank: it has to wait for the
         all-reduce of the dense gradients, which doubles as the barrier that says every rank's pooled gradients are complete."""
         self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
-        out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
+        self._arm_split = True
+        try:
+            out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
+        finally:
+            self._arm_split = False
         main = torch.cuda.current_stream(self.device)
         self.backward(ws)  # towers on two streams, joined on main
         self.reduce_dense_grads()
@@ -404,6 +408,7 @@ class DistributedEngine(TwoTowerEngine):
         self._call("tt_ebc_sort_rows", ptr(ws.rows), ptr(ws.slots), cap, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
                    ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
                    0, ptr(self.stamp), ptr(ws.n_owned), s, n_kernels=7)
+        self._adam_untouched(ws)
 
     def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool, sorted_already: bool = False):
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
@@ -424,7 +429,7 @@ class DistributedEngine(TwoTowerEngine):
                    self.total_rows, E, ptr(ws.sorted_rows), ptr(ws.sorted_slots), cap, ptr(self.row_begin), ptr(self.row_end),
                    ptr(self.row_stamp), 0, ptr(self.stamp), 0, H0 + K0 * E, H0, max(KL0, 1), n0, 0, H0 + K1 * E, H0, max(KL1, 1),
                    n_l - n0, self.act, ptr(ws.piece_ws), ws.piece_ws.numel(), ptr(self.hyper),
-                   self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, ptr(ws.n_owned), ptr(ws.dc_table), n_l,
+                   self._table_mode(ws, apply_adam), ptr(ws.n_owned), ptr(ws.dc_table), n_l,
                    ptr(self.colmap[0]), ptr(self.colmap[1]), s, n_kernels=2)
 
     def similarity_matrix(self, ws: _Ws) -> torch.Tensor:

@@ -13,6 +13,8 @@ Data layout in HBM
 """
 from __future__ import annotations
 
+import os
+
 import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -20,7 +22,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import native
-from .native import TT_ADAM_DENSE_EXACT, TT_ADAM_SPARSE, TT_F32, TT_LAYOUT_KEY_MAJOR, TT_LAYOUT_SAMPLE_MAJOR, ptr
+from .native import TT_ADAM_DENSE_EXACT, TT_ADAM_DENSE_UNTOUCHED, TT_ADAM_SPARSE, TT_F32, TT_LAYOUT_KEY_MAJOR, TT_LAYOUT_SAMPLE_MAJOR, ptr
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -113,6 +115,13 @@ class TwoTowerEngine:
         self.act = native.TT_BF16 if dtype == "bf16" else TT_F32
         self.act_torch = torch.bfloat16 if dtype == "bf16" else torch.float32
         self.adam_mode = {"dense_exact": TT_ADAM_DENSE_EXACT, "sparse": TT_ADAM_SPARSE}[optimizer_mode]
+        # Split exact-dense table update of the fused step (TT_SPLIT_ADAM=1): rows the batch does not touch (g = wd*w) are updated
+        # right behind the sort-dedup, underneath the towers; only the touched rows wait for the gradients. Bit-identical to the
+        # one-kernel update. Measured on B200 at the README-default size: 376 us per step against 361 us unsplit — the extra kernel
+        # lands next to the first sim-CE pass, whose persistent CTAs then find SMs occupied — so it is off by default.
+        self.split_dense_adam = os.environ.get("TT_SPLIT_ADAM", "0") != "0"
+        self.hyper_on_helper = os.environ.get("TT_HYPER_HELPER", "1") != "0"
+        self._arm_split = False
         self.default_layout = value_layout
         E = cfg.emb_dim
         if E % 4 != 0 or cfg.hidden[0] % 4 != 0:
@@ -157,7 +166,8 @@ class TwoTowerEngine:
         self._sort_stream = torch.cuda.Stream(self.device)  # the sort has the whole forward + loss to hide under: normal priority
         self._adam_stream = torch.cuda.Stream(self.device, priority=hi)
         # two helper streams per tower: the weight gradients of a tower's layers are independent of each other
-        self._wg_streams = [[torch.cuda.Stream(self.device) for _ in range(2)] for _ in range(2)]
+        self._pre_streams = [torch.cuda.Stream(self.device, priority=hi) for _ in range(2)]
+        self._wg_streams = [[torch.cuda.Stream(self.device) for _ in range(4)] for _ in range(2)]  # per tower: 3 weight-gradient chains + small tables
         self.launches = 0  # kernels launched through the C ABI (bench.py's gpu_launches)
         self.profile: Optional[list] = None  # set to [] to collect (tag, n_kernels, ev0, ev1) per C-ABI call
         self.profile_tag = ""
@@ -314,7 +324,7 @@ class TwoTowerEngine:
         # one scratch per tower so the two towers may run on different streams
         ws.bn_ws = [torch.empty(max(max_bn, 256), dtype=torch.uint8, device=dev) for _ in range(2)]
         ws.bn_sums = [torch.zeros(2 * max(cfg.hidden[1:] + [1]), dtype=torch.float64, device=dev) for _ in range(2)]
-        ws.wg_ws = [[torch.empty(max_wg, dtype=torch.uint8, device=dev) for _ in range(3)] for _ in range(2)]
+        ws.wg_ws = [[torch.empty(max_wg, dtype=torch.uint8, device=dev) for _ in range(4)] for _ in range(2)]
         ws.sim_ws = torch.empty(q("tt_simce_workspace_bytes", B, B, cfg.final_dim), dtype=torch.uint8, device=dev)
         ws.row_sumexp = torch.empty(B, **f32)
         ws.col_sumexp = torch.empty(B, **f32)
@@ -490,7 +500,7 @@ class TwoTowerEngine:
         main = torch.cuda.current_stream(self.device)
         overlap = self.two_streams and self.profile is None
         if overlap:  # the dense projections do not need the lookup: run them underneath it on helper streams
-            pre = [self._wg_streams[0][0], self._wg_streams[1][0]]
+            pre = self._pre_streams  # high priority: their GEMM CTAs take the SM slots the lookup's first wave frees
             for t, d in ((0, notice_dense), (1, company_dense)):
                 pre[t].wait_stream(main)
                 with torch.cuda.stream(pre[t]):
@@ -504,6 +514,10 @@ class TwoTowerEngine:
             ws.values = [notice_values, company_values]
         else:
             self.embedding_forward(ws, [notice_values, company_values], lay)
+        hd = getattr(self, "_hyper_done", None)
+        if hd is not None:  # the optimizer / dropout scalars of this step (advanced on a helper stream by fused_step)
+            main.wait_event(hd)
+            self._side.wait_event(hd)
         if sort_on_side:  # the index side of the sparse backward only needs the looked-up rows
             self._sort_stream.wait_stream(main)
             if split:
@@ -595,10 +609,10 @@ class TwoTowerEngine:
         joins, used = [], set()
         if after_dc is not None:
             after_dc()
-        if inline:  # this stream is busy with the table update: small tables on a helper
-            st = self._wg_streams[t][0]
+        if inline:  # this stream is busy with the table update: small tables on a helper of their own
+            st = self._wg_streams[t][3]
             st.wait_event(ws.dc_ready[t])
-            used.add(0)
+            used.add(3)
             with torch.cuda.stream(st):
                 self.small_tables_backward(ws, (t,))
         else:
@@ -611,10 +625,10 @@ class TwoTowerEngine:
             if dense_in.dtype != torch.float32:
                 dense_in = dense_in.float()
         wgrads.append((ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", H0, dense_dim))
-        # every dY exists now; the layers' weight gradients are independent: fan them out over the tower's stream and its two
-        # helper streams (own scratch each), join at the end
+        # every dY exists now; the layers' weight gradients are independent chains of four small kernels: each gets a helper
+        # stream of its own (own scratch each; the README-default tower has three), join at the end
         for i, (dy_, ldy_, x_, ldx_, wn_, bn_, n_, k_) in enumerate(wgrads):
-            lane = (1 + i % 2 if inline else i % 3) if fan else 0
+            lane = 1 + i % 3 if fan else 0
             if lane == 0:
                 self._lin_wgrad(dy_, ldy_, x_, ldx_, wn_, bn_, B, n_, k_, ws.wg_ws[t][0])
             else:
@@ -661,6 +675,18 @@ class TwoTowerEngine:
         self._call("tt_ebc_sort_rows", ptr(ws.rows), 0, n, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
                    ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
                    0, ptr(self.stamp), 0, s, n_kernels=7)
+        self._adam_untouched(ws)
+
+    def _adam_untouched(self, ws: _Ws):
+        """First half of the split exact-dense update (armed by fused_step only): every large-table row without the fresh stamp."""
+        ws.adam_untouched_done = False
+        if not (self._arm_split and self.split_dense_adam and self.adam_mode == TT_ADAM_DENSE_EXACT):
+            return
+        self._call("tt_ebc_backward_adam", ptr(self.arena), ptr(self.arena_m), ptr(self.arena_v), 0, self.total_rows, self.cfg.emb_dim,
+                   0, 0, 0, ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp), 0, ptr(self.stamp), 0, 0, 0, 1, 0, 0, 0, 0, 1, 0,
+                   self.act, ptr(ws.piece_ws), ws.piece_ws.numel(), ptr(self.hyper), TT_ADAM_DENSE_UNTOUCHED, 0, 0, 0, 0, 0,
+                   self._stream())
+        ws.adam_untouched_done = True
 
     def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool, sorted_already: bool = False):
         """Large tables: (sort-by-row dedup, then) segment-sum of the pooled gradients (+ fused Adam)."""
@@ -680,8 +706,16 @@ class TwoTowerEngine:
                    self.total_rows, E, ptr(ws.sorted_rows), ptr(ws.sorted_slots), n, ptr(self.row_begin), ptr(self.row_end),
                    ptr(self.row_stamp), 0, ptr(self.stamp), ptr(ws.dc[0]), H0 + self.K[0] * E, H0, max(self.KL[0], 1), n0,
                    ptr(ws.dc[1]), H0 + self.K[1] * E, H0, max(self.KL[1], 1), n1, self.act, ptr(ws.piece_ws), ws.piece_ws.numel(),
-                   ptr(self.hyper), self.adam_mode if apply_adam else TT_ADAM_DENSE_EXACT, 0, 0, 0, ptr(self.colmap[0]),
+                   ptr(self.hyper), self._table_mode(ws, apply_adam), 0, 0, 0, ptr(self.colmap[0]),
                    ptr(self.colmap[1]), s, n_kernels=2)
+
+    def _table_mode(self, ws: _Ws, apply_adam: bool) -> int:
+        if not apply_adam:
+            return TT_ADAM_DENSE_EXACT
+        if getattr(ws, "adam_untouched_done", False):  # the untouched rows were updated behind the sort: only the touched ones now
+            ws.adam_untouched_done = False
+            return TT_ADAM_SPARSE
+        return self.adam_mode
 
     def backward(self, ws: _Ws, dloss: float = 1.0, de_given: bool = False):
         """Backward of the loss and both towers. `de_given`: ws.de already holds the gradients of the two tower outputs
@@ -711,9 +745,25 @@ class TwoTowerEngine:
     def fused_step(self, notice_dense, notice_values, company_dense, company_values, lr=1e-3, warmup_steps=0,
                    betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, layout=None, masks=None):
         """hyper_advance -> forward -> backward -> sparse-dedup + Adam on tables -> Adam on dense. Returns out5."""
-        self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
-        out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
         main = torch.cuda.current_stream(self.device)
+        self._hyper_done = None
+        if self.two_streams and self.profile is None and self.hyper_on_helper:
+            # nothing before the BatchNorm/dropout kernels reads the optimizer scalars: advance them on a helper stream so the
+            # lookups are the first nodes of the step
+            hs = self._wg_streams[0][1]
+            hs.wait_stream(main)
+            with torch.cuda.stream(hs):
+                self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
+                self._hyper_done = torch.cuda.Event()
+                self._hyper_done.record(hs)
+        else:
+            self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
+        self._arm_split = True
+        try:
+            out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
+        finally:
+            self._arm_split = False
+            self._hyper_done = None
         if self.two_streams:
             # Three streams below the loss: the towers' backward passes on `main` / `_side`, and on `_sort_stream` (where the
             # sort-dedup already ran underneath the forward pass) the large-table segment-sum + Adam, which starts as soon as

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libtwotower_b200.so")
 TT_OK = 0
 TT_F32, TT_BF16 = 0, 1
 TT_LAYOUT_SAMPLE_MAJOR, TT_LAYOUT_KEY_MAJOR = 0, 1
-TT_ADAM_DENSE_EXACT, TT_ADAM_SPARSE = 0, 1
+TT_ADAM_DENSE_EXACT, TT_ADAM_SPARSE, TT_ADAM_DENSE_UNTOUCHED = 0, 1, 2
 HYPER_BYTES = 64
 
 _SCALARS = {
