@@ -187,6 +187,16 @@ int tt_ebc_small_backward(const int64_t* values, int32_t B, int32_t K, int32_t l
 int64_t tt_peer_mailbox_bytes(int32_t world, int32_t n_max);
 int tt_peer_allreduce_f64(double* data, int32_t n, int32_t rank, int32_t world, const void* const* d_mailboxes, int32_t n_max,
                           int64_t* d_epoch, tt_stream_t stream);
+/* All-gather over NVLink peer memory: this rank's block (`bytes`, a multiple of 16) is stored into EVERY rank's destination
+ * buffer (d_dst_bases: device array of the world peer-mapped base pointers, same order on every rank) at dst_offset_bytes
+ * (normally rank * bytes); the call completes on the stream only when every rank's block has landed in this rank's buffer.
+ * d_mailboxes / d_epoch: a mailbox site as for tt_peer_allreduce_f64 (only its flags are used); d_count: zero-initialised int32
+ * per call site. tt_sum_slots_f32: slots f32 [world][n + n_tail]; out[i] = sum over r of slots[r][i] (i < n) in rank order —
+ * with the all-gather, a deterministic all-reduce (the column sums of the logits) — and, for the n_tail values that ride behind
+ * every slot, recip_out[r*n_tail + i] = 1 / slots[r][n + i] (the row scales of all ranks). One process per GPU only. */
+int tt_peer_allgather(const void* src, int64_t bytes, int32_t rank, int32_t world, void* const* d_dst_bases, int64_t dst_offset_bytes,
+                      const void* const* d_mailboxes, int64_t* d_epoch, int32_t* d_count, tt_stream_t stream);
+int tt_sum_slots_f32(const float* slots, int32_t world, int64_t n, int64_t n_tail, float* out, float* recip_out, tt_stream_t stream);
 int tt_ebc_clamp_ids(const int64_t* values, const int32_t* d_vocab, int32_t B, int32_t K, int32_t layout, int32_t* ids_out,
                      tt_stream_t stream);
 int tt_ebc_clamp_ids_subset(const int64_t* values, const int32_t* d_vocab, const int32_t* d_keys, int32_t B, int32_t K, int32_t KL,

@@ -19,6 +19,8 @@ Per step and rank (B_l local samples, B_g = world * B_l):
 """
 from __future__ import annotations
 
+import os
+
 import math
 import threading
 from typing import Dict, List, Optional, Sequence
@@ -216,7 +218,7 @@ class DistributedEngine(TwoTowerEngine):
             assert self.total_rows == self.plan.local_rows, (self.total_rows, self.plan.local_rows)
 
     # ---- tiny reductions over NVLink peer memory instead of collective-library calls (csrc/peer.cu)
-    PEER_SITES = ("tower0", "tower1", "partial", "barrier")
+    PEER_SITES = ("tower0", "tower1", "partial", "barrier", "ids", "e0", "e1", "colsum", "invrow", "dcbar")
 
     def _setup_peer_sites(self):
         self.peer_sites = None
@@ -234,12 +236,24 @@ class DistributedEngine(TwoTowerEngine):
         self.peer_sites = {name: torch.tensor([p + i * mb for p in peers], dtype=torch.int64, device=dev)
                            for i, name in enumerate(self.PEER_SITES)}
         self.peer_epochs = torch.zeros(len(self.PEER_SITES), dtype=torch.int64, device=dev)
+        self.peer_counts = torch.zeros(len(self.PEER_SITES), dtype=torch.int32, device=dev)
+        self._metrics_stream = torch.cuda.Stream(dev)
+        self._small_stream = torch.cuda.Stream(dev)
         self._peer_dummy = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._peer_dummy2 = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def _peer_allreduce(self, buf: torch.Tensor, n: int, site: str):
         i = self.PEER_SITES.index(site)
         self._call("tt_peer_allreduce_f64", ptr(buf), n, self.rank, self.world, ptr(self.peer_sites[site]), self.peer_n_max,
                    self.peer_epochs.data_ptr() + 8 * i, self._stream())
+
+    def _peer_allgather(self, src: torch.Tensor, dst_table: torch.Tensor, site: str):
+        """src (this rank's contiguous block) -> block `rank` of every rank's destination buffer; returns (on the stream) when all
+        W blocks have landed here (csrc/peer.cu)."""
+        i = self.PEER_SITES.index(site)
+        nbytes = src.numel() * src.element_size()
+        self._call("tt_peer_allgather", ptr(src), nbytes, self.rank, self.world, ptr(dst_table), self.rank * nbytes,
+                   ptr(self.peer_sites[site]), self.peer_epochs.data_ptr() + 8 * i, self.peer_counts.data_ptr() + 4 * i, self._stream())
 
     def _alloc_rows(self, t: int, k: int, vocab: int, small: bool) -> int:
         return vocab if small else -(-vocab // self.world)
@@ -267,7 +281,7 @@ class DistributedEngine(TwoTowerEngine):
         n_l = B * (self.KL[0] + self.KL[1])
         cap = max(n_l * W, 1)
         i32 = dict(dtype=torch.int32, device=dev)
-        ws.ids_local = torch.zeros(max(n_l, 1), **i32)
+        ws.ids_local = torch.zeros(max(n_l + 3, 4) // 4 * 4, **i32)[:max(n_l, 1)]
         ws.ids_all = torch.zeros(cap, **i32)
         ws.rows = torch.zeros(cap, **i32)          # owned local rows (compact)
         ws.slots = torch.zeros(cap, **i32)         # their global slots
@@ -285,6 +299,30 @@ class DistributedEngine(TwoTowerEngine):
         ws.col_sum_s = torch.empty(Bg, **f32)
         ws.inv_col = torch.empty(Bg, **f32)
         ws.inv_row_all = torch.empty(Bg, **f32)
+        ws.xtab = None
+        # Exchange destinations in peer-mapped memory: with peer kernels available the id exchange, the embedding all-gathers,
+        # the column-sum all-reduce and the row-scale all-gather are pushes over NVLink (tt_peer_allgather) instead of NCCL calls.
+        # Every block must be a multiple of 16 bytes.
+        esz_e = 4 if self.emb_tt == TT_F32 else 2
+        blocks_ok = (n_l * 4) % 16 == 0 and (B * cfg.final_dim * esz_e) % 16 == 0 and (B * 4) % 16 == 0 and n_l > 0
+        if self.peer_sites is not None and blocks_ok and os.environ.get("TT_PEER_EXCHANGE", "1") != "0":
+            parts = {"ids": cap * 4, "e0": Bg * cfg.final_dim * esz_e, "e1": Bg * cfg.final_dim * esz_e,
+                     "colsum": W * (Bg + B) * 4}  # per rank: its column-sum partials [Bg] followed by its row sums [B]
+            xoff, o = {}, 0
+            for k_, nb in parts.items():
+                xoff[k_] = o
+                o += _a256(nb)
+            xbuf, xpeer = self.comm.peer_buffer(o, dev)
+            xbuf.zero_()
+            ws.xbuf = xbuf
+            ws.ids_all = xbuf[xoff["ids"]:xoff["ids"] + cap * 4].view(torch.int32)
+            ws.e_all = [xbuf[xoff[k_]:xoff[k_] + parts[k_]].view(self.emb_torch).view(Bg, cfg.final_dim) for k_ in ("e0", "e1")]
+            ws.colsum_slots = xbuf[xoff["colsum"]:xoff["colsum"] + W * (Bg + B) * 4].view(torch.float32)
+            ws.xmsg = torch.empty(Bg + B, **f32)      # what this rank sends: column-sum partials, then its row sums
+            ws.col_partial, ws.row_sumexp = ws.xmsg[:Bg], ws.xmsg[Bg:]
+            ws.xtab = {k_: torch.tensor([p_ + xoff[k_] for p_ in xpeer], dtype=torch.int64, device=dev) for k_ in parts}
+            torch.cuda.synchronize(dev)
+            self.comm.dist.barrier(group=self.comm.group, device_ids=[dev.index if dev.index is not None else torch.cuda.current_device()])
         ws.sim_ws = torch.empty(q("tt_simce_workspace_bytes", Bg, Bg, cfg.final_dim), dtype=torch.uint8, device=dev)
         return ws
 
@@ -298,13 +336,20 @@ class DistributedEngine(TwoTowerEngine):
         if values[0] is None or values[1] is None:
             raise NotImplementedError("the sharded lookup serves both towers in one exchange; call the train task, not a single tower")
         self.profile_tag = "sharded"
-        # replicated small tables: plain local lookup (large keys skipped)
-        for t, v in enumerate(values):
-            k0 = 0 if t == 0 else K0
-            if self.n_small[t]:
-                self._call("tt_ebc_forward_mixed", ptr(self.flat_w), self.row_base.data_ptr() + 8 * k0,
-                           self.vocab_small_only.data_ptr() + 4 * k0, ptr(v), B, self.K[t], E, layout, ptr(ws.c[t]), self.act,
-                           H0 + self.K[t] * E, H0, self.no_rank.data_ptr() + 4 * k0, 0, 0, 0, s)
+        # replicated small tables: plain local lookup (large keys skipped) — on a stream of its own when the exchange below can
+        # run next to it (it writes other columns of the concat buffers)
+        cur = torch.cuda.current_stream(self.device)
+        par = self.peer_sites is not None and self.profile is None and n_l > 0
+        small_stream = self._small_stream if par else cur
+        if par:
+            small_stream.wait_stream(cur)
+        with torch.cuda.stream(small_stream):
+            for t, v in enumerate(values):
+                k0 = 0 if t == 0 else K0
+                if self.n_small[t]:
+                    self._call("tt_ebc_forward_mixed", ptr(self.flat_w), self.row_base.data_ptr() + 8 * k0,
+                               self.vocab_small_only.data_ptr() + 4 * k0, ptr(v), B, self.K[t], E, layout, ptr(ws.c[t]), self.act,
+                               H0 + self.K[t] * E, H0, self.no_rank.data_ptr() + 4 * k0, 0, 0, 0, small_stream.cuda_stream)
         ws.values, ws.layout = list(values), layout
         if n_l == 0:
             return
@@ -313,7 +358,10 @@ class DistributedEngine(TwoTowerEngine):
                    ptr(ws.ids_local), s)
         self._call("tt_ebc_clamp_ids_subset", ptr(values[1]), self.vocab.data_ptr() + 4 * K0, ptr(self.d_large_keys[1]), B, K1, KL1,
                    layout, ws.ids_local.data_ptr() + 4 * n0, s)
-        self.comm.all_gather(ws.ids_all, ws.ids_local)
+        if ws.xtab is not None:
+            self._peer_allgather(ws.ids_local, ws.xtab["ids"], "ids")
+        else:
+            self.comm.all_gather(ws.ids_all, ws.ids_local)
         self._call("tt_shard_select_owned", ptr(ws.ids_all), ptr(self.block), ptr(self.local_base), n_l, n0, max(KL0, 1), KL1,
                    self.world, self.rank, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), ptr(ws.shard_ws), ws.shard_ws.numel(), s,
                    n_kernels=3)
@@ -325,6 +373,8 @@ class DistributedEngine(TwoTowerEngine):
             self._peer_allreduce(self._peer_dummy, 1, "barrier")
         else:
             self.comm.barrier(self.device)
+        if par:
+            cur.wait_stream(small_stream)
 
     def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int, tower: int = 0) -> int:
         if self.peer_sites is not None and n <= self.peer_n_max:
@@ -333,50 +383,72 @@ class DistributedEngine(TwoTowerEngine):
             self.comm_t[tower].all_reduce(sums[:n])
         return local_count * self.world
 
-    def fused_step(self, notice_dense, notice_values, company_dense, company_values, lr=1e-3, warmup_steps=0,
-                   betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, layout=None, masks=None):
-        """Like the single-GPU step, except that the large-table update pulls gradients from every rank: it has to wait for the
-        all-reduce of the dense gradients, which doubles as the barrier that says every rank's pooled gradients are complete."""
-        self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
-        self._arm_split = True
-        try:
-            out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
-        finally:
-            self._arm_split = False
-        main = torch.cuda.current_stream(self.device)
-        self.backward(ws)  # towers on two streams, joined on main
-        self.reduce_dense_grads()
-        main.wait_stream(self._sort_stream)
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
-            self.dense_adam()
-        self.embedding_backward(ws, apply_adam=True, want_dense_grad=False, sorted_already=True)
-        main.wait_stream(self._side)
-        return out5
+    # fused_step is the base engine's: the large-table update starts on the side stream as soon as this rank's concat-buffer
+    # gradients exist AND every other rank's do (barrier below) — it pulls them over NVLink — and overlaps the weight gradients;
+    # the all-reduce of the dense gradients runs at the end of the step, next to it.
+    def _before_table_update(self, ws: _Ws):
+        if self.peer_sites is not None:
+            self._peer_allreduce(self._peer_dummy2, 1, "dcbar")
+        else:
+            self.comm.barrier(self.device)
+
+    def _end_of_step(self, ws: _Ws):
+        ev = getattr(ws, "metrics_done", None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            ws.metrics_done = None
 
     def loss_forward(self, ws: _Ws):
         cfg, B, s = self.cfg, ws.B, self._stream()
         Bg, off = B * self.world, B * self.rank
         self.profile_tag = ""
         inv_t = 1.0 / cfg.temperature
-        self.comm.all_gather(ws.e_all[0], ws.e[0])
-        self.comm.all_gather(ws.e_all[1], ws.e[1])
+        main = torch.cuda.current_stream(self.device)
+        px = ws.xtab is not None
+        if px:  # the two embedding all-gathers as concurrent pushes over NVLink
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._peer_allgather(ws.e[1], ws.xtab["e1"], "e1")
+            self._peer_allgather(ws.e[0], ws.xtab["e0"], "e0")
+            main.wait_stream(self._side)
+        else:
+            self.comm.all_gather(ws.e_all[0], ws.e[0])
+            self.comm.all_gather(ws.e_all[1], ws.e[1])
         css = ptr(ws.col_sum_s) if cfg.label_smoothing > 0 else 0
         self._call("tt_simce_forward", ptr(ws.e[0]), ptr(ws.e_all[1]), B, Bg, cfg.final_dim, self.emb_tt, inv_t, off,
-                   ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), css, ptr(ws.diag), ptr(ws.row_argmax),
-                   ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=4)
-        self.comm.all_reduce(ws.col_sumexp)
+                   ptr(ws.row_sumexp), ptr(ws.col_partial if px else ws.col_sumexp), ptr(ws.row_sum_s), css, ptr(ws.diag),
+                   ptr(ws.row_argmax), ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=4)
+        if px:
+            # ONE exchange for the column-sum all-reduce and the row-scale all-gather: every rank pushes [its column-sum partials |
+            # its row sums] into slot `rank` of every rank; a fixed-order sum gives the column sums, a reciprocal the row scales
+            self._peer_allgather(ws.xmsg, ws.xtab["colsum"], "colsum")
+            self._call("tt_sum_slots_f32", ptr(ws.colsum_slots), self.world, Bg, B, ptr(ws.col_sumexp), ptr(ws.inv_row_all), s)
+        else:
+            self.comm.all_reduce(ws.col_sumexp)
         if css:
             self.comm.all_reduce(ws.col_sum_s)
         self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), css,
                    ptr(ws.diag), ptr(ws.row_argmax), B, Bg, off, Bg, inv_t, cfg.label_smoothing, ptr(ws.inv_row),
                    ptr(ws.inv_col), ptr(ws.partial), s)
-        if self.peer_sites is not None:
-            self._peer_allreduce(ws.partial, ws.partial.numel(), "partial")
+
+        def metrics():
+            if self.peer_sites is not None:
+                self._peer_allreduce(ws.partial, ws.partial.numel(), "partial")
+            else:
+                self.comm.all_reduce(ws.partial)
+            self._call("tt_simce_scalars", ptr(ws.partial), Bg, ptr(ws.out5), self._stream())
+
+        if px and self._in_fused and self.profile is None:
+            # the loss value / metrics are not needed by the backward pass: off the critical path, joined at the end of the step
+            self._metrics_stream.wait_stream(main)
+            with torch.cuda.stream(self._metrics_stream):
+                metrics()
+                ws.metrics_done = torch.cuda.Event()
+                ws.metrics_done.record(self._metrics_stream)
         else:
-            self.comm.all_reduce(ws.partial)
-        self._call("tt_simce_scalars", ptr(ws.partial), Bg, ptr(ws.out5), s)
-        self.comm.all_gather(ws.inv_row_all, ws.inv_row)
+            metrics()
+        if not px:
+            self.comm.all_gather(ws.inv_row_all, ws.inv_row)
         return ws.out5
 
     def loss_backward(self, ws: _Ws, dloss: float = 1.0):

@@ -122,6 +122,7 @@ class TwoTowerEngine:
         self.split_dense_adam = os.environ.get("TT_SPLIT_ADAM", "0") != "0"
         self.hyper_on_helper = os.environ.get("TT_HYPER_HELPER", "1") != "0"
         self._arm_split = False
+        self._in_fused = False
         self.default_layout = value_layout
         E = cfg.emb_dim
         if E % 4 != 0 or cfg.hidden[0] % 4 != 0:
@@ -641,6 +642,10 @@ class TwoTowerEngine:
             ev = torch.cuda.Event()
             ev.record(self._wg_streams[t][j])
             joins.append(ev)
+        if inline:
+            # this stream still carries the table update: hand the helper joins to the caller, so that the dense-gradient
+            # all-reduce / dense Adam can start when the weight gradients are done, next to the table update
+            ws.wg_joins = joins
         for ev in joins:
             cur.wait_event(ev)
 
@@ -758,11 +763,11 @@ class TwoTowerEngine:
                 self._hyper_done.record(hs)
         else:
             self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
-        self._arm_split = True
+        self._arm_split = self._in_fused = True
         try:
             out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
         finally:
-            self._arm_split = False
+            self._arm_split = self._in_fused = False
             self._hyper_done = None
         if self.two_streams:
             # Three streams below the loss: the towers' backward passes on `main` / `_side`, and on `_sort_stream` (where the
@@ -774,16 +779,21 @@ class TwoTowerEngine:
             def table_update():  # on `_side`, right behind the company tower's last data gradient
                 self._side.wait_event(ws.dc_ready[0])
                 self._side.wait_stream(self._sort_stream)
+                self._before_table_update(ws)
                 self.embedding_backward(ws, apply_adam=True, want_dense_grad=False, sorted_already=True)
 
             with torch.cuda.stream(self._hi0):
                 self.tower_backward(0, ws)
             with torch.cuda.stream(self._side):
                 self.tower_backward(1, ws, after_dc=table_update)
-            main.wait_stream(self._side)
             main.wait_stream(self._hi0)
+            for ev in getattr(ws, "wg_joins", None) or [ws.dc_ready[1]]:
+                main.wait_event(ev)  # the company tower's weight gradients and small-table reductions (helper streams)
+            ws.wg_joins = None
             self.reduce_dense_grads()
             self.dense_adam()
+            main.wait_stream(self._side)  # ... and the large-table update, which ran next to them
+            self._end_of_step(ws)
         else:
             self.backward(ws)
             self.reduce_dense_grads()
@@ -794,6 +804,15 @@ class TwoTowerEngine:
 
     def reduce_dense_grads(self):
         """Single GPU: nothing. Distributed engines all-reduce the flat dense gradient buffer here."""
+        return None
+
+    def _before_table_update(self, ws: _Ws):
+        """Hook on the table-update stream once this rank's concat-buffer gradients are complete. Distributed engines put the
+        'every rank's pooled gradients are complete' barrier here (the update pulls them over NVLink)."""
+        return None
+
+    def _end_of_step(self, ws: _Ws):
+        """Hook at the very end of the fused step (main stream). Distributed engines join their deferred metrics stream here."""
         return None
 
     def hyper_host(self) -> dict:
