@@ -157,7 +157,7 @@ def cpu_baseline(schema, B, budget_s=25.0):
         n = max(1, min(10, int((budget_s / 2) / max(warm, 1e-3))))
         t0 = time.perf_counter()
         for _ in range(n):
-            float(tr.step(batch)["loss"])
+            float(tr.step(batch)["loss"].detach())
         dt = time.perf_counter() - t0
         out[decode] = (B * n / dt, n)
     return {"value": out["loop"][0], "unit": UNIT, "cores": cores, "kind": "port",

@@ -262,7 +262,9 @@ int tt_bn_apply(const void* h, int64_t ldh, int64_t M, int32_t N, int32_t act_dt
                 const float* rstd, const float* gamma, const float* beta, float dropout_p, const uint8_t* mask_in,
                 const tt_adam_hyper* d_hyper, uint32_t rng_stream, void* y, int64_t ldy, tt_stream_t stream);
 /* backward: sums f64 [2N] = (sum_b dy', sum_b dy'*xhat) with dy' = dy * keep/(1-p);  then
- * dh = [h>0] * rstd*gamma*(dy' - sums0/count - xhat*sums1/count);  dgamma = sums1, dbeta = sums0.
+ * dh = [h>0] * rstd*gamma*(dy' - sums0/count - xhat*sums1/count);  dgamma = affine_grad_scale * sums1, dbeta =
+ * affine_grad_scale * sums0 (1 normally; with SyncBN the sums are already global on every rank, so exactly one rank passes 1
+ * and the others 0 before the gradient all-reduce).
  * eval-mode backward (frozen stats) is dh = [h>0]*rstd*gamma*dy' : pass train = 0. */
 int tt_bn_backward_reduce(const void* dy, int64_t lddy, const void* h, int64_t ldh, int64_t M, int32_t N,
                           int32_t act_dtype, const float* mean, const float* rstd, float dropout_p,
@@ -271,8 +273,8 @@ int tt_bn_backward_reduce(const void* dy, int64_t lddy, const void* h, int64_t l
 int tt_bn_backward_apply(const void* dy, int64_t lddy, const void* h, int64_t ldh, int64_t M, int32_t N,
                          int32_t act_dtype, const float* mean, const float* rstd, const float* gamma,
                          float dropout_p, const uint8_t* mask_in, const tt_adam_hyper* d_hyper, uint32_t rng_stream,
-                         const double* sums, int64_t count, int32_t train, float* dgamma, float* dbeta, void* dh,
-                         int64_t lddh, tt_stream_t stream);
+                         const double* sums, int64_t count, int32_t train, float* dgamma, float* dbeta,
+                         float affine_grad_scale, void* dh, int64_t lddh, tt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * F.normalize(p=2, dim=1, eps=1e-12) (src/towers/tower/base_tower.py:145) and its backward

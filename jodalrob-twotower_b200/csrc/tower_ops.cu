@@ -120,7 +120,7 @@ bn_bwd_apply_kernel(const T* __restrict__ DY, int64_t lddy, const T* __restrict_
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                     float p, const uint8_t* mask_in, const tt_adam_hyper* __restrict__ hyp, uint32_t stream,
                     const double* __restrict__ sums, long long count, int train, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, T* __restrict__ DH, int64_t lddh) {
+                    float* __restrict__ dbeta, float affine_scale, T* __restrict__ DH, int64_t lddh) {
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const int64_t total = M * N, stride = (int64_t)gridDim.x * blockDim.x;
   const float inv_count = 1.f / (float)count;
@@ -139,8 +139,8 @@ bn_bwd_apply_kernel(const T* __restrict__ DY, int64_t lddy, const T* __restrict_
     }
     stf<T>(DH + m * lddh + n, h > 0.f ? dh : 0.f);
     if (i < N) {  // first row's threads also publish the affine grads
-      if (dbeta) dbeta[n] = (float)sums[n];
-      if (dgamma) dgamma[n] = (float)sums[N + n];
+      if (dbeta) dbeta[n] = affine_scale * (float)sums[n];
+      if (dgamma) dgamma[n] = affine_scale * (float)sums[N + n];
     }
   }
 }
@@ -273,8 +273,8 @@ int tt_bn_backward_reduce(const void* dy, int64_t lddy, const void* h, int64_t l
 int tt_bn_backward_apply(const void* dy, int64_t lddy, const void* h, int64_t ldh, int64_t M, int32_t N,
                          int32_t act_dtype, const float* mean, const float* rstd, const float* gamma,
                          float dropout_p, const uint8_t* mask_in, const tt_adam_hyper* d_hyper, uint32_t rng_stream,
-                         const double* sums, int64_t count, int32_t train, float* dgamma, float* dbeta, void* dh,
-                         int64_t lddh, tt_stream_t stream) {
+                         const double* sums, int64_t count, int32_t train, float* dgamma, float* dbeta,
+                         float affine_grad_scale, void* dh, int64_t lddh, tt_stream_t stream) {
   TT_CHECK_ARG(dy && h && mean && rstd && gamma && sums && dh && M > 0 && N > 0 && count > 0, "tt_bn_backward_apply: bad arguments");
   TT_CHECK_ARG(dropout_p == 0.f || mask_in || d_hyper, "tt_bn_backward_apply: dropout needs mask_in or d_hyper");
   TT_CHECK_ARG(act_dtype == TT_F32 || act_dtype == TT_BF16, "tt_bn_backward_apply: bad dtype");
@@ -282,11 +282,11 @@ int tt_bn_backward_apply(const void* dy, int64_t lddy, const void* h, int64_t ld
   if (act_dtype == TT_F32)
     bn_bwd_apply_kernel<float><<<ew_grid(M * N), 256, 0, s>>>((const float*)dy, lddy, (const float*)h, ldh, M, N, mean,
                                                               rstd, gamma, dropout_p, mask_in, d_hyper, rng_stream, sums,
-                                                              (long long)count, train, dgamma, dbeta, (float*)dh, lddh);
+                                                              (long long)count, train, dgamma, dbeta, affine_grad_scale, (float*)dh, lddh);
   else
     bn_bwd_apply_kernel<__nv_bfloat16><<<ew_grid(M * N), 256, 0, s>>>(
         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)h, ldh, M, N, mean, rstd, gamma, dropout_p, mask_in,
-        d_hyper, rng_stream, sums, (long long)count, train, dgamma, dbeta, (__nv_bfloat16*)dh, lddh);
+        d_hyper, rng_stream, sums, (long long)count, train, dgamma, dbeta, affine_grad_scale, (__nv_bfloat16*)dh, lddh);
   TT_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return TT_OK;
 }

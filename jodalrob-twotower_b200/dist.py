@@ -209,6 +209,7 @@ class DistributedEngine(TwoTowerEngine):
         self.vocab_small_only = vf
         self.no_rank = torch.full((self.K[0] + self.K[1],), -1, dtype=torch.int32, device=dev)
         self.rng_stream_base = 64 * self.rank
+        self.bn_affine_grad_scale = 1.0 if self.rank == 0 else 0.0  # the SyncBN sums are global: one rank publishes them
         # the company tower runs on the side stream with its own communicator for the SyncBN all-reduces
         self.comm_t = [comm, comm.clone()]
         self._setup_peer_sites()
@@ -517,13 +518,13 @@ class DistributedEngine(TwoTowerEngine):
     def _large_index(self, t: int, k: int) -> int:
         return (0 if t == 0 else self.KL[0]) + self.large_keys[t].index(k)
 
-    def load_full_tables(self, full_tables: Sequence[torch.Tensor]):
+    def load_full_tables(self, full_tables: Sequence[torch.Tensor], which: str = "w"):
         """full_tables: [V_k, E] for notice keys then company keys; small tables are copied whole (replicated), of a large
-        table this rank keeps its row shard."""
+        table this rank keeps its row shard. `which`: weights "w" or the Adam moments "m" / "v"."""
         i = 0
         for t in range(2):
             for k in range(self.K[t]):
-                tab, view = full_tables[i], self.table_view(t, k)
+                tab, view = full_tables[i].to(self.device), self.table_view(t, k, which)
                 i += 1
                 if self.is_small[t][k]:
                     view.copy_(tab)
@@ -630,3 +631,52 @@ def gather_reference_state_dict(task) -> Dict[str, torch.Tensor]:
             out[f"two_tower_model.{name}_tower.categorical_embedder.embeddings.{k}.weight"] = tabs[i]
             i += 1
     return out
+
+
+def _table_param_names(cfg) -> List[str]:
+    return [f"two_tower_model.{cfg.tower(t)[0]}_tower.categorical_embedder.embeddings.{k}.weight" for t in range(2) for k in cfg.tower(t)[1]]
+
+
+def gather_reference_optimizer_state(task) -> dict:
+    """torch.optim.Adam-format optimizer state of the whole model: the row-wise shards of the Adam
+    moments are all-gathered back into full [V_k, E] tensors, in the parameter order of the reference's
+    `train_task.parameters()`, so `torch.optim.Adam.load_state_dict` / a single-GPU FusedAdam can resume from it
+    (scripts/train.py:497-526). Collective: every rank calls it."""
+    eng: DistributedEngine = task.engine
+    opt = task._fused_opt
+    sd = opt.state_dict()  # local view: right for the dense parameters and the replicated small tables
+    if not sd["state"]:
+        return sd
+    full = {w: dict(zip(_table_param_names(eng.full_cfg), eng.gather_full_tables(w))) for w in ("m", "v")}
+    for i, (name, _p) in enumerate(task.named_parameters()):
+        if name in full["m"]:
+            sd["state"][i]["exp_avg"] = full["m"][name]
+            sd["state"][i]["exp_avg_sq"] = full["v"][name]
+    return sd
+
+
+def load_reference_optimizer_state(task, sd: dict):
+    """Inverse of gather_reference_optimizer_state: scatter a full-table torch.optim.Adam state_dict into the shards."""
+    eng: DistributedEngine = task.engine
+    opt = task._fused_opt
+    names = [n for n, _ in task.named_parameters()]
+    tabs = {"m": [], "v": []}
+    for tn in _table_param_names(eng.full_cfg):
+        st = sd["state"].get(names.index(tn)) if sd["state"] else None
+        for w, key in (("m", "exp_avg"), ("v", "exp_avg_sq")):
+            tabs[w].append(st[key] if st is not None else torch.zeros(1))
+    # dense parameters, small tables, counters: the single-engine loader, on a copy whose table entries match the local shapes
+    local = {"state": {}, "param_groups": sd["param_groups"], **{k: v for k, v in sd.items() if k not in ("state", "param_groups")}}
+    tset = set(_table_param_names(eng.full_cfg))
+    for i, (n, p) in enumerate(task.named_parameters()):
+        st = sd["state"].get(i) if sd["state"] else None
+        if st is None:
+            continue
+        if n in tset:
+            local["state"][i] = {"step": st["step"], "exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)}
+        else:
+            local["state"][i] = st
+    opt.load_state_dict(local)
+    if sd["state"]:
+        eng.load_full_tables(tabs["m"], "m")
+        eng.load_full_tables(tabs["v"], "v")

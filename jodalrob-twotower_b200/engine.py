@@ -158,6 +158,9 @@ class TwoTowerEngine:
         # inside a CUDA graph capture this becomes two parallel branches)
         self.two_streams = True
         self.sharded_lookup = False  # DistributedEngine: the lookup is one exchange for both towers
+        # SyncBN leaves the GLOBAL gamma/beta gradient sums on every rank; the dense-gradient all-reduce must count them once:
+        # distributed engines set 1.0 on rank 0 and 0.0 elsewhere
+        self.bn_affine_grad_scale = 1.0
         # Streams on the critical path (the towers' data-gradient chains, the table update) get high priority, so that their
         # CTAs are placed before those of the weight-gradient helper streams whenever SMs free up
         import os as _os
@@ -597,7 +600,7 @@ class TwoTowerEngine:
             self._call("tt_bn_backward_apply", ptr(ws.dy[t][bi]), h, ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean),
                        ptr(ws.rstd[t][bi]), ptr(gamma), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.bn_sums[t]),
                        count, 1 if train else 0, ptr(self.dense(pre + f"mlp.{idx + 2}.weight", "g")),
-                       ptr(self.dense(pre + f"mlp.{idx + 2}.bias", "g")), ptr(ws.dh[t][bi]), h, s)
+                       ptr(self.dense(pre + f"mlp.{idx + 2}.bias", "g")), self.bn_affine_grad_scale, ptr(ws.dh[t][bi]), h, s)
             xin = ws.y[t][bi - 1] if bi > 0 else ws.c[t]
             win = widths[bi]
             dxin = ws.dy[t][bi - 1] if bi > 0 else ws.dc[t]

@@ -571,19 +571,71 @@ class FusedAdam:
     def step(self, closure=None):
         return None
 
-    def state_dict(self):
+    # ---- checkpointing in torch.optim.Adam's own format: the reference saves `optimizer.state_dict()` next to
+    # `model.state_dict()` and loads both back to resume (scripts/train.py:497-512, 523-526). A checkpoint written through the
+    # fused path can be resumed by the reference's torch.optim.Adam (and by façade mode (i)), and the other way round.
+    def _moment_views(self):
         eng = self.task.engine
-        return {"hyper": eng.hyper.clone(), "flat_m": eng.flat_m.clone(), "flat_v": eng.flat_v.clone(),
-                "config": {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
-                           "warmup_steps": self.warmup_steps}}
+        for kind, ref in self.task._param_src:
+            if kind == "table":
+                yield eng.table_view(ref[0], ref[1], "m"), eng.table_view(ref[0], ref[1], "v")
+            else:
+                yield eng.dense(ref, "m"), eng.dense(ref, "v")
+
+    def _next_lr(self, sched_step: int) -> float:
+        w = self.warmup_steps
+        return self.lr * (sched_step / w if (w > 0 and sched_step < w) else 1.0)
+
+    def state_dict(self):
+        h = self.task.engine.hyper_host()
+        step = int(h["step"])
+        state = {}
+        if step > 0:
+            for i, (m, v) in enumerate(self._moment_views()):
+                state[i] = {"step": torch.tensor(float(step)), "exp_avg": m.detach().clone(), "exp_avg_sq": v.detach().clone()}
+        group = {"lr": self._next_lr(int(h["sched_step"])), "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "initial_lr": self.lr, "params": list(range(len(self.task._param_list)))}
+        # extra top-level keys are ignored by torch.optim.Optimizer.load_state_dict; they make our own resume exact
+        return {"state": state, "param_groups": [group],
+                "tt_fused": {"sched_step": int(h["sched_step"]), "warmup_steps": self.warmup_steps, "rng_step": int(h["rng_step"])}}
 
     def load_state_dict(self, sd):
         eng = self.task.engine
-        for k in ("hyper", "flat_m", "flat_v"):
-            getattr(eng, k).copy_(sd[k])
-        c = sd["config"]
-        self.lr, self.betas, self.eps, self.weight_decay = c["lr"], tuple(c["betas"]), c["eps"], c["weight_decay"]
-        self.warmup_steps = c["warmup_steps"]
+        if "param_groups" not in sd:  # the pre-checkpoint-compat format of this class
+            for k in ("hyper", "flat_m", "flat_v"):
+                getattr(eng, k).copy_(sd[k])
+            c = sd["config"]
+            self.lr, self.betas, self.eps, self.weight_decay = c["lr"], tuple(c["betas"]), c["eps"], c["weight_decay"]
+            self.warmup_steps = c["warmup_steps"]
+            return
+        g = sd["param_groups"][0]
+        if len(g["params"]) != len(self.task._param_list):
+            raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+        self.lr = float(g.get("initial_lr", g["lr"]))
+        self.betas, self.eps, self.weight_decay = tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"])
+        state, step = sd["state"], 0
+        for i, (m, v) in enumerate(self._moment_views()):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                m.zero_()
+                v.zero_()
+                continue
+            m.copy_(st["exp_avg"].to(m.device))
+            v.copy_(st["exp_avg_sq"].to(v.device))
+            step = max(step, int(float(st["step"])))
+        extra = sd.get("tt_fused", {})
+        if "warmup_steps" in extra:
+            self.warmup_steps = int(extra["warmup_steps"])
+        # a reference checkpoint carries no scheduler counter here (LambdaLR has its own state_dict): scheduler.step() was
+        # called once per optimizer step in its loop (scripts/train.py:327-330), so the two counters are equal
+        sched = int(extra.get("sched_step", step))
+        h64 = eng.hyper.view(torch.int64)
+        h64[0] = step
+        h64[1] = sched
+        if "rng_step" in extra:
+            h64[7] = int(extra["rng_step"])
+        self.param_groups[0].update(lr=self._next_lr(sched), betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
 
 
 class FusedWarmupScheduler:
@@ -598,6 +650,16 @@ class FusedWarmupScheduler:
 
     def get_last_lr(self):
         return [self.optimizer.task.engine.hyper_host()["lr"]]
+
+    def state_dict(self):
+        """LambdaLR-shaped (loadable by torch.optim.lr_scheduler.LambdaLR.load_state_dict)."""
+        n = int(self.optimizer.task.engine.hyper_host()["sched_step"])
+        lr = self.optimizer._next_lr(n)
+        return {"base_lrs": [self.optimizer.lr], "last_epoch": n, "_step_count": n + 1, "_get_lr_called_within_step": False,
+                "_last_lr": [lr], "lr_lambdas": [None], "_is_initial": False}
+
+    def load_state_dict(self, sd):
+        self.optimizer.task.engine.hyper.view(torch.int64)[1] = int(sd["last_epoch"])
 
 
 def _init_like_reference(engine: TwoTowerEngine):

@@ -271,6 +271,65 @@ def test_cosine_embedding_loss_trajectory_vs_reference_golden(mode):
     assert ev["similarity_matrix"].shape == (cfg["bsz"], cfg["bsz"]) and torch.isfinite(ev["loss"])
 
 
+@pytest.mark.parametrize("direction", ["fused_to_torch", "torch_to_fused", "fused_to_fused"])
+def test_checkpoint_resume_across_implementations(direction):
+    """SURVEY.md §8(f) rank 4 / scripts/train.py:497-526: a checkpoint {model_state_dict, optimizer_state_dict} written after two
+    steps by one optimizer implementation is loaded by the other, which takes the third step; the result must be the reference's
+    own 3-step trajectory (tests/golden/tiny_oob_temp.npz), including the LambdaLR warm-up position."""
+    import io
+    import jodalrob_twotower_b200 as tt
+    d, cfg = load_golden("tiny_oob_temp.npz")
+    w = cfg["warmup_steps"]
+
+    def make(kind):
+        task = make_task(cfg, cfg["schema"])
+        if kind == "torch":
+            opt = torch.optim.Adam(task.parameters(), lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+            sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s_: s_ / w if s_ < w else 1.0, last_epoch=-1)
+        else:
+            opt = tt.FusedAdam(task, lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+            sched = tt.FusedWarmupScheduler(opt, w)
+        task.train()
+        return task, opt, sched
+
+    def step(task, opt, sched, i):
+        nid, cid, nd, cd = batch_inputs(d, i)
+        opt.zero_grad()
+        out = task(make_batch(cfg["schema"], nid, cid, nd, cd), return_metrics=True)
+        out["loss"].backward()
+        opt.step()
+        sched.step()
+        return out["loss"].item()
+
+    first, second = direction.split("_to_")
+    task, opt, sched = make(first)
+    task.load_state_dict(sd_from(d, "init."))
+    for i in range(2):
+        step(task, opt, sched, i)
+    buf = io.BytesIO()  # scripts/train.py:505-512 save_checkpoint
+    torch.save({"epoch": 0, "model_state_dict": task.state_dict(), "optimizer_state_dict": opt.state_dict(),
+                "scheduler_state_dict": sched.state_dict(), "loss": 0.0}, buf)
+    buf.seek(0)
+    ck = torch.load(buf, map_location=DEV, weights_only=False)  # :523 load_checkpoint
+    assert set(ck["optimizer_state_dict"]) >= {"state", "param_groups"}
+    task2, opt2, sched2 = make(second)
+    task2.load_state_dict(ck["model_state_dict"])
+    opt2.load_state_dict(ck["optimizer_state_dict"])
+    sched2.load_state_dict(ck["scheduler_state_dict"])
+    loss2 = step(task2, opt2, sched2, 2)
+    assert abs(loss2 - float(d["s2.loss"])) <= FP32_RTOL * abs(float(d["s2.loss"])) + 1e-6
+    fin = sd_from(d, "final.")
+    for k, v in task2.state_dict().items():
+        if v.is_floating_point():
+            assert rel_err(v.cpu(), fin[k]) < FP32_RTOL, k
+    # the optimizer state after the resumed step is the reference's
+    sd3 = opt2.state_dict()
+    for i, (name, _p) in enumerate(task2.named_parameters()):
+        assert int(float(sd3["state"][i]["step"])) == 3
+        assert rel_err(sd3["state"][i]["exp_avg"].cpu(), torch.from_numpy(d[f"adam_m.{name}"])) < 2e-5, name
+        assert rel_err(sd3["state"][i]["exp_avg_sq"].cpu(), torch.from_numpy(d[f"adam_v.{name}"])) < 2e-5, name
+
+
 def test_key_major_layout_gives_same_step():
     d, cfg = load_golden("tiny_oob_temp.npz")
     outs = []
@@ -704,7 +763,10 @@ def _run_sharded(case, world):
                 sl = slice(r * Bl, (r + 1) * Bl)
                 out = task.fused_step(make_batch(schema, nid[sl], cid[sl], nd[sl], cd[sl]))
                 losses.append(out.clone())
-            results[r] = (losses, ttd.gather_reference_state_dict(task), task.engine.workspace(Bl).n_owned.item(), sum(task.engine.KL))
+            osd = ttd.gather_reference_optimizer_state(task)
+            names = [n for n, _ in task.named_parameters()]
+            results[r] = (losses, ttd.gather_reference_state_dict(task), task.engine.workspace(Bl).n_owned.item(), sum(task.engine.KL),
+                          {names[i]: (st["exp_avg"], st["exp_avg_sq"]) for i, st in osd["state"].items()})
         except Exception as e:  # surface thread failures in the main thread
             import traceback
             errors.append(traceback.format_exc())
@@ -729,7 +791,10 @@ def test_sharded_multirank_step_matches_single_device_reference(case, world):
     owned = sum(r[2] for r in results)
     assert owned == cfg["bsz"] * results[0][3]  # every id of a sharded (large) table has exactly one owner
     assert results[0][3] > 0  # the fixtures do exercise the sharded path (and the replicated small tables next to it)
-    for r, (losses, sd, _, _) in enumerate(results):
+    for r, (losses, sd, _, _, moments) in enumerate(results):
+        for name, (m_, v_) in moments.items():  # sharded Adam moments gathered back into the reference's full-table layout
+            assert rel_err(m_.cpu(), torch.from_numpy(d[f"adam_m.{name}"])) < 2e-5, (r, name)
+            assert rel_err(v_.cpu(), torch.from_numpy(d[f"adam_v.{name}"])) < 2e-5, (r, name)
         for i in range(3):
             # every rank reports the GLOBAL loss/metrics (means over B_g, global diagonal)
             assert abs(losses[i][0].item() - float(d[f"s{i}.loss"])) <= FP32_RTOL * abs(float(d[f"s{i}.loss"])) + 1e-6
@@ -774,7 +839,7 @@ def test_sharded_large_vocab_step_vs_port(world):
     batches = [(ids(schema["notice"]), ids(schema["company"]), torch.randn(B, 24, generator=g), torch.randn(B, 12, generator=g))
                for _ in range(2)]
     tr = ref_port.PortTrainer(port, 1e-3, 1e-5, 0)
-    ref_losses = [float(tr.step(ref_port.make_port_batch(schema, *b))["loss"]) for b in batches]
+    ref_losses = [float(tr.step(ref_port.make_port_batch(schema, *b))["loss"].detach()) for b in batches]
     fin = port.state_dict()
     tw = ttd.ThreadWorld(world)
     tt.native.lib()
