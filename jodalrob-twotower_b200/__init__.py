@@ -18,13 +18,19 @@ def __getattr__(name):
     if name == "TwoTowerEvaluator":
         from . import evaluator
         return evaluator.TwoTowerEvaluator
+    if name == "FeatureProjector":
+        from . import projector
+        return projector.FeatureProjector
+    if name in ("DeviceFeatureStore", "GpuBatchAssembler"):
+        from . import loader
+        return getattr(loader, name)
     if name == "PooledTables":
         from . import tables
         return tables.PooledTables
     if name in ("TwoTowerEngine", "TwoTowerConfig"):
         from . import engine
         return getattr(engine, name)
-    if name in ("native", "ops", "modules", "engine", "dist", "tables", "evaluator"):
+    if name in ("native", "ops", "modules", "engine", "dist", "tables", "evaluator", "loader", "projector"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

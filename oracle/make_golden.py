@@ -200,6 +200,27 @@ def eval_case():
     print("eval_metrics:", {k: float(v) for k, v in out.items() if "recall@5" in k or "mrr" in k})
 
 
+def projector_case():
+    """Outputs of the UNMODIFIED reference FeatureProjector (src/torchrec_preprocess/feature_projector.py) and of the projection
+    loop's concat order (feature_preprocessor.py:195-205) on fixed inputs."""
+    rh.install_shims()
+    from src.torchrec_preprocess.feature_projector import FeatureProjector
+    torch.manual_seed(11)
+    fp = FeatureProjector(num_dim=29, text_dim=768)
+    g = torch.Generator().manual_seed(5)
+    M = 41
+    num = torch.randn(M, 29, generator=g)
+    text = {"title": torch.randn(M, 768, generator=g), "body": torch.randn(M, 768, generator=g)}
+    with torch.no_grad():
+        dp, tp = fp(num, text)
+        cat = torch.cat([dp, tp["title"], tp["body"]], dim=1)
+    out = {f"sd.{k}": v.numpy().copy() for k, v in fp.state_dict().items()}
+    out.update({"numeric": num.numpy(), "text.title": text["title"].numpy(), "text.body": text["body"].numpy(),
+                "dense_proj": dp.numpy(), "proj.title": tp["title"].numpy(), "proj.body": tp["body"].numpy(), "dense_projected": cat.numpy()})
+    np.savez_compressed(os.path.join(GOLD, "projector.npz"), **out)
+    print("projector:", {k: v.shape for k, v in out.items() if not k.startswith("sd.")})
+
+
 def collate_case():
     """Batch produced by the UNMODIFIED reference collate (create_collate_fn, unified_bid_data_loader.py:630-684, with its
     _build_batch_kjt :827-841) on small synthetic feature stores. sqlalchemy & co. are stubbed: the function only touches
@@ -243,6 +264,10 @@ def main():
     import sys
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order → reproducible fixtures
+    if "projector" in sys.argv[1:] or len(sys.argv) == 1:
+        projector_case()
+        if len(sys.argv) > 1 and not {"cosine", "eval", "collate"} & set(sys.argv[1:]):
+            return
     if "collate" in sys.argv[1:] or len(sys.argv) == 1:
         collate_case()
         if len(sys.argv) > 1 and not {"cosine", "eval"} & set(sys.argv[1:]):

@@ -368,3 +368,15 @@ def collate_batch(notice_store: dict, company_store: dict, notice_idx, company_i
         out[name] = {"dense": np.asarray(st["dense_projected"])[idx].astype(np.float32),
                      "values": cat.reshape(-1).astype(np.int64), "lengths": np.ones(cat.size, dtype=np.int64)}
     return out
+
+
+# ----------------------------------------------------------------------------- feature pre-projection
+def feature_projection(sd: Dict[str, np.ndarray], numeric: Optional[np.ndarray], text: Dict[str, np.ndarray],
+                       text_cols: Sequence[str], dtype=np.float64) -> np.ndarray:
+    """FeatureProjector (src/torchrec_preprocess/feature_projector.py:4-28) + the concat order of the store projection
+    (feature_preprocessor.py:195-205): [Linear2(relu(Linear1(numeric))) | the same text MLP on every text column in order]."""
+    def mlp(x, pre):
+        h = np.maximum(x.astype(dtype) @ sd[f"{pre}.0.weight"].astype(dtype).T + sd[f"{pre}.0.bias"].astype(dtype), 0)
+        return h @ sd[f"{pre}.2.weight"].astype(dtype).T + sd[f"{pre}.2.bias"].astype(dtype)
+    parts = ([mlp(numeric, "num_proj")] if numeric is not None else []) + [mlp(text[c], "text_proj") for c in text_cols if c in text]
+    return np.concatenate(parts, axis=1)

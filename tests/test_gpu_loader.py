@@ -110,3 +110,38 @@ def test_assemble_into_graphed_step_equals_host_collated_batch():
     asm.check()
     for (k, v), (_, v2) in zip(a.state_dict().items(), b.state_dict().items()):
         assert torch.equal(v, v2), k
+
+
+def test_feature_projector_matches_reference_golden_and_feeds_the_store():
+    """our FeatureProjector (same ctor / state_dict / init as the reference's) through tt_linear_forward
+    vs outputs of the unmodified reference (tests/golden/projector.npz), fp32 tolerance 1e-5; project_store writes the
+    concatenated layout straight into a device buffer that a DeviceFeatureStore can serve batches from."""
+    from jodalrob_twotower_b200.loader import DeviceFeatureStore
+    from jodalrob_twotower_b200.projector import FeatureProjector
+    from tests.helpers import rel_err
+    z = np.load(os.path.join(GOLDEN, "projector.npz"))
+    torch.manual_seed(11)
+    fp = FeatureProjector(num_dim=29, text_dim=768, device=DEV)
+    sd = fp.state_dict()
+    ref_sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    assert list(sd) == list(ref_sd)
+    for k in sd:  # same module tree, same RNG consumption: seeded construction reproduces the reference init bit for bit
+        assert torch.equal(sd[k].cpu(), ref_sd[k]), k
+    num = torch.from_numpy(z["numeric"]).to(DEV)
+    text = {"title": torch.from_numpy(z["text.title"]).to(DEV), "body": torch.from_numpy(z["text.body"]).to(DEV)}
+    dp, tp = fp(num, text)
+    assert rel_err(dp.cpu(), torch.from_numpy(z["dense_proj"])) < 1e-5
+    assert rel_err(tp["title"].cpu(), torch.from_numpy(z["proj.title"])) < 1e-5
+    assert rel_err(tp["body"].cpu(), torch.from_numpy(z["proj.body"])) < 1e-5
+    # the store projection: numpy inputs, small batches (ragged last one), concat order numeric | title | body
+    out = fp.project_store(z["numeric"], {"body": z["text.body"], "title": z["text.title"]}, ["title", "body"], batch_size=16)
+    assert out.shape == (41, 384) and rel_err(out.cpu(), torch.from_numpy(z["dense_projected"])) < 1e-5
+    exp = orc.feature_projection({k: v.numpy() for k, v in ref_sd.items()}, z["numeric"], {"title": z["text.title"], "body": z["text.body"]},
+                                 ["title", "body"])
+    assert np.abs(out.cpu().numpy() - exp).max() <= 1e-5 * np.abs(exp).max()
+    assert fp.project_store(None, {}, None) is None and fp.project_store(z["numeric"][:0], None).shape == (0, 128)
+    # ... and serves batches without ever leaving the GPU
+    st = DeviceFeatureStore(out, np.zeros((41, 1), dtype=np.int64), ["k"], DEV)
+    idx = torch.tensor([40, 0, 7, 7], device=DEV)
+    d_, _ = st.gather(idx)
+    assert torch.equal(d_, out[idx])

@@ -199,3 +199,16 @@ def test_collate_oracle_matches_reference_collate_fn():
     with pytest.raises(IndexError):
         orc.collate_batch({"dense_projected": z["notice_store.dense"], "categorical": z["notice_store.cat"]},
                           {"dense_projected": z["company_store.dense"], "categorical": z["company_store.cat"]}, [10 ** 6], [0])
+
+
+def test_feature_projection_oracle_matches_reference_projector():
+    """oracle feature_projection vs outputs of the unmodified reference FeatureProjector (tests/golden/projector.npz)."""
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "projector.npz"))
+    sd = {k[3:]: z[k] for k in z.files if k.startswith("sd.")}
+    got = orc.feature_projection(sd, z["numeric"], {"title": z["text.title"], "body": z["text.body"]}, ["title", "body"])
+    assert got.shape == z["dense_projected"].shape
+    assert np.abs(got - z["dense_projected"]).max() <= 1e-5 * np.abs(z["dense_projected"]).max()
+    only_text = orc.feature_projection(sd, None, {"body": z["text.body"]}, ["title", "body"])
+    assert np.abs(only_text - z["proj.body"]).max() <= 1e-5 * np.abs(z["proj.body"]).max()
