@@ -126,7 +126,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     for i in range(args.steps):
         out = tr.step(batches[i % len(batches)])
-        float(out["loss"])
+        float(out["loss"].detach())
     dt = time.perf_counter() - t0
     val = B * args.steps / dt
     sample = f"{args.steps} steps of B={B} (bounded sample of the B={args.batch} workload), decode=as-is python loop, {cores} threads"
