@@ -308,6 +308,18 @@ int tt_simce_finalize(const float* row_sumexp, const float* col_sumexp, const fl
                       int64_t diag_offset, int64_t B_global, float inv_temp, float label_smoothing, float* inv_row,
                       float* inv_col, double* partial, tt_stream_t stream);
 int tt_simce_scalars(const double* partial, int64_t B_global, float* out5, tt_stream_t stream);
+/* Split forward for the train step (bf16 path only). tt_simce_forward_sums produces what the BACKWARD needs — row / column sums
+ * of exp, their reciprocals inv_row / inv_col (== tt_simce_finalize's) and diag; tt_simce_forward_metrics finishes what only the
+ * loss value and the metrics need (row_sum_s, col_sum_s or NULL, row_argmax) from the partials left in the workspace, e.g. on a
+ * side stream next to the backward pass. Together they write exactly what tt_simce_forward writes. The workspace
+ * (tt_simce_split_workspace_bytes) must stay untouched between the two calls. */
+int64_t tt_simce_split_workspace_bytes(int64_t Bx, int64_t By, int32_t F);
+int tt_simce_forward_sums(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
+                          int64_t diag_offset, float* row_sumexp, float* col_sumexp, float* inv_row, float* inv_col, float* diag,
+                          void* workspace, int64_t workspace_bytes, tt_stream_t stream);
+int tt_simce_forward_metrics(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
+                             float* row_sum_s, float* col_sum_s, int32_t* row_argmax, void* workspace, int64_t workspace_bytes,
+                             tt_stream_t stream);
 /* backward: dX[Bx,F] (f32) = dS · Y with
  *   dS_ij = gscale * (exp(S_ij - inv_temp) * (inv_x[i] + inv_y[j]) - 2*((1-ls)*[j == diag_offset+i] + ls/B_global))
  * gscale = dloss * 0.5 / B_global * inv_temp.  Call once with (X=notice, Y=company) for d notice and

@@ -372,6 +372,43 @@ int tt_simce_forward(const void* X, const void* Y, int64_t Bx, int64_t By, int32
   return TT_OK;
 }
 
+/* Split forward for the train step (bf16 / tcgen05 path): what the BACKWARD needs — sum_j exp for rows and columns and their
+ * reciprocals — is produced by tt_simce_forward_sums; what only the loss value and the metrics need (sum_j S_ij, arg-max) by
+ * tt_simce_forward_metrics from the partials the first call left in the workspace, typically on a side stream next to the
+ * backward pass. Together they write exactly what tt_simce_forward writes. */
+int64_t tt_simce_split_workspace_bytes(int64_t Bx, int64_t By, int32_t F) {
+  return (F == 64 || F == 128) ? 2 * a256(simce_tc_workspace_bytes(Bx, By, F)) : 0;
+}
+
+int tt_simce_forward_sums(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
+                          int64_t diag_offset, float* row_sumexp, float* col_sumexp, float* inv_row, float* inv_col, float* diag,
+                          void* workspace, int64_t workspace_bytes, tt_stream_t stream) {
+  TT_CHECK_ARG(X && Y && row_sumexp && col_sumexp && inv_row && inv_col && diag && Bx > 0 && By > 0, "tt_simce_forward_sums: bad arguments");
+  TT_CHECK_ARG(dtype == TT_BF16 && (F == 64 || F == 128), "tt_simce_forward_sums: bf16 with final_embedding_dim 64 or 128 only");
+  TT_CHECK_ARG(diag_offset >= 0 && diag_offset + Bx <= By, "tt_simce_forward_sums: diagonal outside By");
+  TT_CHECK_ARG(workspace && workspace_bytes >= tt_simce_split_workspace_bytes(Bx, By, F), "tt_simce_forward_sums: workspace too small");
+  TT_CHECK_ARG(inv_temp > 0.f && inv_temp <= 40.f, "tt_simce_forward_sums: temperature must be >= 0.025");
+  TT_CHECK_ARG(((uintptr_t)X & 15) == 0 && ((uintptr_t)Y & 15) == 0, "tt_simce_forward_sums: operands must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  char* w1 = (char*)workspace + a256(simce_tc_workspace_bytes(Bx, By, F));
+  int rc = simce_tc_rows(X, Y, Bx, By, F, inv_temp, diag_offset, row_sumexp, nullptr, diag, nullptr, 1, workspace, s, 1, inv_row);
+  if (rc != TT_OK) return rc;
+  return simce_tc_rows(Y, X, By, Bx, F, inv_temp, 0, col_sumexp, nullptr, nullptr, nullptr, 0, w1, s, 1, inv_col);
+}
+
+int tt_simce_forward_metrics(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
+                             float* row_sum_s, float* col_sum_s, int32_t* row_argmax, void* workspace, int64_t workspace_bytes,
+                             tt_stream_t stream) {
+  TT_CHECK_ARG(X && Y && row_sum_s && row_argmax && Bx > 0 && By > 0, "tt_simce_forward_metrics: bad arguments");
+  TT_CHECK_ARG(dtype == TT_BF16 && (F == 64 || F == 128), "tt_simce_forward_metrics: bf16 with final_embedding_dim 64 or 128 only");
+  TT_CHECK_ARG(workspace && workspace_bytes >= tt_simce_split_workspace_bytes(Bx, By, F), "tt_simce_forward_metrics: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  char* w1 = (char*)workspace + a256(simce_tc_workspace_bytes(Bx, By, F));
+  int rc = simce_tc_rows_metrics(X, Y, Bx, By, F, inv_temp, row_sum_s, row_argmax, workspace, s);
+  if (rc != TT_OK || !col_sum_s) return rc;
+  return simce_tc_rows_metrics(Y, X, By, Bx, F, inv_temp, col_sum_s, nullptr, w1, s);
+}
+
 int tt_simce_finalize(const float* row_sumexp, const float* col_sumexp, const float* row_sum_s,
                       const float* col_sum_s, const float* diag, const int32_t* row_argmax, int64_t Bx, int64_t By,
                       int64_t diag_offset, int64_t B_global, float inv_temp, float label_smoothing, float* inv_row,

@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(32 * RR_LANES)
 tc_rows_reduce_kernel(const float* __restrict__ row_e, const float* __restrict__ row_max, const int32_t* __restrict__ row_arg,
                       int64_t Bx, int n_ct, long long T, int G, const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Y, int64_t By,
                       int F, float inv_temp, const float* __restrict__ ysum_part, float* __restrict__ out_e,
-                      float* __restrict__ out_s, int32_t* __restrict__ out_arg) {
+                      float* __restrict__ out_s, int32_t* __restrict__ out_arg, float* __restrict__ out_inv) {
   __shared__ float sh_e[RR_LANES][32], sh_m[RR_LANES][32], sh_d[2 * RR_LANES][32], sh_y[128];
   __shared__ int32_t sh_a[RR_LANES][32];
   const int r = threadIdx.x & 31, q = threadIdx.x >> 5;
@@ -664,7 +664,8 @@ tc_rows_reduce_kernel(const float* __restrict__ row_e, const float* __restrict__
         arg = ta;
       }
     }
-    if (ok) out_e[m] = e;
+    if (ok && out_e) out_e[m] = e;
+    if (ok && out_inv) out_inv[m] = 1.f / e;  // the row scale of the backward pass (same expression as tt_simce_finalize)
     sh_a[0][r] = arg;
   }
   __syncthreads();
@@ -840,9 +841,11 @@ static int g_tc_force_manual = 0;
 static long long* g_tc_dbg_ts = nullptr;
 
 // rows statistics of S = X Y^T (bf16 inputs).  want_metrics: also max/argmax/diag.
+// sums_only: only the row sums (and their reciprocals, out_inv) are reduced here; simce_tc_rows_metrics finishes the job later
+// from the partials this call leaves in `workspace`.
 int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, float inv_temp, int64_t diag_offset,
                   float* row_sumexp, float* row_sum_s, float* diag, int32_t* row_argmax, int want_metrics, void* workspace,
-                  cudaStream_t s) {
+                  cudaStream_t s, int sums_only, float* out_inv) {
   TcPlan pl = make_plan(Bx, By);
   TcParams p = {};
   p.X = (const __nv_bfloat16*)X;
@@ -866,11 +869,37 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   const size_t smem = tc_smem_bytes(F, false);
   TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   simce_tc_kernel<false><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, my, p);
+  if (sums_only) {
+    tc_rows_reduce_kernel<<<ceil_div(Bx, 32), 32 * RR_LANES, 0, s>>>(p.row_e, p.row_max, p.row_arg, Bx, pl.n_col_tiles, pl.total_tiles,
+                                                                     pl.grid, p.X, p.Y, By, F, inv_temp, nullptr, row_sumexp, nullptr,
+                                                                     nullptr, out_inv);
+    TT_LAUNCH_CHECK("simce_tc_rows(sums)");
+    return TT_OK;
+  }
   if (row_sum_s) tc_ysum_partial_kernel<<<YS_BLOCKS, 512, 0, s>>>(p.Y, By, F, ysum_part);
   tc_rows_reduce_kernel<<<ceil_div(Bx, 32), 32 * RR_LANES, 0, s>>>(p.row_e, p.row_max, p.row_arg, Bx, pl.n_col_tiles, pl.total_tiles, pl.grid, p.X, p.Y, By, F,
                                                                    inv_temp, ysum_part, row_sumexp, row_sum_s,
-                                                                   want_metrics ? row_argmax : nullptr);
+                                                                   want_metrics ? row_argmax : nullptr, out_inv);
   TT_LAUNCH_CHECK("simce_tc_rows");
+  return TT_OK;
+}
+
+// The part of the forward statistics that only the loss VALUE and the metrics need (sum_j S_ij, arg-max), from the partials a
+// sums_only simce_tc_rows call left in `workspace`: off the critical path of the train step.
+int simce_tc_rows_metrics(const void* X, const void* Y, int64_t Bx, int64_t By, int F, float inv_temp, float* row_sum_s,
+                          int32_t* row_argmax, void* workspace, cudaStream_t s) {
+  TcPlan pl = make_plan(Bx, By);
+  const int64_t stride = (4 * pl.max_parts * Bx * 4 + 255) / 256 * 256;
+  char* w = (char*)workspace;
+  const float* row_e = (const float*)w;
+  const float* row_max = (const float*)(w + stride);
+  const int32_t* row_arg = (const int32_t*)(w + 2 * stride);
+  float* ysum_part = (float*)(w + 3 * stride);
+  if (row_sum_s) tc_ysum_partial_kernel<<<YS_BLOCKS, 512, 0, s>>>((const __nv_bfloat16*)Y, By, F, ysum_part);
+  tc_rows_reduce_kernel<<<ceil_div(Bx, 32), 32 * RR_LANES, 0, s>>>(row_e, row_max, row_arg, Bx, pl.n_col_tiles, pl.total_tiles, pl.grid,
+                                                                   (const __nv_bfloat16*)X, (const __nv_bfloat16*)Y, By, F, inv_temp,
+                                                                   ysum_part, nullptr, row_sum_s, row_argmax, nullptr);
+  TT_LAUNCH_CHECK("simce_tc_rows_metrics");
   return TT_OK;
 }
 

@@ -238,7 +238,6 @@ class DistributedEngine(TwoTowerEngine):
                            for i, name in enumerate(self.PEER_SITES)}
         self.peer_epochs = torch.zeros(len(self.PEER_SITES), dtype=torch.int64, device=dev)
         self.peer_counts = torch.zeros(len(self.PEER_SITES), dtype=torch.int32, device=dev)
-        self._metrics_stream = torch.cuda.Stream(dev)
         self._small_stream = torch.cuda.Stream(dev)
         self._peer_dummy = torch.zeros(1, dtype=torch.float64, device=dev)
         self._peer_dummy2 = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -392,12 +391,6 @@ class DistributedEngine(TwoTowerEngine):
             self._peer_allreduce(self._peer_dummy2, 1, "dcbar")
         else:
             self.comm.barrier(self.device)
-
-    def _end_of_step(self, ws: _Ws):
-        ev = getattr(ws, "metrics_done", None)
-        if ev is not None:
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            ws.metrics_done = None
 
     def loss_forward(self, ws: _Ws):
         cfg, B, s = self.cfg, ws.B, self._stream()

@@ -121,6 +121,8 @@ class TwoTowerEngine:
         # lands next to the first sim-CE pass, whose persistent CTAs then find SMs occupied — so it is off by default.
         self.split_dense_adam = os.environ.get("TT_SPLIT_ADAM", "0") != "0"
         self.hyper_on_helper = os.environ.get("TT_HYPER_HELPER", "1") != "0"
+        self.defer_metrics = os.environ.get("TT_DEFER_METRICS", "1") != "0"
+        self._metrics_stream = torch.cuda.Stream(self.device)
         self._arm_split = False
         self._in_fused = False
         self.default_layout = value_layout
@@ -338,6 +340,11 @@ class TwoTowerEngine:
         ws.row_argmax = torch.empty(B, dtype=torch.int32, device=dev)
         ws.inv_row = torch.empty(B, **f32)
         ws.inv_col = torch.empty(B, **f32)
+        # deferred-metrics forward (fused step, bf16): its own workspace (the backward calls reuse sim_ws while the metrics stream
+        # still reads the forward partials) and scratch outputs for the reciprocals tt_simce_finalize recomputes there
+        split_bytes = q("tt_simce_split_workspace_bytes", B, B, cfg.final_dim) if self.emb_tt != TT_F32 else 0
+        ws.sim_ws_fwd = torch.empty(max(split_bytes, 16), dtype=torch.uint8, device=dev)
+        ws.inv_scratch = [torch.empty(B, **f32), torch.empty(B, **f32)]
         ws.partial = torch.zeros(128, dtype=torch.float64, device=dev)  # 16 block partials x 8
         ws.out5 = torch.zeros(5, **f32)
         ws.sort_ws = torch.empty(q("tt_ebc_sort_workspace_bytes", n_tot, max(self.total_rows, 1)), dtype=torch.uint8, device=dev)
@@ -478,6 +485,32 @@ class TwoTowerEngine:
         self.profile_tag = ""
         inv_t = 1.0 / cfg.temperature
         css = ptr(ws.col_sum_s) if cfg.label_smoothing > 0 else 0  # column sums of S are only needed for label smoothing
+        if (self.emb_tt != TT_F32 and self._in_fused and self.profile is None and self.defer_metrics and self.two_streams
+                and ws.sim_ws_fwd.numel() > 16):
+            # Fused step, tensor-core path: only the row/column sums of exp (and their reciprocals) are on the critical path — the
+            # backward needs nothing else. sum_j S_ij, the arg-max resolution, the loss partials and the five scalars run on a side
+            # stream from the partials left in the workspace and are joined at the end of the step (_end_of_step).
+            main = torch.cuda.current_stream(self.device)
+            self._call("tt_simce_forward_sums", ptr(ws.e[0]), ptr(ws.e[1]), B, B, cfg.final_dim, self.emb_tt, inv_t, 0,
+                       ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.inv_row), ptr(ws.inv_col), ptr(ws.diag), ptr(ws.sim_ws_fwd),
+                       ws.sim_ws_fwd.numel(), s, n_kernels=4)
+
+            def metrics():  # launched by fused_step BEHIND the backward logits passes (see there)
+                ms_ = self._metrics_stream
+                ms_.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(ms_):
+                    ms = ms_.cuda_stream
+                    self._call("tt_simce_forward_metrics", ptr(ws.e[0]), ptr(ws.e[1]), B, B, cfg.final_dim, self.emb_tt, inv_t,
+                               ptr(ws.row_sum_s), css, ptr(ws.row_argmax), ptr(ws.sim_ws_fwd), ws.sim_ws_fwd.numel(), ms, n_kernels=2)
+                    self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), css, ptr(ws.diag),
+                               ptr(ws.row_argmax), B, B, 0, B, inv_t, cfg.label_smoothing, ptr(ws.inv_scratch[0]),
+                               ptr(ws.inv_scratch[1]), ptr(ws.partial), ms)
+                    self._call("tt_simce_scalars", ptr(ws.partial), B, ptr(ws.out5), ms)
+                    ws.metrics_done = torch.cuda.Event()
+                    ws.metrics_done.record(ms_)
+
+            ws.deferred_metrics = metrics
+            return ws.out5
         self._call("tt_simce_forward", ptr(ws.e[0]), ptr(ws.e[1]), B, B, cfg.final_dim, self.emb_tt, inv_t, 0, ptr(ws.row_sumexp),
                    ptr(ws.col_sumexp), ptr(ws.row_sum_s), css, ptr(ws.diag), ptr(ws.row_argmax),
                    ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=4)
@@ -777,6 +810,13 @@ class TwoTowerEngine:
             # sort-dedup already ran underneath the forward pass) the large-table segment-sum + Adam, which starts as soon as
             # both concat-buffer gradients exist and overlaps the first-layer weight gradients and the small-table reductions.
             self.loss_backward(ws)
+            dm = getattr(ws, "deferred_metrics", None)
+            if dm is not None:
+                # Only now: the persistent logits kernels need every SM, and small kernels of a side stream launched next to them
+                # were measured to delay their CTAs (369 vs 362 us per step). Behind the backward passes the metrics kernels share
+                # the machine with the towers' small backward kernels instead.
+                dm()
+                ws.deferred_metrics = None
             self._side.wait_stream(main)
             self._hi0.wait_stream(main)
             def table_update():  # on `_side`, right behind the company tower's last data gradient
@@ -815,8 +855,11 @@ class TwoTowerEngine:
         return None
 
     def _end_of_step(self, ws: _Ws):
-        """Hook at the very end of the fused step (main stream). Distributed engines join their deferred metrics stream here."""
-        return None
+        """The very end of the fused step (main stream): join the deferred loss / metrics stream."""
+        ev = getattr(ws, "metrics_done", None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            ws.metrics_done = None
 
     def hyper_host(self) -> dict:
         import struct
