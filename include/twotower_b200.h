@@ -234,6 +234,9 @@ int tt_linear_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, flo
  * W_bf16 is a bf16 copy of the fp32 master weight (tt_cast_bf16), dW / dbias stay fp32.  All leading dimensions must
  * be multiples of 8 elements and all pointers 16-byte aligned (TMA).  out_dtype selects bf16 or fp32 for C / dX. */
 int tt_cast_bf16(const float* src, void* dst, int64_t n, tt_stream_t stream);
+/* up to four casts in one launch (segments with n <= 0 are skipped): the weight mirror and both dense inputs of a step */
+int tt_cast_bf16_multi(const float* src0, void* dst0, int64_t n0, const float* src1, void* dst1, int64_t n1, const float* src2,
+                       void* dst2, int64_t n2, const float* src3, void* dst3, int64_t n3, tt_stream_t stream);
 int tt_linear_forward_bf16(const void* A, int64_t lda, const void* W_bf16, const float* bias, void* C, int64_t ldc,
                            int32_t out_dtype, int64_t M, int32_t N, int32_t K, int32_t relu, tt_stream_t stream);
 int tt_linear_dgrad_bf16(const void* dY, int64_t ldy, const void* W_bf16, void* dX, int64_t ldx, int32_t out_dtype, int64_t M,

@@ -216,6 +216,27 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   }
 }
 
+// several fp32 -> bf16 casts in ONE launch (blockIdx.y = segment): at the start of the captured train step every extra root
+// node costs 5-9 us of launch ramp, so the weight mirror and the two dense inputs are cast together
+struct CastSegs {
+  const float* src[4];
+  __nv_bfloat16* dst[4];
+  int64_t n[4];
+};
+__global__ void __launch_bounds__(256) cast_bf16_multi_kernel(const CastSegs segs) {
+  const float* __restrict__ src = segs.src[blockIdx.y];
+  __nv_bfloat16* __restrict__ dst = segs.dst[blockIdx.y];
+  const int64_t n = segs.n[blockIdx.y];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      *reinterpret_cast<uint2*>(dst + i) = pack_bf16x4(*reinterpret_cast<const float4*>(src + i));
+    } else {
+      for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+  }
+}
+
 // column sums of a bf16 matrix (bias gradients), fp64 partials like the fp32 path
 constexpr int GCS_ROWS = 64;
 __global__ void __launch_bounds__(256)
@@ -288,6 +309,32 @@ int tt_cast_bf16(const float* src, void* dst, int64_t n, tt_stream_t stream) {
   const int64_t cap = (int64_t)sm_count() * 8;
   cast_bf16_kernel<<<(int)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
   TT_LAUNCH_CHECK("cast_bf16_kernel");
+  return TT_OK;
+}
+
+int tt_cast_bf16_multi(const float* src0, void* dst0, int64_t n0, const float* src1, void* dst1, int64_t n1, const float* src2,
+                       void* dst2, int64_t n2, const float* src3, void* dst3, int64_t n3, tt_stream_t stream) {
+  CastSegs segs = {};
+  const float* srcs[4] = {src0, src1, src2, src3};
+  void* dsts[4] = {dst0, dst1, dst2, dst3};
+  const int64_t ns[4] = {n0, n1, n2, n3};
+  int cnt = 0;
+  int64_t n_max = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (ns[i] <= 0) continue;
+    TT_CHECK_ARG(srcs[i] && dsts[i], "tt_cast_bf16_multi: NULL segment %d", i);
+    TT_CHECK_ARG((((uintptr_t)srcs[i]) & 15) == 0 && (((uintptr_t)dsts[i]) & 7) == 0, "tt_cast_bf16_multi: segment %d is misaligned", i);
+    segs.src[cnt] = srcs[i];
+    segs.dst[cnt] = (__nv_bfloat16*)dsts[i];
+    segs.n[cnt] = ns[i];
+    n_max = ns[i] > n_max ? ns[i] : n_max;
+    ++cnt;
+  }
+  if (cnt == 0) return TT_OK;
+  int64_t want = ceil_div(n_max, 1024);
+  const int64_t cap = (int64_t)sm_count() * 4;
+  cast_bf16_multi_kernel<<<dim3((unsigned)(want > cap ? cap : want), cnt), 256, 0, (cudaStream_t)stream>>>(segs);
+  TT_LAUNCH_CHECK("cast_bf16_multi_kernel");
   return TT_OK;
 }
 

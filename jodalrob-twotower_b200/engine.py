@@ -415,7 +415,7 @@ class TwoTowerEngine:
                        self.KL[t], self.P_tot // E, ws.rows.data_ptr() + 4 * rows_off, s)
         ws.values, ws.layout = list(values), layout
 
-    def tower_prefix(self, t: int, ws: _Ws, dense: torch.Tensor):
+    def tower_prefix(self, t: int, ws: _Ws, dense: torch.Tensor, cast_done: bool = False):
         """The part of a tower that does not need the embedding lookup: the dense projection into columns [0, H0) of the
         concat buffer. The train step runs it on a helper stream underneath the lookup."""
         cfg, B, s = self.cfg, ws.B, self._stream()
@@ -428,7 +428,8 @@ class TwoTowerEngine:
         if dense.dtype != torch.float32:
             dense = dense.float()
         if self.act != TT_F32:
-            self._call("tt_cast_bf16", ptr(dense), ptr(ws.x16[t]), B * dense_dim, s)
+            if not cast_done:
+                self._call("tt_cast_bf16", ptr(dense), ptr(ws.x16[t]), B * dense_dim, s)
             dense = ws.x16[t]
         self._lin_fwd(dense, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", ws.c[t], ld, False, B, H0,
                       dense_dim, 0)
@@ -533,15 +534,21 @@ class TwoTowerEngine:
         lay = TT_LAYOUT_KEY_MAJOR if (layout or self.default_layout) == "key_major" else TT_LAYOUT_SAMPLE_MAJOR
         ws = self.workspace(B)
         ws.inputs = (notice_dense.contiguous(), company_dense.contiguous())
-        self.refresh_bf16_weights()
         main = torch.cuda.current_stream(self.device)
         overlap = self.two_streams and self.profile is None
+        one_cast = overlap and self.act != TT_F32 and all(d.dtype == torch.float32 for d in ws.inputs)
+        if one_cast:  # the bf16 weight mirror and both dense inputs in ONE launch: every extra root node of the graph costs
+            nd_, cd_ = ws.inputs  # 5-9 us of launch ramp at the start of a replay
+            self._call("tt_cast_bf16_multi", ptr(self.dense_w), ptr(self.dense_w16), self.layout.total, ptr(nd_), ptr(ws.x16[0]),
+                       nd_.numel(), ptr(cd_), ptr(ws.x16[1]), cd_.numel(), 0, 0, 0, self._stream())
+        else:
+            self.refresh_bf16_weights()
         if overlap:  # the dense projections do not need the lookup: run them underneath it on helper streams
             pre = self._pre_streams  # high priority: their GEMM CTAs take the SM slots the lookup's first wave frees
             for t, d in ((0, notice_dense), (1, company_dense)):
                 pre[t].wait_stream(main)
                 with torch.cuda.stream(pre[t]):
-                    self.tower_prefix(t, ws, d)
+                    self.tower_prefix(t, ws, d, cast_done=one_cast)
         split = overlap and not self.sharded_lookup
         if split:  # the two towers' lookups side by side (the company tower continues on `_side` anyway)
             self._side.wait_stream(main)
