@@ -122,6 +122,7 @@ class TwoTowerEngine:
         self.split_dense_adam = os.environ.get("TT_SPLIT_ADAM", "0") != "0"
         self.hyper_on_helper = os.environ.get("TT_HYPER_HELPER", "1") != "0"
         self.defer_metrics = os.environ.get("TT_DEFER_METRICS", "1") != "0"
+        self.one_cast = os.environ.get("TT_ONE_CAST", "0") != "0"  # experiment, not yet measured on hardware: off by default
         self._metrics_stream = torch.cuda.Stream(self.device)
         self._arm_split = False
         self._in_fused = False
@@ -536,7 +537,7 @@ class TwoTowerEngine:
         ws.inputs = (notice_dense.contiguous(), company_dense.contiguous())
         main = torch.cuda.current_stream(self.device)
         overlap = self.two_streams and self.profile is None
-        one_cast = overlap and self.act != TT_F32 and all(d.dtype == torch.float32 for d in ws.inputs)
+        one_cast = (overlap and self.one_cast and self.act != TT_F32 and all(d.dtype == torch.float32 for d in ws.inputs))
         if one_cast:  # the bf16 weight mirror and both dense inputs in ONE launch: every extra root node of the graph costs
             nd_, cd_ = ws.inputs  # 5-9 us of launch ramp at the start of a replay
             self._call("tt_cast_bf16_multi", ptr(self.dense_w), ptr(self.dense_w16), self.layout.total, ptr(nd_), ptr(ws.x16[0]),
