@@ -212,3 +212,50 @@ def test_feature_projection_oracle_matches_reference_projector():
     assert np.abs(got - z["dense_projected"]).max() <= 1e-5 * np.abs(z["dense_projected"]).max()
     only_text = orc.feature_projection(sd, None, {"body": z["text.body"]}, ["title", "body"])
     assert np.abs(only_text - z["proj.body"]).max() <= 1e-5 * np.abs(z["proj.body"]).max()
+
+
+def test_pooled_oracle_consistency_with_torch_autograd_and_single_id_reference_case():
+    """The L>1 (multi-hot) oracle has no reference counterpart (parity unpinned); what CAN be pinned on CPU:
+    (1) with one id per bag it equals the reference-pinned decode_clamp + per-key gather; (2) its dense gradients equal torch
+    autograd through F.embedding_bag(mode='sum') on clamped ids; (3) key-major and sample-major agree after the layout permutation."""
+    g = torch.Generator().manual_seed(0)
+    vocab, E, B = [7, 40, 300], 8, 13
+    K = len(vocab)
+    tables = [torch.randn(v, E, generator=g) for v in vocab]
+    ids = torch.stack([torch.randint(-2, v + 3, (B,), generator=g) for v in vocab], 1)  # includes out-of-range ids
+    unit = torch.arange(B * K + 1)
+    out = orc.pooled_forward(tables, ids.reshape(-1), unit, B)
+    dec = orc.decode_clamp(ids.reshape(-1).numpy(), vocab)  # [B, K], the reference-pinned clamp
+    exp = torch.cat([tables[k][torch.from_numpy(dec[:, k]).long()] for k in range(K)], 1)
+    assert torch.equal(out, exp)
+    # jagged bags + gradients vs autograd
+    lengths = torch.randint(0, 5, (B * K,), generator=g)
+    offs = torch.zeros(B * K + 1, dtype=torch.int64)
+    offs[1:] = torch.cumsum(lengths, 0)
+    vals = torch.cat([torch.randint(0, vocab[j % K], (int(lengths[j]),), generator=g) for j in range(B * K)])
+    leaf = [t.clone().requires_grad_(True) for t in tables]
+    parts = []
+    for b in range(B):
+        row = []
+        for k in range(K):
+            lo, hi = int(offs[b * K + k]), int(offs[b * K + k + 1])
+            row.append(torch.nn.functional.embedding_bag(vals[lo:hi], leaf[k], torch.tensor([0]), mode="sum")[0] if hi > lo
+                       else torch.zeros(E))
+        parts.append(torch.cat(row))
+    pooled = torch.stack(parts)
+    assert torch.allclose(pooled, orc.pooled_forward(tables, vals, offs, B), atol=1e-6)
+    grad = torch.randn(B, K * E, generator=g)
+    pooled.backward(grad)
+    gs = orc.pooled_dense_grads(vocab, E, vals, offs, B, grad)
+    for k in range(K):
+        assert torch.allclose(leaf[k].grad, gs[k], atol=1e-5), k
+    touched = orc.pooled_touched(vocab, vals, offs, B)
+    for k in range(K):
+        assert torch.equal(touched[k], (gs[k].abs().sum(1) > 0) | touched[k])  # every row with a gradient is marked touched
+    # key-major == sample-major after permuting the bags
+    perm = torch.tensor([b * K + k for k in range(K) for b in range(B)])
+    lens_km = lengths[perm]
+    offs_km = torch.zeros(B * K + 1, dtype=torch.int64)
+    offs_km[1:] = torch.cumsum(lens_km, 0)
+    vals_km = torch.cat([vals[int(offs[j]):int(offs[j + 1])] for j in perm.tolist()]) if int(lengths.sum()) else vals
+    assert torch.equal(orc.pooled_forward(tables, vals_km, offs_km, B, layout="key_major"), orc.pooled_forward(tables, vals, offs, B))
