@@ -122,7 +122,10 @@ class TwoTowerEngine:
         self.split_dense_adam = os.environ.get("TT_SPLIT_ADAM", "0") != "0"
         self.hyper_on_helper = os.environ.get("TT_HYPER_HELPER", "1") != "0"
         self.defer_metrics = os.environ.get("TT_DEFER_METRICS", "1") != "0"
-        self.one_cast = os.environ.get("TT_ONE_CAST", "0") != "0"  # experiment, not yet measured on hardware: off by default
+        # TT_ONE_CAST=1: bf16 weight mirror + both dense inputs cast in one launch at the start of the step. Measured on B200:
+        # identical loss bit for bit, but 361.6 us per step against 356.6 us with the three separate casts (the single launch
+        # sits in front of both lookups and both projection GEMMs) — off.
+        self.one_cast = os.environ.get("TT_ONE_CAST", "0") != "0"
         self._metrics_stream = torch.cuda.Stream(self.device)
         self._arm_split = False
         self._in_fused = False
