@@ -133,3 +133,21 @@ def test_gloo_world2_routing_covers_every_id_once():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_sass_shows_blackwell_native_instructions():
+    """What proves a Blackwell-native kernel without a GPU (B200_PROFILING.md): the built library's SASS carries tcgen05 MMAs
+    (UTCHMMA), tensor-memory loads/stores (LDTM/STTM) and TMA loads (UTMALDG), and no legacy mma.sync path (HMMA)."""
+    import shutil
+    import subprocess
+    from jodalrob_twotower_b200 import native
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump) and shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", native.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "MUFU.EX2"):
+        assert mnemonic in sass, f"{mnemonic} missing from the SASS of {native.LIB_PATH}"
+    kernels = {k: sass.count(k) for k in ("simce_tc_kernel", "gemm_tc_kernel")}
+    assert all(v > 0 for v in kernels.values()), kernels
+    assert " HMMA" not in sass and "HGMMA" not in sass  # no mma.sync / wgmma fallbacks
