@@ -259,3 +259,29 @@ def test_pooled_oracle_consistency_with_torch_autograd_and_single_id_reference_c
     offs_km[1:] = torch.cumsum(lens_km, 0)
     vals_km = torch.cat([vals[int(offs[j]):int(offs[j + 1])] for j in perm.tolist()]) if int(lengths.sum()) else vals
     assert torch.equal(orc.pooled_forward(tables, vals_km, offs_km, B, layout="key_major"), orc.pooled_forward(tables, vals, offs, B))
+
+
+def test_oracle_integer_stage_properties():
+    """Definition-level properties of the integer oracles the GPU tests compare against bit-exactly (randomised, CPU)."""
+    rng = np.random.default_rng(12)
+    for _ in range(20):
+        B, n = int(rng.integers(1, 40)), int(rng.integers(1, 60))
+        S = rng.integers(-3, 4, (B, max(B, n))).astype(np.float32)  # many exact ties
+        off = int(rng.integers(0, S.shape[1] - B + 1))
+        r = orc.positive_ranks(S, off)
+        for i in range(B):
+            p, d = off + i, S[i, off + i]
+            assert r[i] == int((S[i] > d).sum() + (S[i, :p] == d).sum())  # greater ones + equal ones before it (stable order)
+        rows = rng.integers(0, 9, n).astype(np.int32)
+        sd = orc.sort_dedup(rows)
+        assert np.array_equal(sd["sorted_rows"], np.sort(rows, kind="stable"))
+        assert np.array_equal(rows[sd["positions"]], sd["sorted_rows"])
+        for a, b in zip(sd["seg_starts"][:-1], sd["seg_starts"][1:]):  # inside a row the positions ascend: fixed summation order
+            assert (np.diff(sd["positions"][a:b]) > 0).all()
+        vocab = [int(v) for v in rng.integers(1, 50, 4)]
+        world = int(rng.integers(1, 6))
+        ids = np.stack([rng.integers(0, v, 11) for v in vocab], 1)
+        owner, local = orc.rw_shard(ids, vocab, world)
+        blk = np.array([orc.rw_block(v, world) for v in vocab])
+        assert ((owner >= 0) & (owner < world)).all() and (local >= 0).all() and (local < blk).all()
+        assert np.array_equal(owner * blk + local, ids)  # the shard map is a bijection onto the ids
