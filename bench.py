@@ -99,70 +99,133 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
+REF_COPY = os.path.join(ROOT, "oracle", "_ref")
+
+
+class RefStepper:
+    """One reference train step on the host cores: zero_grad -> forward(return_metrics=True) -> backward -> Adam.step ->
+    scheduler.step (scripts/train.py:319-330). kind "reference": the UNMODIFIED reference modules from oracle/_ref (verbatim copy
+    made by oracle/make_ref.py; incl. its per-scalar KJT decode loop cat_embed.py:103-121, its per-forward parameter loops
+    base_tower.py:115-127 and the allclose sync two_tower_model.py:81-87), through oracle/ref_harness.py's two shims. kind "port":
+    oracle/ref_port.py (bit-exact restatement) when the copy is absent. Never reads /root/reference."""
+
+    def __init__(self, schema, decode="loop"):
+        self.schema = schema
+        self.kind = "port"
+        have_ref = os.path.isfile(os.path.join(REF_COPY, "src", "towers", "two_tower_train_task.py"))
+        if have_ref and decode == "loop":
+            os.environ["TT_REFERENCE_ROOT"] = REF_COPY
+            from oracle import ref_harness as rh
+            self.rh = rh
+            self.task, self.nk, self.ck = rh.build_reference_task(
+                MODEL["emb_dim"], MODEL["notice_dense"], MODEL["company_dense"], MODEL["hidden"], MODEL["final_dim"],
+                MODEL["dropout"], MODEL["temperature"], seed=0)
+            got = {"notice": [[k, self.task.two_tower_model.notice_tower.categorical_embedder.vocab_sizes[k]] for k in self.nk],
+                   "company": [[k, self.task.two_tower_model.company_tower.categorical_embedder.vocab_sizes[k]] for k in self.ck]}
+            assert got == {"notice": [list(x) for x in schema["notice"]], "company": [list(x) for x in schema["company"]]}, \
+                "oracle/_ref schema differs from tests/golden/schema_readme_default.json"
+            self.task.train()
+            self.opt = torch.optim.Adam(self.task.parameters(), lr=MODEL["lr"], weight_decay=MODEL["weight_decay"])
+            self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda s_: 1.0)
+            self.kind = "reference"
+        else:
+            from oracle import ref_port
+            self.rp = ref_port
+            task = ref_port.build_port_task(schema, MODEL["emb_dim"], MODEL["notice_dense"], MODEL["company_dense"], MODEL["hidden"],
+                                            MODEL["final_dim"], MODEL["dropout"], MODEL["temperature"], seed=0, decode=decode)
+            self.tr = ref_port.PortTrainer(task, MODEL["lr"], MODEL["weight_decay"], 0)
+
+    def make_batch(self, nid, cid, nd, cd):
+        if self.kind == "reference":
+            return self.rh.make_reference_batch(self.nk, self.ck, nid, cid, nd, cd)
+        return self.rp.make_port_batch(self.schema, nid, cid, nd, cd)
+
+    def step(self, batch) -> float:
+        if self.kind == "reference":
+            self.opt.zero_grad()
+            with self.rh.silenced():
+                out = self.task(batch, return_metrics=True)
+            out["loss"].backward()
+            self.opt.step()
+            self.sched.step()
+            return float(out["loss"].detach())
+        return float(self.tr.step(batch)["loss"].detach())
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the path, as the oracle port (the reference is pure Python and cannot
-    travel to the GPU box; oracle/ref_port.py is pinned bit-exactly to it by tests/golden). 'as-is' = with the reference's
-    per-scalar KJT decode loop (src/towers/cat_embed.py:103-121)."""
+    """The reference's own CPU implementation of the path at the SAME configuration (README-default, B = --batch), all host
+    threads. Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import ref_port
     schema = load_schema()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    total_steps = args.steps + args.warmup
-    # bounded sample: the as-is reference runs ~1.5 k samples/s; keep the whole run near two minutes
     B = args.batch
-    budget_samples = 150_000
-    while B > 256 and B * total_steps > budget_samples:
-        B //= 2
-    task = ref_port.build_port_task(schema, MODEL["emb_dim"], MODEL["notice_dense"], MODEL["company_dense"], MODEL["hidden"],
-                                    MODEL["final_dim"], MODEL["dropout"], MODEL["temperature"], seed=0, decode="loop")
-    tr = ref_port.PortTrainer(task, MODEL["lr"], MODEL["weight_decay"], 0)
+    ref = RefStepper(schema)
     gen = torch.Generator().manual_seed(1234)
-    batches = [ref_port.make_port_batch(schema, *synth_batch(schema, B, gen)) for _ in range(min(4, total_steps))]
-    for i in range(args.warmup):
-        tr.step(batches[i % len(batches)])
+    batches = [ref.make_batch(*synth_batch(schema, B, gen)) for _ in range(2)]
+    # bounded run: one probe step decides how many warm-ups fit (a B=8192 step is ~2 s on 16 cores); B is only reduced if even
+    # K timed steps + 1 warm-up would exceed ~6 minutes
+    t0 = time.perf_counter()
+    ref.step(batches[0])
+    probe = time.perf_counter() - t0
+    same = True
+    while B > 256 and probe * (args.steps + 1) > 360.0:
+        B //= 2
+        same = False
+        batches = [ref.make_batch(*synth_batch(schema, B, gen)) for _ in range(2)]
+        t0 = time.perf_counter()
+        ref.step(batches[0])
+        probe = time.perf_counter() - t0
+    warm = max(0, min(args.warmup - 1, int(120.0 / max(probe, 1e-3))))
+    for i in range(warm):
+        ref.step(batches[i % 2])
     t0 = time.perf_counter()
     for i in range(args.steps):
-        out = tr.step(batches[i % len(batches)])
-        float(out["loss"].detach())
+        ref.step(batches[i % 2])
     dt = time.perf_counter() - t0
     val = B * args.steps / dt
-    sample = f"{args.steps} steps of B={B} (bounded sample of the B={args.batch} workload), decode=as-is python loop, {cores} threads"
+    what = ("unmodified reference modules (oracle/_ref), as-is python KJT decode loop" if ref.kind == "reference"
+            else "oracle/ref_port.py (bit-exact port), as-is python KJT decode loop")
+    sample = f"{args.steps} timed steps of B={B} after {warm + 1} warm-up steps, {what}, {cores} torch threads"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm + 1, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"README-default two-tower train step, B={B} sample, fp32, CPU", "batch": B},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": f"README-default two-tower train step (emb 32, towers [128,64]->64, 38 tables / 64,141 rows), "
+                                   f"B={B}, in-batch negatives, dropout 0.1, dense Adam lr 1e-3 wd 1e-5, fp32, CPU",
+                       "batch_per_gpu": B, "same_config_as_gpu_arm": same and B == args.batch},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline(schema, B, budget_s=25.0):
-    """Oracle port timed on the host cores, bounded sample of the same workload (reported baseline, not the target)."""
-    from oracle import ref_port
+    """The reference timed on the host cores, bounded sample of the same workload (reported baseline, not the target)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     out = {}
+    kind = "port"
     for decode in ("loop", "vectorized"):
-        task = ref_port.build_port_task(schema, MODEL["emb_dim"], MODEL["notice_dense"], MODEL["company_dense"], MODEL["hidden"],
-                                        MODEL["final_dim"], MODEL["dropout"], MODEL["temperature"], seed=0, decode=decode)
-        tr = ref_port.PortTrainer(task, MODEL["lr"], MODEL["weight_decay"], 0)
+        ref = RefStepper(schema, decode=decode)
+        if decode == "loop":
+            kind = ref.kind
         gen = torch.Generator().manual_seed(1234)
-        batch = ref_port.make_port_batch(schema, *synth_batch(schema, B, gen))
+        batch = ref.make_batch(*synth_batch(schema, B, gen))
         t0 = time.perf_counter()
-        tr.step(batch)  # warm-up
+        ref.step(batch)  # warm-up
         warm = time.perf_counter() - t0
         n = max(1, min(10, int((budget_s / 2) / max(warm, 1e-3))))
         t0 = time.perf_counter()
         for _ in range(n):
-            float(tr.step(batch)["loss"].detach())
+            ref.step(batch)
         dt = time.perf_counter() - t0
         out[decode] = (B * n / dt, n)
-    return {"value": out["loop"][0], "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{out['loop'][1]} timed steps of B={B} after 1 warm-up, reference as-is (python KJT decode loop), {cores} torch threads",
-            "vectorized_decode_value": out["vectorized"][0]}
+    what = "unmodified reference modules (oracle/_ref)" if kind == "reference" else "oracle/ref_port.py (bit-exact port)"
+    return {"value": out["loop"][0], "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{out['loop'][1]} timed steps of B={B} after 1 warm-up, {what} as-is (python KJT decode loop), {cores} torch threads",
+            "vectorized_decode_value": out["vectorized"][0],
+            "vectorized_decode_note": "fairness footnote: the port with the KJT decode vectorised (not the reference's code)"}
 
 
 
@@ -229,8 +292,10 @@ def tables_section(dev, pk, quick=False):
     return out
 
 # ------------------------------------------------------------------------------------------------ our arm
-def algorithmic(tag: str, B: int, schema) -> dict:
-    """Algorithmic bytes / flops of one C-ABI call."""
+def algorithmic(tag: str, B: int, schema, world: int = 1) -> dict:
+    """Algorithmic bytes / flops of one C-ABI call. B = samples per rank; with global
+    negatives a rank's logits block is B x (world * B)."""
+    Bg = B * world
     E, F, H0, H1 = MODEL["emb_dim"], MODEL["final_dim"], MODEL["hidden"][0], MODEL["hidden"][1]
     Kn, Kc = len(schema["notice"]), len(schema["company"])
     rows = sum(v for _, v in schema["notice"]) + sum(v for _, v in schema["company"])
@@ -249,9 +314,9 @@ def algorithmic(tag: str, B: int, schema) -> dict:
     # dX = dS Y (2 B^2 F); the widened [Y|Ys] operand is not counted. `exps` is the number of exp evaluations a call executes
     # (one per logit per pass), the quantity the MUFU pipe bounds.
     if tag.startswith("tt_simce_forward"):
-        return {"flops": 2 * B * B * F, "exps": 2 * B * B}
+        return {"flops": 2 * B * Bg * F, "exps": 2 * B * Bg}
     if tag.startswith("tt_simce_backward"):
-        return {"flops": 4 * B * B * F, "exps": B * B}
+        return {"flops": 4 * B * Bg * F, "exps": B * Bg}
     return {}
 
 
@@ -283,6 +348,15 @@ def run_ours(args):
             company_dense_input_dim=MODEL["company_dense"], tower_hidden_dims=MODEL["hidden"], final_embedding_dim=MODEL["final_dim"],
             dropout_rate=MODEL["dropout"], temperature=MODEL["temperature"], device=dev,
             vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])}, dtype=args.dtype)
+    # ---- parity of THIS path (graph replay, this dtype, this world size and its peer-memory exchanges) against the reference
+    # port on the concatenated global batch, before anything is timed (checker only; oracle/bench_parity.py)
+    parity = None
+    if not args.no_parity:
+        from oracle import bench_parity
+        parity = bench_parity.run(tt, schema, dev, dtype=args.dtype, B_local=args.parity_batch, steps=3, world=world, rank=rank,
+                                  graph=not args.no_graph, ttdist=ttdist if world > 1 else None)
+        if parity is not None:
+            parity.pop("losses", None); parity.pop("ref_losses", None)
     tt.FusedAdam(task, lr=MODEL["lr"], weight_decay=MODEL["weight_decay"], warmup_steps=0)
     task.train()
     eng = task.engine
@@ -501,7 +575,7 @@ def run_ours(args):
     pk = peaks()
     table = []
     for tag, d in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
-        a = algorithmic(tag, B, schema)
+        a = algorithmic(tag, B, schema, world)
         row = {"call": tag, "ms": round(d["ms"], 5), "kernels": d["kernels"] * max(d["calls"], 1)}
         per_call = d["ms"] / max(d["calls"], 1) * 1e-3
         if "bytes" in a:
@@ -511,10 +585,10 @@ def run_ours(args):
             row["TFLOPs"] = round(a["flops"] / per_call / 1e12, 2)
         table.append(row)
     # dominant call among those with an algorithmic figure (eager per-call times of a multi-rank run include peer waits)
-    top = next((r for r in table if algorithmic(r["call"], B, schema)), table[0] if table else None)
+    top = next((r for r in table if algorithmic(r["call"], B, schema, world)), table[0] if table else None)
     roofline = None
     if top is not None:
-        a = algorithmic(top["call"], B, schema)
+        a = algorithmic(top["call"], B, schema, world)
         per_call_s = kern[top["call"]]["ms"] / max(kern[top["call"]]["calls"], 1) * 1e-3
         if "flops" in a:
             ach = a["flops"] / per_call_s / 1e12
@@ -549,8 +623,10 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
-            "config": {"precision": ("bf16 embeddings + tcgen05 sim-CE (fp32 accumulate in TMEM); towers, reductions, master weights "
-                                     "and Adam in fp32") if args.dtype == "bf16" else "fp32 everywhere (SIMT)",
+            "config": {"precision": ("bf16 activations / gradients / tower outputs: every Linear (forward, dgrad, wgrad) and the B x B "
+                                     "sim-CE on tcgen05 with fp32 accumulation in TMEM; BatchNorm statistics, reductions, "
+                                     "master weights and Adam in fp32 (fp64 partials)") if args.dtype == "bf16"
+                                    else "fp32 everywhere (SIMT)",
                        "workload": f"README-default two-tower train step (emb 32, towers [128,64]->64, 38 tables / 64,141 rows), "
                                    f"B={B} per GPU, in-batch negatives, dropout 0.1, exact dense Adam lr 1e-3 wd 1e-5",
                        "batch_per_gpu": B, "global_batch": B * world, "optimizer": "dense_exact",
@@ -563,7 +639,7 @@ def run_ours(args):
                               "note": "supplementary: as e2e, but the host waits for step i's result only after launching step i+1"},
             "e2e_device_store": e2e_store,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "roofline": roofline, "cpu_baseline": cpu, "tables": tables, "kernels": table, "loss_last": loss_last}
+            "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "tables": tables, "kernels": table, "loss_last": loss_last}
     print(json.dumps(line), flush=True)
     _finish(world, dev)
 
@@ -587,6 +663,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity pre-check against the reference port")
+    ap.add_argument("--parity-batch", type=int, default=1024, help="samples per GPU in the parity pre-check (the port steps the global batch on the CPU)")
     ap.add_argument("--tables-only", nargs="?", const="full", default=None, choices=["full", "quick"])
     ap.add_argument("--no-device-store", action="store_true", help="skip the end-to-end loop with HBM-resident feature stores")
     ap.add_argument("--no-tables", action="store_true", help="skip the large-table (HBM-bound lookup/update) section")

@@ -125,6 +125,13 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
                      int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
                      int32_t* row_end, int32_t* row_stamp, int32_t stamp, const int64_t* d_stamp,
                      const int32_t* d_n, tt_stream_t stream);
+/* Same, for a captured train step: the device epoch counter *d_stamp is advanced by one inside the first kernel of the sort
+ * and the new value is the stamp (stamp argument = 0), so no separate "counter += 1" node is needed in the graph. Every later
+ * consumer of d_stamp on the same stream (tt_ebc_backward_adam) sees the advanced value. n must be > 0. */
+int tt_ebc_sort_rows_advance(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
+                             int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
+                             int32_t* row_end, int32_t* row_stamp, int64_t* d_stamp, const int32_t* d_n,
+                             tt_stream_t stream);
 
 /* Sparse backward, stage 2: segment-sum of the pooled-output gradients in fixed order, fused with
  * the Adam row update.  Gradient slot s < n0 belongs to source 0 (sample s / K0, key s % K0, vector
@@ -183,8 +190,11 @@ int tt_ebc_small_backward(const int64_t* values, int32_t B, int32_t K, int32_t l
  * library call. Every rank owns a mailbox of tt_peer_mailbox_bytes(world, n_max) bytes per call site, zero-initialised once
  * and peer-mapped; d_mailboxes is the device array of the world mailbox pointers (same order on every rank), d_epoch a
  * zero-initialised device counter per call site (graph-replay safe). One process per GPU only: kernels of different ranks wait
- * for each other. A peer that never arrives traps after ~2 s. */
+ * for each other. Rank skew is waited out; a watchdog (default 10 minutes; tt_peer_set_timeout_ms, 0 = never) traps on a peer
+ * that never arrives instead of hanging the GPU for ever. Rank-local work between steps (checkpoint writes, evaluation) may be
+ * as long as the watchdog allows. */
 int64_t tt_peer_mailbox_bytes(int32_t world, int32_t n_max);
+int tt_peer_set_timeout_ms(int64_t ms);
 int tt_peer_allreduce_f64(double* data, int32_t n, int32_t rank, int32_t world, const void* const* d_mailboxes, int32_t n_max,
                           int64_t* d_epoch, tt_stream_t stream);
 /* All-gather over NVLink peer memory: this rank's block (`bytes`, a multiple of 16) is stored into EVERY rank's destination

@@ -172,9 +172,12 @@ static inline int rs_items_for(int64_t n) { return n < ((int64_t)1 << 19) ? RS_I
 template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
 radix_hist_kernel(const int32_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ d_n, int shift,
-                  int32_t* __restrict__ hist, int n_tiles) {
+                  int32_t* __restrict__ hist, int n_tiles, int64_t* __restrict__ d_advance) {
   constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
   __shared__ int32_t s_hist[256];
+  // first pass of tt_ebc_sort_rows_advance: the dedup epoch moves on inside the sort itself (no extra node in a captured step);
+  // every later kernel of this sort and of the table update reads the new value in stream order
+  if (d_advance && blockIdx.x == 0 && threadIdx.x == 0) *d_advance += 1;
   if (d_n) {  // device-side count (sharded tables): the launch covers the capacity, the work and the histogram pitch follow n
     n = *d_n;
     n_tiles = n > 0 ? (int)((n + RS_TILE - 1) / RS_TILE) : 1;
@@ -956,10 +959,10 @@ int64_t tt_ebc_sort_workspace_bytes(int64_t n, int64_t total_rows) {
   return 2 * align_up(n * 4 + 16, 256) + align_up(256 * tiles * 4, 256) + align_up((256 * tiles / SCAN_CHUNK + 2) * 4, 256);
 }
 
-int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
-                     int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
-                     int32_t* row_end, int32_t* row_stamp, int32_t stamp, const int64_t* d_stamp,
-                     const int32_t* d_n, tt_stream_t stream) {
+static int sort_rows_impl(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
+                          int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
+                          int32_t* row_end, int32_t* row_stamp, int32_t stamp, const int64_t* d_stamp,
+                          const int32_t* d_n, tt_stream_t stream, int64_t* d_advance) {
   TT_CHECK_ARG(rows && sorted_rows && sorted_slots && row_begin && row_end && row_stamp, "tt_ebc_sort_rows: NULL pointer");
   TT_CHECK_ARG(n >= 0 && n < (1ll << 31) && total_rows > 0 && total_rows < (1ll << 31), "tt_ebc_sort_rows: bad sizes");
   TT_CHECK_ARG(workspace_bytes >= tt_ebc_sort_workspace_bytes(n, total_rows) && (workspace || n == 0),
@@ -984,8 +987,9 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
     const bool to_final = ((passes - 1 - p) % 2) == 0;
     int32_t* kout = to_final ? sorted_rows : tmp_keys;
     int32_t* vout = to_final ? sorted_slots : tmp_vals;
-    if (items == RS_ITEMS_SMALL) radix_hist_kernel<RS_ITEMS_SMALL><<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles);
-    else radix_hist_kernel<RS_ITEMS_BIG><<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles);
+    int64_t* adv = p == 0 ? d_advance : nullptr;
+    if (items == RS_ITEMS_SMALL) radix_hist_kernel<RS_ITEMS_SMALL><<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles, adv);
+    else radix_hist_kernel<RS_ITEMS_BIG><<<n_tiles, RS_THREADS, 0, s>>>(kin, n, d_n, p * 8, hist, n_tiles, adv);
     { int rc = launch_scan(hist, (int64_t)256 * n_tiles, d_n, scan_totals, tile, s); if (rc != TT_OK) return rc; }
     if (items == RS_ITEMS_SMALL)
       radix_scatter_kernel<RS_ITEMS_SMALL><<<n_tiles, RS_THREADS, 0, s>>>(kin, vin, n, d_n, p * 8, hist, n_tiles, kout, vout);
@@ -997,6 +1001,23 @@ int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64
   segment_bounds_kernel<<<ceil_div(n, 256), 256, 0, s>>>(sorted_rows, n, row_begin, row_end, row_stamp, stamp, d_stamp, d_n);
   TT_LAUNCH_CHECK("ebc_sort_rows");
   return TT_OK;
+}
+
+int tt_ebc_sort_rows(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
+                     int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
+                     int32_t* row_end, int32_t* row_stamp, int32_t stamp, const int64_t* d_stamp,
+                     const int32_t* d_n, tt_stream_t stream) {
+  return sort_rows_impl(rows, slots, n, total_rows, workspace, workspace_bytes, sorted_rows, sorted_slots, row_begin, row_end,
+                        row_stamp, stamp, d_stamp, d_n, stream, nullptr);
+}
+
+int tt_ebc_sort_rows_advance(const int32_t* rows, const int32_t* slots, int64_t n, int64_t total_rows, void* workspace,
+                             int64_t workspace_bytes, int32_t* sorted_rows, int32_t* sorted_slots, int32_t* row_begin,
+                             int32_t* row_end, int32_t* row_stamp, int64_t* d_stamp, const int32_t* d_n,
+                             tt_stream_t stream) {
+  TT_CHECK_ARG(d_stamp && n > 0, "tt_ebc_sort_rows_advance: needs a device epoch counter and n > 0");
+  return sort_rows_impl(rows, slots, n, total_rows, workspace, workspace_bytes, sorted_rows, sorted_slots, row_begin, row_end,
+                        row_stamp, 0, d_stamp, d_n, stream, d_stamp);
 }
 
 int64_t tt_ebc_piece_workspace_bytes(int64_t n, int32_t E) {

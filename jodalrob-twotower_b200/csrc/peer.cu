@@ -7,14 +7,17 @@
 //   4. sum the W slots in rank order (every rank adds the same numbers in the same order: bit-identical results everywhere).
 // The epoch is a device-resident counter per call site, so a captured CUDA graph replays correctly; slots alternate by epoch
 // parity, and a rank can only be one epoch ahead of the slowest rank at a site (it needs that rank's contribution to finish
-// the epoch in between), so a slot is never overwritten before it has been read. The spin is bounded: a missing peer traps
-// after ~2 s instead of hanging the GPU.
+// the epoch in between), so a slot is never overwritten before it has been read. The spin is bounded by a configurable
+// watchdog (tt_peer_set_timeout_ms; default 10 minutes, 0 = wait for ever like NCCL without a watchdog): legitimate rank skew
+// — a checkpoint written by rank 0, a data-loader stall — is waited out, a dead peer traps instead of hanging the GPU for ever.
 //
 // Kernels of DIFFERENT ranks wait for each other here, so this path is for one-process-per-GPU runs only; the in-process rank
 // emulation used by the single-GPU tests keeps the host-mediated collectives (dist.py).
 #include "common.cuh"
 
 namespace tt {
+
+__device__ unsigned long long g_peer_timeout_ns = 600ull * 1000000000ull;  // 0 = no watchdog
 
 // mailbox of one site: flags u64 [2][world] | pad to 128 B | slots f64 [2][world][n_max]
 __device__ __forceinline__ size_t site_flag_off(int par, int r, int world) { return (size_t)par * world + r; }
@@ -42,12 +45,13 @@ peer_allreduce_f64_kernel(double* __restrict__ data, int n, int rank, int world,
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
     const unsigned long long* mine = mailboxes[rank] + site_flag_off(par, t, world);
     unsigned long long seen = 0, t0 = 0, now = 0;
+    const unsigned long long timeout_ns = g_peer_timeout_ns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
       if (seen >= epoch) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (now - t0 > 2000000000ull) {
+      if (timeout_ns && now - t0 > timeout_ns) {
         printf("tt_peer_allreduce: rank %d timed out waiting for rank %d (epoch %llu, saw %llu)\n", rank, t, epoch, seen);
         __trap();
       }
@@ -96,12 +100,13 @@ peer_allgather_kernel(const uint4* __restrict__ src, int64_t n16, int rank, int 
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
     const unsigned long long* mine = mailboxes[rank] + site_flag_off(par, t, world);
     unsigned long long seen = 0, t0 = 0, now = 0;
+    const unsigned long long timeout_ns = g_peer_timeout_ns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
       if (seen >= epoch) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (now - t0 > 2000000000ull) {
+      if (timeout_ns && now - t0 > timeout_ns) {
         printf("tt_peer_allgather: rank %d timed out waiting for rank %d (epoch %llu, saw %llu)\n", rank, t, epoch, seen);
         __trap();
       }
@@ -143,6 +148,13 @@ int64_t tt_peer_mailbox_bytes(int32_t world, int32_t n_max) {
   if (world <= 0 || n_max <= 0) return 0;
   const int64_t flags = ((int64_t)2 * world + 15) / 16 * 16;
   return (flags + (int64_t)2 * world * n_max) * 8;
+}
+
+int tt_peer_set_timeout_ms(int64_t ms) {
+  TT_CHECK_ARG(ms >= 0, "tt_peer_set_timeout_ms: negative timeout");
+  const unsigned long long ns = (unsigned long long)ms * 1000000ull;
+  TT_CUDA(cudaMemcpyToSymbol(g_peer_timeout_ns, &ns, sizeof(ns)));
+  return TT_OK;
 }
 
 int tt_peer_allreduce_f64(double* data, int32_t n, int32_t rank, int32_t world, const void* const* d_mailboxes, int32_t n_max,

@@ -226,6 +226,8 @@ class DistributedEngine(TwoTowerEngine):
         if not getattr(self.comm, "peer_kernels", False) or self.world == 1:
             return
         dev = self.device
+        if "TT_PEER_TIMEOUT_MS" in os.environ:  # watchdog of the peer-wait kernels (default 10 min; 0 = wait for ever)
+            self.lib.call("tt_peer_set_timeout_ms", int(os.environ["TT_PEER_TIMEOUT_MS"]))
         self.peer_n_max = max(2 * max(self.cfg.hidden[1:] + [1]), 128)
         mb = self.lib.query("tt_peer_mailbox_bytes", self.world, self.peer_n_max)
         mb = (mb + 255) // 256 * 256
@@ -470,10 +472,9 @@ class DistributedEngine(TwoTowerEngine):
             return
         cap = n_l * self.world
         self.profile_tag = "sharded"
-        self.stamp.add_(1)
-        self._call("tt_ebc_sort_rows", ptr(ws.rows), ptr(ws.slots), cap, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
+        self._call("tt_ebc_sort_rows_advance", ptr(ws.rows), ptr(ws.slots), cap, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
                    ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
-                   0, ptr(self.stamp), ptr(ws.n_owned), s, n_kernels=7)
+                   ptr(self.stamp), ptr(ws.n_owned), s, n_kernels=7)
         self._adam_untouched(ws)
 
     def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool, sorted_already: bool = False):

@@ -454,6 +454,9 @@ class TwoTowerEngine:
         ld = H0 + K * E
         pre = f"{name}_tower."
         if not skip_prefix:
+            # stand-alone tower call (TwoTowerModel.forward, get_*_embeddings, predict_batch): nobody refreshed the bf16 weight
+            # mirror for us — after load_state_dict / an optimizer step it is stale (all zeros on a fresh engine)
+            self.refresh_bf16_weights()
             self.tower_prefix(t, ws, dense)
             self.profile_tag = name
         x, width, idx = ws.c[t], ld, 0
@@ -723,10 +726,10 @@ class TwoTowerEngine:
         if n == 0 or self.total_rows == 0:
             return
         self.profile_tag = ""
-        self.stamp.add_(1)
-        self._call("tt_ebc_sort_rows", ptr(ws.rows), 0, n, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
+        # the dedup epoch (self.stamp, device counter) is advanced inside the sort's first kernel
+        self._call("tt_ebc_sort_rows_advance", ptr(ws.rows), 0, n, self.total_rows, ptr(ws.sort_ws), ws.sort_ws.numel(),
                    ptr(ws.sorted_rows), ptr(ws.sorted_slots), ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
-                   0, ptr(self.stamp), 0, s, n_kernels=7)
+                   ptr(self.stamp), 0, s, n_kernels=7)
         self._adam_untouched(ws)
 
     def _adam_untouched(self, ws: _Ws):

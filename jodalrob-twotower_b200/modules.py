@@ -235,8 +235,10 @@ class _TrainStepFn(torch.autograd.Function):
         task, ws = ctx.task, ctx.ws
         eng = task.engine
         if task._fused_opt is not None:
-            # backward + sort-dedup + fused Adam all inside the library; upstream gradient is taken as 1
-            eng.backward(ws, 1.0)
+            # backward + sort-dedup + fused Adam all inside the library. The upstream gradient scales every gradient, like under
+            # autograd ((loss / accum).backward(), a GradScaler, loss + other terms). Contract of this mode: exactly one
+            # backward per train-mode forward — the optimizer scalars (Adam step, lr schedule, dropout counter) advance in forward.
+            eng.backward(ws, float(dloss))
             eng.reduce_dense_grads()
             eng.embedding_backward(ws, apply_adam=True, want_dense_grad=False)
             eng.dense_adam()
@@ -292,7 +294,7 @@ class _CosineStepFn(torch.autograd.Function):
             s_ = ctx.s.detach().requires_grad_(True)
             (ds,) = torch.autograd.grad(_cosine_embedding_loss(s_), s_)
         fused = task._fused_opt is not None
-        scale = (1.0 if fused else float(dloss)) / eng.cfg.temperature
+        scale = float(dloss) / eng.cfg.temperature
         n, c = ws.e[0].float(), ws.e[1].float()
         ws.de[0].copy_(torch.mm(ds, c) * scale)
         ws.de[1].copy_(torch.mm(ds.t(), n) * scale)
@@ -495,7 +497,7 @@ class GraphedFusedStep:
             s.copy_(t)
         o = task._fused_opt
         self._args = (o.lr, o.warmup_steps, o.betas, o.eps, o.weight_decay)
-        hyper0, stamp0 = eng.hyper.clone(), eng.stamp.clone()
+        hyper0 = eng.hyper.clone()
         state0 = (eng.flat_w.clone(), eng.flat_m.clone(), eng.flat_v.clone(),
                   [[b.clone() for b in bl] for bl in eng.bn_rm], [[b.clone() for b in bl] for bl in eng.bn_rv],
                   [[b.clone() for b in bl] for bl in eng.bn_nbt])
@@ -511,9 +513,11 @@ class GraphedFusedStep:
         with torch.cuda.graph(self.graph):
             self.out = self._run()
         self.launches_per_step = eng.launches - l0
-        # capture and warm-up must not count as training: restore the parameters and optimizer state
+        # capture and warm-up must not count as training: restore the parameters and optimizer state. The dedup epoch
+        # (eng.stamp) is NOT rolled back: the warm-up left row_stamp / row_begin / row_end entries carrying its values, and an
+        # epoch that repeats would make a later step mistake those rows for rows of its own batch. It only has to be monotonic.
         torch.cuda.synchronize(eng.device)
-        eng.hyper.copy_(hyper0); eng.stamp.copy_(stamp0)
+        eng.hyper.copy_(hyper0)
         eng.flat_w.copy_(state0[0]); eng.flat_m.copy_(state0[1]); eng.flat_v.copy_(state0[2])
         for dst, src in ((eng.bn_rm, state0[3]), (eng.bn_rv, state0[4]), (eng.bn_nbt, state0[5])):
             for dl, sl in zip(dst, src):

@@ -29,7 +29,9 @@ from typing import List
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("TT_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the build container; on the GPU box the verbatim copy that oracle/make_ref.py leaves in oracle/_ref/
+_LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("TT_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference") else _LOCAL_COPY)
 
 
 def reference_available() -> bool:

@@ -9,7 +9,7 @@ Why a port: the reference is pure Python/PyTorch and cannot travel to the GPU bo
 (``/root/reference`` does not exist there).  This file restates it with the same
 modules, the same op order and the same ``state_dict`` names, and is pinned
 against the unmodified reference by ``oracle/make_golden.py`` →
-``tests/golden/*.npz`` and ``tests/test_oracle_vs_reference.py`` (bit-exact on
+``tests/golden/*.npz`` and ``tests/test_oracle_vs_golden.py`` (bit-exact on
 CPU in the build container).
 
 Reference anchors (paths relative to /root/reference):

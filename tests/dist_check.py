@@ -49,9 +49,25 @@ def main():
         ok = ok and good
         if rank == 0:
             print(f"[dist_check] world={world} case={case}: loss rel err {worst:.2e}, weights rel err {werr:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+    # the BENCHMARKED multi-GPU path: bf16 (tcgen05), NVLink peer-memory exchanges, whole step as one CUDA graph per rank —
+    # against the reference port stepping the concatenated global batch (oracle/bench_parity.py)
+    from oracle import bench_parity
+    from tests.helpers import readme_schema
+    for dtype, bl in (("bf16", 1024), ("fp32", 256)):
+        res = bench_parity.run(tt, readme_schema(), dev, dtype=dtype, B_local=bl, steps=3, world=world, rank=rank, graph=True,
+                               ttdist=ttd)
+        if rank == 0:
+            ok = ok and res["ok"]
+            print(f"[dist_check] world={world} README-default {dtype} graph+peer path, B_l={bl}: loss rel {res['loss_rel']:.2e}, "
+                  f"weights rms rel {res['weights_rel']:.2e}, tables max rel {res['tables_rel_max']:.2e}, bad {res['bad_tensors']} "
+                  f"(tol {res['tol']:g}) -> {'OK' if res['ok'] else 'FAIL'}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    ok = bool(flag.item())
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)  # captured graphs hold symmetric-memory handles: skip the destructors (as bench.py does)
 
 
 if __name__ == "__main__":
