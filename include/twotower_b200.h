@@ -294,6 +294,10 @@ int tt_bn_backward_apply(const void* dy, int64_t lddy, const void* h, int64_t ld
  * dz = (de - e*(e·de)) / max(||z||, eps).  z/dz are fp32; e is out_dtype. */
 int tt_l2norm_forward(const float* z, int64_t M, int32_t F, void* e, int32_t out_dtype, float* nrm,
                       tt_stream_t stream);
+/* bf16 tower outputs twice: e (unit rows) and e_scaled = bf16(scale * z / |z|), rounded once from fp32 — the pre-scaled X operand of
+ * the three-pass logits step (scale = log2(e) / temperature). */
+int tt_l2norm_forward_scaled(const float* z, int64_t M, int32_t F, void* e_bf16, void* e_scaled_bf16, float scale, float* nrm,
+                             tt_stream_t stream);
 int tt_l2norm_backward(const float* de, const void* e, int32_t e_dtype, const float* nrm, int64_t M, int32_t F,
                        float* dz, tt_stream_t stream);
 
@@ -333,6 +337,39 @@ int tt_simce_forward_sums(const void* X, const void* Y, int64_t Bx, int64_t By, 
 int tt_simce_forward_metrics(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
                              float* row_sum_s, float* col_sum_s, int32_t* row_argmax, void* workspace, int64_t workspace_bytes,
                              tt_stream_t stream);
+
+/* Three-pass train step of the bf16 path (tcgen05). The fused step needs, per logit, only E = exp(S/T): the row sums (P1), the
+ * column sums together with the company gradient (P2, the transposed problem with its row scale applied afterwards) and the notice
+ * gradient (P3) — one pass fewer than forward(2) + backward(2), and no multiply per logit: the X operand of every pass is
+ * pre-scaled by c1 = log2(e)/T when it is written (tt_l2norm_forward_scaled), so the accumulator is the exponent.
+ * Replaces, for the fused train step, src/towers/two_tower_train_task.py:99-134 + its autograd backward.
+ *   Xs            bf16 [Bx,F]  c1 * unit rows (this rank's rows)        Y   bf16 [By,F]  unit rows (all ranks' rows)
+ *   Ys            bf16 [By,F]  (gscale * k / sumexp_y[j]) * Y[j,:]       (k = exp(-1/T): the public sums are the shifted ones,
+ *                              sum_j exp(S_ij/T - 1/T), as everywhere in this header)
+ *   workspace     tt_simce3_workspace_bytes; the P1 partials stay valid for tt_simce3_metrics until the next tt_simce3_rows.
+ * tt_simce3_rows         P1: partial row sums / chunk maxima -> workspace; diag[i] = S_ii / T
+ * tt_simce3_rows_finish  row_sumexp, inv_row = 1 / row_sumexp; optional Xs_out = (gscale * k / row_sumexp) * X_unit (the Ys of P2)
+ * tt_simce3_grad         P2 (inv_x == NULL: row scale deferred, row sums accumulated on the fly) or P3 (inv_x given)
+ * tt_simce3_grad_finish  dX (fixed-order sum of the parts, target / label-smoothing corrections); deferred: also sumexp_out /
+ *                        inv_out of these rows and optional Xs_out = (gscale * k / sumexp) * X_unit (the Ys of P3)
+ * tt_simce3_scale_rows   Ys from exchanged sums (multi-GPU: the sums of other ranks' rows arrive by all-gather)
+ * tt_simce3_metrics      sum_j S_ij / T and the arg-max column from the P1 partials (off the critical path) */
+int64_t tt_simce3_workspace_bytes(int64_t Bx, int64_t By, int32_t F);
+int tt_simce3_rows(const void* Xs, const void* Y, int64_t Bx, int64_t By, int32_t F, float inv_temp, int64_t diag_offset, float* diag,
+                   void* workspace, int64_t workspace_bytes, tt_stream_t stream);
+int tt_simce3_rows_finish(void* workspace, int64_t workspace_bytes, int64_t Bx, int64_t By, int32_t F, float inv_temp,
+                          float* row_sumexp, float* inv_row, const void* X_unit, float gscale, void* Xs_out, tt_stream_t stream);
+int tt_simce3_grad(const void* Xs, const void* Y, const void* Ys, int64_t Bx, int64_t By, int32_t F, float inv_temp,
+                   int64_t diag_offset, const float* inv_x, float gscale, float label_smoothing, void* workspace,
+                   int64_t workspace_bytes, tt_stream_t stream);
+int tt_simce3_grad_finish(void* workspace, int64_t workspace_bytes, int64_t Bx, int64_t By, int32_t F, float inv_temp,
+                          int64_t diag_offset, const void* Y, int32_t deferred, float gscale, float label_smoothing, int64_t B_global,
+                          float* dX, float* sumexp_out, float* inv_out, const void* X_unit, void* Xs_out, tt_stream_t stream);
+int tt_simce3_scale_rows(const void* Y_unit, const float* sumexp, float gscale, float inv_temp, int64_t By, int32_t F, void* Ys_out,
+                         tt_stream_t stream);
+int tt_simce3_metrics(const void* Xs, const void* Y, int64_t Bx, int64_t By, int32_t F, float* row_sum_s, int32_t* row_argmax,
+                      void* workspace, int64_t workspace_bytes, tt_stream_t stream);
+
 /* backward: dX[Bx,F] (f32) = dS · Y with
  *   dS_ij = gscale * (exp(S_ij - inv_temp) * (inv_x[i] + inv_y[j]) - 2*((1-ls)*[j == diag_offset+i] + ls/B_global))
  * gscale = dloss * 0.5 / B_global * inv_temp.  Call once with (X=notice, Y=company) for d notice and

@@ -409,6 +409,68 @@ int tt_simce_forward_metrics(const void* X, const void* Y, int64_t Bx, int64_t B
   return simce_tc_rows_metrics(Y, X, By, Bx, F, inv_temp, col_sum_s, nullptr, w1, s);
 }
 
+/* ---- three-pass train step of the bf16 path (pre-scaled operands; simce_tc.cu) ---- */
+int64_t tt_simce3_workspace_bytes(int64_t Bx, int64_t By, int32_t F) {
+  if (F != 64 && F != 128) return 0;
+  return a256(simce_tc_workspace_bytes(Bx, By, F)) + simce_tc_grad_workspace_bytes(Bx, By, F);
+}
+static char* simce3_grad_ws(void* workspace, int64_t Bx, int64_t By, int F) {
+  return (char*)workspace + a256(simce_tc_workspace_bytes(Bx, By, F));
+}
+#define SIMCE3_COMMON(name)                                                                                                  \
+  TT_CHECK_ARG(Bx > 0 && By > 0 && (F == 64 || F == 128), name ": needs final_embedding_dim 64 or 128");                     \
+  TT_CHECK_ARG(workspace && workspace_bytes >= tt_simce3_workspace_bytes(Bx, By, F), name ": workspace too small");          \
+  TT_CHECK_ARG(inv_temp > 0.f && inv_temp <= 40.f, name ": temperature must be >= 0.025");
+
+int tt_simce3_rows(const void* Xs, const void* Y, int64_t Bx, int64_t By, int32_t F, float inv_temp, int64_t diag_offset, float* diag,
+                   void* workspace, int64_t workspace_bytes, tt_stream_t stream) {
+  SIMCE3_COMMON("tt_simce3_rows")
+  TT_CHECK_ARG(Xs && Y && diag && diag_offset >= 0 && diag_offset + Bx <= By, "tt_simce3_rows: bad arguments");
+  TT_CHECK_ARG(((uintptr_t)Xs & 15) == 0 && ((uintptr_t)Y & 15) == 0, "tt_simce3_rows: operands must be 16-byte aligned");
+  return simce_tc_rows_pre(Xs, Y, Bx, By, F, inv_temp, diag_offset, diag, workspace, (cudaStream_t)stream);
+}
+
+int tt_simce3_rows_finish(void* workspace, int64_t workspace_bytes, int64_t Bx, int64_t By, int32_t F, float inv_temp,
+                          float* row_sumexp, float* inv_row, const void* X_unit, float gscale, void* Xs_out, tt_stream_t stream) {
+  SIMCE3_COMMON("tt_simce3_rows_finish")
+  TT_CHECK_ARG(row_sumexp && inv_row && (!Xs_out || X_unit), "tt_simce3_rows_finish: bad arguments");
+  return simce_tc_rows_finish(workspace, Bx, By, F, inv_temp, row_sumexp, inv_row, X_unit, gscale, Xs_out, (cudaStream_t)stream);
+}
+
+int tt_simce3_grad(const void* Xs, const void* Y, const void* Ys, int64_t Bx, int64_t By, int32_t F, float inv_temp,
+                   int64_t diag_offset, const float* inv_x, float gscale, float label_smoothing, void* workspace,
+                   int64_t workspace_bytes, tt_stream_t stream) {
+  SIMCE3_COMMON("tt_simce3_grad")
+  TT_CHECK_ARG(Xs && Y && Ys && diag_offset >= 0 && diag_offset + Bx <= By, "tt_simce3_grad: bad arguments");
+  TT_CHECK_ARG(((uintptr_t)Xs & 15) == 0 && ((uintptr_t)Y & 15) == 0 && ((uintptr_t)Ys & 15) == 0, "tt_simce3_grad: operands must be 16-byte aligned");
+  return simce_tc_grad_pre(Xs, Y, Ys, Bx, By, F, inv_temp, diag_offset, inv_x, gscale, label_smoothing != 0.f,
+                           simce3_grad_ws(workspace, Bx, By, F), (cudaStream_t)stream);
+}
+
+int tt_simce3_grad_finish(void* workspace, int64_t workspace_bytes, int64_t Bx, int64_t By, int32_t F, float inv_temp,
+                          int64_t diag_offset, const void* Y, int32_t deferred, float gscale, float label_smoothing, int64_t B_global,
+                          float* dX, float* sumexp_out, float* inv_out, const void* X_unit, void* Xs_out, tt_stream_t stream) {
+  SIMCE3_COMMON("tt_simce3_grad_finish")
+  TT_CHECK_ARG(Y && dX && B_global > 0 && (!Xs_out || (X_unit && deferred)), "tt_simce3_grad_finish: bad arguments");
+  const float t_off = label_smoothing / (float)B_global;
+  return simce_tc_grad_finish(simce3_grad_ws(workspace, Bx, By, F), Bx, By, F, inv_temp, diag_offset, Y, deferred, gscale,
+                              (1.f - label_smoothing) + t_off, t_off, dX, sumexp_out, inv_out, X_unit, Xs_out, (cudaStream_t)stream);
+}
+
+int tt_simce3_scale_rows(const void* Y_unit, const float* sumexp, float gscale, float inv_temp, int64_t By, int32_t F, void* Ys_out,
+                         tt_stream_t stream) {
+  TT_CHECK_ARG(Y_unit && sumexp && Ys_out && By > 0 && (F == 64 || F == 128), "tt_simce3_scale_rows: bad arguments");
+  return simce_tc_scale_rows(Y_unit, sumexp, gscale, inv_temp, By, F, Ys_out, (cudaStream_t)stream);
+}
+
+int tt_simce3_metrics(const void* Xs, const void* Y, int64_t Bx, int64_t By, int32_t F, float* row_sum_s, int32_t* row_argmax,
+                      void* workspace, int64_t workspace_bytes, tt_stream_t stream) {
+  TT_CHECK_ARG(Xs && Y && Bx > 0 && By > 0 && (F == 64 || F == 128) && (row_sum_s || row_argmax), "tt_simce3_metrics: bad arguments");
+  TT_CHECK_ARG(workspace && workspace_bytes >= tt_simce3_workspace_bytes(Bx, By, F), "tt_simce3_metrics: workspace too small");
+  /* Xs carries c1 = log2(e)/T: X'.y * ln 2 = S / T */
+  return simce_tc_rows_metrics(Xs, Y, Bx, By, F, 0.6931471805599453f, row_sum_s, row_argmax, workspace, (cudaStream_t)stream);
+}
+
 int tt_simce_finalize(const float* row_sumexp, const float* col_sumexp, const float* row_sum_s,
                       const float* col_sum_s, const float* diag, const int32_t* row_argmax, int64_t Bx, int64_t By,
                       int64_t diag_offset, int64_t B_global, float inv_temp, float label_smoothing, float* inv_row,

@@ -48,8 +48,9 @@ struct TcParams {
   int n_col_tiles;       // ceil(By / 128)
   long long total_tiles; // row blocks * column tiles: CTA c owns the contiguous tile range [c*T/G, (c+1)*T/G) of the row-block-
                          // major tile sequence, i.e. one or two long items instead of many short ones
-  float c1, c0;          // e = exp2(s_raw * c1 + c0):  c1 = inv_temp*log2e, c0 = -inv_temp*log2e
-  float inv_temp;
+  float c1, c0;          // e = exp2(s_raw * c1 + c0):  c1 = inv_temp*log2e, c0 = -inv_temp*log2e (unused when the X operand is
+                         // pre-scaled by c1: then the accumulator IS the exponent and e = exp2(s) is unshifted)
+  float inv_temp;        // diag = raw * inv_temp (pre-scaled X: ln 2, which maps the exponent back to S / T)
   int64_t diag_offset;
   int use_tma;
   int n_stages;          // Y smem ring depth (<= TC_STAGES)
@@ -67,8 +68,13 @@ struct TcParams {
   const __nv_bfloat16* Ys;  // [By][F] = bf16(gscale * inv_y[j] * Y[j,:]) (column scales folded into the second MMA operand)
   const float* inv_x;    // [Bx] (unscaled)
   float gscale;
-  float* dx_part;        // [max parts][Bx][F]: part = owning CTA - first CTA of the row block
+  float* dx_part;        // [max parts][Bx][F]: part = owning CTA - first CTA of the row block. Deferred row scale (MODE 2):
+                         // [max parts][Bx][2F], the raw halves [E.Y | E.Ys]; the row sums of E go to row_e like in the forward
 };
+
+// MODE of simce_tc_kernel: the forward statistics pass, the gradient pass with a known row scale, and the gradient pass that
+// also accumulates this row block's sum of E (the row scale is only known once the pass is over: the reduce kernel applies it)
+enum { TC_FWD = 0, TC_BWD = 1, TC_BWD_SUMS = 2 };
 
 struct TcSmem {  // carved from dynamic smem after the 1024-aligned tiles
   uint64_t x_full[2], x_empty[2];  // the X row block is double-buffered so the next work item's block loads early
@@ -121,7 +127,10 @@ constexpr int TC_CW = 16;  // columns per TMEM load / epilogue chunk: half of a 
 // 16-column chunk only (three instructions per chunk); tc_rows_reduce_kernel resolves the column inside the winning chunk.
 // sum_j S_ij is not accumulated here at all: it equals X_i . (sum_j Y_j) and is formed in the reduce kernel.
 // GENERIC handles ragged column tiles and the diagonal.
-template <bool GENERIC>
+// PRE: the X operand was pre-scaled by c1 = log2(e) / T when it was written (tt_l2norm_forward_scaled), so the accumulator is the
+// exponent itself: no FFMA per logit, and E = exp2(s) is unshifted (|s| <= 57.8 at the smallest temperature: no overflow in
+// fp32 / bf16 even summed over 2^16 columns).
+template <bool GENERIC, bool PRE>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase, int By, float c1, float c0, int dcol, float (&acc)[4],
                                           float& best, int32_t& best_cb, float& dval, bool& have_diag) {
   float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -131,7 +140,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
     if (GENERIC) {
       const int col = cbase + j;
       if (col < By) {
-        acc[j & 3] += tc_exp2(fmaf(raw, c1, c0), j);
+        acc[j & 3] += PRE ? ex2f(raw) : tc_exp2(fmaf(raw, c1, c0), j);
         m4[j & 3] = fmaxf(m4[j & 3], raw);
         if (col == dcol) {
           dval = raw;
@@ -139,7 +148,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
         }
       }
     } else {
-      acc[j & 3] += tc_exp2(fmaf(raw, c1, c0), j);
+      acc[j & 3] += PRE ? ex2f(raw) : tc_exp2(fmaf(raw, c1, c0), j);
       m4[j & 3] = fmaxf(m4[j & 3], raw);
     }
   }
@@ -156,12 +165,17 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
 // / diagonal corrections added by tc_dx_reduce_kernel:
 //   dX_i = ix_i (E Y)_i + (E Ys)_i - t_off sum_j Y_j - (t_diag - t_off) Y_dcol(i).
 // Ragged tiles need no masks: rows / columns past the edge are zero-filled operands (they contribute nothing, or are not stored).
-__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], float c1, float c0, uint32_t p_taddr) {
+template <bool PRE, bool SUMS>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], float c1, float c0, uint32_t p_taddr, float (&acc)[4]) {
   uint32_t w[TC_CW / 2];
 #pragma unroll
   for (int u = 0; u < TC_CW / 2; ++u) {
-    const float e0 = tc_exp2(fmaf(__uint_as_float(r[2 * u]), c1, c0), 2 * u);
-    const float e1 = tc_exp2(fmaf(__uint_as_float(r[2 * u + 1]), c1, c0), 2 * u + 1);
+    const float e0 = PRE ? ex2f(__uint_as_float(r[2 * u])) : tc_exp2(fmaf(__uint_as_float(r[2 * u]), c1, c0), 2 * u);
+    const float e1 = PRE ? ex2f(__uint_as_float(r[2 * u + 1])) : tc_exp2(fmaf(__uint_as_float(r[2 * u + 1]), c1, c0), 2 * u + 1);
+    if (SUMS) {  // this row's sum of E rides along (one FADD per logit): the transposed gradient pass IS the column-statistics pass
+      acc[(2 * u) & 3] += e0;
+      acc[(2 * u + 1) & 3] += e1;
+    }
     __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);  // low half = even column
     w[u] = *reinterpret_cast<uint32_t*>(&t);
   }
@@ -181,12 +195,14 @@ __host__ __device__ __forceinline__ int tc_parts_of_row_block(int rb, int n_ct, 
   return tc_cta_of_tile((long long)rb * n_ct + n_ct - 1, T, G) - tc_cta_of_tile((long long)rb * n_ct, T, G) + 1;
 }
 
-template <bool BWD>
+template <int MODE, bool PRE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                 const __grid_constant__ CUtensorMap map_ys, const TcParams p) {
   // TMEM map (512 columns). Forward: three S buffers. Backward: n_sbuf S buffers | [E.Y | E.Ys] accumulator (2F columns) |
   // two E buffers (64 columns each: 128 bf16 per row, two per column): F = 64 -> 256 + 128 + 128, F = 128 -> 128 + 256 + 128.
+  constexpr bool BWD = MODE != TC_FWD;
+  constexpr bool SUMS = MODE == TC_BWD_SUMS;
   const int NSB = p.n_sbuf;
   extern __shared__ unsigned char smem_raw[];
   if (p.dbg_ts && threadIdx.x == 0) {  // per-CTA wall-clock stamps (ns): entry, after set-up, exit
@@ -431,13 +447,21 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tmem_ld_wait_dep(r);
         tmem_ld_wait_dep(r2);
         if (ok) {
+          if (SUMS) {  // the row scale is not known yet: both halves leave as they are ([E.Y | E.Ys], 2F floats per row and part)
 #pragma unroll
-          for (int q = 0; q < TC_CW / 4; ++q)
-            *reinterpret_cast<float4*>(out + h + q * 4) =
-                make_float4(fmaf(ix, __uint_as_float(r[q * 4]), __uint_as_float(r2[q * 4])),
-                            fmaf(ix, __uint_as_float(r[q * 4 + 1]), __uint_as_float(r2[q * 4 + 1])),
-                            fmaf(ix, __uint_as_float(r[q * 4 + 2]), __uint_as_float(r2[q * 4 + 2])),
-                            fmaf(ix, __uint_as_float(r[q * 4 + 3]), __uint_as_float(r2[q * 4 + 3])));
+            for (int q = 0; q < TC_CW / 4; ++q) {
+              *reinterpret_cast<uint4*>(out + h + q * 4) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+              *reinterpret_cast<uint4*>(out + p.F + h + q * 4) = make_uint4(r2[q * 4], r2[q * 4 + 1], r2[q * 4 + 2], r2[q * 4 + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < TC_CW / 4; ++q)
+              *reinterpret_cast<float4*>(out + h + q * 4) =
+                  make_float4(fmaf(ix, __uint_as_float(r[q * 4]), __uint_as_float(r2[q * 4])),
+                              fmaf(ix, __uint_as_float(r[q * 4 + 1]), __uint_as_float(r2[q * 4 + 1])),
+                              fmaf(ix, __uint_as_float(r[q * 4 + 2]), __uint_as_float(r2[q * 4 + 2])),
+                              fmaf(ix, __uint_as_float(r[q * 4 + 3]), __uint_as_float(r2[q * 4 + 3])));
+          }
         }
       }
       tc_fence_before();
@@ -465,7 +489,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       int32_t best_cb = 0x7fffffff;
       bool have_diag = false;
       float ixs = 0.f;
-      if (BWD) ixs = row_ok ? p.gscale * p.inv_x[row] : 0.f;
+      if (BWD && !SUMS) ixs = row_ok ? p.gscale * p.inv_x[row] : 0.f;
       // Each warp reads its 32-column slice of an S tile as two 16-column TMEM loads, software-pipelined one half ahead:
       // the tcgen05.ld of the next half (or of the next tile's first half) is in flight while the current half is processed
       // out of the other register set, and the S buffer returns to the MMA warp as soon as its second half sits in registers.
@@ -499,10 +523,10 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 1] = clock64();
         // ... while the first is processed
         if (!BWD) {
-          if (generic) fwd_chunk<true>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
-          else fwd_chunk<false>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          if (generic) fwd_chunk<true, PRE>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          else fwd_chunk<false, PRE>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
         } else {
-          bwd_chunk(rA, c1, c0, p_taddr);
+          bwd_chunk<PRE, SUMS>(rA, c1, c0, p_taddr, acc);
         }
         if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 2] = clock64();
         tmem_ld_wait_dep(rB);
@@ -516,10 +540,16 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           tmem_ld16(t_base + s_nxt * TCN, rA);
         }
         if (!BWD) {
-          if (generic) fwd_chunk<true>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
-          else fwd_chunk<false>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          if (generic) fwd_chunk<true, PRE>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          else fwd_chunk<false, PRE>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
         } else {
-          bwd_chunk(rB, c1, c0, p_taddr + TC_CW / 2);
+          bwd_chunk<PRE, SUMS>(rB, c1, c0, p_taddr + TC_CW / 2, acc);
+          if (SUMS && t == t_part) {
+            // columns past By are zero-filled operands: their logit is exactly 0, E exactly 1 (PRE: exp2(0)); they add nothing to
+            // the MMA (zero rows of Y) but one each to the sum — take them out again (exact in fp32)
+            const int pad = cb + 32 - By;
+            if (pad > 0) acc[0] -= (float)(pad > 32 ? 32 : pad) * (PRE ? 1.f : ex2f(c0));
+          }
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
@@ -546,7 +576,8 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
         }
       } else {
-        float* out = p.dx_part + ((int64_t)ch * p.Bx + row) * p.F;
+        float* out = p.dx_part + ((int64_t)ch * p.Bx + row) * (SUMS ? 2 * p.F : p.F);
+        if (SUMS && row_ok) p.row_e[((int64_t)ch * 4 + slice) * p.Bx + row] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
         if (istamp) p.dbg_ts[1 * 2048 + 1024 + it_iter * 4 + 2] = clock64();
         if (!last_item) {  // deferred: read out after the next item's first tile (no wait for MMA2 then)
           pend = true;
@@ -845,7 +876,7 @@ static long long* g_tc_dbg_ts = nullptr;
 // from the partials this call leaves in `workspace`.
 int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, float inv_temp, int64_t diag_offset,
                   float* row_sumexp, float* row_sum_s, float* diag, int32_t* row_argmax, int want_metrics, void* workspace,
-                  cudaStream_t s, int sums_only, float* out_inv) {
+                  cudaStream_t s, int sums_only, float* out_inv, int pre) {
   TcPlan pl = make_plan(Bx, By);
   TcParams p = {};
   p.X = (const __nv_bfloat16*)X;
@@ -853,7 +884,7 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   p.Bx = Bx; p.By = By; p.F = F;
   p.n_col_tiles = pl.n_col_tiles; p.total_tiles = pl.total_tiles;
   const float log2e = 1.4426950408889634f;
-  p.c1 = inv_temp * log2e; p.c0 = -inv_temp * log2e; p.inv_temp = inv_temp;
+  p.c1 = inv_temp * log2e; p.c0 = -inv_temp * log2e; p.inv_temp = pre ? 0.6931471805599453f : inv_temp;
   p.diag_offset = diag_offset;
   const int64_t stride = (4 * pl.max_parts * Bx * 4 + 255) / 256 * 256;
   char* w = (char*)workspace;
@@ -867,8 +898,14 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   p.use_tma = (!g_tc_force_manual && make_map(&mx, X, Bx, F) && make_map(&my, Y, By, F)) ? 1 : 0;
   if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); }
   const size_t smem = tc_smem_bytes(F, false);
-  TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  simce_tc_kernel<false><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, my, p);
+  if (pre) {
+    TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<TC_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    simce_tc_kernel<TC_FWD, true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, my, p);
+    TT_LAUNCH_CHECK("simce_tc_kernel<fwd,pre>");
+    return TT_OK;
+  }
+  TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<TC_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  simce_tc_kernel<TC_FWD, false><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, my, p);
   if (sums_only) {
     tc_rows_reduce_kernel<<<ceil_div(Bx, 32), 32 * RR_LANES, 0, s>>>(p.row_e, p.row_max, p.row_arg, Bx, pl.n_col_tiles, pl.total_tiles,
                                                                      pl.grid, p.X, p.Y, By, F, inv_temp, nullptr, row_sumexp, nullptr,
@@ -940,11 +977,207 @@ int simce_tc_bwd(const void* X, const void* Y, int64_t Bx, int64_t By, int F, fl
   p.use_tma = (!g_tc_force_manual && make_map(&mx, X, Bx, F) && make_map(&my, Y, By, F) && make_map(&mys, Ys, By, F)) ? 1 : 0;
   if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); memset(&mys, 0, sizeof(mys)); }
   const size_t smem = tc_smem_bytes(F, true);
-  TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  simce_tc_kernel<true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, mys, p);
+  TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<TC_BWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  simce_tc_kernel<TC_BWD, false><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, mys, p);
   tc_dx_reduce_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(p.dx_part, Bx * F, pl.n_col_tiles, pl.total_tiles, pl.grid, F, p.Y, diag_offset, t_off2,
                                                                   t_diag2 - t_off2, smooth ? ysum : nullptr, dX);
   TT_LAUNCH_CHECK("simce_tc_bwd");
+  return TT_OK;
+}
+
+
+// ---------------------------------------------------------------- three-pass train step (pre-scaled X operand)
+// The fused step runs THREE logits passes instead of four:
+//   P1  rows of S        X = c1*N,  Y = C            -> sum_j E_ij                        (simce_tc_kernel<TC_FWD, pre>)
+//   P2  rows of S^T      X = c1*C,  Y = [N | Ns]     -> sum_i E_ij AND the raw halves of dC (simce_tc_kernel<TC_BWD_SUMS, pre>)
+//   P3  rows of S again  X = c1*N,  Y = [C | Cs]     -> dN                                (simce_tc_kernel<TC_BWD, pre>)
+// with Ns = diag(g / rowsum) N (needs P1), Cs = diag(g / colsum) C (needs P2): the transposed gradient pass is the column-
+// statistics pass, its own row scale being applied by the reduce kernel once the pass has finished. E = exp2(c1 * s) here
+// (unshifted); the public sums stay "shifted" (sum exp(s/T - 1/T)) like everywhere else: k = exp(-1/T).
+//
+// tc_finish_kernel: per row, in fixed order: rs = sum of the E partials; row_sumexp = k rs, inv = 1 / row_sumexp;
+//   dX = (g / rs) sum_parts(E.Y) + sum_parts(E.Ys) - t_off sum_j Y_j - (t_diag - t_off) Y_dcol      (if dx_part)
+//   Xs = bf16((g / rs) X_unit)   — the column-scaled operand of the NEXT pass                        (if Xs_out)
+__global__ void __launch_bounds__(256)
+tc_finish_kernel(const float* __restrict__ row_e, const float* __restrict__ dx_part, int64_t Bx, int n_ct, long long T, int G, int F,
+                 const __nv_bfloat16* __restrict__ Y, int64_t diag_offset, float t_off2, float t_dd2, const float* __restrict__ ysum,
+                 float gscale, float k_shift, float* __restrict__ dX, float* __restrict__ sumexp_out, float* __restrict__ inv_out,
+                 const __nv_bfloat16* __restrict__ X_unit, __nv_bfloat16* __restrict__ Xs_out) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= Bx * F) return;
+  const int64_t row = i / F;
+  const int col = (int)(i - row * F);
+  const int n_parts = tc_parts_of_row_block((int)(row / TCM), n_ct, T, G);
+  float rs = 0.f;
+  for (int c = 0; c < 4 * n_parts; ++c) rs += row_e[(int64_t)c * Bx + row];
+  const float ixs = gscale / rs;
+  if (col == 0) {
+    const float se = k_shift * rs;
+    if (sumexp_out) sumexp_out[row] = se;
+    if (inv_out) inv_out[row] = 1.f / se;
+  }
+  if (dx_part) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int c = 0; c < n_parts; ++c) {
+      const float* base = dx_part + ((int64_t)c * Bx + row) * (2 * F) + col;
+      f4_add(a, *reinterpret_cast<const float4*>(base));
+      f4_add(b, *reinterpret_cast<const float4*>(base + F));
+    }
+    a.x = fmaf(ixs, a.x, b.x);
+    a.y = fmaf(ixs, a.y, b.y);
+    a.z = fmaf(ixs, a.z, b.z);
+    a.w = fmaf(ixs, a.w, b.w);
+    const uint2 yv = *reinterpret_cast<const uint2*>(Y + (diag_offset + row) * F + col);
+    const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.x));
+    const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.y));
+    a.x = fmaf(-t_dd2, y01.x, a.x);
+    a.y = fmaf(-t_dd2, y01.y, a.y);
+    a.z = fmaf(-t_dd2, y23.x, a.z);
+    a.w = fmaf(-t_dd2, y23.y, a.w);
+    if (ysum) {
+      const float4 ys = *reinterpret_cast<const float4*>(ysum + col);
+      a.x = fmaf(-t_off2, ys.x, a.x);
+      a.y = fmaf(-t_off2, ys.y, a.y);
+      a.z = fmaf(-t_off2, ys.z, a.z);
+      a.w = fmaf(-t_off2, ys.w, a.w);
+    }
+    *reinterpret_cast<float4*>(dX + i) = a;
+  }
+  if (Xs_out) {
+    const uint2 xv = *reinterpret_cast<const uint2*>(X_unit + i);
+    const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xv.x));
+    const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xv.y));
+    *reinterpret_cast<uint2*>(Xs_out + i) = pack_bf16x4(make_float4(x01.x * ixs, x01.y * ixs, x23.x * ixs, x23.y * ixs));
+  }
+}
+
+// Ys[j,:] = bf16(g * k / sumexp[j] * Y[j,:]) from the (exchanged, shifted) sums: the multi-GPU form of the Xs output above
+__global__ void __launch_bounds__(256)
+tc_scale_rows_sum_kernel(const __nv_bfloat16* __restrict__ Y, const float* __restrict__ sumexp, float gk, int64_t By, int F,
+                         __nv_bfloat16* __restrict__ Ys) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= By * F) return;
+  const float sc = gk / sumexp[i / F];
+  const uint4 v = *reinterpret_cast<const uint4*>(Y + i);
+  const __nv_bfloat162* in = reinterpret_cast<const __nv_bfloat162*>(&v);
+  uint4 o;
+  __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float2 f = __bfloat1622float2(in[u]);
+    out[u] = __floats2bfloat162_rn(f.x * sc, f.y * sc);
+  }
+  *reinterpret_cast<uint4*>(Ys + i) = o;
+}
+
+struct Tc3Ws {  // workspace of one gradient pass
+  float* dx_part;
+  float* ysum_part;
+  float* ysum;
+  float* row_e;
+};
+static int64_t tc3_a256(int64_t x) { return (x + 255) / 256 * 256; }
+static Tc3Ws tc3_carve(void* workspace, int64_t Bx, int F, int max_parts) {
+  char* w = (char*)workspace;
+  Tc3Ws r;
+  r.dx_part = (float*)w;
+  w += tc3_a256((int64_t)max_parts * Bx * 2 * F * 4);
+  r.ysum_part = (float*)w;
+  w += tc3_a256((int64_t)YS_BLOCKS * 128 * 4);
+  r.ysum = (float*)w;
+  w += tc3_a256(128 * 4);
+  r.row_e = (float*)w;
+  return r;
+}
+int64_t simce_tc_grad_workspace_bytes(int64_t Bx, int64_t By, int F) {
+  TcPlan pl = make_plan(Bx, By);
+  return tc3_a256((int64_t)pl.max_parts * Bx * 2 * F * 4) + tc3_a256((int64_t)YS_BLOCKS * 128 * 4) + tc3_a256(128 * 4) +
+         tc3_a256((int64_t)4 * pl.max_parts * Bx * 4) + 1024;
+}
+
+// P1: statistics pass; partials stay in `workspace` (layout of simce_tc_rows) for simce_tc_rows_finish / simce_tc_rows_metrics
+int simce_tc_rows_pre(const void* Xs, const void* Y, int64_t Bx, int64_t By, int F, float inv_temp, int64_t diag_offset, float* diag,
+                      void* workspace, cudaStream_t s) {
+  return simce_tc_rows(Xs, Y, Bx, By, F, inv_temp, diag_offset, nullptr, nullptr, diag, nullptr, 1, workspace, s, 0, nullptr, 1);
+}
+
+int simce_tc_rows_finish(const void* workspace, int64_t Bx, int64_t By, int F, float inv_temp, float* row_sumexp, float* inv_row,
+                         const void* X_unit, float gscale, void* Xs_out, cudaStream_t s) {
+  TcPlan pl = make_plan(Bx, By);
+  const float* row_e = (const float*)workspace;
+  tc_finish_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(row_e, nullptr, Bx, pl.n_col_tiles, pl.total_tiles, pl.grid, F, nullptr, 0, 0.f,
+                                                              0.f, nullptr, gscale, expf(-inv_temp), nullptr, row_sumexp, inv_row,
+                                                              (const __nv_bfloat16*)X_unit, (__nv_bfloat16*)Xs_out);
+  TT_LAUNCH_CHECK("tc_finish_kernel(rows)");
+  return TT_OK;
+}
+
+// P2 / P3. inv_x == NULL: deferred row scale (TC_BWD_SUMS), else inv_x are the (shifted) reciprocal row sums (TC_BWD).
+int simce_tc_grad_pre(const void* Xs, const void* Y, const void* Ys, int64_t Bx, int64_t By, int F, float inv_temp, int64_t diag_offset,
+                      const float* inv_x, float gscale, int smooth, void* workspace, cudaStream_t s) {
+  TcPlan pl = make_plan(Bx, By);
+  Tc3Ws w = tc3_carve(workspace, Bx, F, pl.max_parts);
+  TcParams p = {};
+  p.X = (const __nv_bfloat16*)Xs;
+  p.Y = (const __nv_bfloat16*)Y;
+  p.Ys = (const __nv_bfloat16*)Ys;
+  p.Bx = Bx; p.By = By; p.F = F;
+  p.n_col_tiles = pl.n_col_tiles; p.total_tiles = pl.total_tiles;
+  p.c1 = 1.f; p.c0 = 0.f; p.inv_temp = 0.6931471805599453f;
+  p.diag_offset = diag_offset;
+  p.inv_x = inv_x;
+  p.gscale = gscale * expf(-inv_temp);  // E is unshifted here, the public reciprocals belong to the shifted sums
+  p.dx_part = w.dx_part;
+  p.row_e = w.row_e;
+  p.dbg_ts = g_tc_dbg_ts;
+  tc_buffers(F, true, p.n_stages, p.n_xbuf);
+  p.n_dbuf = 1;
+  p.n_sbuf = F == 64 ? 2 : 1;
+  if (smooth) {
+    tc_ysum_partial_kernel<<<YS_BLOCKS, 512, 0, s>>>(p.Y, By, F, w.ysum_part);
+    tc_ysum_final_kernel<<<1, 128, 0, s>>>(w.ysum_part, F, w.ysum);
+  }
+  CUtensorMap mx, my, mys;
+  p.use_tma = (!g_tc_force_manual && make_map(&mx, Xs, Bx, F) && make_map(&my, Y, By, F) && make_map(&mys, Ys, By, F)) ? 1 : 0;
+  if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); memset(&mys, 0, sizeof(mys)); }
+  const size_t smem = tc_smem_bytes(F, true);
+  if (inv_x) {
+    TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<TC_BWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    simce_tc_kernel<TC_BWD, true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, mys, p);
+  } else {
+    TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<TC_BWD_SUMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    simce_tc_kernel<TC_BWD_SUMS, true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, mys, p);
+  }
+  TT_LAUNCH_CHECK("simce_tc_kernel<bwd,pre>");
+  return TT_OK;
+}
+
+int simce_tc_grad_finish(const void* workspace, int64_t Bx, int64_t By, int F, float inv_temp, int64_t diag_offset, const void* Y,
+                         int deferred, float gscale, float tgt_diag, float tgt_off, float* dX, float* sumexp_out, float* inv_out,
+                         const void* X_unit, void* Xs_out, cudaStream_t s) {
+  TcPlan pl = make_plan(Bx, By);
+  Tc3Ws w = tc3_carve(const_cast<void*>(workspace), Bx, F, pl.max_parts);
+  const float t_diag2 = 2.f * gscale * tgt_diag, t_off2 = 2.f * gscale * tgt_off;
+  const bool smooth = tgt_off != 0.f;
+  if (deferred) {
+    tc_finish_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(w.row_e, w.dx_part, Bx, pl.n_col_tiles, pl.total_tiles, pl.grid, F,
+                                                                (const __nv_bfloat16*)Y, diag_offset, t_off2, t_diag2 - t_off2,
+                                                                smooth ? w.ysum : nullptr, gscale, expf(-inv_temp), dX, sumexp_out,
+                                                                inv_out, (const __nv_bfloat16*)X_unit, (__nv_bfloat16*)Xs_out);
+  } else {
+    tc_dx_reduce_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(w.dx_part, Bx * F, pl.n_col_tiles, pl.total_tiles, pl.grid, F,
+                                                                   (const __nv_bfloat16*)Y, diag_offset, t_off2, t_diag2 - t_off2,
+                                                                   smooth ? w.ysum : nullptr, dX);
+  }
+  TT_LAUNCH_CHECK("simce_tc_grad_finish");
+  return TT_OK;
+}
+
+int simce_tc_scale_rows(const void* Y_unit, const float* sumexp, float gscale, float inv_temp, int64_t By, int F, void* Ys_out,
+                        cudaStream_t s) {
+  tc_scale_rows_sum_kernel<<<ceil_div(By * F / 8, 256), 256, 0, s>>>((const __nv_bfloat16*)Y_unit, sumexp, gscale * expf(-inv_temp), By, F,
+                                                                      (__nv_bfloat16*)Ys_out);
+  TT_LAUNCH_CHECK("tc_scale_rows_sum_kernel");
   return TT_OK;
 }
 

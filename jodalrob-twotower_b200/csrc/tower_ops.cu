@@ -161,6 +161,27 @@ l2norm_fwd_kernel(const float* __restrict__ Z, int64_t M, int F, T* __restrict__
   if (lane == 0 && nrm) nrm[row] = n;
 }
 
+// bf16 tower outputs twice: unit rows, and the same rows times `scale` (rounded once, from the fp32 value): the pre-scaled
+// operand of the logits passes (scale = log2(e) / T makes the tensor-core accumulator the exponent of exp2)
+__global__ void __launch_bounds__(256)
+l2norm_fwd_scaled_kernel(const float* __restrict__ Z, int64_t M, int F, __nv_bfloat16* __restrict__ E, __nv_bfloat16* __restrict__ Es,
+                         float scale, float* __restrict__ nrm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* z = Z + row * F;
+  float ss = 0.f;
+  for (int f = lane; f < F; f += 32) ss += z[f] * z[f];
+  ss = warp_sum(ss);
+  const float n = fmaxf(sqrtf(ss), 1e-12f);
+  for (int f = lane; f < F; f += 32) {
+    const float u = z[f] / n;
+    E[row * F + f] = __float2bfloat16_rn(u);
+    Es[row * F + f] = __float2bfloat16_rn(u * scale);
+  }
+  if (lane == 0 && nrm) nrm[row] = n;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 l2norm_bwd_kernel(const float* __restrict__ DE, const T* __restrict__ E, const float* __restrict__ nrm, int64_t M, int F,
@@ -301,6 +322,15 @@ int tt_l2norm_forward(const float* z, int64_t M, int32_t F, void* e, int32_t out
   else
     l2norm_fwd_kernel<__nv_bfloat16><<<ceil_div(M, 8), 256, 0, s>>>(z, M, F, (__nv_bfloat16*)e, nrm);
   TT_LAUNCH_CHECK("l2norm_fwd_kernel");
+  return TT_OK;
+}
+
+int tt_l2norm_forward_scaled(const float* z, int64_t M, int32_t F, void* e_bf16, void* e_scaled_bf16, float scale, float* nrm,
+                             tt_stream_t stream) {
+  TT_CHECK_ARG(z && e_bf16 && e_scaled_bf16 && M > 0 && F > 0, "tt_l2norm_forward_scaled: bad arguments");
+  l2norm_fwd_scaled_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(z, M, F, (__nv_bfloat16*)e_bf16,
+                                                                            (__nv_bfloat16*)e_scaled_bf16, scale, nrm);
+  TT_LAUNCH_CHECK("l2norm_fwd_scaled_kernel");
   return TT_OK;
 }
 

@@ -309,7 +309,8 @@ class DistributedEngine(TwoTowerEngine):
         blocks_ok = (n_l * 4) % 16 == 0 and (B * cfg.final_dim * esz_e) % 16 == 0 and (B * 4) % 16 == 0 and n_l > 0
         if self.peer_sites is not None and blocks_ok and os.environ.get("TT_PEER_EXCHANGE", "1") != "0":
             parts = {"ids": cap * 4, "e0": Bg * cfg.final_dim * esz_e, "e1": Bg * cfg.final_dim * esz_e,
-                     "colsum": W * (Bg + B) * 4}  # per rank: its column-sum partials [Bg] followed by its row sums [B]
+                     "colsum": W * (Bg + B) * 4,  # per rank: its column-sum partials [Bg] followed by its row sums [B]
+                     "rows3": Bg * 4, "cols3": Bg * 4}  # three-pass step: all ranks' row sums / column sums of exp
             xoff, o = {}, 0
             for k_, nb in parts.items():
                 xoff[k_] = o
@@ -320,12 +321,22 @@ class DistributedEngine(TwoTowerEngine):
             ws.ids_all = xbuf[xoff["ids"]:xoff["ids"] + cap * 4].view(torch.int32)
             ws.e_all = [xbuf[xoff[k_]:xoff[k_] + parts[k_]].view(self.emb_torch).view(Bg, cfg.final_dim) for k_ in ("e0", "e1")]
             ws.colsum_slots = xbuf[xoff["colsum"]:xoff["colsum"] + W * (Bg + B) * 4].view(torch.float32)
+            ws.x_rows3 = xbuf[xoff["rows3"]:xoff["rows3"] + Bg * 4].view(torch.float32)
+            ws.x_cols3 = xbuf[xoff["cols3"]:xoff["cols3"] + Bg * 4].view(torch.float32)
             ws.xmsg = torch.empty(Bg + B, **f32)      # what this rank sends: column-sum partials, then its row sums
             ws.col_partial, ws.row_sumexp = ws.xmsg[:Bg], ws.xmsg[Bg:]
             ws.xtab = {k_: torch.tensor([p_ + xoff[k_] for p_ in xpeer], dtype=torch.int64, device=dev) for k_ in parts}
             torch.cuda.synchronize(dev)
             self.comm.dist.barrier(group=self.comm.group, device_ids=[dev.index if dev.index is not None else torch.cuda.current_device()])
         ws.sim_ws = torch.empty(q("tt_simce_workspace_bytes", Bg, Bg, cfg.final_dim), dtype=torch.uint8, device=dev)
+        # three-pass logits step: this rank's rows against all ranks' columns; the row / column sums of the other ranks arrive
+        # by all-gather (peer pushes when available)
+        self._alloc_sim3(ws, B, Bg)
+        ws.rowsum_all = torch.empty(Bg, **f32)
+        ws.colsum_all = torch.empty(Bg, **f32)
+        ws.sums_loc = [torch.empty(B, **f32) for _ in range(2)]
+        if ws.xtab is not None and "rows3" in ws.xtab:
+            ws.rowsum_all, ws.colsum_all = ws.x_rows3, ws.x_cols3
         return ws
 
     # ---- forward pieces
@@ -411,6 +422,22 @@ class DistributedEngine(TwoTowerEngine):
             self.comm.all_gather(ws.e_all[0], ws.e[0])
             self.comm.all_gather(ws.e_all[1], ws.e[1])
         css = ptr(ws.col_sum_s) if cfg.label_smoothing > 0 else 0
+        ws.pending3 = False
+        if self._in_fused and getattr(ws, "sim3_ws", None) is not None:
+            # three-pass step (engine.loss_forward): P1 over this rank's notice rows x all company columns, then the row sums of
+            # every rank are exchanged and all notice rows scaled by g / row_sum (the second operand of P2)
+            F, nb = cfg.final_dim, ws.sim3_ws.numel()
+            ws.gscale3 = 0.5 / Bg * inv_t
+            self._call("tt_simce3_rows", ptr(ws.es[0]), ptr(ws.e_all[1]), B, Bg, F, inv_t, off, ptr(ws.diag), ptr(ws.sim3_ws), nb, s)
+            self._call("tt_simce3_rows_finish", ptr(ws.sim3_ws), nb, B, Bg, F, inv_t, ptr(ws.sums_loc[0]), ptr(ws.inv_row), 0,
+                       ws.gscale3, 0, s)
+            if px:
+                self._peer_allgather(ws.sums_loc[0], ws.xtab["rows3"], "invrow")
+            else:
+                self.comm.all_gather(ws.rowsum_all, ws.sums_loc[0])
+            self._call("tt_simce3_scale_rows", ptr(ws.e_all[0]), ptr(ws.rowsum_all), ws.gscale3, inv_t, Bg, F, ptr(ws.xs[0]), s)
+            ws.pending3 = True
+            return ws.out5
         self._call("tt_simce_forward", ptr(ws.e[0]), ptr(ws.e_all[1]), B, Bg, cfg.final_dim, self.emb_tt, inv_t, off,
                    ptr(ws.row_sumexp), ptr(ws.col_partial if px else ws.col_sumexp), ptr(ws.row_sum_s), css, ptr(ws.diag),
                    ptr(ws.row_argmax), ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=4)
@@ -454,6 +481,55 @@ class DistributedEngine(TwoTowerEngine):
         inv_t = 1.0 / cfg.temperature
         gscale = dloss * 0.5 / Bg * inv_t
         F = cfg.final_dim
+        if getattr(ws, "pending3", False):
+            ws.pending3 = False
+            px = ws.xtab is not None
+            nb, ls, g = ws.sim3_ws.numel(), cfg.label_smoothing, ws.gscale3
+            css = ptr(ws.col_sum_s) if ls > 0 else 0
+            # P2: this rank's company rows x all notice columns: their sums of exp ARE the column sums of S for this rank's columns
+            # (complete: every notice row is here) — no cross-rank reduction, only an all-gather for P3's operand
+            self._call("tt_simce3_grad", ptr(ws.es[1]), ptr(ws.e_all[0]), ptr(ws.xs[0]), B, Bg, F, inv_t, off, 0, g, ls,
+                       ptr(ws.sim3_ws), nb, s)
+            self._call("tt_simce3_grad_finish", ptr(ws.sim3_ws), nb, B, Bg, F, inv_t, off, ptr(ws.e_all[0]), 1, g, ls, Bg,
+                       ptr(ws.de[1]), ptr(ws.sums_loc[1]), ptr(ws.inv_scratch[1]), 0, 0, s)
+            if px:
+                self._peer_allgather(ws.sums_loc[1], ws.xtab["cols3"], "colsum")
+            else:
+                self.comm.all_gather(ws.colsum_all, ws.sums_loc[1])
+            self._call("tt_simce3_scale_rows", ptr(ws.e_all[1]), ptr(ws.colsum_all), g, inv_t, Bg, F, ptr(ws.xs[1]), s)
+            self._call("tt_simce3_grad", ptr(ws.es[0]), ptr(ws.e_all[1]), ptr(ws.xs[1]), B, Bg, F, inv_t, off, ptr(ws.inv_row), g, ls,
+                       ptr(ws.sim3_ws), nb, s)
+            self._call("tt_simce3_grad_finish", ptr(ws.sim3_ws), nb, B, Bg, F, inv_t, off, ptr(ws.e_all[1]), 0, g, ls, Bg,
+                       ptr(ws.de[0]), 0, 0, 0, 0, s)
+
+            def metrics(ms):
+                self._call("tt_simce3_metrics", ptr(ws.es[0]), ptr(ws.e_all[1]), B, Bg, F, ptr(ws.row_sum_s), ptr(ws.row_argmax),
+                           ptr(ws.sim3_ws), nb, ms, n_kernels=2)
+                if css:  # sum_i S_ij / T of this rank's columns: company rows against the sum of ALL notice rows, complete locally
+                    self._call("tt_simce3_metrics", ptr(ws.es[1]), ptr(ws.e_all[0]), B, Bg, F, ws.col_sum_s.data_ptr() + 4 * off, 0,
+                               ptr(ws.sim3_ws), nb, ms, n_kernels=2)
+                self._call("tt_simce_finalize", ptr(ws.sums_loc[0]), ptr(ws.colsum_all), ptr(ws.row_sum_s), css, ptr(ws.diag),
+                           ptr(ws.row_argmax), B, Bg, off, Bg, inv_t, ls, ptr(ws.inv_scratch[0]), ptr(ws.inv_col), ptr(ws.partial), ms)
+                if self.peer_sites is not None:
+                    self._call("tt_peer_allreduce_f64", ptr(ws.partial), ws.partial.numel(), self.rank, self.world,
+                               ptr(self.peer_sites["partial"]), self.peer_n_max,
+                               self.peer_epochs.data_ptr() + 8 * self.PEER_SITES.index("partial"), ms)
+                else:
+                    self.comm.all_reduce(ws.partial)
+                self._call("tt_simce_scalars", ptr(ws.partial), Bg, ptr(ws.out5), ms)
+
+            if px and self.profile is None and self.defer_metrics:
+                def deferred():
+                    ms_ = self._metrics_stream
+                    ms_.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(ms_):
+                        metrics(ms_.cuda_stream)
+                        ws.metrics_done = torch.cuda.Event()
+                        ws.metrics_done.record(ms_)
+                ws.deferred_metrics = deferred
+            else:
+                metrics(s)
+            return
         self._call("tt_simce_backward", ptr(ws.e[0]), ptr(ws.e_all[1]), B, Bg, F, self.emb_tt, inv_t, off, ptr(ws.inv_row),
                    ptr(ws.inv_col), gscale, cfg.label_smoothing, Bg, ptr(ws.de[0]), ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=2)
         self._call("tt_simce_backward", ptr(ws.e[1]), ptr(ws.e_all[0]), B, Bg, F, self.emb_tt, inv_t, off,

@@ -26,6 +26,7 @@ from .native import TT_ADAM_DENSE_EXACT, TT_ADAM_DENSE_UNTOUCHED, TT_ADAM_SPARSE
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+LOG2E = 1.4426950408889634
 
 
 @dataclass
@@ -349,6 +350,7 @@ class TwoTowerEngine:
         split_bytes = q("tt_simce_split_workspace_bytes", B, B, cfg.final_dim) if self.emb_tt != TT_F32 else 0
         ws.sim_ws_fwd = torch.empty(max(split_bytes, 16), dtype=torch.uint8, device=dev)
         ws.inv_scratch = [torch.empty(B, **f32), torch.empty(B, **f32)]
+        self._alloc_sim3(ws, B, B)
         ws.partial = torch.zeros(128, dtype=torch.float64, device=dev)  # 16 block partials x 8
         ws.out5 = torch.zeros(5, **f32)
         ws.sort_ws = torch.empty(q("tt_ebc_sort_workspace_bytes", n_tot, max(self.total_rows, 1)), dtype=torch.uint8, device=dev)
@@ -357,6 +359,19 @@ class TwoTowerEngine:
                        for t in range(2)]
         self._ws[B] = ws
         return ws
+
+    def _alloc_sim3(self, ws: _Ws, Bx: int, By: int):
+        """Buffers of the three-pass logits step (bf16 / tcgen05, fused step): es = tower outputs pre-scaled by log2(e)/T (the X
+        operand of every pass), xs = the other side's rows scaled by g / sum_exp (the Ys operand of the gradient passes)."""
+        cfg, dev = self.cfg, self.device
+        ws.sim3_ws = None
+        if self.emb_tt == TT_F32 or os.environ.get("TT_SIMCE_PASSES", "3") == "4":
+            return
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        ws.es = [torch.empty(Bx, cfg.final_dim, **bf) for _ in range(2)]
+        ws.xs = [torch.empty(By, cfg.final_dim, **bf) for _ in range(2)]
+        ws.sim3_ws = torch.empty(self.lib.query("tt_simce3_workspace_bytes", Bx, By, cfg.final_dim), dtype=torch.uint8, device=dev)
+        ws.pending3 = False
 
     # ------------------------------------------------------------------ Linear dispatch (fp32 SIMT / bf16 tcgen05)
     def _w16(self, name: str) -> torch.Tensor:
@@ -481,7 +496,12 @@ class TwoTowerEngine:
             x, width, idx = ws.y[t][bi], h, idx + 4
         F = cfg.final_dim
         self._lin_fwd(x, width, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", ws.z[t], F, True, B, F, width, 0)
-        self._call("tt_l2norm_forward", ptr(ws.z[t]), B, F, ptr(ws.e[t]), self.emb_tt, ptr(ws.nrm[t]), s)
+        if getattr(ws, "sim3_ws", None) is not None:
+            # unit rows AND rows pre-scaled by log2(e)/T (rounded once from fp32): the logits passes then need no multiply per logit
+            self._call("tt_l2norm_forward_scaled", ptr(ws.z[t]), B, F, ptr(ws.e[t]), ptr(ws.es[t]), LOG2E / cfg.temperature,
+                       ptr(ws.nrm[t]), s)
+        else:
+            self._call("tt_l2norm_forward", ptr(ws.z[t]), B, F, ptr(ws.e[t]), self.emb_tt, ptr(ws.nrm[t]), s)
         return ws.e[t]
 
     def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int, tower: int = 0) -> int:
@@ -493,6 +513,18 @@ class TwoTowerEngine:
         self.profile_tag = ""
         inv_t = 1.0 / cfg.temperature
         css = ptr(ws.col_sum_s) if cfg.label_smoothing > 0 else 0  # column sums of S are only needed for label smoothing
+        ws.pending3 = False
+        if self._in_fused and getattr(ws, "sim3_ws", None) is not None:
+            # Fused step, tensor-core path: THREE logits passes per step instead of four. Here: P1 (row sums of exp) and its
+            # reduce, which also writes the notice rows scaled by g / row_sum — the second MMA operand of P2. The column sums come
+            # out of P2 (loss_backward), the loss value and the metrics after that, off the critical path.
+            F, nb = cfg.final_dim, ws.sim3_ws.numel()
+            ws.gscale3 = 0.5 / B * inv_t
+            self._call("tt_simce3_rows", ptr(ws.es[0]), ptr(ws.e[1]), B, B, F, inv_t, 0, ptr(ws.diag), ptr(ws.sim3_ws), nb, s)
+            self._call("tt_simce3_rows_finish", ptr(ws.sim3_ws), nb, B, B, F, inv_t, ptr(ws.row_sumexp), ptr(ws.inv_row), ptr(ws.e[0]),
+                       ws.gscale3, ptr(ws.xs[0]), s)
+            ws.pending3 = True
+            return ws.out5
         if (self.emb_tt != TT_F32 and self._in_fused and self.profile is None and self.defer_metrics and self.two_streams
                 and ws.sim_ws_fwd.numel() > 16):
             # Fused step, tensor-core path: only the row/column sums of exp (and their reciprocals) are on the critical path — the
@@ -602,6 +634,43 @@ class TwoTowerEngine:
         inv_t = 1.0 / cfg.temperature
         gscale = dloss * 0.5 / B * inv_t
         F = cfg.final_dim
+        if getattr(ws, "pending3", False):
+            ws.pending3 = False
+            nb, ls, g = ws.sim3_ws.numel(), cfg.label_smoothing, ws.gscale3
+            css = ptr(ws.col_sum_s) if ls > 0 else 0
+            # P2: the transposed problem (rows = company): column sums of exp on the fly + the raw halves of dC; its reduce applies the
+            # row scale, writes col_sumexp / inv_col and the company rows scaled by g / col_sum — the second operand of P3
+            self._call("tt_simce3_grad", ptr(ws.es[1]), ptr(ws.e[0]), ptr(ws.xs[0]), B, B, F, inv_t, 0, 0, g, ls, ptr(ws.sim3_ws), nb, s)
+            self._call("tt_simce3_grad_finish", ptr(ws.sim3_ws), nb, B, B, F, inv_t, 0, ptr(ws.e[0]), 1, g, ls, B, ptr(ws.de[1]),
+                       ptr(ws.col_sumexp), ptr(ws.inv_col), ptr(ws.e[1]), ptr(ws.xs[1]), s)
+            # P3: dN, row scale known from P1
+            self._call("tt_simce3_grad", ptr(ws.es[0]), ptr(ws.e[1]), ptr(ws.xs[1]), B, B, F, inv_t, 0, ptr(ws.inv_row), g, ls,
+                       ptr(ws.sim3_ws), nb, s)
+            self._call("tt_simce3_grad_finish", ptr(ws.sim3_ws), nb, B, B, F, inv_t, 0, ptr(ws.e[1]), 0, g, ls, B, ptr(ws.de[0]), 0, 0,
+                       0, 0, s)
+
+            def metrics(ms):  # loss value + metrics from the P1 partials and the sums
+                self._call("tt_simce3_metrics", ptr(ws.es[0]), ptr(ws.e[1]), B, B, F, ptr(ws.row_sum_s), ptr(ws.row_argmax),
+                           ptr(ws.sim3_ws), nb, ms, n_kernels=2)
+                if css:
+                    self._call("tt_simce3_metrics", ptr(ws.es[1]), ptr(ws.e[0]), B, B, F, css, 0, ptr(ws.sim3_ws), nb, ms, n_kernels=2)
+                self._call("tt_simce_finalize", ptr(ws.row_sumexp), ptr(ws.col_sumexp), ptr(ws.row_sum_s), css, ptr(ws.diag),
+                           ptr(ws.row_argmax), B, B, 0, B, inv_t, ls, ptr(ws.inv_scratch[0]), ptr(ws.inv_scratch[1]),
+                           ptr(ws.partial), ms)
+                self._call("tt_simce_scalars", ptr(ws.partial), B, ptr(ws.out5), ms)
+
+            if self.defer_metrics and self.two_streams and self.profile is None:
+                def deferred():  # launched by fused_step behind the gradient passes, joined at the end of the step
+                    ms_ = self._metrics_stream
+                    ms_.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(ms_):
+                        metrics(ms_.cuda_stream)
+                        ws.metrics_done = torch.cuda.Event()
+                        ws.metrics_done.record(ms_)
+                ws.deferred_metrics = deferred
+            else:
+                metrics(s)
+            return
         self._call("tt_simce_backward", ptr(ws.e[0]), ptr(ws.e[1]), B, B, F, self.emb_tt, inv_t, 0, ptr(ws.inv_row), ptr(ws.inv_col),
                    gscale, cfg.label_smoothing, B, ptr(ws.de[0]), ptr(ws.sim_ws), ws.sim_ws.numel(), s, n_kernels=2)
         self._call("tt_simce_backward", ptr(ws.e[1]), ptr(ws.e[0]), B, B, F, self.emb_tt, inv_t, 0, ptr(ws.inv_col), ptr(ws.inv_row),

@@ -20,6 +20,11 @@ from . import ref_port
 MODEL = dict(emb_dim=32, notice_dense=256, company_dense=128, hidden=[128, 64], final_dim=64, temperature=1.0)
 
 
+def build_port(schema, seed: int = 0):
+    return ref_port.build_port_task(schema, MODEL["emb_dim"], MODEL["notice_dense"], MODEL["company_dense"], MODEL["hidden"],
+                                    MODEL["final_dim"], 0.0, MODEL["temperature"], seed=seed)
+
+
 def global_batches(schema, B_global: int, steps: int, seed: int = 4321):
     g = torch.Generator().manual_seed(seed)
     out = []
@@ -59,7 +64,8 @@ def compare_state(ours: Dict[str, torch.Tensor], ref: Dict[str, torch.Tensor], t
         den += float(b.pow(2).sum())
         if ".embeddings." in k:
             worst_table = max(worst_table, diff / scale)
-            if diff > tol * scale:
+            # fp32: Adam's update is ill-conditioned where |g| ~ eps (oracle/compare.py) — single elements may sit up to a step apart
+            if diff > tol * scale + (2 * travel if tol < 1e-3 else 0.0):
                 bad.append(k)
         else:
             worst_dense = max(worst_dense, max(diff - 2 * travel, 0.0) / scale)
@@ -72,12 +78,13 @@ def compare_state(ours: Dict[str, torch.Tensor], ref: Dict[str, torch.Tensor], t
 
 def run(tt, schema, device, dtype: str = "bf16", B_local: int = 1024, steps: int = 3, world: int = 1, rank: int = 0,
         graph: bool = True, lr: float = 1e-3, weight_decay: float = 1e-5, warmup_steps: int = 2, seed: int = 0,
-        ttdist=None, comm=None, return_task: bool = False) -> Optional[dict]:
-    """Every rank calls it (collective at world > 1); the dict comes back on rank 0, None elsewhere."""
+        ttdist=None, comm=None, return_task: bool = False, port=None) -> Optional[dict]:
+    """Every rank calls it (collective at world > 1); the dict comes back on rank 0, None elsewhere. `port`: a freshly built
+    port shared by in-process rank threads (the global torch RNG is not thread-safe); rank 0 steps it at the end."""
     tol = 2e-2 if dtype == "bf16" else 1e-5
     nk, ck = [k for k, _ in schema["notice"]], [k for k, _ in schema["company"]]
-    port = ref_port.build_port_task(schema, MODEL["emb_dim"], MODEL["notice_dense"], MODEL["company_dense"], MODEL["hidden"],
-                                    MODEL["final_dim"], 0.0, MODEL["temperature"], seed=seed)
+    if port is None:
+        port = build_port(schema, seed)
     init = {k: v.clone() for k, v in port.state_dict().items()}
     if world > 1:
         model = dict(MODEL, dropout=0.0)

@@ -124,3 +124,159 @@ def test_torchrun_sharded_bf16_peer_path_vs_reference(world):
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "bf16" in r.stdout and "FAIL" not in r.stdout
+
+
+@pytest.mark.parametrize("world,dtype,bl", [(2, "bf16", 1024), (4, "bf16", 512), (2, "fp32", 256)])
+def test_emulated_ranks_sharded_step_readme_schema_vs_reference(world, dtype, bl):
+    """The row-wise sharded step in the benchmarked precision on ONE GPU: `world` rank threads, host-mediated collectives
+    (dist.ThreadComm: same engine code, the peer-memory kernels replaced by their all_gather / all_reduce equivalents), against the
+    reference port on the concatenated global batch. Covers the three-pass logits step with its row-sum / column-sum exchanges,
+    SyncBN, sharded lookup / pull update in bf16 — the torchrun test above covers the NVLink kernels themselves."""
+    import threading
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200 import dist as ttd
+    schema = readme_schema()
+    port = bench_parity.build_port(schema, 0)
+    tw = ttd.ThreadWorld(world)
+    tt.native.lib()
+    results, errors = [None] * world, []
+
+    def rank_main(r):
+        try:
+            torch.cuda.set_device(0)
+            results[r] = bench_parity.run(tt, schema, torch.device(DEV), dtype=dtype, B_local=bl, steps=3, world=world, rank=r,
+                                          graph=False, ttdist=ttd, comm=ttd.ThreadComm(tw, r), port=port)
+        except Exception:
+            import traceback
+            errors.append(traceback.format_exc())
+            try:
+                tw.bar.abort()
+            except Exception:
+                pass
+
+    ths = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=600)
+    assert not errors, errors[0]
+    res = results[0]
+    assert res["ok"], res
+
+
+# ------------------------------------------------------------------------------- the logits entry points the timed step calls
+def _unit_pair(Bx, By, off, F, seed):
+    g = torch.Generator().manual_seed(seed)
+    y_all = torch.nn.functional.normalize(torch.randn(By, F, generator=g), dim=1)
+    x = torch.nn.functional.normalize(torch.randn(Bx, F, generator=g) + 0.7 * y_all[off:off + Bx], dim=1)
+    return x, y_all
+
+
+@pytest.mark.parametrize("Bx,By,off,F,T,ls", [(128, 128, 0, 64, 1.0, 0.0), (200, 200, 0, 64, 0.5, 0.1), (1000, 1000, 0, 128, 1.0, 0.0),
+                                              (300, 1200, 600, 64, 0.05, 0.0), (8192, 8192, 0, 64, 1.0, 0.0),
+                                              (8192, 65536, 16384, 64, 1.0, 0.0)])
+def test_three_pass_logits_step_vs_fp64_oracle(Bx, By, off, F, T, ls):
+    """tt_simce3_* (what the fused bf16 step runs: P1 row sums, P2 = transposed gradient pass that also yields the column sums,
+    P3) against fp64 math ON THE OPERANDS THE KERNELS CONSUME (bf16 unit rows, and bf16 rows pre-scaled by log2(e)/T), so what is
+    measured is the kernels (ex2.approx, bf16 E / Ys operands, partial-sum order), not the input rounding — that is covered end to
+    end by the trajectory tests above. This rank owns rows [off, off + Bx) of both towers of a global problem with By rows per
+    tower; the other ranks' row / column sums arrive "by all-gather" (here: the exact ones). fp64 reference on the GPU, chunked.
+    Tolerances: sums / diag 3e-4 relative, gradients 2e-2 (north_star bf16 bar)."""
+    import math
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200.native import ptr
+    lib = tt.native.lib()
+    Bg, LN2 = By, math.log(2.0)
+    g = torch.Generator().manual_seed(Bx + By)
+    c_all = torch.nn.functional.normalize(torch.randn(By, F, generator=g), dim=1)
+    n_all = torch.nn.functional.normalize(torch.randn(By, F, generator=g) + 0.7 * c_all, dim=1)
+    c1 = math.log2(math.e) / T
+    bf = lambda t: t.to(torch.bfloat16).to(DEV).contiguous()
+    N, C, Ns, Cs = bf(n_all), bf(c_all), bf(n_all * c1), bf(c_all * c1)
+    sl = slice(off, off + Bx)
+    N_loc, C_loc, Ns_loc, Cs_loc = N[sl].contiguous(), C[sl].contiguous(), Ns[sl].contiguous(), Cs[sl].contiguous()
+    Nd, Cd, Nsd, Csd = N.double(), C.double(), Ns.double(), Cs.double()
+
+    def sums(scaled, unit):  # sum_j exp(S_ij / T - 1 / T) for every row of `scaled`, 8192 rows at a time
+        return torch.cat([torch.exp(scaled[k:k + 8192] @ unit.t() * LN2 - 1 / T).sum(1) for k in range(0, scaled.shape[0], 8192)])
+
+    row_sum_all, col_sum_all = sums(Nsd, Cd), sums(Csd, Nd)
+    S_r = Nsd[sl] @ Cd.t() * LN2   # this rank's rows of S / T as P1 / P3 see them
+    S_c = Csd[sl] @ Nd.t() * LN2   # this rank's rows of S^T / T as P2 sees them
+    E_r, E_c = torch.exp(S_r - 1 / T), torch.exp(S_c - 1 / T)
+    ar = torch.arange(Bx, device=DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    f32 = dict(dtype=torch.float32, device=DEV)
+    nb = lib.query("tt_simce3_workspace_bytes", Bx, By, F)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    inv_t, gs = 1.0 / T, 0.5 / Bg / T
+    diag, rse, inv_r = torch.empty(Bx, **f32), torch.empty(Bx, **f32), torch.empty(Bx, **f32)
+    cse, inv_c = torch.empty(Bx, **f32), torch.empty(Bx, **f32)
+    dN, dC = torch.empty(Bx, F, **f32), torch.empty(Bx, F, **f32)
+    single = Bx == By
+    # P1 + reduce
+    lib.call("tt_simce3_rows", ptr(Ns_loc), ptr(C), Bx, By, F, inv_t, off, ptr(diag), ptr(ws), nb, s)
+    xs0 = torch.empty(By, F, dtype=torch.bfloat16, device=DEV)
+    lib.call("tt_simce3_rows_finish", ptr(ws), nb, Bx, By, F, inv_t, ptr(rse), ptr(inv_r), ptr(N_loc) if single else 0, gs,
+             ptr(xs0) if single else 0, s)
+    assert rel_err(rse, E_r.sum(1)) < 3e-4
+    assert rel_err(rse, row_sum_all[sl]) < 3e-4
+    assert rel_err(diag, S_r[ar, off + ar]) < 1e-5
+    assert rel_err(inv_r, 1 / E_r.sum(1)) < 3e-4
+    arg, rss = torch.empty(Bx, dtype=torch.int32, device=DEV), torch.empty(Bx, **f32)
+    lib.call("tt_simce3_metrics", ptr(Ns_loc), ptr(C), Bx, By, F, ptr(rss), ptr(arg), ptr(ws), nb, s)
+    assert rel_err(rss, S_r.sum(1)) < 1e-4
+    assert (arg.long() == S_r.argmax(1)).float().mean() > 0.999  # fp32 vs fp64 near-ties only
+    if not single:
+        lib.call("tt_simce3_scale_rows", ptr(N), ptr(row_sum_all.float()), gs, inv_t, By, F, ptr(xs0), s)
+    assert rel_err(xs0.double(), (gs / row_sum_all)[:, None] * Nd) < 1e-2  # bf16 rounding of the scaled operand
+    # P2: transposed gradient pass, row scale deferred
+    lib.call("tt_simce3_grad", ptr(Cs_loc), ptr(N), ptr(xs0), Bx, By, F, inv_t, off, 0, gs, ls, ptr(ws), nb, s)
+    xs1 = torch.empty(By, F, dtype=torch.bfloat16, device=DEV)
+    lib.call("tt_simce3_grad_finish", ptr(ws), nb, Bx, By, F, inv_t, off, ptr(N), 1, gs, ls, Bg, ptr(dC), ptr(cse), ptr(inv_c),
+             ptr(C_loc) if single else 0, ptr(xs1) if single else 0, s)
+    assert rel_err(cse, E_c.sum(1)) < 3e-4 and rel_err(inv_c, 1 / E_c.sum(1)) < 3e-4
+    tgt = torch.full((Bx, By), ls / Bg, dtype=torch.float64, device=DEV)
+    tgt[ar, off + ar] += 1 - ls
+    dS_c = gs * (E_c * ((1 / E_c.sum(1))[:, None] + (1 / row_sum_all)[None, :]) - 2 * tgt)
+    assert rel_err(dC, dS_c @ Nd) < 2e-2
+    del dS_c
+    if not single:
+        lib.call("tt_simce3_scale_rows", ptr(C), ptr(col_sum_all.float()), gs, inv_t, By, F, ptr(xs1), s)
+    # P3: row scale known from P1
+    lib.call("tt_simce3_grad", ptr(Ns_loc), ptr(C), ptr(xs1), Bx, By, F, inv_t, off, ptr(inv_r), gs, ls, ptr(ws), nb, s)
+    lib.call("tt_simce3_grad_finish", ptr(ws), nb, Bx, By, F, inv_t, off, ptr(C), 0, gs, ls, Bg, ptr(dN), 0, 0, 0, 0, s)
+    dS_r = gs * (E_r * ((1 / E_r.sum(1))[:, None] + (1 / col_sum_all)[None, :]) - 2 * tgt)
+    assert rel_err(dN, dS_r @ Cd) < 2e-2
+
+
+@pytest.mark.parametrize("Bx,By,off", [(8192, 8192, 0), (8192, 65536, 16384), (1000, 1000, 0)])
+def test_split_forward_equals_fused_forward_entry_points(Bx, By, off):
+    """tt_simce_forward_sums + tt_simce_forward_metrics write exactly what tt_simce_forward writes (bit for bit), and
+    inv_row / inv_col equal tt_simce_finalize's."""
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200.native import ptr, TT_BF16
+    lib = tt.native.lib()
+    F, T = 64, 1.0
+    x, y = _unit_pair(Bx, By, off, F, 3)
+    xb, yb = x.to(torch.bfloat16).to(DEV), y.to(torch.bfloat16).to(DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    f32 = dict(dtype=torch.float32, device=DEV)
+    mk = lambda: dict(rse=torch.empty(Bx, **f32), cse=torch.empty(By, **f32), rss=torch.empty(Bx, **f32), css=torch.empty(By, **f32),
+                      dg=torch.empty(Bx, **f32), arg=torch.empty(Bx, dtype=torch.int32, device=DEV))
+    a, b = mk(), mk()
+    ws = torch.empty(lib.query("tt_simce_workspace_bytes", max(Bx, By), max(Bx, By), F), dtype=torch.uint8, device=DEV)
+    lib.call("tt_simce_forward", ptr(xb), ptr(yb), Bx, By, F, TT_BF16, 1.0 / T, off, ptr(a["rse"]), ptr(a["cse"]), ptr(a["rss"]),
+             ptr(a["css"]), ptr(a["dg"]), ptr(a["arg"]), ptr(ws), ws.numel(), s)
+    ws2 = torch.empty(lib.query("tt_simce_split_workspace_bytes", Bx, By, F), dtype=torch.uint8, device=DEV)
+    inv_r, inv_c = torch.empty(Bx, **f32), torch.empty(By, **f32)
+    lib.call("tt_simce_forward_sums", ptr(xb), ptr(yb), Bx, By, F, TT_BF16, 1.0 / T, off, ptr(b["rse"]), ptr(b["cse"]), ptr(inv_r),
+             ptr(inv_c), ptr(b["dg"]), ptr(ws2), ws2.numel(), s)
+    lib.call("tt_simce_forward_metrics", ptr(xb), ptr(yb), Bx, By, F, TT_BF16, 1.0 / T, ptr(b["rss"]), ptr(b["css"]), ptr(b["arg"]),
+             ptr(ws2), ws2.numel(), s)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(inv_r, 1.0 / a["rse"]) and torch.equal(inv_c, 1.0 / a["cse"])
+    xd, yd = xb.double().cpu(), yb.double().cpu()
+    E = torch.exp(xd @ yd.t() / T - 1 / T)
+    assert rel_err(a["rse"].cpu(), E.sum(1)) < 2e-4 and rel_err(a["cse"].cpu(), E.sum(0)) < 2e-4
