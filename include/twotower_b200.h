@@ -298,6 +298,47 @@ int tt_l2norm_forward(const float* z, int64_t M, int32_t F, void* e, int32_t out
  * the three-pass logits step (scale = log2(e) / temperature). */
 int tt_l2norm_forward_scaled(const float* z, int64_t M, int32_t F, void* e_bf16, void* e_scaled_bf16, float scale, float* nrm,
                              tt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused tower kernels of the bf16 train step (tower_fused.cu): the MLP of base_tower.py:87-97,142-145 — Linear -> ReLU ->
+ * BatchNorm1d -> Dropout -> Linear -> F.normalize — in two kernels forward and two backward (the BatchNorm batch statistics are the
+ * only grid-wide dependencies). One hidden block, hidden width H1 and final dim F in {64, 128}, dense-projection width H0 a multiple
+ * of 128 (tt_tower_fused_supported); other shapes use the per-stage entry points above.
+ *   tt_linear_forward_bf16_stats  tt_linear_forward_bf16 + colstat f32 [tt_linear_stats_tiles(M)][2][N]: per 128-row tile the column
+ *                                 sums of the stored (bf16-rounded) outputs and of their squares
+ *   tt_tower_tail_forward         statistics (stat_part of n_tiles tiles, or — SyncBN — the all-reduced `sums` f64 [2][H1] over `count`
+ *                                 rows) -> mean / rstd / running stats; y = dropout(bn(h)) (bf16, kept for Linear2's weight gradient);
+ *                                 z = y W2^T + b2; nrm = |z|; e = z / nrm (bf16) and e_scaled = e * e_scale (may be NULL)
+ *   tt_tower_head_backward        dz = (de - e (e.de)) / nrm -> bf16 (dz_bf16, and its per-tile column sums dz_colpart [n_tiles][F]);
+ *                                 dy = dz W2; dyp = dy * keep/(1-p) (bf16); bn_part [n_tiles][2][H1] = column sums of dyp, dyp * xhat
+ *   tt_tower_mid_backward         BatchNorm backward from bn_part (or all-reduced sums) + ReLU mask -> dh (bf16, dh_colpart
+ *                                 [n_tiles][H1]); dc = dh W1 (bf16 [M, LD], all LD columns of the concat buffer) and dc_colpart
+ *                                 [n_tiles][H0] (bias gradient of the dense projection); block 0 writes dgamma / dbeta (scaled by
+ *                                 affine_grad_scale) and dbias2 = sum of dz_colpart
+ *   tt_colpart_reduce_f64 / tt_colpart_reduce2   fold per-tile partials (fp64, tile order) into f64 sums (SyncBN hand-off) / into one
+ *                                 or two fp32 bias gradients */
+int tt_tower_fused_supported(int32_t H0, int32_t H1, int32_t F, int32_t LD);
+int64_t tt_linear_stats_tiles(int64_t M);
+int tt_linear_forward_bf16_stats(const void* A, int64_t lda, const void* W_bf16, const float* bias, void* C, int64_t ldc,
+                                 int32_t out_dtype, int64_t M, int32_t N, int32_t K, int32_t relu, float* colstat,
+                                 tt_stream_t stream);
+int tt_tower_tail_forward(const void* h, int64_t M, int32_t H1, int32_t F, const float* stat_part, int32_t n_tiles, const double* sums,
+                          int64_t count, const float* gamma, const float* beta, float eps, float momentum, float* mean, float* rstd,
+                          float* running_mean, float* running_var, int64_t* num_batches_tracked, float dropout_p,
+                          const uint8_t* mask_in, const tt_adam_hyper* d_hyper, uint32_t rng_stream, void* y, const void* W2_bf16,
+                          const float* bias2, void* e, void* e_scaled, float e_scale, float* nrm, tt_stream_t stream);
+int tt_tower_head_backward(const float* de, const void* e, const float* nrm, int64_t M, int32_t F, int32_t H1, const void* W2_bf16,
+                           void* dz_bf16, float* dz_colpart, const void* h, const float* mean, const float* rstd, float dropout_p,
+                           const uint8_t* mask_in, const tt_adam_hyper* d_hyper, uint32_t rng_stream, void* dyp, float* bn_part,
+                           tt_stream_t stream);
+int tt_tower_mid_backward(const void* dyp, const void* h, int64_t M, int32_t H1, int32_t LD, const void* W1_bf16, const float* bn_part,
+                          int32_t n_tiles, const double* sums, int64_t count, const float* mean, const float* rstd, const float* gamma,
+                          float* dgamma, float* dbeta, float affine_grad_scale, const float* dz_colpart, int32_t F, float* dbias2,
+                          void* dh, float* dh_colpart, void* dc, int32_t H0, float* dc_colpart, tt_stream_t stream);
+int tt_colpart_reduce_f64(const float* part, int32_t n_tiles, int32_t C, double* sums, tt_stream_t stream);
+int tt_colpart_reduce2(const float* part0, int32_t C0, float* out0, const float* part1, int32_t C1, float* out1, int32_t n_tiles,
+                       tt_stream_t stream);
+
 int tt_l2norm_backward(const float* de, const void* e, int32_t e_dtype, const float* nrm, int64_t M, int32_t F,
                        float* dz, tt_stream_t stream);
 
@@ -380,8 +421,9 @@ int tt_simce_backward(const void* X, const void* Y, int64_t Bx, int64_t By, int3
                       tt_stream_t stream);
 /* Test hook: make the tcgen05 (bf16) sim-CE kernels stage operands with the generic-proxy loader instead of TMA. */
 int tt_debug_simce_force_manual_loads(int32_t on);
-/* Profiling knobs for the tcgen05 kernels (results become meaningless): 2 = no TMEM loads, 8 = no TMA after the ring
- * fill, 16 = no MMAs (barrier skeleton only). */
+/* A/B knob of the three-pass logits kernels (results stay correct): by default every fourth exp2 of a chunk runs as a degree-4
+ * polynomial on the FMA pipe (the passes are bound by the 16/clk/SM MUFU pipe; scripts/microbench/mufu2.cu). bit 0 = all exp2 on
+ * the MUFU pipe in the forward pass (P1), bit 1 = in the gradient passes (P2 / P3). Process-wide, not stream-ordered. */
 int tt_debug_simce_knobs(int32_t bits);
 /* Profiling: CTA 0 of the next metric-pass forward kernels writes clock64 stamps into an i64[3*2048] device buffer
  * ([mma | epilogue | loader][tile*4 + event]); pass NULL to switch it off. */

@@ -31,6 +31,8 @@ struct GemmTcParams {
   int out_bf16;
   const float* bias;
   int relu;
+  float* colstat;         // optional [gridDim.x][2][N]: per row tile, column sums of the STORED values and of their squares
+                          // (BatchNorm statistics of the layer output, taken where the tile is still on chip)
   // EPI_PARTIAL_T: part[(split * N + n) * M + m]
   float* part;
 };
@@ -148,14 +150,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       const int64_t nb = n0 + c32 * 32;
       if (p.epi == EPI_STORE) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
         if (m < p.M) {
-          float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[j]);
             if (p.bias && nb + j < p.N) x += __ldg(p.bias + nb + j);
             if (p.relu) x = fmaxf(x, 0.f);
             v[j] = x;
+          }
+          if (p.colstat) {  // what the consumer will read: the bf16-rounded value
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (p.out_bf16) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
           }
           if (nb + 32 <= p.N) {
             if (p.out_bf16) {
@@ -179,6 +187,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               else reinterpret_cast<float*>(p.C)[m * p.ldc + nb + j] = v[j];
             }
           }
+        }
+        if (p.colstat) {
+          // column sums over the tile's 128 rows through shared memory (the operand ring is free: every MMA has retired):
+          // red[row][33] <- v; 4 x 32 partial sums; fixed order -> deterministic. Rows past M hold zeros.
+          float* red = reinterpret_cast<float*>(base);
+          float* red2 = red + 128 * 33;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) red[r_in * 33 + j] = v[j];
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          {
+            const int col = r_in & 31, q = r_in >> 5;
+            float s1 = 0.f, s2 = 0.f;
+            for (int r = q * 32; r < q * 32 + 32; ++r) {
+              const float x = red[r * 33 + col];
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+            red2[q * 32 + col] = s1;
+            red2[128 + q * 32 + col] = s2;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (r_in < 64) {
+            const int which = r_in >> 5, col = r_in & 31;
+            const float* src = red2 + which * 128 + col;
+            const float t = (src[0] + src[32]) + (src[64] + src[96]);
+            if (nb + col < p.N) p.colstat[((int64_t)blockIdx.x * 2 + which) * p.N + nb + col] = t;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       } else {  // transposed fp32 partial: consecutive threads (m) -> consecutive addresses
         if (m < p.M) {
@@ -338,8 +374,9 @@ int tt_cast_bf16_multi(const float* src0, void* dst0, int64_t n0, const float* s
   return TT_OK;
 }
 
-int tt_linear_forward_bf16(const void* A, int64_t lda, const void* W_bf16, const float* bias, void* C, int64_t ldc,
-                           int32_t out_dtype, int64_t M, int32_t N, int32_t K, int32_t relu, tt_stream_t stream) {
+static int linear_forward_bf16_impl(const void* A, int64_t lda, const void* W_bf16, const float* bias, void* C, int64_t ldc,
+                                    int32_t out_dtype, int64_t M, int32_t N, int32_t K, int32_t relu, float* colstat,
+                                    tt_stream_t stream) {
   TT_CHECK_ARG(A && W_bf16 && C && M > 0 && N > 0 && K > 0 && lda >= K && ldc >= N, "tt_linear_forward_bf16: bad arguments");
   TT_CHECK_ARG(aligned_ok(A, lda) && aligned_ok(W_bf16, K), "tt_linear_forward_bf16: operands need 16-byte alignment and ld %% 8 == 0");
   TT_CHECK_ARG(out_dtype == TT_F32 || out_dtype == TT_BF16, "tt_linear_forward_bf16: bad out dtype");
@@ -348,13 +385,27 @@ int tt_linear_forward_bf16(const void* A, int64_t lda, const void* W_bf16, const
   GemmTcParams p = {};
   p.M = M; p.N = N; p.R = K; p.tn = N > 64 ? 128 : 64; p.a_mn = 0; p.b_mn = 0;
   p.stages_per_split = ceil_div(K, GT_BK); p.epi = EPI_STORE; p.C = C; p.ldc = ldc; p.out_bf16 = out_dtype == TT_BF16;
-  p.bias = bias; p.relu = relu;
+  p.bias = bias; p.relu = relu; p.colstat = colstat;
   CUtensorMap ma, mb;
   if (!make_map_bf16(&ma, A, M, K, lda, 64, 128) || !make_map_bf16(&mb, W_bf16, N, K, K, 64, p.tn)) {
     set_error("tt_linear_forward_bf16: cuTensorMapEncodeTiled failed");
     return TT_ERR_CUDA;
   }
   return launch_gemm(ma, mb, p, 1, (cudaStream_t)stream);
+}
+
+int tt_linear_forward_bf16(const void* A, int64_t lda, const void* W_bf16, const float* bias, void* C, int64_t ldc,
+                           int32_t out_dtype, int64_t M, int32_t N, int32_t K, int32_t relu, tt_stream_t stream) {
+  return linear_forward_bf16_impl(A, lda, W_bf16, bias, C, ldc, out_dtype, M, N, K, relu, nullptr, stream);
+}
+
+int64_t tt_linear_stats_tiles(int64_t M) { return (M + 127) / 128; }
+
+int tt_linear_forward_bf16_stats(const void* A, int64_t lda, const void* W_bf16, const float* bias, void* C, int64_t ldc,
+                                 int32_t out_dtype, int64_t M, int32_t N, int32_t K, int32_t relu, float* colstat,
+                                 tt_stream_t stream) {
+  TT_CHECK_ARG(colstat, "tt_linear_forward_bf16_stats: colstat is NULL");
+  return linear_forward_bf16_impl(A, lda, W_bf16, bias, C, ldc, out_dtype, M, N, K, relu, colstat, stream);
 }
 
 int tt_linear_dgrad_bf16(const void* dY, int64_t ldy, const void* W_bf16, void* dX, int64_t ldx, int32_t out_dtype, int64_t M,

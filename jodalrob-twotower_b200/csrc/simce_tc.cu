@@ -57,6 +57,7 @@ struct TcParams {
   int n_xbuf;            // X row-block buffers (1 or 2)
   int n_dbuf;            // backward: [E.Y | E.Ys] accumulators in TMEM
   int n_sbuf;            // S buffers in TMEM: 3 forward; backward 2 (F = 64) or 1 (F = 128), see the TMEM map in the kernel
+  int poly;              // pre-scaled passes: 1 = every fourth exp2 runs as a polynomial on the FMA pipe (tt_debug_simce_knobs)
   long long* dbg_ts;     // optional timeline buffer (block 0): [4 roles][512 tiles][4 events] clock64 stamps, see scripts/time_simce.py
   // forward outputs: partials per (chunk, row)
   float* row_e;
@@ -120,6 +121,13 @@ constexpr int TC_POLY_EVERY = 0;
 __device__ __forceinline__ float tc_exp2(float x, int j) {
   return (TC_POLY_EVERY > 0 && (j % (TC_POLY_EVERY > 0 ? TC_POLY_EVERY : 1)) == TC_POLY_EVERY - 1) ? ex2_poly(x) : ex2f(x);
 }
+// Pre-scaled passes (no FFMA, no shift): the epilogue is bound by the MUFU pipe alone (16 ex2/clk/SM: 1024 cycles per 128x128
+// tile), with issue slots to spare. scripts/microbench/mufu2.cu: MUFU alone 15.9 exps/clk/SM, the degree-4 polynomial alone
+// 12.0, three MUFU + one polynomial 20.4 — so every fourth exponential of a chunk goes to the FMA pipe when POLY is set.
+template <bool POLY>
+__device__ __forceinline__ float tc_exp2p(float x, int j) {
+  return (POLY && (j & 3) == 3) ? ex2_poly(x) : ex2f(x);
+}
 constexpr int TC_CW = 16;  // columns per TMEM load / epilogue chunk: half of a warp's 32-column slice
 
 // The epilogue is issue-bound, not just MUFU-bound (four warps per scheduler): every instruction per logit counts.
@@ -130,7 +138,7 @@ constexpr int TC_CW = 16;  // columns per TMEM load / epilogue chunk: half of a 
 // PRE: the X operand was pre-scaled by c1 = log2(e) / T when it was written (tt_l2norm_forward_scaled), so the accumulator is the
 // exponent itself: no FFMA per logit, and E = exp2(s) is unshifted (|s| <= 57.8 at the smallest temperature: no overflow in
 // fp32 / bf16 even summed over 2^16 columns).
-template <bool GENERIC, bool PRE>
+template <bool GENERIC, bool PRE, bool POLY>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase, int By, float c1, float c0, int dcol, float (&acc)[4],
                                           float& best, int32_t& best_cb, float& dval, bool& have_diag) {
   float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -140,7 +148,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
     if (GENERIC) {
       const int col = cbase + j;
       if (col < By) {
-        acc[j & 3] += PRE ? ex2f(raw) : tc_exp2(fmaf(raw, c1, c0), j);
+        acc[j & 3] += PRE ? tc_exp2p<POLY>(raw, j) : tc_exp2(fmaf(raw, c1, c0), j);
         m4[j & 3] = fmaxf(m4[j & 3], raw);
         if (col == dcol) {
           dval = raw;
@@ -148,7 +156,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
         }
       }
     } else {
-      acc[j & 3] += PRE ? ex2f(raw) : tc_exp2(fmaf(raw, c1, c0), j);
+      acc[j & 3] += PRE ? tc_exp2p<POLY>(raw, j) : tc_exp2(fmaf(raw, c1, c0), j);
       m4[j & 3] = fmaxf(m4[j & 3], raw);
     }
   }
@@ -165,13 +173,14 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[TC_CW], int cbase,
 // / diagonal corrections added by tc_dx_reduce_kernel:
 //   dX_i = ix_i (E Y)_i + (E Ys)_i - t_off sum_j Y_j - (t_diag - t_off) Y_dcol(i).
 // Ragged tiles need no masks: rows / columns past the edge are zero-filled operands (they contribute nothing, or are not stored).
-template <bool PRE, bool SUMS>
+template <bool PRE, bool SUMS, bool POLY>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], float c1, float c0, uint32_t p_taddr, float (&acc)[4]) {
   uint32_t w[TC_CW / 2];
 #pragma unroll
   for (int u = 0; u < TC_CW / 2; ++u) {
-    const float e0 = PRE ? ex2f(__uint_as_float(r[2 * u])) : tc_exp2(fmaf(__uint_as_float(r[2 * u]), c1, c0), 2 * u);
-    const float e1 = PRE ? ex2f(__uint_as_float(r[2 * u + 1])) : tc_exp2(fmaf(__uint_as_float(r[2 * u + 1]), c1, c0), 2 * u + 1);
+    const float e0 = PRE ? tc_exp2p<POLY>(__uint_as_float(r[2 * u]), 2 * u) : tc_exp2(fmaf(__uint_as_float(r[2 * u]), c1, c0), 2 * u);
+    const float e1 = PRE ? tc_exp2p<POLY>(__uint_as_float(r[2 * u + 1]), 2 * u + 1)
+                         : tc_exp2(fmaf(__uint_as_float(r[2 * u + 1]), c1, c0), 2 * u + 1);
     if (SUMS) {  // this row's sum of E rides along (one FADD per logit): the transposed gradient pass IS the column-statistics pass
       acc[(2 * u) & 3] += e0;
       acc[(2 * u + 1) & 3] += e1;
@@ -416,6 +425,7 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t t_base = tmem + ((uint32_t)(quarter * 32) << 16) + slice * 32;  // this thread's lanes / columns of S buffer 0
     const int By = (int)p.By;
     const float c1 = p.c1, c0 = p.c0;
+    const bool poly = p.poly != 0;
     const int t_part = (By & (TCN - 1)) ? p.n_col_tiles - 1 : -1;  // the ragged last column tile, if any
     uint32_t p_iter = 0, e_iter = 0;
     // backward: the accumulator of an item is read out one tile into the NEXT item, so the epilogue never idles while the last
@@ -523,10 +533,12 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 1] = clock64();
         // ... while the first is processed
         if (!BWD) {
-          if (generic) fwd_chunk<true, PRE>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
-          else fwd_chunk<false, PRE>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          if (generic) fwd_chunk<true, PRE, false>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          else if (PRE && poly) fwd_chunk<false, PRE, true>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          else fwd_chunk<false, PRE, false>(rA, cb, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
         } else {
-          bwd_chunk<PRE, SUMS>(rA, c1, c0, p_taddr, acc);
+          if (PRE && poly) bwd_chunk<PRE, SUMS, true>(rA, c1, c0, p_taddr, acc);
+          else bwd_chunk<PRE, SUMS, false>(rA, c1, c0, p_taddr, acc);
         }
         if (stamp) p.dbg_ts[1 * 2048 + e_iter * 4 + 2] = clock64();
         tmem_ld_wait_dep(rB);
@@ -540,10 +552,12 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           tmem_ld16(t_base + s_nxt * TCN, rA);
         }
         if (!BWD) {
-          if (generic) fwd_chunk<true, PRE>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
-          else fwd_chunk<false, PRE>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          if (generic) fwd_chunk<true, PRE, false>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          else if (PRE && poly) fwd_chunk<false, PRE, true>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
+          else fwd_chunk<false, PRE, false>(rB, cb + TC_CW, By, c1, c0, dcol, acc, best, best_cb, dval, have_diag);
         } else {
-          bwd_chunk<PRE, SUMS>(rB, c1, c0, p_taddr + TC_CW / 2, acc);
+          if (PRE && poly) bwd_chunk<PRE, SUMS, true>(rB, c1, c0, p_taddr + TC_CW / 2, acc);
+          else bwd_chunk<PRE, SUMS, false>(rB, c1, c0, p_taddr + TC_CW / 2, acc);
           if (SUMS && t == t_part) {
             // columns past By are zero-filled operands: their logit is exactly 0, E exactly 1 (PRE: exp2(0)); they add nothing to
             // the MMA (zero rows of Y) but one each to the sum — take them out again (exact in fp32)
@@ -869,6 +883,7 @@ int64_t simce_tc_workspace_bytes(int64_t Bx, int64_t By, int F) {
 }
 
 static int g_tc_force_manual = 0;
+static int g_tc_poly_fwd = 1, g_tc_poly_bwd = 1;  // tt_debug_simce_knobs: bit 0 / bit 1 switch the polynomial share OFF
 static long long* g_tc_dbg_ts = nullptr;
 
 // rows statistics of S = X Y^T (bf16 inputs).  want_metrics: also max/argmax/diag.
@@ -894,6 +909,7 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   tc_buffers(F, false, p.n_stages, p.n_xbuf);
   p.n_dbuf = 1;
   p.n_sbuf = TC_SBUF;
+  p.poly = pre ? g_tc_poly_fwd : 0;
   CUtensorMap mx, my;
   p.use_tma = (!g_tc_force_manual && make_map(&mx, X, Bx, F) && make_map(&my, Y, By, F)) ? 1 : 0;
   if (!p.use_tma) { memset(&mx, 0, sizeof(mx)); memset(&my, 0, sizeof(my)); }
@@ -1129,6 +1145,7 @@ int simce_tc_grad_pre(const void* Xs, const void* Y, const void* Ys, int64_t Bx,
   p.gscale = gscale * expf(-inv_temp);  // E is unshifted here, the public reciprocals belong to the shifted sums
   p.dx_part = w.dx_part;
   p.row_e = w.row_e;
+  p.poly = g_tc_poly_bwd;
   p.dbg_ts = g_tc_dbg_ts;
   tc_buffers(F, true, p.n_stages, p.n_xbuf);
   p.n_dbuf = 1;
@@ -1182,7 +1199,10 @@ int simce_tc_scale_rows(const void* Y_unit, const float* sumexp, float gscale, f
 }
 
 void simce_tc_set_force_manual(int v) { g_tc_force_manual = v; }
-void simce_tc_set_debug(int v) { (void)v; }  // profiling knobs were removed from the hot loops; kept for ABI stability
+void simce_tc_set_debug(int v) {  // A/B knob of the pre-scaled passes: bit 0 = no polynomial share forward, bit 1 = backward
+  g_tc_poly_fwd = (v & 1) ? 0 : 1;
+  g_tc_poly_bwd = (v & 2) ? 0 : 1;
+}
 void simce_tc_set_timeline(long long* buf) { g_tc_dbg_ts = buf; }
 
 }  // namespace tt

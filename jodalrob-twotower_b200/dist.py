@@ -396,6 +396,11 @@ class DistributedEngine(TwoTowerEngine):
             self.comm_t[tower].all_reduce(sums[:n])
         return local_count * self.world
 
+    def bn_sync(self, part: torch.Tensor, n_tiles: int, n: int, local_count: int, tower: int, sums: torch.Tensor):
+        # fused tower kernels: fold this rank's per-tile partials (fp64, tile order), all-reduce, hand the global sums on
+        self._call("tt_colpart_reduce_f64", ptr(part), n_tiles, n, ptr(sums), self._stream())
+        return self.bn_allreduce(sums, n, local_count, tower), sums
+
     # fused_step is the base engine's: the large-table update starts on the side stream as soon as this rank's concat-buffer
     # gradients exist AND every other rank's do (barrier below) — it pulls them over NVLink — and overlaps the weight gradients;
     # the all-reduce of the dense gradients runs at the end of the step, next to it.

@@ -150,6 +150,12 @@ class TwoTowerEngine:
         self.arena_grad: Optional[torch.Tensor] = None
         self.dense_w16 = torch.zeros(self.layout.total, dtype=torch.bfloat16, device=dev) if dtype == "bf16" else None
         nblk = len(cfg.hidden) - 1
+        # Fused tower kernels (tower_fused.cu): bf16, one hidden block, widths the kernels are instantiated for — else the
+        # per-stage kernels. TT_FUSED_TOWER=0 forces the per-stage path (A/B measurements, tests of both paths).
+        self.fused_tower = bool(
+            dtype == "bf16" and nblk == 1 and os.environ.get("TT_FUSED_TOWER", "1") != "0"
+            and all(self.lib.query("tt_tower_fused_supported", cfg.hidden[0], cfg.hidden[1], cfg.final_dim,
+                                   cfg.hidden[0] + len(cfg.tower(t)[1]) * E) for t in range(2)))
         self.bn_rm = [[torch.zeros(h, device=dev) for h in cfg.hidden[1:]] for _ in range(2)]
         self.bn_rv = [[torch.ones(h, device=dev) for h in cfg.hidden[1:]] for _ in range(2)]
         self.bn_nbt = [[torch.zeros((), dtype=torch.int64, device=dev) for _ in range(nblk)] for _ in range(2)]
@@ -332,6 +338,15 @@ class TwoTowerEngine:
                 max_wg = max(max_wg, q(wgq, B, h, width))
                 width = h
             max_wg = max(max_wg, q(wgq, B, cfg.final_dim, width))
+        if self.fused_tower:
+            nt = int(self.lib.query("tt_linear_stats_tiles", B))
+            ws.n_tiles = nt
+            H0_, H1_, F_ = cfg.hidden[0], cfg.hidden[1], cfg.final_dim
+            ws.stat_part = [torch.zeros(nt * 2 * H1_, **f32) for _ in range(2)]
+            ws.bn_part = [torch.zeros(nt * 2 * H1_, **f32) for _ in range(2)]
+            ws.dz_colpart = [torch.zeros(nt * F_, **f32) for _ in range(2)]
+            ws.dh_colpart = [torch.zeros(nt * H1_, **f32) for _ in range(2)]
+            ws.dc_colpart = [torch.zeros(nt * H0_, **f32) for _ in range(2)]
         # one scratch per tower so the two towers may run on different streams
         ws.bn_ws = [torch.empty(max(max_bn, 256), dtype=torch.uint8, device=dev) for _ in range(2)]
         ws.bn_sums = [torch.zeros(2 * max(cfg.hidden[1:] + [1]), dtype=torch.float64, device=dev) for _ in range(2)]
@@ -399,8 +414,9 @@ class TwoTowerEngine:
             self._call("tt_linear_wgrad", ptr(dy), ldy, ptr(x), ldx, ptr(self.dense(wname, "g")), ptr(self.dense(bname, "g")), M, N, K,
                        TT_F32, ptr(wsbuf), wsbuf.numel(), s, n_kernels=4)
         else:
-            self._call("tt_linear_wgrad_bf16", ptr(dy), ldy, ptr(x), ldx, ptr(self.dense(wname, "g")), ptr(self.dense(bname, "g")),
-                       M, N, K, ptr(wsbuf), wsbuf.numel(), s, n_kernels=4)
+            self._call("tt_linear_wgrad_bf16", ptr(dy), ldy, ptr(x), ldx, ptr(self.dense(wname, "g")),
+                       ptr(self.dense(bname, "g")) if bname else 0, M, N, K, ptr(wsbuf), wsbuf.numel(), s,
+                       n_kernels=4 if bname else 2)
 
     def refresh_bf16_weights(self):
         if self.dense_w16 is not None:
@@ -474,6 +490,21 @@ class TwoTowerEngine:
             self.refresh_bf16_weights()
             self.tower_prefix(t, ws, dense)
             self.profile_tag = name
+        if self.fused_tower and train:
+            # two kernels: [Linear1 + ReLU + per-tile column statistics] -> [BN finalize/apply + dropout -> Linear2 + bias -> L2 norm]
+            h, F = cfg.hidden[1], cfg.final_dim
+            self._call("tt_linear_forward_bf16_stats", ptr(ws.c[t]), ld, ptr(self._w16(pre + "mlp.0.weight")), ptr(self.dense(pre + "mlp.0.bias")),
+                       ptr(ws.h[t][0]), h, native.TT_BF16, B, h, ld, 1, ptr(ws.stat_part[t]), s)
+            count, sums = self.bn_sync(ws.stat_part[t], ws.n_tiles, 2 * h, B, t, ws.bn_sums[t])
+            p = cfg.dropout
+            mask = masks[0] if (masks is not None and p > 0) else None
+            es = ws.es[t] if getattr(ws, "sim3_ws", None) is not None else None
+            self._call("tt_tower_tail_forward", ptr(ws.h[t][0]), B, h, F, ptr(ws.stat_part[t]), ws.n_tiles, ptr(sums), count,
+                       ptr(self.dense(pre + "mlp.2.weight")), ptr(self.dense(pre + "mlp.2.bias")), BN_EPS, BN_MOMENTUM,
+                       ptr(ws.mean[t][0]), ptr(ws.rstd[t][0]), ptr(self.bn_rm[t][0]), ptr(self.bn_rv[t][0]), ptr(self.bn_nbt[t][0]), p,
+                       ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16, ptr(ws.y[t][0]), ptr(self._w16(pre + "mlp.4.weight")),
+                       ptr(self.dense(pre + "mlp.4.bias")), ptr(ws.e[t]), ptr(es), LOG2E / cfg.temperature, ptr(ws.nrm[t]), s)
+            return ws.e[t]
         x, width, idx = ws.c[t], ld, 0
         for bi, h in enumerate(cfg.hidden[1:]):
             self._lin_fwd(x, width, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", ws.h[t][bi], h, False, B, h, width, 1)
@@ -507,6 +538,12 @@ class TwoTowerEngine:
     def bn_allreduce(self, sums: torch.Tensor, n: int, local_count: int, tower: int = 0) -> int:
         """Single GPU: nothing to do. Distributed engines all-reduce `sums[:n]` and return the global count."""
         return local_count
+
+    def bn_sync(self, part: torch.Tensor, n_tiles: int, n: int, local_count: int, tower: int, sums: torch.Tensor):
+        """Fused tower kernels: per-tile column partials `part` [n_tiles][n] of this rank's rows. Single GPU: the consumer folds
+        them itself -> (count, None). Distributed engines fold them into `sums` (f64 [n]), all-reduce, and return (global count,
+        sums)."""
+        return local_count, None
 
     def loss_forward(self, ws: _Ws):
         cfg, B, s = self.cfg, ws.B, self._stream()
@@ -689,39 +726,60 @@ class TwoTowerEngine:
         train = ws.train
         nblk = len(cfg.hidden) - 1
         widths = [ld] + list(cfg.hidden[1:])
-        self._call("tt_l2norm_backward", ptr(ws.de[t]), ptr(ws.e[t]), self.emb_tt, ptr(ws.nrm[t]), B, F, ptr(ws.dz[t]), s)
-        idx = 4 * nblk
-        xlast = ws.y[t][nblk - 1] if nblk > 0 else ws.c[t]
-        wl = widths[-1]
-        dz = ws.dz[t]
-        if self.act != TT_F32:
-            self._call("tt_cast_bf16", ptr(ws.dz[t]), ptr(ws.dz16[t]), B * F, s)
-            dz = ws.dz16[t]
-        # The chain of data gradients runs first, top to bottom: it is the critical path (at its end the large-table update can
-        # start). Every layer's dY stays in its own buffer, so the weight gradients are formed afterwards, off that path.
-        wgrads = [(dz, F, xlast, wl, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", F, wl)]
-        dx = ws.dy[t][nblk - 1] if nblk > 0 else ws.dc[t]
-        self._lin_dgrad(dz, F, pre + f"mlp.{idx}.weight", dx, wl, B, F, wl)
-        for bi in range(nblk - 1, -1, -1):
-            h = cfg.hidden[1 + bi]
-            idx = 4 * bi
-            p = cfg.dropout if train else 0.0
-            mask = ws.masks[t][bi] if (ws.masks is not None and p > 0) else None
-            mean = ws.mean[t][bi] if train else self.bn_rm[t][bi]
-            gamma = self.dense(pre + f"mlp.{idx + 2}.weight")
-            self._call("tt_bn_backward_reduce", ptr(ws.dy[t][bi]), h, ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean),
-                       ptr(ws.rstd[t][bi]), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.bn_sums[t]),
-                       ptr(ws.bn_ws[t]), ws.bn_ws[t].numel(), s, n_kernels=2)
-            count = self.bn_allreduce(ws.bn_sums[t], 2 * h, B, t)
-            self._call("tt_bn_backward_apply", ptr(ws.dy[t][bi]), h, ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean),
-                       ptr(ws.rstd[t][bi]), ptr(gamma), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.bn_sums[t]),
-                       count, 1 if train else 0, ptr(self.dense(pre + f"mlp.{idx + 2}.weight", "g")),
-                       ptr(self.dense(pre + f"mlp.{idx + 2}.bias", "g")), self.bn_affine_grad_scale, ptr(ws.dh[t][bi]), h, s)
-            xin = ws.y[t][bi - 1] if bi > 0 else ws.c[t]
-            win = widths[bi]
-            dxin = ws.dy[t][bi - 1] if bi > 0 else ws.dc[t]
-            self._lin_dgrad(ws.dh[t][bi], h, pre + f"mlp.{idx}.weight", dxin, win, B, h, win)
-            wgrads.append((ws.dh[t][bi], h, xin, win, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", h, win))
+        fused = self.fused_tower and train
+        bias_of = (lambda n_: None) if fused else (lambda n_: n_)  # fused kernels leave bias gradients as per-tile partials
+        if fused:
+            # two kernels: [L2-norm backward -> dgrad Linear2 -> dropout mask -> BN-backward sums] -> [BN backward + ReLU mask ->
+            # dgrad Linear1 over all columns of the concat buffer + bias-gradient partials]
+            h = cfg.hidden[1]
+            p = cfg.dropout
+            mask = ws.masks[t][0] if (ws.masks is not None and p > 0) else None
+            self._call("tt_tower_head_backward", ptr(ws.de[t]), ptr(ws.e[t]), ptr(ws.nrm[t]), B, F, h, ptr(self._w16(pre + "mlp.4.weight")),
+                       ptr(ws.dz16[t]), ptr(ws.dz_colpart[t]), ptr(ws.h[t][0]), ptr(ws.mean[t][0]), ptr(ws.rstd[t][0]), p, ptr(mask),
+                       ptr(self.hyper), self.rng_stream_base + t * 16, ptr(ws.dy[t][0]), ptr(ws.bn_part[t]), s)
+            count, sums = self.bn_sync(ws.bn_part[t], ws.n_tiles, 2 * h, B, t, ws.bn_sums[t])
+            self._call("tt_tower_mid_backward", ptr(ws.dy[t][0]), ptr(ws.h[t][0]), B, h, ld, ptr(self._w16(pre + "mlp.0.weight")),
+                       ptr(ws.bn_part[t]), ws.n_tiles, ptr(sums), count, ptr(ws.mean[t][0]), ptr(ws.rstd[t][0]),
+                       ptr(self.dense(pre + "mlp.2.weight")), ptr(self.dense(pre + "mlp.2.weight", "g")),
+                       ptr(self.dense(pre + "mlp.2.bias", "g")), self.bn_affine_grad_scale, ptr(ws.dz_colpart[t]), F,
+                       ptr(self.dense(pre + "mlp.4.bias", "g")), ptr(ws.dh[t][0]), ptr(ws.dh_colpart[t]), ptr(ws.dc[t]), H0,
+                       ptr(ws.dc_colpart[t]), s)
+            wgrads = [(ws.dz16[t], F, ws.y[t][0], h, pre + "mlp.4.weight", None, F, h),
+                      (ws.dh[t][0], h, ws.c[t], ld, pre + "mlp.0.weight", None, h, ld)]
+        else:
+            self._call("tt_l2norm_backward", ptr(ws.de[t]), ptr(ws.e[t]), self.emb_tt, ptr(ws.nrm[t]), B, F, ptr(ws.dz[t]), s)
+            idx = 4 * nblk
+            xlast = ws.y[t][nblk - 1] if nblk > 0 else ws.c[t]
+            wl = widths[-1]
+            dz = ws.dz[t]
+            if self.act != TT_F32:
+                self._call("tt_cast_bf16", ptr(ws.dz[t]), ptr(ws.dz16[t]), B * F, s)
+                dz = ws.dz16[t]
+            # The chain of data gradients runs first, top to bottom: it is the critical path (at its end the large-table update can
+            # start). Every layer's dY stays in its own buffer, so the weight gradients are formed afterwards, off that path.
+            wgrads = [(dz, F, xlast, wl, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", F, wl)]
+            dx = ws.dy[t][nblk - 1] if nblk > 0 else ws.dc[t]
+            self._lin_dgrad(dz, F, pre + f"mlp.{idx}.weight", dx, wl, B, F, wl)
+            for bi in range(nblk - 1, -1, -1):
+                h = cfg.hidden[1 + bi]
+                idx = 4 * bi
+                p = cfg.dropout if train else 0.0
+                mask = ws.masks[t][bi] if (ws.masks is not None and p > 0) else None
+                mean = ws.mean[t][bi] if train else self.bn_rm[t][bi]
+                gamma = self.dense(pre + f"mlp.{idx + 2}.weight")
+                self._call("tt_bn_backward_reduce", ptr(ws.dy[t][bi]), h, ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean),
+                           ptr(ws.rstd[t][bi]), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.bn_sums[t]),
+                           ptr(ws.bn_ws[t]), ws.bn_ws[t].numel(), s, n_kernels=2)
+                count = self.bn_allreduce(ws.bn_sums[t], 2 * h, B, t)
+                self._call("tt_bn_backward_apply", ptr(ws.dy[t][bi]), h, ptr(ws.h[t][bi]), h, B, h, self.act, ptr(mean),
+                           ptr(ws.rstd[t][bi]), ptr(gamma), p, ptr(mask), ptr(self.hyper), self.rng_stream_base + t * 16 + bi, ptr(ws.bn_sums[t]),
+                           count, 1 if train else 0, ptr(self.dense(pre + f"mlp.{idx + 2}.weight", "g")),
+                           ptr(self.dense(pre + f"mlp.{idx + 2}.bias", "g")), self.bn_affine_grad_scale, ptr(ws.dh[t][bi]), h, s)
+                xin = ws.y[t][bi - 1] if bi > 0 else ws.c[t]
+                win = widths[bi]
+                dxin = ws.dy[t][bi - 1] if bi > 0 else ws.dc[t]
+                self._lin_dgrad(ws.dh[t][bi], h, pre + f"mlp.{idx}.weight", dxin, win, B, h, win)
+                wgrads.append((ws.dh[t][bi], h, xin, win, pre + f"mlp.{idx}.weight", pre + f"mlp.{idx}.bias", h, win))
         self._mark_dc_ready(t, ws)
         cur = torch.cuda.current_stream(self.device)
         fan = self.two_streams and self.profile is None
@@ -744,7 +802,8 @@ class TwoTowerEngine:
             dense_in = ws.inputs[t]
             if dense_in.dtype != torch.float32:
                 dense_in = dense_in.float()
-        wgrads.append((ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", H0, dense_dim))
+        wgrads.append((ws.dc[t], ld, dense_in, dense_dim, pre + "dense_projection.weight", bias_of(pre + "dense_projection.bias"), H0,
+                       dense_dim))
         # every dY exists now; the layers' weight gradients are independent chains of four small kernels: each gets a helper
         # stream of its own (own scratch each; the README-default tower has three), join at the end
         for i, (dy_, ldy_, x_, ldx_, wn_, bn_, n_, k_) in enumerate(wgrads):
@@ -757,6 +816,19 @@ class TwoTowerEngine:
                 used.add(lane - 1)
                 with torch.cuda.stream(st):
                     self._lin_wgrad(dy_, ldy_, x_, ldx_, wn_, bn_, B, n_, k_, ws.wg_ws[t][lane])
+        if fused:  # the bias gradients of Linear1 and of the dense projection: one fold of the per-tile partials
+            def bias_fold():
+                self._call("tt_colpart_reduce2", ptr(ws.dh_colpart[t]), cfg.hidden[1], ptr(self.dense(pre + "mlp.0.bias", "g")),
+                           ptr(ws.dc_colpart[t]), H0, ptr(self.dense(pre + "dense_projection.bias", "g")), ws.n_tiles, self._stream())
+            if fan:  # behind the small-table reduction on its helper stream (or alone there)
+                st = self._wg_streams[t][3]
+                if 3 not in used:
+                    st.wait_event(ws.dc_ready[t])
+                    used.add(3)
+                with torch.cuda.stream(st):
+                    bias_fold()
+            else:
+                bias_fold()
         for j in sorted(used):
             ev = torch.cuda.Event()
             ev.record(self._wg_streams[t][j])
