@@ -421,9 +421,9 @@ int tt_simce_backward(const void* X, const void* Y, int64_t Bx, int64_t By, int3
                       tt_stream_t stream);
 /* Test hook: make the tcgen05 (bf16) sim-CE kernels stage operands with the generic-proxy loader instead of TMA. */
 int tt_debug_simce_force_manual_loads(int32_t on);
-/* A/B knob of the three-pass logits kernels (results stay correct): by default every fourth exp2 of a chunk runs as a degree-4
- * polynomial on the FMA pipe (the passes are bound by the 16/clk/SM MUFU pipe; scripts/microbench/mufu2.cu). bit 0 = all exp2 on
- * the MUFU pipe in the forward pass (P1), bit 1 = in the gradient passes (P2 / P3). Process-wide, not stream-ordered. */
+/* A/B knob of the three-pass logits kernels (results stay correct): in the gradient passes (P2 / P3) every fourth exp2 of a chunk
+ * runs as a degree-4 polynomial on the FMA pipe (the MUFU pipe does 16 ex2/clk/SM; scripts/microbench/mufu2.cu). bit 0 = also in
+ * the statistics pass P1 (measured slower: off by default), bit 1 = not in P2 / P3. Process-wide, not stream-ordered. */
 int tt_debug_simce_knobs(int32_t bits);
 /* Profiling: CTA 0 of the next metric-pass forward kernels writes clock64 stamps into an i64[3*2048] device buffer
  * ([mma | epilogue | loader][tile*4 + event]); pass NULL to switch it off. */

@@ -88,6 +88,43 @@ __device__ __forceinline__ void tile_colsum_bf16(const unsigned char* tile, int 
   bar128();
 }
 
+
+// Fold per-tile partials part[t][C] (fp32, C % 4 == 0, C <= 512) over n_tiles tiles into out[C] (fp64, shared memory) with all 128
+// elementwise threads: thread -> one float4 column group and every (128 / groups)-th tile, eight independent 16-byte loads in
+// flight, then the tile subsets are added in a fixed order — deterministic, and one L2 round trip instead of n_tiles of them.
+// scratch: 512 doubles of shared memory. Ends with a barrier (out is valid for every thread).
+__device__ __forceinline__ void fold_partials(const float* __restrict__ part, int n_tiles, int C, double* out, double* scratch, int tid) {
+  const int groups = C >> 2;
+  const int n_sub = 128 / groups > 0 ? 128 / groups : 1;
+  if (tid < groups * n_sub) {
+    const int g = tid % groups, q = tid / groups;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int t = q;
+    for (; t + 7 * n_sub < n_tiles; t += 8 * n_sub) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(part + (int64_t)(t + u * n_sub) * C) + g);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a0 += (double)v[u].x; a1 += (double)v[u].y; a2 += (double)v[u].z; a3 += (double)v[u].w;
+      }
+    }
+    for (; t < n_tiles; t += n_sub) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part + (int64_t)t * C) + g);
+      a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+    }
+    double* dst = scratch + (q * groups + g) * 4;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+  }
+  bar128();
+  for (int c = tid; c < C; c += 128) {
+    double t = 0.0;
+    for (int q = 0; q < n_sub; ++q) t += scratch[q * C + c];
+    out[c] = t;
+  }
+  bar128();
+}
+
 // ============================================================================================== forward tail
 struct TailFwdParams {
   const __nv_bfloat16* H;  // [M, H1] ReLU(Linear1) as stored by the producing GEMM
@@ -124,7 +161,8 @@ tower_tail_fwd_kernel(const __grid_constant__ CUtensorMap map_w2, const TailFwdP
   const int NA = p.H1 >> 6;                 // K atoms
   unsigned char* sA = base;                 // NA x 16 KB
   unsigned char* sB = sA + NA * ATOM_BYTES; // NA x (F x 128 B)
-  float* sc = reinterpret_cast<float*>(sB + NA * p.F * 128);
+  double* s_sum = reinterpret_cast<double*>(sB + NA * p.F * 128);  // [2 * H1] folded statistics, then 512 doubles of scratch
+  float* sc = reinterpret_cast<float*>(s_sum + 2 * p.H1 + 512);
   float* sh = sc + p.H1;
   FusedSmem* sb = reinterpret_cast<FusedSmem*>(sh + p.H1);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -164,18 +202,24 @@ tower_tail_fwd_kernel(const __grid_constant__ CUtensorMap map_w2, const TailFwdP
     }
     __syncwarp();
   } else {
-    // ---- BatchNorm statistics -> per-column scale / shift (every CTA folds the partials itself: 2 * n_tiles loads per column)
+    // this thread's first eight 16-byte chunks of h are requested before anything else: their latency hides behind the
+    // statistics fold (chunk idx = tid + 128 it: consecutive threads -> consecutive chunks, coalesced)
+    const int cpr = p.H1 >> 3;  // chunks per row == iterations per thread (8 or 16)
+    uint4 hv[8];
+    auto load_h = [&](int it, uint4& v) {
+      const int idx = tid + it * 128;
+      const int r = idx / cpr, c = idx - r * cpr;
+      const int64_t mr = m0 + r;
+      v = make_uint4(0u, 0u, 0u, 0u);
+      if (mr < p.M) v = __ldg(reinterpret_cast<const uint4*>(p.H + mr * p.H1) + c);
+    };
+#pragma unroll
+    for (int u = 0; u < 8; ++u) load_h(u, hv[u]);
+    // ---- BatchNorm statistics -> per-column scale / shift (every CTA folds the per-tile partials itself)
+    if (!p.sums) fold_partials(p.stat_part, p.n_tiles, 2 * p.H1, s_sum, s_sum + 2 * p.H1, tid);
     for (int n = tid; n < p.H1; n += 128) {
-      double s0 = 0.0, s1 = 0.0;
-      if (p.sums) {
-        s0 = p.sums[n];
-        s1 = p.sums[p.H1 + n];
-      } else {
-        for (int t = 0; t < p.n_tiles; ++t) {
-          s0 += (double)p.stat_part[((int64_t)t * 2 + 0) * p.H1 + n];
-          s1 += (double)p.stat_part[((int64_t)t * 2 + 1) * p.H1 + n];
-        }
-      }
+      const double s0 = p.sums ? p.sums[n] : s_sum[n];
+      const double s1 = p.sums ? p.sums[p.H1 + n] : s_sum[p.H1 + n];
       const double mu = s0 / (double)p.count;
       double var = s1 / (double)p.count - mu * mu;  // biased
       if (var < 0.0) var = 0.0;
@@ -196,23 +240,29 @@ tower_tail_fwd_kernel(const __grid_constant__ CUtensorMap map_w2, const TailFwdP
     if (blockIdx.x == 0 && tid == 0 && p.nbt) *p.nbt += 1;
     bar128();
     // ---- y = dropout(bn(h)) -> bf16 -> HBM (for the weight gradient) and the swizzled A operand
-    const int cpr = p.H1 >> 3;
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    for (int idx = tid; idx < TF_ROWS * cpr; idx += 128) {
-      const int r = idx / cpr, c = idx - r * cpr;
-      const int64_t m = m0 + r;
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (m < p.M) {
-        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(p.H + m * p.H1) + c);
-        float f[8], k[8];
-        unpack8(hv, f);
-        keep8(p.mask_in, p.hyp, p.rng_stream, m * p.H1 + c * 8, p.p_drop, inv_keep, k);
+    for (int base_it = 0; base_it < cpr; base_it += 8) {
+      if (base_it > 0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) f[u] = fmaf(f[u], sc[c * 8 + u], sh[c * 8 + u]) * k[u];
-        o = pack8(f);
-        *(reinterpret_cast<uint4*>(p.Y + m * p.H1) + c) = o;
+        for (int u = 0; u < 8; ++u) load_h(base_it + u, hv[u]);
       }
-      *reinterpret_cast<uint4*>(sA + swz_off(r, c)) = o;
+#pragma unroll
+      for (int u8 = 0; u8 < 8; ++u8) {
+        const int idx = tid + (base_it + u8) * 128;
+        const int r = idx / cpr, c = idx - r * cpr;
+        const int64_t mr = m0 + r;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (mr < p.M) {
+          float f[8], k[8];
+          unpack8(hv[u8], f);
+          keep8(p.mask_in, p.hyp, p.rng_stream, mr * p.H1 + c * 8, p.p_drop, inv_keep, k);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[u] = fmaf(f[u], sc[c * 8 + u], sh[c * 8 + u]) * k[u];
+          o = pack8(f);
+          *(reinterpret_cast<uint4*>(p.Y + mr * p.H1) + c) = o;
+        }
+        *reinterpret_cast<uint4*>(sA + swz_off(r, c)) = o;
+      }
     }
     fence_proxy_async();
     mbar_arrive(&sb->a_full);
@@ -333,35 +383,48 @@ tower_head_bwd_kernel(const __grid_constant__ CUtensorMap map_w2, const HeadBwdP
       s_mean[n] = p.mean[n];
       s_rstd[n] = p.rstd[n];
     }
-    // ---- dz = (de - e (e . de)) / |z|, thread == row: two passes over the row (dot, then dz) in 8-element chunks
-    const int64_t m = m0 + tid;
-    const int cpr = p.F >> 3;
-    float dot = 0.f, inv = 0.f;
-    if (m < p.M) {
-      for (int c = 0; c < cpr; ++c) {
-        float e[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.E + m * p.F) + c), e);
-        const float4 d0 = __ldg(reinterpret_cast<const float4*>(p.DE + m * p.F) + 2 * c);
-        const float4 d1 = __ldg(reinterpret_cast<const float4*>(p.DE + m * p.F) + 2 * c + 1);
-        dot = fmaf(e[0], d0.x, dot); dot = fmaf(e[1], d0.y, dot); dot = fmaf(e[2], d0.z, dot); dot = fmaf(e[3], d0.w, dot);
-        dot = fmaf(e[4], d1.x, dot); dot = fmaf(e[5], d1.y, dot); dot = fmaf(e[6], d1.z, dot); dot = fmaf(e[7], d1.w, dot);
-      }
-      inv = 1.f / p.nrm[m];
-    }
-    for (int c = 0; c < cpr; ++c) {
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (m < p.M) {
-        float e[8], dz[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.E + m * p.F) + c), e);
-        const float4 d0 = __ldg(reinterpret_cast<const float4*>(p.DE + m * p.F) + 2 * c);
-        const float4 d1 = __ldg(reinterpret_cast<const float4*>(p.DE + m * p.F) + 2 * c + 1);
-        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    // ---- dz = (de - e (e . de)) / |z|: F / 8 lanes per row (one 16-byte chunk of e, two of de each: coalesced), the row dot
+    // through F / 8-lane shuffles; warp w owns rows 32 w .. 32 w + 31 of the tile
+    const int64_t m = m0 + tid;  // the epilogue's row of this thread
+    {
+      const int lpr = p.F >> 3;                 // lanes per row: 8 or 16
+      const int rpi = 32 / lpr;                 // rows per warp iteration: 4 or 2
+      const int lane = tid & 31, c = lane % lpr;
+      for (int base_it = 0; base_it < 32 / rpi; base_it += 8) {
+        uint4 ev[8];
+        float4 dv0[8], dv1[8];
+        float invs[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) dz[u] = (d[u] - e[u] * dot) * inv;
-        o = pack8(dz);
-        *(reinterpret_cast<uint4*>(p.DZ16 + m * p.F) + c) = o;
+        for (int u = 0; u < 8; ++u) {  // all loads of eight iterations first
+          const int64_t mr = m0 + warp * 32 + (base_it + u) * rpi + lane / lpr;
+          ev[u] = make_uint4(0u, 0u, 0u, 0u);
+          dv0[u] = dv1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          invs[u] = 0.f;
+          if (mr < p.M) {
+            ev[u] = __ldg(reinterpret_cast<const uint4*>(p.E + mr * p.F) + c);
+            dv0[u] = __ldg(reinterpret_cast<const float4*>(p.DE + mr * p.F) + 2 * c);
+            dv1[u] = __ldg(reinterpret_cast<const float4*>(p.DE + mr * p.F) + 2 * c + 1);
+            invs[u] = 1.f / __ldg(p.nrm + mr);
+          }
+        }
+#pragma unroll
+        for (int u8 = 0; u8 < 8; ++u8) {
+          const int r = warp * 32 + (base_it + u8) * rpi + lane / lpr;
+          const int64_t mr = m0 + r;
+          float e[8], dot = 0.f;
+          unpack8(ev[u8], e);
+          const float d[8] = {dv0[u8].x, dv0[u8].y, dv0[u8].z, dv0[u8].w, dv1[u8].x, dv1[u8].y, dv1[u8].z, dv1[u8].w};
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dot = fmaf(e[u], d[u], dot);
+          for (int o = lpr >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);  // same value on the row's lanes
+          float dz[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dz[u] = (d[u] - e[u] * dot) * invs[u8];
+          const uint4 o = pack8(dz);  // rows past M: zeros
+          if (mr < p.M) *(reinterpret_cast<uint4*>(p.DZ16 + mr * p.F) + c) = o;
+          *reinterpret_cast<uint4*>(sA + swz_off(r, c)) = o;
+        }
       }
-      *reinterpret_cast<uint4*>(sA + swz_off(tid, c)) = o;
     }
     fence_proxy_async();
     mbar_arrive(&sb->a_full);
@@ -436,7 +499,7 @@ tower_head_bwd_kernel(const __grid_constant__ CUtensorMap map_w2, const HeadBwdP
 
 // ============================================================================================== backward middle
 constexpr int MID_WSTAGES = 3;  // weight-tile ring
-constexpr int MID_ABUF = 4;     // accumulator buffers in TMEM (4 x 128 columns)
+constexpr int MID_ABUF = 2;     // accumulator buffers in TMEM (2 x 128 columns: two CTAs fit one SM's 512 columns)
 
 struct MidBwdParams {
   const __nv_bfloat16* DYP;  // [M, H1]
@@ -476,13 +539,19 @@ tower_mid_bwd_kernel(const __grid_constant__ CUtensorMap map_w1, const MidBwdPar
   unsigned char* sA = base;                        // NA x 16 KB: dh, K-major
   unsigned char* sW = sA + NA * ATOM_BYTES;        // MID_WSTAGES weight tiles
   unsigned char* sStage = sW + MID_WSTAGES * wtile_bytes;  // 4 warps x [32 rows x 256 B] output staging
-  float* s_col = reinterpret_cast<float*>(sStage + 4 * 8192);  // mu, rs, g, a0, a1: 5 x H1
+  double* s_sum = reinterpret_cast<double*>(sStage + 4 * 8192);  // [2 * H1] folded sums, then 512 doubles of scratch
+  float* s_col = reinterpret_cast<float*>(s_sum + 2 * p.H1 + 512);  // mu, rs, g, a0, a1: 5 x H1
   float* red = s_col + 5 * p.H1;                   // 4 x 128 floats
   MidSmem* sb = reinterpret_cast<MidSmem*>(red + 512);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tid = threadIdx.x;
   const int64_t m0 = (int64_t)blockIdx.x * TF_ROWS;
-  const int n_out = (p.LD + 127) / 128;
+  // blockIdx.y = column group: the 128-column output tiles [t_begin, t_end) of this CTA (every group recomputes the cheap dh
+  // tile; group 0 stores it). More CTAs than row tiles: the epilogue — the bulk of the kernel — spreads over the machine.
+  const int n_out_all = (p.LD + 127) / 128;
+  const int t_begin = (int)((long long)blockIdx.y * n_out_all / gridDim.y);
+  const int t_end = (int)((long long)(blockIdx.y + 1) * n_out_all / gridDim.y);
+  const bool lead = blockIdx.y == 0;
   if (tid == 0) {
     mbar_init(&sb->a_full, 128);
     for (int i = 0; i < MID_WSTAGES; ++i) {
@@ -495,7 +564,7 @@ tower_mid_bwd_kernel(const __grid_constant__ CUtensorMap map_w1, const MidBwdPar
     }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(&sb->tmem_base, 512);
+  if (warp == 4) tmem_alloc(&sb->tmem_base, MID_ABUF * 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -505,7 +574,7 @@ tower_mid_bwd_kernel(const __grid_constant__ CUtensorMap map_w1, const MidBwdPar
     // ---- weight tiles: W1[:, k0 : k0 + 128] as two MN-major blocks of [H1 rows x 64 columns] (out-of-range columns read as zero)
     int st = 0;
     uint32_t ph = 0;
-    for (int t = 0; t < n_out; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(&sb->w_empty[st], ph ^ 1);
       if (elect_one_sync()) {
         unsigned char* dst = sW + st * wtile_bytes;
@@ -527,7 +596,7 @@ tower_mid_bwd_kernel(const __grid_constant__ CUtensorMap map_w1, const MidBwdPar
     tc_fence_after();
     int st = 0, ab = 0;
     uint32_t ph = 0, aph = 0;
-    for (int t = 0; t < n_out; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(&sb->w_full[st], ph);
       mbar_wait(&sb->acc_empty[ab], aph ^ 1);
       tc_fence_after();
@@ -556,67 +625,80 @@ tower_mid_bwd_kernel(const __grid_constant__ CUtensorMap map_w1, const MidBwdPar
     float* s_a0 = s_col + 3 * p.H1;
     float* s_a1 = s_col + 4 * p.H1;
     // ---- BatchNorm-backward sums -> per-column coefficients; block 0 publishes the affine and bias gradients
-    for (int n = tid; n < p.H1; n += 128) {
-      double S0 = 0.0, S1 = 0.0;
-      if (p.sums) {
-        S0 = p.sums[n];
-        S1 = p.sums[p.H1 + n];
-      } else {
-        for (int t = 0; t < p.n_tiles; ++t) {
-          S0 += (double)p.bn_part[((int64_t)t * 2 + 0) * p.H1 + n];
-          S1 += (double)p.bn_part[((int64_t)t * 2 + 1) * p.H1 + n];
-        }
+    const int cpr = p.H1 >> 3;
+    uint4 hv[8], dv[8];
+    auto load_hd = [&](int it, uint4& vh, uint4& vd) {
+      const int idx = tid + it * 128;
+      const int r = idx / cpr, c = idx - r * cpr;
+      const int64_t mr = m0 + r;
+      vh = vd = make_uint4(0u, 0u, 0u, 0u);
+      if (mr < p.M) {
+        vh = __ldg(reinterpret_cast<const uint4*>(p.H + mr * p.H1) + c);
+        vd = __ldg(reinterpret_cast<const uint4*>(p.DYP + mr * p.H1) + c);
       }
+    };
+#pragma unroll
+    for (int u = 0; u < 8; ++u) load_hd(u, hv[u], dv[u]);  // in flight underneath the folds below
+    if (blockIdx.x == 0 && lead && p.dbias2) {  // bias gradient of Linear2: fold of the head kernel's per-tile column sums of dz
+      fold_partials(p.dz_colpart, p.n_tiles, p.F, s_sum, s_sum + 2 * p.H1, tid);
+      for (int f = tid; f < p.F; f += 128) p.dbias2[f] = (float)s_sum[f];
+      bar128();
+    }
+    if (!p.sums) fold_partials(p.bn_part, p.n_tiles, 2 * p.H1, s_sum, s_sum + 2 * p.H1, tid);
+    for (int n = tid; n < p.H1; n += 128) {
+      const double S0 = p.sums ? p.sums[n] : s_sum[n];
+      const double S1 = p.sums ? p.sums[p.H1 + n] : s_sum[p.H1 + n];
       const float rs = p.rstd[n];
       s_mu[n] = p.mean[n];
       s_rs[n] = rs;
       s_g[n] = rs * p.gamma[n];
       s_a0[n] = (float)S0 * (1.f / (float)p.count);
       s_a1[n] = (float)S1 * (1.f / (float)p.count);
-      if (blockIdx.x == 0) {
+      if (blockIdx.x == 0 && lead) {
         if (p.dbeta) p.dbeta[n] = p.affine_scale * (float)S0;
         if (p.dgamma) p.dgamma[n] = p.affine_scale * (float)S1;
       }
     }
-    if (blockIdx.x == 0 && p.dbias2)
-      for (int f = tid; f < p.F; f += 128) {
-        double s = 0.0;
-        for (int t = 0; t < p.n_tiles; ++t) s += (double)p.dz_colpart[(int64_t)t * p.F + f];
-        p.dbias2[f] = (float)s;
-      }
     bar128();
     // ---- dh = relu'(h) rstd gamma (dyp - mean(dyp) - xhat mean(dyp xhat)) -> bf16 -> HBM + swizzled A operand
-    const int cpr = p.H1 >> 3;
-    for (int idx = tid; idx < TF_ROWS * cpr; idx += 128) {
-      const int r = idx / cpr, c = idx - r * cpr;
-      const int64_t m = m0 + r;
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (m < p.M) {
-        float h[8], d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.H + m * p.H1) + c), h);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.DYP + m * p.H1) + c), d);
+    for (int base_it = 0; base_it < cpr; base_it += 8) {
+      if (base_it > 0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int n = c * 8 + u;
-          const float xhat = (h[u] - s_mu[n]) * s_rs[n];
-          const float dh = s_g[n] * (d[u] - s_a0[n] - xhat * s_a1[n]);
-          d[u] = h[u] > 0.f ? dh : 0.f;
-        }
-        o = pack8(d);
-        *(reinterpret_cast<uint4*>(p.DH + m * p.H1) + c) = o;
+        for (int u = 0; u < 8; ++u) load_hd(base_it + u, hv[u], dv[u]);
       }
-      *reinterpret_cast<uint4*>(sA + swz_off(r, c)) = o;
+#pragma unroll
+      for (int u8 = 0; u8 < 8; ++u8) {
+        const int idx = tid + (base_it + u8) * 128;
+        const int r = idx / cpr, c = idx - r * cpr;
+        const int64_t mr = m0 + r;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (mr < p.M) {
+          float h[8], d[8];
+          unpack8(hv[u8], h);
+          unpack8(dv[u8], d);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int n = c * 8 + u;
+            const float xhat = (h[u] - s_mu[n]) * s_rs[n];
+            const float dh = s_g[n] * (d[u] - s_a0[n] - xhat * s_a1[n]);
+            d[u] = h[u] > 0.f ? dh : 0.f;
+          }
+          o = pack8(d);
+          if (lead) *(reinterpret_cast<uint4*>(p.DH + mr * p.H1) + c) = o;
+        }
+        *reinterpret_cast<uint4*>(sA + swz_off(r, c)) = o;
+      }
     }
     fence_proxy_async();
     mbar_arrive(&sb->a_full);
     bar128();
-    tile_colsum_bf16(sA, p.H1, red, p.dh_colpart + (int64_t)blockIdx.x * p.H1, tid);
+    if (lead) tile_colsum_bf16(sA, p.H1, red, p.dh_colpart + (int64_t)blockIdx.x * p.H1, tid);
     // ---- epilogue: per 128-column output tile, TMEM -> bf16 -> per-warp staging (XOR-swizzled 16-byte chunks) -> coalesced rows
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     unsigned char* stg = sStage + warp * 8192;
     int ab = 0;
     uint32_t aph = 0;
-    for (int t = 0; t < n_out; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(&sb->acc_full[ab], aph);
       tc_fence_after();
 #pragma unroll
@@ -671,7 +753,7 @@ tower_mid_bwd_kernel(const __grid_constant__ CUtensorMap map_w1, const MidBwdPar
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, MID_ABUF * 128);
   }
 }
 
@@ -733,7 +815,7 @@ int tt_tower_tail_forward(const void* h, int64_t M, int32_t H1, int32_t F, const
     return TT_ERR_CUDA;
   }
   const int NA = H1 / 64;
-  const size_t smem = 1024 + (size_t)NA * ATOM_BYTES + (size_t)NA * F * 128 + 2 * H1 * 4 + sizeof(FusedSmem) + 64;
+  const size_t smem = 1024 + (size_t)NA * ATOM_BYTES + (size_t)NA * F * 128 + (2 * H1 + 512) * 8 + 2 * H1 * 4 + sizeof(FusedSmem) + 64;
   TT_CUDA(cudaFuncSetAttribute(tower_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tower_tail_fwd_kernel<<<ceil_div(M, TF_ROWS), TF_THREADS, smem, (cudaStream_t)stream>>>(mw, p);
   TT_LAUNCH_CHECK("tower_tail_fwd_kernel");
@@ -782,10 +864,15 @@ int tt_tower_mid_backward(const void* dyp, const void* h, int64_t M, int32_t H1,
     set_error("tt_tower_mid_backward: cuTensorMapEncodeTiled failed");
     return TT_ERR_CUDA;
   }
-  const size_t smem = 1024 + (size_t)(H1 / 64) * ATOM_BYTES + (size_t)MID_WSTAGES * H1 * 256 + 4 * 8192 + 5 * H1 * 4 + 512 * 4 +
-                      sizeof(MidSmem) + 64;
+  const size_t smem = 1024 + (size_t)(H1 / 64) * ATOM_BYTES + (size_t)MID_WSTAGES * H1 * 256 + 4 * 8192 + (2 * H1 + 512) * 8 +
+                      5 * H1 * 4 + 512 * 4 + sizeof(MidSmem) + 64;
   TT_CUDA(cudaFuncSetAttribute(tower_mid_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tower_mid_bwd_kernel<<<ceil_div(M, TF_ROWS), TF_MID_THREADS, smem, (cudaStream_t)stream>>>(mw, p);
+  // column groups: as many as keep roughly two CTAs per SM busy (two fit: ~100 KB of shared memory, 256 TMEM columns each)
+  const int row_tiles = ceil_div(M, TF_ROWS), n_out = (LD + 127) / 128;
+  int groups = (2 * sm_count()) / row_tiles;
+  if (groups < 1) groups = 1;
+  if (groups > n_out) groups = n_out;
+  tower_mid_bwd_kernel<<<dim3(row_tiles, groups), TF_MID_THREADS, smem, (cudaStream_t)stream>>>(mw, p);
   TT_LAUNCH_CHECK("tower_mid_bwd_kernel");
   return TT_OK;
 }
