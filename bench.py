@@ -313,6 +313,11 @@ def algorithmic(tag: str, B: int, schema, world: int = 1) -> dict:
     # not counted); a backward call forms one tower's gradient from logits that were never stored: S again (2 B^2 F) and
     # dX = dS Y (2 B^2 F); the widened [Y|Ys] operand is not counted. `exps` is the number of exp evaluations a call executes
     # (one per logit per pass), the quantity the MUFU pipe bounds.
+    # three-pass step: P1 = S once (2 B Bg F); P2 / P3 = S again + dS Y (4 B Bg F each); one exp per logit per pass
+    if tag.startswith("tt_simce3_rows") and "finish" not in tag or tag.startswith("simce_tc_kernel<0"):
+        return {"flops": 2 * B * Bg * F, "exps": B * Bg}
+    if tag.startswith("tt_simce3_grad") and "finish" not in tag or tag.startswith("simce_tc_kernel<1") or tag.startswith("simce_tc_kernel<2"):
+        return {"flops": 4 * B * Bg * F, "exps": B * Bg}
     if tag.startswith("tt_simce_forward"):
         return {"flops": 2 * B * Bg * F, "exps": 2 * B * Bg}
     if tag.startswith("tt_simce_backward"):
@@ -569,10 +574,36 @@ def run_ours(args):
         for d in kern.values():
             d["ms"] = d["ms"] / n_prof
             d["calls"] = d["calls"] // n_prof
+    # ---- per-kernel device times of the GRAPH REPLAYS themselves (CUPTI through torch.profiler, after the timed region): the
+    # kernels as they run inside the step, concurrency included; every rank replays (the step has cross-rank exchanges)
+    gk = {}
+    n_cupti = 5
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        for i in range(2):
+            run_step(i)
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(n_cupti):
+                run_step(i)
+            torch.cuda.synchronize(dev)
+        for ev in prof.key_averages():
+            if ev.device_time_total > 0 and ev.count > 0:
+                name = ev.key.replace("void ", "").replace("tt::", "")
+                name = name.split("(")[0]
+                d = gk.setdefault(name, {"us_per_step": 0.0, "launches_per_step": 0.0})
+                d["us_per_step"] += ev.device_time_total / n_cupti
+                d["launches_per_step"] += ev.count / n_cupti
+    except Exception as e:  # the line must still come out
+        gk = {"error": {"us_per_step": 0.0, "launches_per_step": 0.0, "what": repr(e)}}
+    barrier()
     if rank != 0:
         _finish(world, dev)
         return
     pk = peaks()
+    graph_kernels = [dict(kernel=k, us_per_step=round(v["us_per_step"], 2), launches_per_step=round(v["launches_per_step"], 2),
+                          us_per_launch=round(v["us_per_step"] / max(v["launches_per_step"], 1e-9), 2))
+                     for k, v in sorted(gk.items(), key=lambda kv: -kv[1]["us_per_step"])]
     table = []
     for tag, d in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
         a = algorithmic(tag, B, schema, world)
@@ -584,36 +615,57 @@ def run_ours(args):
         if "flops" in a:
             row["TFLOPs"] = round(a["flops"] / per_call / 1e12, 2)
         table.append(row)
-    # dominant call among those with an algorithmic figure (eager per-call times of a multi-rank run include peer waits)
-    top = next((r for r in table if algorithmic(r["call"], B, schema, world)), table[0] if table else None)
+    # ---- roofline of the dominant kernel: the logits pass with the largest share of the step (graph-replay kernel time, CUPTI);
+    # the eager CUDA-event bracket of the same C-ABI call is listed next to it
     roofline = None
-    if top is not None:
-        a = algorithmic(top["call"], B, schema, world)
-        per_call_s = kern[top["call"]]["ms"] / max(kern[top["call"]]["calls"], 1) * 1e-3
-        if "flops" in a:
-            ach = a["flops"] / per_call_s / 1e12
-            traffic = None
-            prof = os.path.join(ROOT, "profiles", "r01_ncu_simce_bwd.json" if top["call"].startswith("tt_simce_backward")
-                                else "r01_ncu_simce_fwd.json")
-            if os.path.isfile(prof) and B == 8192 and world == 1:
-                with open(prof) as f:
-                    traffic = json.load(f)["dram_bytes_per_launch"]  # dram read+write of one launch, ncu --set full capture
-            sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
-            mufu_peak = 16 * 148 * sm_hz * 1e6  # ex2.approx per second: 16 / clk / SM (scripts/microbench/mufu.cu)
-            roofline = {"kernel": top["call"] + " (simce_tc_kernel + 2 small kernels per call)", "bound": "tensor", "achieved": ach,
-                        "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic,
-                        "peak_source": pk["source"] + ", burst bf16",
-                        "note": "the kernel is bound by the exp of every logit (MUFU) and by instruction issue, not by the tensor "
-                                "pipe or HBM: see `mufu`",
-                        "mufu": {"achieved_exps_per_s": a["exps"] / per_call_s, "peak_exps_per_s": mufu_peak,
-                                 "frac": a["exps"] / per_call_s / mufu_peak}}
-        elif "bytes" in a:
-            ach = a["bytes"] / per_call_s / 1e9
-            roofline = {"kernel": top["call"], "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}
-        else:
-            roofline = {"kernel": top["call"], "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None,
-                        "traffic": None, "peak_source": pk["source"]}
+    sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+    mufu_peak = 16 * 148 * sm_hz * 1e6  # ex2.approx per second: 16 / clk / SM (scripts/microbench/mufu2.cu)
+    logits = [r for r in graph_kernels if r["kernel"].startswith("simce_tc_kernel")]
+    if logits:
+        top = logits[0]
+        a = algorithmic(top["kernel"], B, schema, world)
+        sec = top["us_per_launch"] * 1e-6
+        ach = a["flops"] / sec / 1e12
+        which = {"simce_tc_kernel<0": "p1", "simce_tc_kernel<2": "p2", "simce_tc_kernel<1": "p3"}.get(top["kernel"][:17], "p2")
+        call = {"p1": "tt_simce3_rows", "p2": "tt_simce3_grad", "p3": "tt_simce3_grad"}[which]
+        ev_ms = [r["ms"] for r in table if r["call"].startswith(call) and "finish" not in r["call"]]
+        traffic = None
+        prof_json = os.path.join(ROOT, "profiles", f"r02_ncu_simce_{which}.json")
+        if os.path.isfile(prof_json) and B == 8192 and world == 1:
+            with open(prof_json) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")  # dram read + write of one launch, ncu --set full capture
+        roofline = {"kernel": top["kernel"] + {"p1": " (P1: row sums of exp)", "p2": " (P2: column sums of exp + company gradient)",
+                                              "p3": " (P3: notice gradient)"}[which],
+                    "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                    "traffic": traffic, "peak_source": pk["source"] + ", burst bf16",
+                    "algorithmic": f"{a['flops'] / 1e9:.2f} GFLOP per launch (B_l x B_g x F logits" +
+                                   (", computed once" if which == "p1" else " recomputed + dS.Y") + f"), {a['exps'] / 1e6:.1f} M exp",
+                    "us_per_launch": top["us_per_launch"], "timing": "CUPTI kernel duration inside the graph replays",
+                    "cuda_event_ms_per_call_eager": ev_ms[:2] or None,
+                    "share_of_step": top["us_per_step"] / (ms / args.steps * 1e3),
+                    "note": "K = F = 64 and one exp per logit: the pass is bound by the MUFU pipe (16 ex2/clk/SM) and the epilogue's issue "
+                            "slots, not by the tensor pipe or HBM — see `mufu` (fraction of the MUFU peak at the sampled SM clock)",
+                    "mufu": {"achieved_exps_per_s": a["exps"] / sec, "peak_exps_per_s": mufu_peak, "frac": a["exps"] / sec / mufu_peak}}
+    # ---- where the step goes, and what global negatives allow when scaling out (weak scaling in B_l: every rank's logits block is
+    # B_l x W B_l, so the three logits passes grow with W while everything else stays constant)
+    logits_us = sum(r["us_per_step"] for r in logits)
+    peer_us = sum(r["us_per_step"] for r in graph_kernels if r["kernel"].startswith("peer_") or "ncclDevKernel" in r["kernel"])
+    scaling_model = {"logits_passes_us": round(logits_us, 1), "peer_exchange_kernels_us": round(peer_us, 1),
+                     "step_us": round(ms / args.steps * 1e3, 1)}
+    n1 = os.path.join(ROOT, "profiles", "r02_bench_n1.json")
+    if os.path.isfile(n1):
+        try:
+            with open(n1) as f:
+                d1 = json.load(f)
+            s1, l1 = d1["ms_per_step"] * 1e3, d1["scaling_model"]["logits_passes_us"]
+            ideal = s1 + (world - 1) * l1
+            scaling_model.update({"n1_step_us": round(s1, 1), "n1_logits_passes_us": round(l1, 1),
+                                  "ideal_step_us_given_global_negatives": round(ideal, 1),
+                                  "ideal_weak_scaling_efficiency": round(s1 / ideal, 3),
+                                  "achieved_over_ideal": round(ideal / (ms / args.steps * 1e3), 3),
+                                  "model": "N=1 step + (W - 1) x N=1 logits passes (profiles/r02_bench_n1.json); exchanges cost nothing in the ideal"})
+        except Exception:
+            pass
     tables = None
     if world == 1 and not args.no_tables:
         del gstep, packed_res, resident
@@ -639,7 +691,10 @@ def run_ours(args):
                               "note": "supplementary: as e2e, but the host waits for step i's result only after launching step i+1"},
             "e2e_device_store": e2e_store,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "tables": tables, "kernels": table, "loss_last": loss_last}
+            "parity": parity, "roofline": roofline, "scaling_model": scaling_model, "cpu_baseline": cpu,
+            "hbm": None if not tables else {k: {kk: round(vv["frac_hbm"], 3) for kk, vv in t.items() if isinstance(vv, dict) and "frac_hbm" in vv}
+                                            for k, t in tables.items()},
+            "tables": tables, "kernels": graph_kernels[:24], "calls": table, "loss_last": loss_last}
     print(json.dumps(line), flush=True)
     _finish(world, dev)
 

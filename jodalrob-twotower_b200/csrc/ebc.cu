@@ -206,7 +206,21 @@ __global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __re
     len = 256 * (*d_n > 0 ? (*d_n + RS_TILE - 1) / RS_TILE : 1);
     per = (len + 1023) / 1024;
   }
-  for (int i = t; i < len; i += 1024) sh[(i / per) * (per | 1) + (i % per)] = data[i];  // odd row pitch: no bank conflicts
+  // element i lives at sh[(i / per) * (per | 1) + i % per] (odd row pitch: no bank conflicts); quotient and remainder are carried
+  // incrementally — two runtime divisions per element made this single-CTA kernel the long pole of the small sorts
+  const int pitch = per | 1, dq = 1024 / per, dr = 1024 % per;
+  {
+    int q = t / per, r = t % per;
+    for (int i = t; i < len; i += 1024) {
+      sh[q * pitch + r] = data[i];
+      q += dq;
+      r += dr;
+      if (r >= per) {
+        r -= per;
+        ++q;
+      }
+    }
+  }
   __syncthreads();
   int32_t* mine = sh + t * (per | 1);
   const int lo = t * per, cnt = lo >= len ? 0 : (lo + per <= len ? per : len - lo);
@@ -214,11 +228,28 @@ __global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __re
   for (int i = 0; i < cnt; ++i) sum += mine[i];
   s_part[t] = sum;
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    int32_t v = (t >= off) ? s_part[t - off] : 0;
+  {  // inclusive scan of the 1024 thread sums: shuffles inside each warp, then the 32 warp totals by warp 0
+    const int lane = t & 31, warp = t >> 5;
+    int32_t x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    __shared__ int32_t s_wtot[32];
+    if (lane == 31) s_wtot[warp] = x;
     __syncthreads();
-    s_part[t] += v;
+    if (warp == 0) {
+      int32_t w = s_wtot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_wtot[lane] = w;
+    }
     __syncthreads();
+    s_part[t] = x + (warp > 0 ? s_wtot[warp - 1] : 0);
   }
   int32_t run = s_part[t] - sum;
   for (int i = 0; i < cnt; ++i) {
@@ -227,7 +258,18 @@ __global__ void __launch_bounds__(1024) scan_exclusive_smem_kernel(int32_t* __re
     run += c;
   }
   __syncthreads();
-  for (int i = t; i < len; i += 1024) data[i] = sh[(i / per) * (per | 1) + (i % per)];
+  {
+    int q = t / per, r = t % per;
+    for (int i = t; i < len; i += 1024) {
+      data[i] = sh[q * pitch + r];
+      q += dq;
+      r += dr;
+      if (r >= per) {
+        r -= per;
+        ++q;
+      }
+    }
+  }
 }
 
 // Large inputs (millions of pairs: the multi-hot configurations): the counter array no longer fits one CTA's shared memory and a

@@ -121,7 +121,9 @@ class TwoTowerEngine:
         # one-kernel update. Measured on B200 at the README-default size: 376 us per step against 361 us unsplit — the extra kernel
         # lands next to the first sim-CE pass, whose persistent CTAs then find SMs occupied — so it is off by default.
         self.split_dense_adam = os.environ.get("TT_SPLIT_ADAM", "0") != "0"
-        self.hyper_on_helper = os.environ.get("TT_HYPER_HELPER", "1") != "0"
+        # TT_HYPER_HELPER=1: optimizer scalars advanced on a helper stream (was a gain with the per-stage tower kernels; with the fused
+        # kernels measured 295.1 us per step against 289.6 us with the plain in-order launch) — off
+        self.hyper_on_helper = os.environ.get("TT_HYPER_HELPER", "0") != "0"
         self.defer_metrics = os.environ.get("TT_DEFER_METRICS", "1") != "0"
         # TT_ONE_CAST=1: bf16 weight mirror + both dense inputs cast in one launch at the start of the step. Measured on B200:
         # identical loss bit for bit, but 361.6 us per step against 356.6 us with the three separate casts (the single launch
@@ -966,10 +968,13 @@ class TwoTowerEngine:
             # both concat-buffer gradients exist and overlaps the first-layer weight gradients and the small-table reductions.
             self.loss_backward(ws)
             dm = getattr(ws, "deferred_metrics", None)
-            if dm is not None:
-                # Only now: the persistent logits kernels need every SM, and small kernels of a side stream launched next to them
-                # were measured to delay their CTAs (369 vs 362 us per step). Behind the backward passes the metrics kernels share
-                # the machine with the towers' small backward kernels instead.
+            # TT_METRICS_LATE=1 launches them behind both towers' data-gradient chains instead: the tower kernels get faster (head
+            # 16.6 -> 12.8 us) but the metrics kernel then sits next to the table update at the end of the step and the join waits
+            # for it: 315.2 us per step against 295.1 us — off
+            late_metrics = dm is not None and os.environ.get("TT_METRICS_LATE", "0") != "0"
+            if dm is not None and not late_metrics:
+                # Behind the logits passes: the persistent logits kernels need every SM, and small kernels of a side stream launched
+                # next to them were measured to delay their CTAs (369 vs 362 us per step).
                 dm()
                 ws.deferred_metrics = None
             self._side.wait_stream(main)
@@ -984,6 +989,14 @@ class TwoTowerEngine:
                 self.tower_backward(0, ws)
             with torch.cuda.stream(self._side):
                 self.tower_backward(1, ws, after_dc=table_update)
+            if late_metrics:
+                # ... and the loss value / metrics kernels only behind BOTH towers' data-gradient chains (they were measured to slow
+                # the fused tower backward kernels by half when launched next to them): they share the machine with the weight
+                # gradients and the table update instead, and are joined at the end of the step.
+                main.wait_event(ws.dc_ready[0])
+                main.wait_event(ws.dc_ready[1])
+                dm()
+                ws.deferred_metrics = None
             main.wait_stream(self._hi0)
             for ev in getattr(ws, "wg_joins", None) or [ws.dc_ready[1]]:
                 main.wait_event(ev)  # the company tower's weight gradients and small-table reductions (helper streams)

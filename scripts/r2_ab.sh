@@ -1,0 +1,13 @@
+mkdir -p gpurun_out
+run() { env "$@" timeout 600 python bench.py --steps 100 --warmup 10 --no-tables --no-cpu-baseline --no-device-store --no-parity 2>/dev/null | python -c "
+import json,sys
+for ln in sys.stdin:
+    if ln.startswith('{'):
+        d=json.loads(ln); print('$*', round(d['ms_per_step']*1e3,1), 'us', round(d['value']/1e6,2), 'M/s')"; }
+run TT_METRICS_LATE=1
+run TT_METRICS_LATE=0
+run TT_METRICS_LATE=0 TT_SPLIT_ADAM=1
+run TT_METRICS_LATE=1 TT_SPLIT_ADAM=1
+run TT_METRICS_LATE=0 TT_HYPER_HELPER=0
+run TT_METRICS_LATE=0 TT_FUSED_TOWER=0
+run TT_METRICS_LATE=0 TT_SIMCE_PASSES=4
