@@ -346,13 +346,14 @@ def run_ours(args):
     torch.manual_seed(0)
     if world > 1:
         from jodalrob_twotower_b200 import dist as ttdist
-        task = ttdist.create_distributed_train_task(nk, ck, schema, MODEL, dev, dtype=args.dtype)
+        task = ttdist.create_distributed_train_task(nk, ck, schema, MODEL, dev, dtype=args.dtype, optimizer_mode=args.optimizer)
     else:
         task = tt.create_two_tower_train_task(
             nk, ck, categorical_embedding_dim=MODEL["emb_dim"], notice_dense_input_dim=MODEL["notice_dense"],
             company_dense_input_dim=MODEL["company_dense"], tower_hidden_dims=MODEL["hidden"], final_embedding_dim=MODEL["final_dim"],
             dropout_rate=MODEL["dropout"], temperature=MODEL["temperature"], device=dev,
-            vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])}, dtype=args.dtype)
+            vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])}, dtype=args.dtype,
+            optimizer_mode=args.optimizer)
     # ---- parity of THIS path (graph replay, this dtype, this world size and its peer-memory exchanges) against the reference
     # port on the concatenated global batch, before anything is timed (checker only; oracle/bench_parity.py)
     parity = None
@@ -681,7 +682,7 @@ def run_ours(args):
                                     else "fp32 everywhere (SIMT)",
                        "workload": f"README-default two-tower train step (emb 32, towers [128,64]->64, 38 tables / 64,141 rows), "
                                    f"B={B} per GPU, in-batch negatives, dropout 0.1, exact dense Adam lr 1e-3 wd 1e-5",
-                       "batch_per_gpu": B, "global_batch": B * world, "optimizer": "dense_exact",
+                       "batch_per_gpu": B, "global_batch": B * world, "optimizer": args.optimizer,
                        "parallelism": f"dp{world}" + (" row-wise sharded tables" if world > 1 else ""),
                        "l2_policy": f"inputs rotate over {N_ROTATE} resident batches ({in_bytes * N_ROTATE / 1e6:.0f} MB > 126 MB L2)",
                        "cuda_graph": bool(use_graph)},
@@ -717,6 +718,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="samples per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--optimizer", default="dense_exact", choices=["dense_exact", "lazy_exact", "sparse"],
+                    help="table update: dense_exact streams every row every step (torch.optim.Adam as the reference runs it); lazy_exact "
+                         "gives the same bits by replaying skipped steps when a row is next touched; sparse is NOT the reference semantics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity pre-check against the reference port")
     ap.add_argument("--parity-batch", type=int, default=1024, help="samples per GPU in the parity pre-check (the port steps the global batch on the CPU)")

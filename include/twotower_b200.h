@@ -72,6 +72,24 @@ typedef struct tt_adam_hyper {
   uint64_t rng_step; /* dropout Philox step counter (== step) */
 } tt_adam_hyper;
 
+/* Lazy exact-replay Adam (device-resident context, built once per engine; kernels take a DEVICE pointer to it).
+ * The reference's optimizer is dense: every embedding row moves every step, touched by the batch or not (g = wd * w;
+ * scripts/train.py:231, nn.Embedding(sparse=False)). Instead of streaming every row every step, a row's (w, m, v) stay as they are
+ * in HBM together with row_last[row] = the optimizer step they are current to; when the row is next looked up or updated, the
+ * steps it sat out are replayed in registers, each with its own (step_size, bc2_sqrt) from the history ring written by
+ * tt_hyper_advance_hist — the same operations in the same order as the dense update, bit for bit. tt_ebc_lazy_flush brings
+ * every row up to date (before parameters are read from outside, and at least every hist_len - 1 steps). beta1 / beta2 / eps /
+ * weight_decay must not change between two flushes. */
+typedef struct tt_lazy_ctx {
+  const float* arena_w; /* [rows, E] the sorted (large) tables */
+  float* arena_m;
+  float* arena_v;
+  int32_t* row_last;    /* [rows] */
+  const float* hist;    /* [hist_len][2]: (step_size_t, bc2_sqrt_t) at index t & (hist_len - 1) */
+  int64_t hist_len;     /* power of two */
+  const tt_adam_hyper* hyper;
+} tt_lazy_ctx;
+
 const char* tt_last_error(void);
 int tt_version(void);
 int tt_device_sm_count(void);
@@ -82,6 +100,9 @@ int tt_device_sm_count(void);
  * warmup_steps <= 0 disables the schedule. */
 int tt_hyper_advance(tt_adam_hyper* d_hyper, float base_lr, int64_t warmup_steps, float beta1, float beta2,
                      float eps, float weight_decay, uint64_t rng_seed, tt_stream_t stream);
+/* ... and records (step_size_t, bc2_sqrt_t) in the lazy-Adam history ring */
+int tt_hyper_advance_hist(tt_adam_hyper* d_hyper, float base_lr, int64_t warmup_steps, float beta1, float beta2, float eps,
+                          float weight_decay, uint64_t rng_seed, float* d_hist, int64_t hist_len, tt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pooled embedding-bag lookup for all K tables of a tower in one launch.
@@ -155,6 +176,22 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
                          int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, const int32_t* d_n,
                          const void* const* grad_table, int64_t n_per_rank, const int32_t* d_colmap0, const int32_t* d_colmap1,
                          tt_stream_t stream);
+/* Lazy exact-replay variants (see tt_lazy_ctx). tt_ebc_forward_mixed_lazy: rows of the sorted tables that are behind are caught up
+ * on the fly, read-only, through step hyper->step + upto_offset (-1 inside a train step, whose own update is still to come; 0 for a
+ * forward outside of one). tt_ebc_backward_adam_lazy: only the rows the batch touched — replay of the steps they sat out, then this
+ * step with its gradient — and row_last = step. Results equal TT_ADAM_DENSE_EXACT bit for bit once flushed. */
+int tt_ebc_forward_mixed_lazy(const float* arena, const int64_t* d_row_base, const int32_t* d_vocab, const int64_t* values, int32_t B,
+                              int32_t K, int32_t E, int32_t layout, void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0,
+                              const int32_t* d_large_rank, int32_t K_large, int64_t row_sub, int32_t* rows_out,
+                              const tt_lazy_ctx* d_lazy, int32_t upto_offset, tt_stream_t stream);
+int tt_ebc_backward_adam_lazy(float* arena_w, float* arena_m, float* arena_v, int64_t total_rows, int32_t E,
+                              const int32_t* sorted_rows, const int32_t* sorted_slots, int64_t n, const int32_t* row_begin,
+                              const int32_t* row_end, const int32_t* row_stamp, const int64_t* d_stamp, const void* grad0, int64_t ld0,
+                              int64_t col0_0, int32_t K0, int64_t n0, const void* grad1, int64_t ld1, int64_t col0_1, int32_t K1,
+                              int64_t n1, int32_t grad_dtype, void* piece_ws, int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper,
+                              const int32_t* d_n, const void* const* grad_table, int64_t n_per_rank, const int32_t* d_colmap0,
+                              const int32_t* d_colmap1, const tt_lazy_ctx* d_lazy, tt_stream_t stream);
+int tt_ebc_lazy_flush(const tt_lazy_ctx* d_lazy, int64_t rows, int32_t E, tt_stream_t stream);
 
 /* Two table classes.  "Large" tables go through the sort-dedup path above.  "Small" tables (a few dozen rows: 24 of the
  * reference's 32 notice keys have <= 25) are hit by every sample, so sorting them is wasted work and sharding them across
@@ -215,10 +252,29 @@ int64_t tt_shard_workspace_bytes(int64_t n_total);
 int tt_shard_select_owned(const int32_t* ids_all, const int32_t* d_block, const int32_t* d_local_base, int64_t n_per_rank,
                           int64_t n0, int32_t K0, int32_t K1, int32_t world, int32_t me, int32_t* rows_out, int32_t* slots_out,
                           int32_t* d_n_owned, void* workspace, int64_t workspace_bytes, tt_stream_t stream);
+/* All-to-all id routing: the SENDER buckets its ids by owner and pushes (local row, global slot) straight into each owner's receive
+ * buffer over NVLink peer memory; the owner packs its W segments. Replaces all-gather + tt_shard_select_owned (whose per-rank work
+ * and traffic grow with W): n * 8 bytes leave a rank instead of W * n * 4 arriving. The packed order (sender-major, slot order
+ * inside) is the order tt_shard_select_owned produces: everything downstream is bit-identical.
+ *   tt_shard_a2a_send     d_recv_rows / d_recv_slots: device arrays of `world` peer pointers to every rank's receive buffers
+ *                         i32 [world][n_per_rank]; d_recv_counts: peer pointers to i32 [world] (segment lengths, index = sender).
+ *                         A cross-rank barrier must separate it from tt_shard_a2a_compact on every rank.
+ *   tt_shard_a2a_compact  this rank's receive buffers -> rows_out / slots_out (compact), *d_n_owned. */
+int64_t tt_shard_a2a_workspace_bytes(int64_t n_per_rank, int32_t world);
+int tt_shard_a2a_send(const int32_t* ids_local, const int32_t* d_block, const int32_t* d_local_base, int64_t n_per_rank, int64_t n0,
+                      int32_t K0, int32_t K1, int32_t world, int32_t me, void* const* d_recv_rows, void* const* d_recv_slots,
+                      void* const* d_recv_counts, void* workspace, int64_t workspace_bytes, tt_stream_t stream);
+int tt_shard_a2a_compact(const int32_t* recv_rows, const int32_t* recv_slots, const int32_t* recv_counts, int32_t world,
+                         int64_t n_per_rank, int32_t* rows_out, int32_t* slots_out, int32_t* d_n_owned, tt_stream_t stream);
 int tt_ebc_push_rows(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
                      int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
                      int64_t ld1, int64_t col0_0, int64_t col0_1, const int32_t* d_colmap0, const int32_t* d_colmap1,
                      int32_t out_dtype, tt_stream_t stream);
+/* ... with the owner-side lazy catch-up of tt_ebc_forward_mixed_lazy */
+int tt_ebc_push_rows_lazy(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
+                          int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
+                          int64_t ld1, int64_t col0_0, int64_t col0_1, const int32_t* d_colmap0, const int32_t* d_colmap1,
+                          int32_t out_dtype, const tt_lazy_ctx* d_lazy, int32_t upto_offset, tt_stream_t stream);
 
 /* Dense-parameter Adam over a flat fp32 buffer (tower Linear/BatchNorm weights), same update rule.
  * Replaces torch.optim.Adam.step for the non-embedding parameters (scripts/train.py:327). */

@@ -5,6 +5,7 @@
 // warp moves 4 rows per instruction and consecutive bags of a sample land contiguously in the
 // tower's concat buffer.  Table metadata (row base, vocab) is staged through shared memory.
 #include "common.cuh"
+#include "adam.cuh"
 
 namespace tt {
 
@@ -29,11 +30,20 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
                   const int32_t* __restrict__ vocab, const int64_t* __restrict__ values, int B, int K, int E,
                   int layout, OutT* __restrict__ out, int64_t out_ld, int64_t out_col0, int32_t* __restrict__ rows_out,
                   int32_t* __restrict__ slots_out, int64_t slot_base, int G, const int32_t* __restrict__ large_rank,
-                  int K_large, int64_t row_sub) {
+                  int K_large, int64_t row_sub, const tt_lazy_ctx* __restrict__ lazy, int upto_off) {
   extern __shared__ unsigned char smem_raw[];
   int64_t* s_base = reinterpret_cast<int64_t*>(smem_raw);
   int32_t* s_vocab = reinterpret_cast<int32_t*>(s_base + K);
   int32_t* s_rank = s_vocab + K;
+  // lazy exact-replay Adam: rows of the sorted (large) tables may be several steps behind; they are caught up on the fly
+  tt_lazy_ctx L = {};
+  tt_adam_hyper lh = {};
+  long long upto = 0;
+  if (lazy) {
+    L = *lazy;
+    lh = *L.hyper;
+    upto = lh.step + upto_off;
+  }
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     s_base[i] = row_base[i];
     s_vocab[i] = vocab[i];
@@ -50,11 +60,13 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
   for (int64_t base = group0; base < n_bags; base += (int64_t)groups_total * UNROLL) {
     int64_t row[UNROLL];
     int bb[UNROLL], kk[UNROLL];
+    long long lag_from[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const int64_t s64 = base + (int64_t)u * groups_total;
       row[u] = -1;
       bb[u] = kk[u] = 0;
+      lag_from[u] = -1;
       if (s64 < n_bags) {
         const int slot = (int)s64;
         const int b = slot / K, k = slot - b * K;
@@ -67,6 +79,10 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
           id = id < 0 ? 0 : (id > hi ? hi : id);  // clamp(id, 0, V_k-1)
           row[u] = s_base[k] + id;
           const int rk = s_rank[k];
+          if (lazy && rk >= 0) {
+            const long long last = L.row_last[row[u] - row_sub];
+            if (last < upto) lag_from[u] = last + 1;
+          }
           if (lane == 0 && rk >= 0) {  // only tables on the sort-dedup path record their (compact) row
             const int64_t o = (int64_t)b * K_out + rk;
             if (rows_out) rows_out[o] = (int32_t)(row[u] - row_sub);
@@ -80,6 +96,16 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
         if (row[u] >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(arena + row[u] * E) + c);
+      if (lazy) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (row[u] >= 0 && lag_from[u] >= 0) {  // read-only catch-up: the update kernel replays again and writes back
+            const int64_t lo = (row[u] - row_sub) * E;
+            float4 mm = *(reinterpret_cast<const float4*>(L.arena_m + lo) + c);
+            float4 vv = *(reinterpret_cast<const float4*>(L.arena_v + lo) + c);
+            lazy_replay_vec4(v[u], mm, vv, lag_from[u], upto, L, lh);
+          }
+      }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
         if (row[u] >= 0) store_vec4<OutT>(out + (int64_t)bb[u] * out_ld + out_col0 + (int64_t)kk[u] * E + 4 * c, v[u]);
@@ -635,22 +661,6 @@ __device__ __forceinline__ float4 row_grad_sum(const GradFetch& gs, int64_t b, i
   return acc;
 }
 
-// torch.optim.Adam single-tensor update, element-wise (op order of torch/optim/adam.py)
-__device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g, const tt_adam_hyper& h) {
-  g = g + h.weight_decay * w;                     // grad.add(param, alpha=weight_decay)
-  m = m + (1.0f - h.beta1) * (g - m);             // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * h.beta2 + (1.0f - h.beta2) * g * g;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
-  const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
-  w = w - h.step_size * (m / denom);              // param.addcdiv_(exp_avg, denom, value=-step_size)
-}
-
-__device__ __forceinline__ void adam_vec4(float4& w, float4& m, float4& v, const float4& g, const tt_adam_hyper& h) {
-  adam_elem(w.x, m.x, v.x, g.x, h);
-  adam_elem(w.y, m.y, v.y, g.y, h);
-  adam_elem(w.z, m.z, v.z, g.z, h);
-  adam_elem(w.w, m.w, v.w, g.w, h);
-}
-
 // one lane group per arena row, every row (dense-exact Adam and/or dense gradient materialisation)
 template <bool DO_ADAM, bool WRITE_GRAD, bool DIRECT>
 __global__ void __launch_bounds__(256, 3)
@@ -739,6 +749,34 @@ ebc_rows_dense_stream_kernel(float* __restrict__ w, float* __restrict__ m, float
   }
 }
 
+// Bring every row up to the current step (before the parameters are read from outside: state_dict / checkpoints, and before the
+// history ring would wrap). One lane group per row; rows that are current cost one 4-byte read.
+__global__ void __launch_bounds__(256)
+ebc_lazy_flush_kernel(const tt_lazy_ctx* __restrict__ lazy, int64_t rows, int E, int G) {
+  const tt_lazy_ctx L = *lazy;
+  const tt_adam_hyper h = *L.hyper;
+  const int lane = threadIdx.x % G;
+  const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
+  const int vec_per_row = E >> 2;
+  float* w = const_cast<float*>(L.arena_w);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; r < rows; r += groups_total) {
+    const long long last = L.row_last[r];
+    if (last >= h.step) continue;
+    for (int c = lane; c < vec_per_row; c += G) {
+      const int64_t off = r * E + 4 * c;
+      float4 wv = *reinterpret_cast<const float4*>(w + off), mv = *reinterpret_cast<const float4*>(L.arena_m + off),
+             vv = *reinterpret_cast<const float4*>(L.arena_v + off);
+      lazy_replay_vec4(wv, mv, vv, last + 1, h.step, L, h);
+      *reinterpret_cast<float4*>(w + off) = wv;
+      *reinterpret_cast<float4*>(L.arena_m + off) = mv;
+      *reinterpret_cast<float4*>(L.arena_v + off) = vv;
+    }
+    __syncwarp(gmask);
+    if (lane == 0) L.row_last[r] = (int32_t)h.step;
+  }
+}
+
 // sparse mode: lane groups walk the sorted entries; only segment heads work. HBM-bound at scale (millions of touched rows, each
 // a random 3 x E*4-byte read-modify-write), so the kernel is built around memory-level parallelism:
 //   * persistent grid-stride CTAs, SP_ROWS entries per lane group and iteration: the w/m/v loads of all of them are issued
@@ -752,9 +790,13 @@ __global__ void __launch_bounds__(256, 3)
 ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int E, int G,
                        const int32_t* __restrict__ srow, const GradFetch gs, int64_t n,
                        const int32_t* __restrict__ d_n, const int32_t* __restrict__ row_end,
-                       const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper) {
+                       const float* __restrict__ pieces, const tt_adam_hyper* __restrict__ d_hyper,
+                       const tt_lazy_ctx* __restrict__ lazy) {
   if (d_n) n = *d_n;
   const tt_adam_hyper h = *d_hyper;
+  tt_lazy_ctx L = {};
+  if (lazy) L = *lazy;
+  const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int lane = threadIdx.x % G;
   const int vec_per_row = E >> 2;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
@@ -762,6 +804,7 @@ ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __re
     int32_t i[SP_ROWS], e[SP_ROWS];  // sorted positions fit 31 bits (tt_ebc_sort_rows checks n)
     int32_t r[SP_ROWS];
     bool head[SP_ROWS];
+    long long last[SP_ROWS];
     float4 wv[SP_ROWS], mv[SP_ROWS], vv[SP_ROWS], g0[SP_ROWS];
 #pragma unroll
     for (int u = 0; u < SP_ROWS; ++u) {
@@ -769,9 +812,11 @@ ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __re
       i[u] = (int32_t)iu;
       head[u] = false;
       r[u] = 0;
+      last[u] = 0;
       if (iu < n) {
         r[u] = __ldg(srow + i[u]);
         head[u] = i[u] == 0 || __ldg(srow + i[u] - 1) != r[u];
+        if (lazy && head[u]) last[u] = L.row_last[r[u]];
       }
     }
 #pragma unroll
@@ -810,11 +855,18 @@ ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __re
             for (int32_t ch = i[u] / SEG_CHUNK; ch <= (e[u] - 1) / SEG_CHUNK; ++ch)
               f4_add(g, *reinterpret_cast<const float4*>(pieces + (((int64_t)ch * 2 + (i[u] <= ch * SEG_CHUNK ? 0 : 1)) * E) + 4 * c));
           }
+          if (lazy) lazy_replay_vec4(wv[u], mv[u], vv[u], last[u] + 1, h.step - 1, L, h);  // the steps this row sat out
           adam_vec4(wv[u], mv[u], vv[u], g, h);
           __stcs(reinterpret_cast<float4*>(w + off), wv[u]);
           __stcs(reinterpret_cast<float4*>(m + off), mv[u]);
           __stcs(reinterpret_cast<float4*>(v + off), vv[u]);
         }
+    }
+    if (lazy) {  // the lanes of a group took the same path (group-uniform control flow) and have all read row_last by now
+      __syncwarp(gmask);
+#pragma unroll
+      for (int u = 0; u < SP_ROWS; ++u)
+        if (head[u] && lane == 0) L.row_last[r[u]] = (int32_t)h.step;
     }
   }
 }
@@ -928,8 +980,9 @@ static int ebc_forward_impl(const float* arena, const int64_t* d_row_base, const
                             const int64_t* bag_offsets, int64_t n_values, int32_t B, int32_t K, int32_t E, int32_t layout,
                             void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0, int32_t* rows_out,
                             int32_t* slots_out, int64_t slot_base, const int32_t* large_rank, int32_t K_large, int64_t row_sub,
-                            tt_stream_t stream) {
+                            tt_stream_t stream, const tt_lazy_ctx* d_lazy = nullptr, int upto_off = 0) {
   TT_CHECK_ARG(arena && d_row_base && d_vocab && values && out, "tt_ebc_forward: NULL pointer");
+  TT_CHECK_ARG(!d_lazy || (bag_offsets == nullptr && large_rank), "tt_ebc_forward: lazy catch-up is implemented for the one-id-per-bag mixed lookup");
   TT_CHECK_ARG(B >= 0 && K > 0 && E > 0 && (E % 4) == 0, "tt_ebc_forward: need K>0, E%%4==0 (B=%d K=%d E=%d)", B, K, E);
   TT_CHECK_ARG(layout == TT_LAYOUT_SAMPLE_MAJOR || layout == TT_LAYOUT_KEY_MAJOR, "tt_ebc_forward: bad layout %d", layout);
   TT_CHECK_ARG(out_dtype == TT_F32 || out_dtype == TT_BF16, "tt_ebc_forward: bad out_dtype %d", out_dtype);
@@ -956,11 +1009,11 @@ static int ebc_forward_impl(const float* arena, const int64_t* d_row_base, const
     if (out_dtype == TT_F32)
       ebc_fwd_l1_kernel<float, UNROLL><<<grid, threads, smem, s>>>(arena, d_row_base, d_vocab, values, B, K, E, layout,
                                                                    (float*)out, out_ld, out_col0, rows_out, slots_out, slot_base, G,
-                                                                   large_rank, K_large, row_sub);
+                                                                   large_rank, K_large, row_sub, d_lazy, upto_off);
     else
       ebc_fwd_l1_kernel<__nv_bfloat16, UNROLL><<<grid, threads, smem, s>>>(
           arena, d_row_base, d_vocab, values, B, K, E, layout, (__nv_bfloat16*)out, out_ld, out_col0, rows_out,
-          slots_out, slot_base, G, large_rank, K_large, row_sub);
+          slots_out, slot_base, G, large_rank, K_large, row_sub, d_lazy, upto_off);
   } else {
     int64_t want = ceil_div(n_bags, groups_per_block);
     int grid = (int)(want < 1 ? 1 : (want > (int64_t)sm_count() * 16 ? (int64_t)sm_count() * 16 : want));
@@ -991,6 +1044,16 @@ int tt_ebc_forward_mixed(const float* arena, const int64_t* d_row_base, const in
   TT_CHECK_ARG(d_large_rank && K_large >= 0 && K_large <= K, "tt_ebc_forward_mixed: bad large-table map");
   return ebc_forward_impl(arena, d_row_base, d_vocab, values, nullptr, (int64_t)B * K, B, K, E, layout, out, out_dtype, out_ld,
                           out_col0, rows_out, nullptr, 0, d_large_rank, K_large, row_sub, stream);
+}
+
+int tt_ebc_forward_mixed_lazy(const float* arena, const int64_t* d_row_base, const int32_t* d_vocab, const int64_t* values, int32_t B,
+                              int32_t K, int32_t E, int32_t layout, void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col0,
+                              const int32_t* d_large_rank, int32_t K_large, int64_t row_sub, int32_t* rows_out,
+                              const tt_lazy_ctx* d_lazy, int32_t upto_offset, tt_stream_t stream) {
+  TT_CHECK_ARG(d_large_rank && K_large >= 0 && K_large <= K && d_lazy && (upto_offset == 0 || upto_offset == -1),
+               "tt_ebc_forward_mixed_lazy: bad arguments");
+  return ebc_forward_impl(arena, d_row_base, d_vocab, values, nullptr, (int64_t)B * K, B, K, E, layout, out, out_dtype, out_ld,
+                          out_col0, rows_out, nullptr, 0, d_large_rank, K_large, row_sub, stream, d_lazy, upto_offset);
 }
 
 int64_t tt_ebc_sort_workspace_bytes(int64_t n, int64_t total_rows) {
@@ -1068,14 +1131,14 @@ int64_t tt_ebc_piece_workspace_bytes(int64_t n, int32_t E) {
   return align_up(chunks * 2 * (int64_t)E * 4, 256) + (n > 0 ? n : 0) * (int64_t)E * 4;
 }
 
-int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* grad_arena, int64_t total_rows,
+static int backward_adam_impl(float* arena_w, float* arena_m, float* arena_v, float* grad_arena, int64_t total_rows,
                          int32_t E, const int32_t* sorted_rows, const int32_t* sorted_slots, int64_t n,
                          const int32_t* row_begin, const int32_t* row_end, const int32_t* row_stamp, int32_t stamp,
                          const int64_t* d_stamp, const void* grad0, int64_t ld0, int64_t col0_0, int32_t K0, int64_t n0, const void* grad1,
                          int64_t ld1, int64_t col0_1, int32_t K1, int64_t n1, int32_t grad_dtype, void* piece_ws,
                          int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, const int32_t* d_n,
                          const void* const* grad_table, int64_t n_per_rank, const int32_t* d_colmap0, const int32_t* d_colmap1,
-                         tt_stream_t stream) {
+                         tt_stream_t stream, const tt_lazy_ctx* d_lazy) {
   const bool do_adam = arena_w != nullptr;
   TT_CHECK_ARG(do_adam || grad_arena, "tt_ebc_backward_adam: nothing to do (arena_w and grad_arena both NULL)");
   TT_CHECK_ARG(!do_adam || (arena_m && arena_v && d_hyper), "tt_ebc_backward_adam: Adam needs m, v and d_hyper");
@@ -1148,7 +1211,7 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
       int64_t want = ceil_div(n, (int64_t)gpb * SP_ROWS);
       const int64_t cap = (int64_t)sm_count() * 12;  // 3 resident CTAs per SM, 4 waves
       (direct ? ebc_rows_sparse_kernel<true> : ebc_rows_sparse_kernel<false>)<<<(int)(want > cap ? cap : want), threads, 0, s>>>(
-          arena_w, arena_m, arena_v, E, G, sorted_rows, gs, n, d_n, row_end, pieces, d_hyper);
+          arena_w, arena_m, arena_v, E, G, sorted_rows, gs, n, d_n, row_end, pieces, d_hyper, d_lazy);
     }
   } else {
     int64_t want = ceil_div(total_rows, gpb);
@@ -1167,6 +1230,43 @@ int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* 
 #undef TT_ROWS_LAUNCH
   }
   TT_LAUNCH_CHECK("ebc_backward_adam");
+  return TT_OK;
+}
+
+int tt_ebc_backward_adam(float* arena_w, float* arena_m, float* arena_v, float* grad_arena, int64_t total_rows,
+                         int32_t E, const int32_t* sorted_rows, const int32_t* sorted_slots, int64_t n,
+                         const int32_t* row_begin, const int32_t* row_end, const int32_t* row_stamp, int32_t stamp,
+                         const int64_t* d_stamp, const void* grad0, int64_t ld0, int64_t col0_0, int32_t K0, int64_t n0, const void* grad1,
+                         int64_t ld1, int64_t col0_1, int32_t K1, int64_t n1, int32_t grad_dtype, void* piece_ws,
+                         int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper, int32_t mode, const int32_t* d_n,
+                         const void* const* grad_table, int64_t n_per_rank, const int32_t* d_colmap0, const int32_t* d_colmap1,
+                         tt_stream_t stream) {
+  return backward_adam_impl(arena_w, arena_m, arena_v, grad_arena, total_rows, E, sorted_rows, sorted_slots, n, row_begin, row_end,
+                            row_stamp, stamp, d_stamp, grad0, ld0, col0_0, K0, n0, grad1, ld1, col0_1, K1, n1, grad_dtype, piece_ws,
+                            piece_ws_bytes, d_hyper, mode, d_n, grad_table, n_per_rank, d_colmap0, d_colmap1, stream, nullptr);
+}
+
+/* TT_ADAM_LAZY_EXACT: the touched rows only, each first caught up over the steps it sat out (lazy_replay_vec4) */
+int tt_ebc_backward_adam_lazy(float* arena_w, float* arena_m, float* arena_v, int64_t total_rows, int32_t E,
+                              const int32_t* sorted_rows, const int32_t* sorted_slots, int64_t n, const int32_t* row_begin,
+                              const int32_t* row_end, const int32_t* row_stamp, const int64_t* d_stamp, const void* grad0, int64_t ld0,
+                              int64_t col0_0, int32_t K0, int64_t n0, const void* grad1, int64_t ld1, int64_t col0_1, int32_t K1,
+                              int64_t n1, int32_t grad_dtype, void* piece_ws, int64_t piece_ws_bytes, const tt_adam_hyper* d_hyper,
+                              const int32_t* d_n, const void* const* grad_table, int64_t n_per_rank, const int32_t* d_colmap0,
+                              const int32_t* d_colmap1, const tt_lazy_ctx* d_lazy, tt_stream_t stream) {
+  TT_CHECK_ARG(d_lazy && arena_w, "tt_ebc_backward_adam_lazy: needs the lazy context and the arena");
+  return backward_adam_impl(arena_w, arena_m, arena_v, nullptr, total_rows, E, sorted_rows, sorted_slots, n, row_begin, row_end,
+                            row_stamp, 0, d_stamp, grad0, ld0, col0_0, K0, n0, grad1, ld1, col0_1, K1, n1, grad_dtype, piece_ws,
+                            piece_ws_bytes, d_hyper, TT_ADAM_SPARSE, d_n, grad_table, n_per_rank, d_colmap0, d_colmap1, stream, d_lazy);
+}
+
+int tt_ebc_lazy_flush(const tt_lazy_ctx* d_lazy, int64_t rows, int32_t E, tt_stream_t stream) {
+  TT_CHECK_ARG(d_lazy && rows > 0 && E > 0 && (E % 4) == 0, "tt_ebc_lazy_flush: bad arguments");
+  const int G = lanes_per_row(E);
+  int64_t want = ceil_div(rows, 256 / G);
+  const int64_t cap = (int64_t)sm_count() * 32;
+  ebc_lazy_flush_kernel<<<(int)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(d_lazy, rows, E, G);
+  TT_LAUNCH_CHECK("ebc_lazy_flush_kernel");
   return TT_OK;
 }
 

@@ -35,7 +35,7 @@ int sm_count() {
 // (torch/optim/adam.py _single_tensor_adam: bias_correction1 = 1 - beta1 ** step, step_size = lr / bc1,
 //  bias_correction2_sqrt = sqrt(1 - beta2 ** step)).
 __global__ void hyper_advance_kernel(tt_adam_hyper* h, float base_lr, long long warmup, float b1, float b2, float eps,
-                                     float wd, unsigned long long seed) {
+                                     float wd, unsigned long long seed, float* hist, long long hist_len) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   long long t = h->step + 1;
   long long s = h->sched_step;
@@ -54,6 +54,10 @@ __global__ void hyper_advance_kernel(tt_adam_hyper* h, float base_lr, long long 
   h->weight_decay = wd;
   h->rng_seed = seed;
   h->rng_step = (unsigned long long)t;
+  if (hist) {  // lazy exact-replay Adam: the per-step scalars a skipped step is replayed with
+    hist[2 * (t & (hist_len - 1))] = h->step_size;
+    hist[2 * (t & (hist_len - 1)) + 1] = h->bc2_sqrt;
+  }
 }
 
 }  // namespace tt
@@ -68,7 +72,18 @@ int tt_hyper_advance(tt_adam_hyper* d_hyper, float base_lr, int64_t warmup_steps
                      float weight_decay, uint64_t rng_seed, tt_stream_t stream) {
   TT_CHECK_ARG(d_hyper != nullptr, "tt_hyper_advance: d_hyper is NULL");
   tt::hyper_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_hyper, base_lr, (long long)warmup_steps, beta1, beta2,
-                                                              eps, weight_decay, (unsigned long long)rng_seed);
+                                                              eps, weight_decay, (unsigned long long)rng_seed, nullptr, 0);
+  TT_LAUNCH_CHECK("hyper_advance_kernel");
+  return TT_OK;
+}
+
+int tt_hyper_advance_hist(tt_adam_hyper* d_hyper, float base_lr, int64_t warmup_steps, float beta1, float beta2, float eps,
+                          float weight_decay, uint64_t rng_seed, float* d_hist, int64_t hist_len, tt_stream_t stream) {
+  TT_CHECK_ARG(d_hyper != nullptr && d_hist != nullptr && hist_len > 0 && (hist_len & (hist_len - 1)) == 0,
+               "tt_hyper_advance_hist: needs a history ring with a power-of-two length");
+  tt::hyper_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_hyper, base_lr, (long long)warmup_steps, beta1, beta2,
+                                                              eps, weight_decay, (unsigned long long)rng_seed, d_hist,
+                                                              (long long)hist_len);
   TT_LAUNCH_CHECK("hyper_advance_kernel");
   return TT_OK;
 }

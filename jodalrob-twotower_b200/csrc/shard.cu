@@ -8,6 +8,7 @@
 // (5) PULLS the pooled-output gradients of its rows from the requesters' buffers inside the segment-sum kernel
 // (ebc.cu, GradSrc::table).  Every buffer has a static size, so the whole step stays CUDA-graph capturable.
 #include "common.cuh"
+#include "adam.cuh"
 
 namespace tt {
 
@@ -118,6 +119,129 @@ route_compact_kernel(RouteMeta m, const int32_t* __restrict__ tile_offsets, int 
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_owned = tile_offsets[n_tiles];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// All-to-all id routing (the sender buckets, the owner only ever sees its own ids). tt_shard_select_owned above has every rank
+// all-gather and scan ALL W * n ids; here each rank
+//   1. counts, per 2048-entry tile of its OWN n ids, how many go to each owner            (a2a_count_kernel)
+//   2. scans the [owner][tile] counts: a bucket's entries keep their slot order              (scan_exclusive_small_kernel)
+//   3. writes (local row, global slot) of every id straight into its owner's receive buffer, segment `sender`, over NVLink
+//      peer memory, plus the segment length                                                  (a2a_push_kernel)
+//   — barrier —
+//   4. the owner packs its W segments (sender-major, slot order inside: exactly the order of the all-gather path, so
+//      everything downstream is bit-identical)                                               (a2a_compact_kernel)
+// Per rank n * 8 bytes leave over NVLink instead of W * n * 4 arriving, and the per-rank work no longer grows with W.
+struct A2aMeta {
+  const int32_t* ids;         // [n] this rank's clamped global ids in slot order
+  const int32_t* block;       // [K0+K1] rows per rank of table k
+  const int32_t* local_base;  // [K0+K1] first local row of table k
+  int64_t n, n0;
+  int K0, K1, me, world;
+};
+
+__device__ __forceinline__ int a2a_route(const A2aMeta& m, int64_t s_, int32_t& local_row) {
+  const int k = s_ < m.n0 ? (int)(s_ % m.K0) : m.K0 + (int)((s_ - m.n0) % m.K1);
+  const int32_t id = m.ids[s_];
+  const int32_t blk = m.block[k];
+  const int32_t owner = id / blk;
+  local_row = m.local_base[k] + id - owner * blk;
+  return owner;
+}
+
+constexpr int A2A_MAX_WORLD = 64;
+
+// counts[(owner * (n_tiles + 1)) + tile]; the extra slot per owner stays 0 and becomes the bucket end after the scan
+__global__ void __launch_bounds__(RT_THREADS) a2a_count_kernel(A2aMeta m, int32_t* __restrict__ counts, int n_tiles) {
+  __shared__ int32_t s_cnt[A2A_MAX_WORLD];
+  if (threadIdx.x < m.world) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t base = (int64_t)blockIdx.x * RT_TILE + (int64_t)warp * (32 * RT_ITEMS);
+#pragma unroll
+  for (int i = 0; i < RT_ITEMS; ++i) {
+    const int64_t g = base + i * 32 + lane;
+    int32_t lr;
+    const int owner = g < m.n ? a2a_route(m, g, lr) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, owner);
+    if (owner >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&s_cnt[owner], __popc(peers));  // integer adds: order-independent
+  }
+  __syncthreads();
+  if (threadIdx.x < m.world) counts[(int64_t)threadIdx.x * (n_tiles + 1) + blockIdx.x] = s_cnt[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x < m.world) counts[(int64_t)threadIdx.x * (n_tiles + 1) + n_tiles] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[(int64_t)m.world * (n_tiles + 1)] = 0;
+}
+
+// offsets = exclusive scan of counts (flattened): offsets[o][t] - offsets[o][0] = position of tile t's first id inside bucket o
+__global__ void __launch_bounds__(RT_THREADS)
+a2a_push_kernel(A2aMeta m, const int32_t* __restrict__ offsets, int n_tiles, int32_t* const* __restrict__ recv_rows,
+                int32_t* const* __restrict__ recv_slots, int32_t* const* __restrict__ recv_counts) {
+  __shared__ int32_t s_warp[RT_THREADS / 32][A2A_MAX_WORLD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (RT_THREADS / 32) * A2A_MAX_WORLD; i += RT_THREADS) (&s_warp[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RT_TILE + (int64_t)warp * (32 * RT_ITEMS);
+  int owner[RT_ITEMS], rank_in_warp[RT_ITEMS];
+  int32_t lr[RT_ITEMS];
+  // stable rank of every id among the ids of the same owner inside this warp's 256-entry chunk: item i of the warp is entries
+  // [32 i, 32 i + 32), so (item, lane) order == slot order
+#pragma unroll
+  for (int i = 0; i < RT_ITEMS; ++i) {
+    const int64_t g = base + i * 32 + lane;
+    owner[i] = g < m.n ? a2a_route(m, g, lr[i]) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, owner[i]);
+    rank_in_warp[i] = 0;
+    if (owner[i] >= 0) {
+      rank_in_warp[i] = s_warp[warp][owner[i]] + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncwarp();
+    if (owner[i] >= 0 && lane == (__ffs(peers) - 1)) s_warp[warp][owner[i]] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RT_ITEMS; ++i) {
+    if (owner[i] < 0) continue;
+    const int o = owner[i];
+    int pos = offsets[(int64_t)o * (n_tiles + 1) + blockIdx.x] - offsets[(int64_t)o * (n_tiles + 1)];
+    for (int w = 0; w < warp; ++w) pos += s_warp[w][o];
+    pos += rank_in_warp[i];
+    const int64_t g = base + i * 32 + lane;
+    const int64_t dst = (int64_t)m.me * m.n + pos;   // my segment of owner o's receive buffer
+    recv_rows[o][dst] = lr[i];
+    recv_slots[o][dst] = (int32_t)((int64_t)m.me * m.n + g);  // global slot
+  }
+  if (blockIdx.x == 0 && threadIdx.x < m.world) {
+    const int o = threadIdx.x;
+    recv_counts[o][m.me] = offsets[(int64_t)o * (n_tiles + 1) + n_tiles] - offsets[(int64_t)o * (n_tiles + 1)];
+  }
+}
+
+// owner side: pack the W received segments (counts[sender] entries each) into rows_c / slots_c, sender-major
+__global__ void __launch_bounds__(256)
+a2a_compact_kernel(const int32_t* __restrict__ recv_rows, const int32_t* __restrict__ recv_slots, const int32_t* __restrict__ counts,
+                   int world, int64_t n, int32_t* __restrict__ rows_c, int32_t* __restrict__ slots_c, int32_t* __restrict__ n_owned) {
+  __shared__ int32_t s_off[A2A_MAX_WORLD + 1];
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int r = 0; r < world; ++r) {
+      s_off[r] = run;
+      run += counts[r];
+    }
+    s_off[world] = run;
+    if (blockIdx.x == 0) *n_owned = run;
+  }
+  __syncthreads();
+  const int64_t total = (int64_t)world * n;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(j / n);
+    const int64_t pos = j - (int64_t)r * n;
+    if (pos < counts[r]) {
+      rows_c[s_off[r] + pos] = recv_rows[j];
+      slots_c[s_off[r] + pos] = recv_slots[j];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024) scan_exclusive_small_kernel(int32_t* __restrict__ data, int64_t len) {
   __shared__ int32_t s_part[1024];
   const int t = threadIdx.x;
@@ -148,8 +272,17 @@ __global__ void __launch_bounds__(256)
 push_rows_kernel(const float* __restrict__ arena, int E, int G, const int32_t* __restrict__ rows_c,
                  const int32_t* __restrict__ slots_c, const int32_t* __restrict__ n_owned, void* const* __restrict__ dst_table,
                  int64_t n_per_rank, int64_t n0, int K0, int K1, int64_t ld0, int64_t ld1, int64_t col0_0, int64_t col0_1,
-                 const int32_t* __restrict__ cmap0, const int32_t* __restrict__ cmap1) {
+                 const int32_t* __restrict__ cmap0, const int32_t* __restrict__ cmap1, const tt_lazy_ctx* __restrict__ lazy,
+                 int upto_off) {
   const int n = *n_owned;
+  tt_lazy_ctx L = {};
+  tt_adam_hyper lh = {};
+  long long upto = 0;
+  if (lazy) {  // lazy exact-replay Adam: the owner catches a row up (read-only) before it sends it
+    L = *lazy;
+    lh = *L.hyper;
+    upto = lh.step + upto_off;
+  }
   const int lane = threadIdx.x % G;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
   const int vec_per_row = E >> 2;
@@ -167,8 +300,18 @@ push_rows_kernel(const float* __restrict__ arena, int E, int G, const int32_t* _
       const int b = (int)(g / K1), k = (int)(g - (int64_t)b * K1);
       dst = reinterpret_cast<OutT*>(dst_table[2 * r + 1]) + (int64_t)b * ld1 + (cmap1 ? (int64_t)cmap1[k] : col0_1 + (int64_t)k * E);
     }
+    long long lag_from = -1;
+    if (lazy) {
+      const long long last = L.row_last[row];
+      if (last < upto) lag_from = last + 1;
+    }
     for (int c = lane; c < vec_per_row; c += G) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(arena + (int64_t)row * E) + c);
+      float4 v = __ldg(reinterpret_cast<const float4*>(arena + (int64_t)row * E) + c);
+      if (lag_from >= 0) {
+        float4 mm = *(reinterpret_cast<const float4*>(L.arena_m + (int64_t)row * E) + c);
+        float4 vv = *(reinterpret_cast<const float4*>(L.arena_v + (int64_t)row * E) + c);
+        lazy_replay_vec4(v, mm, vv, lag_from, upto, L, lh);
+      }
       if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(dst + 4 * c) = v;
       else *reinterpret_cast<uint2*>(dst + 4 * c) = pack_bf16x4(v);
     }
@@ -229,10 +372,48 @@ int tt_shard_select_owned(const int32_t* ids_all, const int32_t* d_block, const 
   return TT_OK;
 }
 
-int tt_ebc_push_rows(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
-                     int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
-                     int64_t ld1, int64_t col0_0, int64_t col0_1, const int32_t* d_colmap0, const int32_t* d_colmap1,
-                     int32_t out_dtype, tt_stream_t stream) {
+int64_t tt_shard_a2a_workspace_bytes(int64_t n_per_rank, int32_t world) {
+  const int64_t tiles = (n_per_rank + RT_TILE - 1) / RT_TILE + 1;
+  return ((int64_t)world * tiles + 2) * 4 + 256;
+}
+
+int tt_shard_a2a_send(const int32_t* ids_local, const int32_t* d_block, const int32_t* d_local_base, int64_t n_per_rank, int64_t n0,
+                      int32_t K0, int32_t K1, int32_t world, int32_t me, void* const* d_recv_rows, void* const* d_recv_slots,
+                      void* const* d_recv_counts, void* workspace, int64_t workspace_bytes, tt_stream_t stream) {
+  TT_CHECK_ARG(ids_local && d_block && d_local_base && d_recv_rows && d_recv_slots && d_recv_counts && workspace, "tt_shard_a2a_send: NULL pointer");
+  TT_CHECK_ARG(world > 0 && world <= A2A_MAX_WORLD && me >= 0 && me < world && n_per_rank > 0 && n0 >= 0 && n0 <= n_per_rank && K0 > 0,
+               "tt_shard_a2a_send: bad sizes");
+  TT_CHECK_ARG(n0 == n_per_rank || K1 > 0, "tt_shard_a2a_send: K1 missing");
+  TT_CHECK_ARG(n_per_rank * world < (1ll << 31), "tt_shard_a2a_send: too many ids for int32 slots");
+  TT_CHECK_ARG(workspace_bytes >= tt_shard_a2a_workspace_bytes(n_per_rank, world), "tt_shard_a2a_send: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  A2aMeta m{ids_local, d_block, d_local_base, n_per_rank, n0, K0, K1 > 0 ? K1 : 1, me, world};
+  const int n_tiles = (int)((n_per_rank + RT_TILE - 1) / RT_TILE);
+  int32_t* counts = (int32_t*)workspace;
+  a2a_count_kernel<<<n_tiles, RT_THREADS, 0, s>>>(m, counts, n_tiles);
+  scan_exclusive_small_kernel<<<1, 1024, 0, s>>>(counts, (int64_t)world * (n_tiles + 1) + 1);
+  a2a_push_kernel<<<n_tiles, RT_THREADS, 0, s>>>(m, counts, n_tiles, (int32_t* const*)d_recv_rows, (int32_t* const*)d_recv_slots,
+                                                 (int32_t* const*)d_recv_counts);
+  TT_LAUNCH_CHECK("shard_a2a_send");
+  return TT_OK;
+}
+
+int tt_shard_a2a_compact(const int32_t* recv_rows, const int32_t* recv_slots, const int32_t* recv_counts, int32_t world,
+                         int64_t n_per_rank, int32_t* rows_out, int32_t* slots_out, int32_t* d_n_owned, tt_stream_t stream) {
+  TT_CHECK_ARG(recv_rows && recv_slots && recv_counts && rows_out && slots_out && d_n_owned && world > 0 && world <= A2A_MAX_WORLD &&
+               n_per_rank > 0, "tt_shard_a2a_compact: bad arguments");
+  int64_t want = ceil_div((int64_t)world * n_per_rank, 256);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  a2a_compact_kernel<<<(int)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(recv_rows, recv_slots, recv_counts, world, n_per_rank,
+                                                                                       rows_out, slots_out, d_n_owned);
+  TT_LAUNCH_CHECK("a2a_compact_kernel");
+  return TT_OK;
+}
+
+static int push_rows_impl(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
+                          int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
+                          int64_t ld1, int64_t col0_0, int64_t col0_1, const int32_t* d_colmap0, const int32_t* d_colmap1,
+                          int32_t out_dtype, tt_stream_t stream, const tt_lazy_ctx* d_lazy, int upto_off) {
   TT_CHECK_ARG(arena && rows && slots && d_n_owned && dst_table && E > 0 && (E % 4) == 0, "tt_ebc_push_rows: bad arguments");
   TT_CHECK_ARG(out_dtype == TT_F32 || out_dtype == TT_BF16, "tt_ebc_push_rows: bad dtype");
   int g = 1;
@@ -243,12 +424,30 @@ int tt_ebc_push_rows(const float* arena, int32_t E, const int32_t* rows, const i
   cudaStream_t s = (cudaStream_t)stream;
   if (out_dtype == TT_F32)
     push_rows_kernel<float><<<grid, 256, 0, s>>>(arena, E, g, rows, slots, d_n_owned, dst_table, n_per_rank, n0, K0, K1 > 0 ? K1 : 1,
-                                                 ld0, ld1, col0_0, col0_1, d_colmap0, d_colmap1);
+                                                 ld0, ld1, col0_0, col0_1, d_colmap0, d_colmap1, d_lazy, upto_off);
   else
     push_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(arena, E, g, rows, slots, d_n_owned, dst_table, n_per_rank, n0, K0,
-                                                         K1 > 0 ? K1 : 1, ld0, ld1, col0_0, col0_1, d_colmap0, d_colmap1);
+                                                         K1 > 0 ? K1 : 1, ld0, ld1, col0_0, col0_1, d_colmap0, d_colmap1, d_lazy,
+                                                         upto_off);
   TT_LAUNCH_CHECK("push_rows_kernel");
   return TT_OK;
+}
+
+int tt_ebc_push_rows(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
+                     int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
+                     int64_t ld1, int64_t col0_0, int64_t col0_1, const int32_t* d_colmap0, const int32_t* d_colmap1,
+                     int32_t out_dtype, tt_stream_t stream) {
+  return push_rows_impl(arena, E, rows, slots, d_n_owned, capacity, dst_table, n_per_rank, n0, K0, K1, ld0, ld1, col0_0, col0_1,
+                        d_colmap0, d_colmap1, out_dtype, stream, nullptr, 0);
+}
+
+int tt_ebc_push_rows_lazy(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
+                          int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
+                          int64_t ld1, int64_t col0_0, int64_t col0_1, const int32_t* d_colmap0, const int32_t* d_colmap1,
+                          int32_t out_dtype, const tt_lazy_ctx* d_lazy, int32_t upto_offset, tt_stream_t stream) {
+  TT_CHECK_ARG(d_lazy && (upto_offset == 0 || upto_offset == -1), "tt_ebc_push_rows_lazy: bad arguments");
+  return push_rows_impl(arena, E, rows, slots, d_n_owned, capacity, dst_table, n_per_rank, n0, K0, K1, ld0, ld1, col0_0, col0_1,
+                        d_colmap0, d_colmap1, out_dtype, stream, d_lazy, upto_offset);
 }
 
 }  // extern "C"

@@ -243,6 +243,7 @@ class DistributedEngine(TwoTowerEngine):
         self._small_stream = torch.cuda.Stream(dev)
         self._peer_dummy = torch.zeros(1, dtype=torch.float64, device=dev)
         self._peer_dummy2 = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._peer_dummy3 = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def _peer_allreduce(self, buf: torch.Tensor, n: int, site: str):
         i = self.PEER_SITES.index(site)
@@ -292,6 +293,19 @@ class DistributedEngine(TwoTowerEngine):
         ws.n_owned = torch.zeros(1, **i32)
         q = self.lib.query
         ws.shard_ws = torch.empty(q("tt_shard_workspace_bytes", cap), dtype=torch.uint8, device=dev)
+        # all-to-all id routing: receive buffers [W senders][n_l] for (local row, global slot) + the W segment lengths, peer-mapped
+        ws.a2a = None
+        if n_l > 0 and os.environ.get("TT_A2A", "1") != "0":
+            seg = _a256(cap * 4)
+            abuf, apeer = self.comm.peer_buffer(2 * seg + 256, dev)
+            abuf.zero_()
+            ws.a2a_buf = abuf
+            ws.a2a = dict(rows=abuf[:cap * 4].view(torch.int32), slots=abuf[seg:seg + cap * 4].view(torch.int32),
+                          counts=abuf[2 * seg:2 * seg + 4 * W].view(torch.int32),
+                          t_rows=torch.tensor(apeer, dtype=torch.int64, device=dev),
+                          t_slots=torch.tensor([p_ + seg for p_ in apeer], dtype=torch.int64, device=dev),
+                          t_counts=torch.tensor([p_ + 2 * seg for p_ in apeer], dtype=torch.int64, device=dev),
+                          ws=torch.empty(q("tt_shard_a2a_workspace_bytes", max(n_l, 1), W), dtype=torch.uint8, device=dev))
         ws.sort_ws = torch.empty(q("tt_ebc_sort_workspace_bytes", cap, max(self.total_rows, 1)), dtype=torch.uint8, device=dev)
         ws.piece_ws = torch.empty(q("tt_ebc_piece_workspace_bytes", cap, E), dtype=torch.uint8, device=dev)
         Bg = B * W
@@ -371,16 +385,34 @@ class DistributedEngine(TwoTowerEngine):
                    ptr(ws.ids_local), s)
         self._call("tt_ebc_clamp_ids_subset", ptr(values[1]), self.vocab.data_ptr() + 4 * K0, ptr(self.d_large_keys[1]), B, K1, KL1,
                    layout, ws.ids_local.data_ptr() + 4 * n0, s)
-        if ws.xtab is not None:
-            self._peer_allgather(ws.ids_local, ws.xtab["ids"], "ids")
+        if ws.a2a is not None:
+            # all-to-all: bucket my ids by owner, push (local row, slot) into the owners' receive buffers over NVLink, barrier, pack
+            a = ws.a2a
+            self._call("tt_shard_a2a_send", ptr(ws.ids_local), ptr(self.block), ptr(self.local_base), n_l, n0, max(KL0, 1), KL1,
+                       self.world, self.rank, ptr(a["t_rows"]), ptr(a["t_slots"]), ptr(a["t_counts"]), ptr(a["ws"]), a["ws"].numel(), s,
+                       n_kernels=3)
+            if self.peer_sites is not None:
+                self._peer_allreduce(self._peer_dummy3, 1, "ids")
+            else:
+                self.comm.barrier(self.device)
+            self._call("tt_shard_a2a_compact", ptr(a["rows"]), ptr(a["slots"]), ptr(a["counts"]), self.world, n_l, ptr(ws.rows),
+                       ptr(ws.slots), ptr(ws.n_owned), s)
         else:
-            self.comm.all_gather(ws.ids_all, ws.ids_local)
-        self._call("tt_shard_select_owned", ptr(ws.ids_all), ptr(self.block), ptr(self.local_base), n_l, n0, max(KL0, 1), KL1,
-                   self.world, self.rank, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), ptr(ws.shard_ws), ws.shard_ws.numel(), s,
-                   n_kernels=3)
-        self._call("tt_ebc_push_rows", ptr(self.arena), E, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), n_l * self.world,
-                   ptr(ws.c_table), n_l, n0, max(KL0, 1), KL1, H0 + K0 * E, H0 + K1 * E, H0, H0, ptr(self.colmap[0]),
-                   ptr(self.colmap[1]), self.act, s)
+            if ws.xtab is not None:
+                self._peer_allgather(ws.ids_local, ws.xtab["ids"], "ids")
+            else:
+                self.comm.all_gather(ws.ids_all, ws.ids_local)
+            self._call("tt_shard_select_owned", ptr(ws.ids_all), ptr(self.block), ptr(self.local_base), n_l, n0, max(KL0, 1), KL1,
+                       self.world, self.rank, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), ptr(ws.shard_ws), ws.shard_ws.numel(), s,
+                       n_kernels=3)
+        if self.lazy:  # lazy exact-replay Adam: the owner catches a row up (read-only) before it sends it
+            self._call("tt_ebc_push_rows_lazy", ptr(self.arena), E, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), n_l * self.world,
+                       ptr(ws.c_table), n_l, n0, max(KL0, 1), KL1, H0 + K0 * E, H0 + K1 * E, H0, H0, ptr(self.colmap[0]),
+                       ptr(self.colmap[1]), self.act, ptr(self.lazy_ctx), self._lazy_offset, s)
+        else:
+            self._call("tt_ebc_push_rows", ptr(self.arena), E, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), n_l * self.world,
+                       ptr(ws.c_table), n_l, n0, max(KL0, 1), KL1, H0 + K0 * E, H0 + K1 * E, H0, H0, ptr(self.colmap[0]),
+                       ptr(self.colmap[1]), self.act, s)
         # every owner has finished writing into my concat buffers
         if self.peer_sites is not None:
             self._peer_allreduce(self._peer_dummy, 1, "barrier")
@@ -570,6 +602,15 @@ class DistributedEngine(TwoTowerEngine):
         if not sorted_already:
             self.embedding_sort(ws)
         self.profile_tag = "sharded"
+        if self.lazy:
+            if want_dense_grad or not apply_adam:
+                raise native.TwoTowerNativeError("optimizer_mode='lazy_exact' updates the tables inside the library (attach a FusedAdam)")
+            self._call("tt_ebc_backward_adam_lazy", ptr(self.arena), ptr(self.arena_m), ptr(self.arena_v), self.total_rows, E,
+                       ptr(ws.sorted_rows), ptr(ws.sorted_slots), cap, ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
+                       ptr(self.stamp), 0, H0 + K0 * E, H0, max(KL0, 1), n0, 0, H0 + K1 * E, H0, max(KL1, 1), n_l - n0, self.act,
+                       ptr(ws.piece_ws), ws.piece_ws.numel(), ptr(self.hyper), ptr(ws.n_owned), ptr(ws.dc_table), n_l,
+                       ptr(self.colmap[0]), ptr(self.colmap[1]), ptr(self.lazy_ctx), s, n_kernels=3)
+            return
         if want_dense_grad and self.arena_grad is None:
             self.arena_grad = torch.zeros_like(self.arena)
         self._call("tt_ebc_backward_adam", ptr(self.arena) if apply_adam else 0, ptr(self.arena_m) if apply_adam else 0,
@@ -596,6 +637,7 @@ class DistributedEngine(TwoTowerEngine):
     def load_full_tables(self, full_tables: Sequence[torch.Tensor], which: str = "w"):
         """full_tables: [V_k, E] for notice keys then company keys; small tables are copied whole (replicated), of a large
         table this rank keeps its row shard. `which`: weights "w" or the Adam moments "m" / "v"."""
+        self.lazy_mark_current()
         i = 0
         for t in range(2):
             for k in range(self.K[t]):
@@ -612,6 +654,7 @@ class DistributedEngine(TwoTowerEngine):
     def gather_full_tables(self, which: str = "w") -> List[torch.Tensor]:
         out = []
         E = self.cfg.emb_dim
+        self.flush_lazy()
         if self.total_rows > 0:
             src = {"w": self.arena, "m": self.arena_m, "v": self.arena_v}[which]
             allsh = torch.empty(self.world * src.numel(), dtype=src.dtype, device=self.device)
@@ -651,8 +694,16 @@ def create_distributed_train_task(notice_keys, company_keys, schema: dict, model
     for t in range(2):
         name, keys, vocab, dense_dim = cfg.tower(t)
         pre = f"{name}_tower."
-        for v in vocab:
-            full.append(nn.Embedding(v, E).weight.detach())
+        for ki, v in enumerate(vocab):
+            if seed_full_init:
+                full.append(nn.Embedding(v, E).weight.detach())
+            else:
+                # tables too large to draw on the host of every rank (10 M rows x 38 tables): N(0, 1) drawn on the device, shard by
+                # shard (sharded tables: seeded by table and rank; replicated small tables: by table only, identical everywhere)
+                view = eng.table_view(t, ki)
+                g = torch.Generator(device=eng.device)
+                g.manual_seed(1_000_003 * (t * 4096 + ki) + (0 if eng.is_small[t][ki] else 1 + eng.rank))
+                view.normal_(generator=g)
         lin = nn.Linear(dense_dim, cfg.hidden[0])
         eng.dense(pre + "dense_projection.weight").copy_(lin.weight.detach())
         eng.dense(pre + "dense_projection.bias").copy_(lin.bias.detach())
@@ -667,7 +718,8 @@ def create_distributed_train_task(notice_keys, company_keys, schema: dict, model
         lin = nn.Linear(width, cfg.final_dim)
         eng.dense(pre + f"mlp.{idx}.weight").copy_(lin.weight.detach())
         eng.dense(pre + f"mlp.{idx}.bias").copy_(lin.bias.detach())
-    eng.load_full_tables(full)
+    if seed_full_init:
+        eng.load_full_tables(full)
     del full
     model_mod = TwoTowerModel(eng)
     return TwoTowerTrainTask(model_mod, temperature=cfg.temperature, label_smoothing=cfg.label_smoothing)

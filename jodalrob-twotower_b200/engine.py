@@ -115,7 +115,12 @@ class TwoTowerEngine:
         self.lib = native.lib()
         self.act = native.TT_BF16 if dtype == "bf16" else TT_F32
         self.act_torch = torch.bfloat16 if dtype == "bf16" else torch.float32
-        self.adam_mode = {"dense_exact": TT_ADAM_DENSE_EXACT, "sparse": TT_ADAM_SPARSE}[optimizer_mode]
+        if optimizer_mode not in ("dense_exact", "sparse", "lazy_exact"):
+            raise ValueError(f"optimizer_mode must be 'dense_exact', 'lazy_exact' or 'sparse', got {optimizer_mode}")
+        # lazy_exact: the reference's dense Adam semantics (every row moves every step) without streaming every row every step —
+        # rows are caught up, bit for bit, when they are next read or updated (tt_lazy_ctx in include/twotower_b200.h)
+        self.lazy = optimizer_mode == "lazy_exact"
+        self.adam_mode = {"dense_exact": TT_ADAM_DENSE_EXACT, "sparse": TT_ADAM_SPARSE, "lazy_exact": native.TT_ADAM_LAZY_EXACT}[optimizer_mode]
         # Split exact-dense table update of the fused step (TT_SPLIT_ADAM=1): rows the batch does not touch (g = wd*w) are updated
         # right behind the sort-dedup, underneath the towers; only the touched rows wait for the gradients. Bit-identical to the
         # one-kernel update. Measured on B200 at the README-default size: 376 us per step against 361 us unsplit — the extra kernel
@@ -139,7 +144,7 @@ class TwoTowerEngine:
         dev = self.device
         self.K = (len(cfg.notice_keys), len(cfg.company_keys))
         self.layout = DenseLayout(cfg)
-        self._plan_tables(small_tables and optimizer_mode == "dense_exact")
+        self._plan_tables(small_tables and optimizer_mode in ("dense_exact", "lazy_exact"))
         P_tot, RL = self.P_tot, self.total_rows
         # ONE flat fp32 allocation: [dense params | small tables | large-table arena]; Adam moments mirror it
         self.flat_w = torch.zeros(P_tot + RL * E, dtype=torch.float32, device=dev)
@@ -166,6 +171,18 @@ class TwoTowerEngine:
         self.row_begin = torch.zeros(max(self.total_rows, 1), dtype=torch.int32, device=dev)
         self.row_end = torch.zeros(max(self.total_rows, 1), dtype=torch.int32, device=dev)
         self.row_stamp = torch.zeros(max(self.total_rows, 1), dtype=torch.int32, device=dev)
+        self._lazy_offset = 0      # -1 while a train step is in flight (its own update of the looked-up rows is still to come)
+        self._steps_since_flush = 0
+        if self.lazy:
+            import struct
+            self.hist_len = int(os.environ.get("TT_LAZY_HIST", "65536"))
+            if self.hist_len & (self.hist_len - 1):
+                raise ValueError("TT_LAZY_HIST must be a power of two")
+            self.row_last = torch.zeros(max(self.total_rows, 1), dtype=torch.int32, device=dev)
+            self.lazy_hist = torch.zeros(2 * self.hist_len, dtype=torch.float32, device=dev)
+            raw = struct.pack("<5Qq1Q", self.arena.data_ptr(), self.arena_m.data_ptr(), self.arena_v.data_ptr(), self.row_last.data_ptr(),
+                              self.lazy_hist.data_ptr(), self.hist_len, self.hyper.data_ptr())
+            self.lazy_ctx = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
         self._ws: Dict[int, _Ws] = {}
         self.rng_seed = 0x5EED
         self.rng_stream_base = 0  # distributed engines offset it by rank so ranks draw different dropout masks
@@ -447,6 +464,11 @@ class TwoTowerEngine:
             k0 = 0 if t == 0 else self.K[0]
             rows_off = 0 if t == 0 else B * self.KL[0]
             self.profile_tag = self.cfg.tower(t)[0]
+            if self.lazy and self.total_rows > 0:
+                self._call("tt_ebc_forward_mixed_lazy", ptr(self.flat_w), self.row_base.data_ptr() + 8 * k0, self.vocab.data_ptr() + 4 * k0,
+                           ptr(v), B, K, E, layout, ptr(ws.c[t]), self.act, H0 + K * E, H0, self.large_rank.data_ptr() + 4 * k0,
+                           self.KL[t], self.P_tot // E, ws.rows.data_ptr() + 4 * rows_off, ptr(self.lazy_ctx), self._lazy_offset, s)
+                continue
             self._call("tt_ebc_forward_mixed", ptr(self.flat_w), self.row_base.data_ptr() + 8 * k0, self.vocab.data_ptr() + 4 * k0,
                        ptr(v), B, K, E, layout, ptr(ws.c[t]), self.act, H0 + K * E, H0, self.large_rank.data_ptr() + 4 * k0,
                        self.KL[t], self.P_tot // E, ws.rows.data_ptr() + 4 * rows_off, s)
@@ -897,6 +919,16 @@ class TwoTowerEngine:
         if not sorted_already:
             self.embedding_sort(ws)
         self.profile_tag = ""
+        if self.lazy:
+            if want_dense_grad or not apply_adam:
+                raise native.TwoTowerNativeError("optimizer_mode='lazy_exact' updates the tables inside the library (attach a FusedAdam): "
+                                                 "dense table gradients for an external optimizer need optimizer_mode='dense_exact'")
+            self._call("tt_ebc_backward_adam_lazy", ptr(self.arena), ptr(self.arena_m), ptr(self.arena_v), self.total_rows, E,
+                       ptr(ws.sorted_rows), ptr(ws.sorted_slots), n, ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp),
+                       ptr(self.stamp), ptr(ws.dc[0]), H0 + self.K[0] * E, H0, max(self.KL[0], 1), n0, ptr(ws.dc[1]), H0 + self.K[1] * E,
+                       H0, max(self.KL[1], 1), n1, self.act, ptr(ws.piece_ws), ws.piece_ws.numel(), ptr(self.hyper), 0, 0, 0,
+                       ptr(self.colmap[0]), ptr(self.colmap[1]), ptr(self.lazy_ctx), s, n_kernels=3)
+            return
         if want_dense_grad and self.arena_grad is None:
             self.arena_grad = torch.zeros_like(self.arena)
         self._call("tt_ebc_backward_adam", ptr(self.arena) if apply_adam else 0, ptr(self.arena_m) if apply_adam else 0,
@@ -933,8 +965,35 @@ class TwoTowerEngine:
 
     # ------------------------------------------------------------------ optimizer
     def hyper_advance(self, lr: float, warmup_steps: int, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
+        if self.lazy:
+            self.note_step()
+            self._call("tt_hyper_advance_hist", ptr(self.hyper), lr, warmup_steps, betas[0], betas[1], eps, weight_decay,
+                       self.rng_seed, ptr(self.lazy_hist), self.hist_len, self._stream())
+            return
         self._call("tt_hyper_advance", ptr(self.hyper), lr, warmup_steps, betas[0], betas[1], eps, weight_decay,
                    self.rng_seed, self._stream())
+
+    # ---- lazy exact-replay Adam bookkeeping (host side)
+    def note_step(self):
+        """One more optimizer step is about to run (eagerly, or as a graph replay): flush before the history ring could wrap."""
+        if not self.lazy:
+            return
+        if self._steps_since_flush >= self.hist_len - 4 and not torch.cuda.is_current_stream_capturing():
+            self.flush_lazy()
+        self._steps_since_flush += 1
+
+    def flush_lazy(self):
+        """Bring every row of the sorted tables up to the current optimizer step (before weights / moments are read from outside
+        the engine: state_dict, checkpoints, gathers). No-op unless optimizer_mode='lazy_exact'."""
+        if self.lazy and self.total_rows > 0:
+            self._call("tt_ebc_lazy_flush", ptr(self.lazy_ctx), self.total_rows, self.cfg.emb_dim, self._stream())
+            self._steps_since_flush = 0
+
+    def lazy_mark_current(self):
+        """The tables were just written from outside (load_state_dict / resume): every row is current as of the present step."""
+        if self.lazy:
+            self.row_last.fill_(int(self.hyper.view(torch.int64)[0].item()))
+            self._steps_since_flush = 0
 
     def dense_adam(self):
         self._call("tt_dense_adam", ptr(self.dense_w), ptr(self.dense_g), ptr(self.dense_m), ptr(self.dense_v),
@@ -957,10 +1016,12 @@ class TwoTowerEngine:
         else:
             self.hyper_advance(lr, warmup_steps, betas, eps, weight_decay)
         self._arm_split = self._in_fused = True
+        self._lazy_offset = -1
         try:
             out5, ws = self.forward(notice_dense, notice_values, company_dense, company_values, True, layout, masks, sort_on_side=True)
         finally:
             self._arm_split = self._in_fused = False
+            self._lazy_offset = 0
             self._hyper_done = None
         if self.two_streams:
             # Three streams below the loss: the towers' backward passes on `main` / `_side`, and on `_sort_stream` (where the

@@ -222,9 +222,15 @@ class _TrainStepFn(torch.autograd.Function):
         if task._fused_opt is not None:
             o = task._fused_opt
             eng.hyper_advance(o.lr, o.warmup_steps, o.betas, o.eps, o.weight_decay)
+        elif eng.lazy:
+            raise native.TwoTowerNativeError("optimizer_mode='lazy_exact' needs a FusedAdam(task, ...): the table update runs inside the library")
         elif eng.cfg.dropout > 0:
             eng.hyper_advance(0.0, 0, (0.9, 0.999), 1e-8, 0.0)  # only the dropout RNG step matters here
-        out5, ws = eng.forward(nd, nv, cd, cv, True, layout, masks)
+        eng._lazy_offset = -1 if task._fused_opt is not None else 0
+        try:
+            out5, ws = eng.forward(nd, nv, cd, cv, True, layout, masks)
+        finally:
+            eng._lazy_offset = 0
         ctx.task, ctx.ws = task, ws
         res = out5.clone()
         ctx.mark_non_differentiable(res)
@@ -276,9 +282,15 @@ class _CosineStepFn(torch.autograd.Function):
         if task._fused_opt is not None:
             o = task._fused_opt
             eng.hyper_advance(o.lr, o.warmup_steps, o.betas, o.eps, o.weight_decay)
+        elif eng.lazy:
+            raise native.TwoTowerNativeError("optimizer_mode='lazy_exact' needs a FusedAdam(task, ...): the table update runs inside the library")
         elif eng.cfg.dropout > 0:
             eng.hyper_advance(0.0, 0, (0.9, 0.999), 1e-8, 0.0)
-        out5, ws = eng.forward(nd, nv, cd, cv, True, layout, masks)
+        eng._lazy_offset = -1 if task._fused_opt is not None else 0
+        try:
+            out5, ws = eng.forward(nd, nv, cd, cv, True, layout, masks)
+        finally:
+            eng._lazy_offset = 0
         s = eng.similarity_matrix(ws)
         res = out5.clone()
         res[0] = _cosine_embedding_loss(s)
@@ -351,6 +363,15 @@ class TwoTowerTrainTask(nn.Module):
             raise RuntimeError("TwoTowerTrainTask lives on the device it was created on (fp32 masters); "
                                "pass device= to create_two_tower_train_task instead of calling .to()/.half()")
         return self
+
+    def state_dict(self, *args, **kwargs):
+        self.engine.flush_lazy()  # lazy exact-replay Adam: every row up to date before anybody reads the tables
+        return super().state_dict(*args, **kwargs)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        out = super().load_state_dict(state_dict, *args, **kwargs)
+        self.engine.lazy_mark_current()
+        return out
 
     def _sync_cfg(self):
         cfg = self.engine.cfg
@@ -498,6 +519,7 @@ class GraphedFusedStep:
         o = task._fused_opt
         self._args = (o.lr, o.warmup_steps, o.betas, o.eps, o.weight_decay)
         hyper0 = eng.hyper.clone()
+        lazy0 = (eng.row_last.clone(), eng.lazy_hist.clone(), eng._steps_since_flush) if eng.lazy else None
         state0 = (eng.flat_w.clone(), eng.flat_m.clone(), eng.flat_v.clone(),
                   [[b.clone() for b in bl] for bl in eng.bn_rm], [[b.clone() for b in bl] for bl in eng.bn_rv],
                   [[b.clone() for b in bl] for bl in eng.bn_nbt])
@@ -518,6 +540,8 @@ class GraphedFusedStep:
         # epoch that repeats would make a later step mistake those rows for rows of its own batch. It only has to be monotonic.
         torch.cuda.synchronize(eng.device)
         eng.hyper.copy_(hyper0)
+        if lazy0 is not None:
+            eng.row_last.copy_(lazy0[0]); eng.lazy_hist.copy_(lazy0[1]); eng._steps_since_flush = lazy0[2]
         eng.flat_w.copy_(state0[0]); eng.flat_m.copy_(state0[1]); eng.flat_v.copy_(state0[2])
         for dst, src in ((eng.bn_rm, state0[3]), (eng.bn_rv, state0[4]), (eng.bn_nbt, state0[5])):
             for dl, sl in zip(dst, src):
@@ -551,6 +575,7 @@ class GraphedFusedStep:
             self.static_blob.copy_(packed, non_blocking=True)
         elif batch is not None:
             self.load(batch)
+        self.task.engine.note_step()  # lazy exact-replay Adam: flush (eagerly, between replays) before the history ring wraps
         self.graph.replay()
         self.task.engine.launches += self.launches_per_step
         return self.out
@@ -591,6 +616,7 @@ class FusedAdam:
         return self.lr * (sched_step / w if (w > 0 and sched_step < w) else 1.0)
 
     def state_dict(self):
+        self.task.engine.flush_lazy()
         h = self.task.engine.hyper_host()
         step = int(h["step"])
         state = {}
@@ -640,6 +666,7 @@ class FusedAdam:
         if "rng_step" in extra:
             h64[7] = int(extra["rng_step"])
         self.param_groups[0].update(lr=self._next_lr(sched), betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+        eng.lazy_mark_current()
 
 
 class FusedWarmupScheduler:

@@ -19,6 +19,7 @@ TT_OK = 0
 TT_F32, TT_BF16 = 0, 1
 TT_LAYOUT_SAMPLE_MAJOR, TT_LAYOUT_KEY_MAJOR = 0, 1
 TT_ADAM_DENSE_EXACT, TT_ADAM_SPARSE, TT_ADAM_DENSE_UNTOUCHED = 0, 1, 2
+TT_ADAM_LAZY_EXACT = 3  # engine-side name: tt_ebc_backward_adam_lazy / tt_ebc_forward_mixed_lazy (include/twotower_b200.h, tt_lazy_ctx)
 HYPER_BYTES = 64
 
 _SCALARS = {

@@ -78,7 +78,7 @@ def compare_state(ours: Dict[str, torch.Tensor], ref: Dict[str, torch.Tensor], t
 
 def run(tt, schema, device, dtype: str = "bf16", B_local: int = 1024, steps: int = 3, world: int = 1, rank: int = 0,
         graph: bool = True, lr: float = 1e-3, weight_decay: float = 1e-5, warmup_steps: int = 2, seed: int = 0,
-        ttdist=None, comm=None, return_task: bool = False, port=None) -> Optional[dict]:
+        ttdist=None, comm=None, return_task: bool = False, port=None, optimizer_mode: str = "dense_exact") -> Optional[dict]:
     """Every rank calls it (collective at world > 1); the dict comes back on rank 0, None elsewhere. `port`: a freshly built
     port shared by in-process rank threads (the global torch RNG is not thread-safe); rank 0 steps it at the end."""
     tol = 2e-2 if dtype == "bf16" else 1e-5
@@ -88,14 +88,15 @@ def run(tt, schema, device, dtype: str = "bf16", B_local: int = 1024, steps: int
     init = {k: v.clone() for k, v in port.state_dict().items()}
     if world > 1:
         model = dict(MODEL, dropout=0.0)
-        task = ttdist.create_distributed_train_task(nk, ck, schema, model, device, comm=comm, dtype=dtype)
+        task = ttdist.create_distributed_train_task(nk, ck, schema, model, device, comm=comm, dtype=dtype, optimizer_mode=optimizer_mode)
         ttdist.load_reference_state_dict(task, init)
     else:
         task = tt.create_two_tower_train_task(
             nk, ck, categorical_embedding_dim=MODEL["emb_dim"], notice_dense_input_dim=MODEL["notice_dense"],
             company_dense_input_dim=MODEL["company_dense"], tower_hidden_dims=MODEL["hidden"], final_embedding_dim=MODEL["final_dim"],
             dropout_rate=0.0, temperature=MODEL["temperature"], device=device,
-            vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])}, dtype=dtype)
+            vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])}, dtype=dtype,
+            optimizer_mode=optimizer_mode)
         task.load_state_dict(init)
     tt.FusedAdam(task, lr=lr, weight_decay=weight_decay, warmup_steps=warmup_steps)
     task.train()

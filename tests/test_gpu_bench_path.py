@@ -126,8 +126,9 @@ def test_torchrun_sharded_bf16_peer_path_vs_reference(world):
     assert "bf16" in r.stdout and "FAIL" not in r.stdout
 
 
-@pytest.mark.parametrize("world,dtype,bl", [(2, "bf16", 1024), (4, "bf16", 512), (2, "fp32", 256)])
-def test_emulated_ranks_sharded_step_readme_schema_vs_reference(world, dtype, bl):
+@pytest.mark.parametrize("world,dtype,bl,opt", [(2, "bf16", 1024, "dense_exact"), (4, "bf16", 512, "dense_exact"), (2, "fp32", 256, "dense_exact"),
+                                                (3, "fp32", 256, "lazy_exact"), (2, "bf16", 512, "lazy_exact")])
+def test_emulated_ranks_sharded_step_readme_schema_vs_reference(world, dtype, bl, opt):
     """The row-wise sharded step in the benchmarked precision on ONE GPU: `world` rank threads, host-mediated collectives
     (dist.ThreadComm: same engine code, the peer-memory kernels replaced by their all_gather / all_reduce equivalents), against the
     reference port on the concatenated global batch. Covers the three-pass logits step with its row-sum / column-sum exchanges,
@@ -145,7 +146,7 @@ def test_emulated_ranks_sharded_step_readme_schema_vs_reference(world, dtype, bl
         try:
             torch.cuda.set_device(0)
             results[r] = bench_parity.run(tt, schema, torch.device(DEV), dtype=dtype, B_local=bl, steps=3, world=world, rank=r,
-                                          graph=False, ttdist=ttd, comm=ttd.ThreadComm(tw, r), port=port)
+                                          graph=False, ttdist=ttd, comm=ttd.ThreadComm(tw, r), port=port, optimizer_mode=opt)
         except Exception:
             import traceback
             errors.append(traceback.format_exc())
@@ -162,6 +163,58 @@ def test_emulated_ranks_sharded_step_readme_schema_vs_reference(world, dtype, bl
     assert not errors, errors[0]
     res = results[0]
     assert res["ok"], res
+
+
+def test_all_to_all_id_routing_equals_allgather_selection(monkeypatch):
+    """tt_shard_a2a_send + tt_shard_a2a_compact (the sender buckets by owner, the owner packs its W segments) produce exactly the
+    (rows, slots, n_owned) of all-gather + tt_shard_select_owned, for every rank — bit-exact integer stage; W ranks emulated on one GPU
+    (the peer pointers are plain device pointers here)."""
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200.native import ptr
+    lib = tt.native.lib()
+    W, n0, K0, K1 = 5, 3000 * 3, 3, 2
+    n = n0 + 3000 * K1
+    vocab = [100_000, 37, 5000, 123_457, 64]
+    block = [-(-v // W) for v in vocab]
+    base = [0]
+    for b in block[:-1]:
+        base.append(base[-1] + b)
+    g = torch.Generator().manual_seed(0)
+    ids = []
+    for r in range(W):
+        a = torch.stack([torch.randint(0, v, (3000,), generator=g) for v in vocab[:K0]], 1).reshape(-1)
+        b = torch.stack([torch.randint(0, v, (3000,), generator=g) for v in vocab[K0:]], 1).reshape(-1)
+        ids.append(torch.cat([a, b]).to(torch.int32).to(DEV))
+    d_block, d_base = torch.tensor(block, dtype=torch.int32, device=DEV), torch.tensor(base, dtype=torch.int32, device=DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    # reference: all-gather + select_owned per rank
+    ids_all = torch.cat(ids)
+    ref = []
+    for r in range(W):
+        rows, slots, cnt = torch.zeros(W * n, dtype=torch.int32, device=DEV), torch.zeros(W * n, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+        wsb = torch.empty(lib.query("tt_shard_workspace_bytes", W * n), dtype=torch.uint8, device=DEV)
+        lib.call("tt_shard_select_owned", ptr(ids_all), ptr(d_block), ptr(d_base), n, n0, K0, K1, W, r, ptr(rows), ptr(slots), ptr(cnt), ptr(wsb), wsb.numel(), s)
+        c = int(cnt.item())
+        ref.append((rows[:c].clone(), slots[:c].clone()))
+    # all-to-all
+    recv_rows = [torch.full((W * n,), -7, dtype=torch.int32, device=DEV) for _ in range(W)]
+    recv_slots = [torch.full((W * n,), -7, dtype=torch.int32, device=DEV) for _ in range(W)]
+    recv_cnt = [torch.zeros(W, dtype=torch.int32, device=DEV) for _ in range(W)]
+    tab = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=DEV)
+    t_rows, t_slots, t_cnt = tab(recv_rows), tab(recv_slots), tab(recv_cnt)
+    for r in range(W):
+        wsb = torch.empty(lib.query("tt_shard_a2a_workspace_bytes", n, W), dtype=torch.uint8, device=DEV)
+        lib.call("tt_shard_a2a_send", ptr(ids[r]), ptr(d_block), ptr(d_base), n, n0, K0, K1, W, r, ptr(t_rows), ptr(t_slots), ptr(t_cnt), ptr(wsb), wsb.numel(), s)
+    torch.cuda.synchronize()
+    total = 0
+    for r in range(W):
+        rows, slots, cnt = torch.zeros(W * n, dtype=torch.int32, device=DEV), torch.zeros(W * n, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+        lib.call("tt_shard_a2a_compact", ptr(recv_rows[r]), ptr(recv_slots[r]), ptr(recv_cnt[r]), W, n, ptr(rows), ptr(slots), ptr(cnt), s)
+        c = int(cnt.item())
+        total += c
+        assert c == ref[r][0].numel()
+        assert torch.equal(rows[:c], ref[r][0]) and torch.equal(slots[:c], ref[r][1])
+    assert total == W * n  # every id has exactly one owner
 
 
 # ------------------------------------------------------------------------------- the logits entry points the timed step calls
@@ -280,3 +333,83 @@ def test_split_forward_equals_fused_forward_entry_points(Bx, By, off):
     xd, yd = xb.double().cpu(), yb.double().cpu()
     E = torch.exp(xd @ yd.t() / T - 1 / T)
     assert rel_err(a["rse"].cpu(), E.sum(1)) < 2e-4 and rel_err(a["cse"].cpu(), E.sum(0)) < 2e-4
+
+
+# ------------------------------------------------------------------------------- lazy exact-replay Adam
+@pytest.mark.parametrize("dtype,B,warmup", [("fp32", 64, 0), ("fp32", 512, 3), ("bf16", 1024, 2)])
+def test_lazy_exact_adam_is_bitwise_the_dense_update(dtype, B, warmup):
+    """optimizer_mode='lazy_exact' (rows caught up when next read / updated) against optimizer_mode='dense_exact' (every row
+    streamed every step == torch.optim.Adam, scripts/train.py:231): same batches, same seeds -> every weight, every Adam moment
+    and every loss bit-identical after the flush; small batches leave most rows untouched for several steps (long replays)."""
+    import jodalrob_twotower_b200 as tt
+    schema = readme_schema()
+    nk, ck = [k for k, _ in schema["notice"]], [k for k, _ in schema["company"]]
+    batches = bench_parity.global_batches(schema, B, 7, seed=123)
+    finals = []
+    for mode in ("dense_exact", "lazy_exact"):
+        torch.manual_seed(33)
+        task = tt.create_two_tower_train_task(
+            nk, ck, categorical_embedding_dim=32, notice_dense_input_dim=256, company_dense_input_dim=128, tower_hidden_dims=[128, 64],
+            final_embedding_dim=64, dropout_rate=0.1, temperature=1.0, device=DEV,
+            vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])}, dtype=dtype, optimizer_mode=mode)
+        opt = tt.FusedAdam(task, lr=1e-3, weight_decay=1e-5, warmup_steps=warmup)
+        task.train()
+        losses = []
+        for i, b in enumerate(batches):
+            losses.append(task.fused_step(_batch(tt, schema, b)).clone())
+            if i == 3:  # an eval forward in between sees the caught-up rows without disturbing the trajectory
+                task.eval()
+                with torch.no_grad():
+                    ev = task(_batch(tt, schema, batches[0]), return_metrics=True)["loss"].clone()
+                task.train()
+                losses.append(ev.reshape(1).repeat(5))
+        sd = {k: v.clone() for k, v in task.state_dict().items()}  # flushes
+        osd = opt.state_dict()
+        eng = task.engine
+        finals.append((torch.stack(losses), sd, eng.flat_m.clone(), eng.flat_v.clone(), osd))
+    a, b = finals
+    assert torch.equal(a[0], b[0])
+    for k in a[1]:
+        assert torch.equal(a[1][k], b[1][k]), k
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    for i in a[4]["state"]:
+        assert torch.equal(a[4]["state"][i]["exp_avg_sq"], b[4]["state"][i]["exp_avg_sq"])
+
+
+def test_lazy_exact_adam_graph_replay_flush_and_resume():
+    """Graph replays with a tiny history ring (TT_LAZY_HIST=8): the ring wraps several times, so the automatic flush between
+    replays is exercised; then a checkpoint written in lazy mode resumes in dense mode on the same trajectory."""
+    import os
+    import jodalrob_twotower_b200 as tt
+    schema = readme_schema()
+    nk, ck = [k for k, _ in schema["notice"]], [k for k, _ in schema["company"]]
+    batches = bench_parity.global_batches(schema, 256, 21, seed=5)
+    mk = lambda mode: tt.create_two_tower_train_task(
+        nk, ck, categorical_embedding_dim=32, notice_dense_input_dim=256, company_dense_input_dim=128, tower_hidden_dims=[128, 64],
+        final_embedding_dim=64, dropout_rate=0.0, temperature=1.0, device=DEV,
+        vocab_sizes={"notice": dict(schema["notice"]), "company": dict(schema["company"])}, dtype="fp32", optimizer_mode=mode)
+    outs = {}
+    for mode in ("dense_exact", "lazy_exact"):
+        os.environ["TT_LAZY_HIST"] = "8"
+        try:
+            torch.manual_seed(2)
+            task = mk(mode)
+        finally:
+            os.environ.pop("TT_LAZY_HIST")
+        opt = tt.FusedAdam(task, lr=1e-3, weight_decay=1e-5, warmup_steps=4)
+        task.train()
+        step = tt.GraphedFusedStep(task, _batch(tt, schema, batches[0]))
+        for b in batches[1:15]:
+            step(_batch(tt, schema, b))
+        ck_model, ck_opt = {k: v.clone() for k, v in task.state_dict().items()}, opt.state_dict()
+        # resume the checkpoint in the OTHER mode and continue eagerly
+        other = mk("dense_exact" if mode == "lazy_exact" else "lazy_exact")
+        opt2 = tt.FusedAdam(other, lr=1e-3, weight_decay=1e-5, warmup_steps=4)
+        other.load_state_dict(ck_model)
+        opt2.load_state_dict(ck_opt)
+        other.train()
+        for b in batches[15:]:
+            other.fused_step(_batch(tt, schema, b))
+        outs[mode] = {k: v.clone() for k, v in other.state_dict().items()}
+    for k in outs["dense_exact"]:
+        assert torch.equal(outs["dense_exact"][k], outs["lazy_exact"][k]), k
