@@ -291,6 +291,176 @@ def tables_section(dev, pk, quick=False):
     torch.cuda.empty_cache()
     return out
 
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs[2]: 10 M-row tables
+def zipf_ids(n, V, alpha, gen, dev):
+    """Zipf(alpha)-distributed ids over [0, V) (continuous inverse-CDF approximation), scrambled by a fixed bijection of [0, V) so
+    that the hot rows spread over the row-wise shards the way hashed ids do in practice (rank r owns the contiguous block r)."""
+    u = torch.rand(n, generator=gen, device=dev, dtype=torch.float64)
+    a = 1.0 - alpha
+    x = ((float(V) ** a - 1.0) * u + 1.0) ** (1.0 / a)
+    ids = (x.floor().long() - 1).clamp_(0, V - 1)
+    return (ids * 2_654_435_761 + 12_345) % V if V % 2_654_435_761 else ids
+
+
+def run_cfg3(args):
+    """BASELINE.json configs[2]: the README-default towers on 38 tables of --rows-per-table rows (10 M), row-wise sharded over the
+    ranks, Zipf(1.05) ids, B = --batch per GPU, all-to-all id routing, fused lookup + row push and gradient pull over NVLink peer
+    memory. One JSON line: samples/s, the kernel table of the graph replays (CUPTI) and the HBM fractions of the table kernels
+    against their algorithmic bytes, NVLink bytes per rank against the formulas."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    os.environ.setdefault("RANK", "0")
+    os.environ.setdefault("WORLD_SIZE", "1")
+    dist.init_process_group("nccl", device_id=dev)
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200 import dist as ttdist
+    base = load_schema()
+    V = int(args.rows_per_table)
+    schema = {"notice": [[k, V] for k, _ in base["notice"]], "company": [[k, V] for k, _ in base["company"]]}
+    nk, ck = [k for k, _ in schema["notice"]], [k for k, _ in schema["company"]]
+    B, E, K = args.batch, MODEL["emb_dim"], len(nk) + len(ck)
+    torch.manual_seed(0)
+    task = ttdist.create_distributed_train_task(nk, ck, schema, MODEL, dev, dtype=args.dtype, optimizer_mode=args.optimizer,
+                                                seed_full_init=False)
+    tt.FusedAdam(task, lr=MODEL["lr"], weight_decay=MODEL["weight_decay"], warmup_steps=0)
+    task.train()
+    eng = task.engine
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    n_rot = 4
+    mk = lambda keys, v: tt.KeyedJaggedTensor(keys, v)
+
+    def batch():
+        nid = torch.stack([zipf_ids(B, V, args.zipf, gen, dev) for _ in nk], 1).reshape(-1)
+        cid = torch.stack([zipf_ids(B, V, args.zipf, gen, dev) for _ in ck], 1).reshape(-1)
+        return {"notice": {"dense": torch.randn(B, MODEL["notice_dense"], generator=gen, device=dev), "kjt": mk(nk, nid)},
+                "company": {"dense": torch.randn(B, MODEL["company_dense"], generator=gen, device=dev), "kjt": mk(ck, cid)}}
+
+    batches = [batch() for _ in range(n_rot)]
+    gstep = tt.GraphedFusedStep(task, batches[0])
+    packed = [gstep.pack(b) for b in batches]
+
+    def barrier():
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        gstep(packed=packed[i % n_rot])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.current_stream(dev)
+    barrier()
+    e0.record(st)
+    for i in range(args.steps):
+        out = gstep(packed=packed[i % n_rot])
+    e1.record(st)
+    barrier()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    loss_last = float(out[0].item())
+    # kernel table of the replays (CUPTI)
+    gk = {}
+    from torch.profiler import ProfilerActivity, profile
+    n_cupti = 3
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(n_cupti):
+            gstep(packed=packed[i % n_rot])
+        torch.cuda.synchronize(dev)
+    for ev in prof.key_averages():
+        if ev.device_time_total > 0 and ev.count > 0:
+            name = ev.key.replace("void ", "").replace("tt::", "").split("(")[0]
+            d = gk.setdefault(name, {"us": 0.0, "n": 0.0})
+            d["us"] += ev.device_time_total / n_cupti
+            d["n"] += ev.count / n_cupti
+    barrier()
+    # lazy exact-replay Adam: what the deferred dense update costs when it is finally paid — a flush after `lag` more steps replays
+    # (rows x E x lag) element-steps in registers; reported as picoseconds per element-step next to the 24 B / 6.5 TB/s = 3.7 ps the
+    # streaming dense update needs at the HBM peak
+    lazy_replay = None
+    if eng.lazy:
+        eng.flush_lazy()
+        lag = 32
+        for i in range(lag):
+            gstep(packed=packed[i % n_rot])
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(st)
+        eng.flush_lazy()
+        f1.record(st)
+        torch.cuda.synchronize(dev)
+        fl_ms = f0.elapsed_time(f1)
+        lazy_replay = {"flush_ms_after_32_steps": fl_ms, "rows": eng.total_rows, "element_steps_upper_bound": eng.total_rows * E * lag,
+                       "ps_per_element_step": fl_ms * 1e-3 / (eng.total_rows * E * lag) * 1e12,
+                       "note": "every row-step is replayed exactly once (at the row's next touch, or at a flush): in steady state the "
+                               "deferred arithmetic per step is rows x E element-steps at this rate, instead of rows x E x 24 B of HBM traffic"}
+        barrier()
+    ws = eng.workspace(B)
+    n_owned = int(ws.n_owned.item())
+    uniq = int(torch.unique(ws.sorted_rows[:n_owned]).numel()) if n_owned else 0
+    stats = torch.tensor([n_owned, uniq], dtype=torch.float64, device=dev)
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        _finish(world, dev)
+        return
+    pk = peaks()
+    n_l = B * K
+    n_owned_avg, uniq_avg = float(stats[0]) / world, float(stats[1]) / world
+    w_o = 2 if args.dtype == "bf16" else 4
+    rows_local = eng.total_rows
+    alg = {
+        "push_rows_kernel": n_owned_avg * (E * 4 + 8 + E * w_o),                       # row read + (row, slot) + row pushed to the requester
+        "ebc_gather_sorted_kernel": n_owned_avg * (E * w_o + 4 + E * 4),               # gradient pulled over NVLink + slot + compacted copy
+        "ebc_rows_dense_stream_kernel": rows_local * E * 24 + n_owned_avg * E * 4,     # every row: w, m, v read + written
+        "ebc_rows_sparse_kernel": uniq_avg * E * 24 + n_owned_avg * (E * 4 + 4),       # touched rows only
+    }
+    kernels = []
+    for k_, v in sorted(gk.items(), key=lambda kv: -kv[1]["us"]):
+        row = {"kernel": k_, "us_per_step": round(v["us"], 1), "launches_per_step": round(v["n"], 2)}
+        for key, by in alg.items():
+            if k_.startswith(key):
+                row["algorithmic_MB"] = round(by / 1e6, 2)
+                row["GBps"] = round(by / (v["us"] * 1e-6) / 1e9, 1)
+                row["frac_hbm"] = round(row["GBps"] / pk["hbm_gbs"], 3)
+        kernels.append(row)
+    f = (world - 1) / world
+    nvlink = {"id_all_to_all_sent": n_l * 8 * f, "rows_received": n_l * E * w_o * f, "gradients_pulled_by_owner": n_owned_avg * E * w_o * f,
+              "embedding_all_gathers_received": 2 * B * world * MODEL["final_dim"] * 2 * f, "sum_exchanges_received": 2 * B * world * 4 * f,
+              "dense_gradient_all_reduce": 2 * eng.P_tot * 4 * f}
+    top_tab = next((r for r in kernels if "frac_hbm" in r), None)
+    roofline = None
+    if top_tab is not None:
+        roofline = {"kernel": top_tab["kernel"], "bound": "hbm", "achieved": top_tab["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": top_tab["frac_hbm"], "traffic": None, "peak_source": pk["source"],
+                    "algorithmic": f"{top_tab['algorithmic_MB']} MB per launch (SURVEY.md 8(d))"}
+    line = {"metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2]: README-default towers on {K} tables x {V:,} rows x E={E} ({K * V * E * 4 / 1e9:.1f} GB of "
+                                   f"fp32 weights, x3 with the Adam moments), row-wise sharded over {world} GPUs, Zipf({args.zipf}) ids "
+                                   f"(scrambled), B={B} per GPU, global negatives",
+                       "batch_per_gpu": B, "global_batch": B * world, "rows_per_table": V, "rows_per_gpu": rows_local,
+                       "optimizer": args.optimizer, "routing": "all-to-all over NVLink peer memory (sender buckets by owner)",
+                       "l2_policy": f"tables of {rows_local * E * 4 / 1e9:.1f} GB per GPU >> 126 MB L2; inputs rotate over {n_rot} batches",
+                       "cuda_graph": True},
+            "clocks": clocks, "gpu_launches": gstep.launches_per_step * args.steps, "launches_per_step": gstep.launches_per_step,
+            "roofline": roofline, "kernels": kernels[:20],
+            "ids_per_rank": {"requested": n_l, "owned_avg": n_owned_avg, "unique_rows_avg": uniq_avg},
+            "nvlink_bytes_per_rank_per_step": {k_: round(v) for k_, v in nvlink.items()},
+            "nvlink_total_MB_per_rank_per_step": round(sum(nvlink.values()) / 1e6, 2), "lazy_replay": lazy_replay, "loss_last": loss_last}
+    print(json.dumps(line), flush=True)
+    _finish(world, dev)
+
 # ------------------------------------------------------------------------------------------------ our arm
 def algorithmic(tag: str, B: int, schema, world: int = 1) -> dict:
     """Algorithmic bytes / flops of one C-ABI call. B = samples per rank; with global
@@ -727,12 +897,19 @@ def main():
     ap.add_argument("--tables-only", nargs="?", const="full", default=None, choices=["full", "quick"])
     ap.add_argument("--no-device-store", action="store_true", help="skip the end-to-end loop with HBM-resident feature stores")
     ap.add_argument("--no-tables", action="store_true", help="skip the large-table (HBM-bound lookup/update) section")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg2 (default): BASELINE configs[1], the headline line. cfg3: BASELINE configs[2], 10 M-row tables sharded over the ranks "
+                         "(run under torchrun; --optimizer lazy_exact / dense_exact / sparse)")
+    ap.add_argument("--rows-per-table", type=int, default=10_000_000)
+    ap.add_argument("--zipf", type=float, default=1.05)
     args = ap.parse_args()
     if args.tables_only:  # development aid: only the large-table section (not the contract line)
         torch.cuda.set_device(0)
         print(json.dumps({"tables": tables_section(torch.device("cuda", 0), peaks(), quick=args.tables_only == "quick")}), flush=True)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.config == "cfg3":
+        run_cfg3(args)
     else:
         run_ours(args)
 

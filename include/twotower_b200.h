@@ -275,6 +275,19 @@ int tt_ebc_push_rows_lazy(const float* arena, int32_t E, const int32_t* rows, co
                           int64_t capacity, void* const* dst_table, int64_t n_per_rank, int64_t n0, int32_t K0, int32_t K1, int64_t ld0,
                           int64_t ld1, int64_t col0_0, int64_t col0_1, const int32_t* d_colmap0, const int32_t* d_colmap1,
                           int32_t out_dtype, const tt_lazy_ctx* d_lazy, int32_t upto_offset, tt_stream_t stream);
+/* Multi-hot bags (pooling factor L, BASELINE configs[4]) over row-wise shards: every id-slot of a rank is slot = bag * L + l; the
+ * routing entry points take the (key, position) pairs as K * L pseudo-keys. The OWNER pre-pools its ids of a bag and stores one
+ * fp32 partial per (owner, bag) into the requester's peer-mapped partial buffer f32 [world][n_bags][E] (which the requester zeroes
+ * at the start of the step, tt_zero_bytes: owners without an id of a bag write nothing); the REQUESTER sums the W partials in rank
+ * order into its concat buffers (column of bag (b, k): d_colmap[k]). The gradient return is tt_ebc_backward_adam with the pseudo-
+ * key column maps: every id of a bag pulls the bag's pooled gradient. */
+int tt_ebc_push_pooled(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
+                       int64_t capacity, void* const* part_table, int64_t n_per_rank, int32_t L, int64_t n_bags, int32_t me,
+                       tt_stream_t stream);
+int tt_ebc_sum_partials(const float* part, int32_t world, int64_t n_bags, int32_t E, void* c0, int64_t ld0, const int32_t* d_colmap0,
+                        int64_t n0_bags, int32_t K0, void* c1, int64_t ld1, const int32_t* d_colmap1, int32_t K1, int32_t out_dtype,
+                        tt_stream_t stream);
+int tt_zero_bytes(void* p, int64_t bytes, tt_stream_t stream);
 
 /* Dense-parameter Adam over a flat fp32 buffer (tower Linear/BatchNorm weights), same update rule.
  * Replaces torch.optim.Adam.step for the non-embedding parameters (scripts/train.py:327). */

@@ -286,34 +286,124 @@ push_rows_kernel(const float* __restrict__ arena, int E, int G, const int32_t* _
   const int lane = threadIdx.x % G;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
   const int vec_per_row = E >> 2;
-  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; e < n; e += groups_total) {
-    const int32_t row = rows_c[e];
-    int64_t g = slots_c[e];
-    const int r = (int)(g / n_per_rank);
-    g -= (int64_t)r * n_per_rank;
-    OutT* dst;
-    if (g < n0) {
-      const int b = (int)(g / K0), k = (int)(g - (int64_t)b * K0);
-      dst = reinterpret_cast<OutT*>(dst_table[2 * r]) + (int64_t)b * ld0 + (cmap0 ? (int64_t)cmap0[k] : col0_0 + (int64_t)k * E);
-    } else {
-      g -= n0;
-      const int b = (int)(g / K1), k = (int)(g - (int64_t)b * K1);
-      dst = reinterpret_cast<OutT*>(dst_table[2 * r + 1]) + (int64_t)b * ld1 + (cmap1 ? (int64_t)cmap1[k] : col0_1 + (int64_t)k * E);
-    }
-    long long lag_from = -1;
-    if (lazy) {
-      const long long last = L.row_last[row];
-      if (last < upto) lag_from = last + 1;
+  // PR_ROWS owned ids per lane group and iteration: their (row, slot) pairs, then all row loads, are issued before the first store
+  // (the kernel is a random 128-byte gather: latency-bound with one row in flight per group)
+  constexpr int PR_ROWS = 4;
+  for (int64_t e0 = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; e0 < n; e0 += PR_ROWS * groups_total) {
+    int32_t row[PR_ROWS];
+    OutT* dst[PR_ROWS];
+    long long lag_from[PR_ROWS];
+#pragma unroll
+    for (int u = 0; u < PR_ROWS; ++u) {
+      const int64_t e = e0 + (int64_t)u * groups_total;
+      row[u] = -1;
+      dst[u] = nullptr;
+      lag_from[u] = -1;
+      if (e < n) {
+        row[u] = __ldg(rows_c + e);
+        int64_t g = __ldg(slots_c + e);
+        const int r = (int)(g / n_per_rank);
+        g -= (int64_t)r * n_per_rank;
+        if (g < n0) {
+          const int b = (int)(g / K0), k = (int)(g - (int64_t)b * K0);
+          dst[u] = reinterpret_cast<OutT*>(dst_table[2 * r]) + (int64_t)b * ld0 + (cmap0 ? (int64_t)cmap0[k] : col0_0 + (int64_t)k * E);
+        } else {
+          g -= n0;
+          const int b = (int)(g / K1), k = (int)(g - (int64_t)b * K1);
+          dst[u] = reinterpret_cast<OutT*>(dst_table[2 * r + 1]) + (int64_t)b * ld1 + (cmap1 ? (int64_t)cmap1[k] : col0_1 + (int64_t)k * E);
+        }
+        if (lazy) {
+          const long long last = L.row_last[row[u]];
+          if (last < upto) lag_from[u] = last + 1;
+        }
+      }
     }
     for (int c = lane; c < vec_per_row; c += G) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(arena + (int64_t)row * E) + c);
-      if (lag_from >= 0) {
-        float4 mm = *(reinterpret_cast<const float4*>(L.arena_m + (int64_t)row * E) + c);
-        float4 vv = *(reinterpret_cast<const float4*>(L.arena_v + (int64_t)row * E) + c);
-        lazy_replay_vec4(v, mm, vv, lag_from, upto, L, lh);
+      float4 v[PR_ROWS];
+#pragma unroll
+      for (int u = 0; u < PR_ROWS; ++u)
+        if (row[u] >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(arena + (int64_t)row[u] * E) + c);
+#pragma unroll
+      for (int u = 0; u < PR_ROWS; ++u) {
+        if (row[u] < 0) continue;
+        if (lag_from[u] >= 0) {
+          float4 mm = *(reinterpret_cast<const float4*>(L.arena_m + (int64_t)row[u] * E) + c);
+          float4 vv = *(reinterpret_cast<const float4*>(L.arena_v + (int64_t)row[u] * E) + c);
+          lazy_replay_vec4(v[u], mm, vv, lag_from[u], upto, L, lh);
+        }
+        if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(dst[u] + 4 * c) = v[u];
+        else *reinterpret_cast<uint2*>(dst[u] + 4 * c) = pack_bf16x4(v[u]);
       }
-      if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(dst + 4 * c) = v;
-      else *reinterpret_cast<uint2*>(dst + 4 * c) = pack_bf16x4(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Multi-hot bags across shards (BASELINE configs[4]: pooling factor L). A bag's L ids live on up to W owners; each owner pre-pools
+// ITS ids of the bag and sends one partial sum per (bag, owner) instead of up to L rows ("owners pre-pool their part
+// of each bag": the reduce-scatter pattern). The owned entries arrive in global slot order (sender-major, slot order inside), and
+// the L id-slots of a bag are consecutive, so a bag's entries at one owner are one run of the list.
+//   push_pooled_kernel   one lane group per owned entry; run heads sum their run (ascending slot order) and store the fp32 partial
+//                        into the requester's partial buffer [owner][bag][E] over NVLink peer memory
+//   sum_partials_kernel  requester: bag = sum over the W owners in rank order (fixed order: deterministic) -> concat buffer
+// The backward needs nothing new: every id of a bag pulls the bag's pooled gradient through its slot (GradSrc with one column-map
+// entry per (key, position) pseudo-key).
+__global__ void __launch_bounds__(256)
+push_pooled_kernel(const float* __restrict__ arena, int E, int G, const int32_t* __restrict__ rows_c, const int32_t* __restrict__ slots_c,
+                   const int32_t* __restrict__ n_owned, float* const* __restrict__ part_table, int64_t n_per_rank, int L, int64_t n_bags,
+                   int me) {
+  const int n = *n_owned;
+  const int lane = threadIdx.x % G;
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
+  const int vec_per_row = E >> 2;
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; e < n; e += groups_total) {
+    const int32_t slot = __ldg(slots_c + e);
+    const int32_t bag = slot / L;  // global bag index: n_per_rank is a multiple of L
+    if (e > 0 && __ldg(slots_c + e - 1) / L == bag) continue;  // not the head of its run
+    int64_t x = e + 1;
+    while (x < n && x - e < L && __ldg(slots_c + x) / L == bag) ++x;
+    const int r = (int)(slot / n_per_rank);
+    const int64_t local_bag = (int64_t)bag - (int64_t)r * (n_per_rank / L);
+    float* dst = part_table[r] + ((int64_t)me * n_bags + local_bag) * E;
+    for (int c = lane; c < vec_per_row; c += G) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t i = e; i < x; i += 4) {  // up to four rows of the run in flight
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i + u < x) v[u] = __ldg(reinterpret_cast<const float4*>(arena + (int64_t)__ldg(rows_c + i + u) * E) + c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i + u < x) f4_add(acc, v[u]);
+      }
+      *reinterpret_cast<float4*>(dst + 4 * c) = acc;
+    }
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const float* __restrict__ part, int world, int64_t n_bags, int E, int G, OutT* __restrict__ c0, int64_t ld0,
+                    const int32_t* __restrict__ cmap0, int64_t n0_bags, int K0, OutT* __restrict__ c1, int64_t ld1,
+                    const int32_t* __restrict__ cmap1, int K1) {
+  const int lane = threadIdx.x % G;
+  const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
+  const int vec_per_row = E >> 2;
+  for (int64_t j = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; j < n_bags; j += groups_total) {
+    OutT* dst;
+    if (j < n0_bags) {
+      const int b = (int)(j / K0), k = (int)(j - (int64_t)b * K0);
+      dst = c0 + (int64_t)b * ld0 + cmap0[k];
+    } else {
+      const int64_t jj = j - n0_bags;
+      const int b = (int)(jj / K1), k = (int)(jj - (int64_t)b * K1);
+      dst = c1 + (int64_t)b * ld1 + cmap1[k];
+    }
+    for (int c = lane; c < vec_per_row; c += G) {
+      float4 acc = *reinterpret_cast<const float4*>(part + j * E + 4 * c);
+      for (int w = 1; w < world; ++w) f4_add(acc, *reinterpret_cast<const float4*>(part + ((int64_t)w * n_bags + j) * E + 4 * c));
+      if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(dst + 4 * c) = acc;
+      else *reinterpret_cast<uint2*>(dst + 4 * c) = pack_bf16x4(acc);
     }
   }
 }
@@ -407,6 +497,50 @@ int tt_shard_a2a_compact(const int32_t* recv_rows, const int32_t* recv_slots, co
   a2a_compact_kernel<<<(int)(want > cap ? cap : want), 256, 0, (cudaStream_t)stream>>>(recv_rows, recv_slots, recv_counts, world, n_per_rank,
                                                                                        rows_out, slots_out, d_n_owned);
   TT_LAUNCH_CHECK("a2a_compact_kernel");
+  return TT_OK;
+}
+
+int tt_ebc_push_pooled(const float* arena, int32_t E, const int32_t* rows, const int32_t* slots, const int32_t* d_n_owned,
+                       int64_t capacity, void* const* part_table, int64_t n_per_rank, int32_t L, int64_t n_bags, int32_t me,
+                       tt_stream_t stream) {
+  TT_CHECK_ARG(arena && rows && slots && d_n_owned && part_table && E > 0 && (E % 4) == 0 && L > 0 && n_bags > 0 && n_per_rank == n_bags * L,
+               "tt_ebc_push_pooled: bad arguments");
+  int g = 1;
+  while (g < (E >> 2) && g < 32) g <<= 1;
+  int64_t want = ceil_div(capacity, 256 / g);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  push_pooled_kernel<<<(int)(want < 1 ? 1 : (want > cap ? cap : want)), 256, 0, (cudaStream_t)stream>>>(
+      arena, E, g, rows, slots, d_n_owned, (float* const*)part_table, n_per_rank, L, n_bags, me);
+  TT_LAUNCH_CHECK("push_pooled_kernel");
+  return TT_OK;
+}
+
+int tt_ebc_sum_partials(const float* part, int32_t world, int64_t n_bags, int32_t E, void* c0, int64_t ld0, const int32_t* d_colmap0,
+                        int64_t n0_bags, int32_t K0, void* c1, int64_t ld1, const int32_t* d_colmap1, int32_t K1, int32_t out_dtype,
+                        tt_stream_t stream) {
+  TT_CHECK_ARG(part && world > 0 && n_bags > 0 && E > 0 && (E % 4) == 0 && c0 && d_colmap0 && K0 > 0 && n0_bags >= 0 && n0_bags <= n_bags,
+               "tt_ebc_sum_partials: bad arguments");
+  TT_CHECK_ARG(n0_bags == n_bags || (c1 && d_colmap1 && K1 > 0), "tt_ebc_sum_partials: second tower missing");
+  TT_CHECK_ARG(out_dtype == TT_F32 || out_dtype == TT_BF16, "tt_ebc_sum_partials: bad dtype");
+  int g = 1;
+  while (g < (E >> 2) && g < 32) g <<= 1;
+  int64_t want = ceil_div(n_bags, 256 / g);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  const int grid = (int)(want > cap ? cap : want);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_dtype == TT_F32)
+    sum_partials_kernel<float><<<grid, 256, 0, s>>>(part, world, n_bags, E, g, (float*)c0, ld0, d_colmap0, n0_bags, K0, (float*)c1, ld1,
+                                                    d_colmap1, K1 > 0 ? K1 : 1);
+  else
+    sum_partials_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(part, world, n_bags, E, g, (__nv_bfloat16*)c0, ld0, d_colmap0, n0_bags, K0,
+                                                            (__nv_bfloat16*)c1, ld1, d_colmap1, K1 > 0 ? K1 : 1);
+  TT_LAUNCH_CHECK("sum_partials_kernel");
+  return TT_OK;
+}
+
+int tt_zero_bytes(void* p, int64_t bytes, tt_stream_t stream) {
+  TT_CHECK_ARG(p && bytes >= 0, "tt_zero_bytes: bad arguments");
+  TT_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
   return TT_OK;
 }
 

@@ -186,19 +186,34 @@ class DistributedEngine(TwoTowerEngine):
     all-reduce; large tables are sharded row-wise and exchanged over peer memory."""
 
     def __init__(self, cfg: TwoTowerConfig, device, comm, optimizer_mode: str = "dense_exact", value_layout: str = "sample_major",
-                 dtype: str = "fp32", small_tables: bool = True):
+                 dtype: str = "fp32", small_tables: bool = True, bag_len: int = 1):
         self.comm = comm
         self.world, self.rank = comm.world, comm.rank
         self.full_cfg = cfg
+        # Multi-hot bags (BASELINE configs[4]): every (sample, key) bag holds exactly `bag_len` ids, values [B, K, L] flattened
+        # sample-major; sum pooling (TorchRec EBC semantics; the reference's bags hold one id, unified_bid_data_loader.py:835).
+        # Owners pre-pool their ids of a bag; all tables go through the sharded path.
+        if bag_len > 1:
+            if optimizer_mode == "lazy_exact" or value_layout != "sample_major":
+                raise ValueError("bag_len > 1 supports optimizer_mode 'dense_exact' / 'sparse' and the sample-major value layout")
+            small_tables = False
         super().__init__(cfg, device, optimizer_mode, value_layout, dtype, small_tables)
+        self.bag_len = int(bag_len)
         dev = self.device
         # large keys in slot order (notice large keys, then company large keys) and their shard map
         self.large_keys = [[k for k in range(self.K[t]) if not self.is_small[t][k]] for t in range(2)]
         lv = [cfg.tower(t)[2][k] for t in range(2) for k in self.large_keys[t]]
         self.plan = ShardPlan(lv if lv else [1], self.world)
-        self.block = torch.tensor(self.plan.block, dtype=torch.int32, device=dev)
-        self.local_base = torch.tensor(self.plan.local_base, dtype=torch.int32, device=dev)
-        self.d_large_keys = [torch.tensor(k if k else [0], dtype=torch.int32, device=dev) for k in self.large_keys]
+        L = self.bag_len
+        rep = lambda xs: [x for x in xs for _ in range(L)]
+        # routing sees one pseudo-key per (key, position in the bag): slot = b * (KL * L) + kl * L + l
+        self.block = torch.tensor(rep(self.plan.block), dtype=torch.int32, device=dev)
+        self.local_base = torch.tensor(rep(self.plan.local_base), dtype=torch.int32, device=dev)
+        self.d_large_keys = [torch.tensor([k * L + l for k in ks for l in range(L)] if ks else [0], dtype=torch.int32, device=dev)
+                             for ks in self.large_keys]
+        self.KLp = (self.KL[0] * L, self.KL[1] * L)
+        self.vocab_p = torch.tensor(rep(self.vocab.tolist()), dtype=torch.int32, device=dev)
+        self.colmap_p = [torch.tensor(rep(c.tolist()), dtype=torch.int32, device=dev) for c in self.colmap]
         # the local mixed lookup serves the replicated small tables only: large keys are marked "skip" (vocab 0)
         vf = self.vocab.clone()
         off = 0
@@ -281,7 +296,7 @@ class DistributedEngine(TwoTowerEngine):
         ws.peer_buf = buf
         ws.c_table = torch.tensor([p + offs[t] for p in peer for t in range(2)], dtype=torch.int64, device=dev)
         ws.dc_table = torch.tensor([p + offs[2 + t] for p in peer for t in range(2)], dtype=torch.int64, device=dev)
-        n_l = B * (self.KL[0] + self.KL[1])
+        n_l = B * (self.KLp[0] + self.KLp[1])
         cap = max(n_l * W, 1)
         i32 = dict(dtype=torch.int32, device=dev)
         ws.ids_local = torch.zeros(max(n_l + 3, 4) // 4 * 4, **i32)[:max(n_l, 1)]
@@ -294,8 +309,14 @@ class DistributedEngine(TwoTowerEngine):
         q = self.lib.query
         ws.shard_ws = torch.empty(q("tt_shard_workspace_bytes", cap), dtype=torch.uint8, device=dev)
         # all-to-all id routing: receive buffers [W senders][n_l] for (local row, global slot) + the W segment lengths, peer-mapped
+        ws.part = None
+        if self.bag_len > 1:  # per-(owner, bag) partial sums land here (peer-mapped): f32 [W][n_bags][E]
+            n_bags = B * (self.KL[0] + self.KL[1])
+            pbuf, ppeer = self.comm.peer_buffer(W * n_bags * E * 4, dev)
+            ws.part = pbuf
+            ws.part_table = torch.tensor(ppeer, dtype=torch.int64, device=dev)
         ws.a2a = None
-        if n_l > 0 and os.environ.get("TT_A2A", "1") != "0":
+        if n_l > 0 and (os.environ.get("TT_A2A", "1") != "0" or self.bag_len > 1):
             seg = _a256(cap * 4)
             abuf, apeer = self.comm.peer_buffer(2 * seg + 256, dev)
             abuf.zero_()
@@ -358,7 +379,8 @@ class DistributedEngine(TwoTowerEngine):
         E, B, s = self.cfg.emb_dim, ws.B, self._stream()
         H0 = self.cfg.hidden[0]
         K0, K1 = self.K
-        KL0, KL1 = self.KL
+        KL0, KL1 = self.KLp  # (key, position) pseudo-keys: == the large keys when bags hold one id
+        L = self.bag_len
         n0, n_l = B * KL0, B * (KL0 + KL1)
         if values[0] is None or values[1] is None:
             raise NotImplementedError("the sharded lookup serves both towers in one exchange; call the train task, not a single tower")
@@ -381,10 +403,12 @@ class DistributedEngine(TwoTowerEngine):
         if n_l == 0:
             return
         # sharded large tables: clamp -> all-gather ids -> owned-id compaction -> fused lookup + push over peer memory
-        self._call("tt_ebc_clamp_ids_subset", ptr(values[0]), ptr(self.vocab), ptr(self.d_large_keys[0]), B, K0, KL0, layout,
+        if ws.part is not None:  # owners only write the (owner, bag) partials they have: everything else must read as zero
+            self._call("tt_zero_bytes", ptr(ws.part), ws.part.numel(), s)
+        self._call("tt_ebc_clamp_ids_subset", ptr(values[0]), ptr(self.vocab_p), ptr(self.d_large_keys[0]), B, K0 * L, KL0, layout,
                    ptr(ws.ids_local), s)
-        self._call("tt_ebc_clamp_ids_subset", ptr(values[1]), self.vocab.data_ptr() + 4 * K0, ptr(self.d_large_keys[1]), B, K1, KL1,
-                   layout, ws.ids_local.data_ptr() + 4 * n0, s)
+        self._call("tt_ebc_clamp_ids_subset", ptr(values[1]), self.vocab_p.data_ptr() + 4 * K0 * L, ptr(self.d_large_keys[1]), B, K1 * L,
+                   KL1, layout, ws.ids_local.data_ptr() + 4 * n0, s)
         if ws.a2a is not None:
             # all-to-all: bucket my ids by owner, push (local row, slot) into the owners' receive buffers over NVLink, barrier, pack
             a = ws.a2a
@@ -405,6 +429,21 @@ class DistributedEngine(TwoTowerEngine):
             self._call("tt_shard_select_owned", ptr(ws.ids_all), ptr(self.block), ptr(self.local_base), n_l, n0, max(KL0, 1), KL1,
                        self.world, self.rank, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), ptr(ws.shard_ws), ws.shard_ws.numel(), s,
                        n_kernels=3)
+        if L > 1:
+            # owners pre-pool their ids of every bag and store one partial per (owner, bag) at the requester; after the barrier the
+            # requester folds the W partials in rank order into its concat buffers
+            n_bags = B * (self.KL[0] + self.KL[1])
+            self._call("tt_ebc_push_pooled", ptr(self.arena), E, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), n_l * self.world,
+                       ptr(ws.part_table), n_l, L, n_bags, self.rank, s)
+            if self.peer_sites is not None:
+                self._peer_allreduce(self._peer_dummy, 1, "barrier")
+            else:
+                self.comm.barrier(self.device)
+            self._call("tt_ebc_sum_partials", ptr(ws.part), self.world, n_bags, E, ptr(ws.c[0]), H0 + K0 * E, ptr(self.colmap[0]),
+                       B * self.KL[0], max(self.KL[0], 1), ptr(ws.c[1]), H0 + K1 * E, ptr(self.colmap[1]), self.KL[1], self.act, s)
+            if par:
+                cur.wait_stream(small_stream)
+            return
         if self.lazy:  # lazy exact-replay Adam: the owner catches a row up (read-only) before it sends it
             self._call("tt_ebc_push_rows_lazy", ptr(self.arena), E, ptr(ws.rows), ptr(ws.slots), ptr(ws.n_owned), n_l * self.world,
                        ptr(ws.c_table), n_l, n0, max(KL0, 1), KL1, H0 + K0 * E, H0 + K1 * E, H0, H0, ptr(self.colmap[0]),
@@ -580,7 +619,7 @@ class DistributedEngine(TwoTowerEngine):
 
     def embedding_sort(self, ws: _Ws):
         B, s = ws.B, self._stream()
-        n_l = B * (self.KL[0] + self.KL[1])
+        n_l = B * (self.KLp[0] + self.KLp[1])
         if n_l == 0 or self.total_rows == 0:
             return
         cap = n_l * self.world
@@ -593,7 +632,7 @@ class DistributedEngine(TwoTowerEngine):
     def embedding_backward(self, ws: _Ws, apply_adam: bool, want_dense_grad: bool, sorted_already: bool = False):
         cfg, E, B, s = self.cfg, self.cfg.emb_dim, ws.B, self._stream()
         K0, K1 = self.K
-        KL0, KL1 = self.KL
+        KL0, KL1 = self.KLp
         n0, n_l = B * KL0, B * (KL0 + KL1)
         if n_l == 0 or self.total_rows == 0:
             return
@@ -619,7 +658,7 @@ class DistributedEngine(TwoTowerEngine):
                    ptr(self.row_stamp), 0, ptr(self.stamp), 0, H0 + K0 * E, H0, max(KL0, 1), n0, 0, H0 + K1 * E, H0, max(KL1, 1),
                    n_l - n0, self.act, ptr(ws.piece_ws), ws.piece_ws.numel(), ptr(self.hyper),
                    self._table_mode(ws, apply_adam), ptr(ws.n_owned), ptr(ws.dc_table), n_l,
-                   ptr(self.colmap[0]), ptr(self.colmap[1]), s, n_kernels=2)
+                   ptr(self.colmap_p[0]), ptr(self.colmap_p[1]), s, n_kernels=2)
 
     def similarity_matrix(self, ws: _Ws) -> torch.Tensor:
         """This rank's rows of the global logits: [B_l, B_g]."""
@@ -673,7 +712,8 @@ class DistributedEngine(TwoTowerEngine):
 
 
 def create_distributed_train_task(notice_keys, company_keys, schema: dict, model: dict, device, comm=None, dtype: str = "bf16",
-                                  optimizer_mode: str = "dense_exact", seed_full_init: bool = True, small_tables: bool = True):
+                                  optimizer_mode: str = "dense_exact", seed_full_init: bool = True, small_tables: bool = True,
+                                  bag_len: int = 1):
     """Build the façade on a DistributedEngine. `schema` = {"notice": [[key, vocab], ...], "company": [...]};
     `model` has emb_dim / notice_dense / company_dense / hidden / final_dim / dropout / temperature.
     With seed_full_init every rank draws the full tables with the current torch RNG (same on every rank) and keeps its
@@ -687,7 +727,7 @@ def create_distributed_train_task(notice_keys, company_keys, schema: dict, model
     cfg = TwoTowerConfig(list(notice_keys), list(company_keys), nv, cv, model["emb_dim"], model["notice_dense"],
                          model["company_dense"], list(model["hidden"]), model["final_dim"], model.get("dropout", 0.0),
                          model.get("temperature", 1.0), model.get("label_smoothing", 0.0))
-    eng = DistributedEngine(cfg, device, comm, optimizer_mode, "sample_major", dtype, small_tables)
+    eng = DistributedEngine(cfg, device, comm, optimizer_mode, "sample_major", dtype, small_tables, bag_len)
     # same RNG consumption order as the single-GPU factory: all notice tables, notice dense layers, then company
     full = []
     E = cfg.emb_dim

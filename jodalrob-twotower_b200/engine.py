@@ -629,8 +629,8 @@ class TwoTowerEngine:
         self._check_inputs(0, notice_dense, notice_values, B)
         self._check_inputs(1, company_dense, company_values, B)
         for t, v in ((0, notice_values), (1, company_values)):
-            if v.numel() != B * self.K[t]:
-                raise ValueError(f"kjt values hold {v.numel()} ids, expected B*K = {B * self.K[t]}")
+            if v.numel() != B * self.K[t] * getattr(self, "bag_len", 1):
+                raise ValueError(f"kjt values hold {v.numel()} ids, expected B*K = {B * self.K[t] * getattr(self, 'bag_len', 1)}")
         lay = TT_LAYOUT_KEY_MAJOR if (layout or self.default_layout) == "key_major" else TT_LAYOUT_SAMPLE_MAJOR
         ws = self.workspace(B)
         ws.inputs = (notice_dense.contiguous(), company_dense.contiguous())
