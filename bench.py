@@ -322,13 +322,16 @@ def run_cfg3(args):
     import jodalrob_twotower_b200 as tt
     from jodalrob_twotower_b200 import dist as ttdist
     base = load_schema()
-    V = int(args.rows_per_table)
+    cfg5 = args.config == "cfg5"
+    L = 20 if cfg5 else 1
+    model = dict(MODEL, emb_dim=64 if cfg5 else MODEL["emb_dim"])
+    V = int(args.rows_per_table) if args.rows_per_table else (500_000_000 // 38 if cfg5 else 10_000_000)
     schema = {"notice": [[k, V] for k, _ in base["notice"]], "company": [[k, V] for k, _ in base["company"]]}
     nk, ck = [k for k, _ in schema["notice"]], [k for k, _ in schema["company"]]
-    B, E, K = args.batch, MODEL["emb_dim"], len(nk) + len(ck)
+    B, E, K = args.batch, model["emb_dim"], len(nk) + len(ck)
     torch.manual_seed(0)
-    task = ttdist.create_distributed_train_task(nk, ck, schema, MODEL, dev, dtype=args.dtype, optimizer_mode=args.optimizer,
-                                                seed_full_init=False)
+    task = ttdist.create_distributed_train_task(nk, ck, schema, model, dev, dtype=args.dtype, optimizer_mode=args.optimizer,
+                                                seed_full_init=False, bag_len=L)
     tt.FusedAdam(task, lr=MODEL["lr"], weight_decay=MODEL["weight_decay"], warmup_steps=0)
     task.train()
     eng = task.engine
@@ -337,8 +340,8 @@ def run_cfg3(args):
     mk = lambda keys, v: tt.KeyedJaggedTensor(keys, v)
 
     def batch():
-        nid = torch.stack([zipf_ids(B, V, args.zipf, gen, dev) for _ in nk], 1).reshape(-1)
-        cid = torch.stack([zipf_ids(B, V, args.zipf, gen, dev) for _ in ck], 1).reshape(-1)
+        nid = torch.stack([zipf_ids(B * L, V, args.zipf, gen, dev).view(B, L) for _ in nk], 1).reshape(-1)  # [B, K, L] sample-major
+        cid = torch.stack([zipf_ids(B * L, V, args.zipf, gen, dev).view(B, L) for _ in ck], 1).reshape(-1)
         return {"notice": {"dense": torch.randn(B, MODEL["notice_dense"], generator=gen, device=dev), "kjt": mk(nk, nid)},
                 "company": {"dense": torch.randn(B, MODEL["company_dense"], generator=gen, device=dev), "kjt": mk(ck, cid)}}
 
@@ -414,11 +417,13 @@ def run_cfg3(args):
         _finish(world, dev)
         return
     pk = peaks()
-    n_l = B * K
+    n_l = B * K * L
     n_owned_avg, uniq_avg = float(stats[0]) / world, float(stats[1]) / world
     w_o = 2 if args.dtype == "bf16" else 4
     rows_local = eng.total_rows
     alg = {
+        "push_pooled_kernel": n_owned_avg * (E * 4 + 8) + min(n_owned_avg, world * B * K) * E * 4,  # rows read + (row, slot) + partials pushed
+        "sum_partials_kernel": B * K * E * (4 * world + w_o),                          # W partials read, pooled bag written
         "push_rows_kernel": n_owned_avg * (E * 4 + 8 + E * w_o),                       # row read + (row, slot) + row pushed to the requester
         "ebc_gather_sorted_kernel": n_owned_avg * (E * w_o + 4 + E * 4),               # gradient pulled over NVLink + slot + compacted copy
         "ebc_rows_dense_stream_kernel": rows_local * E * 24 + n_owned_avg * E * 4,     # every row: w, m, v read + written
@@ -434,7 +439,9 @@ def run_cfg3(args):
                 row["frac_hbm"] = round(row["GBps"] / pk["hbm_gbs"], 3)
         kernels.append(row)
     f = (world - 1) / world
-    nvlink = {"id_all_to_all_sent": n_l * 8 * f, "rows_received": n_l * E * w_o * f, "gradients_pulled_by_owner": n_owned_avg * E * w_o * f,
+    nvlink = {"id_all_to_all_sent": n_l * 8 * f,
+              "rows_received": (n_l * E * w_o if L == 1 else min(n_l, world * B * K) * E * 4) * f,  # L > 1: one fp32 partial per (owner, bag)
+              "gradients_pulled_by_owner": n_owned_avg * E * w_o * f,
               "embedding_all_gathers_received": 2 * B * world * MODEL["final_dim"] * 2 * f, "sum_exchanges_received": 2 * B * world * 4 * f,
               "dense_gradient_all_reduce": 2 * eng.P_tot * 4 * f}
     top_tab = next((r for r in kernels if "frac_hbm" in r), None)
@@ -446,9 +453,11 @@ def run_cfg3(args):
     line = {"metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2]: README-default towers on {K} tables x {V:,} rows x E={E} ({K * V * E * 4 / 1e9:.1f} GB of "
-                                   f"fp32 weights, x3 with the Adam moments), row-wise sharded over {world} GPUs, Zipf({args.zipf}) ids "
-                                   f"(scrambled), B={B} per GPU, global negatives",
+            "config": {"workload": f"BASELINE configs[{4 if cfg5 else 2}]: README-default towers on {K} tables x {V:,} rows x E={E} ({K * V * E * 4 / 1e9:.1f} GB of "
+                                   f"fp32 weights, x3 with the Adam moments), row-wise sharded over {world} GPUs, " +
+                                   (f"multi-hot bags of {L} ids (sum pooling, owners pre-pool), " if L > 1 else "") +
+                                   f"Zipf({args.zipf}) ids (scrambled), B={B} per GPU, global negatives",
+                       "ids_per_bag": L,
                        "batch_per_gpu": B, "global_batch": B * world, "rows_per_table": V, "rows_per_gpu": rows_local,
                        "optimizer": args.optimizer, "routing": "all-to-all over NVLink peer memory (sender buckets by owner)",
                        "l2_policy": f"tables of {rows_local * E * 4 / 1e9:.1f} GB per GPU >> 126 MB L2; inputs rotate over {n_rot} batches",
@@ -897,10 +906,11 @@ def main():
     ap.add_argument("--tables-only", nargs="?", const="full", default=None, choices=["full", "quick"])
     ap.add_argument("--no-device-store", action="store_true", help="skip the end-to-end loop with HBM-resident feature stores")
     ap.add_argument("--no-tables", action="store_true", help="skip the large-table (HBM-bound lookup/update) section")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"],
-                    help="cfg2 (default): BASELINE configs[1], the headline line. cfg3: BASELINE configs[2], 10 M-row tables sharded over the ranks "
-                         "(run under torchrun; --optimizer lazy_exact / dense_exact / sparse)")
-    ap.add_argument("--rows-per-table", type=int, default=10_000_000)
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
+                    help="cfg2 (default): BASELINE configs[1], the headline line. cfg3: BASELINE configs[2], 38 x 10 M-row tables sharded over the "
+                         "ranks. cfg5: BASELINE configs[4], 500 M rows x E=64 over the ranks, bags of 20 ids (both under torchrun; "
+                         "--optimizer lazy_exact / dense_exact / sparse)")
+    ap.add_argument("--rows-per-table", type=int, default=0, help="cfg3 / cfg5: override the table size (default 10 M / 500 M / 38)")
     ap.add_argument("--zipf", type=float, default=1.05)
     args = ap.parse_args()
     if args.tables_only:  # development aid: only the large-table section (not the contract line)
@@ -908,7 +918,7 @@ def main():
         print(json.dumps({"tables": tables_section(torch.device("cuda", 0), peaks(), quick=args.tables_only == "quick")}), flush=True)
     elif args.impl == "reference":
         run_reference(args)
-    elif args.config == "cfg3":
+    elif args.config in ("cfg3", "cfg5"):
         run_cfg3(args)
     else:
         run_ours(args)

@@ -286,9 +286,9 @@ push_rows_kernel(const float* __restrict__ arena, int E, int G, const int32_t* _
   const int lane = threadIdx.x % G;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
   const int vec_per_row = E >> 2;
-  // PR_ROWS owned ids per lane group and iteration: their (row, slot) pairs, then all row loads, are issued before the first store
-  // (the kernel is a random 128-byte gather: latency-bound with one row in flight per group)
-  constexpr int PR_ROWS = 4;
+  // PR_ROWS owned ids per lane group and iteration. Measured at the config-3 shard (311 k owned ids, 10 M-row tables, N = 2): four
+  // rows in flight per group 121 us (89 registers, two CTAs per SM), one row 75 us — occupancy beats per-thread batching here
+  constexpr int PR_ROWS = 1;
   for (int64_t e0 = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; e0 < n; e0 += PR_ROWS * groups_total) {
     int32_t row[PR_ROWS];
     OutT* dst[PR_ROWS];
