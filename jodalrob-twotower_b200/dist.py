@@ -319,7 +319,8 @@ class DistributedEngine(TwoTowerEngine):
         if n_l > 0 and (os.environ.get("TT_A2A", "1") != "0" or self.bag_len > 1):
             seg = _a256(cap * 4)
             abuf, apeer = self.comm.peer_buffer(2 * seg + 256, dev)
-            abuf.zero_()
+            # NOT zeroed here: every segment length is written by its sender before the owner reads it, and a local memset with no
+            # cross-rank barrier behind it could wipe what a faster peer has already pushed for the first step
             ws.a2a_buf = abuf
             ws.a2a = dict(rows=abuf[:cap * 4].view(torch.int32), slots=abuf[seg:seg + cap * 4].view(torch.int32),
                           counts=abuf[2 * seg:2 * seg + 4 * W].view(torch.int32),

@@ -784,7 +784,8 @@ def _run_sharded(case, world):
     return d, cfg, results
 
 
-@pytest.mark.parametrize("case,world", [("base", 1), ("oob_temp", 1), ("base", 2), ("oob_temp", 2), ("deep_ls", 4), ("nohidden", 3)])
+@pytest.mark.parametrize("case,world", [("base", 1), ("oob_temp", 1), ("base", 2), ("oob_temp", 2), ("deep_ls", 4), ("nohidden", 3),
+                                        ("deep_ls", 8), ("base", 8), ("deep_ls", 12)])
 def test_sharded_multirank_step_matches_single_device_reference(case, world):
     d, cfg, results = _run_sharded(case, world)
     fin = sd_from(d, "final.")
