@@ -36,9 +36,36 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// ---- programmatic dependent launch (PDL): kernels of one stream's dependency chain are launched with the
+// programmatic-stream-serialization attribute; each of them waits for its predecessor with griddepcontrol.wait AFTER its own set-up
+// (barrier init, TMEM allocation) and lets its successor be scheduled early with griddepcontrol.launch_dependents. The predecessor's
+// drain + the launch latency (2-3 us per kernel boundary of the latency-bound step) then overlap the successor's prologue.
+// Rule: a kernel launched through launch_pdl MUST execute pdl_wait() before it touches global memory (completion is transitive
+// along the chain only if every link waits). Measured slower on the multi-stream step (see pdl_enabled): off unless TT_PDL=1 — the
+// kernels are then launched as ordinary kernels and the two instructions are no-ops.
+bool pdl_enabled();
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

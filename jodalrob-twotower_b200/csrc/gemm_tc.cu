@@ -74,6 +74,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
+  pdl_wait();  // programmatic dependent launch: the set-up above overlapped the predecessor's tail
+  pdl_launch_dependents();
 
   if (warp == 5) {
     int st = 0;
@@ -314,7 +316,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmTcParam
   const size_t smem = gt_smem_bytes(p.tn, p.ring);
   TT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_bytes(128, GT_STAGES)));
   dim3 grid(ceil_div(p.M, 128), ceil_div(p.N, p.tn), splits);
-  gemm_tc_kernel<<<grid, GT_THREADS, smem, s>>>(ma, mb, p);
+  TT_CUDA(launch_pdl(gemm_tc_kernel, grid, dim3(GT_THREADS), smem, s, ma, mb, p));
   TT_LAUNCH_CHECK("gemm_tc_kernel");
   return TT_OK;
 }

@@ -261,6 +261,10 @@ simce_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
+  // programmatic dependent launch: everything above (barriers, tensor memory) overlapped the predecessor's tail; its results are
+  // read from here on. The successor may be scheduled as soon as every CTA of this grid has got this far.
+  pdl_wait();
+  pdl_launch_dependents();
   if (p.dbg_ts && threadIdx.x == 0) {
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
@@ -808,6 +812,8 @@ __global__ void tc_ysum_final_kernel(const float* __restrict__ part, int F, floa
 __global__ void __launch_bounds__(256)
 tc_dx_reduce_kernel(const float* __restrict__ part, int64_t n, int n_ct, long long T, int G, int F, const __nv_bfloat16* __restrict__ Y,
                     int64_t diag_offset, float t_off2, float t_dd2, const float* __restrict__ ysum, float* __restrict__ dX) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   const int64_t row = i / F;
@@ -916,7 +922,7 @@ int simce_tc_rows(const void* X, const void* Y, int64_t Bx, int64_t By, int F, f
   const size_t smem = tc_smem_bytes(F, false);
   if (pre) {
     TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<TC_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    simce_tc_kernel<TC_FWD, true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, my, p);
+    TT_CUDA(launch_pdl(simce_tc_kernel<TC_FWD, true>, dim3(pl.grid), dim3(TC_THREADS), smem, s, mx, my, my, p));
     TT_LAUNCH_CHECK("simce_tc_kernel<fwd,pre>");
     return TT_OK;
   }
@@ -1019,6 +1025,8 @@ tc_finish_kernel(const float* __restrict__ row_e, const float* __restrict__ dx_p
                  const __nv_bfloat16* __restrict__ Y, int64_t diag_offset, float t_off2, float t_dd2, const float* __restrict__ ysum,
                  float gscale, float k_shift, float* __restrict__ dX, float* __restrict__ sumexp_out, float* __restrict__ inv_out,
                  const __nv_bfloat16* __restrict__ X_unit, __nv_bfloat16* __restrict__ Xs_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= Bx * F) return;
   const int64_t row = i / F;
@@ -1121,9 +1129,9 @@ int simce_tc_rows_finish(const void* workspace, int64_t Bx, int64_t By, int F, f
                          const void* X_unit, float gscale, void* Xs_out, cudaStream_t s) {
   TcPlan pl = make_plan(Bx, By);
   const float* row_e = (const float*)workspace;
-  tc_finish_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(row_e, nullptr, Bx, pl.n_col_tiles, pl.total_tiles, pl.grid, F, nullptr, 0, 0.f,
-                                                              0.f, nullptr, gscale, expf(-inv_temp), nullptr, row_sumexp, inv_row,
-                                                              (const __nv_bfloat16*)X_unit, (__nv_bfloat16*)Xs_out);
+  TT_CUDA(launch_pdl(tc_finish_kernel, dim3(ceil_div(Bx * F / 4, 256)), dim3(256), 0, s, row_e, (const float*)nullptr, Bx, pl.n_col_tiles,
+                     pl.total_tiles, pl.grid, F, (const __nv_bfloat16*)nullptr, (int64_t)0, 0.f, 0.f, (const float*)nullptr, gscale,
+                     expf(-inv_temp), (float*)nullptr, row_sumexp, inv_row, (const __nv_bfloat16*)X_unit, (__nv_bfloat16*)Xs_out));
   TT_LAUNCH_CHECK("tc_finish_kernel(rows)");
   return TT_OK;
 }
@@ -1160,10 +1168,10 @@ int simce_tc_grad_pre(const void* Xs, const void* Y, const void* Ys, int64_t Bx,
   const size_t smem = tc_smem_bytes(F, true);
   if (inv_x) {
     TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<TC_BWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    simce_tc_kernel<TC_BWD, true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, mys, p);
+    TT_CUDA(launch_pdl(simce_tc_kernel<TC_BWD, true>, dim3(pl.grid), dim3(TC_THREADS), smem, s, mx, my, mys, p));
   } else {
     TT_CUDA(cudaFuncSetAttribute(simce_tc_kernel<TC_BWD_SUMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    simce_tc_kernel<TC_BWD_SUMS, true><<<pl.grid, TC_THREADS, smem, s>>>(mx, my, mys, p);
+    TT_CUDA(launch_pdl(simce_tc_kernel<TC_BWD_SUMS, true>, dim3(pl.grid), dim3(TC_THREADS), smem, s, mx, my, mys, p));
   }
   TT_LAUNCH_CHECK("simce_tc_kernel<bwd,pre>");
   return TT_OK;
@@ -1177,14 +1185,14 @@ int simce_tc_grad_finish(const void* workspace, int64_t Bx, int64_t By, int F, f
   const float t_diag2 = 2.f * gscale * tgt_diag, t_off2 = 2.f * gscale * tgt_off;
   const bool smooth = tgt_off != 0.f;
   if (deferred) {
-    tc_finish_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(w.row_e, w.dx_part, Bx, pl.n_col_tiles, pl.total_tiles, pl.grid, F,
-                                                                (const __nv_bfloat16*)Y, diag_offset, t_off2, t_diag2 - t_off2,
-                                                                smooth ? w.ysum : nullptr, gscale, expf(-inv_temp), dX, sumexp_out,
-                                                                inv_out, (const __nv_bfloat16*)X_unit, (__nv_bfloat16*)Xs_out);
+    TT_CUDA(launch_pdl(tc_finish_kernel, dim3(ceil_div(Bx * F / 4, 256)), dim3(256), 0, s, (const float*)w.row_e, (const float*)w.dx_part, Bx,
+                       pl.n_col_tiles, pl.total_tiles, pl.grid, F, (const __nv_bfloat16*)Y, diag_offset, t_off2, t_diag2 - t_off2,
+                       (const float*)(smooth ? w.ysum : nullptr), gscale, expf(-inv_temp), dX, sumexp_out, inv_out,
+                       (const __nv_bfloat16*)X_unit, (__nv_bfloat16*)Xs_out));
   } else {
-    tc_dx_reduce_kernel<<<ceil_div(Bx * F / 4, 256), 256, 0, s>>>(w.dx_part, Bx * F, pl.n_col_tiles, pl.total_tiles, pl.grid, F,
-                                                                   (const __nv_bfloat16*)Y, diag_offset, t_off2, t_diag2 - t_off2,
-                                                                   smooth ? w.ysum : nullptr, dX);
+    TT_CUDA(launch_pdl(tc_dx_reduce_kernel, dim3(ceil_div(Bx * F / 4, 256)), dim3(256), 0, s, (const float*)w.dx_part, Bx * F, pl.n_col_tiles,
+                       pl.total_tiles, pl.grid, F, (const __nv_bfloat16*)Y, diag_offset, t_off2, t_diag2 - t_off2,
+                       (const float*)(smooth ? w.ysum : nullptr), dX));
   }
   TT_LAUNCH_CHECK("simce_tc_grad_finish");
   return TT_OK;

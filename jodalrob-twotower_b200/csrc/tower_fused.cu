@@ -180,6 +180,8 @@ tower_tail_fwd_kernel(const __grid_constant__ CUtensorMap map_w2, const TailFwdP
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
+  pdl_wait();  // programmatic dependent launch: the set-up above overlapped the predecessor's tail
+  pdl_launch_dependents();
 
   if (warp == 4) {
     if (elect_one_sync()) {
@@ -358,6 +360,8 @@ tower_head_bwd_kernel(const __grid_constant__ CUtensorMap map_w2, const HeadBwdP
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
+  pdl_wait();  // programmatic dependent launch: the set-up above overlapped the predecessor's tail
+  pdl_launch_dependents();
 
   if (warp == 4) {
     // dy[m, k] = sum_n dz[m, n] W2[n, k]: B is MN-major (k contiguous), the F reduction rows of a 64-column block back to back
@@ -569,6 +573,8 @@ tower_mid_bwd_kernel(const __grid_constant__ CUtensorMap map_w1, const MidBwdPar
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sb->tmem_base;
+  pdl_wait();  // programmatic dependent launch: the set-up above overlapped the predecessor's tail
+  pdl_launch_dependents();
 
   if (warp == 5) {
     // ---- weight tiles: W1[:, k0 : k0 + 128] as two MN-major blocks of [H1 rows x 64 columns] (out-of-range columns read as zero)
@@ -817,7 +823,7 @@ int tt_tower_tail_forward(const void* h, int64_t M, int32_t H1, int32_t F, const
   const int NA = H1 / 64;
   const size_t smem = 1024 + (size_t)NA * ATOM_BYTES + (size_t)NA * F * 128 + (2 * H1 + 512) * 8 + 2 * H1 * 4 + sizeof(FusedSmem) + 64;
   TT_CUDA(cudaFuncSetAttribute(tower_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tower_tail_fwd_kernel<<<ceil_div(M, TF_ROWS), TF_THREADS, smem, (cudaStream_t)stream>>>(mw, p);
+  TT_CUDA(launch_pdl(tower_tail_fwd_kernel, dim3(ceil_div(M, TF_ROWS)), dim3(TF_THREADS), smem, (cudaStream_t)stream, mw, p));
   TT_LAUNCH_CHECK("tower_tail_fwd_kernel");
   return TT_OK;
 }
@@ -841,7 +847,7 @@ int tt_tower_head_backward(const float* de, const void* e, const float* nrm, int
   const size_t smem = 1024 + (size_t)(F / 64) * ATOM_BYTES + (size_t)(H1 / 64) * F * 128 + 2 * H1 * 4 + (2 * 128 * 33 + 512) * 4 +
                       sizeof(FusedSmem) + 64;
   TT_CUDA(cudaFuncSetAttribute(tower_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tower_head_bwd_kernel<<<ceil_div(M, TF_ROWS), TF_THREADS, smem, (cudaStream_t)stream>>>(mw, p);
+  TT_CUDA(launch_pdl(tower_head_bwd_kernel, dim3(ceil_div(M, TF_ROWS)), dim3(TF_THREADS), smem, (cudaStream_t)stream, mw, p));
   TT_LAUNCH_CHECK("tower_head_bwd_kernel");
   return TT_OK;
 }
@@ -872,7 +878,7 @@ int tt_tower_mid_backward(const void* dyp, const void* h, int64_t M, int32_t H1,
   int groups = (2 * sm_count()) / row_tiles;
   if (groups < 1) groups = 1;
   if (groups > n_out) groups = n_out;
-  tower_mid_bwd_kernel<<<dim3(row_tiles, groups), TF_MID_THREADS, smem, (cudaStream_t)stream>>>(mw, p);
+  TT_CUDA(launch_pdl(tower_mid_bwd_kernel, dim3(row_tiles, groups), dim3(TF_MID_THREADS), smem, (cudaStream_t)stream, mw, p));
   TT_LAUNCH_CHECK("tower_mid_bwd_kernel");
   return TT_OK;
 }
