@@ -339,8 +339,9 @@ class TwoTowerEngine:
             ws.dy.append([torch.empty(B, h, **act) for h in cfg.hidden[1:]])
             if self.act != TT_F32:
                 if t == 0:
-                    ws.x16, ws.dz16 = [], []
+                    ws.x16, ws.dz16, ws.x16_owned = [], [], []
                 ws.x16.append(torch.empty(B, dense_dim, **act))
+                ws.x16_owned.append(True)
                 ws.dz16.append(torch.empty(B, cfg.final_dim, **act))
             ws.mean.append([torch.empty(h, **f32) for h in cfg.hidden[1:]])
             ws.rstd.append([torch.empty(h, **f32) for h in cfg.hidden[1:]])
@@ -484,12 +485,21 @@ class TwoTowerEngine:
         ld = H0 + len(keys) * cfg.emb_dim
         pre = f"{name}_tower."
         dense = dense.contiguous()
-        if dense.dtype != torch.float32:
-            dense = dense.float()
-        if self.act != TT_F32:
-            if not cast_done:
-                self._call("tt_cast_bf16", ptr(dense), ptr(ws.x16[t]), B * dense_dim, s)
-            dense = ws.x16[t]
+        if self.act != TT_F32 and dense.dtype == torch.bfloat16 and dense.data_ptr() % 16 == 0:
+            # already in the compute dtype (GraphedFusedStep(compact_inputs=True) stages the dense features as bf16: half the bytes
+            # over PCIe, no cast kernel; same bits as the device-side round-to-nearest-even cast): the weight gradient reads it too
+            ws.x16[t] = dense
+            ws.x16_owned[t] = False
+        else:
+            if dense.dtype != torch.float32:
+                dense = dense.float()
+            if self.act != TT_F32:
+                if ws.x16[t].shape != dense.shape or ws.x16[t].data_ptr() == dense.data_ptr() or not ws.x16_owned[t]:
+                    ws.x16[t] = torch.empty(B, dense_dim, dtype=self.act_torch, device=self.device)
+                    ws.x16_owned[t] = True
+                if not cast_done:
+                    self._call("tt_cast_bf16", ptr(dense), ptr(ws.x16[t]), B * dense_dim, s)
+                dense = ws.x16[t]
         self._lin_fwd(dense, dense_dim, pre + "dense_projection.weight", pre + "dense_projection.bias", ws.c[t], ld, False, B, H0,
                       dense_dim, 0)
 

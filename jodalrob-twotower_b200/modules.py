@@ -496,7 +496,10 @@ class GraphedFusedStep:
         for batch in loader: out5 = step(batch)           # [loss, acc, pos_mean, neg_mean, gap] on the device
     """
 
-    def __init__(self, task: "TwoTowerTrainTask", example_batch):
+    def __init__(self, task: "TwoTowerTrainTask", example_batch, compact_inputs: bool = False):
+        """compact_inputs: with a bf16 engine the dense features are staged in bf16 — the engine's first act on them is the
+        round-to-nearest-even cast to bf16 anyway, so the results are bit-identical, the host->device copy halves (12.6 -> 6.3 MB at
+        B = 8192) and the two cast kernels drop out of the step. `pack()` / `load()` convert; the ids stay int64."""
         if task._fused_opt is None:
             raise RuntimeError("attach a FusedAdam(task, ...) before capturing the fused step")
         if task.loss_type != "cross_entropy":
@@ -506,6 +509,9 @@ class GraphedFusedStep:
         task._sync_cfg()
         nd, nv, cd, cv, lay = task._unpack(example_batch)
         self.layout = lay
+        self.compact = bool(compact_inputs and eng.dtype == "bf16")
+        if self.compact:
+            nd, cd = nd.to(torch.bfloat16), cd.to(torch.bfloat16)
         # the four inputs live back to back in ONE buffer, so a pre-packed batch is staged with a single copy
         self._slots, off = [], 0
         for t in (nd, nv, cd, cv):

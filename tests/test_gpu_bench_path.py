@@ -507,3 +507,28 @@ def test_emulated_ranks_multihot_bags_vs_pooled_port(world, L, mode):
                     # momentum in the dense reference — compare the rows the LAST batch touched... (not the reference semantics)
                     continue
                 assert_updated_close(v.cpu(), fin[k], None, 2e-5, name=f"rank{r}.{k}")
+
+
+def test_compact_bf16_inputs_give_the_same_bits():
+    """GraphedFusedStep(compact_inputs=True) stages the dense features as bf16 (half the PCIe bytes, no cast kernels): the engine's
+    first act on fp32 inputs is the same round-to-nearest-even cast, so the trajectory is bit-identical."""
+    import jodalrob_twotower_b200 as tt
+    schema = readme_schema()
+    batches = bench_parity.global_batches(schema, 2048, 4, seed=9)
+    finals = []
+    for compact in (False, True):
+        torch.manual_seed(6)
+        task = _task(tt, schema, "bf16", dropout=0.1)
+        tt.FusedAdam(task, lr=1e-3, weight_decay=1e-5)
+        task.train()
+        step = tt.GraphedFusedStep(task, _batch(tt, schema, batches[0]), compact_inputs=compact)
+        assert step.compact == compact
+        outs = []
+        for i, b in enumerate(batches[1:]):
+            if i % 2:
+                outs.append(step(packed=step.pack(_batch(tt, schema, b, device="cpu"), pin=True).to(DEV)).clone())
+            else:
+                outs.append(step(_batch(tt, schema, b)).clone())
+        finals.append((torch.stack(outs), task.engine.flat_w.clone(), task.engine.flat_v.clone()))
+    for a, b in zip(*finals):
+        assert torch.equal(a, b)
