@@ -404,7 +404,9 @@ class TwoTowerTrainTask(nn.Module):
                 out5, ws = eng.forward(nd, nv, cd, cv, self.training, lay, dropout_masks)
                 res = out5.clone()
                 loss = res[0]
-        if self.debug_pair_check and not hasattr(self, "_pair_check_done"):
+        if self.debug_pair_check and self.training and not hasattr(self, "_pair_check_done"):
+            # the reference runs this once, at its first forward (two_tower_train_task.py:80-83); here it is opt-in
+            # (task.debug_pair_check = True) because it materialises the B x B matrix the train path otherwise never stores
             self._verify_positive_pair_alignment(eng.similarity_matrix(ws))
             self._pair_check_done = True
         if not return_metrics:
@@ -480,11 +482,34 @@ class TwoTowerTrainTask(nn.Module):
             return {"top_similarities": top_sim, "top_indices": top_idx, "all_similarities": s}
 
     def _verify_positive_pair_alignment(self, similarity_matrix: torch.Tensor):
+        """One-time diagnostic of the first train-mode forward (two_tower_train_task.py:80-83, 253-290): is the diagonal really the
+        positive? Top-1 hit rate of the diagonal along rows (notice -> company) and columns (company -> notice), the share of rows
+        whose diagonal IS the row maximum, and the reference's three-way verdict (both hit rates < 0.05: the loader's notice /
+        company order is broken; either < 0.3: too few positives; else fine). The numbers are kept in `self.pair_alignment`."""
         b = similarity_matrix.size(0)
         idx = torch.arange(b, device=similarity_matrix.device)
         row_hit = (similarity_matrix.argmax(dim=1) == idx).float().mean().item()
         col_hit = (similarity_matrix.argmax(dim=0) == idx).float().mean().item()
-        print(f"[Positive Pair Alignment Check] notice->company top-1 {row_hit:.3f}, company->notice top-1 {col_hit:.3f}")
+        diag_is_max = (similarity_matrix.diag() == similarity_matrix.max(dim=1)[0]).float().mean().item()
+        if row_hit < 0.05 and col_hit < 0.05:
+            verdict = "CRITICAL"
+        elif row_hit < 0.3 or col_hit < 0.3:
+            verdict = "WARNING"
+        else:
+            verdict = "OK"
+        self.pair_alignment = {"row_top1": row_hit, "col_top1": col_hit, "diag_is_row_max": diag_is_max, "verdict": verdict}
+        print("[Positive Pair Alignment Check]")
+        print(f"   Notice->Company top-1 accuracy: {row_hit:.3f}")
+        print(f"   Company->Notice top-1 accuracy: {col_hit:.3f}")
+        print(f"   share of rows whose diagonal is the row maximum: {diag_is_max:.3f}")
+        if verdict == "CRITICAL":
+            print("   CRITICAL: positive pairs are not aligned - notice / company order differs in the DataLoader;")
+            print("   build the pairs with one sampler / one index")
+        elif verdict == "WARNING":
+            print("   WARNING: weak positive-pair alignment - check the share of positives per batch")
+        else:
+            print("   positive-pair alignment looks fine")
+        print()
 
 
 class GraphedFusedStep:

@@ -956,3 +956,38 @@ def test_linear_tcgen05_vs_fp64(M, N, K):
     Y2 = torch.zeros(M, N, device=DEV)
     lib.call("tt_linear_forward_bf16", big.data_ptr() + 128, ld, ptr(W), 0, ptr(Y2), N, TT_F32, M, N, K, 0, s)
     assert rel_err(Y2, Xd @ Wd.t()) < 2e-6
+
+
+def test_positive_pair_alignment_report_matches_reference_numbers(capsys):
+    """a19: the one-time pair-alignment diagnostic (two_tower_train_task.py:253-290) — row / column top-1 hit rates of the diagonal,
+    share of rows whose diagonal is the row maximum, and the three-way verdict — against the same quantities computed from the
+    golden similarity matrix of the unmodified reference; and the CRITICAL verdict when the company side is shuffled."""
+    import jodalrob_twotower_b200 as tt
+    d, cfg = load_golden("tiny_base.npz")
+    schema = cfg["schema"]
+    task = make_task(cfg, schema)
+    task.load_state_dict(sd_from(d, "init."))
+    task.train()
+    task.debug_pair_check = True
+    nid, cid, nd, cd = batch_inputs(d, 0)
+    out = task(make_batch(schema, nid, cid, nd, cd), return_metrics=True)
+    printed = capsys.readouterr().out
+    assert "[Positive Pair Alignment Check]" in printed and hasattr(task, "_pair_check_done")
+    S = torch.from_numpy(np.array(d["s0.similarity_matrix"])) if "s0.similarity_matrix" in d else out["similarity_matrix"].cpu()
+    idx = torch.arange(S.shape[0])
+    rep = task.pair_alignment
+    assert abs(rep["row_top1"] - (S.argmax(1) == idx).float().mean().item()) < 1e-6
+    assert abs(rep["col_top1"] - (S.argmax(0) == idx).float().mean().item()) < 1e-6
+    assert abs(rep["diag_is_row_max"] - (S.diag() == S.max(1)[0]).float().mean().item()) < 1e-6
+    assert abs(rep["row_top1"] - out["accuracy"].item()) < 1e-6
+    # runs once
+    task(make_batch(schema, nid, cid, nd, cd))
+    assert "[Positive Pair Alignment Check]" not in capsys.readouterr().out
+    # a trained-looking matrix whose company side is shuffled must be flagged
+    t2 = make_task(cfg, schema)
+    n = 64
+    eye = torch.eye(n, device=DEV) * 5
+    t2._verify_positive_pair_alignment(eye[torch.randperm(n, generator=torch.Generator().manual_seed(1)).to(DEV)])
+    assert t2.pair_alignment["verdict"] == "CRITICAL"
+    t2._verify_positive_pair_alignment(eye)
+    assert t2.pair_alignment["verdict"] == "OK"
