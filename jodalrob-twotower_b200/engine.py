@@ -126,6 +126,9 @@ class TwoTowerEngine:
         # one-kernel update. Measured on B200 at the README-default size: 376 us per step against 361 us unsplit — the extra kernel
         # lands next to the first sim-CE pass, whose persistent CTAs then find SMs occupied — so it is off by default.
         self.split_dense_adam = os.environ.get("TT_SPLIT_ADAM", "0") != "0"
+        # TT_SPLIT_ADAM=2: the untouched-rows half runs behind the logits passes instead, underneath the towers' backward kernels
+        # (64-CTA kernels that leave SMs free), so that only the touched rows are left for the end of the step
+        self.split_late = os.environ.get("TT_SPLIT_ADAM", "0") == "2"
         # TT_HYPER_HELPER=1: optimizer scalars advanced on a helper stream (was a gain with the per-stage tower kernels; with the fused
         # kernels measured 295.1 us per step against 289.6 us with the plain in-order launch) — off
         self.hyper_on_helper = os.environ.get("TT_HYPER_HELPER", "0") != "0"
@@ -197,6 +200,7 @@ class TwoTowerEngine:
         # CTAs are placed before those of the weight-gradient helper streams whenever SMs free up
         import os as _os
         hi = 0 if _os.environ.get("TT_NO_PRIO") else -1
+        self._crit_stream = torch.cuda.Stream(self.device, priority=-1) if _os.environ.get("TT_CRIT_PRIO", "0") == "1" else None
         self._side = torch.cuda.Stream(self.device, priority=hi)
         self._hi0 = torch.cuda.Stream(self.device, priority=hi)
         self._sort_stream = torch.cuda.Stream(self.device)  # the sort has the whole forward + loss to hide under: normal priority
@@ -907,10 +911,13 @@ class TwoTowerEngine:
                    ptr(self.stamp), 0, s, n_kernels=7)
         self._adam_untouched(ws)
 
-    def _adam_untouched(self, ws: _Ws):
+    def _adam_untouched(self, ws: _Ws, late: bool = False):
         """First half of the split exact-dense update (armed by fused_step only): every large-table row without the fresh stamp."""
-        ws.adam_untouched_done = False
-        if not (self._arm_split and self.split_dense_adam and self.adam_mode == TT_ADAM_DENSE_EXACT):
+        if not late:
+            ws.adam_untouched_done = False
+        if not ((self._arm_split or late) and self.split_dense_adam and self.adam_mode == TT_ADAM_DENSE_EXACT):
+            return
+        if self.split_late != late:
             return
         self._call("tt_ebc_backward_adam", ptr(self.arena), ptr(self.arena_m), ptr(self.arena_v), 0, self.total_rows, self.cfg.emb_dim,
                    0, 0, 0, ptr(self.row_begin), ptr(self.row_end), ptr(self.row_stamp), 0, ptr(self.stamp), 0, 0, 0, 1, 0, 0, 0, 0, 1, 0,
@@ -1012,6 +1019,22 @@ class TwoTowerEngine:
     def fused_step(self, notice_dense, notice_values, company_dense, company_values, lr=1e-3, warmup_steps=0,
                    betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, layout=None, masks=None):
         """hyper_advance -> forward -> backward -> sparse-dedup + Adam on tables -> Adam on dense. Returns out5."""
+        if self._crit_stream is not None and self.two_streams and self.profile is None:
+            # the step's critical chain (lookup -> towers -> logits passes -> tower backward) on a HIGH-priority stream: the caller's
+            # stream has the lowest priority there is, i.e. the same as the sort-dedup / weight-gradient helper streams whose CTAs
+            # then compete with the persistent logits kernels for SM slots
+            outer = torch.cuda.current_stream(self.device)
+            self._crit_stream.wait_stream(outer)
+            with torch.cuda.stream(self._crit_stream):
+                out = self._fused_step(notice_dense, notice_values, company_dense, company_values, lr, warmup_steps, betas, eps,
+                                       weight_decay, layout, masks)
+            outer.wait_stream(self._crit_stream)
+            return out
+        return self._fused_step(notice_dense, notice_values, company_dense, company_values, lr, warmup_steps, betas, eps, weight_decay,
+                                layout, masks)
+
+    def _fused_step(self, notice_dense, notice_values, company_dense, company_values, lr, warmup_steps, betas, eps, weight_decay,
+                    layout, masks):
         main = torch.cuda.current_stream(self.device)
         self._hyper_done = None
         if self.two_streams and self.profile is None and self.hyper_on_helper:
@@ -1038,6 +1061,10 @@ class TwoTowerEngine:
             # sort-dedup already ran underneath the forward pass) the large-table segment-sum + Adam, which starts as soon as
             # both concat-buffer gradients exist and overlaps the first-layer weight gradients and the small-table reductions.
             self.loss_backward(ws)
+            if self.split_late and self.total_rows > 0:
+                self._sort_stream.wait_stream(main)
+                with torch.cuda.stream(self._sort_stream):
+                    self._adam_untouched(ws, late=True)
             dm = getattr(ws, "deferred_metrics", None)
             # TT_METRICS_LATE=1 launches them behind both towers' data-gradient chains instead: the tower kernels get faster (head
             # 16.6 -> 12.8 us) but the metrics kernel then sits next to the table update at the end of the step and the join waits
