@@ -24,8 +24,10 @@ __device__ __forceinline__ void store_vec4<__nv_bfloat16>(__nv_bfloat16* p, cons
 }
 
 // L = 1 fast path (the reference's only case): UNROLL bags in flight per lane group.
-template <typename OutT, int UNROLL>
-__global__ void __launch_bounds__(256)
+// LAZY (lazy exact-replay Adam) is a template flag: the replay state costs ~50 registers, which capped the plain lookup at two
+// blocks per SM (ncu: 91 registers, 23 % of the warp slots in use, 34 us for the notice tower).
+template <typename OutT, int UNROLL, bool LAZY>
+__global__ void __launch_bounds__(256, LAZY ? 2 : 4)
 ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ row_base,
                   const int32_t* __restrict__ vocab, const int64_t* __restrict__ values, int B, int K, int E,
                   int layout, OutT* __restrict__ out, int64_t out_ld, int64_t out_col0, int32_t* __restrict__ rows_out,
@@ -39,7 +41,7 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
   tt_lazy_ctx L = {};
   tt_adam_hyper lh = {};
   long long upto = 0;
-  if (lazy) {
+  if (LAZY) {
     L = *lazy;
     lh = *L.hyper;
     upto = lh.step + upto_off;
@@ -57,49 +59,66 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
   const int group0 = blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
   const int K_out = large_rank ? K_large : K;
   const int vec_per_row = E >> 2;
+  const int step_b = groups_total / K, step_k = groups_total - step_b * K;
   for (int64_t base = group0; base < n_bags; base += (int64_t)groups_total * UNROLL) {
-    int64_t row[UNROLL];
-    int bb[UNROLL], kk[UNROLL];
-    long long lag_from[UNROLL];
+    // Three phases, each over all UNROLL bags, with no branch between the loads of a phase: the UNROLL id loads leave back to
+    // back, then the UNROLL row loads (a bag past the end, or one of a skipped key, reads id 0 / arena row 0 and stores nothing).
+    // With the per-bag branches of the first version the compiler had serialised the bags on the id-load latency.
+    int bb[UNROLL], kk[UNROLL], voc[UNROLL];
+    bool ok[UNROLL];
+    int64_t id[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const int64_t s64 = base + (int64_t)u * groups_total;
-      row[u] = -1;
-      bb[u] = kk[u] = 0;
-      lag_from[u] = -1;
-      if (s64 < n_bags) {
-        const int slot = (int)s64;
-        const int b = slot / K, k = slot - b * K;
-        bb[u] = b;
-        kk[u] = k;
-        const int64_t hi = (int64_t)s_vocab[k] - 1;
-        if (hi >= 0) {  // vocab <= 0 marks a key this launch must skip (tables served by another path)
-          const int64_t vi = layout == TT_LAYOUT_SAMPLE_MAJOR ? (int64_t)slot : (int64_t)k * B + b;
-          int64_t id = __ldg(values + vi);
-          id = id < 0 ? 0 : (id > hi ? hi : id);  // clamp(id, 0, V_k-1)
-          row[u] = s_base[k] + id;
-          const int rk = s_rank[k];
-          if (lazy && rk >= 0) {
-            const long long last = L.row_last[row[u] - row_sub];
-            if (last < upto) lag_from[u] = last + 1;
-          }
-          if (lane == 0 && rk >= 0) {  // only tables on the sort-dedup path record their (compact) row
-            const int64_t o = (int64_t)b * K_out + rk;
-            if (rows_out) rows_out[o] = (int32_t)(row[u] - row_sub);
-            if (slots_out) slots_out[o] = (int32_t)(slot_base + o);
-          }
+      int b, k;
+      if (u == 0) {  // one division per thread and iteration: the UNROLL slots of a lane group are groups_total apart
+        b = (int)base / K;
+        k = (int)base - b * K;
+      } else {
+        k = kk[u - 1] + step_k;
+        b = bb[u - 1] + step_b;
+        if (k >= K) {
+          k -= K;
+          ++b;
         }
       }
+      bb[u] = b;
+      kk[u] = k;
+      voc[u] = s_vocab[k];
+      ok[u] = s64 < n_bags && voc[u] > 0;  // vocab <= 0 marks a key this launch must skip (tables served by another path)
+      const int64_t vi = layout == TT_LAYOUT_SAMPLE_MAJOR ? s64 : (int64_t)k * B + b;
+      id[u] = __ldg(values + (ok[u] ? vi : 0));
     }
-    for (int c = lane; c < vec_per_row; c += G) {
+    int64_t row[UNROLL];
+    long long lag_from[LAZY ? UNROLL : 1];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t hi = (int64_t)voc[u] - 1;
+      const int64_t idc = id[u] < 0 ? 0 : (id[u] > hi ? hi : id[u]);  // clamp(id, 0, V_k-1)
+      row[u] = ok[u] ? s_base[kk[u]] + idc : 0;
+      const int rk = s_rank[kk[u]];
+      if (LAZY) {
+        lag_from[u] = -1;
+        if (ok[u] && rk >= 0) {
+          const long long last = L.row_last[row[u] - row_sub];
+          if (last < upto) lag_from[u] = last + 1;
+        }
+      }
+      if (ok[u] && lane == 0 && rk >= 0) {  // only tables on the sort-dedup path record their (compact) row
+        const int64_t o = (int64_t)bb[u] * K_out + rk;
+        if (rows_out) rows_out[o] = (int32_t)(row[u] - row_sub);
+        if (slots_out) slots_out[o] = (int32_t)(slot_base + o);
+      }
+    }
+#pragma unroll 1
+    for (int c = lane; c < vec_per_row; c += G) {  // lanes_per_row() gives one 16-byte chunk per lane for E <= 128: a single trip
       float4 v[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u)
-        if (row[u] >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(arena + row[u] * E) + c);
-      if (lazy) {
+      for (int u = 0; u < UNROLL; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(arena + row[u] * E) + c);
+      if (LAZY) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-          if (row[u] >= 0 && lag_from[u] >= 0) {  // read-only catch-up: the update kernel replays again and writes back
+          if (ok[u] && lag_from[u] >= 0) {  // read-only catch-up: the update kernel replays again and writes back
             const int64_t lo = (row[u] - row_sub) * E;
             float4 mm = *(reinterpret_cast<const float4*>(L.arena_m + lo) + c);
             float4 vv = *(reinterpret_cast<const float4*>(L.arena_v + lo) + c);
@@ -108,7 +127,7 @@ ebc_fwd_l1_kernel(const float* __restrict__ arena, const int64_t* __restrict__ r
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
-        if (row[u] >= 0) store_vec4<OutT>(out + (int64_t)bb[u] * out_ld + out_col0 + (int64_t)kk[u] * E + 4 * c, v[u]);
+        if (ok[u]) store_vec4<OutT>(out + (int64_t)bb[u] * out_ld + out_col0 + kk[u] * E + 4 * c, v[u]);
     }
   }
 }
@@ -884,12 +903,12 @@ struct SmallTab {
   int col;        // column offset (elements) of the key's slice in the pooled-gradient row
   int64_t g_off;  // offset (floats) of the table's gradient inside gout
 };
-constexpr int SM_CHUNK = 128;  // samples per CTA
+constexpr int SM_CHUNK = 128;  // smallest number of samples per CTA (sizes the partials workspace)
 
 template <typename GT>
 __global__ void __launch_bounds__(256)
 ebc_small_partial_kernel(const int64_t* __restrict__ values, int B, int K, int layout, const GT* __restrict__ grad, int64_t ld,
-                         int E, const SmallTab* __restrict__ tabs, float* __restrict__ part, int64_t part_stride) {
+                         int E, const SmallTab* __restrict__ tabs, float* __restrict__ part, int64_t part_stride, int chunk) {
   extern __shared__ float s_acc[];  // [8 warps][vocab * E]
   const SmallTab tb = tabs[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -897,8 +916,8 @@ ebc_small_partial_kernel(const int64_t* __restrict__ values, int B, int K, int l
   for (int i = threadIdx.x; i < 8 * ve; i += 256) s_acc[i] = 0.f;
   __syncthreads();
   float* mine = s_acc + warp * ve;
-  const int b_lo = blockIdx.y * SM_CHUNK;
-  const int b_hi = min(b_lo + SM_CHUNK, B);
+  const int b_lo = blockIdx.y * chunk;
+  const int b_hi = min(b_lo + chunk, B);
   if (E <= 32) {
     // eight samples of this warp per round: their ids (one lane each) and gradient vectors (one element per lane) are all in
     // flight together; the shared-memory accumulation then runs in ascending sample order (same order as the plain loop)
@@ -1006,14 +1025,16 @@ static int ebc_forward_impl(const float* arena, const int64_t* d_row_base, const
     // from 18.8 to 31.9 us and the step got slower)
     const int64_t gcap = (int64_t)sm_count() * 16;
     int grid = (int)(want < 1 ? 1 : (want > gcap ? gcap : want));
-    if (out_dtype == TT_F32)
-      ebc_fwd_l1_kernel<float, UNROLL><<<grid, threads, smem, s>>>(arena, d_row_base, d_vocab, values, B, K, E, layout,
-                                                                   (float*)out, out_ld, out_col0, rows_out, slots_out, slot_base, G,
-                                                                   large_rank, K_large, row_sub, d_lazy, upto_off);
-    else
-      ebc_fwd_l1_kernel<__nv_bfloat16, UNROLL><<<grid, threads, smem, s>>>(
-          arena, d_row_base, d_vocab, values, B, K, E, layout, (__nv_bfloat16*)out, out_ld, out_col0, rows_out,
-          slots_out, slot_base, G, large_rank, K_large, row_sub, d_lazy, upto_off);
+#define TT_L1_LAUNCH(OUT_T, LZ)                                                                                                  \
+  ebc_fwd_l1_kernel<OUT_T, UNROLL, LZ><<<grid, threads, smem, s>>>(arena, d_row_base, d_vocab, values, B, K, E, layout, (OUT_T*)out, \
+                                                                   out_ld, out_col0, rows_out, slots_out, slot_base, G, large_rank, \
+                                                                   K_large, row_sub, d_lazy, upto_off)
+    if (out_dtype == TT_F32) {
+      if (d_lazy) TT_L1_LAUNCH(float, true); else TT_L1_LAUNCH(float, false);
+    } else {
+      if (d_lazy) TT_L1_LAUNCH(__nv_bfloat16, true); else TT_L1_LAUNCH(__nv_bfloat16, false);
+    }
+#undef TT_L1_LAUNCH
   } else {
     int64_t want = ceil_div(n_bags, groups_per_block);
     int grid = (int)(want < 1 ? 1 : (want > (int64_t)sm_count() * 16 ? (int64_t)sm_count() * 16 : want));
@@ -1286,17 +1307,24 @@ int tt_ebc_small_backward(const int64_t* values, int32_t B, int32_t K, int32_t l
   const size_t smem = (size_t)8 * max_vocab * E * sizeof(float);
   TT_CHECK_ARG(smem <= 160 * 1024, "tt_ebc_small_backward: max_vocab * E too large for the shared-memory accumulators");
   cudaStream_t s = (cudaStream_t)stream;
-  const int chunks = (B + SM_CHUNK - 1) / SM_CHUNK;
+  // ONE wave of CTAs (about four per SM): the fused step launches this kernel next to the large-table update, and the CTAs of a
+  // kernel launched behind a multi-wave grid are only placed once that grid's last wave has been — 27 tables x 64 chunks of 128
+  // samples (two waves) held the segment-sum kernel back by ~10 us
+  const int chunks_max = (B + SM_CHUNK - 1) / SM_CHUNK;
+  int chunks = sm_count() * 4 / n_small;
+  chunks = chunks < 1 ? 1 : (chunks > chunks_max ? chunks_max : chunks);
+  const int chunk = ((B + chunks - 1) / chunks + 63) / 64 * 64;  // whole rounds of the eight warps
+  chunks = (B + chunk - 1) / chunk;
   float* part = (float*)workspace;
   dim3 grid(n_small, chunks);
   if (grad_dtype == TT_F32) {
     TT_CUDA(cudaFuncSetAttribute(ebc_small_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ebc_small_partial_kernel<float><<<grid, 256, smem, s>>>(values, B, K, layout, (const float*)grad, ld, E,
-                                                            (const SmallTab*)d_small_tabs, part, small_floats);
+                                                            (const SmallTab*)d_small_tabs, part, small_floats, chunk);
   } else {
     TT_CUDA(cudaFuncSetAttribute(ebc_small_partial_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ebc_small_partial_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(values, B, K, layout, (const __nv_bfloat16*)grad, ld, E,
-                                                                    (const SmallTab*)d_small_tabs, part, small_floats);
+                                                                    (const SmallTab*)d_small_tabs, part, small_floats, chunk);
   }
   ebc_small_reduce_kernel<<<ceil_div(small_floats, 256), 256, 0, s>>>(part, small_floats, chunks, small_floats, gout);
   TT_LAUNCH_CHECK("ebc_small_backward");

@@ -38,9 +38,11 @@ path = os.path.join(tempfile.gettempdir(), "tt_trace.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "ts" in e]
 ev.sort(key=lambda e: e["ts"])
-# split the three replays at the largest gaps and keep the last one
-gaps = sorted(range(1, len(ev)), key=lambda i: ev[i]["ts"] - (ev[i - 1]["ts"] + ev[i - 1]["dur"]), reverse=True)[:2]
-start = max(gaps)
+# keep the last of the three replays: it starts with the staging copies in front of the last hyper_advance_kernel
+first = [i for i, e in enumerate(ev) if "hyper_advance" in e["name"]]
+start = first[-1]
+while start > 0 and ev[start - 1].get("cat") == "gpu_memcpy":
+    start -= 1
 ev = ev[start:]
 t0 = ev[0]["ts"]
 streams = {s: i for i, s in enumerate(sorted({e["args"].get("stream", 0) for e in ev}))}
