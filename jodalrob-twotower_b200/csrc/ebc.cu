@@ -1236,7 +1236,8 @@ static int backward_adam_impl(float* arena_w, float* arena_m, float* arena_v, fl
     }
   } else {
     int64_t want = ceil_div(total_rows, gpb);
-    const int64_t cap = (int64_t)sm_count() * 32;
+    static const int cap_env = [] { const char* e = getenv("TT_ROWS_DENSE_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    const int64_t cap = (int64_t)sm_count() * (cap_env > 0 ? cap_env : 32);
     const int grid = (int)(want > cap ? cap : want);
 #define TT_ROWS_LAUNCH(A, W)                                                                                         \
   (direct ? ebc_rows_dense_kernel<A, W, true> : ebc_rows_dense_kernel<A, W, false>)<<<grid, threads, 0, s>>>(arena_w, arena_m, arena_v, grad_arena, total_rows, E, G, gs, \

@@ -193,11 +193,10 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[TC_CW], float c1, 
 
 // ---- work partition: the T = row blocks x column tiles tiles, row-block-major, cut into G equal contiguous ranges ----
 __host__ __device__ __forceinline__ long long tc_range_begin(int c, long long T, int G) { return (long long)c * T / G; }
+// the CTA whose range holds tile g: the largest c with floor(c T / G) <= g, i.e. c T < (g + 1) G — one division (the reduce kernels
+// evaluate this per thread, in front of their loads)
 __host__ __device__ __forceinline__ int tc_cta_of_tile(long long g, long long T, int G) {
-  int c = (int)(g * G / T);
-  while (c + 1 < G && tc_range_begin(c + 1, T, G) <= g) ++c;
-  while (c > 0 && tc_range_begin(c, T, G) > g) --c;
-  return c;
+  return (int)((unsigned long long)((g + 1) * G - 1) / (unsigned long long)T);
 }
 // the pieces of row block rb are numbered by owning CTA, starting at the CTA that owns the block's first tile
 __host__ __device__ __forceinline__ int tc_parts_of_row_block(int rb, int n_ct, long long T, int G) {
@@ -819,7 +818,16 @@ tc_dx_reduce_kernel(const float* __restrict__ part, int64_t n, int n_ct, long lo
   const int64_t row = i / F;
   const int n_parts = tc_parts_of_row_block((int)(row / TCM), n_ct, T, G);
   float4 a = *reinterpret_cast<const float4*>(part + i);
-  for (int c = 1; c < n_parts; ++c) f4_add(a, *reinterpret_cast<const float4*>(part + (int64_t)c * n + i));
+  if (n_parts <= 4) {  // all loads first, then the adds in part order (see tc_finish_kernel)
+    float4 q[3];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) q[c - 1] = *reinterpret_cast<const float4*>(part + (int64_t)(c < n_parts ? c : 0) * n + i);
+#pragma unroll
+    for (int c = 1; c < 4; ++c)
+      if (c < n_parts) f4_add(a, q[c - 1]);
+  } else {
+    for (int c = 1; c < n_parts; ++c) f4_add(a, *reinterpret_cast<const float4*>(part + (int64_t)c * n + i));
+  }
   const int col = (int)(i - row * F);
   const uint2 yv = *reinterpret_cast<const uint2*>(Y + (diag_offset + row) * F + col);
   const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.x));
@@ -1032,8 +1040,44 @@ tc_finish_kernel(const float* __restrict__ row_e, const float* __restrict__ dx_p
   const int64_t row = i / F;
   const int col = (int)(i - row * F);
   const int n_parts = tc_parts_of_row_block((int)(row / TCM), n_ct, T, G);
+  // The kernel is one L2 round trip long if every load leaves before the first add: up to four parts (the usual split of a row
+  // block) are fetched into registers in one go and then added in part order — the same order as the plain loops below.
   float rs = 0.f;
-  for (int c = 0; c < 4 * n_parts; ++c) rs += row_e[(int64_t)c * Bx + row];
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (n_parts <= 4) {
+    float e[16];
+    float4 pa[4], pb[4];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) e[c] = c < 4 * n_parts ? row_e[(int64_t)c * Bx + row] : 0.f;
+    if (dx_part) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float* base = dx_part + ((int64_t)(c < n_parts ? c : 0) * Bx + row) * (2 * F) + col;
+        pa[c] = *reinterpret_cast<const float4*>(base);
+        pb[c] = *reinterpret_cast<const float4*>(base + F);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < 4 * n_parts) rs += e[c];
+    if (dx_part) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < n_parts) {
+          f4_add(a, pa[c]);
+          f4_add(b, pb[c]);
+        }
+    }
+  } else {
+    for (int c = 0; c < 4 * n_parts; ++c) rs += row_e[(int64_t)c * Bx + row];
+    if (dx_part) {
+      for (int c = 0; c < n_parts; ++c) {
+        const float* base = dx_part + ((int64_t)c * Bx + row) * (2 * F) + col;
+        f4_add(a, *reinterpret_cast<const float4*>(base));
+        f4_add(b, *reinterpret_cast<const float4*>(base + F));
+      }
+    }
+  }
   const float ixs = gscale / rs;
   if (col == 0) {
     const float se = k_shift * rs;
@@ -1041,12 +1085,6 @@ tc_finish_kernel(const float* __restrict__ row_e, const float* __restrict__ dx_p
     if (inv_out) inv_out[row] = 1.f / se;
   }
   if (dx_part) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    for (int c = 0; c < n_parts; ++c) {
-      const float* base = dx_part + ((int64_t)c * Bx + row) * (2 * F) + col;
-      f4_add(a, *reinterpret_cast<const float4*>(base));
-      f4_add(b, *reinterpret_cast<const float4*>(base + F));
-    }
     a.x = fmaf(ixs, a.x, b.x);
     a.y = fmaf(ixs, a.y, b.y);
     a.z = fmaf(ixs, a.z, b.z);

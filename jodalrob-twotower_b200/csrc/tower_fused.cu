@@ -165,7 +165,7 @@ tower_tail_fwd_kernel(const __grid_constant__ CUtensorMap map_w2, const TailFwdP
   float* sc = reinterpret_cast<float*>(s_sum + 2 * p.H1 + 512);
   float* sh = sc + p.H1;
   FusedSmem* sb = reinterpret_cast<FusedSmem*>(sh + p.H1);
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int tid = threadIdx.x;
   const int64_t m0 = (int64_t)blockIdx.x * TF_ROWS;
   const uint32_t tmem_cols = p.F <= 64 ? 64 : 128;
