@@ -1236,14 +1236,18 @@ static int backward_adam_impl(float* arena_w, float* arena_m, float* arena_v, fl
     }
   } else {
     int64_t want = ceil_div(total_rows, gpb);
+    const bool wg = grad_arena != nullptr;
+    const bool streaming = do_adam && !wg && total_rows * (int64_t)E * 4 >= ((int64_t)256 << 20);  // arena >> L2
+    // L2-resident arena (the reference's sizes): two waves of resident CTAs walking the rows grid-stride instead of one CTA per
+    // 32 rows — the kernels launched next to this one (bias folds, split-K reduces) are then placed at once instead of behind
+    // its last wave: 275.8 -> 271.2 us per step (three CTAs per SM: 273.3). TT_ROWS_DENSE_CTAS_PER_SM overrides (experiments).
     static const int cap_env = [] { const char* e = getenv("TT_ROWS_DENSE_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-    const int64_t cap = (int64_t)sm_count() * (cap_env > 0 ? cap_env : 32);
+    const int64_t cap = (int64_t)sm_count() * (cap_env > 0 ? cap_env : (streaming ? 32 : 6));
     const int grid = (int)(want > cap ? cap : want);
 #define TT_ROWS_LAUNCH(A, W)                                                                                         \
   (direct ? ebc_rows_dense_kernel<A, W, true> : ebc_rows_dense_kernel<A, W, false>)<<<grid, threads, 0, s>>>(arena_w, arena_m, arena_v, grad_arena, total_rows, E, G, gs, \
                                                        row_begin, row_end, row_stamp, stamp, d_stamp, pieces, d_hyper, 0)
-    const bool wg = grad_arena != nullptr;
-    if (do_adam && !wg && total_rows * (int64_t)E * 4 >= ((int64_t)256 << 20))  // arena >> L2: the streaming variant
+    if (streaming)
       (direct ? ebc_rows_dense_stream_kernel<true> : ebc_rows_dense_stream_kernel<false>)<<<grid, threads, 0, s>>>(
           arena_w, arena_m, arena_v, total_rows, E, G, gs, row_begin, row_end, row_stamp, stamp, d_stamp, pieces, d_hyper);
     else if (do_adam && wg) TT_ROWS_LAUNCH(true, true);

@@ -143,3 +143,54 @@ def test_pooled_tables_full_size_properties():
     touched = torch.zeros(tab.total_rows, dtype=torch.bool, device=DEV)
     touched[rows] = True
     assert torch.equal(changed, touched)
+
+
+@pytest.mark.parametrize("E,vocabs,B,layout,bf16", [
+    (32, [12, 25, 48, 49, 137], 1000, 0, False), (32, [12, 64, 100, 160], 8192, 0, True), (32, [5, 50], 300, 1, False),
+    (64, [3, 24, 25, 80], 2049, 0, True), (128, [7, 12, 13, 40], 513, 1, False)])
+def test_small_table_one_hot_reduction(E, vocabs, B, layout, bf16):
+    """tt_ebc_small_backward (the dense one-hot gradient of the replicated small tables, two_tower_train_task.py's
+    EmbeddingBagCollection backward for tables with a handful of rows) against torch index_add in fp64, at every chunking the
+    single-wave grid picks (B from 300 to 8192). Ids include out-of-range values (clamped like the lookup clamps them).
+    Deterministic: two runs are bit-identical."""
+    import jodalrob_twotower_b200 as tt
+    from jodalrob_twotower_b200.native import ptr, TT_BF16, TT_F32
+    lib = tt.native.lib()
+    g = torch.Generator().manual_seed(B + E)
+    K = len(vocabs) + 2  # two keys of the tower are not small tables: their columns must be ignored
+    key_of = [0, 2, 3, 4, 5, 6, 7][:len(vocabs)]
+    H0 = 16
+    ld = H0 + K * E
+    ids = torch.stack([torch.randint(-2, max(vocabs) + 3, (B,), generator=g) for _ in range(K)], 1)  # [B, K]
+    for t, k in enumerate(key_of):
+        ids[:, k] = torch.randint(-1, vocabs[t] + 2, (B,), generator=g)
+        ids[: B // 3, k] = t % vocabs[t]  # a hot row
+    values = (ids.reshape(-1) if layout == 0 else ids.t().reshape(-1)).contiguous().to(DEV)
+    grad = torch.randn(B, ld, generator=g)
+    gdev = (grad.to(torch.bfloat16) if bf16 else grad).to(DEV).contiguous()
+    gref = gdev.double().cpu()
+    desc = np.zeros(len(vocabs), dtype=np.dtype([("key", "<i4"), ("vocab", "<i4"), ("col", "<i4"), ("pad", "<i4"), ("g_off", "<i8")]))
+    off = 0
+    for t, k in enumerate(key_of):
+        desc[t] = (k, vocabs[t], H0 + k * E, 0, off)
+        off += vocabs[t] * E
+    small_floats = off
+    tabs = torch.from_numpy(desc.view(np.uint8).copy()).to(DEV)
+    nb = lib.query("tt_ebc_small_workspace_bytes", B, small_floats)
+    s = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for _ in range(2):
+        ws = torch.full((nb,), 0x7F, dtype=torch.uint8, device=DEV)
+        gout = torch.full((small_floats,), float("nan"), dtype=torch.float32, device=DEV)
+        lib.call("tt_ebc_small_backward", ptr(values), B, K, layout, ptr(gdev), ld, TT_BF16 if bf16 else TT_F32, E, ptr(tabs), len(vocabs),
+                 max(vocabs), small_floats, ptr(gout), ptr(ws), nb, s)
+        torch.cuda.synchronize()
+        outs.append(gout.cpu())
+    assert torch.equal(outs[0], outs[1])
+    off = 0
+    for t, k in enumerate(key_of):
+        V = vocabs[t]
+        want = torch.zeros(V, E, dtype=torch.float64).index_add_(0, ids[:, k].clamp(0, V - 1), gref[:, H0 + k * E: H0 + (k + 1) * E])
+        got = outs[0][off: off + V * E].view(V, E).double()
+        assert rel_err(got, want) < 2e-6, (t, V)
+        off += V * E
