@@ -534,28 +534,26 @@ struct GradSrc {
   const int32_t* cmap1;
 };
 
+// Branch-free on purpose (selects, one division): callers keep several of these slot -> column map -> gradient chains in flight
+// per thread, and a branch between the loads of two chains makes the compiler serialise them.
 template <typename GT>
 __device__ __forceinline__ float4 load_grad_vec(const GradSrc& s, int32_t slot, int E, int c) {
-  const GT* base;
-  int64_t off;
   const void* p0 = s.g0;
   const void* p1 = s.g1;
-  if (s.table) {
+  if (s.table) {  // kernel-uniform
     const int r = (int)(slot / s.n_per_rank);
     slot -= (int32_t)(r * s.n_per_rank);
     p0 = s.table[2 * r];
     p1 = s.table[2 * r + 1];
   }
-  if (slot < s.n0) {
-    const int b = slot / s.K0, k = slot - b * s.K0;
-    base = reinterpret_cast<const GT*>(p0);
-    off = (int64_t)b * s.ld0 + (s.cmap0 ? (int64_t)__ldg(s.cmap0 + k) : s.col0 + (int64_t)k * E) + 4 * c;
-  } else {
-    const int sl = slot - (int32_t)s.n0;
-    const int b = sl / s.K1, k = sl - b * s.K1;
-    base = reinterpret_cast<const GT*>(p1);
-    off = (int64_t)b * s.ld1 + (s.cmap1 ? (int64_t)__ldg(s.cmap1 + k) : s.col1 + (int64_t)k * E) + 4 * c;
-  }
+  const bool first = slot < s.n0;
+  const int sl = first ? slot : slot - (int32_t)s.n0;
+  const int K = first ? s.K0 : s.K1;
+  const int b = sl / K, k = sl - b * K;
+  const int32_t* cm = first ? s.cmap0 : s.cmap1;
+  const int64_t colk = cm ? (int64_t)__ldg(cm + k) : (first ? s.col0 : s.col1) + (int64_t)k * E;
+  const GT* base = reinterpret_cast<const GT*>(first ? p0 : p1);
+  const int64_t off = (int64_t)b * (first ? s.ld0 : s.ld1) + colk + 4 * c;
   if constexpr (sizeof(GT) == 4) {
     return __ldg(reinterpret_cast<const float4*>(base + off));
   } else {
@@ -581,6 +579,65 @@ ebc_gather_sorted_kernel(const int32_t* __restrict__ sslot, int64_t n, const int
   }
 }
 
+// The same compaction for LOCAL sources (no peer table) and fewer than 2^31 vectors: four entries per thread, walked in phases
+// (slots, column maps, gradient vectors, stores) with no branch between the loads of a phase, so that the four dependent chains of
+// a thread overlap — the kernel is the first link of the table update at the tail of the train step, and latency-bound there.
+template <typename GT>
+__global__ void __launch_bounds__(256)
+ebc_gather_sorted4_kernel(const int32_t* __restrict__ sslot, int64_t n, const int32_t* __restrict__ d_n, GradSrc src, int E,
+                          float* __restrict__ gs) {
+  if (d_n) n = *d_n;
+  constexpr int U = 4;
+  // thread -> (entry lane, 16-byte chunk c of the row); the host launches this kernel only when the chunk count divides the block
+  // size, so one division serves all four entries of a thread (they are `istride` entries apart)
+  const unsigned vec = (unsigned)E >> 2;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned c0 = gid % vec, lane_e = gid / vec;
+  const unsigned istride = gridDim.x * blockDim.x / vec;
+  for (unsigned i0 = lane_e; i0 < (unsigned)n; i0 += istride * U) {
+    unsigned idx[U], c[U];
+    int32_t slot[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned i = i0 + u * istride;
+      ok[u] = i < (unsigned)n;
+      idx[u] = ok[u] ? i : 0u;
+      c[u] = c0;
+      slot[u] = __ldg(sslot + idx[u]);
+    }
+    const GT* base[U];
+    int64_t off[U];
+    int k[U], colk[U];
+    bool first[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      first[u] = slot[u] < src.n0;
+      const int sl = first[u] ? slot[u] : slot[u] - (int32_t)src.n0;
+      const int K = first[u] ? src.K0 : src.K1;
+      const int b = sl / K;
+      k[u] = sl - b * K;
+      base[u] = reinterpret_cast<const GT*>(first[u] ? src.g0 : src.g1);
+      off[u] = (int64_t)b * (first[u] ? src.ld0 : src.ld1) + 4 * c[u];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int32_t* cm = first[u] ? src.cmap0 : src.cmap1;
+      colk[u] = cm ? __ldg(cm + k[u]) : (int)(first[u] ? src.col0 : src.col1) + k[u] * E;
+    }
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const GT* p = base[u] + off[u] + colk[u];
+      if constexpr (sizeof(GT) == 4) v[u] = __ldg(reinterpret_cast<const float4*>(p));
+      else v[u] = unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(p)));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (ok[u]) *reinterpret_cast<float4*>(gs + (int64_t)idx[u] * E + 4 * c[u]) = v[u];
+  }
+}
+
 // Where the segment sums read the gradient vector of sorted entry i: from the compacted copy `gs` (small steps: the copy is
 // L2-resident and the sums stream it), or straight from the pooled-gradient buffers through the sorted slot (`gs` NULL; large
 // multi-hot steps: B*K*L compacted vectors would cost an HBM round trip while the B*K pooled gradients themselves stay in L2).
@@ -592,25 +649,35 @@ struct GradFetch {
   int bf16;
 };
 
+template <bool DIRECT, typename GT>
+__device__ __forceinline__ float4 fetch_grad_t(const GradFetch& f, int64_t i, int E, int c) {
+  if (!DIRECT) return __ldg(reinterpret_cast<const float4*>(f.gs + i * E + 4 * c));
+  return load_grad_vec<GT>(f.src, __ldg(f.sslot + i), E, c);
+}
 template <bool DIRECT>
 __device__ __forceinline__ float4 fetch_grad(const GradFetch& f, int64_t i, int E, int c) {
-  if (!DIRECT) return __ldg(reinterpret_cast<const float4*>(f.gs + i * E + 4 * c));
-  const int32_t slot = __ldg(f.sslot + i);
-  return f.bf16 ? load_grad_vec<__nv_bfloat16>(f.src, slot, E, c) : load_grad_vec<float>(f.src, slot, E, c);
+  return (DIRECT && f.bf16) ? fetch_grad_t<DIRECT, __nv_bfloat16>(f, i, E, c) : fetch_grad_t<DIRECT, float>(f, i, E, c);
 }
 
-// acc += sum_{i in [lo,hi)} grad(i) in ascending i; batches of BATCH keep that many loads in flight before the first add
-template <bool DIRECT, int BATCH = 8>
-__device__ __forceinline__ void gather_sum(float4& acc, const GradFetch& f, int64_t lo, int64_t hi, int E, int c) {
-  int64_t i = lo;
-  for (; i + BATCH <= hi; i += BATCH) {
+// acc += sum_{i in [lo,hi)} grad(i) in ascending i; batches of BATCH keep that many loads in flight before the first add. The
+// ragged last batch is fetched like a full one (entries past `hi` re-read entry `lo` and are not added): a segment of up to BATCH
+// entries — almost every row of a large table — costs one load latency instead of one per entry. The source dtype is dispatched
+// OUTSIDE the batch: a branch between the fetches of a batch makes the compiler serialise their slot -> gradient chains.
+template <bool DIRECT, typename GT, int BATCH>
+__device__ __forceinline__ void gather_sum_t(float4& acc, const GradFetch& f, int64_t lo, int64_t hi, int E, int c) {
+  for (int64_t i = lo; i < hi; i += BATCH) {
     float4 v[BATCH];
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u) v[u] = fetch_grad<DIRECT>(f, i + u, E, c);
+    for (int u = 0; u < BATCH; ++u) v[u] = fetch_grad_t<DIRECT, GT>(f, i + u < hi ? i + u : lo, E, c);
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u) f4_add(acc, v[u]);
+    for (int u = 0; u < BATCH; ++u)
+      if (i + u < hi) f4_add(acc, v[u]);
   }
-  for (; i < hi; ++i) f4_add(acc, fetch_grad<DIRECT>(f, i, E, c));
+}
+template <bool DIRECT, int BATCH = 8>
+__device__ __forceinline__ void gather_sum(float4& acc, const GradFetch& f, int64_t lo, int64_t hi, int E, int c) {
+  if (DIRECT && f.bf16) gather_sum_t<DIRECT, __nv_bfloat16, BATCH>(acc, f, lo, hi, E, c);
+  else gather_sum_t<DIRECT, float, BATCH>(acc, f, lo, hi, E, c);
 }
 
 // level 1 for long rows: SUB lane groups per chunk of SEG_CHUNK sorted entries. Each group sums a contiguous
@@ -798,13 +865,15 @@ ebc_lazy_flush_kernel(const tt_lazy_ctx* __restrict__ lazy, int64_t rows, int E,
 
 // sparse mode: lane groups walk the sorted entries; only segment heads work. HBM-bound at scale (millions of touched rows, each
 // a random 3 x E*4-byte read-modify-write), so the kernel is built around memory-level parallelism:
-//   * persistent grid-stride CTAs, SP_ROWS entries per lane group and iteration: the w/m/v loads of all of them are issued
-//     before anything that depends on memory;
-//   * the dependent chain in front of the gradient is ONE sequential read: a head finds its segment end by scanning the sorted
-//     rows forward (coalesced, mostly 1-2 entries) instead of a random row_end[r] lookup;
+//   * persistent grid-stride CTAs, SP_ROWS entries per lane group and iteration. The sorted rows of the NEXT iteration (the entry,
+//     its predecessor for the head test, its successor for the segment end) are fetched while this iteration's rows are in
+//     flight, so the dependent chain of an iteration is ONE memory round trip: w / m / v / gradient of every entry leave together,
+//     with no branch between them (an entry that is not a head reads row 0 and stores nothing);
+//   * a head finds its segment end from that successor (most segments are one entry; longer ones scan forward through the
+//     sorted rows: sequential, cached) instead of a random row_end[r] lookup;
 //   * w/m/v accesses are streaming (evict-first), so the pooled/compacted gradients keep the L2.
 constexpr int SP_ROWS = 2;
-template <bool DIRECT>
+template <bool DIRECT, bool LAZY>
 __global__ void __launch_bounds__(256, 3)
 ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int E, int G,
                        const int32_t* __restrict__ srow, const GradFetch gs, int64_t n,
@@ -814,46 +883,65 @@ ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __re
   if (d_n) n = *d_n;
   const tt_adam_hyper h = *d_hyper;
   tt_lazy_ctx L = {};
-  if (lazy) L = *lazy;
+  if (LAZY) L = *lazy;
   const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int lane = threadIdx.x % G;
   const int vec_per_row = E >> 2;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x / G);
-  for (int64_t base = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; base < n; base += SP_ROWS * groups_total) {
-    int32_t i[SP_ROWS], e[SP_ROWS];  // sorted positions fit 31 bits (tt_ebc_sort_rows checks n)
-    int32_t r[SP_ROWS];
-    bool head[SP_ROWS];
-    long long last[SP_ROWS];
-    float4 wv[SP_ROWS], mv[SP_ROWS], vv[SP_ROWS], g0[SP_ROWS];
+  const int32_t n32 = (int32_t)n;  // sorted positions fit 31 bits (tt_ebc_sort_rows checks n)
+  // (row, predecessor's row, successor's row) of the SP_ROWS entries of an iteration; -1 / -2 / -3 where there is none
+  auto fetch_rows = [&](int64_t base, int32_t (&rr)[SP_ROWS], int32_t (&rp)[SP_ROWS], int32_t (&rn)[SP_ROWS]) {
 #pragma unroll
     for (int u = 0; u < SP_ROWS; ++u) {
       const int64_t iu = base + u * groups_total;
-      i[u] = (int32_t)iu;
-      head[u] = false;
-      r[u] = 0;
-      last[u] = 0;
-      if (iu < n) {
-        r[u] = __ldg(srow + i[u]);
-        head[u] = i[u] == 0 || __ldg(srow + i[u] - 1) != r[u];
-        if (lazy && head[u]) last[u] = L.row_last[r[u]];
-      }
+      const bool in = iu < n;
+      const int32_t i = in ? (int32_t)iu : 0;
+      const int32_t a = __ldg(srow + i), p = __ldg(srow + (i > 0 ? i - 1 : 0)), x = __ldg(srow + (i + 1 < n32 ? i + 1 : i));
+      rr[u] = in ? a : -1;
+      rp[u] = (in && i > 0) ? p : -2;
+      rn[u] = (in && i + 1 < n32) ? x : -3;
     }
+  };
+  int32_t r_nx[SP_ROWS], p_nx[SP_ROWS], x_nx[SP_ROWS];
+  int64_t base = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+  if (base < n) fetch_rows(base, r_nx, p_nx, x_nx);
+  for (; base < n; base += SP_ROWS * groups_total) {
+    int32_t i[SP_ROWS], e[SP_ROWS], r[SP_ROWS], nx[SP_ROWS];
+    bool head[SP_ROWS];
+    int32_t last[SP_ROWS];
+    float4 wv[SP_ROWS], mv[SP_ROWS], vv[SP_ROWS], g0[SP_ROWS];
 #pragma unroll
-    for (int u = 0; u < SP_ROWS; ++u)
-      if (head[u] && lane < vec_per_row) {  // first (for E <= 128: only) vector of the row, and the head's own gradient entry
-        const int64_t off = (int64_t)r[u] * E + 4 * lane;
-        wv[u] = __ldcs(reinterpret_cast<const float4*>(w + off));
-        mv[u] = __ldcs(reinterpret_cast<const float4*>(m + off));
-        vv[u] = __ldcs(reinterpret_cast<const float4*>(v + off));
-        g0[u] = fetch_grad<DIRECT>(gs, i[u], E, lane);
-      }
+    for (int u = 0; u < SP_ROWS; ++u) {
+      i[u] = (int32_t)(base + u * groups_total);
+      head[u] = r_nx[u] >= 0 && p_nx[u] != r_nx[u];
+      r[u] = head[u] ? r_nx[u] : 0;
+      nx[u] = x_nx[u];
+    }
+    // one round trip: state and the head's own gradient entry of every row of this iteration (first — for E <= 128 only —
+    // vector of the row), branch-free ...
+    const int c0 = lane < vec_per_row ? lane : 0;
 #pragma unroll
-    for (int u = 0; u < SP_ROWS; ++u)
-      if (head[u]) {
-        int32_t x = i[u] + 1;
-        while (x < (int32_t)n && x - i[u] <= SEG_CHUNK && __ldg(srow + x) == r[u]) ++x;
+    for (int u = 0; u < SP_ROWS; ++u) {
+      const int64_t off = (int64_t)r[u] * E + 4 * c0;
+      wv[u] = __ldcs(reinterpret_cast<const float4*>(w + off));
+      mv[u] = __ldcs(reinterpret_cast<const float4*>(m + off));
+      vv[u] = __ldcs(reinterpret_cast<const float4*>(v + off));
+      g0[u] = fetch_grad<DIRECT>(gs, head[u] ? i[u] : 0, E, c0);
+      last[u] = 0;
+      if (LAZY) last[u] = L.row_last[r[u]];
+    }
+    // ... and, underneath it, the sorted rows of the next iteration
+    const int64_t base_nx = base + SP_ROWS * groups_total;
+    if (base_nx < n) fetch_rows(base_nx, r_nx, p_nx, x_nx);
+#pragma unroll
+    for (int u = 0; u < SP_ROWS; ++u) {
+      e[u] = i[u] + 1;
+      if (head[u] && nx[u] == r[u]) {  // a segment of several entries: scan on (sequential reads of the sorted rows)
+        int32_t x = i[u] + 2;
+        while (x < n32 && x - i[u] <= SEG_CHUNK && __ldg(srow + x) == r[u]) ++x;
         e[u] = (x - i[u] > SEG_CHUNK) ? row_end[r[u]] : x;  // long rows were reduced to pieces: take the recorded end
       }
+    }
     for (int c = lane; c < vec_per_row; c += G) {
 #pragma unroll
       for (int u = 0; u < SP_ROWS; ++u)
@@ -868,20 +956,20 @@ ebc_rows_sparse_kernel(float* __restrict__ w, float* __restrict__ m, float* __re
           float4 g;
           if (e[u] - i[u] <= SEG_CHUNK) {  // 0 + g0 + ... == the plain ascending sum, bit for bit
             g = g0[u];
-            gather_sum<DIRECT, DIRECT ? 2 : 8>(g, gs, (int64_t)i[u] + 1, e[u], E, c);  // compacted: a contiguous stream
+            if (e[u] - i[u] > 1) gather_sum<DIRECT, DIRECT ? 2 : 8>(g, gs, (int64_t)i[u] + 1, e[u], E, c);  // compacted: a contiguous stream
           } else {  // long row: its per-chunk pieces, in chunk order (same as row_grad_sum)
             g = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int32_t ch = i[u] / SEG_CHUNK; ch <= (e[u] - 1) / SEG_CHUNK; ++ch)
               f4_add(g, *reinterpret_cast<const float4*>(pieces + (((int64_t)ch * 2 + (i[u] <= ch * SEG_CHUNK ? 0 : 1)) * E) + 4 * c));
           }
-          if (lazy) lazy_replay_vec4(wv[u], mv[u], vv[u], last[u] + 1, h.step - 1, L, h);  // the steps this row sat out
+          if (LAZY) lazy_replay_vec4(wv[u], mv[u], vv[u], (long long)last[u] + 1, h.step - 1, L, h);  // the steps this row sat out
           adam_vec4(wv[u], mv[u], vv[u], g, h);
           __stcs(reinterpret_cast<float4*>(w + off), wv[u]);
           __stcs(reinterpret_cast<float4*>(m + off), mv[u]);
           __stcs(reinterpret_cast<float4*>(v + off), vv[u]);
         }
     }
-    if (lazy) {  // the lanes of a group took the same path (group-uniform control flow) and have all read row_last by now
+    if (LAZY) {  // the lanes of a group took the same path (group-uniform control flow) and have all read row_last by now
       __syncwarp(gmask);
 #pragma unroll
       for (int u = 0; u < SP_ROWS; ++u)
@@ -1211,7 +1299,15 @@ static int backward_adam_impl(float* arena_w, float* arena_m, float* arena_v, fl
       int64_t want = ceil_div(n * (E / 4), (int64_t)threads);
       const int64_t cap = (int64_t)sm_count() * 16;
       const int ggrid = (int)(want > cap ? cap : want);
-      if (grad_dtype == TT_F32)
+      static const int g4_env = [] { const char* e = getenv("TT_EBC_GATHER4"); return e ? atoi(e) : 1; }();
+      const bool local4 = g4_env && !grad_table && (threads % (E / 4)) == 0 && n * (E / 4) < ((int64_t)1 << 30) && col0_0 < ((int64_t)1 << 30) && col0_1 < ((int64_t)1 << 30);
+      if (local4) {
+        const int g4 = (int)ceil_div(want, 4);
+        if (grad_dtype == TT_F32)
+          ebc_gather_sorted4_kernel<float><<<g4 < 1 ? 1 : g4, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs_buf);
+        else
+          ebc_gather_sorted4_kernel<__nv_bfloat16><<<g4 < 1 ? 1 : g4, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs_buf);
+      } else if (grad_dtype == TT_F32)
         ebc_gather_sorted_kernel<float><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs_buf);
       else
         ebc_gather_sorted_kernel<__nv_bfloat16><<<ggrid, threads, 0, s>>>(sorted_slots, n, d_n, src, E, (float*)gs_buf);
@@ -1223,16 +1319,18 @@ static int backward_adam_impl(float* arena_w, float* arena_m, float* arena_v, fl
       ebc_piece_kernel<true><<<ceil_div(n_chunks, threads / (G * SUB)), threads, 0, s>>>(sorted_rows, gs, n, d_n, row_begin, row_end,
                                                                                          E, G, SUB, pieces);
     else
-    ebc_piece_kernel<false><<<ceil_div(n_chunks, threads / (G * SUB)), threads, 0, s>>>(sorted_rows, gs, n, d_n, row_begin, row_end, E, G,
-                                                                                 SUB, pieces);
+      ebc_piece_kernel<false><<<ceil_div(n_chunks, threads / (G * SUB)), threads, 0, s>>>(sorted_rows, gs, n, d_n, row_begin, row_end, E,
+                                                                                          G, SUB, pieces);
   }
   if (mode == TT_ADAM_SPARSE) {
     if (n > 0)
     {
       int64_t want = ceil_div(n, (int64_t)gpb * SP_ROWS);
       const int64_t cap = (int64_t)sm_count() * 12;  // 3 resident CTAs per SM, 4 waves
-      (direct ? ebc_rows_sparse_kernel<true> : ebc_rows_sparse_kernel<false>)<<<(int)(want > cap ? cap : want), threads, 0, s>>>(
-          arena_w, arena_m, arena_v, E, G, sorted_rows, gs, n, d_n, row_end, pieces, d_hyper, d_lazy);
+      auto kern = d_lazy ? (direct ? ebc_rows_sparse_kernel<true, true> : ebc_rows_sparse_kernel<false, true>)
+                         : (direct ? ebc_rows_sparse_kernel<true, false> : ebc_rows_sparse_kernel<false, false>);
+      kern<<<(int)(want > cap ? cap : want), threads, 0, s>>>(arena_w, arena_m, arena_v, E, G, sorted_rows, gs, n, d_n, row_end, pieces,
+                                                              d_hyper, d_lazy);
     }
   } else {
     int64_t want = ceil_div(total_rows, gpb);
