@@ -55,6 +55,23 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def cupti_kernel_table(prof, n_steps, drop_first=1):
+    """{kernel name: (device us per step, launches per step)} over the LAST n_steps of the n_steps + drop_first identical steps run
+    inside `prof`. The first step(s) are dropped per kernel (its earliest launches): under torchrun the ranks leave the profiler's
+    start-up at different times, and the first peer-memory kernel of the first profiled step then spins for the slowest rank —
+    28 ms "per launch" in an N=2 table once."""
+    per = {}
+    for e in prof.events():
+        if e.device_time_total > 0:
+            per.setdefault(e.key, []).append((e.time_range.start, e.device_time_total))
+    out = {}
+    for key, lst in per.items():
+        lst.sort()
+        kept = lst[len(lst) * drop_first // (n_steps + drop_first):]
+        out[key] = (sum(d for _, d in kept) / n_steps, len(kept) / n_steps)
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -377,15 +394,14 @@ def run_cfg3(args):
     from torch.profiler import ProfilerActivity, profile
     n_cupti = 3
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for i in range(n_cupti):
+        for i in range(n_cupti + 1):
             gstep(packed=packed[i % n_rot])
         torch.cuda.synchronize(dev)
-    for ev in prof.key_averages():
-        if ev.device_time_total > 0 and ev.count > 0:
-            name = ev.key.replace("void ", "").replace("tt::", "").split("(")[0]
-            d = gk.setdefault(name, {"us": 0.0, "n": 0.0})
-            d["us"] += ev.device_time_total / n_cupti
-            d["n"] += ev.count / n_cupti
+    for key, (us, cnt) in cupti_kernel_table(prof, n_cupti).items():
+        name = key.replace("void ", "").replace("tt::", "").split("(")[0]
+        d = gk.setdefault(name, {"us": 0.0, "n": 0.0})
+        d["us"] += us
+        d["n"] += cnt
     barrier()
     # lazy exact-replay Adam: what the deferred dense update costs when it is finally paid — a flush after `lag` more steps replays
     # (rows x E x lag) element-steps in registers; reported as picoseconds per element-step next to the 24 B / 6.5 TB/s = 3.7 ps the
@@ -772,16 +788,15 @@ def run_ours(args):
             run_step(i)
         barrier()
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            for i in range(n_cupti):
+            for i in range(n_cupti + 1):
                 run_step(i)
             torch.cuda.synchronize(dev)
-        for ev in prof.key_averages():
-            if ev.device_time_total > 0 and ev.count > 0:
-                name = ev.key.replace("void ", "").replace("tt::", "")
-                name = name.split("(")[0]
-                d = gk.setdefault(name, {"us_per_step": 0.0, "launches_per_step": 0.0})
-                d["us_per_step"] += ev.device_time_total / n_cupti
-                d["launches_per_step"] += ev.count / n_cupti
+        for key, (us, cnt) in cupti_kernel_table(prof, n_cupti).items():
+            name = key.replace("void ", "").replace("tt::", "")
+            name = name.split("(")[0]
+            d = gk.setdefault(name, {"us_per_step": 0.0, "launches_per_step": 0.0})
+            d["us_per_step"] += us
+            d["launches_per_step"] += cnt
     except Exception as e:  # the line must still come out
         gk = {"error": {"us_per_step": 0.0, "launches_per_step": 0.0, "what": repr(e)}}
     barrier()

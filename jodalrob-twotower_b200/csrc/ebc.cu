@@ -1053,7 +1053,15 @@ __global__ void ebc_small_reduce_kernel(const float* __restrict__ part, int64_t 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float t = 0.f;
-  for (int c = 0; c < chunks; ++c) t += part[(int64_t)c * part_stride + i];
+  int c = 0;
+  for (; c + 8 <= chunks; c += 8) {  // eight chunk partials in flight, added in chunk order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = part[(int64_t)(c + u) * part_stride + i];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t += v[u];
+  }
+  for (; c < chunks; ++c) t += part[(int64_t)c * part_stride + i];
   gout[i] = t;
 }
 

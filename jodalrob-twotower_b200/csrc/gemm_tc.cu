@@ -239,7 +239,15 @@ __global__ void gt_splitk_reduce_kernel(const float* __restrict__ part, int64_t 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * stride + i];
+  int z = 0;
+  for (; z + 8 <= splits; z += 8) {  // eight split partials in flight, added in split order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = part[(int64_t)(z + u) * stride + i];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; z < splits; ++z) s += part[(int64_t)z * stride + i];
   out[i] = s;
 }
 

@@ -674,8 +674,12 @@ tc_rows_reduce_kernel(const float* __restrict__ row_e, const float* __restrict__
   const bool ok = m < Bx;
   if (out_s) {
     for (int c = threadIdx.x; c < F; c += 32 * RR_LANES) {
+      float t[YS_BLOCKS];  // all partials in flight, then the fold in block order: one L2 round trip instead of YS_BLOCKS
+#pragma unroll
+      for (int b = 0; b < YS_BLOCKS; ++b) t[b] = ysum_part[b * F + c];
       float a = 0.f;
-      for (int b = 0; b < YS_BLOCKS; ++b) a += ysum_part[b * F + c];
+#pragma unroll
+      for (int b = 0; b < YS_BLOCKS; ++b) a += t[b];
       sh_y[c] = a;
     }
   }
@@ -732,7 +736,8 @@ tc_rows_reduce_kernel(const float* __restrict__ row_e, const float* __restrict__
       const __nv_bfloat16* y1 = Y + j1 * F;
       float a0 = 0.f, a1 = 0.f;
       const bool v0 = j0 < By, v1 = j1 < By;
-      for (int k = 0; k < F; k += 8) {
+#pragma unroll 4
+      for (int k = 0; k < F; k += 8) {  // F is 64 or 128: four iterations' loads (twelve 16-byte vectors) in flight per round
         const uint4 xv = *reinterpret_cast<const uint4*>(xr + k);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         const uint4 yv0 = v0 ? __ldg(reinterpret_cast<const uint4*>(y0 + k)) : z;

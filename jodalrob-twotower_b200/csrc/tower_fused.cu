@@ -784,7 +784,17 @@ __global__ void __launch_bounds__(256) colpart_reduce_multi_kernel(const ColSegs
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= s.C[seg]) return;
   double a = 0.0;
-  for (int t = 0; t < s.n_tiles; ++t) a += (double)s.part[seg][(int64_t)t * s.C[seg] + c];
+  const float* src = s.part[seg] + c;
+  const int64_t ld = s.C[seg];
+  int t = 0;
+  for (; t + 16 <= s.n_tiles; t += 16) {  // sixteen partials in flight, added in tile order
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = src[(int64_t)(t + u) * ld];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) a += (double)v[u];
+  }
+  for (; t < s.n_tiles; ++t) a += (double)src[(int64_t)t * ld];
   s.out[seg][c] = (float)a;
 }
 

@@ -364,7 +364,11 @@ class DistributedEngine(TwoTowerEngine):
             ws.xtab = {k_: torch.tensor([p_ + xoff[k_] for p_ in xpeer], dtype=torch.int64, device=dev) for k_ in parts}
             torch.cuda.synchronize(dev)
             self.comm.dist.barrier(group=self.comm.group, device_ids=[dev.index if dev.index is not None else torch.cuda.current_device()])
-        ws.sim_ws = torch.empty(q("tt_simce_workspace_bytes", Bg, Bg, cfg.final_dim), dtype=torch.uint8, device=dev)
+        # the four-pass entry points run this rank's B rows against all Bg columns; the size is NOT monotone in the row count (a
+        # short, wide problem splits a row block over more CTAs: more partials per row) — at W = 8 and B = 256 the square size was
+        # too small ("workspace too small" in the fp32 check of tests/dist_check.py on 8 GPUs)
+        ws.sim_ws = torch.empty(max(q("tt_simce_workspace_bytes", B, Bg, cfg.final_dim), q("tt_simce_workspace_bytes", Bg, Bg, cfg.final_dim)),
+                                dtype=torch.uint8, device=dev)
         # three-pass logits step: this rank's rows against all ranks' columns; the row / column sums of the other ranks arrive
         # by all-gather (peer pushes when available)
         self._alloc_sim3(ws, B, Bg)

@@ -127,7 +127,8 @@ def test_torchrun_sharded_bf16_peer_path_vs_reference(world):
 
 
 @pytest.mark.parametrize("world,dtype,bl,opt", [(2, "bf16", 1024, "dense_exact"), (4, "bf16", 512, "dense_exact"), (2, "fp32", 256, "dense_exact"),
-                                                (3, "fp32", 256, "lazy_exact"), (2, "bf16", 512, "lazy_exact")])
+                                                (3, "fp32", 256, "lazy_exact"), (2, "bf16", 512, "lazy_exact"),
+                                                (8, "fp32", 256, "dense_exact"), (8, "bf16", 256, "dense_exact")])
 def test_emulated_ranks_sharded_step_readme_schema_vs_reference(world, dtype, bl, opt):
     """The row-wise sharded step in the benchmarked precision on ONE GPU: `world` rank threads, host-mediated collectives
     (dist.ThreadComm: same engine code, the peer-memory kernels replaced by their all_gather / all_reduce equivalents), against the
