@@ -683,6 +683,9 @@ __device__ __forceinline__ void gather_sum(float4& acc, const GradFetch& f, int6
 // level 1 for long rows: SUB lane groups per chunk of SEG_CHUNK sorted entries. Each group sums a contiguous
 // SEG_CHUNK / SUB slice of the piece in order, the SUB partial sums are folded by a fixed butterfly ((0+1)+(2+3)):
 // deterministic, and SUB times the parallelism of one group per chunk (the kernel is latency bound: few chunks, long chains).
+// a sub-group's whole slice (SEG_CHUNK / SUB = 16 entries at E <= 32) in one batch: the kernel is a chain of dependent round trips
+// (sorted row -> row bounds -> gradients) run by few CTAs (ncu: 10 % of the warp slots), so every batch is a round trip saved
+constexpr int PIECE_BATCH = 16;
 template <bool DIRECT>
 __global__ void __launch_bounds__(256)
 ebc_piece_kernel(const int32_t* __restrict__ srow, const GradFetch gs, int64_t n,
@@ -713,11 +716,11 @@ ebc_piece_kernel(const int32_t* __restrict__ srow, const GradFetch gs, int64_t n
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p0 && cv) {
       const int64_t s_lo = lo + (int64_t)sub * span, s_hi = s_lo + span < pe ? s_lo + span : pe;
-      if (s_lo < s_hi) gather_sum<DIRECT>(a0, gs, s_lo, s_hi, E, c);
+      if (s_lo < s_hi) gather_sum<DIRECT, PIECE_BATCH>(a0, gs, s_lo, s_hi, E, c);
     }
     if (p1 && cv) {
       const int64_t s_lo = b1 + (int64_t)sub * span, s_hi = s_lo + span < hi ? s_lo + span : hi;
-      if (s_lo < s_hi) gather_sum<DIRECT>(a1, gs, s_lo, s_hi, E, c);
+      if (s_lo < s_hi) gather_sum<DIRECT, PIECE_BATCH>(a1, gs, s_lo, s_hi, E, c);
     }
     for (int off = G; off < unit; off <<= 1) {
       a0.x += __shfl_xor_sync(0xffffffffu, a0.x, off); a0.y += __shfl_xor_sync(0xffffffffu, a0.y, off);
