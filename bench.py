@@ -655,8 +655,9 @@ def run_ours(args):
             for t, s_ in zip(src[0], stage[0]):
                 s_.copy_(t, non_blocking=True)
             ready[0].record(copy_stream)
-        for i in range(n):
-            cur, nxt = i % 2, (i + 1) % 2
+
+        def prefetch(i):  # H2D of batch i + 1 into the other staging buffer, on the copy stream
+            nxt = (i + 1) % 2
             if i + 1 < n:
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
@@ -664,15 +665,27 @@ def run_ours(args):
                     for t, s_ in zip(src[(i + 1) % N_ROTATE], stage[nxt]):
                         s_.copy_(t, non_blocking=True)
                     ready[nxt].record(copy_stream)
+
+        for i in range(n):
+            cur, nxt = i % 2, (i + 1) % 2
+            # step i is launched FIRST (the GPU is idle while the host gets here), the copy of batch i + 1 is issued underneath it;
+            # the staging buffer is free again as soon as the device-to-device copy into the graph's input buffer has run
             main.wait_event(ready[cur])
-            res = gstep(packed=stage[cur][0]) if gstep is not None else task.fused_step(as_batch(stage[cur]))
-            freed[cur].record(main)
+            if gstep is not None:
+                gstep.stage_packed(stage[cur][0])
+                freed[cur].record(main)
+                res = gstep()
+            else:
+                res = task.fused_step(as_batch(stage[cur]))
+                freed[cur].record(main)
             if lag == 0:
                 out_host.copy_(res, non_blocking=True)
+                prefetch(i)
                 main.synchronize()  # the D2H read of this step's loss/metrics
             else:
                 out_hosts[cur].copy_(res, non_blocking=True)  # ordered before the next replay overwrites the result buffer
                 read_done[cur].record(main)
+                prefetch(i)
                 if i >= 1:
                     read_done[nxt].synchronize()  # step i-1's result is on the host now
                     last = float(out_hosts[nxt][0])
@@ -729,17 +742,17 @@ def run_ours(args):
                 ready[0].record(copy_stream)
             for i in range(n):
                 cur, nxt = i % 2, (i + 1) % 2
-                if i + 1 < n:
-                    with torch.cuda.stream(copy_stream):
-                        if i >= 1:
-                            copy_stream.wait_event(freed[nxt])
-                        idx_stage[nxt].copy_(idx_pin[(i + 1) % N_ROTATE], non_blocking=True)
-                        ready[nxt].record(copy_stream)
                 main.wait_event(ready[cur])
                 asm.assemble_into(gstep, idx_stage[cur][0], idx_stage[cur][1])
                 freed[cur].record(main)
                 res = gstep()
                 out_host.copy_(res, non_blocking=True)
+                if i + 1 < n:  # the next step's indices cross PCIe underneath this step (issued after the launch, like e2e_loop)
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(freed[nxt])
+                        idx_stage[nxt].copy_(idx_pin[(i + 1) % N_ROTATE], non_blocking=True)
+                        ready[nxt].record(copy_stream)
                 main.synchronize()
             return float(out_host[0])
 

@@ -601,6 +601,11 @@ class GraphedFusedStep:
             out[o:o + nb].view(dt).view(shape).copy_(t.to(dt).reshape(shape))
         return out
 
+    def stage_packed(self, packed: torch.Tensor):
+        """Stage a pre-packed batch (see pack()) into the static input buffer without replaying: one asynchronous copy on the current
+        stream. The source buffer may be refilled as soon as this copy has run (record an event behind it); `step()` then replays."""
+        self.static_blob.copy_(packed, non_blocking=True)
+
     def __call__(self, batch=None, packed: Optional[torch.Tensor] = None) -> torch.Tensor:
         if packed is not None:
             self.static_blob.copy_(packed, non_blocking=True)
