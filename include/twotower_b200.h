@@ -425,7 +425,9 @@ int tt_l2norm_backward(const float* de, const void* e, int32_t e_dtype, const fl
  * tt_simce_finalize turns (globally summed) sums into  inv_row [Bx], inv_col [By] for the backward
  * and partial f64[16][8]: 16 block partials of {sum_i l_row, sum_{j in my diag range} l_col, hits, sum diag, sum S, 0,0,0}
  * (the buffer must hold 128 doubles; distributed callers all-reduce all of it);
- * tt_simce_scalars maps (globally summed) partials to {loss, accuracy, pos_mean, neg_mean, gap}. */
+ * tt_simce_scalars maps (globally summed) partials to {loss, accuracy, pos_mean, neg_mean, gap}.
+ * Workspace sizes (all tt_simce*_workspace_bytes) are NOT monotone in Bx: a short, wide problem splits a row block over more CTAs
+ * (more partial results per row) than a square one — query them with the exact (Bx, By) of the calls, not with an upper bound. */
 int64_t tt_simce_workspace_bytes(int64_t Bx, int64_t By, int32_t F);
 int tt_simce_forward(const void* X, const void* Y, int64_t Bx, int64_t By, int32_t F, int32_t dtype, float inv_temp,
                      int64_t diag_offset, float* row_sumexp, float* col_sumexp, float* row_sum_s, float* col_sum_s,

@@ -177,3 +177,29 @@ def test_reference_copy_recipe_and_bench_reference_arm_use_the_reference_itself(
     # dropout 0.1 draws from the global torch RNG in both: seed equal => masks equal only if the RNG consumption matches,
     # which build_*_task(seed=0) + identical module order guarantees for the first step
     assert losses["reference"][0] == losses["port"][0]
+
+
+def test_bench_cupti_table_drops_the_first_profiled_step():
+    """bench.cupti_kernel_table: per kernel, the launches of the first profiled step are dropped (under torchrun the first
+    peer-memory kernel of that step waits for the rank that left the profiler's start-up last) and the rest is averaged per step."""
+    import bench
+
+    class _Range:
+        def __init__(self, start):
+            self.start = start
+
+    class _Ev:
+        def __init__(self, key, start, dur):
+            self.key, self.time_range, self.device_time_total = key, _Range(start), dur
+
+    class _Prof:
+        def events(self):
+            skewed = [_Ev("peer_allreduce", 0.0, 28000.0)] + [_Ev("peer_allreduce", 10.0 * i, 9.0) for i in range(1, 8)]  # 2 per step
+            gemm = [_Ev("gemm", 3.0 + 10 * i, 5.0 + (i % 2)) for i in range(8)]                                          # 2 per step
+            host_only = [_Ev("cudaLaunchKernel", 1.0, 0.0)]
+            return skewed + gemm + host_only
+
+    t = bench.cupti_kernel_table(_Prof(), n_steps=3, drop_first=1)
+    assert set(t) == {"peer_allreduce", "gemm"}
+    assert t["peer_allreduce"] == (18.0, 2.0)          # 6 launches of 9 us over 3 steps: the 28 ms outlier is gone
+    assert t["gemm"][1] == 2.0 and abs(t["gemm"][0] - 11.0) < 1e-9
