@@ -634,7 +634,18 @@ def run_ours(args):
     # ---- end to end through the public API: pinned host inputs -> H2D -> step -> D2H of the result, every step.
     # H2D of batch i+1 (copy stream, double-buffered staging) overlaps the step of batch i. ----
     copy_stream = torch.cuda.Stream(dev)
-    if gstep is not None:
+    # Two captures of the same step, each with its own static input buffer: the host-to-device copy of batch i+1 goes straight into
+    # the buffer of the graph that will run it while the other graph runs step i — no device-to-device staging copy, and nothing
+    # between the host's return from step i and the replay of step i+1 but one event wait (--e2e-single-graph: one capture, staged).
+    # Single GPU only: measured 27.6 -> 28.6 M samples/s there; under torchrun the strict loop is paced by the ranks waiting for
+    # each other in the first exchange of every step, and one sample at N=2 showed no gain (26.2 vs 28.0 M).
+    gpair = None
+    if gstep is not None and world == 1 and not args.e2e_single_graph:
+        gpair = [gstep, tt.GraphedFusedStep(task, as_batch(resident[0]), compact_inputs=compact)]
+    if gpair is not None:
+        stage = [(g_.static_blob,) for g_ in gpair]
+        src = [(b,) for b in packed_pin]
+    elif gstep is not None:
         stage = [(torch.empty_like(packed_res[0]),) for _ in range(2)]
         src = [(b,) for b in packed_pin]
     else:
@@ -671,7 +682,10 @@ def run_ours(args):
             # step i is launched FIRST (the GPU is idle while the host gets here), the copy of batch i + 1 is issued underneath it;
             # the staging buffer is free again as soon as the device-to-device copy into the graph's input buffer has run
             main.wait_event(ready[cur])
-            if gstep is not None:
+            if gpair is not None:
+                res = gpair[cur]()  # its input buffer was filled by the copy stream
+                freed[cur].record(main)  # ... and is free again when this replay is over (the weight gradients read it last)
+            elif gstep is not None:
                 gstep.stage_packed(stage[cur][0])
                 freed[cur].record(main)
                 res = gstep()
@@ -943,6 +957,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the parity pre-check against the reference port")
     ap.add_argument("--parity-batch", type=int, default=1024, help="samples per GPU in the parity pre-check (the port steps the global batch on the CPU)")
     ap.add_argument("--tables-only", nargs="?", const="full", default=None, choices=["full", "quick"])
+    ap.add_argument("--e2e-single-graph", action="store_true", help="end-to-end loop: one captured graph fed through a staging buffer instead of two captures fed directly")
     ap.add_argument("--no-device-store", action="store_true", help="skip the end-to-end loop with HBM-resident feature stores")
     ap.add_argument("--no-tables", action="store_true", help="skip the large-table (HBM-bound lookup/update) section")
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
